@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the rasterizer hot path: train-views/sec (forward + backward) @ N Gaussians, 1080p.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200gs|reference] [--mode vanilla|gsplat]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload = BASELINE.json configs[1] shape ("Mip-NeRF360 garden, 1920x1080, ~1M Gaussians, SH deg 3, fwd+bwd") with the
+deterministic synthetic scene of SURVEY.md §8(d): G(1 000 000, seed 0) in [-1.3,1.3]^3, 32-pose camera ring, one
+camera per step (a fresh pose every step: 236 MB of parameters + ~180 MB of per-view buffers > L2, no L2 flush needed).
+
+One "step" = what `GaussianSplatting.training_step` asks of the renderer (internal/gaussian_splatting.py:344,380):
+renderer.forward(camera, model, bg) from RAW parameters (activations included) and backward of a fixed random
+cotangent G[3,H,W] ~ U(-1,1) down to the gradients of the six raw parameter tensors.  No loss, optimizer, dataloader.
+
+Keys of the JSON line: see the driver contract.  `value` times K steps with everything resident in HBM; `e2e` times the
+same steps through the public plug-in API with that step's cotangent image coming from pinned host memory (H2D inside
+the timed region, standing for the ground-truth image upload of gaussian_splatting.py:250-264) and the step's scalar
+result read back (D2H).  `roofline` is for the kernel with the largest share of the step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train-views/sec (fwd+bwd) @ N Gaussians, 1080p"
+UNIT = "views/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200gs", choices=["b200gs", "reference"])
+    ap.add_argument("--mode", default="vanilla", choices=["vanilla", "gsplat"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--cpu-sample-iters", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own CPU-runnable part of the path: projection + SH, forward + autograd
+# backward, as restated (and pinned against the reference) in oracle/gs_oracle.py
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_projection_views_per_sec(n, width, height, mode_name, iters, warm=2):
+    from oracle import gs_oracle as O
+    from b200gs.scene import activate, make_ring_cameras, make_scene
+    torch.set_num_threads(os.cpu_count() or 1)
+    mode = O.MODE_GSPLAT if mode_name == "gsplat" else O.MODE_VANILLA
+    sc = activate(make_scene(n, 0))
+    cams = make_ring_cameras(width, height)
+    g = torch.Generator().manual_seed(1)
+    c_xy, c_con, c_rgb = torch.randn(n, 2, generator=g), torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
+    times = []
+    for it in range(warm + iters):
+        cam = cams[it % len(cams)]
+        ov = O.make_view(cam.R, cam.T, float(cam.fx), float(cam.fy), float(cam.cx), float(cam.cy), width, height)
+        ins = {k: sc[k].clone().requires_grad_(True) for k in ("means", "scales", "rotations", "shs")}
+        t0 = time.perf_counter()
+        p = O.project(mode, ins["means"], ins["scales"], ins["rotations"], ov)
+        col = O.sh_colors(3, ins["shs"], ins["means"], cam.camera_center, detach_dir=(mode == O.MODE_GSPLAT))
+        ((p["xy"] * c_xy).sum() + (p["conic"] * c_con).sum() + (col * c_rgb).sum()).backward()
+        dt = time.perf_counter() - t0
+        if it >= warm:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return 1.0 / med, med
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 12))
+    vps, med = cpu_projection_views_per_sec(args.n, args.width, args.height, args.mode, steps, warm=max(1, min(args.warmup, 3)))
+    cores = os.cpu_count() or 1
+    sample = (f"projection+SH forward + autograd backward only (the reference has no CPU blend/sort: BASELINE.md §3), "
+              f"{steps} views of the same workload, median")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
+        "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, "cpu"),
+        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, parallelism):
+    return {"workload": f"configs[1]: synthetic G({args.n}, seed 0) SH deg 3, {args.width}x{args.height}, 32-pose ring, "
+                        f"{args.mode} semantics, fwd+bwd from raw parameters",
+            "n_gaussians": args.n, "width": args.width, "height": args.height, "mode": args.mode, "parallelism": parallelism,
+            "l2": "inputs larger than L2 (236 MB parameters + fresh camera every step); no explicit flush"}
+
+
+# bytes per view, SURVEY.md §8(d) / BASELINE.md §5 (V visible, I pairs, P pixels, N total; SH degree 3)
+def algorithmic_bytes(stage, N, V, I, P, n_tiles):
+    return {
+        "project_fwd": V * 268 + N * 16,
+        "bin_count": N * (16 + 4 * 16 + 8 + 12),      # keys+ids+tiles write, 4 radix passes of 8 B pairs (r+w), scan
+        "bin_sort": V * 24 + I * 8 + I * (4 + 2 * 16) + I * 4 + n_tiles * 8,  # emit, 2-pass 8 B pair partition, ranges
+        "blend_fwd": I * 40 + P * 20,
+        "blend_bwd": I * 76 + P * 20,
+        "project_bwd": V * 552,
+    }[stage]
+
+
+LAUNCHES_PER_STEP = {"project_fwd": 1, "bin_count": 1 + 6 + 2 + 1, "bin_sort": 1 + 4 + 1, "blend_fwd": 1, "blend_bwd": 1, "project_bwd": 1}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from b200gs import ops
+    from b200gs.renderers import B200GSplatRenderer, B200VanillaRenderer
+    from b200gs.scene import SyntheticGaussians, make_ring_cameras, make_scene
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (b200gs has no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, W, H = args.n, args.width, args.height
+    raw = make_scene(N, 0)
+    model = SyntheticGaussians(raw).to(dev)
+    cams = [c.to_device(dev) for c in make_ring_cameras(W, H)]
+    renderer = (B200VanillaRenderer() if args.mode == "vanilla" else B200GSplatRenderer()).to(dev)
+    bg = torch.zeros(3, device=dev)
+    gen = torch.Generator().manual_seed(1)
+    cot_host = (torch.rand(3, H, W, generator=gen) * 2 - 1).pin_memory()
+    cot = cot_host.to(dev)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(i, e2e=False):
+        cam = cams[(i * world + rank) % len(cams)]   # each rank renders a different pose
+        for p in model.parameters():
+            p.grad = None
+        c = cot_host.to(dev, non_blocking=True) if e2e else cot
+        out = renderer(cam, model, bg)
+        loss = (out["render"] * c).sum()
+        loss.backward()
+        if e2e:
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            step(i, e2e)
+            if e2e:
+                torch.cuda.current_stream().synchronize()   # the user reads the step's result
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(args.steps, False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(args.steps, True)
+
+    # per-stage timing (CUDA events on the launching stream) for the roofline numbers
+    timer = ops.StageTimer()
+    ops.set_stage_timer(timer)
+    for i in range(min(args.steps, 32)):
+        step(i)
+    stage_ms, stage_calls = timer.summary_ms()
+    ops.set_stage_timer(None)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # workload statistics of pose 0 for the algorithmic byte counts
+    with torch.no_grad():
+        out = renderer(cams[0], model, bg)
+        V = int((out["radii"] > 0).sum())
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    from b200gs.renderers import camera_view
+    mode_id = 0 if args.mode == "vanilla" else 1
+    view = camera_view(cams[0], mode_id)
+    with torch.no_grad():
+        xy, depth, radii, conic, comp, tiles, _, _, _ = ops.project_forward(view, model.get_xyz.detach(), model.get_scaling.detach().contiguous(),
+                                                                            model.get_rotation.detach().contiguous(), None, True)
+        I = int(tiles.sum())
+    P = W * H
+    hbm_peak, peak_src = peaks()
+    kernels = {}
+    for k, ms in stage_ms.items():
+        b = algorithmic_bytes(k, N, V, I, P, gx * gy)
+        kernels[k] = {"ms": round(ms, 4), "alg_bytes": b, "gbs": round(b / (ms * 1e-3) / 1e9, 1), "launches": LAUNCHES_PER_STEP.get(k, 1)}
+    top = max(stage_ms, key=stage_ms.get)
+    ach = kernels[top]["gbs"]
+    views_per_s = args.steps * world / (ms_total * 1e-3)
+    e2e_vps = args.steps * world / (ms_e2e * 1e-3)
+    launches = sum(LAUNCHES_PER_STEP.values()) * args.steps
+
+    line = {
+        "metric": METRIC, "value": views_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, "replicas" if world > 1 else "single"),
+        "e2e": {"value": e2e_vps, "unit": UNIT, "h2d_bytes_per_step": int(cot_host.numel() * 4), "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
+                     "traffic": None, "peak_source": peak_src,
+                     "note": "blend kernels are SM-issue (FP32+MUFU) bound, not HBM bound (SURVEY §8d); HBM fraction reported as asked"},
+        "kernels": kernels,
+        "scene": {"N": N, "V": V, "I": I, "P": P, "stage_sum_ms": round(sum(stage_ms.values()), 4)},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        vps, med = cpu_projection_views_per_sec(N, W, H, args.mode, args.cpu_sample_iters)
+        line["cpu_baseline"] = {"value": vps, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": f"oracle projection+SH fwd+autograd bwd (reference has no CPU blend), {args.cpu_sample_iters} views, median"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

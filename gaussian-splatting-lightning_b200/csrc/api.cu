@@ -1,0 +1,146 @@
+// C ABI of libb200gs.so — see include/b200gs.h for the contract of every entry point.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b200gs {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+static int check_view(const B200gsView* v, bool needs_sh) {
+    if (v == nullptr) { set_error("view is NULL"); return B200GS_EINVAL; }
+    if (v->width <= 0 || v->height <= 0) { set_error("bad image size %dx%d", v->width, v->height); return B200GS_EINVAL; }
+    if (v->mode != B200GS_MODE_VANILLA && v->mode != B200GS_MODE_GSPLAT) { set_error("bad mode %d", v->mode); return B200GS_EINVAL; }
+    if (needs_sh) {
+        if (v->sh_degree < 0 || v->sh_degree > 3) { set_error("sh_degree %d unsupported (0..3)", v->sh_degree); return B200GS_EINVAL; }
+        if (v->sh_stride < (v->sh_degree + 1) * (v->sh_degree + 1)) {
+            set_error("sh_stride %d < (sh_degree+1)^2", v->sh_stride);
+            return B200GS_EINVAL;
+        }
+    }
+    return B200GS_OK;
+}
+
+}  // namespace b200gs
+
+using namespace b200gs;
+
+extern "C" {
+
+const char* b200gs_last_error(void) { return g_error; }
+int b200gs_version(void) { return 100; }
+
+int b200gs_project_fwd(const B200gsView* view, int64_t n, const float* means, const float* scales, const float* quats,
+                       const float* shs, float* xy, float* depth, int32_t* radii, float* conic, float* comp,
+                       int32_t* tiles, float* cov3d, float* rgb, uint8_t* clamped, void* stream) {
+    int rc = check_view(view, shs != nullptr);
+    if (rc) return rc;
+    B200GS_CHECK_ARG(n >= 0, "n < 0");
+    if (n > 0) {
+        B200GS_CHECK_ARG(means && scales && quats, "means/scales/quats must not be NULL");
+        B200GS_CHECK_ARG(xy && depth && radii && conic && tiles, "xy/depth/radii/conic/tiles must not be NULL");
+        B200GS_CHECK_ARG(shs == nullptr || (rgb && clamped), "rgb/clamped required when shs is given");
+    }
+    return launch_project_fwd(*view, n, means, scales, quats, shs, xy, depth, radii, conic, comp, tiles, cov3d, rgb, clamped,
+                              (cudaStream_t)stream);
+}
+
+int b200gs_project_bwd(const B200gsView* view, int64_t n, const float* means, const float* scales, const float* quats,
+                       const float* shs, const int32_t* radii, const uint8_t* clamped, const float* v_xy,
+                       const float* v_depth, const float* v_conic, const float* v_comp, const float* v_rgb,
+                       float* v_means, float* v_scales, float* v_quats, float* v_shs, void* stream) {
+    int rc = check_view(view, shs != nullptr);
+    if (rc) return rc;
+    B200GS_CHECK_ARG(n >= 0, "n < 0");
+    if (n > 0) {
+        B200GS_CHECK_ARG(means && scales && quats && radii, "means/scales/quats/radii must not be NULL");
+        B200GS_CHECK_ARG(v_xy && v_conic, "v_xy/v_conic must not be NULL");
+        B200GS_CHECK_ARG(v_means && v_scales && v_quats, "v_means/v_scales/v_quats must not be NULL");
+        B200GS_CHECK_ARG((shs == nullptr) == (v_shs == nullptr), "shs and v_shs must be given together");
+        B200GS_CHECK_ARG(shs == nullptr || (clamped && v_rgb), "clamped/v_rgb required when shs is given");
+    }
+    return launch_project_bwd(*view, n, means, scales, quats, shs, radii, clamped, v_xy, v_depth, v_conic, v_comp, v_rgb,
+                              v_means, v_scales, v_quats, v_shs, (cudaStream_t)stream);
+}
+
+int b200gs_sh_fwd(int32_t degree, int32_t sh_stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, void* stream) {
+    B200GS_CHECK_ARG(degree >= 0 && degree <= 3, "degree must be 0..3");
+    B200GS_CHECK_ARG(sh_stride >= (degree + 1) * (degree + 1), "sh_stride < (degree+1)^2");
+    B200GS_CHECK_ARG(n >= 0, "n < 0");
+    B200GS_CHECK_ARG(n == 0 || (dirs && coeffs && rgb), "NULL pointer");
+    return launch_sh_fwd(degree, sh_stride, n, dirs, coeffs, rgb, (cudaStream_t)stream);
+}
+
+int b200gs_sh_bwd(int32_t degree, int32_t sh_stride, int64_t n, const float* dirs, const float* coeffs, const float* v_rgb,
+                  float* v_coeffs, float* v_dirs, void* stream) {
+    B200GS_CHECK_ARG(degree >= 0 && degree <= 3, "degree must be 0..3");
+    B200GS_CHECK_ARG(sh_stride >= (degree + 1) * (degree + 1), "sh_stride < (degree+1)^2");
+    B200GS_CHECK_ARG(n >= 0, "n < 0");
+    B200GS_CHECK_ARG(n == 0 || (dirs && coeffs && v_rgb && v_coeffs), "NULL pointer");
+    return launch_sh_bwd(degree, sh_stride, n, dirs, coeffs, v_rgb, v_coeffs, v_dirs, (cudaStream_t)stream);
+}
+
+size_t b200gs_bin_count_workspace_bytes(int64_t n) { return n < 0 ? 0 : bin_count_workspace_bytes(n); }
+
+size_t b200gs_bin_sort_workspace_bytes(int64_t n, int64_t max_pairs, int32_t width, int32_t height) {
+    if (n < 0 || max_pairs < 0) return 0;
+    return bin_sort_workspace_bytes(n, max_pairs, width, height);
+}
+
+int b200gs_bin_count(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const float* depth,
+                     const int32_t* radii, void* workspace, size_t workspace_bytes, int64_t* d_total,
+                     int64_t* host_total, void* stream) {
+    B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
+    B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0, "bad size");
+    B200GS_CHECK_ARG(workspace && d_total, "workspace/d_total must not be NULL");
+    B200GS_CHECK_ARG(n == 0 || (xy && depth && radii), "NULL pointer");
+    B200GS_CHECK_ARG(n < (int64_t(1) << 31), "n >= 2^31");
+    return bin_count(mode, width, height, n, xy, depth, radii, workspace, workspace_bytes, d_total, host_total, (cudaStream_t)stream);
+}
+
+int b200gs_bin_sort(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const int32_t* radii,
+                    int64_t total, int64_t max_pairs, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes,
+                    int32_t* sorted_ids, int32_t* tile_ranges, void* stream) {
+    B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
+    B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0 && total >= 0 && max_pairs >= 0, "bad size");
+    B200GS_CHECK_ARG(workspace_a && workspace_b && tile_ranges, "workspace/tile_ranges must not be NULL");
+    B200GS_CHECK_ARG(total == 0 || (xy && radii && sorted_ids), "NULL pointer");
+    return bin_sort(mode, width, height, n, xy, radii, total, max_pairs, workspace_a, workspace_b, workspace_b_bytes, sorted_ids,
+                    tile_ranges, (cudaStream_t)stream);
+}
+
+int b200gs_blend_fwd(int32_t mode, int32_t width, int32_t height, int32_t channels, const int32_t* tile_ranges,
+                     const int32_t* sorted_ids, const float* xy, const float* conic, const float* opacity,
+                     const float* colors, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride,
+                     float* final_T, int32_t* n_contrib, float* alpha, void* stream) {
+    B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
+    B200GS_CHECK_ARG(width > 0 && height > 0, "bad size");
+    B200GS_CHECK_ARG(tile_ranges && image && final_T && n_contrib, "NULL output/range pointer");
+    return launch_blend_fwd(mode, width, height, channels, tile_ranges, sorted_ids, xy, conic, opacity, colors, bg, image,
+                            pix_stride, ch_stride, final_T, n_contrib, alpha, (cudaStream_t)stream);
+}
+
+int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int32_t channels, const int32_t* tile_ranges,
+                     const int32_t* sorted_ids, const float* xy, const float* conic, const float* opacity,
+                     const float* colors, const float* bg, const float* final_T, const int32_t* n_contrib,
+                     const float* v_image, int64_t pix_stride, int64_t ch_stride, const float* v_alpha,
+                     float xy_scale_x, float xy_scale_y, float* v_xy, float* v_conic, float* v_opacity,
+                     float* v_colors, float* v_xy_abs, void* stream) {
+    B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
+    B200GS_CHECK_ARG(width > 0 && height > 0, "bad size");
+    B200GS_CHECK_ARG(tile_ranges && final_T && n_contrib && v_image, "NULL input pointer");
+    B200GS_CHECK_ARG(v_xy && v_conic && v_opacity && v_colors, "NULL output pointer");
+    return launch_blend_bwd(mode, width, height, channels, tile_ranges, sorted_ids, xy, conic, opacity, colors, bg, final_T,
+                            n_contrib, v_image, pix_stride, ch_stride, v_alpha, xy_scale_x, xy_scale_y, v_xy, v_conic,
+                            v_opacity, v_colors, v_xy_abs, (cudaStream_t)stream);
+}
+
+}  // extern "C"

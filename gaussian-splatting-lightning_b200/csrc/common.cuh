@@ -1,0 +1,102 @@
+// Shared device/host helpers for libb200gs (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b200gs.h"
+
+namespace b200gs {
+
+void set_error(const char* fmt, ...);
+
+#define B200GS_CHECK_ARG(cond, msg)                                  \
+    do {                                                              \
+        if (!(cond)) {                                                \
+            b200gs::set_error("%s: %s", __func__, msg);              \
+            return B200GS_EINVAL;                                     \
+        }                                                             \
+    } while (0)
+
+#define B200GS_CUDA(call)                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            b200gs::set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(_e));  \
+            return B200GS_ECUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define B200GS_LAUNCH_CHECK()                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            b200gs::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(_e)); \
+            return B200GS_ECUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+constexpr int TILE = B200GS_TILE;
+
+__host__ __device__ inline int div_up(int a, int b) { return (a + b - 1) / b; }
+inline int64_t div_up64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Tile rectangle touched by a splat: the two rules of SURVEY §8c.
+//   vanilla (dgr getRect):   min = clamp(int((p - r)/16)),  max = clamp(int((p + r + 15)/16))
+//   gsplat  (gaussian_projection.py:118-123): min = clamp(int((p - r)/16)),  max = clamp(int((p + r)/16) + 1)
+// (int) truncates toward zero exactly like torch's .int(); clamp to [0, grid].
+template <bool GSPLAT>
+__device__ __forceinline__ void tile_rect(float x, float y, float r, int grid_x, int grid_y, int& x0, int& y0, int& x1, int& y1) {
+    const float inv = 1.0f / float(TILE);  // exact power of two: same result as dividing
+    x0 = min(grid_x, max(0, (int)((x - r) * inv)));
+    y0 = min(grid_y, max(0, (int)((y - r) * inv)));
+    if (GSPLAT) {
+        x1 = min(grid_x, max(0, (int)((x + r) * inv) + 1));
+        y1 = min(grid_y, max(0, (int)((y + r) * inv) + 1));
+    } else {
+        x1 = min(grid_x, max(0, (int)((x + r + float(TILE - 1)) * inv)));
+        y1 = min(grid_y, max(0, (int)((y + r + float(TILE - 1)) * inv)));
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// launchers (one per translation unit)
+int launch_project_fwd(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
+                       const float* shs, float* xy, float* depth, int32_t* radii, float* conic, float* comp,
+                       int32_t* tiles, float* cov3d, float* rgb, uint8_t* clamped, cudaStream_t s);
+int launch_project_bwd(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
+                       const float* shs, const int32_t* radii, const uint8_t* clamped, const float* v_xy,
+                       const float* v_depth, const float* v_conic, const float* v_comp, const float* v_rgb,
+                       float* v_means, float* v_scales, float* v_quats, float* v_shs, cudaStream_t s);
+int launch_sh_fwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, cudaStream_t s);
+int launch_sh_bwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, const float* v_rgb,
+                  float* v_coeffs, float* v_dirs, cudaStream_t s);
+
+size_t bin_count_workspace_bytes(int64_t n);
+size_t bin_sort_workspace_bytes(int64_t n, int64_t max_pairs, int width, int height);
+int bin_count(int mode, int width, int height, int64_t n, const float* xy, const float* depth, const int32_t* radii,
+              void* ws, size_t ws_bytes, int64_t* d_total, int64_t* host_total, cudaStream_t s);
+int bin_sort(int mode, int width, int height, int64_t n, const float* xy, const int32_t* radii, int64_t total,
+             int64_t max_pairs, const void* ws_a, void* ws_b, size_t ws_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges,
+             cudaStream_t s);
+
+int launch_blend_fwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids,
+                     const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
+                     float* image, int64_t pix_stride, int64_t ch_stride, float* final_T, int32_t* n_contrib,
+                     float* alpha, cudaStream_t s);
+int launch_blend_bwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids,
+                     const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
+                     const float* final_T, const int32_t* n_contrib, const float* v_image, int64_t pix_stride,
+                     int64_t ch_stride, const float* v_alpha, float sx, float sy, float* v_xy, float* v_conic,
+                     float* v_opacity, float* v_colors, float* v_xy_abs, cudaStream_t s);
+
+}  // namespace b200gs

@@ -1,0 +1,599 @@
+// K1 / K8: per-Gaussian EWA projection + SH colour, forward and backward, both constant sets.
+//
+// One thread per Gaussian.  Forward restates the arithmetic of
+//   /root/reference/internal/utils/gaussian_projection.py:6-138   (gsplat mode; live-pinned by tests/golden)
+//   /root/reference/internal/utils/sh_utils.py:57-112             (SH polynomials)
+// and, for vanilla mode, the published preprocessCUDA of diff-gaussian-rasterization@59f5f77.
+// Backward is hand-derived and checked against torch autograd through the oracle.
+//
+// HBM-bound: per visible Gaussian 268 B fwd / 552 B bwd at SH degree 3.  SH coefficients are streamed with
+// 128-bit read-only loads (ld.global.nc), outputs written with 64/128-bit stores where the layout allows.
+#include "common.cuh"
+
+namespace b200gs {
+
+namespace {
+
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+__device__ constexpr float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                       -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                                       -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+constexpr int MAX_COEFFS = 16;
+
+// Loads the first ncoef*3 floats of one Gaussian's SH block into registers. 128-bit path when the block is 16B aligned.
+__device__ __forceinline__ void load_sh(const float* __restrict__ base, int ncoef, bool vec4, float* sh) {
+    const int nf = ncoef * 3;
+    if (vec4) {
+        const float4* b4 = reinterpret_cast<const float4*>(base);
+#pragma unroll
+        for (int q = 0; q < MAX_COEFFS * 3 / 4; ++q) {
+            if (q * 4 < nf) {
+                float4 t = __ldg(b4 + q);
+                sh[q * 4 + 0] = t.x; sh[q * 4 + 1] = t.y; sh[q * 4 + 2] = t.z; sh[q * 4 + 3] = t.w;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < MAX_COEFFS * 3; ++q)
+            if (q < nf) sh[q] = __ldg(base + q);
+    }
+}
+
+// basis values for unit direction (x,y,z); writes (deg+1)^2 entries
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float* b) {
+    b[0] = SH_C0;
+    if (deg > 0) {
+        b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            b[4] = SH_C2[0] * xy; b[5] = SH_C2[1] * yz; b[6] = SH_C2[2] * (2.0f * zz - xx - yy);
+            b[7] = SH_C2[3] * xz; b[8] = SH_C2[4] * (xx - yy);
+            if (deg > 2) {
+                b[9] = SH_C3[0] * y * (3.0f * xx - yy); b[10] = SH_C3[1] * xy * z;
+                b[11] = SH_C3[2] * y * (4.0f * zz - xx - yy); b[12] = SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                b[13] = SH_C3[4] * x * (4.0f * zz - xx - yy); b[14] = SH_C3[5] * z * (xx - yy);
+                b[15] = SH_C3[6] * x * (xx - 3.0f * yy);
+            }
+        }
+    }
+}
+
+// d(basis)/d(x,y,z)
+__device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z, float* bx, float* by, float* bz) {
+    bx[0] = by[0] = bz[0] = 0.f;
+    if (deg > 0) {
+        bx[1] = 0.f; by[1] = -SH_C1; bz[1] = 0.f;
+        bx[2] = 0.f; by[2] = 0.f; bz[2] = SH_C1;
+        bx[3] = -SH_C1; by[3] = 0.f; bz[3] = 0.f;
+        if (deg > 1) {
+            bx[4] = SH_C2[0] * y; by[4] = SH_C2[0] * x; bz[4] = 0.f;
+            bx[5] = 0.f; by[5] = SH_C2[1] * z; bz[5] = SH_C2[1] * y;
+            bx[6] = SH_C2[2] * -2.f * x; by[6] = SH_C2[2] * -2.f * y; bz[6] = SH_C2[2] * 4.f * z;
+            bx[7] = SH_C2[3] * z; by[7] = 0.f; bz[7] = SH_C2[3] * x;
+            bx[8] = SH_C2[4] * 2.f * x; by[8] = SH_C2[4] * -2.f * y; bz[8] = 0.f;
+            if (deg > 2) {
+                const float xx = x * x, yy = y * y, zz = z * z;
+                bx[9] = SH_C3[0] * 6.f * x * y; by[9] = SH_C3[0] * (3.f * xx - 3.f * yy); bz[9] = 0.f;
+                bx[10] = SH_C3[1] * y * z; by[10] = SH_C3[1] * x * z; bz[10] = SH_C3[1] * x * y;
+                bx[11] = SH_C3[2] * -2.f * x * y; by[11] = SH_C3[2] * (4.f * zz - xx - 3.f * yy); bz[11] = SH_C3[2] * 8.f * y * z;
+                bx[12] = SH_C3[3] * -6.f * x * z; by[12] = SH_C3[3] * -6.f * y * z; bz[12] = SH_C3[3] * (6.f * zz - 3.f * xx - 3.f * yy);
+                bx[13] = SH_C3[4] * (4.f * zz - 3.f * xx - yy); by[13] = SH_C3[4] * -2.f * x * y; bz[13] = SH_C3[4] * 8.f * x * z;
+                bx[14] = SH_C3[5] * 2.f * x * z; by[14] = SH_C3[5] * -2.f * y * z; bz[14] = SH_C3[5] * (xx - yy);
+                bx[15] = SH_C3[6] * (3.f * xx - 3.f * yy); by[15] = SH_C3[6] * -6.f * x * y; bz[15] = 0.f;
+            }
+        }
+    }
+}
+
+struct Proj {
+    float tx, ty, tz;        // camera-space mean
+    float cxp, cyp;          // clamped tx', ty' used in J
+    bool clx, cly;           // clamp active
+    float fx, fy;            // focal used by J
+    float R[9];              // rotation from quaternion (row major)
+    float s[3];              // scales * modifier
+    float S3[6];             // cov3D upper triangle xx xy xz yy yz zz
+    float T[6];              // T = J * Rw, rows 0,1 (2x3)
+    float a, b, c, det;      // blurred cov2D and determinant
+    float a0, c0, det0;      // un-blurred diag and determinant (gsplat compensation)
+};
+
+__device__ __forceinline__ void quat_to_rot(const float* q, float* R) {
+    const float r = q[0], x = q[1], y = q[2], z = q[3];
+    R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - r * z); R[2] = 2.f * (x * z + r * y);
+    R[3] = 2.f * (x * y + r * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - r * x);
+    R[6] = 2.f * (x * z - r * y); R[7] = 2.f * (y * z + r * x); R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+// Shared forward geometry (everything up to the blurred cov2D).
+template <bool GSPLAT>
+__device__ __forceinline__ void project_geometry(const B200gsView& v, const float* p, const float* sc, const float* q, Proj& g) {
+    const float* V = v.viewmatrix;
+    g.tx = p[0] * V[0] + p[1] * V[4] + p[2] * V[8] + V[12];
+    g.ty = p[0] * V[1] + p[1] * V[5] + p[2] * V[9] + V[13];
+    g.tz = p[0] * V[2] + p[1] * V[6] + p[2] * V[10] + V[14];
+    quat_to_rot(q, g.R);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g.s[k] = sc[k] * v.scale_modifier;
+    float M[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) M[i * 3 + k] = g.R[i * 3 + k] * g.s[k];
+    g.S3[0] = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
+    g.S3[1] = M[0] * M[3] + M[1] * M[4] + M[2] * M[5];
+    g.S3[2] = M[0] * M[6] + M[1] * M[7] + M[2] * M[8];
+    g.S3[3] = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
+    g.S3[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
+    g.S3[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
+
+    float tanx, tany;
+    if (GSPLAT) {
+        g.fx = v.fx; g.fy = v.fy;
+        tanx = (0.5f * float(v.width)) / v.fx;
+        tany = (0.5f * float(v.height)) / v.fy;
+    } else {
+        tanx = v.tanfovx; tany = v.tanfovy;
+        g.fx = float(v.width) / (2.0f * tanx);
+        g.fy = float(v.height) / (2.0f * tany);
+    }
+    const float limx = 1.3f * tanx, limy = 1.3f * tany;
+    const float txtz = g.tx / g.tz, tytz = g.ty / g.tz;
+    g.clx = (txtz < -limx) || (txtz > limx);
+    g.cly = (tytz < -limy) || (tytz > limy);
+    g.cxp = fminf(limx, fmaxf(-limx, txtz)) * g.tz;
+    g.cyp = fminf(limy, fmaxf(-limy, tytz)) * g.tz;
+    const float itz = 1.0f / g.tz;
+    const float j00 = g.fx * itz, j02 = -(g.fx * g.cxp) * itz * itz;
+    const float j11 = g.fy * itz, j12 = -(g.fy * g.cyp) * itz * itz;
+    // T = J * Rw ; Rw[j][i] = V[i*4+j]
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g.T[i] = j00 * V[i * 4 + 0] + j02 * V[i * 4 + 2];
+        g.T[3 + i] = j11 * V[i * 4 + 1] + j12 * V[i * 4 + 2];
+    }
+    // cov2D = T S3 T^T
+    const float* S = g.S3;
+    const float u0 = S[0] * g.T[0] + S[1] * g.T[1] + S[2] * g.T[2];
+    const float u1 = S[1] * g.T[0] + S[3] * g.T[1] + S[4] * g.T[2];
+    const float u2 = S[2] * g.T[0] + S[4] * g.T[1] + S[5] * g.T[2];
+    const float w0 = S[0] * g.T[3] + S[1] * g.T[4] + S[2] * g.T[5];
+    const float w1 = S[1] * g.T[3] + S[3] * g.T[4] + S[4] * g.T[5];
+    const float w2 = S[2] * g.T[3] + S[4] * g.T[4] + S[5] * g.T[5];
+    g.a0 = g.T[0] * u0 + g.T[1] * u1 + g.T[2] * u2;
+    g.b = g.T[3] * u0 + g.T[4] * u1 + g.T[5] * u2;
+    g.c0 = g.T[3] * w0 + g.T[4] * w1 + g.T[5] * w2;
+    g.det0 = g.a0 * g.c0 - g.b * g.b;
+    g.a = g.a0 + v.eps2d;
+    g.c = g.c0 + v.eps2d;
+    g.det = g.a * g.c - g.b * g.b;
+}
+
+template <bool GSPLAT>
+__device__ __forceinline__ float near_of(const B200gsView& v) {
+    return v.near_plane > 0.f ? v.near_plane : (GSPLAT ? 0.01f : 0.2f);
+}
+
+template <bool GSPLAT>
+__global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant__ B200gsView v, int64_t n,
+                                                          const float* __restrict__ means, const float* __restrict__ scales,
+                                                          const float* __restrict__ quats, const float* __restrict__ shs,
+                                                          float2* __restrict__ xy_out, float* __restrict__ depth_out,
+                                                          int32_t* __restrict__ radii_out, float* __restrict__ conic_out,
+                                                          float* __restrict__ comp_out, int32_t* __restrict__ tiles_out,
+                                                          float* __restrict__ cov3d_out, float* __restrict__ rgb_out,
+                                                          uint8_t* __restrict__ clamped_out) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
+    const float sc[3] = {__ldg(scales + 3 * i), __ldg(scales + 3 * i + 1), __ldg(scales + 3 * i + 2)};
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + i);
+    const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+    Proj g;
+    project_geometry<GSPLAT>(v, p, sc, q, g);
+
+    const float near = near_of<GSPLAT>(v);
+    bool vis = GSPLAT ? (g.tz >= near) : (g.tz > near);
+    if (!GSPLAT) vis = vis && (g.det != 0.0f);
+
+    float px, py;
+    if (GSPLAT) {
+        const float iz = 1.0f / (g.tz + 1e-6f);
+        const float zn = g.tz * iz;
+        px = (g.tx * iz) * v.fx + zn * v.cx;
+        py = (g.ty * iz) * v.fy + zn * v.cy;
+    } else {
+        const float* P = v.projmatrix;
+        const float hx = p[0] * P[0] + p[1] * P[4] + p[2] * P[8] + P[12];
+        const float hy = p[0] * P[1] + p[1] * P[5] + p[2] * P[9] + P[13];
+        const float hw = p[0] * P[3] + p[1] * P[7] + p[2] * P[11] + P[15];
+        const float iw = 1.0f / (hw + 0.0000001f);
+        px = ((hx * iw + 1.0f) * float(v.width) - 1.0f) * 0.5f;
+        py = ((hy * iw + 1.0f) * float(v.height) - 1.0f) * 0.5f;
+    }
+    const float inv_det = 1.0f / g.det;
+    const float mid = 0.5f * (g.a + g.c);
+    const float sq = sqrtf(fmaxf(0.1f, mid * mid - g.det));
+    const float lam = fmaxf(mid + sq, mid - sq);
+    const float radius = ceilf(3.0f * sqrtf(lam));
+    const int grid_x = div_up(v.width, TILE), grid_y = div_up(v.height, TILE);
+    int x0, y0, x1, y1;
+    tile_rect<GSPLAT>(px, py, radius, grid_x, grid_y, x0, y0, x1, y1);
+    const int ntiles = (x1 - x0) * (y1 - y0);
+    vis = vis && (ntiles > 0) && (radius > 0.f);  // NaN radius compares false
+
+    if (vis) {
+        xy_out[i] = make_float2(px, py);
+        depth_out[i] = g.tz;
+        radii_out[i] = (int32_t)radius;
+        conic_out[3 * i + 0] = g.c * inv_det;
+        conic_out[3 * i + 1] = -g.b * inv_det;
+        conic_out[3 * i + 2] = g.a * inv_det;
+        tiles_out[i] = ntiles;
+        if (comp_out) comp_out[i] = GSPLAT ? sqrtf(fmaxf(g.det0 * inv_det, 0.f)) : 1.0f;
+    } else {
+        xy_out[i] = make_float2(0.f, 0.f);
+        depth_out[i] = 0.f;
+        radii_out[i] = 0;
+        conic_out[3 * i + 0] = 0.f; conic_out[3 * i + 1] = 0.f; conic_out[3 * i + 2] = 0.f;
+        tiles_out[i] = 0;
+        if (comp_out) comp_out[i] = 0.f;
+    }
+    if (cov3d_out) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cov3d_out[6 * i + k] = vis ? g.S3[k] : 0.f;
+    }
+    if (shs != nullptr) {
+        float r = 0.f, gc = 0.f, bc = 0.f;
+        uint8_t cl = 0;
+        if (vis) {
+            const int deg = v.sh_degree;
+            const int ncoef = (deg + 1) * (deg + 1);
+            float sh[MAX_COEFFS * 3];
+            const bool vec4 = ((v.sh_stride * 3) & 3) == 0;
+            load_sh(shs + i * int64_t(v.sh_stride) * 3, ncoef, vec4, sh);
+            float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
+            const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            dx *= inv_len; dy *= inv_len; dz *= inv_len;
+            float bs[MAX_COEFFS];
+            sh_basis(deg, dx, dy, dz, bs);
+#pragma unroll
+            for (int k = 0; k < MAX_COEFFS; ++k) {
+                if (k < ncoef) {
+                    r += bs[k] * sh[3 * k + 0];
+                    gc += bs[k] * sh[3 * k + 1];
+                    bc += bs[k] * sh[3 * k + 2];
+                }
+            }
+            r += 0.5f; gc += 0.5f; bc += 0.5f;
+            if (r < 0.f) { r = 0.f; cl |= 1; }
+            if (gc < 0.f) { gc = 0.f; cl |= 2; }
+            if (bc < 0.f) { bc = 0.f; cl |= 4; }
+        }
+        rgb_out[3 * i + 0] = r; rgb_out[3 * i + 1] = gc; rgb_out[3 * i + 2] = bc;
+        clamped_out[i] = cl;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------------------
+template <bool GSPLAT>
+__global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant__ B200gsView v, int64_t n,
+                                                          const float* __restrict__ means, const float* __restrict__ scales,
+                                                          const float* __restrict__ quats, const float* __restrict__ shs,
+                                                          const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
+                                                          const float2* __restrict__ v_xy, const float* __restrict__ v_depth,
+                                                          const float* __restrict__ v_conic, const float* __restrict__ v_comp,
+                                                          const float* __restrict__ v_rgb, float* __restrict__ v_means,
+                                                          float* __restrict__ v_scales, float4* __restrict__ v_quats,
+                                                          float* __restrict__ v_shs) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int stride3 = v.sh_stride * 3;
+    const bool vec4 = (stride3 & 3) == 0;
+    if (radii[i] <= 0) {
+        v_means[3 * i] = 0.f; v_means[3 * i + 1] = 0.f; v_means[3 * i + 2] = 0.f;
+        v_scales[3 * i] = 0.f; v_scales[3 * i + 1] = 0.f; v_scales[3 * i + 2] = 0.f;
+        v_quats[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v_shs) {
+            float* o = v_shs + i * int64_t(stride3);
+            if (vec4) {
+                for (int k = 0; k < stride3 / 4; ++k) reinterpret_cast<float4*>(o)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int k = 0; k < stride3; ++k) o[k] = 0.f;
+            }
+        }
+        return;
+    }
+    const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
+    const float sc[3] = {__ldg(scales + 3 * i), __ldg(scales + 3 * i + 1), __ldg(scales + 3 * i + 2)};
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + i);
+    const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+    Proj g;
+    project_geometry<GSPLAT>(v, p, sc, q, g);
+    const float* V = v.viewmatrix;
+
+    float dmx = 0.f, dmy = 0.f, dmz = 0.f;  // dL/dmean (world)
+    float dtx = 0.f, dty = 0.f, dtz = 0.f;  // dL/dt (camera)
+
+    // ---- SH colour -------------------------------------------------------------------------------------------
+    if (v_shs != nullptr) {
+        const int deg = v.sh_degree;
+        const int ncoef = (deg + 1) * (deg + 1);
+        const uint8_t cl = clamped[i];
+        const float gr = (cl & 1) ? 0.f : __ldg(v_rgb + 3 * i + 0);
+        const float gg = (cl & 2) ? 0.f : __ldg(v_rgb + 3 * i + 1);
+        const float gb = (cl & 4) ? 0.f : __ldg(v_rgb + 3 * i + 2);
+        float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
+        const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+        dx *= inv_len; dy *= inv_len; dz *= inv_len;
+        float bs[MAX_COEFFS];
+        sh_basis(deg, dx, dy, dz, bs);
+        float out[MAX_COEFFS * 3];
+#pragma unroll
+        for (int k = 0; k < MAX_COEFFS; ++k) {
+            const float bk = (k < ncoef) ? bs[k] : 0.f;
+            out[3 * k + 0] = bk * gr; out[3 * k + 1] = bk * gg; out[3 * k + 2] = bk * gb;
+        }
+        float* o = v_shs + i * int64_t(stride3);
+        if (vec4) {
+            for (int k = 0; k < stride3 / 4; ++k) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k * 4 < MAX_COEFFS * 3) t = make_float4(out[k * 4], out[k * 4 + 1], out[k * 4 + 2], out[k * 4 + 3]);
+                reinterpret_cast<float4*>(o)[k] = t;
+            }
+        } else {
+            for (int k = 0; k < stride3; ++k) o[k] = (k < MAX_COEFFS * 3) ? out[k] : 0.f;
+        }
+        if (!GSPLAT && deg > 0) {
+            // view direction -> mean (dgr back-propagates it; gsplat renderers detach the direction)
+            float sh[MAX_COEFFS * 3];
+            load_sh(shs + i * int64_t(stride3), ncoef, vec4, sh);
+            float bx[MAX_COEFFS], by[MAX_COEFFS], bz[MAX_COEFFS];
+            sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
+            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+#pragma unroll
+            for (int k = 1; k < MAX_COEFFS; ++k) {
+                if (k < ncoef) {
+                    const float w = sh[3 * k] * gr + sh[3 * k + 1] * gg + sh[3 * k + 2] * gb;
+                    ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
+                }
+            }
+            const float dot = dx * ddx + dy * ddy + dz * ddz;
+            dmx += (ddx - dx * dot) * inv_len;
+            dmy += (ddy - dy * dot) * inv_len;
+            dmz += (ddz - dz * dot) * inv_len;
+        }
+    }
+
+    // ---- conic (+ compensation) -> blurred cov2D (a, b, c) ----------------------------------------------------
+    const float inv_det = 1.0f / g.det;
+    const float A = g.c * inv_det, B = -g.b * inv_det, C = g.a * inv_det;
+    const float vA = __ldg(v_conic + 3 * i), vB = __ldg(v_conic + 3 * i + 1), vC = __ldg(v_conic + 3 * i + 2);
+    // X = -Q G Q, Q = [[A,B],[B,C]], G = [[vA, vB/2],[vB/2, vC]]
+    const float hB = 0.5f * vB;
+    const float m00 = A * vA + B * hB, m01 = A * hB + B * vC;
+    const float m10 = B * vA + C * hB, m11 = B * hB + C * vC;
+    float da = -(m00 * A + m01 * B);
+    float db = -2.0f * (m00 * B + m01 * C);
+    float dc = -(m10 * B + m11 * C);
+    (void)m10;
+    if (GSPLAT && v_comp != nullptr) {
+        const float vc = __ldg(v_comp + i);
+        if (g.det0 > 0.f && vc != 0.f) {
+            const float comp = sqrtf(g.det0 * inv_det);
+            const float d_det0 = vc * 0.5f * comp / g.det0;
+            const float d_det = -vc * 0.5f * comp * inv_det;
+            da += d_det0 * g.c0 + d_det * g.c;
+            dc += d_det0 * g.a0 + d_det * g.a;
+            db += -2.0f * g.b * (d_det0 + d_det);
+        }
+    }
+    // symmetric gradient wrt the 2x2 cov: [[da, db/2],[db/2, dc]]
+    const float g00 = da, g01 = 0.5f * db, g11 = dc;
+    const float* T = g.T;
+    // dL/dSigma3 = T^T Gc T  (symmetric 3x3)
+    float dS[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cidx = 0; cidx < 3; ++cidx)
+            dS[r * 3 + cidx] = T[r] * (g00 * T[cidx] + g01 * T[3 + cidx]) + T[3 + r] * (g01 * T[cidx] + g11 * T[3 + cidx]);
+    // dL/dT = 2 Gc T Sigma3 (2x3)
+    const float* S = g.S3;
+    const float Sf[9] = {S[0], S[1], S[2], S[1], S[3], S[4], S[2], S[4], S[5]};
+    float TS0[3], TS1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        TS0[k] = T[0] * Sf[k] + T[1] * Sf[3 + k] + T[2] * Sf[6 + k];
+        TS1[k] = T[3] * Sf[k] + T[4] * Sf[3 + k] + T[5] * Sf[6 + k];
+    }
+    float dT0[3], dT1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        dT0[k] = 2.0f * (g00 * TS0[k] + g01 * TS1[k]);
+        dT1[k] = 2.0f * (g01 * TS0[k] + g11 * TS1[k]);
+    }
+    // T = J Rw -> dL/dJ = dL/dT Rw^T ; Rw[j][i] = V[i*4+j]
+    // dJ00 = sum_i dT0[i] Rw[0][i], dJ02 = sum_i dT0[i] Rw[2][i], dJ11 = sum_i dT1[i] Rw[1][i], dJ12 = sum_i dT1[i] Rw[2][i]
+    const float dJ00 = dT0[0] * V[0] + dT0[1] * V[4] + dT0[2] * V[8];
+    const float dJ02 = dT0[0] * V[2] + dT0[1] * V[6] + dT0[2] * V[10];
+    const float dJ11 = dT1[0] * V[1] + dT1[1] * V[5] + dT1[2] * V[9];
+    const float dJ12 = dT1[0] * V[2] + dT1[1] * V[6] + dT1[2] * V[10];
+    const float itz = 1.0f / g.tz, itz2 = itz * itz, itz3 = itz2 * itz;
+    const float dcx = -g.fx * itz2 * dJ02;  // dL/d(tx')
+    const float dcy = -g.fy * itz2 * dJ12;
+    dtz += -g.fx * itz2 * dJ00 - g.fy * itz2 * dJ11 + 2.0f * g.fx * g.cxp * itz3 * dJ02 + 2.0f * g.fy * g.cyp * itz3 * dJ12;
+    if (!g.clx) dtx += dcx; else if (GSPLAT) dtz += dcx * g.cxp * itz;  // dgr drops the clamped branch's z-dependence
+    if (!g.cly) dty += dcy; else if (GSPLAT) dtz += dcy * g.cyp * itz;
+
+    // ---- mean2D / depth --------------------------------------------------------------------------------------
+    const float2 vxy = v_xy[i];
+    if (GSPLAT) {
+        const float iz = 1.0f / (g.tz + 1e-6f);
+        dtx += v.fx * iz * vxy.x;
+        dty += v.fy * iz * vxy.y;
+        dtz += (-v.fx * g.tx * iz * iz + v.cx * 1e-6f * iz * iz) * vxy.x + (-v.fy * g.ty * iz * iz + v.cy * 1e-6f * iz * iz) * vxy.y;
+        if (v_depth) dtz += __ldg(v_depth + i);
+    } else {
+        // v_xy is dL/d(ndc) (pixel gradient x 0.5 W/H), straight through the 4x4 full projection
+        const float* P = v.projmatrix;
+        const float hw = p[0] * P[3] + p[1] * P[7] + p[2] * P[11] + P[15];
+        const float mw = 1.0f / (hw + 0.0000001f);
+        const float mul1 = (p[0] * P[0] + p[1] * P[4] + p[2] * P[8] + P[12]) * mw * mw;
+        const float mul2 = (p[0] * P[1] + p[1] * P[5] + p[2] * P[9] + P[13]) * mw * mw;
+        dmx += (P[0] * mw - P[3] * mul1) * vxy.x + (P[1] * mw - P[3] * mul2) * vxy.y;
+        dmy += (P[4] * mw - P[7] * mul1) * vxy.x + (P[5] * mw - P[7] * mul2) * vxy.y;
+        dmz += (P[8] * mw - P[11] * mul1) * vxy.x + (P[9] * mw - P[11] * mul2) * vxy.y;
+    }
+    // t = p * V[:3,:3] + V[3,:3]  ->  dL/dp_i = sum_j V[i][j] dt_j
+    dmx += V[0] * dtx + V[1] * dty + V[2] * dtz;
+    dmy += V[4] * dtx + V[5] * dty + V[6] * dtz;
+    dmz += V[8] * dtx + V[9] * dty + V[10] * dtz;
+    v_means[3 * i] = dmx; v_means[3 * i + 1] = dmy; v_means[3 * i + 2] = dmz;
+
+    // ---- Sigma3 = M M^T, M = R diag(s) ------------------------------------------------------------------------
+    float M[9], dM[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) M[r * 3 + k] = g.R[r * 3 + k] * g.s[k];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            dM[r * 3 + k] = 2.0f * (dS[r * 3 + 0] * M[0 + k] + dS[r * 3 + 1] * M[3 + k] + dS[r * 3 + 2] * M[6 + k]);
+    float dR[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        v_scales[3 * i + k] = v.scale_modifier * (g.R[k] * dM[k] + g.R[3 + k] * dM[3 + k] + g.R[6 + k] * dM[6 + k]);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) dR[r * 3 + k] = dM[r * 3 + k] * g.s[k];
+    }
+    const float r = q[0], x = q[1], y = q[2], z = q[3];
+    float4 dq;
+    dq.x = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+    dq.y = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
+    dq.z = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
+    dq.w = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+    v_quats[i] = dq;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// standalone SH (gsplat.sh.spherical_harmonics)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sh_fwd_kernel(int deg, int stride, int64_t n, const float* __restrict__ dirs,
+                                                     const float* __restrict__ coeffs, float* __restrict__ rgb) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ncoef = (deg + 1) * (deg + 1);
+    float dx = __ldg(dirs + 3 * i), dy = __ldg(dirs + 3 * i + 1), dz = __ldg(dirs + 3 * i + 2);
+    const float inv_len = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+    dx *= inv_len; dy *= inv_len; dz *= inv_len;
+    float sh[MAX_COEFFS * 3];
+    load_sh(coeffs + i * int64_t(stride) * 3, ncoef, ((stride * 3) & 3) == 0, sh);
+    float bs[MAX_COEFFS];
+    sh_basis(deg, dx, dy, dz, bs);
+    float r = 0.f, g = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAX_COEFFS; ++k)
+        if (k < ncoef) { r += bs[k] * sh[3 * k]; g += bs[k] * sh[3 * k + 1]; b += bs[k] * sh[3 * k + 2]; }
+    rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
+}
+
+__global__ void __launch_bounds__(256) sh_bwd_kernel(int deg, int stride, int64_t n, const float* __restrict__ dirs,
+                                                     const float* __restrict__ coeffs, const float* __restrict__ v_rgb,
+                                                     float* __restrict__ v_coeffs, float* __restrict__ v_dirs) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ncoef = (deg + 1) * (deg + 1);
+    const int stride3 = stride * 3;
+    const bool vec4 = (stride3 & 3) == 0;
+    float dx = __ldg(dirs + 3 * i), dy = __ldg(dirs + 3 * i + 1), dz = __ldg(dirs + 3 * i + 2);
+    const float inv_len = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+    dx *= inv_len; dy *= inv_len; dz *= inv_len;
+    const float gr = __ldg(v_rgb + 3 * i), gg = __ldg(v_rgb + 3 * i + 1), gb = __ldg(v_rgb + 3 * i + 2);
+    float bs[MAX_COEFFS];
+    sh_basis(deg, dx, dy, dz, bs);
+    float* o = v_coeffs + i * int64_t(stride3);
+    for (int k = 0; k < stride; ++k) {
+        const float bk = (k < ncoef) ? bs[k] : 0.f;
+        o[3 * k] = bk * gr; o[3 * k + 1] = bk * gg; o[3 * k + 2] = bk * gb;
+    }
+    if (v_dirs != nullptr) {
+        float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+        if (deg > 0) {
+            float sh[MAX_COEFFS * 3];
+            load_sh(coeffs + i * int64_t(stride3), ncoef, vec4, sh);
+            float bx[MAX_COEFFS], by[MAX_COEFFS], bz[MAX_COEFFS];
+            sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
+#pragma unroll
+            for (int k = 1; k < MAX_COEFFS; ++k)
+                if (k < ncoef) {
+                    const float w = sh[3 * k] * gr + sh[3 * k + 1] * gg + sh[3 * k + 2] * gb;
+                    ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
+                }
+            const float dot = dx * ddx + dy * ddy + dz * ddz;
+            ddx = (ddx - dx * dot) * inv_len; ddy = (ddy - dy * dot) * inv_len; ddz = (ddz - dz * dot) * inv_len;
+        }
+        v_dirs[3 * i] = ddx; v_dirs[3 * i + 1] = ddy; v_dirs[3 * i + 2] = ddz;
+    }
+}
+
+}  // namespace
+
+int launch_project_fwd(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
+                       const float* shs, float* xy, float* depth, int32_t* radii, float* conic, float* comp,
+                       int32_t* tiles, float* cov3d, float* rgb, uint8_t* clamped, cudaStream_t s) {
+    if (n == 0) return B200GS_OK;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)div_up64(n, threads);
+    if (v.mode == B200GS_MODE_GSPLAT)
+        project_fwd_kernel<true><<<blocks, threads, 0, s>>>(v, n, means, scales, quats, shs, (float2*)xy, depth, radii, conic,
+                                                            comp, tiles, cov3d, rgb, clamped);
+    else
+        project_fwd_kernel<false><<<blocks, threads, 0, s>>>(v, n, means, scales, quats, shs, (float2*)xy, depth, radii, conic,
+                                                             comp, tiles, cov3d, rgb, clamped);
+    B200GS_LAUNCH_CHECK();
+    return B200GS_OK;
+}
+
+int launch_project_bwd(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
+                       const float* shs, const int32_t* radii, const uint8_t* clamped, const float* v_xy,
+                       const float* v_depth, const float* v_conic, const float* v_comp, const float* v_rgb,
+                       float* v_means, float* v_scales, float* v_quats, float* v_shs, cudaStream_t s) {
+    if (n == 0) return B200GS_OK;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)div_up64(n, threads);
+    if (v.mode == B200GS_MODE_GSPLAT)
+        project_bwd_kernel<true><<<blocks, threads, 0, s>>>(v, n, means, scales, quats, shs, radii, clamped, (const float2*)v_xy,
+                                                            v_depth, v_conic, v_comp, v_rgb, v_means, v_scales,
+                                                            (float4*)v_quats, v_shs);
+    else
+        project_bwd_kernel<false><<<blocks, threads, 0, s>>>(v, n, means, scales, quats, shs, radii, clamped, (const float2*)v_xy,
+                                                             v_depth, v_conic, v_comp, v_rgb, v_means, v_scales,
+                                                             (float4*)v_quats, v_shs);
+    B200GS_LAUNCH_CHECK();
+    return B200GS_OK;
+}
+
+int launch_sh_fwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, cudaStream_t s) {
+    if (n == 0) return B200GS_OK;
+    sh_fwd_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(degree, stride, n, dirs, coeffs, rgb);
+    B200GS_LAUNCH_CHECK();
+    return B200GS_OK;
+}
+
+int launch_sh_bwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, const float* v_rgb,
+                  float* v_coeffs, float* v_dirs, cudaStream_t s) {
+    if (n == 0) return B200GS_OK;
+    sh_bwd_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(degree, stride, n, dirs, coeffs, v_rgb, v_coeffs, v_dirs);
+    B200GS_LAUNCH_CHECK();
+    return B200GS_OK;
+}
+
+}  // namespace b200gs

@@ -1,0 +1,426 @@
+"""torch.autograd.Function wrappers over the C ABI (``libb200gs.so``).
+
+PyTorch is used for device memory (its caching allocator owns every buffer, including workspaces), the current CUDA
+stream and autograd bookkeeping only; all arithmetic of the hot path runs in the hand-written kernels.
+
+Functions
+  rasterize_vanilla(...)      the whole dgr-semantics pipeline as ONE autograd node (what
+                              ``diff_gaussian_rasterization.GaussianRasterizer`` is; vanilla_renderer.py:111-120)
+  project_gaussians(...)      gsplat v0 ``project_gaussians``          (gsplat_renderer.py:64-79)
+  spherical_harmonics(...)    gsplat ``spherical_harmonics``           (gsplat_renderer.py:105)
+  rasterize_gaussians(...)    gsplat v0 ``rasterize_gaussians``        (gsplat_renderer.py:86-99)
+"""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MODE_GSPLAT, MODE_VANILLA, TILE, B200gsView, check, lib, ptr
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class StageTimer:
+    """Optional per-stage CUDA-event timing on the launching stream (used by bench.py for the roofline numbers)."""
+
+    def __init__(self):
+        self.events = {}
+        self.calls = {}
+
+    class _Ctx:
+        __slots__ = ("timer", "name", "start")
+
+        def __init__(self, timer, name):
+            self.timer, self.name = timer, name
+
+        def __enter__(self):
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+        def __exit__(self, *exc):
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            self.timer.events.setdefault(self.name, []).append((self.start, end))
+            return False
+
+    def stage(self, name):
+        return StageTimer._Ctx(self, name)
+
+    def reset(self):
+        self.events.clear()
+
+    def summary_ms(self):
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in self.events.items()}, {k: len(v) for k, v in self.events.items()}
+
+
+class _Null:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _Null()
+_TIMER: Optional[StageTimer] = None
+
+
+def set_stage_timer(timer: Optional[StageTimer]):
+    global _TIMER
+    _TIMER = timer
+
+
+def _stage(name):
+    return _NULL if _TIMER is None else _TIMER.stage(name)
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (b200gs has no CPU path)")
+    return t.contiguous()
+
+
+def make_view(mode: int, width: int, height: int, *, fx: float = 0.0, fy: float = 0.0, cx: float = 0.0, cy: float = 0.0,
+              tanfovx: float = 0.0, tanfovy: float = 0.0, viewmatrix=None, projmatrix=None, campos=None,
+              sh_degree: int = 0, sh_stride: int = 1, scale_modifier: float = 1.0, eps2d: float = 0.3,
+              near_plane: float = -1.0) -> B200gsView:
+    """Pack a host-side B200gsView.  ``viewmatrix`` / ``projmatrix`` are the reference's transposed 4x4 tensors
+    (Camera.world_to_camera / Camera.full_projection); they are copied to the host here (16 floats)."""
+    v = B200gsView()
+    v.width, v.height, v.mode = int(width), int(height), int(mode)
+    v.sh_degree, v.sh_stride = int(sh_degree), int(sh_stride)
+    v.fx, v.fy, v.cx, v.cy = float(fx), float(fy), float(cx), float(cy)
+    v.tanfovx, v.tanfovy = float(tanfovx), float(tanfovy)
+    v.scale_modifier, v.eps2d, v.near_plane = float(scale_modifier), float(eps2d), float(near_plane)
+    if viewmatrix is not None:
+        vm = viewmatrix.detach().to("cpu", torch.float32).reshape(-1).tolist()
+        v.viewmatrix[:] = vm
+    if projmatrix is not None:
+        pm = projmatrix.detach().to("cpu", torch.float32).reshape(-1).tolist()
+        v.projmatrix[:] = pm
+    if campos is not None:
+        cp = campos.detach().to("cpu", torch.float32).reshape(-1).tolist()
+        v.campos[:] = cp
+    return v
+
+
+def _copy_view(v: B200gsView, **updates) -> B200gsView:
+    out = B200gsView()
+    ctypes.memmove(ctypes.byref(out), ctypes.byref(v), ctypes.sizeof(B200gsView))
+    for k, val in updates.items():
+        setattr(out, k, val)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# binning helper (no autograd)
+# ----------------------------------------------------------------------------------------------------------------------
+class Binning:
+    """Result of K2-K5 for one view: depth-sorted per-tile Gaussian id lists."""
+    __slots__ = ("sorted_ids", "tile_ranges", "total")
+
+    def __init__(self, sorted_ids, tile_ranges, total):
+        self.sorted_ids, self.tile_ranges, self.total = sorted_ids, tile_ranges, total
+
+
+_host_total = None
+
+
+def bin_gaussians(mode: int, width: int, height: int, xy: torch.Tensor, depth: torch.Tensor, radii: torch.Tensor) -> Binning:
+    L = lib()
+    n = xy.shape[0]
+    dev = xy.device
+    st = _stream()
+    gx, gy = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+    ws_a = torch.empty(L.b200gs_bin_count_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    d_total = torch.empty(1, dtype=torch.int64, device=dev)
+    global _host_total
+    if _host_total is None:
+        _host_total = torch.zeros(1, dtype=torch.int64).pin_memory()
+    with _stage("bin_count"):
+        check(L.b200gs_bin_count(mode, width, height, n, ptr(xy), ptr(depth), ptr(radii), ptr(ws_a), ws_a.numel(),
+                                 ptr(d_total), _host_total.data_ptr(), st), "b200gs_bin_count")
+    total = int(_host_total[0])
+    sorted_ids = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
+    ws_b = torch.empty(L.b200gs_bin_sort_workspace_bytes(n, total, width, height), dtype=torch.uint8, device=dev)
+    with _stage("bin_sort"):
+        check(L.b200gs_bin_sort(mode, width, height, n, ptr(xy), ptr(radii), total, total, ptr(ws_a), ptr(ws_b), ws_b.numel(),
+                                ptr(sorted_ids), ptr(ranges), st), "b200gs_bin_sort")
+    return Binning(sorted_ids, ranges, total)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# raw stage calls (no autograd) — also used directly by tests
+# ----------------------------------------------------------------------------------------------------------------------
+def project_forward(view: B200gsView, means, scales, quats, shs=None, want_comp=False, want_cov3d=False):
+    L = lib()
+    n = means.shape[0]
+    dev = means.device
+    xy = torch.empty(n, 2, dtype=torch.float32, device=dev)
+    depth = torch.empty(n, dtype=torch.float32, device=dev)
+    radii = torch.empty(n, dtype=torch.int32, device=dev)
+    conic = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    tiles = torch.empty(n, dtype=torch.int32, device=dev)
+    comp = torch.empty(n, dtype=torch.float32, device=dev) if want_comp else None
+    cov3d = torch.empty(n, 6, dtype=torch.float32, device=dev) if want_cov3d else None
+    rgb = clamped = None
+    if shs is not None:
+        rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        clamped = torch.empty(n, dtype=torch.uint8, device=dev)
+    with _stage("project_fwd"):
+        check(L.b200gs_project_fwd(ctypes.byref(view), n, ptr(means), ptr(scales), ptr(quats), ptr(shs), ptr(xy), ptr(depth),
+                                   ptr(radii), ptr(conic), ptr(comp), ptr(tiles), ptr(cov3d), ptr(rgb), ptr(clamped), _stream()),
+              "b200gs_project_fwd")
+    return xy, depth, radii, conic, comp, tiles, cov3d, rgb, clamped
+
+
+def project_backward(view: B200gsView, means, scales, quats, shs, radii, clamped, v_xy, v_depth, v_conic, v_comp, v_rgb):
+    L = lib()
+    n = means.shape[0]
+    dev = means.device
+    v_means = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    v_scales = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    v_quats = torch.empty(n, 4, dtype=torch.float32, device=dev)
+    v_shs = torch.empty_like(shs) if shs is not None else None
+    with _stage("project_bwd"):
+        check(L.b200gs_project_bwd(ctypes.byref(view), n, ptr(means), ptr(scales), ptr(quats), ptr(shs), ptr(radii), ptr(clamped),
+                                   ptr(v_xy), ptr(v_depth), ptr(v_conic), ptr(v_comp), ptr(v_rgb), ptr(v_means), ptr(v_scales),
+                                   ptr(v_quats), ptr(v_shs), _stream()), "b200gs_project_bwd")
+    return v_means, v_scales, v_quats, v_shs
+
+
+def blend_forward(mode, width, height, binning: Binning, xy, conic, opacity, colors, bg, planar: bool, want_alpha: bool):
+    """planar=True -> image [C,H,W] (vanilla); else [H,W,C] (gsplat)."""
+    L = lib()
+    ch = colors.shape[1]
+    dev = xy.device
+    if planar:
+        image = torch.empty(ch, height, width, dtype=torch.float32, device=dev)
+        ps, cs = 1, height * width
+    else:
+        image = torch.empty(height, width, ch, dtype=torch.float32, device=dev)
+        ps, cs = ch, 1
+    final_T = torch.empty(height, width, dtype=torch.float32, device=dev)
+    n_contrib = torch.empty(height, width, dtype=torch.int32, device=dev)
+    alpha = torch.empty(height, width, dtype=torch.float32, device=dev) if want_alpha else None
+    with _stage("blend_fwd"):
+        check(L.b200gs_blend_fwd(mode, width, height, ch, ptr(binning.tile_ranges), ptr(binning.sorted_ids), ptr(xy), ptr(conic),
+                                 ptr(opacity), ptr(colors), ptr(bg), ptr(image), ps, cs, ptr(final_T), ptr(n_contrib), ptr(alpha),
+                                 _stream()), "b200gs_blend_fwd")
+    return image, final_T, n_contrib, alpha
+
+
+def blend_backward(mode, width, height, binning: Binning, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, v_alpha,
+                   planar: bool, xy_scale=(1.0, 1.0), want_abs: bool = False):
+    L = lib()
+    n, ch = colors.shape
+    dev = xy.device
+    # one zero-filled slab for all atomically accumulated outputs
+    width_cols = 2 + 3 + 1 + ch + (2 if want_abs else 0)
+    slab = torch.zeros(n * width_cols, dtype=torch.float32, device=dev)
+    o = 0
+    v_xy = slab[o:o + 2 * n].view(n, 2); o += 2 * n
+    v_conic = slab[o:o + 3 * n].view(n, 3); o += 3 * n
+    v_opacity = slab[o:o + n]; o += n
+    v_colors = slab[o:o + ch * n].view(n, ch); o += ch * n
+    v_abs = slab[o:o + 2 * n].view(n, 2) if want_abs else None
+    ps, cs = (1, height * width) if planar else (ch, 1)
+    with _stage("blend_bwd"):
+        check(L.b200gs_blend_bwd(mode, width, height, ch, ptr(binning.tile_ranges), ptr(binning.sorted_ids), ptr(xy), ptr(conic),
+                                 ptr(opacity), ptr(colors), ptr(bg), ptr(final_T), ptr(n_contrib), ptr(v_image), ps, cs,
+                                 ptr(v_alpha), float(xy_scale[0]), float(xy_scale[1]), ptr(v_xy), ptr(v_conic), ptr(v_opacity),
+                                 ptr(v_colors), ptr(v_abs), _stream()), "b200gs_blend_bwd")
+    return v_xy, v_conic, v_opacity, v_colors, v_abs
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# vanilla: one autograd node for the whole pipeline (diff_gaussian_rasterization semantics)
+# ----------------------------------------------------------------------------------------------------------------------
+class _RasterizeVanilla(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, bg, view: B200gsView):
+        n = means3D.shape[0]
+        means3D = _f32c(means3D, "means3D")
+        scales = _f32c(scales, "scales")
+        rotations = _f32c(rotations, "rotations")
+        opac = _f32c(opacities, "opacities").reshape(-1)
+        bg = _f32c(bg, "bg")
+        use_sh = shs is not None
+        if use_sh:
+            shs = _f32c(shs, "shs")
+            view = _copy_view(view, sh_stride=int(shs.shape[1]))
+        else:
+            colors_precomp = _f32c(colors_precomp, "colors_precomp")
+        W, H = view.width, view.height
+        xy, depth, radii, conic, _, tiles, _, rgb, clamped = project_forward(view, means3D, scales, rotations, shs if use_sh else None)
+        colors = rgb if use_sh else colors_precomp
+        binning = bin_gaussians(MODE_VANILLA, W, H, xy, depth, radii)
+        image, final_T, n_contrib, _ = blend_forward(MODE_VANILLA, W, H, binning, xy, conic, opac, colors, bg, True, False)
+        ctx.view = view
+        ctx.use_sh = use_sh
+        ctx.binning = binning
+        ctx.means2D_shape = tuple(means2D.shape)
+        ctx.opac_shape = tuple(opacities.shape)
+        ctx.save_for_backward(means3D, scales, rotations, shs if use_sh else colors_precomp, opac, bg, xy, conic, radii,
+                              clamped if use_sh else None, rgb if use_sh else None, final_T, n_contrib)
+        ctx.mark_non_differentiable(radii)
+        return image, radii
+
+    @staticmethod
+    def backward(ctx, v_image, _v_radii):
+        means3D, scales, rotations, sh_or_col, opac, bg, xy, conic, radii, clamped, rgb, final_T, n_contrib = ctx.saved_tensors
+        view = ctx.view
+        W, H = view.width, view.height
+        use_sh = ctx.use_sh
+        colors = rgb if use_sh else sh_or_col
+        v_image = _f32c(v_image, "grad_image")
+        # dgr stores dL/dmean2D in NDC-scaled units: pixel gradient x (0.5 W, 0.5 H)
+        v_xy, v_conic, v_opacity, v_colors, _ = blend_backward(MODE_VANILLA, W, H, ctx.binning, xy, conic, opac, colors, bg,
+                                                              final_T, n_contrib, v_image, None, True, (0.5 * W, 0.5 * H))
+        v_means, v_scales, v_quats, v_shs = project_backward(view, means3D, scales, rotations, sh_or_col if use_sh else None,
+                                                             radii, clamped, v_xy, None, v_conic, None, v_colors if use_sh else None)
+        n = means3D.shape[0]
+        v_means2D = torch.zeros(ctx.means2D_shape, dtype=torch.float32, device=means3D.device)
+        v_means2D[:, :2] = v_xy
+        return (v_means, v_means2D, v_shs if use_sh else None, None if use_sh else v_colors, v_opacity.reshape(ctx.opac_shape),
+                v_scales, v_quats, None, None)
+
+
+def rasterize_vanilla(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, bg, view: B200gsView):
+    """-> (color [3,H,W], radii int32 [N]).  Exactly one of shs / colors_precomp."""
+    if (shs is None) == (colors_precomp is None):
+        raise ValueError("Please provide exactly one of either SHs or precomputed colors!")
+    if scales is None or rotations is None:
+        raise NotImplementedError("cov3D_precomp is not supported by b200gs; pass scales and rotations")
+    return _RasterizeVanilla.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, bg, view)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# gsplat v0 surface
+# ----------------------------------------------------------------------------------------------------------------------
+class _ProjectGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3d, scales, quats, view: B200gsView):
+        means3d = _f32c(means3d, "means3d")
+        scales = _f32c(scales, "scales")
+        quats = _f32c(quats, "quats")
+        xy, depth, radii, conic, comp, tiles, cov3d, _, _ = project_forward(view, means3d, scales, quats, None, True, True)
+        ctx.view = view
+        ctx.save_for_backward(means3d, scales, quats, radii)
+        ctx.mark_non_differentiable(radii, tiles, cov3d)
+        return xy, depth, radii, conic, comp, tiles, cov3d
+
+    @staticmethod
+    def backward(ctx, v_xy, v_depth, _v_radii, v_conic, v_comp, _v_tiles, _v_cov3d):
+        means3d, scales, quats, radii = ctx.saved_tensors
+        n = means3d.shape[0]
+        dev = means3d.device
+
+        def z(t, shape):
+            return torch.zeros(shape, dtype=torch.float32, device=dev) if t is None else _f32c(t, "grad")
+
+        v_means, v_scales, v_quats, _ = project_backward(ctx.view, means3d, scales, quats, None, radii, None, z(v_xy, (n, 2)),
+                                                         z(v_depth, (n,)), z(v_conic, (n, 3)), z(v_comp, (n,)), None)
+        return v_means, v_scales, v_quats, None
+
+
+def project_gaussians(means3d, scales, glob_scale, quats, viewmat, fx, fy, cx, cy, img_height, img_width, block_width=16,
+                      clip_thresh=0.01, filter_2d_kernel_size=0.3, view: Optional[B200gsView] = None):
+    """gsplat v0 ``project_gaussians``: -> (xys [N,2], depths [N], radii int32 [N], conics [N,3], compensation [N],
+    num_tiles_hit int32 [N], cov3d [N,6]).  ``viewmat`` is the standard [3|4,4] world-to-camera (rows R|t), i.e.
+    ``camera.world_to_camera.T[:3,:]`` as the reference passes it (gsplat_renderer.py:69)."""
+    if block_width != TILE:
+        raise ValueError(f"b200gs supports block_width {TILE} only (the reference default, gsplat_renderer.py:7)")
+    if view is None:
+        vm = torch.eye(4, dtype=torch.float32)
+        vm[:viewmat.shape[0], :] = viewmat.detach().to("cpu", torch.float32)
+        view = make_view(MODE_GSPLAT, img_width, img_height, fx=fx, fy=fy, cx=cx, cy=cy, viewmatrix=vm.T.contiguous(),
+                         scale_modifier=glob_scale, eps2d=filter_2d_kernel_size, near_plane=clip_thresh)
+    return _ProjectGaussians.apply(means3d, scales, quats, view)
+
+
+class _SphericalHarmonics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, degree: int, dirs, coeffs):
+        dirs = _f32c(dirs, "dirs")
+        coeffs = _f32c(coeffs, "coeffs")
+        n, k = coeffs.shape[0], coeffs.shape[1]
+        rgb = torch.empty(n, 3, dtype=torch.float32, device=coeffs.device)
+        check(lib().b200gs_sh_fwd(int(degree), k, n, ptr(dirs), ptr(coeffs), ptr(rgb), _stream()), "b200gs_sh_fwd")
+        ctx.degree = int(degree)
+        ctx.save_for_backward(dirs, coeffs)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, v_rgb):
+        dirs, coeffs = ctx.saved_tensors
+        n, k = coeffs.shape[0], coeffs.shape[1]
+        v_rgb = _f32c(v_rgb, "grad")
+        v_coeffs = torch.empty_like(coeffs)
+        v_dirs = torch.empty_like(dirs) if ctx.needs_input_grad[1] else None
+        check(lib().b200gs_sh_bwd(ctx.degree, k, n, ptr(dirs), ptr(coeffs), ptr(v_rgb), ptr(v_coeffs), ptr(v_dirs), _stream()),
+              "b200gs_sh_bwd")
+        return None, v_dirs, v_coeffs
+
+
+def spherical_harmonics(degrees_to_use: int, dirs: torch.Tensor, coeffs: torch.Tensor) -> torch.Tensor:
+    """gsplat ``spherical_harmonics(deg, dirs[N,3], coeffs[N,K,3]) -> [N,3]`` (directions normalised inside)."""
+    if coeffs.shape[-1] != 3 or coeffs.dim() != 3:
+        raise ValueError("coeffs must be [N, K, 3]")
+    return _SphericalHarmonics.apply(degrees_to_use, dirs, coeffs)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xys, depths, radii, conics, colors, opacity, img_height, img_width, background, return_alpha, absgrad):
+        xys = _f32c(xys, "xys")
+        depths = _f32c(depths, "depths")
+        conics = _f32c(conics, "conics")
+        colors = _f32c(colors, "colors")
+        opac = _f32c(opacity, "opacity").reshape(-1)
+        radii = radii.contiguous()
+        bg = _f32c(background, "background") if background is not None else None
+        H, W = int(img_height), int(img_width)
+        binning = bin_gaussians(MODE_GSPLAT, W, H, xys, depths, radii)
+        image, final_T, n_contrib, alpha = blend_forward(MODE_GSPLAT, W, H, binning, xys, conics, opac, colors, bg, False, True)
+        ctx.binning = binning
+        ctx.hw = (H, W)
+        ctx.absgrad = absgrad
+        ctx.opac_shape = tuple(opacity.shape)
+        ctx.save_for_backward(xys, conics, colors, opac, bg, final_T, n_contrib)
+        ctx.xys_ref = xys
+        return image, alpha
+
+    @staticmethod
+    def backward(ctx, v_image, v_alpha):
+        xys, conics, colors, opac, bg, final_T, n_contrib = ctx.saved_tensors
+        H, W = ctx.hw
+        v_image = _f32c(v_image, "grad_image")
+        v_alpha = _f32c(v_alpha, "grad_alpha") if v_alpha is not None else None
+        v_xy, v_conic, v_opacity, v_colors, v_abs = blend_backward(MODE_GSPLAT, W, H, ctx.binning, xys, conics, opac, colors, bg,
+                                                                   final_T, n_contrib, v_image, v_alpha, False, (1.0, 1.0),
+                                                                   ctx.absgrad)
+        if ctx.absgrad:
+            ctx.xys_ref.absgrad = v_abs
+        return v_xy, None, None, v_conic, v_colors, v_opacity.reshape(ctx.opac_shape), None, None, None, None, None
+
+
+def rasterize_gaussians(xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height, img_width, block_width=16,
+                        background=None, return_alpha=False, absgrad=False):
+    """gsplat v0 ``rasterize_gaussians`` -> [H,W,D] (and alpha [H,W] when return_alpha)."""
+    if block_width != TILE:
+        raise ValueError(f"b200gs supports block_width {TILE} only")
+    if colors.dim() != 2 or not (1 <= colors.shape[1] <= 4):
+        raise ValueError("colors must be [N, D] with 1 <= D <= 4")
+    if background is not None and background.shape[0] != colors.shape[1]:
+        raise ValueError("background must have one entry per colour channel")
+    image, alpha = _RasterizeGaussians.apply(xys, depths, radii, conics, colors, opacity, img_height, img_width, background,
+                                             return_alpha, absgrad)
+    return (image, alpha) if return_alpha else image

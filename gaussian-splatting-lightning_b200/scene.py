@@ -58,3 +58,37 @@ def make_ring_cameras(width: int, height: int, n_poses: int = 32, distance: floa
         R, T = ring_pose(k, n_poses, distance)
         cams.append(make_camera(R, T, fx, fx, width / 2.0, height / 2.0, width, height, idx=k))
     return cams
+
+
+class SyntheticGaussians(torch.nn.Module):
+    """Parameter container with the getters the reference's renderers read
+    (``VanillaGaussianModel``: internal/models/vanilla_gaussian.py:345-358,422-440; internal/models/gaussian.py:250-254)."""
+
+    def __init__(self, scene: Dict[str, torch.Tensor], sh_degree: int = 3, active_sh_degree: int = None):
+        super().__init__()
+        self.gaussians = torch.nn.ParameterDict({k: torch.nn.Parameter(v.clone()) for k, v in scene.items()})
+        self.max_sh_degree = sh_degree
+        self.active_sh_degree = sh_degree if active_sh_degree is None else active_sh_degree
+
+    @property
+    def get_xyz(self):
+        return self.gaussians["means"]
+
+    @property
+    def get_scaling(self):
+        return torch.exp(self.gaussians["scales"])
+
+    @property
+    def get_rotation(self):
+        return torch.nn.functional.normalize(self.gaussians["rotations"])
+
+    @property
+    def get_opacity(self):
+        return torch.sigmoid(self.gaussians["opacities"])
+
+    @property
+    def get_features(self):
+        return torch.cat((self.gaussians["shs_dc"], self.gaussians["shs_rest"]), dim=1)
+
+    def get_shs(self):
+        return self.get_features

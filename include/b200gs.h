@@ -1,0 +1,157 @@
+/*
+ * b200gs — C ABI of the sm_100a differentiable 3D-Gaussian rasterizer (libb200gs.so).
+ *
+ * This is the drop-in boundary for the hot path of yzslab/gaussian-splatting-lightning.  The reference has no
+ * native code of its own: its renderers call two pip extensions through Python, and these entry points are what a
+ * binding for those call sites needs (citations relative to /root/reference):
+ *
+ *   diff_gaussian_rasterization.GaussianRasterizer(...)(means3D, means2D, shs, colors_precomp, opacities, scales,
+ *       rotations, cov3D_precomp) -> (color, radii)            internal/renderers/vanilla_renderer.py:62-77,111-120
+ *   gsplat.v0_interfaces.project_gaussians(...) -> 7-tuple     internal/renderers/gsplat_renderer.py:64-79
+ *   gsplat.sh.spherical_harmonics(deg, dirs, coeffs)           internal/renderers/gsplat_renderer.py:105
+ *   gsplat.rasterize.rasterize_gaussians(...) -> [H,W,D](,alpha)  internal/renderers/gsplat_renderer.py:86-99
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; all floating point is fp32, contiguous.
+ *   - the library never allocates or frees device memory: the caller (PyTorch's caching allocator) owns every
+ *     buffer including the workspace -> no hidden cudaMalloc, no hidden synchronisation (except where stated).
+ *   - all work is enqueued on the cudaStream_t passed as `stream` (a CUstream handle; pass
+ *     torch.cuda.current_stream().cuda_stream).
+ *   - return 0 on success, a negative B200GS_E* code on failure; b200gs_last_error() gives a thread-local message.
+ *     Nothing throws across the ABI; nothing calls exit().  Re-entrant: no global mutable state.
+ *   - "mode": B200GS_MODE_VANILLA = diff-gaussian-rasterization semantics (near 0.2, mean2D via the NDC projection
+ *     matrix, pixel sample at integer coords, alpha clamp 0.99 straight-through, stop T<1e-4, rect max uses +15);
+ *     B200GS_MODE_GSPLAT = the semantics of internal/utils/gaussian_projection.py + gsplat's rasterizer (near 0.01,
+ *     K t/(z+1e-6), blur compensation, pixel centres +0.5, alpha clamp 0.999 as a true clamp, stop T<=1e-4,
+ *     rect max = int((p+r)/16)+1).
+ */
+#ifndef B200GS_H
+#define B200GS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200GS_API __attribute__((visibility("default")))
+#else
+#define B200GS_API
+#endif
+
+#define B200GS_MODE_VANILLA 0
+#define B200GS_MODE_GSPLAT 1
+
+#define B200GS_OK 0
+#define B200GS_EINVAL (-1)    /* bad argument (null pointer, bad size, unsupported degree/channels) */
+#define B200GS_ECUDA (-2)     /* a CUDA call or launch failed; message holds cudaGetErrorString */
+#define B200GS_ENOSPACE (-3)  /* workspace or pair capacity too small */
+
+#define B200GS_TILE 16
+
+/* One view.  Matrices are stored exactly as the reference's Camera stores them (cameras.py:147-189):
+ * viewmatrix = world_to_camera, "transposed" (row-major [4][4], translation in the last ROW; p_cam = p * M[:3,:3] + M[3,:3]);
+ * projmatrix = full_projection = world_to_camera @ projection (same layout; vanilla mode only). */
+typedef struct B200gsView {
+    int32_t width;
+    int32_t height;
+    int32_t mode;           /* B200GS_MODE_* */
+    int32_t sh_degree;      /* active degree 0..3 */
+    int32_t sh_stride;      /* coefficients stored per Gaussian (K of shs[N,K,3]); >= (sh_degree+1)^2 */
+    int32_t reserved0;
+    float fx, fy, cx, cy;   /* gsplat mode intrinsics (gsplat_renderer.py:70-73) */
+    float tanfovx, tanfovy; /* vanilla mode (vanilla_renderer.py:59-60) */
+    float scale_modifier;
+    float eps2d;            /* 2D low-pass added to the cov2D diagonal: 0.3 */
+    float near_plane;       /* <=0 selects the mode default (0.2 vanilla / 0.01 gsplat) */
+    float reserved1;
+    float viewmatrix[16];
+    float projmatrix[16];
+    float campos[3];
+    float reserved2;
+} B200gsView;
+
+B200GS_API const char* b200gs_last_error(void);
+B200GS_API int b200gs_version(void);
+
+/* ---- K1: per-Gaussian projection (+ optional fused SH colour) ------------------------------------------------
+ * replaces dgr preprocessCUDA / gsplat project_gaussians (+ spherical_harmonics when shs != NULL).
+ * in : means[n,3] scales[n,3] quats[n,4] (wxyz, used as given); shs[n,sh_stride,3] or NULL.
+ * out: xy[n,2] depth[n] radii[n] conic[n,3] tiles[n]; comp[n] (gsplat, nullable); cov3d[n,6] upper triangle (nullable);
+ *      rgb[n,3] = max(SH+0.5,0) and clamped[n] (bit c set when channel c was clamped) when shs != NULL.
+ *      Culled Gaussians get zeros everywhere (radii 0, tiles 0).
+ * SH view direction: normalize(mean - campos).  */
+B200GS_API int b200gs_project_fwd(const B200gsView* view, int64_t n, const float* means, const float* scales, const float* quats,
+                       const float* shs, float* xy, float* depth, int32_t* radii, float* conic, float* comp,
+                       int32_t* tiles, float* cov3d, float* rgb, uint8_t* clamped, void* stream);
+
+/* ---- K8: backward of K1 ------------------------------------------------------------------------------------------
+ * in : the K1 inputs, radii (visibility), clamped (when shs), and cotangents v_xy[n,2] (vanilla: dgr's NDC-scaled
+ *      dL/dmean2D, i.e. pixel gradient x (0.5W, 0.5H); gsplat: pixel units), v_depth[n] (nullable), v_conic[n,3] (true
+ *      partials of power = -(A dx^2 + C dy^2)/2 - B dx dy), v_comp[n] (nullable), v_rgb[n,3] (nullable unless shs).
+ * out: v_means[n,3] v_scales[n,3] v_quats[n,4] and v_shs[n,sh_stride,3] (when shs) — fully written (zeros for culled).
+ * vanilla mode back-propagates the SH view direction into v_means; gsplat mode does not (renderers detach it). */
+B200GS_API int b200gs_project_bwd(const B200gsView* view, int64_t n, const float* means, const float* scales, const float* quats,
+                       const float* shs, const int32_t* radii, const uint8_t* clamped, const float* v_xy,
+                       const float* v_depth, const float* v_conic, const float* v_comp, const float* v_rgb,
+                       float* v_means, float* v_scales, float* v_quats, float* v_shs, void* stream);
+
+/* ---- standalone SH (gsplat.sh.spherical_harmonics; gsplat_renderer.py:105) -------------------------------------------
+ * dirs[n,3] need not be unit (normalised inside, as gsplat does).  out rgb[n,3] = SH (no +0.5, no clamp).
+ * bwd: v_coeffs[n,sh_stride,3] fully written; v_dirs[n,3] nullable. */
+B200GS_API int b200gs_sh_fwd(int32_t degree, int32_t sh_stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, void* stream);
+B200GS_API int b200gs_sh_bwd(int32_t degree, int32_t sh_stride, int64_t n, const float* dirs, const float* coeffs, const float* v_rgb,
+                  float* v_coeffs, float* v_dirs, void* stream);
+
+/* ---- K2-K5: tile binning ------------------------------------------------------------------------------------------
+ * replaces dgr InclusiveSum + duplicateWithKeys + SortPairs + identifyTileRanges / gsplat isect_tiles + isect_offset_encode.
+ * Result order is exactly that of a stable sort of (tile_id << 32 | float_bits(depth)) keys emitted Gaussian-major:
+ * implemented as a stable depth sort of the visible Gaussians followed by a stable tile-id partition of the pairs.
+ *
+ * b200gs_bin_count_workspace_bytes / b200gs_bin_sort_workspace_bytes: bytes of scratch for phase A (n Gaussians) and
+ *     phase B (up to max_pairs (tile,Gaussian) pairs).  Two buffers because the pair count is only known after phase A.
+ * b200gs_bin_count: phase A. Depth-sorts, scans tiles-per-Gaussian (recomputed from xy/radii with the mode's rect
+ *     rule) and writes the pair total to d_total (device int64) and, when host_total != NULL (pinned or pageable
+ *     host int64), copies it there and SYNCHRONISES the stream — the one optional host sync of the forward.
+ *     workspace_a must stay untouched until phase B has been enqueued.
+ * b200gs_bin_sort: phase B. Emits pairs, partitions by tile, writes sorted_ids[total] (Gaussian ids, front to back
+ *     inside each tile) and tile_ranges[n_tiles,2] (int32 [start,end)).  `total` must be the value phase A produced;
+ *     returns B200GS_ENOSPACE if total > max_pairs. */
+B200GS_API size_t b200gs_bin_count_workspace_bytes(int64_t n);
+B200GS_API size_t b200gs_bin_sort_workspace_bytes(int64_t n, int64_t max_pairs, int32_t width, int32_t height);
+B200GS_API int b200gs_bin_count(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const float* depth,
+                     const int32_t* radii, void* workspace_a, size_t workspace_a_bytes, int64_t* d_total,
+                     int64_t* host_total, void* stream);
+B200GS_API int b200gs_bin_sort(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const int32_t* radii,
+                    int64_t total, int64_t max_pairs, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes,
+                    int32_t* sorted_ids, int32_t* tile_ranges, void* stream);
+
+/* ---- K6: blend forward ---------------------------------------------------------------------------------------------
+ * replaces dgr renderCUDA fwd / gsplat rasterize_to_pixels fwd.  channels in {1,2,3,4}.
+ * in : xy[n,2] conic[n,3] opacity[n] colors[n,channels]; bg[channels] or NULL.
+ * out: image, addressed as image[pixel*pix_stride + channel*ch_stride] (vanilla [C,H,W]: pix_stride 1, ch_stride H*W;
+ *      gsplat [H,W,C]: pix_stride C, ch_stride 1); final_T[H*W]; n_contrib[H*W] (1-based position in the tile's list of
+ *      the last contributing splat); alpha[H*W] = 1 - final_T (nullable). */
+B200GS_API int b200gs_blend_fwd(int32_t mode, int32_t width, int32_t height, int32_t channels, const int32_t* tile_ranges,
+                     const int32_t* sorted_ids, const float* xy, const float* conic, const float* opacity,
+                     const float* colors, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride,
+                     float* final_T, int32_t* n_contrib, float* alpha, void* stream);
+
+/* ---- K7: blend backward --------------------------------------------------------------------------------------------
+ * replaces dgr renderCUDA bwd / gsplat rasterize_to_pixels bwd.
+ * in : forward inputs + final_T, n_contrib + v_image (same addressing as image) + v_alpha[H*W] (nullable).
+ * out (ACCUMULATED with atomics — caller zero-fills): v_xy[n,2] (pixel units x (xy_scale_x, xy_scale_y)),
+ *      v_conic[n,3], v_opacity[n], v_colors[n,channels]; v_xy_abs[n,2] (nullable; sum of |pixel grad|, gsplat absgrad). */
+B200GS_API int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int32_t channels, const int32_t* tile_ranges,
+                     const int32_t* sorted_ids, const float* xy, const float* conic, const float* opacity,
+                     const float* colors, const float* bg, const float* final_T, const int32_t* n_contrib,
+                     const float* v_image, int64_t pix_stride, int64_t ch_stride, const float* v_alpha,
+                     float xy_scale_x, float xy_scale_y, float* v_xy, float* v_conic, float* v_opacity,
+                     float* v_colors, float* v_xy_abs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GS_H */

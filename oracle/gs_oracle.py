@@ -170,14 +170,21 @@ def compute_cov_3d(scales: torch.Tensor, scale_modifier: float, quats: torch.Ten
     return M @ M.transpose(1, 2)
 
 
-def compute_cov_2d(t, tan_fovx, tan_fovy, focal_x, focal_y, cov_3d, world_to_camera) -> torch.Tensor:
-    """gaussian_projection.py:257-287 (same arithmetic as dgr computeCov2D before the +0.3)."""
+def compute_cov_2d(t, tan_fovx, tan_fovy, focal_x, focal_y, cov_3d, world_to_camera, dgr_clamp_grad: bool = False) -> torch.Tensor:
+    """gaussian_projection.py:257-287 (same arithmetic as dgr computeCov2D before the +0.3).
+
+    dgr_clamp_grad: the published dgr backward (computeCov2DCUDA) zeroes dL/dt_x when the +-1.3 tan(fov) clamp is active
+    and does NOT propagate the clamped value's dependence on t_z; torch.clamp autograd (gsplat mode / the reference's
+    python) does.  Forward values are identical."""
     limx = 1.3 * tan_fovx
     limy = 1.3 * tan_fovy
     txtz = t[:, 0] / t[:, 2]
     tytz = t[:, 1] / t[:, 2]
     cx_ = torch.clamp(txtz, min=-limx, max=limx) * t[:, 2]
     cy_ = torch.clamp(tytz, min=-limy, max=limy) * t[:, 2]
+    if dgr_clamp_grad:
+        cx_ = torch.where((txtz < -limx) | (txtz > limx), cx_.detach(), cx_)
+        cy_ = torch.where((tytz < -limy) | (tytz > limy), cy_.detach(), cy_)
     tz = t[:, 2]
     zero = torch.zeros_like(tz)
     J = torch.stack([
@@ -249,7 +256,7 @@ def project(mode: int, means: torch.Tensor, scales: torch.Tensor, quats: torch.T
         ndc = ph[:, :2] * pw[:, None]
         focal_x = v.width / (2.0 * v.tanfovx)
         focal_y = v.height / (2.0 * v.tanfovy)
-        cov2d = compute_cov_2d(t, v.tanfovx, v.tanfovy, focal_x, focal_y, cov3d, W2C)
+        cov2d = compute_cov_2d(t, v.tanfovx, v.tanfovy, focal_x, focal_y, cov3d, W2C, dgr_clamp_grad=True)
         a = cov2d[:, 0, 0] + 0.3
         b = cov2d[:, 0, 1]
         c = cov2d[:, 1, 1] + 0.3
