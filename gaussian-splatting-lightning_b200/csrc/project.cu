@@ -88,41 +88,47 @@ __device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z
     }
 }
 
+// Geometry shared by forward and backward.  R = double in the forward: the conic is the inverse of a 2x2 matrix whose
+// condition number reaches 1e4 for elongated splats, so fp32 intermediates put ~1e-4 of noise on pixels (measured: two
+// fp32 evaluation orders of the same formulas differ by 1.1e-4 on a 256x256 render).  Evaluating the ~150 flops per
+// Gaussian in fp64 (inputs and outputs stay fp32) removes that noise for ~10 us per million Gaussians on B200.
+template <typename R>
 struct Proj {
-    float tx, ty, tz;        // camera-space mean
-    float cxp, cyp;          // clamped tx', ty' used in J
-    bool clx, cly;           // clamp active
-    float fx, fy;            // focal used by J
-    float R[9];              // rotation from quaternion (row major)
-    float s[3];              // scales * modifier
-    float S3[6];             // cov3D upper triangle xx xy xz yy yz zz
-    float T[6];              // T = J * Rw, rows 0,1 (2x3)
-    float a, b, c, det;      // blurred cov2D and determinant
-    float a0, c0, det0;      // un-blurred diag and determinant (gsplat compensation)
+    R tx, ty, tz;        // camera-space mean
+    R cxp, cyp;          // clamped tx', ty' used in J
+    bool clx, cly;       // clamp active
+    R fx, fy;            // focal used by J
+    R Rm[9];             // rotation from quaternion (row major)
+    R s[3];              // scales * modifier
+    R S3[6];             // cov3D upper triangle xx xy xz yy yz zz
+    R T[6];              // T = J * Rw, rows 0,1 (2x3)
+    R a, b, c, det;      // blurred cov2D and determinant
+    R a0, c0, det0;      // un-blurred diag and determinant (gsplat compensation)
 };
 
-__device__ __forceinline__ void quat_to_rot(const float* q, float* R) {
-    const float r = q[0], x = q[1], y = q[2], z = q[3];
-    R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - r * z); R[2] = 2.f * (x * z + r * y);
-    R[3] = 2.f * (x * y + r * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - r * x);
-    R[6] = 2.f * (x * z - r * y); R[7] = 2.f * (y * z + r * x); R[8] = 1.f - 2.f * (x * x + y * y);
+template <typename R>
+__device__ __forceinline__ void quat_to_rot(const float* q, R* Rm) {
+    const R r = q[0], x = q[1], y = q[2], z = q[3];
+    Rm[0] = R(1) - R(2) * (y * y + z * z); Rm[1] = R(2) * (x * y - r * z); Rm[2] = R(2) * (x * z + r * y);
+    Rm[3] = R(2) * (x * y + r * z); Rm[4] = R(1) - R(2) * (x * x + z * z); Rm[5] = R(2) * (y * z - r * x);
+    Rm[6] = R(2) * (x * z - r * y); Rm[7] = R(2) * (y * z + r * x); Rm[8] = R(1) - R(2) * (x * x + y * y);
 }
 
-// Shared forward geometry (everything up to the blurred cov2D).
-template <bool GSPLAT>
-__device__ __forceinline__ void project_geometry(const B200gsView& v, const float* p, const float* sc, const float* q, Proj& g) {
+template <bool GSPLAT, typename R>
+__device__ __forceinline__ void project_geometry(const B200gsView& v, const float* p, const float* sc, const float* q, Proj<R>& g) {
     const float* V = v.viewmatrix;
-    g.tx = p[0] * V[0] + p[1] * V[4] + p[2] * V[8] + V[12];
-    g.ty = p[0] * V[1] + p[1] * V[5] + p[2] * V[9] + V[13];
-    g.tz = p[0] * V[2] + p[1] * V[6] + p[2] * V[10] + V[14];
-    quat_to_rot(q, g.R);
+    const R p0 = p[0], p1 = p[1], p2 = p[2];
+    g.tx = p0 * R(V[0]) + p1 * R(V[4]) + p2 * R(V[8]) + R(V[12]);
+    g.ty = p0 * R(V[1]) + p1 * R(V[5]) + p2 * R(V[9]) + R(V[13]);
+    g.tz = p0 * R(V[2]) + p1 * R(V[6]) + p2 * R(V[10]) + R(V[14]);
+    quat_to_rot<R>(q, g.Rm);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) g.s[k] = sc[k] * v.scale_modifier;
-    float M[9];
+    for (int k = 0; k < 3; ++k) g.s[k] = R(sc[k]) * R(v.scale_modifier);
+    R M[9];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) M[i * 3 + k] = g.R[i * 3 + k] * g.s[k];
+        for (int k = 0; k < 3; ++k) M[i * 3 + k] = g.Rm[i * 3 + k] * g.s[k];
     g.S3[0] = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
     g.S3[1] = M[0] * M[3] + M[1] * M[4] + M[2] * M[5];
     g.S3[2] = M[0] * M[6] + M[1] * M[7] + M[2] * M[8];
@@ -130,45 +136,45 @@ __device__ __forceinline__ void project_geometry(const B200gsView& v, const floa
     g.S3[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
     g.S3[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
 
-    float tanx, tany;
+    R tanx, tany;
     if (GSPLAT) {
         g.fx = v.fx; g.fy = v.fy;
-        tanx = (0.5f * float(v.width)) / v.fx;
-        tany = (0.5f * float(v.height)) / v.fy;
+        tanx = (R(0.5) * R(v.width)) / R(v.fx);
+        tany = (R(0.5) * R(v.height)) / R(v.fy);
     } else {
         tanx = v.tanfovx; tany = v.tanfovy;
-        g.fx = float(v.width) / (2.0f * tanx);
-        g.fy = float(v.height) / (2.0f * tany);
+        g.fx = R(v.width) / (R(2) * tanx);
+        g.fy = R(v.height) / (R(2) * tany);
     }
-    const float limx = 1.3f * tanx, limy = 1.3f * tany;
-    const float txtz = g.tx / g.tz, tytz = g.ty / g.tz;
+    const R limx = R(1.3) * tanx, limy = R(1.3) * tany;
+    const R txtz = g.tx / g.tz, tytz = g.ty / g.tz;
     g.clx = (txtz < -limx) || (txtz > limx);
     g.cly = (tytz < -limy) || (tytz > limy);
-    g.cxp = fminf(limx, fmaxf(-limx, txtz)) * g.tz;
-    g.cyp = fminf(limy, fmaxf(-limy, tytz)) * g.tz;
-    const float itz = 1.0f / g.tz;
-    const float j00 = g.fx * itz, j02 = -(g.fx * g.cxp) * itz * itz;
-    const float j11 = g.fy * itz, j12 = -(g.fy * g.cyp) * itz * itz;
+    g.cxp = fmin(limx, fmax(-limx, txtz)) * g.tz;
+    g.cyp = fmin(limy, fmax(-limy, tytz)) * g.tz;
+    const R itz = R(1) / g.tz;
+    const R j00 = g.fx * itz, j02 = -(g.fx * g.cxp) * itz * itz;
+    const R j11 = g.fy * itz, j12 = -(g.fy * g.cyp) * itz * itz;
     // T = J * Rw ; Rw[j][i] = V[i*4+j]
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        g.T[i] = j00 * V[i * 4 + 0] + j02 * V[i * 4 + 2];
-        g.T[3 + i] = j11 * V[i * 4 + 1] + j12 * V[i * 4 + 2];
+        g.T[i] = j00 * R(V[i * 4 + 0]) + j02 * R(V[i * 4 + 2]);
+        g.T[3 + i] = j11 * R(V[i * 4 + 1]) + j12 * R(V[i * 4 + 2]);
     }
     // cov2D = T S3 T^T
-    const float* S = g.S3;
-    const float u0 = S[0] * g.T[0] + S[1] * g.T[1] + S[2] * g.T[2];
-    const float u1 = S[1] * g.T[0] + S[3] * g.T[1] + S[4] * g.T[2];
-    const float u2 = S[2] * g.T[0] + S[4] * g.T[1] + S[5] * g.T[2];
-    const float w0 = S[0] * g.T[3] + S[1] * g.T[4] + S[2] * g.T[5];
-    const float w1 = S[1] * g.T[3] + S[3] * g.T[4] + S[4] * g.T[5];
-    const float w2 = S[2] * g.T[3] + S[4] * g.T[4] + S[5] * g.T[5];
+    const R* S = g.S3;
+    const R u0 = S[0] * g.T[0] + S[1] * g.T[1] + S[2] * g.T[2];
+    const R u1 = S[1] * g.T[0] + S[3] * g.T[1] + S[4] * g.T[2];
+    const R u2 = S[2] * g.T[0] + S[4] * g.T[1] + S[5] * g.T[2];
+    const R w0 = S[0] * g.T[3] + S[1] * g.T[4] + S[2] * g.T[5];
+    const R w1 = S[1] * g.T[3] + S[3] * g.T[4] + S[4] * g.T[5];
+    const R w2 = S[2] * g.T[3] + S[4] * g.T[4] + S[5] * g.T[5];
     g.a0 = g.T[0] * u0 + g.T[1] * u1 + g.T[2] * u2;
     g.b = g.T[3] * u0 + g.T[4] * u1 + g.T[5] * u2;
     g.c0 = g.T[3] * w0 + g.T[4] * w1 + g.T[5] * w2;
     g.det0 = g.a0 * g.c0 - g.b * g.b;
-    g.a = g.a0 + v.eps2d;
-    g.c = g.c0 + v.eps2d;
+    g.a = g.a0 + R(v.eps2d);
+    g.c = g.c0 + R(v.eps2d);
     g.det = g.a * g.c - g.b * g.b;
 }
 
@@ -192,33 +198,36 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant_
     const float sc[3] = {__ldg(scales + 3 * i), __ldg(scales + 3 * i + 1), __ldg(scales + 3 * i + 2)};
     const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + i);
     const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-    Proj g;
-    project_geometry<GSPLAT>(v, p, sc, q, g);
+    typedef double R;
+    Proj<R> g;
+    project_geometry<GSPLAT, R>(v, p, sc, q, g);
 
     const float near = near_of<GSPLAT>(v);
-    bool vis = GSPLAT ? (g.tz >= near) : (g.tz > near);
-    if (!GSPLAT) vis = vis && (g.det != 0.0f);
+    bool vis = GSPLAT ? (float(g.tz) >= near) : (float(g.tz) > near);
+    if (!GSPLAT) vis = vis && (g.det != R(0));
 
-    float px, py;
+    R pxd, pyd;
     if (GSPLAT) {
-        const float iz = 1.0f / (g.tz + 1e-6f);
-        const float zn = g.tz * iz;
-        px = (g.tx * iz) * v.fx + zn * v.cx;
-        py = (g.ty * iz) * v.fy + zn * v.cy;
+        const R iz = R(1) / (g.tz + R(1e-6));
+        const R zn = g.tz * iz;
+        pxd = (g.tx * iz) * R(v.fx) + zn * R(v.cx);
+        pyd = (g.ty * iz) * R(v.fy) + zn * R(v.cy);
     } else {
         const float* P = v.projmatrix;
-        const float hx = p[0] * P[0] + p[1] * P[4] + p[2] * P[8] + P[12];
-        const float hy = p[0] * P[1] + p[1] * P[5] + p[2] * P[9] + P[13];
-        const float hw = p[0] * P[3] + p[1] * P[7] + p[2] * P[11] + P[15];
-        const float iw = 1.0f / (hw + 0.0000001f);
-        px = ((hx * iw + 1.0f) * float(v.width) - 1.0f) * 0.5f;
-        py = ((hy * iw + 1.0f) * float(v.height) - 1.0f) * 0.5f;
+        const R p0 = p[0], p1 = p[1], p2 = p[2];
+        const R hx = p0 * R(P[0]) + p1 * R(P[4]) + p2 * R(P[8]) + R(P[12]);
+        const R hy = p0 * R(P[1]) + p1 * R(P[5]) + p2 * R(P[9]) + R(P[13]);
+        const R hw = p0 * R(P[3]) + p1 * R(P[7]) + p2 * R(P[11]) + R(P[15]);
+        const R iw = R(1) / (hw + R(0.0000001));
+        pxd = ((hx * iw + R(1)) * R(v.width) - R(1)) * R(0.5);
+        pyd = ((hy * iw + R(1)) * R(v.height) - R(1)) * R(0.5);
     }
-    const float inv_det = 1.0f / g.det;
-    const float mid = 0.5f * (g.a + g.c);
-    const float sq = sqrtf(fmaxf(0.1f, mid * mid - g.det));
-    const float lam = fmaxf(mid + sq, mid - sq);
-    const float radius = ceilf(3.0f * sqrtf(lam));
+    const float px = float(pxd), py = float(pyd);
+    const R inv_det = R(1) / g.det;
+    const R mid = R(0.5) * (g.a + g.c);
+    const R sq = sqrt(fmax(R(0.1), mid * mid - g.det));
+    const R lam = fmax(mid + sq, mid - sq);
+    const float radius = float(ceil(R(3) * sqrt(lam)));
     const int grid_x = div_up(v.width, TILE), grid_y = div_up(v.height, TILE);
     int x0, y0, x1, y1;
     tile_rect<GSPLAT>(px, py, radius, grid_x, grid_y, x0, y0, x1, y1);
@@ -227,13 +236,13 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant_
 
     if (vis) {
         xy_out[i] = make_float2(px, py);
-        depth_out[i] = g.tz;
+        depth_out[i] = float(g.tz);
         radii_out[i] = (int32_t)radius;
-        conic_out[3 * i + 0] = g.c * inv_det;
-        conic_out[3 * i + 1] = -g.b * inv_det;
-        conic_out[3 * i + 2] = g.a * inv_det;
+        conic_out[3 * i + 0] = float(g.c * inv_det);
+        conic_out[3 * i + 1] = float(-g.b * inv_det);
+        conic_out[3 * i + 2] = float(g.a * inv_det);
         tiles_out[i] = ntiles;
-        if (comp_out) comp_out[i] = GSPLAT ? sqrtf(fmaxf(g.det0 * inv_det, 0.f)) : 1.0f;
+        if (comp_out) comp_out[i] = GSPLAT ? float(sqrt(fmax(g.det0 * inv_det, R(0)))) : 1.0f;
     } else {
         xy_out[i] = make_float2(0.f, 0.f);
         depth_out[i] = 0.f;
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant_
     }
     if (cov3d_out) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) cov3d_out[6 * i + k] = vis ? g.S3[k] : 0.f;
+        for (int k = 0; k < 6; ++k) cov3d_out[6 * i + k] = vis ? float(g.S3[k]) : 0.f;
     }
     if (shs != nullptr) {
         float r = 0.f, gc = 0.f, bc = 0.f;
@@ -313,8 +322,8 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant_
     const float sc[3] = {__ldg(scales + 3 * i), __ldg(scales + 3 * i + 1), __ldg(scales + 3 * i + 2)};
     const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + i);
     const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-    Proj g;
-    project_geometry<GSPLAT>(v, p, sc, q, g);
+    Proj<float> g;
+    project_geometry<GSPLAT, float>(v, p, sc, q, g);
     const float* V = v.viewmatrix;
 
     float dmx = 0.f, dmy = 0.f, dmz = 0.f;  // dL/dmean (world)
@@ -461,7 +470,7 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant_
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) M[r * 3 + k] = g.R[r * 3 + k] * g.s[k];
+        for (int k = 0; k < 3; ++k) M[r * 3 + k] = g.Rm[r * 3 + k] * g.s[k];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -470,7 +479,7 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant_
     float dR[9];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        v_scales[3 * i + k] = v.scale_modifier * (g.R[k] * dM[k] + g.R[3 + k] * dM[3 + k] + g.R[6 + k] * dM[6 + k]);
+        v_scales[3 * i + k] = v.scale_modifier * (g.Rm[k] * dM[k] + g.Rm[3 + k] * dM[3 + k] + g.Rm[6 + k] * dM[6 + k]);
 #pragma unroll
         for (int r = 0; r < 3; ++r) dR[r * 3 + k] = dM[r * 3 + k] * g.s[k];
     }

@@ -52,27 +52,26 @@ def test_project_forward(mode, n, W, H, seed, pose, ms):
     from b200gs import ops
     sc = _scene(n, seed, ms)
     cam = _cam(W, H, pose)
-    ref = O.project(mode, sc["means"], sc["scales"], sc["rotations"], _oview(cam))
-    ref_rgb = O.sh_colors(3, sc["shs"], sc["means"], cam.camera_center, detach_dir=True)
+    d = {k: v.double() for k, v in sc.items()}
+    ref = O.project(mode, d["means"], d["scales"], d["rotations"], _oview(cam))      # float64 evaluation of the formulas
+    ref_rgb = O.sh_colors(3, d["shs"], d["means"], cam.camera_center.double(), detach_dir=True)
     g = {k: v.to(DEV) for k, v in sc.items()}
     xy, depth, radii, conic, comp, tiles, cov3d, rgb, clamped = ops.project_forward(
         _cview(cam, mode), g["means"], g["scales"], g["rotations"], g["shs"], want_comp=True, want_cov3d=True)
     radii, tiles = radii.cpu(), tiles.cpu()
     diff = radii != ref["radii"]
-    assert int(diff.sum()) <= max(1, n // 20000), f"{int(diff.sum())} radii differ"
-    assert int((radii - ref["radii"]).abs().max()) <= 1
+    assert int(diff.sum()) <= 1, f"{int(diff.sum())} radii differ"
     same = ~diff
     assert torch.equal(tiles[same], ref["tiles"][same])
     vis = ref["mask"] & same
-    assert torch.allclose(xy.cpu()[vis], ref["xy"][vis], rtol=1e-5, atol=2e-3)
-    assert torch.allclose(depth.cpu()[vis], ref["depth"][vis], rtol=1e-5, atol=1e-6)
-    assert _rel(conic.cpu()[vis], ref["conic"][vis]) < 1e-4
-    assert torch.allclose(conic.cpu()[vis], ref["conic"][vis], rtol=2e-3, atol=1e-6)
+    assert torch.allclose(xy.cpu().double()[vis], ref["xy"][vis], rtol=2e-7, atol=1e-4)
+    assert torch.allclose(depth.cpu().double()[vis], ref["depth"][vis], rtol=2e-7, atol=1e-7)
+    assert torch.allclose(conic.cpu().double()[vis], ref["conic"][vis], rtol=1e-6, atol=1e-9)
     if mode == O.MODE_GSPLAT:
-        assert torch.allclose(comp.cpu()[vis], ref["comp"][vis], rtol=1e-3, atol=1e-5)
-    assert torch.allclose(rgb.cpu()[vis], ref_rgb[vis], rtol=1e-4, atol=1e-5)
+        assert torch.allclose(comp.cpu().double()[vis], ref["comp"][vis], rtol=1e-6, atol=1e-7)
+    assert torch.allclose(rgb.cpu().double()[vis], ref_rgb[vis], rtol=1e-4, atol=2e-5)   # SH is evaluated in fp32
     up = ref["cov3d"].reshape(-1, 9)[:, [0, 1, 2, 4, 5, 8]]
-    assert torch.allclose(cov3d.cpu()[vis], up[vis], rtol=1e-4, atol=1e-9)
+    assert torch.allclose(cov3d.cpu().double()[vis], up[vis], rtol=1e-6, atol=1e-7 * float(up.abs().max()))
     # culled entries are zero
     inv = ~ref["mask"] & same
     assert float(xy.cpu()[inv].abs().sum()) == 0 and int(radii[inv].abs().sum()) == 0
@@ -228,38 +227,50 @@ def _model_and_cam(n, W, H, seed, pose, ms):
 @pytest.mark.parametrize("mode", [O.MODE_VANILLA, O.MODE_GSPLAT])
 @pytest.mark.parametrize("n,W,H,seed,pose,ms", CASES[:3])
 def test_renderer_end_to_end(mode, n, W, H, seed, pose, ms):
-    """The plug-in renderers (the call the training loop makes) vs the oracle's end-to-end render + autograd,
-    gradients taken w.r.t. the RAW parameters (through the activations), as training sees them."""
+    """The renderers' static render() (every kernel chained: K1..K8) vs the oracle's end-to-end render + autograd.
+    Both sides get bit-identical fp32 activated inputs; the oracle evaluates its formulas in float64."""
     from b200gs.renderers import B200VanillaRenderer, B200GSplatRenderer
+    from b200gs.scene import activate
     raw, model, cam = _model_and_cam(n, W, H, seed, pose, ms)
+    act = activate(raw)
     bg = torch.tensor([0.3, 0.1, 0.7])
     gen = torch.Generator().manual_seed(1)
     cot = torch.rand(3, H, W, generator=gen) * 2 - 1
 
-    # oracle on raw params
-    rp = {k: v.clone().requires_grad_(True) for k, v in raw.items()}
-    quats = torch.nn.functional.normalize(rp["rotations"])
-    shs = torch.cat((rp["shs_dc"], rp["shs_rest"]), dim=1)
-    out_ref = O.render(mode, rp["means"], torch.exp(rp["scales"]), quats, torch.sigmoid(rp["opacities"]), shs, _oview(cam), bg)
-    (out_ref["render"] * cot).sum().backward()
+    ap = {k: v.double().requires_grad_(True) for k, v in act.items()}
+    out_ref = O.render(mode, ap["means"], ap["scales"], ap["rotations"], ap["opacities"], ap["shs"], _oview(cam), bg.double())
+    (out_ref["render"] * cot.double()).sum().backward()
 
-    renderer = (B200VanillaRenderer() if mode == O.MODE_VANILLA else B200GSplatRenderer()).to(DEV)
+    gp = {k: v.to(DEV).requires_grad_(True) for k, v in act.items()}
+    R = B200VanillaRenderer if mode == O.MODE_VANILLA else B200GSplatRenderer
     cam_d = cam.to_device(DEV)
-    out = renderer(cam_d, model, bg.to(DEV))
+    out = R.render(gp["means"], gp["opacities"], gp["scales"], gp["rotations"], gp["shs"], 3, cam_d, bg.to(DEV))
     out["viewspace_points"].retain_grad()
     (out["render"] * cot.to(DEV)).sum().backward()
 
-    err = (out["render"].detach().cpu() - out_ref["render"].detach()).abs()
+    err = (out["render"].detach().cpu().double() - out_ref["render"].detach()).abs()
     assert float(err.max()) < 1e-4, float(err.max())
     assert int((out["radii"].cpu() != out_ref["radii"]).sum()) <= 1
     assert torch.equal(out["visibility_filter"].cpu(), out["radii"].cpu() > 0)
-    for k in rp:
-        assert _rel(model.gaussians[k].grad, rp[k].grad) < 1e-3, k
+    for k in ap:
+        assert _rel(gp[k].grad, ap[k].grad) < 1e-3, k
     vs = out["viewspace_points"].grad[:, :2].cpu()
     if mode == O.MODE_GSPLAT:
         assert torch.allclose(out["viewspace_points_grad_scale"].cpu(), 0.5 * torch.tensor([[W, H]], dtype=torch.float32))
     ref_vs = O.viewspace_grad(mode, out_ref["xy"].grad, W, H)
     assert _rel(vs, ref_vs) < 1e-3
+
+    # the plug-in forward(camera, model, bg) — the call the training loop makes — is the same computation on the
+    # model's own activations, with gradients reaching the RAW parameters
+    renderer = R().to(DEV)
+    out2 = renderer(cam_d, model, bg.to(DEV))
+    assert float((out2["render"] - out["render"]).abs().max()) < 2e-4      # torch-GPU vs torch-CPU activations differ by ulps
+    (out2["render"] * cot.to(DEV)).sum().backward()
+    chain = {"means": gp["means"].grad, "scales": gp["scales"].grad * act["scales"].to(DEV),
+             "opacities": gp["opacities"].grad * (act["opacities"] * (1 - act["opacities"])).to(DEV)}
+    for k, ref_g in chain.items():
+        assert _rel(model.gaussians[k].grad, ref_g) < 2e-3, k
+    assert set(out2.keys()) >= {"render", "viewspace_points", "visibility_filter", "radii"}
 
 
 def test_edge_cases():
