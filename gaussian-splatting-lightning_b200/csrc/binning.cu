@@ -86,26 +86,136 @@ LayoutB make_layout_b(int64_t max_pairs) {
     return L;
 }
 
+// ---- exact tile culling ------------------------------------------------------------------------------------------------
+// A (tile, splat) pair can only contribute if some pixel sample p of the tile has alpha = o * exp(-q(p - mu)) >= 1/255,
+// q(d) = (A dx^2 + C dy^2)/2 + B dx dy.  q is convex, so its minimum over the tile's box of pixel samples is 0 when mu is
+// inside the box and otherwise lies on one of the four edges (a clamped 1-D quadratic each).  Pairs with
+// q_min > ln(255 o) (+ a safety margin for fp32 rounding) are dropped: every pixel of the tile would have skipped that
+// splat in the blend loop anyway, so images and gradients are bit-identical, while the pair list (sort, staging, blend
+// evaluations) shrinks ~2x.  Round-to-nearest intrinsics pin the arithmetic so that the counting and the emitting
+// kernels agree on every pair.
+struct CullParams {
+    float mx, my, A, B, C, thresh;  // thresh < 0: drop everything; cull disabled when A is NaN-free and thresh = +inf
+};
+
+template <bool GSPLAT>
+__device__ __forceinline__ bool tile_hit(const CullParams& c, int tx, int ty) {
+    if (!(c.thresh < 3.0e38f)) return true;  // culling disabled
+    const float off = GSPLAT ? 0.5f : 0.0f;
+    const float X0 = __fsub_rn(__fadd_rn(float(tx * TILE), off), c.mx), X1 = __fadd_rn(X0, float(TILE - 1));
+    const float Y0 = __fsub_rn(__fadd_rn(float(ty * TILE), off), c.my), Y1 = __fadd_rn(Y0, float(TILE - 1));
+    if (X0 <= 0.f && X1 >= 0.f && Y0 <= 0.f && Y1 >= 0.f) return true;
+    const float iA = __frcp_rn(c.A), iC = __frcp_rn(c.C);
+    float qmin = 3.0e38f;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const float Xe = e ? X1 : X0;
+        const float bx = __fmul_rn(c.B, Xe);
+        const float ys = fminf(Y1, fmaxf(Y0, __fmul_rn(-bx, iC)));
+        const float q1 = __fmaf_rn(ys, __fmaf_rn(__fmul_rn(0.5f, c.C), ys, bx), __fmul_rn(__fmul_rn(0.5f, c.A), __fmul_rn(Xe, Xe)));
+        const float Ye = e ? Y1 : Y0;
+        const float by = __fmul_rn(c.B, Ye);
+        const float xs = fminf(X1, fmaxf(X0, __fmul_rn(-by, iA)));
+        const float q2 = __fmaf_rn(xs, __fmaf_rn(__fmul_rn(0.5f, c.A), xs, by), __fmul_rn(__fmul_rn(0.5f, c.C), __fmul_rn(Ye, Ye)));
+        qmin = fminf(qmin, fminf(q1, q2));
+    }
+    return !(qmin > c.thresh);  // NaN -> keep
+}
+
+__device__ __forceinline__ CullParams load_cull(const float2 p, const float* __restrict__ conic, const float* __restrict__ opacity, int64_t g) {
+    CullParams c;
+    c.mx = p.x; c.my = p.y;
+    c.A = 1.f; c.B = 0.f; c.C = 1.f;
+    c.thresh = 3.4e38f;
+    if (conic != nullptr) {
+        c.A = __ldg(conic + 3 * g); c.B = __ldg(conic + 3 * g + 1); c.C = __ldg(conic + 3 * g + 2);
+        const float o255 = 255.0f * __ldg(opacity + g);
+        // alpha >= 1/255  <=>  q <= ln(255 o); margin covers the fp32 / ex2.approx rounding of the blend loop
+        c.thresh = (o255 > 1.0f) ? __fmaf_rn(__logf(o255), 1.0001f, 1e-3f) : -1.0f;
+        if (!(o255 > 1.0f) && !(o255 <= 1.0f)) c.thresh = 3.4e38f;  // NaN opacity: keep
+    }
+    return c;
+}
+
+constexpr int SMALL_RECT = 16;
+
+// Shared walk over the rect of one Gaussian per lane (small rects serially, large ones warp-cooperatively).
+// COUNT: returns the number of kept tiles.  EMIT: writes (tile id, g) pairs from `start`.
+template <bool GSPLAT, bool EMIT>
+__device__ __forceinline__ int walk_rect(unsigned lane, bool active, int g, const CullParams& c, int x0, int y0, int x1, int y1,
+                                         int grid_x, int64_t start, int64_t max_pairs, uint32_t* __restrict__ pkeys,
+                                         int32_t* __restrict__ pvals) {
+    const int w = x1 - x0;
+    const int t_rect = active ? w * (y1 - y0) : 0;
+    int kept = 0;
+    if (t_rect > 0 && t_rect <= SMALL_RECT) {
+        for (int k = 0; k < t_rect; ++k) {
+            const int ty = y0 + k / w, tx = x0 + k % w;
+            if (tile_hit<GSPLAT>(c, tx, ty)) {
+                if (EMIT) {
+                    const int64_t o = start + kept;
+                    if (o < max_pairs) { pkeys[o] = (uint32_t)(ty * grid_x + tx); pvals[o] = g; }
+                }
+                ++kept;
+            }
+        }
+    }
+    unsigned big = __ballot_sync(0xffffffffu, t_rect > SMALL_RECT);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        CullParams bc;
+        bc.mx = __shfl_sync(0xffffffffu, c.mx, src); bc.my = __shfl_sync(0xffffffffu, c.my, src);
+        bc.A = __shfl_sync(0xffffffffu, c.A, src); bc.B = __shfl_sync(0xffffffffu, c.B, src);
+        bc.C = __shfl_sync(0xffffffffu, c.C, src); bc.thresh = __shfl_sync(0xffffffffu, c.thresh, src);
+        const int bg = __shfl_sync(0xffffffffu, g, src);
+        const int bt = __shfl_sync(0xffffffffu, t_rect, src);
+        const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+        const int bw = __shfl_sync(0xffffffffu, w, src);
+        const int64_t bstart = __shfl_sync(0xffffffffu, start, src);
+        int bkept = 0;
+        for (int k0 = 0; k0 < bt; k0 += 32) {
+            const int k = k0 + (int)lane;
+            const int ty = by0 + k / bw, tx = bx0 + k % bw;
+            const bool hit = (k < bt) && tile_hit<GSPLAT>(bc, tx, ty);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (EMIT && hit) {
+                const int64_t o = bstart + bkept + __popc(m & ((1u << lane) - 1u));
+                if (o < max_pairs) { pkeys[o] = (uint32_t)(ty * grid_x + tx); pvals[o] = bg; }
+            }
+            bkept += __popc(m);
+        }
+        if ((int)lane == src) kept = bkept;
+    }
+    return kept;
+}
+
 template <bool GSPLAT>
 __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, int grid_y, const float2* __restrict__ xy,
                                                          const float* __restrict__ depth, const int32_t* __restrict__ radii,
+                                                         const float* __restrict__ conic, const float* __restrict__ opacity,
                                                          uint32_t* __restrict__ keys, int32_t* __restrict__ ids,
                                                          int32_t* __restrict__ tiles) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int r = radii[i];
-    uint32_t key = 0xFFFFFFFFu;
-    int t = 0;
-    if (r > 0) {
-        const float2 p = xy[i];
-        int x0, y0, x1, y1;
-        tile_rect<GSPLAT>(p.x, p.y, (float)r, grid_x, grid_y, x0, y0, x1, y1);
-        t = (x1 - x0) * (y1 - y0);
-        if (t > 0) key = __float_as_uint(depth[i]);
+    const unsigned lane = threadIdx.x & 31u;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    bool active = false;
+    CullParams c{};
+    if (i < n) {
+        const int r = radii[i];
+        if (r > 0) {
+            const float2 p = xy[i];
+            tile_rect<GSPLAT>(p.x, p.y, (float)r, grid_x, grid_y, x0, y0, x1, y1);
+            c = load_cull(p, conic, opacity, i);
+            active = (x1 - x0) * (y1 - y0) > 0;
+        }
     }
-    keys[i] = key;
-    ids[i] = (int32_t)i;
-    tiles[i] = t;
+    const int t = walk_rect<GSPLAT, false>(lane, active, (int)i, c, x0, y0, x1, y1, grid_x, 0, 0, nullptr, nullptr);
+    if (i < n) {
+        keys[i] = t > 0 ? __float_as_uint(depth[i]) : 0xFFFFFFFFu;
+        ids[i] = (int32_t)i;
+        tiles[i] = t;
+    }
 }
 
 __global__ void write_total_kernel(int64_t n, const int64_t* __restrict__ offsets, int64_t* __restrict__ d_total) {
@@ -116,51 +226,28 @@ __global__ void write_total_kernel(int64_t n, const int64_t* __restrict__ offset
 template <bool GSPLAT>
 __global__ void __launch_bounds__(256) emit_pairs_kernel(int64_t n, int grid_x, int grid_y, int64_t max_pairs,
                                                          const float2* __restrict__ xy, const int32_t* __restrict__ radii,
+                                                         const float* __restrict__ conic, const float* __restrict__ opacity,
                                                          const int32_t* __restrict__ order, const int32_t* __restrict__ tiles,
                                                          const int64_t* __restrict__ offsets, uint32_t* __restrict__ pkeys,
                                                          int32_t* __restrict__ pvals) {
     const int64_t rnk = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
-    int g = -1, t = 0, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    int g = -1, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     int64_t start = 0;
+    bool active = false;
+    CullParams c{};
     if (rnk < n) {
         g = order[rnk];
-        t = tiles[g];
+        const int t = tiles[g];
         if (t > 0) {
             const float2 p = xy[g];
             tile_rect<GSPLAT>(p.x, p.y, (float)radii[g], grid_x, grid_y, x0, y0, x1, y1);
+            c = load_cull(p, conic, opacity, g);
             start = offsets[rnk] - t;
+            active = true;
         }
     }
-    constexpr int SMALL = 16;
-    if (t > 0 && t <= SMALL) {
-        const int w = x1 - x0;
-        for (int k = 0; k < t; ++k) {
-            const int64_t o = start + k;
-            if (o < max_pairs) {
-                pkeys[o] = (uint32_t)((y0 + k / w) * grid_x + x0 + k % w);
-                pvals[o] = g;
-            }
-        }
-    }
-    unsigned big = __ballot_sync(0xffffffffu, t > SMALL);
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const int bg = __shfl_sync(0xffffffffu, g, src);
-        const int bt = __shfl_sync(0xffffffffu, t, src);
-        const int bx0 = __shfl_sync(0xffffffffu, x0, src);
-        const int by0 = __shfl_sync(0xffffffffu, y0, src);
-        const int bw = __shfl_sync(0xffffffffu, x1, src) - bx0;
-        const int64_t bstart = __shfl_sync(0xffffffffu, start, src);
-        for (int k = lane; k < bt; k += 32) {
-            const int64_t o = bstart + k;
-            if (o < max_pairs) {
-                pkeys[o] = (uint32_t)((by0 + k / bw) * grid_x + bx0 + k % bw);
-                pvals[o] = bg;
-            }
-        }
-    }
+    walk_rect<GSPLAT, true>(lane, active, g, c, x0, y0, x1, y1, grid_x, start, max_pairs, pkeys, pvals);
 }
 
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t total, const uint32_t* __restrict__ keys, int2* __restrict__ ranges) {
@@ -185,7 +272,8 @@ size_t bin_count_workspace_bytes(int64_t n) { return make_layout_a(n).total; }
 size_t bin_sort_workspace_bytes(int64_t, int64_t max_pairs, int, int) { return make_layout_b(max_pairs).total; }
 
 int bin_count(int mode, int width, int height, int64_t n, const float* xy, const float* depth, const int32_t* radii,
-              void* ws, size_t ws_bytes, int64_t* d_total, int64_t* host_total, cudaStream_t s) {
+              const float* conic, const float* opacity, void* ws, size_t ws_bytes, int64_t* d_total, int64_t* host_total,
+              cudaStream_t s) {
     const LayoutA L = make_layout_a(n);
     if (ws_bytes < L.total) {
         set_error("bin_count: workspace too small (%zu < %zu)", ws_bytes, L.total);
@@ -202,9 +290,9 @@ int bin_count(int mode, int width, int height, int64_t n, const float* xy, const
     if (n > 0) {
         const unsigned blocks = (unsigned)div_up64(n, 256);
         if (mode == B200GS_MODE_GSPLAT)
-            depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, (const float2*)xy, depth, radii, keys_in, ids_in, tiles);
+            depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, (const float2*)xy, depth, radii, conic, opacity, keys_in, ids_in, tiles);
         else
-            depth_keys_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, (const float2*)xy, depth, radii, keys_in, ids_in, tiles);
+            depth_keys_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, (const float2*)xy, depth, radii, conic, opacity, keys_in, ids_in, tiles);
         B200GS_LAUNCH_CHECK();
         size_t tb = L.temp_bytes;
         B200GS_CUDA(cub::DeviceRadixSort::SortPairs(w + L.temp, tb, keys_in, keys_out, ids_in, order, (int)n, 0, 32, s));
@@ -221,9 +309,9 @@ int bin_count(int mode, int width, int height, int64_t n, const float* xy, const
     return B200GS_OK;
 }
 
-int bin_sort(int mode, int width, int height, int64_t n, const float* xy, const int32_t* radii, int64_t total,
-             int64_t max_pairs, const void* ws_a, void* ws_b, size_t ws_bytes, int32_t* sorted_ids, int32_t* tile_ranges,
-             cudaStream_t s) {
+int bin_sort(int mode, int width, int height, int64_t n, const float* xy, const int32_t* radii, const float* conic,
+             const float* opacity, int64_t total, int64_t max_pairs, const void* ws_a, void* ws_b, size_t ws_bytes,
+             int32_t* sorted_ids, int32_t* tile_ranges, cudaStream_t s) {
     const int grid_x = div_up(width, TILE), grid_y = div_up(height, TILE);
     const int n_tiles = grid_x * grid_y;
     B200GS_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(int32_t) * 2 * (size_t)n_tiles, s));
@@ -252,9 +340,9 @@ int bin_sort(int mode, int width, int height, int64_t n, const float* xy, const 
     int32_t* pvals_in = (int32_t*)(w + L.pvals_in);
     const unsigned blocks = (unsigned)div_up64(n, 256);
     if (mode == B200GS_MODE_GSPLAT)
-        emit_pairs_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, (const float2*)xy, radii, order, tiles, offsets, pkeys_in, pvals_in);
+        emit_pairs_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, (const float2*)xy, radii, conic, opacity, order, tiles, offsets, pkeys_in, pvals_in);
     else
-        emit_pairs_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, (const float2*)xy, radii, order, tiles, offsets, pkeys_in, pvals_in);
+        emit_pairs_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, (const float2*)xy, radii, conic, opacity, order, tiles, offsets, pkeys_in, pvals_in);
     B200GS_LAUNCH_CHECK();
     size_t tb = L.temp_bytes;
     // temp_b was sized for max_pairs items; cub's requirement is monotone in the item count

@@ -4,17 +4,21 @@
 // rasterize_to_pixels (gsplat mode) — SURVEY.md §8c / Appendix B; the sources are not under /root/reference, the CPU
 // restatement in oracle/gs_oracle.py::blend is the checker.
 //
-// One CTA per 16x16 tile, one thread per pixel; a warp covers an 8x4 pixel block so that a splat's footprint skips
-// whole warps (warp-ballot early out).  Each round stages up to 256 splats of the tile's depth-sorted slab into shared
-// memory (coalesced id read, L2-resident gathers of the 36 B splat record), then every pixel walks the staged slab.
+// One CTA per 16x16 tile, one thread per pixel; a warp owns an 8x4 pixel block.  Each round stages up to 256 splats of
+// the tile's depth-sorted slab into shared memory (coalesced id read, L2-resident gathers of the 36 B splat record).
+// While staging, the thread that fetched a splat also computes an 8-bit mask: which of the tile's eight 8x4 blocks
+// the splat can reach with alpha >= 1/255 (exact convex minimum of the conic's quadratic over the block, same test as
+// the tile culling of binning.cu).  Every warp then compacts the staged slab into its own index list with ballots, so
+// its pixel loop only visits splats that can touch its block: ~half of the (warp, splat) visits of the plain loop
+// disappear, and results stay bit-identical (a skipped splat would have failed the alpha test in all 32 lanes).
 //
 // Forward: the conic is pre-scaled by -0.5*log2(e) / -log2(e) while staging, so the per-(pixel,splat) body is
 // 5 FP32 ops + one MUFU.EX2 + compare/blend; colours are fetched (one LDS.128) only by contributing lanes.
 //
-// Backward walks the slab in reverse, only up to the deepest contributor of the tile.  Each pixel evaluates RB
-// consecutive splats and keeps their 9 partial derivatives in registers; the warp then reduces them with a
-// reduce-SCATTER butterfly (halving exchanges: RB -> RB/2 -> ... -> 1 value per lane), i.e. ~10 shuffles per splat
-// instead of 45 for nine independent all-reduces, and 32x fewer L2 atomics than the reference's per-pixel atomicAdd.
+// Backward walks each warp's list in reverse, only up to the deepest contributor of the warp.  Each pixel evaluates RB
+// consecutive list entries and keeps their 9 partial derivatives in registers; the warp then reduces them with a
+// reduce-SCATTER butterfly (halving exchanges: RB -> RB/2 -> ... -> 1 value per lane) and one lane per splat issues
+// the atomics: 32x fewer L2 atomics than the reference's per-pixel atomicAdd.
 #include "common.cuh"
 
 namespace b200gs {
@@ -22,6 +26,7 @@ namespace b200gs {
 namespace {
 
 constexpr int BLOCK_PIX = TILE * TILE;  // 256 threads
+constexpr int NWARP = BLOCK_PIX / 32;
 constexpr float ALPHA_MIN = 1.0f / 255.0f;
 constexpr float T_STOP = 1e-4f;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -39,6 +44,57 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// Minimum of q(d) = (A dx^2 + C dy^2)/2 + B dx dy over the box [X0,X1]x[Y0,Y1] (d measured from the splat centre).
+__device__ __forceinline__ float box_qmin(float A, float B, float C, float iA, float iC, float X0, float X1, float Y0, float Y1) {
+    if (X0 <= 0.f && X1 >= 0.f && Y0 <= 0.f && Y1 >= 0.f) return 0.f;
+    float qmin = 3.0e38f;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const float Xe = e ? X1 : X0;
+        const float bx = B * Xe;
+        const float ys = fminf(Y1, fmaxf(Y0, -bx * iC));
+        qmin = fminf(qmin, fmaf(ys, fmaf(0.5f * C, ys, bx), 0.5f * A * Xe * Xe));
+        const float Ye = e ? Y1 : Y0;
+        const float by = B * Ye;
+        const float xs = fminf(X1, fmaxf(X0, -by * iA));
+        qmin = fminf(qmin, fmaf(xs, fmaf(0.5f * A, xs, by), 0.5f * C * Ye * Ye));
+    }
+    return qmin;
+}
+
+// bit w set <=> the splat can reach alpha >= 1/255 somewhere in warp w's 8x4 block of the tile at (ox, oy)
+__device__ __forceinline__ unsigned block_mask(float mx, float my, float A, float B, float C, float opac, float ox, float oy) {
+    const float o255 = 255.0f * opac;
+    if (o255 <= 1.0f) return 0u;
+    const float thresh = fmaf(__logf(o255), 1.0001f, 1e-3f);  // ln(255 o) + margin for fp32 / ex2.approx rounding
+    const float iA = 1.0f / A, iC = 1.0f / C;
+    unsigned m = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) {
+        const float X0 = ox + float((w & 1) << 3) - mx, Y0 = oy + float((w >> 1) << 2) - my;
+        const float q = box_qmin(A, B, C, iA, iC, X0, X0 + 7.0f, Y0, Y0 + 3.0f);
+        m |= (!(q > thresh)) ? (1u << w) : 0u;  // NaN -> keep
+    }
+    return m;
+}
+
+// Every warp compacts the staged slab [0,cnt) into the ascending list of entries whose mask has its bit set (and whose
+// index is below `limit`).  Returns the list length.  s_list[w] is private to warp w.
+__device__ __forceinline__ int build_list(const unsigned char* __restrict__ s_mask, unsigned char* __restrict__ my_list, int cnt, int limit,
+                                          int warp, unsigned lane) {
+    int n = 0;
+    const int top = min(cnt, limit);
+    for (int c = 0; c < top; c += 32) {
+        const int j = c + (int)lane;
+        const bool hit = (j < top) && ((s_mask[j] >> warp) & 1u);
+        const unsigned b = __ballot_sync(FULL, hit);
+        if (hit) my_list[n + __popc(b & ((1u << lane) - 1u))] = (unsigned char)j;
+        n += __popc(b);
+    }
+    __syncwarp();
+    return n;
+}
+
 template <int CH, bool GSPLAT>
 __global__ void __launch_bounds__(BLOCK_PIX) blend_fwd_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
                                                               const int32_t* __restrict__ ids, const float2* __restrict__ xy,
@@ -50,15 +106,20 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_fwd_kernel(int width, int hei
     __shared__ float4 s_g1[BLOCK_PIX];  // x, y, -0.5*log2e*A, -log2e*B
     __shared__ float2 s_g2[BLOCK_PIX];  // -0.5*log2e*C, opacity
     __shared__ float4 s_col[BLOCK_PIX];
+    __shared__ unsigned char s_mask[BLOCK_PIX];
+    __shared__ unsigned char s_list[NWARP][BLOCK_PIX];
 
     const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const unsigned lane = tid & 31u;
     const int tile = blockIdx.y * grid_x + blockIdx.x;
     int lx, ly;
     pixel_of_thread(tid, lx, ly);
     const int px = blockIdx.x * TILE + lx, py = blockIdx.y * TILE + ly;
     const bool inside = (px < width) && (py < height);
-    const float pxf = float(px) + (GSPLAT ? 0.5f : 0.0f);
-    const float pyf = float(py) + (GSPLAT ? 0.5f : 0.0f);
+    const float off = GSPLAT ? 0.5f : 0.0f;
+    const float pxf = float(px) + off, pyf = float(py) + off;
+    const float ox = float(blockIdx.x * TILE) + off, oy = float(blockIdx.y * TILE) + off;
     const float amax = GSPLAT ? 0.999f : 0.99f;
 
     const int2 range = ranges[tile];
@@ -76,20 +137,27 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_fwd_kernel(int width, int hei
         if (tid < cnt) {
             const int g = __ldg(ids + range.x + base + tid);
             const float2 m = __ldg(xy + g);
-            s_g1[tid] = make_float4(m.x, m.y, (-0.5f * LOG2E) * __ldg(conic + 3 * g), -LOG2E * __ldg(conic + 3 * g + 1));
-            s_g2[tid] = make_float2((-0.5f * LOG2E) * __ldg(conic + 3 * g + 2), __ldg(opacity + g));
+            const float A = __ldg(conic + 3 * g), B = __ldg(conic + 3 * g + 1), Cc = __ldg(conic + 3 * g + 2);
+            const float o = __ldg(opacity + g);
+            s_g1[tid] = make_float4(m.x, m.y, (-0.5f * LOG2E) * A, -LOG2E * B);
+            s_g2[tid] = make_float2((-0.5f * LOG2E) * Cc, o);
             float col[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * CH + c);
             s_col[tid] = make_float4(col[0], col[1], col[2], col[3]);
+            s_mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
         }
         __syncthreads();
-        for (int j0 = 0; j0 < cnt; j0 += 4) {
+        if (__all_sync(FULL, done)) continue;  // warp finished: only keeps the block barriers company
+        const unsigned char* my_list = s_list[warp];
+        const int nl = build_list(s_mask, s_list[warp], cnt, cnt, warp, lane);
+        for (int i0 = 0; i0 < nl; i0 += 4) {
             if (__all_sync(FULL, done)) break;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u;
-                if (j < cnt && !done) {
+                const int i = i0 + u;
+                if (i < nl && !done) {
+                    const int j = my_list[i];
                     const float4 g1 = s_g1[j];
                     const float2 g2 = s_g2[j];
                     const float dx = g1.x - pxf, dy = g1.y - pyf;
@@ -181,17 +249,21 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
     __shared__ float2 s_g2[BLOCK_PIX];  // C, opacity
     __shared__ float4 s_col[BLOCK_PIX];
     __shared__ int s_id[BLOCK_PIX];
-    __shared__ int s_wmax[BLOCK_PIX / 32];
+    __shared__ unsigned char s_mask[BLOCK_PIX];
+    __shared__ unsigned char s_list[NWARP][BLOCK_PIX];
+    __shared__ int s_wmax[NWARP];
 
     const int tid = threadIdx.x;
+    const int warp = tid >> 5;
     const unsigned lane = tid & 31u;
     const int tile = blockIdx.y * grid_x + blockIdx.x;
     int lx, ly;
     pixel_of_thread(tid, lx, ly);
     const int px = blockIdx.x * TILE + lx, py = blockIdx.y * TILE + ly;
     const bool inside = (px < width) && (py < height);
-    const float pxf = float(px) + (GSPLAT ? 0.5f : 0.0f);
-    const float pyf = float(py) + (GSPLAT ? 0.5f : 0.0f);
+    const float off = GSPLAT ? 0.5f : 0.0f;
+    const float pxf = float(px) + off, pyf = float(py) + off;
+    const float ox = float(blockIdx.x * TILE) + off, oy = float(blockIdx.y * TILE) + off;
     const float amax = GSPLAT ? 0.999f : 0.99f;
     const int64_t pix = int64_t(py) * width + px;
 
@@ -206,14 +278,14 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
         if (bg) bg_dot += __ldg(bg + c) * vo[c];
     }
     const float va = (v_alpha && inside) ? __ldg(v_alpha + pix) : 0.f;
-    const float tail = Tf * (va - bg_dot);  // d(out)/d(alpha_i) term through everything behind the last contributor
+    const float tail = Tf * (va - bg_dot);  // d(out)/d(alpha_i) through everything behind the last contributor
 
     const int wmax = __reduce_max_sync(FULL, last);
-    if (lane == 0) s_wmax[tid >> 5] = wmax;
+    if (lane == 0) s_wmax[warp] = wmax;
     __syncthreads();
     int max_last = 0;
 #pragma unroll
-    for (int w = 0; w < BLOCK_PIX / 32; ++w) max_last = max(max_last, s_wmax[w]);
+    for (int w = 0; w < NWARP; ++w) max_last = max(max_last, s_wmax[w]);
     if (max_last == 0) return;
 
     float T = Tf;
@@ -231,75 +303,79 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
             const int g = __ldg(ids + range.x + lo + tid);
             s_id[tid] = g;
             const float2 m = __ldg(xy + g);
-            s_g1[tid] = make_float4(m.x, m.y, __ldg(conic + 3 * g), __ldg(conic + 3 * g + 1));
-            s_g2[tid] = make_float2(__ldg(conic + 3 * g + 2), __ldg(opacity + g));
+            const float A = __ldg(conic + 3 * g), B = __ldg(conic + 3 * g + 1), Cc = __ldg(conic + 3 * g + 2);
+            const float o = __ldg(opacity + g);
+            s_g1[tid] = make_float4(m.x, m.y, A, B);
+            s_g2[tid] = make_float2(Cc, o);
             float col[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * CH + c);
             s_col[tid] = make_float4(col[0], col[1], col[2], col[3]);
+            s_mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
         }
         __syncthreads();
         if (wmax <= lo) continue;  // this warp has no contributor in the batch
-        for (int jj = min(cnt, wmax - lo) - 1; jj >= 0; jj -= RB) {
+        const unsigned char* my_list = s_list[warp];
+        const int nl = build_list(s_mask, s_list[warp], cnt, wmax - lo, warp, lane);
+        for (int ii = nl - 1; ii >= 0; ii -= RB) {
             float part[NT][RB];
-            unsigned present = 0;  // bit u set when any lane of the warp has a valid sample of splat jj-u
+            unsigned present = 0;  // bit u set when any lane of the warp has a valid sample of list entry ii-u
 #pragma unroll
             for (int u = 0; u < RB; ++u) {
-                const int j = jj - u;
-                bool valid = (j >= 0) && ((lo + j) < last);
-                float dx = 0.f, dy = 0.f, G = 0.f, a = 0.f;
+                const int i = ii - u;
+                float vs = 0.f, fac = 0.f, go = 0.f, dx = 0.f, dy = 0.f;
                 float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 float2 g2 = make_float2(0.f, 0.f);
-                if (valid) {
+                bool valid = false;
+                if (i >= 0) {  // warp-uniform
+                    const int j = my_list[i];
                     g1 = s_g1[j];
                     g2 = s_g2[j];
                     dx = g1.x - pxf; dy = g1.y - pyf;
                     const float power = -0.5f * (g1.z * dx * dx + g2.x * dy * dy) - g1.w * dx * dy;
-                    G = __expf(power);
-                    a = fminf(amax, g2.y * G);
-                    valid = !(power > 0.0f) && (a >= ALPHA_MIN);
-                }
-                present |= (__ballot_sync(FULL, valid) != 0u) ? (1u << u) : 0u;
+                    const float G = __expf(power);
+                    const float a = fminf(amax, g2.y * G);
+                    valid = ((lo + j) < last) && !(power > 0.0f) && (a >= ALPHA_MIN);
+                    if (valid) {
+                        const float ra = 1.0f / (1.0f - a);
+                        T *= ra;
+                        fac = a * T;
+                        const float4 col4 = s_col[j];
+                        const float col[4] = {col4.x, col4.y, col4.z, col4.w};
+                        float v_al = tail * ra;
 #pragma unroll
-                for (int k = 0; k < NT; ++k) part[k][u] = 0.f;
-                if (valid) {
-                    const float ra = 1.0f / (1.0f - a);
-                    T *= ra;
-                    const float fac = a * T;
-                    const float4 col4 = s_col[j];
-                    const float col[4] = {col4.x, col4.y, col4.z, col4.w};
-                    float v_al = 0.f;
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                        part[6 + c][u] = fac * vo[c];
-                        v_al += (col[c] * T - buf[c] * ra) * vo[c];
-                        buf[c] += col[c] * fac;
-                    }
-                    v_al += tail * ra;
-                    if (!GSPLAT || (g2.y * G <= 0.999f)) {
-                        const float v_sigma = -g2.y * G * v_al;
-                        const float gx = v_sigma * (g1.z * dx + g1.w * dy);
-                        const float gy = v_sigma * (g1.w * dx + g2.x * dy);
-                        part[0][u] = gx;
-                        part[1][u] = gy;
-                        part[2][u] = 0.5f * v_sigma * dx * dx;
-                        part[3][u] = v_sigma * dx * dy;
-                        part[4][u] = 0.5f * v_sigma * dy * dy;
-                        part[5][u] = G * v_al;
-                        if (ABS) {
-                            part[6 + CH][u] = fabsf(gx);
-                            part[(7 + CH) % NT][u] = fabsf(gy);
+                        for (int c = 0; c < CH; ++c) {
+                            v_al += (col[c] * T - buf[c] * ra) * vo[c];
+                            buf[c] += col[c] * fac;
+                        }
+                        if (!GSPLAT || (g2.y * G <= 0.999f)) {
+                            vs = -g2.y * G * v_al;
+                            go = G * v_al;
                         }
                     }
+                }
+                present |= (__ballot_sync(FULL, valid) != 0u) ? (1u << u) : 0u;
+                const float gx = vs * (g1.z * dx + g1.w * dy);
+                const float gy = vs * (g1.w * dx + g2.x * dy);
+                part[0][u] = gx;
+                part[1][u] = gy;
+                part[2][u] = 0.5f * vs * dx * dx;
+                part[3][u] = vs * dx * dy;
+                part[4][u] = 0.5f * vs * dy * dy;
+                part[5][u] = go;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) part[6 + c][u] = fac * vo[c];
+                if (ABS) {
+                    part[6 + CH][u] = fabsf(gx);
+                    part[(7 + CH) % NT][u] = fabsf(gy);
                 }
             }
             if (present == 0u) continue;
             float tot[NT];
 #pragma unroll
             for (int k = 0; k < NT; ++k) tot[k] = reduce_scatter<RB>(part[k], lane);
-            const int j = jj - my_slot;
             if (writer && ((present >> my_slot) & 1u)) {
-                const int g = s_id[j];
+                const int g = s_id[my_list[ii - my_slot]];
                 atomicAdd(v_xy + 2 * g, tot[0] * sx);
                 atomicAdd(v_xy + 2 * g + 1, tot[1] * sy);
                 atomicAdd(v_conic + 3 * g, tot[2]);

@@ -132,8 +132,15 @@ class Binning:
 _host_total = None
 
 
-def bin_gaussians(mode: int, width: int, height: int, xy: torch.Tensor, depth: torch.Tensor, radii: torch.Tensor) -> Binning:
+TILE_CULLING = True   # exact (tile, splat) culling in K2/K3; False reproduces the reference's full 3-sigma-rect pair list
+
+
+def bin_gaussians(mode: int, width: int, height: int, xy: torch.Tensor, depth: torch.Tensor, radii: torch.Tensor,
+                  conic: Optional[torch.Tensor] = None, opacity: Optional[torch.Tensor] = None) -> Binning:
+    """K2-K5.  Passing conic+opacity enables exact tile culling (see include/b200gs.h)."""
     L = lib()
+    if not TILE_CULLING or conic is None or opacity is None:
+        conic = opacity = None
     n = xy.shape[0]
     dev = xy.device
     st = _stream()
@@ -144,14 +151,14 @@ def bin_gaussians(mode: int, width: int, height: int, xy: torch.Tensor, depth: t
     if _host_total is None:
         _host_total = torch.zeros(1, dtype=torch.int64).pin_memory()
     with _stage("bin_count"):
-        check(L.b200gs_bin_count(mode, width, height, n, ptr(xy), ptr(depth), ptr(radii), ptr(ws_a), ws_a.numel(),
+        check(L.b200gs_bin_count(mode, width, height, n, ptr(xy), ptr(depth), ptr(radii), ptr(conic), ptr(opacity), ptr(ws_a), ws_a.numel(),
                                  ptr(d_total), _host_total.data_ptr(), st), "b200gs_bin_count")
     total = int(_host_total[0])
     sorted_ids = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
     ws_b = torch.empty(L.b200gs_bin_sort_workspace_bytes(n, total, width, height), dtype=torch.uint8, device=dev)
     with _stage("bin_sort"):
-        check(L.b200gs_bin_sort(mode, width, height, n, ptr(xy), ptr(radii), total, total, ptr(ws_a), ptr(ws_b), ws_b.numel(),
+        check(L.b200gs_bin_sort(mode, width, height, n, ptr(xy), ptr(radii), ptr(conic), ptr(opacity), total, total, ptr(ws_a), ptr(ws_b), ws_b.numel(),
                                 ptr(sorted_ids), ptr(ranges), st), "b200gs_bin_sort")
     return Binning(sorted_ids, ranges, total)
 
@@ -261,7 +268,7 @@ class _RasterizeVanilla(torch.autograd.Function):
         W, H = view.width, view.height
         xy, depth, radii, conic, _, tiles, _, rgb, clamped = project_forward(view, means3D, scales, rotations, shs if use_sh else None)
         colors = rgb if use_sh else colors_precomp
-        binning = bin_gaussians(MODE_VANILLA, W, H, xy, depth, radii)
+        binning = bin_gaussians(MODE_VANILLA, W, H, xy, depth, radii, conic, opac)
         image, final_T, n_contrib, _ = blend_forward(MODE_VANILLA, W, H, binning, xy, conic, opac, colors, bg, True, False)
         ctx.view = view
         ctx.use_sh = use_sh
@@ -388,7 +395,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         radii = radii.contiguous()
         bg = _f32c(background, "background") if background is not None else None
         H, W = int(img_height), int(img_width)
-        binning = bin_gaussians(MODE_GSPLAT, W, H, xys, depths, radii)
+        binning = bin_gaussians(MODE_GSPLAT, W, H, xys, depths, radii, conics, opac)
         image, final_T, n_contrib, alpha = blend_forward(MODE_GSPLAT, W, H, binning, xys, conics, opac, colors, bg, False, True)
         ctx.binning = binning
         ctx.hw = (H, W)

@@ -110,6 +110,11 @@ B200GS_API int b200gs_sh_bwd(int32_t degree, int32_t sh_stride, int64_t n, const
  * Result order is exactly that of a stable sort of (tile_id << 32 | float_bits(depth)) keys emitted Gaussian-major:
  * implemented as a stable depth sort of the visible Gaussians followed by a stable tile-id partition of the pairs.
  *
+ * cull_conic[n,3] / cull_opacity[n] (both NULL, or both given — and then the SAME arrays in phase A and B): exact tile
+ *     culling.  A (tile, Gaussian) pair is dropped when no pixel sample of the tile can reach alpha >= 1/255 for that
+ *     Gaussian (minimum of the conic's quadratic over the tile box > ln(255*opacity)); the blend loop would have skipped
+ *     it at every pixel, so images and gradients do not change while the pair list shrinks ~2x.  With NULL the pair
+ *     list is exactly the reference's (every tile of the 3-sigma bounding rect).
  * b200gs_bin_count_workspace_bytes / b200gs_bin_sort_workspace_bytes: bytes of scratch for phase A (n Gaussians) and
  *     phase B (up to max_pairs (tile,Gaussian) pairs).  Two buffers because the pair count is only known after phase A.
  * b200gs_bin_count: phase A. Depth-sorts, scans tiles-per-Gaussian (recomputed from xy/radii with the mode's rect
@@ -122,10 +127,10 @@ B200GS_API int b200gs_sh_bwd(int32_t degree, int32_t sh_stride, int64_t n, const
 B200GS_API size_t b200gs_bin_count_workspace_bytes(int64_t n);
 B200GS_API size_t b200gs_bin_sort_workspace_bytes(int64_t n, int64_t max_pairs, int32_t width, int32_t height);
 B200GS_API int b200gs_bin_count(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const float* depth,
-                     const int32_t* radii, void* workspace_a, size_t workspace_a_bytes, int64_t* d_total,
+                     const int32_t* radii, const float* cull_conic, const float* cull_opacity, void* workspace_a, size_t workspace_a_bytes, int64_t* d_total,
                      int64_t* host_total, void* stream);
 B200GS_API int b200gs_bin_sort(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const int32_t* radii,
-                    int64_t total, int64_t max_pairs, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes,
+                    const float* cull_conic, const float* cull_opacity, int64_t total, int64_t max_pairs, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes,
                     int32_t* sorted_ids, int32_t* tile_ranges, void* stream);
 
 /* ---- K6: blend forward ---------------------------------------------------------------------------------------------

@@ -131,6 +131,36 @@ def test_binning_exact(mode, n, W, H, seed, pose, ms):
     assert torch.equal(b.tile_ranges.cpu().long(), ranges)
 
 
+@pytest.mark.parametrize("mode", [O.MODE_VANILLA, O.MODE_GSPLAT])
+@pytest.mark.parametrize("n,W,H,seed,pose,ms", CASES[:3])
+def test_tile_culling_is_exact(mode, n, W, H, seed, pose, ms):
+    """Exact tile culling drops only pairs no pixel of the tile would have used: per tile the culled list is an
+    order-preserving subsequence of the reference list, and the blended image / saved state are BIT-identical."""
+    from b200gs import ops
+    ref, colors, op, sids, ranges = _projected_inputs(mode, n, W, H, seed, pose, ms)
+    dxy, ddep, drad, dcon, dop, dcol = (t.detach().to(DEV).contiguous() for t in
+                                        (ref["xy"], ref["depth"], ref["radii"], ref["conic"], op, colors))
+    full = ops.bin_gaussians(mode, W, H, dxy, ddep, drad)
+    cul = ops.bin_gaussians(mode, W, H, dxy, ddep, drad, dcon, dop)
+    assert torch.equal(full.sorted_ids[:full.total].cpu(), sids)
+    assert 0 < cul.total < full.total
+    fr, cr = full.tile_ranges.cpu().tolist(), cul.tile_ranges.cpu().tolist()
+    fi, ci = full.sorted_ids.cpu().tolist(), cul.sorted_ids.cpu().tolist()
+    for (fs, fe), (cs, ce) in zip(fr, cr):
+        it = iter(fi[fs:fe])
+        assert all(any(x == y for y in it) for x in ci[cs:ce])
+    bg = torch.tensor([0.1, 0.25, 0.6], device=DEV)
+    planar = mode == O.MODE_VANILLA
+    a = ops.blend_forward(mode, W, H, full, dxy, dcon, dop, dcol, bg, planar, True)
+    b = ops.blend_forward(mode, W, H, cul, dxy, dcon, dop, dcol, bg, planar, True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[3], b[3])
+    v_image = (torch.rand(a[0].shape, generator=torch.Generator().manual_seed(3)) * 2 - 1).to(DEV)
+    ga = ops.blend_backward(mode, W, H, full, dxy, dcon, dop, dcol, bg, a[1], a[2], v_image, None, planar)
+    gb = ops.blend_backward(mode, W, H, cul, dxy, dcon, dop, dcol, bg, b[1], b[2], v_image, None, planar)
+    for x, y in zip(ga[:4], gb[:4]):
+        assert _rel(x, y) < 1e-5      # same terms, different atomic order
+
+
 def _projected_inputs(mode, n, W, H, seed, pose, ms, dtype=torch.float32):
     sc = _scene(n, seed, ms)
     cam = _cam(W, H, pose)
