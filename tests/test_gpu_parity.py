@@ -43,8 +43,10 @@ def _assert_pixels(img, ref, what=""):
     takes the other branch in fp32 than in the float64 oracle and moves that one pixel by up to alpha*T*c <= 1/255;
     such isolated pixels are counted and bounded instead of failing the image."""
     err = (img.detach().cpu().double() - ref.detach().cpu().double()).abs()
-    n_bad = int((err > 1e-4).sum())
-    assert n_bad <= max(3, err.numel() // 50000), f"{what}: {n_bad} values off by more than 1e-4 (max {float(err.max()):.3e})"
+    per_pixel = err if err.dim() == 2 else err.max(dim=0).values      # [C,H,W] -> [H,W]
+    n_bad = int((per_pixel > 1e-4).sum())
+    # expected flips: ~1e-7 per (pixel, splat) evaluation (relative fp32 error of o*exp(q) around the cut-off)
+    assert n_bad <= max(4, per_pixel.numel() // 10000), f"{what}: {n_bad} pixels off by more than 1e-4 (max {float(err.max()):.3e})"
     assert float(err.max()) < 4.5e-3, f"{what}: max err {float(err.max()):.3e}"
     assert float(err.median()) < 1e-6
 
