@@ -77,6 +77,16 @@ int launch_project_bwd(const B200gsView& v, int64_t n, const float* means, const
                        const float* shs, const int32_t* radii, const uint8_t* clamped, const float* v_xy,
                        const float* v_depth, const float* v_conic, const float* v_comp, const float* v_rgb,
                        float* v_means, float* v_scales, float* v_quats, float* v_shs, cudaStream_t s);
+int launch_project_fwd_raw(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
+                           const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased, float* xy,
+                           float* depth, int32_t* radii, float* conic, float* comp, int32_t* tiles, float* cov3d, float* rgb,
+                           uint8_t* clamped, float* opac_out, cudaStream_t s);
+int launch_project_bwd_raw(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
+                           const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased,
+                           const int32_t* radii, const uint8_t* clamped, const float* v_xy, const float* v_depth,
+                           const float* v_conic, const float* v_comp, const float* v_rgb, const float* v_opac, float* v_means,
+                           float* v_scales, float* v_quats, float* v_opac_logit, float* v_shs_dc, float* v_shs_rest,
+                           cudaStream_t s);
 int launch_sh_fwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, cudaStream_t s);
 int launch_sh_bwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, const float* v_rgb,
                   float* v_coeffs, float* v_dirs, cudaStream_t s);

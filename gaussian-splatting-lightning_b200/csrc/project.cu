@@ -107,7 +107,7 @@ struct Proj {
 };
 
 template <typename R>
-__device__ __forceinline__ void quat_to_rot(const float* q, R* Rm) {
+__device__ __forceinline__ void quat_to_rot(const R* q, R* Rm) {
     const R r = q[0], x = q[1], y = q[2], z = q[3];
     Rm[0] = R(1) - R(2) * (y * y + z * z); Rm[1] = R(2) * (x * y - r * z); Rm[2] = R(2) * (x * z + r * y);
     Rm[3] = R(2) * (x * y + r * z); Rm[4] = R(1) - R(2) * (x * x + z * z); Rm[5] = R(2) * (y * z - r * x);
@@ -115,7 +115,7 @@ __device__ __forceinline__ void quat_to_rot(const float* q, R* Rm) {
 }
 
 template <bool GSPLAT, typename R>
-__device__ __forceinline__ void project_geometry(const B200gsView& v, const float* p, const float* sc, const float* q, Proj<R>& g) {
+__device__ __forceinline__ void project_geometry(const B200gsView& v, const float* p, const R* sc, const R* q, Proj<R>& g) {
     const float* V = v.viewmatrix;
     const R p0 = p[0], p1 = p[1], p2 = p[2];
     g.tx = p0 * R(V[0]) + p1 * R(V[4]) + p2 * R(V[8]) + R(V[12]);
@@ -123,7 +123,7 @@ __device__ __forceinline__ void project_geometry(const B200gsView& v, const floa
     g.tz = p0 * R(V[2]) + p1 * R(V[6]) + p2 * R(V[10]) + R(V[14]);
     quat_to_rot<R>(q, g.Rm);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) g.s[k] = R(sc[k]) * R(v.scale_modifier);
+    for (int k = 0; k < 3; ++k) g.s[k] = sc[k] * R(v.scale_modifier);
     R M[9];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -178,13 +178,58 @@ __device__ __forceinline__ void project_geometry(const B200gsView& v, const floa
     g.det = g.a * g.c - g.b * g.b;
 }
 
+// Optional fused-activation ("raw parameter") operands: the model's exp / normalize / sigmoid activations and the
+// dc|rest concatenation (vanilla_gaussian.py:345-358, gaussian.py:250-254) folded into K1 / K8.
+struct RawIO {
+    const float* opac_in;    // [n] opacity logits
+    const float* shs_rest;   // [n, sh_stride-1, 3]; the `shs` argument then points at shs_dc [n,1,3]
+    float* opac_out;         // [n] opacity handed to the blend kernels (sigmoid, x compensation when anti_aliased)
+    const float* v_opac;     // [n] dL/d(opac_out) from the blend backward
+    float* v_opac_logit;     // [n]
+    float* v_shs_rest;       // [n, sh_stride-1, 3]; `v_shs` then receives the dc gradient [n,1,3]
+    int anti_aliased;
+};
+
+template <bool RAW, typename R>
+__device__ __forceinline__ void load_scale_quat(const float* __restrict__ scales, const float* __restrict__ quats, int64_t i, R* sc, R* q,
+                                                R* inv_qnorm) {
+    const float s0 = __ldg(scales + 3 * i), s1 = __ldg(scales + 3 * i + 1), s2 = __ldg(scales + 3 * i + 2);
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + i);
+    if (RAW) {
+        sc[0] = exp(R(s0)); sc[1] = exp(R(s1)); sc[2] = exp(R(s2));
+        const R w = q4.x, x = q4.y, y = q4.z, z = q4.w;
+        const R inv = R(1) / fmax(sqrt(w * w + x * x + y * y + z * z), R(1e-12));  // F.normalize eps
+        q[0] = w * inv; q[1] = x * inv; q[2] = y * inv; q[3] = z * inv;
+        *inv_qnorm = inv;
+    } else {
+        sc[0] = s0; sc[1] = s1; sc[2] = s2;
+        q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+        *inv_qnorm = R(1);
+    }
+}
+
+// SH block of Gaussian i into registers: [K,3] contiguous, or dc [1,3] + rest [K-1,3] when RAW
+template <bool RAW>
+__device__ __forceinline__ void load_sh_any(const float* __restrict__ shs, const float* __restrict__ shs_rest, int64_t i, int stride,
+                                            int ncoef, float* sh) {
+    if (RAW) {
+        sh[0] = __ldg(shs + 3 * i); sh[1] = __ldg(shs + 3 * i + 1); sh[2] = __ldg(shs + 3 * i + 2);
+        const float* r = shs_rest + i * int64_t(stride - 1) * 3;
+#pragma unroll
+        for (int q = 3; q < MAX_COEFFS * 3; ++q)
+            if (q < ncoef * 3) sh[q] = __ldg(r + q - 3);
+    } else {
+        load_sh(shs + i * int64_t(stride) * 3, ncoef, ((stride * 3) & 3) == 0, sh);
+    }
+}
+
 template <bool GSPLAT>
 __device__ __forceinline__ float near_of(const B200gsView& v) {
     return v.near_plane > 0.f ? v.near_plane : (GSPLAT ? 0.01f : 0.2f);
 }
 
-template <bool GSPLAT>
-__global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant__ B200gsView v, int64_t n,
+template <bool GSPLAT, bool RAW>
+__global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
                                                           const float* __restrict__ means, const float* __restrict__ scales,
                                                           const float* __restrict__ quats, const float* __restrict__ shs,
                                                           float2* __restrict__ xy_out, float* __restrict__ depth_out,
@@ -195,10 +240,9 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant_
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
-    const float sc[3] = {__ldg(scales + 3 * i), __ldg(scales + 3 * i + 1), __ldg(scales + 3 * i + 2)};
-    const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + i);
-    const float q[4] = {q4.x, q4.y, q4.z, q4.w};
     typedef double R;
+    R sc[3], q[4], inv_qn;
+    load_scale_quat<RAW, R>(scales, quats, i, sc, q, &inv_qn);
     Proj<R> g;
     project_geometry<GSPLAT, R>(v, p, sc, q, g);
 
@@ -242,8 +286,14 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant_
         conic_out[3 * i + 1] = float(-g.b * inv_det);
         conic_out[3 * i + 2] = float(g.a * inv_det);
         tiles_out[i] = ntiles;
-        if (comp_out) comp_out[i] = GSPLAT ? float(sqrt(fmax(g.det0 * inv_det, R(0)))) : 1.0f;
+        const float comp = GSPLAT ? float(sqrt(fmax(g.det0 * inv_det, R(0)))) : 1.0f;
+        if (comp_out) comp_out[i] = comp;
+        if (RAW) {
+            const float o = 1.0f / (1.0f + expf(-__ldg(raw.opac_in + i)));
+            raw.opac_out[i] = (GSPLAT && raw.anti_aliased) ? o * comp : o;
+        }
     } else {
+        if (RAW) raw.opac_out[i] = 0.f;
         xy_out[i] = make_float2(0.f, 0.f);
         depth_out[i] = 0.f;
         radii_out[i] = 0;
@@ -262,8 +312,7 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant_
             const int deg = v.sh_degree;
             const int ncoef = (deg + 1) * (deg + 1);
             float sh[MAX_COEFFS * 3];
-            const bool vec4 = ((v.sh_stride * 3) & 3) == 0;
-            load_sh(shs + i * int64_t(v.sh_stride) * 3, ncoef, vec4, sh);
+            load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
             float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
             const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
             dx *= inv_len; dy *= inv_len; dz *= inv_len;
@@ -290,8 +339,8 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------------
-template <bool GSPLAT>
-__global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant__ B200gsView v, int64_t n,
+template <bool GSPLAT, bool RAW>
+__global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
                                                           const float* __restrict__ means, const float* __restrict__ scales,
                                                           const float* __restrict__ quats, const float* __restrict__ shs,
                                                           const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
@@ -309,19 +358,25 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant_
         v_scales[3 * i] = 0.f; v_scales[3 * i + 1] = 0.f; v_scales[3 * i + 2] = 0.f;
         v_quats[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (v_shs) {
-            float* o = v_shs + i * int64_t(stride3);
-            if (vec4) {
-                for (int k = 0; k < stride3 / 4; ++k) reinterpret_cast<float4*>(o)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (RAW) {
+                v_shs[3 * i] = 0.f; v_shs[3 * i + 1] = 0.f; v_shs[3 * i + 2] = 0.f;
+                float* o = raw.v_shs_rest + i * int64_t(stride3 - 3);
+                for (int k = 0; k < stride3 - 3; ++k) o[k] = 0.f;
             } else {
-                for (int k = 0; k < stride3; ++k) o[k] = 0.f;
+                float* o = v_shs + i * int64_t(stride3);
+                if (vec4) {
+                    for (int k = 0; k < stride3 / 4; ++k) reinterpret_cast<float4*>(o)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    for (int k = 0; k < stride3; ++k) o[k] = 0.f;
+                }
             }
         }
+        if (RAW) raw.v_opac_logit[i] = 0.f;
         return;
     }
     const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
-    const float sc[3] = {__ldg(scales + 3 * i), __ldg(scales + 3 * i + 1), __ldg(scales + 3 * i + 2)};
-    const float4 q4 = __ldg(reinterpret_cast<const float4*>(quats) + i);
-    const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+    float sc[3], q[4], inv_qn;
+    load_scale_quat<RAW, float>(scales, quats, i, sc, q, &inv_qn);
     Proj<float> g;
     project_geometry<GSPLAT, float>(v, p, sc, q, g);
     const float* V = v.viewmatrix;
@@ -348,20 +403,28 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant_
             const float bk = (k < ncoef) ? bs[k] : 0.f;
             out[3 * k + 0] = bk * gr; out[3 * k + 1] = bk * gg; out[3 * k + 2] = bk * gb;
         }
-        float* o = v_shs + i * int64_t(stride3);
-        if (vec4) {
-            for (int k = 0; k < stride3 / 4; ++k) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k * 4 < MAX_COEFFS * 3) t = make_float4(out[k * 4], out[k * 4 + 1], out[k * 4 + 2], out[k * 4 + 3]);
-                reinterpret_cast<float4*>(o)[k] = t;
-            }
+        if (RAW) {
+            v_shs[3 * i] = out[0]; v_shs[3 * i + 1] = out[1]; v_shs[3 * i + 2] = out[2];
+            float* o = raw.v_shs_rest + i * int64_t(stride3 - 3);
+#pragma unroll
+            for (int k = 3; k < MAX_COEFFS * 3; ++k)
+                if (k < stride3) o[k - 3] = out[k];
         } else {
-            for (int k = 0; k < stride3; ++k) o[k] = (k < MAX_COEFFS * 3) ? out[k] : 0.f;
+            float* o = v_shs + i * int64_t(stride3);
+            if (vec4) {
+                for (int k = 0; k < stride3 / 4; ++k) {
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (k * 4 < MAX_COEFFS * 3) t = make_float4(out[k * 4], out[k * 4 + 1], out[k * 4 + 2], out[k * 4 + 3]);
+                    reinterpret_cast<float4*>(o)[k] = t;
+                }
+            } else {
+                for (int k = 0; k < stride3; ++k) o[k] = (k < MAX_COEFFS * 3) ? out[k] : 0.f;
+            }
         }
         if (!GSPLAT && deg > 0) {
             // view direction -> mean (dgr back-propagates it; gsplat renderers detach the direction)
             float sh[MAX_COEFFS * 3];
-            load_sh(shs + i * int64_t(stride3), ncoef, vec4, sh);
+            load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
             float bx[MAX_COEFFS], by[MAX_COEFFS], bz[MAX_COEFFS];
             sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
@@ -391,8 +454,21 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant_
     float db = -2.0f * (m00 * B + m01 * C);
     float dc = -(m10 * B + m11 * C);
     (void)m10;
-    if (GSPLAT && v_comp != nullptr) {
-        const float vc = __ldg(v_comp + i);
+    float vc_total = (GSPLAT && v_comp != nullptr) ? __ldg(v_comp + i) : 0.f;
+    if (RAW) {
+        // blend opacity = sigmoid(logit) [* compensation]: split dL/d(opac_out) between the logit and the compensation
+        const float o = 1.0f / (1.0f + expf(-__ldg(raw.opac_in + i)));
+        const float vo = __ldg(raw.v_opac + i);
+        float v_sig = vo;
+        if (GSPLAT && raw.anti_aliased) {
+            const float comp = sqrtf(fmaxf(g.det0 / g.det, 0.f));
+            v_sig = vo * comp;
+            vc_total += vo * o;
+        }
+        raw.v_opac_logit[i] = v_sig * o * (1.0f - o);
+    }
+    if (GSPLAT && (v_comp != nullptr || RAW)) {
+        const float vc = vc_total;
         if (g.det0 > 0.f && vc != 0.f) {
             const float comp = sqrtf(g.det0 * inv_det);
             const float d_det0 = vc * 0.5f * comp / g.det0;
@@ -479,7 +555,8 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant_
     float dR[9];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        v_scales[3 * i + k] = v.scale_modifier * (g.Rm[k] * dM[k] + g.Rm[3 + k] * dM[3 + k] + g.Rm[6 + k] * dM[6 + k]);
+        const float vs_k = v.scale_modifier * (g.Rm[k] * dM[k] + g.Rm[3 + k] * dM[3 + k] + g.Rm[6 + k] * dM[6 + k]);
+        v_scales[3 * i + k] = RAW ? vs_k * sc[k] : vs_k;   // d exp(x) = exp(x)
 #pragma unroll
         for (int r = 0; r < 3; ++r) dR[r * 3 + k] = dM[r * 3 + k] * g.s[k];
     }
@@ -489,6 +566,11 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant_
     dq.y = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
     dq.z = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
     dq.w = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+    if (RAW) {  // through q / |q|
+        const float dot = dq.x * q[0] + dq.y * q[1] + dq.z * q[2] + dq.w * q[3];
+        dq.x = (dq.x - q[0] * dot) * inv_qn; dq.y = (dq.y - q[1] * dot) * inv_qn;
+        dq.z = (dq.z - q[2] * dot) * inv_qn; dq.w = (dq.w - q[3] * dot) * inv_qn;
+    }
     v_quats[i] = dq;
 }
 
@@ -558,15 +640,28 @@ __global__ void __launch_bounds__(256) sh_bwd_kernel(int deg, int stride, int64_
 int launch_project_fwd(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
                        const float* shs, float* xy, float* depth, int32_t* radii, float* conic, float* comp,
                        int32_t* tiles, float* cov3d, float* rgb, uint8_t* clamped, cudaStream_t s) {
+    return launch_project_fwd_raw(v, n, means, scales, quats, nullptr, shs, nullptr, 0, xy, depth, radii, conic, comp, tiles, cov3d,
+                                  rgb, clamped, nullptr, s);
+}
+
+int launch_project_fwd_raw(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
+                           const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased, float* xy,
+                           float* depth, int32_t* radii, float* conic, float* comp, int32_t* tiles, float* cov3d, float* rgb,
+                           uint8_t* clamped, float* opac_out, cudaStream_t s) {
     if (n == 0) return B200GS_OK;
     const int threads = 256;
     const unsigned blocks = (unsigned)div_up64(n, threads);
-    if (v.mode == B200GS_MODE_GSPLAT)
-        project_fwd_kernel<true><<<blocks, threads, 0, s>>>(v, n, means, scales, quats, shs, (float2*)xy, depth, radii, conic,
-                                                            comp, tiles, cov3d, rgb, clamped);
-    else
-        project_fwd_kernel<false><<<blocks, threads, 0, s>>>(v, n, means, scales, quats, shs, (float2*)xy, depth, radii, conic,
-                                                             comp, tiles, cov3d, rgb, clamped);
+    const bool raw_mode = opac_out != nullptr;
+    RawIO raw{opac_logits, shs_rest, opac_out, nullptr, nullptr, nullptr, anti_aliased};
+#define B200GS_PF_ARGS v, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth, radii, conic, comp, tiles, cov3d, rgb, clamped
+    if (v.mode == B200GS_MODE_GSPLAT) {
+        if (raw_mode) project_fwd_kernel<true, true><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);
+        else project_fwd_kernel<true, false><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);
+    } else {
+        if (raw_mode) project_fwd_kernel<false, true><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);
+        else project_fwd_kernel<false, false><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);
+    }
+#undef B200GS_PF_ARGS
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }
@@ -575,17 +670,31 @@ int launch_project_bwd(const B200gsView& v, int64_t n, const float* means, const
                        const float* shs, const int32_t* radii, const uint8_t* clamped, const float* v_xy,
                        const float* v_depth, const float* v_conic, const float* v_comp, const float* v_rgb,
                        float* v_means, float* v_scales, float* v_quats, float* v_shs, cudaStream_t s) {
+    return launch_project_bwd_raw(v, n, means, scales, quats, nullptr, shs, nullptr, 0, radii, clamped, v_xy, v_depth, v_conic,
+                                  v_comp, v_rgb, nullptr, v_means, v_scales, v_quats, nullptr, v_shs, nullptr, s);
+}
+
+int launch_project_bwd_raw(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
+                           const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased,
+                           const int32_t* radii, const uint8_t* clamped, const float* v_xy, const float* v_depth,
+                           const float* v_conic, const float* v_comp, const float* v_rgb, const float* v_opac, float* v_means,
+                           float* v_scales, float* v_quats, float* v_opac_logit, float* v_shs_dc, float* v_shs_rest,
+                           cudaStream_t s) {
     if (n == 0) return B200GS_OK;
     const int threads = 256;
     const unsigned blocks = (unsigned)div_up64(n, threads);
-    if (v.mode == B200GS_MODE_GSPLAT)
-        project_bwd_kernel<true><<<blocks, threads, 0, s>>>(v, n, means, scales, quats, shs, radii, clamped, (const float2*)v_xy,
-                                                            v_depth, v_conic, v_comp, v_rgb, v_means, v_scales,
-                                                            (float4*)v_quats, v_shs);
-    else
-        project_bwd_kernel<false><<<blocks, threads, 0, s>>>(v, n, means, scales, quats, shs, radii, clamped, (const float2*)v_xy,
-                                                             v_depth, v_conic, v_comp, v_rgb, v_means, v_scales,
-                                                             (float4*)v_quats, v_shs);
+    const bool raw_mode = v_opac_logit != nullptr;
+    RawIO raw{opac_logits, shs_rest, nullptr, v_opac, v_opac_logit, v_shs_rest, anti_aliased};
+#define B200GS_PB_ARGS v, raw, n, means, scales, quats, shs_dc, radii, clamped, (const float2*)v_xy, v_depth, v_conic, v_comp, v_rgb, \
+                       v_means, v_scales, (float4*)v_quats, v_shs_dc
+    if (v.mode == B200GS_MODE_GSPLAT) {
+        if (raw_mode) project_bwd_kernel<true, true><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);
+        else project_bwd_kernel<true, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);
+    } else {
+        if (raw_mode) project_bwd_kernel<false, true><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);
+        else project_bwd_kernel<false, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);
+    }
+#undef B200GS_PB_ARGS
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }

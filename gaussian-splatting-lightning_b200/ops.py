@@ -310,6 +310,97 @@ def rasterize_vanilla(means3D, means2D, shs, colors_precomp, opacities, scales, 
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# vanilla, activations fused: the same node fed with the model's RAW parameter tensors (b200gs_project_*_raw)
+# ----------------------------------------------------------------------------------------------------------------------
+def project_forward_raw(view: B200gsView, means, log_scales, raw_quats, opac_logits, shs_dc, shs_rest, anti_aliased=False,
+                        want_comp=False):
+    L = lib()
+    n = means.shape[0]
+    dev = means.device
+    xy = torch.empty(n, 2, dtype=torch.float32, device=dev)
+    depth = torch.empty(n, dtype=torch.float32, device=dev)
+    radii = torch.empty(n, dtype=torch.int32, device=dev)
+    conic = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    tiles = torch.empty(n, dtype=torch.int32, device=dev)
+    comp = torch.empty(n, dtype=torch.float32, device=dev) if want_comp else None
+    rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    clamped = torch.empty(n, dtype=torch.uint8, device=dev)
+    opac = torch.empty(n, dtype=torch.float32, device=dev)
+    with _stage("project_fwd"):
+        check(L.b200gs_project_fwd_raw(ctypes.byref(view), n, ptr(means), ptr(log_scales), ptr(raw_quats), ptr(opac_logits),
+                                       ptr(shs_dc), ptr(shs_rest), int(bool(anti_aliased)), ptr(xy), ptr(depth), ptr(radii),
+                                       ptr(conic), ptr(comp), ptr(tiles), ptr(rgb), ptr(clamped), ptr(opac), _stream()),
+              "b200gs_project_fwd_raw")
+    return xy, depth, radii, conic, comp, tiles, rgb, clamped, opac
+
+
+def project_backward_raw(view: B200gsView, means, log_scales, raw_quats, opac_logits, shs_dc, shs_rest, anti_aliased, radii,
+                         clamped, v_xy, v_depth, v_conic, v_rgb, v_opac):
+    L = lib()
+    n = means.shape[0]
+    dev = means.device
+    v_means = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    v_ls = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    v_q = torch.empty(n, 4, dtype=torch.float32, device=dev)
+    v_ol = torch.empty(n, dtype=torch.float32, device=dev)
+    v_dc = torch.empty_like(shs_dc)
+    v_rest = torch.empty_like(shs_rest)
+    with _stage("project_bwd"):
+        check(L.b200gs_project_bwd_raw(ctypes.byref(view), n, ptr(means), ptr(log_scales), ptr(raw_quats), ptr(opac_logits),
+                                       ptr(shs_dc), ptr(shs_rest), int(bool(anti_aliased)), ptr(radii), ptr(clamped), ptr(v_xy),
+                                       ptr(v_depth), ptr(v_conic), ptr(v_rgb), ptr(v_opac), ptr(v_means), ptr(v_ls), ptr(v_q),
+                                       ptr(v_ol), ptr(v_dc), ptr(v_rest), _stream()), "b200gs_project_bwd_raw")
+    return v_means, v_ls, v_q, v_ol, v_dc, v_rest
+
+
+class _RasterizeVanillaRaw(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, shs_dc, shs_rest, opacity_logits, log_scales, raw_quats, bg, view: B200gsView):
+        means3D = _f32c(means3D, "means3D")
+        log_scales = _f32c(log_scales, "scales")
+        raw_quats = _f32c(raw_quats, "rotations")
+        ol = _f32c(opacity_logits, "opacities").reshape(-1)
+        shs_dc = _f32c(shs_dc, "shs_dc")
+        shs_rest = _f32c(shs_rest, "shs_rest")
+        bg = _f32c(bg, "bg")
+        view = _copy_view(view, sh_stride=int(shs_dc.shape[1] + shs_rest.shape[1]))
+        W, H = view.width, view.height
+        xy, depth, radii, conic, _, tiles, rgb, clamped, opac = project_forward_raw(view, means3D, log_scales, raw_quats, ol, shs_dc,
+                                                                                    shs_rest)
+        binning = bin_gaussians(MODE_VANILLA, W, H, xy, depth, radii, conic, opac)
+        image, final_T, n_contrib, _ = blend_forward(MODE_VANILLA, W, H, binning, xy, conic, opac, rgb, bg, True, False)
+        ctx.view = view
+        ctx.binning = binning
+        ctx.means2D_shape = tuple(means2D.shape)
+        ctx.opac_shape = tuple(opacity_logits.shape)
+        ctx.save_for_backward(means3D, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, xy, conic, radii, clamped, rgb, opac,
+                              final_T, n_contrib)
+        ctx.mark_non_differentiable(radii)
+        return image, radii
+
+    @staticmethod
+    def backward(ctx, v_image, _v_radii):
+        (means3D, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, xy, conic, radii, clamped, rgb, opac, final_T,
+         n_contrib) = ctx.saved_tensors
+        view = ctx.view
+        W, H = view.width, view.height
+        v_image = _f32c(v_image, "grad_image")
+        v_xy, v_conic, v_opacity, v_colors, _ = blend_backward(MODE_VANILLA, W, H, ctx.binning, xy, conic, opac, rgb, bg, final_T,
+                                                              n_contrib, v_image, None, True, (0.5 * W, 0.5 * H))
+        v_means, v_ls, v_q, v_ol, v_dc, v_rest = project_backward_raw(view, means3D, log_scales, raw_quats, ol, shs_dc, shs_rest,
+                                                                     False, radii, clamped, v_xy, None, v_conic, v_colors, v_opacity)
+        v_means2D = torch.zeros(ctx.means2D_shape, dtype=torch.float32, device=means3D.device)
+        v_means2D[:, :2] = v_xy
+        return v_means, v_means2D, v_dc, v_rest, v_ol.reshape(ctx.opac_shape), v_ls, v_q, None, None
+
+
+def rasterize_vanilla_raw(means3D, means2D, shs_dc, shs_rest, opacity_logits, log_scales, raw_quats, bg, view: B200gsView):
+    """Fused-activation variant of rasterize_vanilla: inputs are the model's RAW parameters
+    (means, shs_dc [N,1,3], shs_rest [N,K-1,3], opacity logits, log-scales, un-normalised quaternions)."""
+    return _RasterizeVanillaRaw.apply(means3D, means2D, shs_dc, shs_rest, opacity_logits, log_scales, raw_quats, bg, view)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # gsplat v0 surface
 # ----------------------------------------------------------------------------------------------------------------------
 class _ProjectGaussians(torch.autograd.Function):

@@ -111,17 +111,40 @@ def _view_with(view, **kw):
     return ops._copy_view(view, **kw)
 
 
+_FUSABLE_MODELS = ("VanillaGaussianModel", "SyntheticGaussians")
+_RAW_KEYS = ("means", "scales", "rotations", "opacities", "shs_dc", "shs_rest")
+
+
+def _raw_parameters(pc):
+    """The raw parameter tensors of a vanilla Gaussian model, or None when the model is anything else (a subclass may
+    override an activation, e.g. mip-splatting's filtered scales/opacities: those must go through the getters)."""
+    if type(pc).__name__ not in _FUSABLE_MODELS:
+        return None
+    params = getattr(pc, "gaussians", None)
+    if params is None or any(k not in params for k in _RAW_KEYS):
+        return None
+    raw = {k: params[k] for k in _RAW_KEYS}
+    if raw["shs_rest"].shape[1] == 0 or raw["opacities"].dim() != 2:
+        return None
+    return raw
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # vanilla
 # ----------------------------------------------------------------------------------------------------------------------
 class B200VanillaRenderer(Renderer):
-    def __init__(self, compute_cov3D_python: bool = False, convert_SHs_python: bool = False, cache_cameras: bool = True):
+    def __init__(self, compute_cov3D_python: bool = False, convert_SHs_python: bool = False, cache_cameras: bool = True,
+                 fused_activations: bool = True):
+        """fused_activations: when the model is the vanilla Gaussian model (raw ``means / scales / rotations / opacities /
+        shs_dc / shs_rest`` parameters with exp / normalize / sigmoid activations, vanilla_gaussian.py:345-358), feed the
+        RAW parameters to the kernels and apply the activations there.  Any other model goes through its getters."""
         super().__init__()
         if compute_cov3D_python:
             raise NotImplementedError("b200gs computes cov3D in the projection kernel; compute_cov3D_python is unsupported")
         self.compute_cov3D_python = compute_cov3D_python
         self.convert_SHs_python = convert_SHs_python
         self.cache_cameras = cache_cameras
+        self.fused_activations = fused_activations
 
     def forward(self, viewpoint_camera, pc, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
                 render_types: list = None, **kwargs):
@@ -135,6 +158,20 @@ class B200VanillaRenderer(Renderer):
             depth = (torch.matmul(pc.get_xyz, w2c[:3, :3]) + w2c[3, :3])[:, 2:]
             bg_color = torch.zeros_like(bg_color)
             override_color = depth.repeat(1, 3)
+        raw = _raw_parameters(pc) if (self.fused_activations and override_color is None) else None
+        if raw is not None:
+            # fused path: exp / sigmoid / normalize / cat run inside K1 and K8 on the raw parameter tensors
+            screenspace_points = torch.zeros_like(raw["means"], requires_grad=True) + 0
+            view = camera_view(viewpoint_camera, MODE_VANILLA, self.cache_cameras)
+            view = _view_with(view, sh_degree=int(pc.active_sh_degree), scale_modifier=float(scaling_modifier))
+            image, radii = ops.rasterize_vanilla_raw(raw["means"], screenspace_points, raw["shs_dc"], raw["shs_rest"],
+                                                     raw["opacities"], raw["scales"], raw["rotations"], bg_color, view)
+            return {
+                rendered_image_key: image,
+                "viewspace_points": screenspace_points,
+                "visibility_filter": radii > 0,
+                "radii": radii,
+            }
         out = self.render(pc.get_xyz, pc.get_opacity, pc.get_scaling, pc.get_rotation,
                           pc.get_features if override_color is None else None, pc.active_sh_degree, viewpoint_camera,
                           bg_color, scaling_modifier, colors_precomp=override_color, cache_cameras=self.cache_cameras)

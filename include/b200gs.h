@@ -98,6 +98,26 @@ B200GS_API int b200gs_project_bwd(const B200gsView* view, int64_t n, const float
                        const float* v_depth, const float* v_conic, const float* v_comp, const float* v_rgb,
                        float* v_means, float* v_scales, float* v_quats, float* v_shs, void* stream);
 
+/* ---- K1 / K8 with the model's activations fused ("raw parameter" fast path) -------------------------------------------
+ * Same kernels, reading the RAW parameter tensors of VanillaGaussianModel (internal/models/vanilla_gaussian.py:66,345-358;
+ * internal/models/gaussian.py:250-254) instead of its getters: scales = exp(log_scales), quats = normalize(raw_quats),
+ * opacity = sigmoid(opacity_logits) (all evaluated inside the kernel, the geometry part in fp64), SH = shs_dc[n,1,3] |
+ * shs_rest[n,sh_stride-1,3] read in place (no torch.cat).  Removes 5 elementwise kernels + the 192 B/Gaussian
+ * concatenation and their autograd backward from every training step.
+ * fwd extra out: opacity_out[n] = the opacity the blend kernels consume (x compensation in gsplat mode when
+ *     anti_aliased != 0; gsplat_renderer.py:81-83).
+ * bwd extra in : v_opacity[n] = dL/d(opacity_out) from b200gs_blend_bwd; outputs are gradients w.r.t. the RAW tensors. */
+B200GS_API int b200gs_project_fwd_raw(const B200gsView* view, int64_t n, const float* means, const float* log_scales,
+                           const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
+                           int32_t anti_aliased, float* xy, float* depth, int32_t* radii, float* conic, float* comp,
+                           int32_t* tiles, float* rgb, uint8_t* clamped, float* opacity_out, void* stream);
+B200GS_API int b200gs_project_bwd_raw(const B200gsView* view, int64_t n, const float* means, const float* log_scales,
+                           const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
+                           int32_t anti_aliased, const int32_t* radii, const uint8_t* clamped, const float* v_xy,
+                           const float* v_depth, const float* v_conic, const float* v_rgb, const float* v_opacity, float* v_means,
+                           float* v_log_scales, float* v_raw_quats, float* v_opacity_logits, float* v_shs_dc, float* v_shs_rest,
+                           void* stream);
+
 /* ---- standalone SH (gsplat.sh.spherical_harmonics; gsplat_renderer.py:105) -------------------------------------------
  * dirs[n,3] need not be unit (normalised inside, as gsplat does).  out rgb[n,3] = SH (no +0.5, no clamp).
  * bwd: v_coeffs[n,sh_stride,3] fully written; v_dirs[n,3] nullable. */

@@ -314,6 +314,38 @@ def test_renderer_end_to_end(mode, n, W, H, seed, pose, ms):
     assert set(out2.keys()) >= {"render", "viewspace_points", "visibility_filter", "radii"}
 
 
+@pytest.mark.parametrize("n,W,H,seed,pose,ms", CASES[:3])
+def test_fused_activation_path(n, W, H, seed, pose, ms):
+    """B200VanillaRenderer with the activations folded into K1/K8 (raw parameters in) against the float64 oracle fed
+    with torch's own activations of the same raw parameters: image 1e-4, raw-parameter gradients 1e-3."""
+    from b200gs.renderers import B200VanillaRenderer
+    raw, model, cam = _model_and_cam(n, W, H, seed, pose, ms)
+    bg = torch.tensor([0.3, 0.1, 0.7])
+    cot = torch.rand(3, H, W, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    rp = {k: v.double().requires_grad_(True) for k, v in raw.items()}
+    out_ref = O.render(O.MODE_VANILLA, rp["means"], torch.exp(rp["scales"]), torch.nn.functional.normalize(rp["rotations"]),
+                       torch.sigmoid(rp["opacities"]), torch.cat((rp["shs_dc"], rp["shs_rest"]), dim=1), _oview(cam), bg.double())
+    (out_ref["render"] * cot.double()).sum().backward()
+    cam_d = cam.to_device(DEV)
+    fused = B200VanillaRenderer(fused_activations=True).to(DEV)
+    out = fused(cam_d, model, bg.to(DEV))
+    out["viewspace_points"].retain_grad()
+    (out["render"] * cot.to(DEV)).sum().backward()
+    _assert_pixels(out["render"], out_ref["render"], "fused render")
+    for k in rp:
+        assert _rel(model.gaussians[k].grad, rp[k].grad) < 1e-3, k
+    assert _rel(out["viewspace_points"].grad[:, :2], O.viewspace_grad(O.MODE_VANILLA, out_ref["xy"].grad, W, H)) < 1e-3
+    # and the unfused plug-in path gives the same picture
+    g_fused = {k: p.grad.clone() for k, p in model.gaussians.items()}
+    for p_ in model.parameters():
+        p_.grad = None
+    out_u = B200VanillaRenderer(fused_activations=False).to(DEV)(cam_d, model, bg.to(DEV))
+    (out_u["render"] * cot.to(DEV)).sum().backward()
+    assert float((out_u["render"] - out["render"]).abs().max()) < 2e-4
+    for k in g_fused:
+        assert _rel(model.gaussians[k].grad, g_fused[k]) < 2e-3, k
+
+
 def test_edge_cases():
     """empty scene, everything behind the camera, one huge splat covering all tiles, opaque stack, sh degrees 0..3."""
     from b200gs.renderers import B200VanillaRenderer, B200GSplatRenderer
