@@ -282,6 +282,8 @@ def main():
         xy, depth, radii, conic, comp, tiles, _, _, _ = ops.project_forward(view, model.get_xyz.detach(), model.get_scaling.detach().contiguous(),
                                                                             model.get_rotation.detach().contiguous(), None, True)
         I = int(tiles.sum())
+        opac_act = model.get_opacity.detach().reshape(-1).contiguous() * (comp if args.mode == "gsplat" else 1.0)
+        I_culled = ops.bin_gaussians(mode_id, W, H, xy, depth, radii, conic, opac_act.contiguous()).total
     P = W * H
     hbm_peak, peak_src = peaks()
     kernels = {}
@@ -305,7 +307,7 @@ def main():
                      "traffic": None, "peak_source": peak_src,
                      "note": "blend kernels are SM-issue (FP32+MUFU) bound, not HBM bound (SURVEY §8d); HBM fraction reported as asked"},
         "kernels": kernels,
-        "scene": {"N": N, "V": V, "I": I, "P": P, "stage_sum_ms": round(sum(stage_ms.values()), 4)},
+        "scene": {"N": N, "V": V, "I": I, "I_after_exact_culling": I_culled, "P": P, "stage_sum_ms": round(sum(stage_ms.values()), 4)},
     }
     if not args.no_cpu_baseline and world == 1:
         vps, med, cores = cpu_projection_views_per_sec(N, W, H, args.mode, args.cpu_sample_iters)

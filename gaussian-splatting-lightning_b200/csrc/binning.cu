@@ -137,7 +137,7 @@ __device__ __forceinline__ CullParams load_cull(const float2 p, const float* __r
     return c;
 }
 
-constexpr int SMALL_RECT = 16;
+constexpr int SMALL_RECT = 48;
 
 // Shared walk over the rect of one Gaussian per lane (small rects serially, large ones warp-cooperatively).
 // COUNT: returns the number of kept tiles.  EMIT: writes (tile id, g) pairs from `start`.
