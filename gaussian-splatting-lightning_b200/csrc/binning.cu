@@ -88,102 +88,120 @@ LayoutB make_layout_b(int64_t max_pairs) {
 
 // ---- exact tile culling ------------------------------------------------------------------------------------------------
 // A (tile, splat) pair can only contribute if some pixel sample p of the tile has alpha = o * exp(-q(p - mu)) >= 1/255,
-// q(d) = (A dx^2 + C dy^2)/2 + B dx dy.  q is convex, so its minimum over the tile's box of pixel samples is 0 when mu is
-// inside the box and otherwise lies on one of the four edges (a clamped 1-D quadratic each).  Pairs with
-// q_min > ln(255 o) (+ a safety margin for fp32 rounding) are dropped: every pixel of the tile would have skipped that
-// splat in the blend loop anyway, so images and gradients are bit-identical, while the pair list (sort, staging, blend
-// evaluations) shrinks ~2x.  Round-to-nearest intrinsics pin the arithmetic so that the counting and the emitting
-// kernels agree on every pair.
-struct CullParams {
-    float mx, my, A, B, C, thresh;  // thresh < 0: drop everything; cull disabled when A is NaN-free and thresh = +inf
+// q(d) = (A dx^2 + C dy^2)/2 + B dx dy, i.e. if the tile's box of pixel samples meets the ellipse E = {q <= ln(255 o)}.
+// E and a tile ROW (a band of 16 sample rows) are convex, so the tiles of that row that meet E are exactly those whose
+// sample columns meet the x-extent of (E ∩ band): one interval per row, from two clamped evaluations of the ellipse's
+// left/right boundary.  Cost O(rows) per Gaussian instead of O(tiles); every pair dropped would have been skipped by
+// the blend loop at all 256 pixels, so images and gradients are bit-identical while the pair list (sort, staging,
+// blend evaluations) shrinks ~1.8x on the benchmark scene.  The threshold carries a margin for the fp32 / ex2.approx
+// rounding of the blend loop, the interval a 0.01 px slack; round-to-nearest intrinsics pin the arithmetic so that the
+// counting and the emitting kernel agree on every pair.
+struct CullE {
+    float mx, my, A, B, iA, two_tA, det, ymax, yR;
+    int mode;  // 0: full rect (culling off / degenerate conic), 1: spans, 2: nothing visible (opacity <= 1/255)
 };
 
+__device__ __forceinline__ CullE load_cull(const float2 p, const float* __restrict__ conic, const float* __restrict__ opacity, int64_t g) {
+    CullE e;
+    e.mx = p.x; e.my = p.y;
+    e.A = 1.f; e.B = 0.f; e.iA = 1.f; e.two_tA = 0.f; e.det = 1.f; e.ymax = 0.f; e.yR = 0.f;
+    e.mode = 0;
+    if (conic == nullptr) return e;
+    const float A = __ldg(conic + 3 * g), B = __ldg(conic + 3 * g + 1), C = __ldg(conic + 3 * g + 2);
+    const float o255 = 255.0f * __ldg(opacity + g);
+    if (o255 <= 1.0f) { e.mode = 2; return e; }
+    // alpha >= 1/255  <=>  q <= ln(255 o); margin covers the fp32 / ex2.approx rounding of the blend loop
+    const float t = __fmaf_rn(__logf(o255), 1.0001f, 1e-3f);
+    const float det = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, B));
+    if (!(det > 0.f) || !(A > 0.f) || !(C > 0.f) || !(t < 3.0e38f)) return e;  // degenerate / NaN: keep the full rect
+    const float idet = __frcp_rn(det);
+    e.A = A; e.B = B; e.iA = __frcp_rn(A);
+    e.two_tA = __fmul_rn(__fmul_rn(2.0f, t), A);
+    e.det = det;
+    e.ymax = __fsqrt_rn(__fmul_rn(e.two_tA, idet));
+    const float xext = __fsqrt_rn(__fmul_rn(__fmul_rn(__fmul_rn(2.0f, t), C), idet));
+    e.yR = __fmul_rn(__fmul_rn(-B, xext), __frcp_rn(C));  // the ellipse's rightmost point sits at y = yR, leftmost at -yR
+    e.mode = 1;
+    return e;
+}
+
+// tiles [a, b) of tile row ty (clipped to [x0, x1)) whose pixel samples can meet the ellipse
 template <bool GSPLAT>
-__device__ __forceinline__ bool tile_hit(const CullParams& c, int tx, int ty) {
-    if (!(c.thresh < 3.0e38f)) return true;  // culling disabled
+__device__ __forceinline__ bool row_span(const CullE& e, int ty, int x0, int x1, int& a, int& b) {
+    a = x0; b = x1;
+    if (e.mode == 0) return true;
     const float off = GSPLAT ? 0.5f : 0.0f;
-    const float X0 = __fsub_rn(__fadd_rn(float(tx * TILE), off), c.mx), X1 = __fadd_rn(X0, float(TILE - 1));
-    const float Y0 = __fsub_rn(__fadd_rn(float(ty * TILE), off), c.my), Y1 = __fadd_rn(Y0, float(TILE - 1));
-    if (X0 <= 0.f && X1 >= 0.f && Y0 <= 0.f && Y1 >= 0.f) return true;
-    const float iA = __frcp_rn(c.A), iC = __frcp_rn(c.C);
-    float qmin = 3.0e38f;
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        const float Xe = e ? X1 : X0;
-        const float bx = __fmul_rn(c.B, Xe);
-        const float ys = fminf(Y1, fmaxf(Y0, __fmul_rn(-bx, iC)));
-        const float q1 = __fmaf_rn(ys, __fmaf_rn(__fmul_rn(0.5f, c.C), ys, bx), __fmul_rn(__fmul_rn(0.5f, c.A), __fmul_rn(Xe, Xe)));
-        const float Ye = e ? Y1 : Y0;
-        const float by = __fmul_rn(c.B, Ye);
-        const float xs = fminf(X1, fmaxf(X0, __fmul_rn(-by, iA)));
-        const float q2 = __fmaf_rn(xs, __fmaf_rn(__fmul_rn(0.5f, c.A), xs, by), __fmul_rn(__fmul_rn(0.5f, c.C), __fmul_rn(Ye, Ye)));
-        qmin = fminf(qmin, fminf(q1, q2));
+    const float Y0 = __fsub_rn(__fadd_rn(float(ty * TILE), off), e.my);
+    const float ya = fmaxf(Y0, -e.ymax), yb = fminf(__fadd_rn(Y0, float(TILE - 1)), e.ymax);
+    if (ya > yb) { b = a; return false; }
+    const float yr = fminf(yb, fmaxf(ya, e.yR)), yl = fminf(yb, fmaxf(ya, -e.yR));
+    const float dr = __fsqrt_rn(fmaxf(0.f, __fmaf_rn(-e.det, __fmul_rn(yr, yr), e.two_tA)));
+    const float dl = __fsqrt_rn(fmaxf(0.f, __fmaf_rn(-e.det, __fmul_rn(yl, yl), e.two_tA)));
+    const float xr = __fmul_rn(__fadd_rn(__fmul_rn(-e.B, yr), dr), e.iA);   // right end of E ∩ band (relative to mu)
+    const float xl = __fmul_rn(__fsub_rn(__fmul_rn(-e.B, yl), dl), e.iA);   // left end
+    // tile tx holds sample columns [16 tx + off, 16 tx + off + 15]
+    const float inv = 1.0f / float(TILE);
+    const float fa = ceilf(__fmul_rn(__fsub_rn(__fadd_rn(xl, e.mx), off + float(TILE - 1) + 0.01f), inv));
+    const float fb = floorf(__fmul_rn(__fadd_rn(__fsub_rn(__fadd_rn(xr, e.mx), off), 0.01f), inv));
+    if (!(fa <= fb)) {  // also catches NaN
+        if (fa == fa && fb == fb) { b = a; return false; }
+        return true;    // NaN: keep the whole row
     }
-    return !(qmin > c.thresh);  // NaN -> keep
+    a = max(x0, (int)fmaxf(fa, -1.0e9f));
+    b = min(x1, (int)fminf(fb, 1.0e9f) + 1);
+    if (a >= b) { b = a; return false; }
+    return true;
 }
 
-__device__ __forceinline__ CullParams load_cull(const float2 p, const float* __restrict__ conic, const float* __restrict__ opacity, int64_t g) {
-    CullParams c;
-    c.mx = p.x; c.my = p.y;
-    c.A = 1.f; c.B = 0.f; c.C = 1.f;
-    c.thresh = 3.4e38f;
-    if (conic != nullptr) {
-        c.A = __ldg(conic + 3 * g); c.B = __ldg(conic + 3 * g + 1); c.C = __ldg(conic + 3 * g + 2);
-        const float o255 = 255.0f * __ldg(opacity + g);
-        // alpha >= 1/255  <=>  q <= ln(255 o); margin covers the fp32 / ex2.approx rounding of the blend loop
-        c.thresh = (o255 > 1.0f) ? __fmaf_rn(__logf(o255), 1.0001f, 1e-3f) : -1.0f;
-        if (!(o255 > 1.0f) && !(o255 <= 1.0f)) c.thresh = 3.4e38f;  // NaN opacity: keep
-    }
-    return c;
-}
+constexpr int BIG_RECT = 512;   // Gaussians covering more tiles than this are walked by the whole warp
 
-constexpr int SMALL_RECT = 48;
-
-// Shared walk over the rect of one Gaussian per lane (small rects serially, large ones warp-cooperatively).
-// COUNT: returns the number of kept tiles.  EMIT: writes (tile id, g) pairs from `start`.
+// Shared walk over the rect of one Gaussian per lane.  EMIT=false: returns the number of kept tiles.
+// EMIT=true: writes (tile id, g) pairs from `start`, row-major like the reference's emission order.
 template <bool GSPLAT, bool EMIT>
-__device__ __forceinline__ int walk_rect(unsigned lane, bool active, int g, const CullParams& c, int x0, int y0, int x1, int y1,
+__device__ __forceinline__ int walk_rect(unsigned lane, bool active, int g, const CullE& e, int x0, int y0, int x1, int y1,
                                          int grid_x, int64_t start, int64_t max_pairs, uint32_t* __restrict__ pkeys,
                                          int32_t* __restrict__ pvals) {
-    const int w = x1 - x0;
-    const int t_rect = active ? w * (y1 - y0) : 0;
+    const int t_rect = active ? (x1 - x0) * (y1 - y0) : 0;
+    const bool none = (e.mode == 2);
     int kept = 0;
-    if (t_rect > 0 && t_rect <= SMALL_RECT) {
-        for (int k = 0; k < t_rect; ++k) {
-            const int ty = y0 + k / w, tx = x0 + k % w;
-            if (tile_hit<GSPLAT>(c, tx, ty)) {
-                if (EMIT) {
-                    const int64_t o = start + kept;
+    if (t_rect > 0 && t_rect <= BIG_RECT && !none) {
+        for (int ty = y0; ty < y1; ++ty) {
+            int a, b;
+            if (!row_span<GSPLAT>(e, ty, x0, x1, a, b)) continue;
+            if (EMIT) {
+                for (int tx = a; tx < b; ++tx) {
+                    const int64_t o = start + kept + (tx - a);
                     if (o < max_pairs) { pkeys[o] = (uint32_t)(ty * grid_x + tx); pvals[o] = g; }
                 }
-                ++kept;
             }
+            kept += b - a;
         }
     }
-    unsigned big = __ballot_sync(0xffffffffu, t_rect > SMALL_RECT);
+    unsigned big = __ballot_sync(0xffffffffu, t_rect > BIG_RECT && !none);
     while (big) {
         const int src = __ffs(big) - 1;
         big &= big - 1;
-        CullParams bc;
-        bc.mx = __shfl_sync(0xffffffffu, c.mx, src); bc.my = __shfl_sync(0xffffffffu, c.my, src);
-        bc.A = __shfl_sync(0xffffffffu, c.A, src); bc.B = __shfl_sync(0xffffffffu, c.B, src);
-        bc.C = __shfl_sync(0xffffffffu, c.C, src); bc.thresh = __shfl_sync(0xffffffffu, c.thresh, src);
+        CullE be;
+        be.mx = __shfl_sync(0xffffffffu, e.mx, src); be.my = __shfl_sync(0xffffffffu, e.my, src);
+        be.A = __shfl_sync(0xffffffffu, e.A, src); be.B = __shfl_sync(0xffffffffu, e.B, src);
+        be.iA = __shfl_sync(0xffffffffu, e.iA, src); be.two_tA = __shfl_sync(0xffffffffu, e.two_tA, src);
+        be.det = __shfl_sync(0xffffffffu, e.det, src); be.ymax = __shfl_sync(0xffffffffu, e.ymax, src);
+        be.yR = __shfl_sync(0xffffffffu, e.yR, src); be.mode = __shfl_sync(0xffffffffu, e.mode, src);
         const int bg = __shfl_sync(0xffffffffu, g, src);
-        const int bt = __shfl_sync(0xffffffffu, t_rect, src);
         const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-        const int bw = __shfl_sync(0xffffffffu, w, src);
+        const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
         const int64_t bstart = __shfl_sync(0xffffffffu, start, src);
         int bkept = 0;
-        for (int k0 = 0; k0 < bt; k0 += 32) {
-            const int k = k0 + (int)lane;
-            const int ty = by0 + k / bw, tx = bx0 + k % bw;
-            const bool hit = (k < bt) && tile_hit<GSPLAT>(bc, tx, ty);
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (EMIT && hit) {
-                const int64_t o = bstart + bkept + __popc(m & ((1u << lane) - 1u));
-                if (o < max_pairs) { pkeys[o] = (uint32_t)(ty * grid_x + tx); pvals[o] = bg; }
+        for (int ty = by0; ty < by1; ++ty) {
+            int a, b;
+            if (!row_span<GSPLAT>(be, ty, bx0, bx1, a, b)) continue;
+            if (EMIT) {
+                for (int tx = a + (int)lane; tx < b; tx += 32) {
+                    const int64_t o = bstart + bkept + (tx - a);
+                    if (o < max_pairs) { pkeys[o] = (uint32_t)(ty * grid_x + tx); pvals[o] = bg; }
+                }
             }
-            bkept += __popc(m);
+            bkept += b - a;
         }
         if ((int)lane == src) kept = bkept;
     }
@@ -200,17 +218,17 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
     const unsigned lane = threadIdx.x & 31u;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     bool active = false;
-    CullParams c{};
+    CullE e{};
     if (i < n) {
         const int r = radii[i];
         if (r > 0) {
             const float2 p = xy[i];
             tile_rect<GSPLAT>(p.x, p.y, (float)r, grid_x, grid_y, x0, y0, x1, y1);
-            c = load_cull(p, conic, opacity, i);
+            e = load_cull(p, conic, opacity, i);
             active = (x1 - x0) * (y1 - y0) > 0;
         }
     }
-    const int t = walk_rect<GSPLAT, false>(lane, active, (int)i, c, x0, y0, x1, y1, grid_x, 0, 0, nullptr, nullptr);
+    const int t = walk_rect<GSPLAT, false>(lane, active, (int)i, e, x0, y0, x1, y1, grid_x, 0, 0, nullptr, nullptr);
     if (i < n) {
         keys[i] = t > 0 ? __float_as_uint(depth[i]) : 0xFFFFFFFFu;
         ids[i] = (int32_t)i;
@@ -222,7 +240,7 @@ __global__ void write_total_kernel(int64_t n, const int64_t* __restrict__ offset
     *d_total = n > 0 ? offsets[n - 1] : 0;
 }
 
-// One lane per depth-ranked Gaussian; Gaussians with many tiles are written by the whole warp.
+// One lane per depth-ranked Gaussian; Gaussians with very large rects are written by the whole warp.
 template <bool GSPLAT>
 __global__ void __launch_bounds__(256) emit_pairs_kernel(int64_t n, int grid_x, int grid_y, int64_t max_pairs,
                                                          const float2* __restrict__ xy, const int32_t* __restrict__ radii,
@@ -235,19 +253,19 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(int64_t n, int grid_x, 
     int g = -1, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     int64_t start = 0;
     bool active = false;
-    CullParams c{};
+    CullE e{};
     if (rnk < n) {
         g = order[rnk];
         const int t = tiles[g];
         if (t > 0) {
             const float2 p = xy[g];
             tile_rect<GSPLAT>(p.x, p.y, (float)radii[g], grid_x, grid_y, x0, y0, x1, y1);
-            c = load_cull(p, conic, opacity, g);
+            e = load_cull(p, conic, opacity, g);
             start = offsets[rnk] - t;
             active = true;
         }
     }
-    walk_rect<GSPLAT, true>(lane, active, g, c, x0, y0, x1, y1, grid_x, start, max_pairs, pkeys, pvals);
+    walk_rect<GSPLAT, true>(lane, active, g, e, x0, y0, x1, y1, grid_x, start, max_pairs, pkeys, pvals);
 }
 
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t total, const uint32_t* __restrict__ keys, int2* __restrict__ ranges) {

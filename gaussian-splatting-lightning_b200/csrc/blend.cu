@@ -410,7 +410,7 @@ int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
 }
 
 #ifndef B200GS_BWD_RB
-#define B200GS_BWD_RB 8
+#define B200GS_BWD_RB 4
 #endif
 
 template <int CH>
