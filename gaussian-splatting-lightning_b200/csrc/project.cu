@@ -339,8 +339,10 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int BWD_THREADS = 128;
+
 template <bool GSPLAT, bool RAW>
-__global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
+__global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
                                                           const float* __restrict__ means, const float* __restrict__ scales,
                                                           const float* __restrict__ quats, const float* __restrict__ shs,
                                                           const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
@@ -349,37 +351,18 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant_
                                                           const float* __restrict__ v_rgb, float* __restrict__ v_means,
                                                           float* __restrict__ v_scales, float4* __restrict__ v_quats,
                                                           float* __restrict__ v_shs) {
+    // SH-gradient rows are staged per warp in shared memory (odd row stride: conflict-free) and written back with
+    // fully coalesced 128-bit stores: every row must be written (zeros for culled Gaussians), so the warp's 32 rows are
+    // one contiguous 5.6-6 KB span of the output.
+    __shared__ float s_rows[BWD_THREADS / 32][32 * 49];
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const int warp = threadIdx.x >> 5;
+    const bool in_range = i < n;
+    const bool vis = in_range && (radii[i] > 0);
     const int stride3 = v.sh_stride * 3;
-    const bool vec4 = (stride3 & 3) == 0;
-    if (radii[i] <= 0) {
-        v_means[3 * i] = 0.f; v_means[3 * i + 1] = 0.f; v_means[3 * i + 2] = 0.f;
-        v_scales[3 * i] = 0.f; v_scales[3 * i + 1] = 0.f; v_scales[3 * i + 2] = 0.f;
-        v_quats[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (v_shs) {
-            if (RAW) {
-                v_shs[3 * i] = 0.f; v_shs[3 * i + 1] = 0.f; v_shs[3 * i + 2] = 0.f;
-                float* o = raw.v_shs_rest + i * int64_t(stride3 - 3);
-                for (int k = 0; k < stride3 - 3; ++k) o[k] = 0.f;
-            } else {
-                float* o = v_shs + i * int64_t(stride3);
-                if (vec4) {
-                    for (int k = 0; k < stride3 / 4; ++k) reinterpret_cast<float4*>(o)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-                    for (int k = 0; k < stride3; ++k) o[k] = 0.f;
-                }
-            }
-        }
-        if (RAW) raw.v_opac_logit[i] = 0.f;
-        return;
-    }
-    const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
-    float sc[3], q[4], inv_qn;
-    load_scale_quat<RAW, float>(scales, quats, i, sc, q, &inv_qn);
-    Proj<float> g;
-    project_geometry<GSPLAT, float>(v, p, sc, q, g);
-    const float* V = v.viewmatrix;
+    float p[3] = {0.f, 0.f, 0.f};
+    if (vis) { p[0] = __ldg(means + 3 * i); p[1] = __ldg(means + 3 * i + 1); p[2] = __ldg(means + 3 * i + 2); }
 
     float dmx = 0.f, dmy = 0.f, dmz = 0.f;  // dL/dmean (world)
     float dtx = 0.f, dty = 0.f, dtz = 0.f;  // dL/dt (camera)
@@ -388,40 +371,65 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant_
     if (v_shs != nullptr) {
         const int deg = v.sh_degree;
         const int ncoef = (deg + 1) * (deg + 1);
-        const uint8_t cl = clamped[i];
-        const float gr = (cl & 1) ? 0.f : __ldg(v_rgb + 3 * i + 0);
-        const float gg = (cl & 2) ? 0.f : __ldg(v_rgb + 3 * i + 1);
-        const float gb = (cl & 4) ? 0.f : __ldg(v_rgb + 3 * i + 2);
-        float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
-        const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-        dx *= inv_len; dy *= inv_len; dz *= inv_len;
-        float bs[MAX_COEFFS];
-        sh_basis(deg, dx, dy, dz, bs);
+        float gr = 0.f, gg = 0.f, gb = 0.f, dx = 0.f, dy = 0.f, dz = 1.f, inv_len = 0.f;
         float out[MAX_COEFFS * 3];
 #pragma unroll
-        for (int k = 0; k < MAX_COEFFS; ++k) {
-            const float bk = (k < ncoef) ? bs[k] : 0.f;
-            out[3 * k + 0] = bk * gr; out[3 * k + 1] = bk * gg; out[3 * k + 2] = bk * gb;
-        }
-        if (RAW) {
-            v_shs[3 * i] = out[0]; v_shs[3 * i + 1] = out[1]; v_shs[3 * i + 2] = out[2];
-            float* o = raw.v_shs_rest + i * int64_t(stride3 - 3);
+        for (int k = 0; k < MAX_COEFFS * 3; ++k) out[k] = 0.f;
+        if (vis) {
+            const uint8_t cl = clamped[i];
+            gr = (cl & 1) ? 0.f : __ldg(v_rgb + 3 * i + 0);
+            gg = (cl & 2) ? 0.f : __ldg(v_rgb + 3 * i + 1);
+            gb = (cl & 4) ? 0.f : __ldg(v_rgb + 3 * i + 2);
+            dx = p[0] - v.campos[0]; dy = p[1] - v.campos[1]; dz = p[2] - v.campos[2];
+            inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            dx *= inv_len; dy *= inv_len; dz *= inv_len;
+            float bs[MAX_COEFFS];
+            sh_basis(deg, dx, dy, dz, bs);
 #pragma unroll
-            for (int k = 3; k < MAX_COEFFS * 3; ++k)
-                if (k < stride3) o[k - 3] = out[k];
-        } else {
-            float* o = v_shs + i * int64_t(stride3);
-            if (vec4) {
-                for (int k = 0; k < stride3 / 4; ++k) {
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (k * 4 < MAX_COEFFS * 3) t = make_float4(out[k * 4], out[k * 4 + 1], out[k * 4 + 2], out[k * 4 + 3]);
-                    reinterpret_cast<float4*>(o)[k] = t;
-                }
-            } else {
-                for (int k = 0; k < stride3; ++k) o[k] = (k < MAX_COEFFS * 3) ? out[k] : 0.f;
+            for (int k = 0; k < MAX_COEFFS; ++k) {
+                const float bk = (k < ncoef) ? bs[k] : 0.f;
+                out[3 * k + 0] = bk * gr; out[3 * k + 1] = bk * gg; out[3 * k + 2] = bk * gb;
             }
         }
-        if (!GSPLAT && deg > 0) {
+        const int rw = RAW ? stride3 - 3 : stride3;          // floats per output row
+        float* dst_base = RAW ? raw.v_shs_rest : v_shs;
+        if (RAW && in_range) { v_shs[3 * i] = out[0]; v_shs[3 * i + 1] = out[1]; v_shs[3 * i + 2] = out[2]; }
+        if (rw <= 48) {
+            const int rwp = rw | 1;
+            float* row = s_rows[warp] + lane * rwp;
+#pragma unroll
+            for (int k = 0; k < MAX_COEFFS * 3; ++k) {
+                const int c = RAW ? k - 3 : k;
+                if (c >= 0 && c < rw) row[c] = out[k];
+            }
+            __syncwarp();
+            const int64_t i0 = i - lane;
+            const int rows_valid = (i0 < n) ? (int)min((int64_t)32, n - i0) : 0;
+            const int total = rows_valid * rw;
+            float* dst = dst_base + i0 * rw;
+            const float* sw = s_rows[warp];
+            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                for (int idx = lane; idx * 4 + 3 < total; idx += 32) {
+                    int f = idx * 4, r = f / rw, c = f - r * rw;
+                    float t[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        t[e] = sw[r * rwp + c];
+                        if (++c == rw) { c = 0; ++r; }
+                    }
+                    reinterpret_cast<float4*>(dst)[idx] = make_float4(t[0], t[1], t[2], t[3]);
+                }
+                for (int f = (total & ~3) + lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw];
+            } else {
+                for (int f = lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw];
+            }
+        } else if (in_range) {  // wider coefficient storage than the kernel evaluates: plain per-thread rows
+            float* o = dst_base + i * int64_t(rw);
+#pragma unroll
+            for (int k = RAW ? 3 : 0; k < MAX_COEFFS * 3; ++k) o[RAW ? k - 3 : k] = out[k];
+            for (int c = MAX_COEFFS * 3 - (RAW ? 3 : 0); c < rw; ++c) o[c] = 0.f;
+        }
+        if (vis && !GSPLAT && deg > 0) {
             // view direction -> mean (dgr back-propagates it; gsplat renderers detach the direction)
             float sh[MAX_COEFFS * 3];
             load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
@@ -441,6 +449,19 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const __grid_constant_
             dmz += (ddz - dz * dot) * inv_len;
         }
     }
+    if (!in_range) return;
+    if (!vis) {
+        v_means[3 * i] = 0.f; v_means[3 * i + 1] = 0.f; v_means[3 * i + 2] = 0.f;
+        v_scales[3 * i] = 0.f; v_scales[3 * i + 1] = 0.f; v_scales[3 * i + 2] = 0.f;
+        v_quats[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (RAW) raw.v_opac_logit[i] = 0.f;
+        return;
+    }
+    float sc[3], q[4], inv_qn;
+    load_scale_quat<RAW, float>(scales, quats, i, sc, q, &inv_qn);
+    Proj<float> g;
+    project_geometry<GSPLAT, float>(v, p, sc, q, g);
+    const float* V = v.viewmatrix;
 
     // ---- conic (+ compensation) -> blurred cov2D (a, b, c) ----------------------------------------------------
     const float inv_det = 1.0f / g.det;
@@ -681,7 +702,7 @@ int launch_project_bwd_raw(const B200gsView& v, int64_t n, const float* means, c
                            float* v_scales, float* v_quats, float* v_opac_logit, float* v_shs_dc, float* v_shs_rest,
                            cudaStream_t s) {
     if (n == 0) return B200GS_OK;
-    const int threads = 256;
+    const int threads = BWD_THREADS;
     const unsigned blocks = (unsigned)div_up64(n, threads);
     const bool raw_mode = v_opac_logit != nullptr;
     RawIO raw{opac_logits, shs_rest, nullptr, v_opac, v_opac_logit, v_shs_rest, anti_aliased};
