@@ -132,7 +132,7 @@ size_t b200gs_bin_sort_workspace_bytes(int64_t n, int64_t max_pairs, int32_t wid
 
 int b200gs_bin_count(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const float* depth,
                      const int32_t* radii, const float* cull_conic, const float* cull_opacity, void* workspace,
-                     size_t workspace_bytes, int64_t* d_total, int64_t* host_total, void* stream) {
+                     size_t workspace_bytes, int64_t* d_total, int64_t* host_total, int32_t sync_host, void* stream) {
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
     B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0, "bad size");
     B200GS_CHECK_ARG(workspace && d_total, "workspace/d_total must not be NULL");
@@ -140,18 +140,19 @@ int b200gs_bin_count(int32_t mode, int32_t width, int32_t height, int64_t n, con
     B200GS_CHECK_ARG(n < (int64_t(1) << 31), "n >= 2^31");
     B200GS_CHECK_ARG((cull_conic == nullptr) == (cull_opacity == nullptr), "cull_conic and cull_opacity go together");
     return bin_count(mode, width, height, n, xy, depth, radii, cull_conic, cull_opacity, workspace, workspace_bytes, d_total,
-                     host_total, (cudaStream_t)stream);
+                     host_total, sync_host, (cudaStream_t)stream);
 }
 
 int b200gs_bin_sort(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const int32_t* radii,
-                    const float* cull_conic, const float* cull_opacity, int64_t total, int64_t max_pairs, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes,
+                    const float* cull_conic, const float* cull_opacity, int64_t total, const int64_t* d_total, int64_t max_pairs, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes,
                     int32_t* sorted_ids, int32_t* tile_ranges, void* stream) {
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
-    B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0 && total >= 0 && max_pairs >= 0, "bad size");
+    B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0 && max_pairs >= 0, "bad size");
+    B200GS_CHECK_ARG(d_total != nullptr, "d_total must not be NULL");
     B200GS_CHECK_ARG(workspace_a && workspace_b && tile_ranges, "workspace/tile_ranges must not be NULL");
     B200GS_CHECK_ARG(total == 0 || (xy && radii && sorted_ids), "NULL pointer");
     B200GS_CHECK_ARG((cull_conic == nullptr) == (cull_opacity == nullptr), "cull_conic and cull_opacity go together");
-    return bin_sort(mode, width, height, n, xy, radii, cull_conic, cull_opacity, total, max_pairs, workspace_a, workspace_b, workspace_b_bytes, sorted_ids,
+    return bin_sort(mode, width, height, n, xy, radii, cull_conic, cull_opacity, total, d_total, max_pairs, workspace_a, workspace_b, workspace_b_bytes, sorted_ids,
                     tile_ranges, (cudaStream_t)stream);
 }
 

@@ -50,6 +50,9 @@ struct Taker {
 };
 
 LayoutA make_layout_a(int64_t n) {
+    static thread_local int64_t cached_n = -1;
+    static thread_local LayoutA cached{};
+    if (n == cached_n) return cached;
     LayoutA L{};
     Taker take;
     const size_t nn = (size_t)(n > 0 ? n : 1);
@@ -67,10 +70,15 @@ LayoutA make_layout_a(int64_t n) {
     L.temp_bytes = t_sort > t_scan ? t_sort : t_scan;
     L.temp = take(L.temp_bytes);
     L.total = take.off;
+    cached = L;
+    cached_n = n;
     return L;
 }
 
 LayoutB make_layout_b(int64_t max_pairs) {
+    static thread_local int64_t cached_p = -1;
+    static thread_local LayoutB cached{};
+    if (max_pairs == cached_p) return cached;
     LayoutB L{};
     Taker take;
     const size_t pp = (size_t)(max_pairs > 0 ? max_pairs : 1);
@@ -83,6 +91,8 @@ LayoutB make_layout_b(int64_t max_pairs) {
     L.temp_bytes = t_psort;
     L.temp = take(t_psort);
     L.total = take.off;
+    cached = L;
+    cached_p = max_pairs;
     return L;
 }
 
@@ -268,8 +278,17 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(int64_t n, int grid_x, 
     walk_rect<GSPLAT, true>(lane, active, g, e, x0, y0, x1, y1, grid_x, start, max_pairs, pkeys, pvals);
 }
 
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t total, const uint32_t* __restrict__ keys, int2* __restrict__ ranges) {
+// capacity mode: entries [total, cap) of the key buffer get a key above every tile id so they sort to the end
+__global__ void __launch_bounds__(256) pad_keys_kernel(int64_t cap, const int64_t* __restrict__ d_total, uint32_t* __restrict__ keys,
+                                                       uint32_t pad) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < cap && i >= *d_total) keys[i] = pad;
+}
+
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t cap, const int64_t* __restrict__ d_total, const uint32_t* __restrict__ keys,
+                                                          int2* __restrict__ ranges) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = min(cap, *d_total);
     if (i >= total) return;
     const uint32_t cur = keys[i];
     if (i == 0) {
@@ -291,7 +310,7 @@ size_t bin_sort_workspace_bytes(int64_t, int64_t max_pairs, int, int) { return m
 
 int bin_count(int mode, int width, int height, int64_t n, const float* xy, const float* depth, const int32_t* radii,
               const float* conic, const float* opacity, void* ws, size_t ws_bytes, int64_t* d_total, int64_t* host_total,
-              cudaStream_t s) {
+              int sync_host, cudaStream_t s) {
     const LayoutA L = make_layout_a(n);
     if (ws_bytes < L.total) {
         set_error("bin_count: workspace too small (%zu < %zu)", ws_bytes, L.total);
@@ -322,26 +341,28 @@ int bin_count(int mode, int width, int height, int64_t n, const float* xy, const
     B200GS_LAUNCH_CHECK();
     if (host_total != nullptr) {
         B200GS_CUDA(cudaMemcpyAsync(host_total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        B200GS_CUDA(cudaStreamSynchronize(s));
+        if (sync_host) B200GS_CUDA(cudaStreamSynchronize(s));
     }
     return B200GS_OK;
 }
 
 int bin_sort(int mode, int width, int height, int64_t n, const float* xy, const int32_t* radii, const float* conic,
-             const float* opacity, int64_t total, int64_t max_pairs, const void* ws_a, void* ws_b, size_t ws_bytes,
-             int32_t* sorted_ids, int32_t* tile_ranges, cudaStream_t s) {
+             const float* opacity, int64_t total, const int64_t* d_total, int64_t max_pairs, const void* ws_a, void* ws_b,
+             size_t ws_bytes, int32_t* sorted_ids, int32_t* tile_ranges, cudaStream_t s) {
     const int grid_x = div_up(width, TILE), grid_y = div_up(height, TILE);
     const int n_tiles = grid_x * grid_y;
+    const bool capacity_mode = total < 0;   // pair count known on the device only: sort the whole capacity, padded
     B200GS_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(int32_t) * 2 * (size_t)n_tiles, s));
-    if (total > max_pairs) {
+    if (!capacity_mode && total > max_pairs) {
         set_error("bin_sort: %lld pairs exceed capacity %lld", (long long)total, (long long)max_pairs);
         return B200GS_ENOSPACE;
     }
-    if (total >= (int64_t(1) << 31)) {
-        set_error("bin_sort: %lld pairs exceed 2^31", (long long)total);
+    const int64_t items = capacity_mode ? max_pairs : total;
+    if (items >= (int64_t(1) << 31)) {
+        set_error("bin_sort: %lld pairs exceed 2^31", (long long)items);
         return B200GS_ENOSPACE;
     }
-    if (total == 0 || n == 0) return B200GS_OK;
+    if (items == 0 || n == 0) return B200GS_OK;
     const LayoutA LA = make_layout_a(n);
     const LayoutB L = make_layout_b(max_pairs);
     if (ws_bytes < L.total) {
@@ -362,11 +383,16 @@ int bin_sort(int mode, int width, int height, int64_t n, const float* xy, const 
     else
         emit_pairs_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, (const float2*)xy, radii, conic, opacity, order, tiles, offsets, pkeys_in, pvals_in);
     B200GS_LAUNCH_CHECK();
+    int bits = tile_bits_for(n_tiles);
+    if (capacity_mode) {
+        pad_keys_kernel<<<(unsigned)div_up64(items, 256), 256, 0, s>>>(items, d_total, pkeys_in, 1u << bits);
+        B200GS_LAUNCH_CHECK();
+        bits += 1;
+    }
     size_t tb = L.temp_bytes;
-    // temp_b was sized for max_pairs items; cub's requirement is monotone in the item count
-    B200GS_CUDA(cub::DeviceRadixSort::SortPairs(w + L.temp, tb, pkeys_in, pkeys_out, pvals_in, sorted_ids, (int)total, 0,
-                                                tile_bits_for(n_tiles), s));
-    tile_ranges_kernel<<<(unsigned)div_up64(total, 256), 256, 0, s>>>(total, pkeys_out, (int2*)tile_ranges);
+    // temp was sized for max_pairs items; cub's requirement is monotone in the item count
+    B200GS_CUDA(cub::DeviceRadixSort::SortPairs(w + L.temp, tb, pkeys_in, pkeys_out, pvals_in, sorted_ids, (int)items, 0, bits, s));
+    tile_ranges_kernel<<<(unsigned)div_up64(items, 256), 256, 0, s>>>(items, d_total, pkeys_out, (int2*)tile_ranges);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }

@@ -95,10 +95,10 @@ size_t bin_count_workspace_bytes(int64_t n);
 size_t bin_sort_workspace_bytes(int64_t n, int64_t max_pairs, int width, int height);
 int bin_count(int mode, int width, int height, int64_t n, const float* xy, const float* depth, const int32_t* radii,
               const float* conic, const float* opacity, void* ws, size_t ws_bytes, int64_t* d_total, int64_t* host_total,
-              cudaStream_t s);
+              int sync_host, cudaStream_t s);
 int bin_sort(int mode, int width, int height, int64_t n, const float* xy, const int32_t* radii, const float* conic,
-             const float* opacity, int64_t total, int64_t max_pairs, const void* ws_a, void* ws_b, size_t ws_b_bytes,
-             int32_t* sorted_ids, int32_t* tile_ranges, cudaStream_t s);
+             const float* opacity, int64_t total, const int64_t* d_total, int64_t max_pairs, const void* ws_a, void* ws_b,
+             size_t ws_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges, cudaStream_t s);
 
 int launch_blend_fwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids,
                      const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,

@@ -122,22 +122,41 @@ def _copy_view(v: B200gsView, **updates) -> B200gsView:
 # binning helper (no autograd)
 # ----------------------------------------------------------------------------------------------------------------------
 class Binning:
-    """Result of K2-K5 for one view: depth-sorted per-tile Gaussian id lists."""
-    __slots__ = ("sorted_ids", "tile_ranges", "total")
+    """Result of K2-K5 for one view: depth-sorted per-tile Gaussian id lists.  In lazy mode `total` is None until
+    resolve() has read the pair counter back (see bin_gaussians)."""
+    __slots__ = ("sorted_ids", "tile_ranges", "total", "_pending")
 
-    def __init__(self, sorted_ids, tile_ranges, total):
-        self.sorted_ids, self.tile_ranges, self.total = sorted_ids, tile_ranges, total
+    def __init__(self, sorted_ids, tile_ranges, total, pending=None):
+        self.sorted_ids, self.tile_ranges, self.total, self._pending = sorted_ids, tile_ranges, total, pending
+
+    def resolve(self) -> bool:
+        """Lazy mode: wait for the asynchronous copy of the pair counter.  Returns False when the counter exceeded
+        the capacity the lists were built with (pairs were dropped: the caller must re-bin in exact mode)."""
+        if self._pending is None:
+            return True
+        event, key, capacity = self._pending
+        self._pending = None
+        event.synchronize()
+        self.total = int(_host_total[0])
+        _last_total[key] = self.total
+        return self.total <= capacity
 
 
 _host_total = None
+_last_total = {}       # (mode, width, height, n) -> pair count of the previous view: sizes the next view's buffers
 
-
-TILE_CULLING = True   # exact (tile, splat) culling in K2/K3; False reproduces the reference's full 3-sigma-rect pair list
+TILE_CULLING = True    # exact (tile, splat) culling in K2/K3; False reproduces the reference's full 3-sigma-rect pair list
+LAZY_SLACK = 1.25      # lazy mode: capacity = slack x previous pair count
 
 
 def bin_gaussians(mode: int, width: int, height: int, xy: torch.Tensor, depth: torch.Tensor, radii: torch.Tensor,
-                  conic: Optional[torch.Tensor] = None, opacity: Optional[torch.Tensor] = None) -> Binning:
-    """K2-K5.  Passing conic+opacity enables exact tile culling (see include/b200gs.h)."""
+                  conic: Optional[torch.Tensor] = None, opacity: Optional[torch.Tensor] = None, lazy: bool = False) -> Binning:
+    """K2-K5.  Passing conic+opacity enables exact tile culling (see include/b200gs.h).
+
+    lazy=False: the pair count is read back synchronously (one host sync, like the reference backends) and the lists
+    are allocated exactly.  lazy=True: buffers are sized from the previous view's count (x LAZY_SLACK), nothing blocks
+    here; call Binning.resolve() once the rest of the forward is enqueued — it returns False in the rare case the
+    capacity was exceeded and the forward has to be redone with lazy=False."""
     L = lib()
     if not TILE_CULLING or conic is None or opacity is None:
         conic = opacity = None
@@ -147,20 +166,42 @@ def bin_gaussians(mode: int, width: int, height: int, xy: torch.Tensor, depth: t
     gx, gy = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
     ws_a = torch.empty(L.b200gs_bin_count_workspace_bytes(n), dtype=torch.uint8, device=dev)
     d_total = torch.empty(1, dtype=torch.int64, device=dev)
+    ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
     global _host_total
     if _host_total is None:
         _host_total = torch.zeros(1, dtype=torch.int64).pin_memory()
+    key = (mode, width, height, n, conic is not None)
+    prev = _last_total.get(key) if lazy else None
+    sync = prev is None
     with _stage("bin_count"):
-        check(L.b200gs_bin_count(mode, width, height, n, ptr(xy), ptr(depth), ptr(radii), ptr(conic), ptr(opacity), ptr(ws_a), ws_a.numel(),
-                                 ptr(d_total), _host_total.data_ptr(), st), "b200gs_bin_count")
-    total = int(_host_total[0])
-    sorted_ids = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-    ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
-    ws_b = torch.empty(L.b200gs_bin_sort_workspace_bytes(n, total, width, height), dtype=torch.uint8, device=dev)
+        check(L.b200gs_bin_count(mode, width, height, n, ptr(xy), ptr(depth), ptr(radii), ptr(conic), ptr(opacity), ptr(ws_a),
+                                 ws_a.numel(), ptr(d_total), _host_total.data_ptr(), 1 if sync else 0, st), "b200gs_bin_count")
+    if sync:
+        total = capacity = int(_host_total[0])
+        _last_total[key] = total
+        pending = None
+    else:
+        event = torch.cuda.Event()
+        event.record()
+        total = -1
+        capacity = int(prev * LAZY_SLACK) + 4096
+        pending = (event, key, capacity)
+    sorted_ids = torch.empty(max(capacity, 1), dtype=torch.int32, device=dev)
+    ws_b = torch.empty(L.b200gs_bin_sort_workspace_bytes(n, capacity, width, height), dtype=torch.uint8, device=dev)
     with _stage("bin_sort"):
-        check(L.b200gs_bin_sort(mode, width, height, n, ptr(xy), ptr(radii), ptr(conic), ptr(opacity), total, total, ptr(ws_a), ptr(ws_b), ws_b.numel(),
-                                ptr(sorted_ids), ptr(ranges), st), "b200gs_bin_sort")
-    return Binning(sorted_ids, ranges, total)
+        check(L.b200gs_bin_sort(mode, width, height, n, ptr(xy), ptr(radii), ptr(conic), ptr(opacity), total, ptr(d_total), capacity,
+                                ptr(ws_a), ptr(ws_b), ws_b.numel(), ptr(sorted_ids), ptr(ranges), st), "b200gs_bin_sort")
+    return Binning(sorted_ids, ranges, None if pending else total, pending)
+
+
+def bin_and_blend(mode, width, height, xy, depth, radii, conic, opacity, colors, bg, planar, want_alpha):
+    """Forward binning + blend with the lazy (sync-free) pair count; falls back to an exact re-run on overflow."""
+    binning = bin_gaussians(mode, width, height, xy, depth, radii, conic, opacity, lazy=True)
+    out = blend_forward(mode, width, height, binning, xy, conic, opacity, colors, bg, planar, want_alpha)
+    if not binning.resolve():
+        binning = bin_gaussians(mode, width, height, xy, depth, radii, conic, opacity, lazy=False)
+        out = blend_forward(mode, width, height, binning, xy, conic, opacity, colors, bg, planar, want_alpha)
+    return binning, out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -268,8 +309,7 @@ class _RasterizeVanilla(torch.autograd.Function):
         W, H = view.width, view.height
         xy, depth, radii, conic, _, tiles, _, rgb, clamped = project_forward(view, means3D, scales, rotations, shs if use_sh else None)
         colors = rgb if use_sh else colors_precomp
-        binning = bin_gaussians(MODE_VANILLA, W, H, xy, depth, radii, conic, opac)
-        image, final_T, n_contrib, _ = blend_forward(MODE_VANILLA, W, H, binning, xy, conic, opac, colors, bg, True, False)
+        binning, (image, final_T, n_contrib, _) = bin_and_blend(MODE_VANILLA, W, H, xy, depth, radii, conic, opac, colors, bg, True, False)
         ctx.view = view
         ctx.use_sh = use_sh
         ctx.binning = binning
@@ -367,8 +407,7 @@ class _RasterizeVanillaRaw(torch.autograd.Function):
         W, H = view.width, view.height
         xy, depth, radii, conic, _, tiles, rgb, clamped, opac = project_forward_raw(view, means3D, log_scales, raw_quats, ol, shs_dc,
                                                                                     shs_rest)
-        binning = bin_gaussians(MODE_VANILLA, W, H, xy, depth, radii, conic, opac)
-        image, final_T, n_contrib, _ = blend_forward(MODE_VANILLA, W, H, binning, xy, conic, opac, rgb, bg, True, False)
+        binning, (image, final_T, n_contrib, _) = bin_and_blend(MODE_VANILLA, W, H, xy, depth, radii, conic, opac, rgb, bg, True, False)
         ctx.view = view
         ctx.binning = binning
         ctx.means2D_shape = tuple(means2D.shape)
@@ -486,8 +525,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         radii = radii.contiguous()
         bg = _f32c(background, "background") if background is not None else None
         H, W = int(img_height), int(img_width)
-        binning = bin_gaussians(MODE_GSPLAT, W, H, xys, depths, radii, conics, opac)
-        image, final_T, n_contrib, alpha = blend_forward(MODE_GSPLAT, W, H, binning, xys, conics, opac, colors, bg, False, True)
+        binning, (image, final_T, n_contrib, alpha) = bin_and_blend(MODE_GSPLAT, W, H, xys, depths, radii, conics, opac, colors, bg, False, True)
         ctx.binning = binning
         ctx.hw = (H, W)
         ctx.absgrad = absgrad

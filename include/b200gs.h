@@ -139,18 +139,24 @@ B200GS_API int b200gs_sh_bwd(int32_t degree, int32_t sh_stride, int64_t n, const
  *     phase B (up to max_pairs (tile,Gaussian) pairs).  Two buffers because the pair count is only known after phase A.
  * b200gs_bin_count: phase A. Depth-sorts, scans tiles-per-Gaussian (recomputed from xy/radii with the mode's rect
  *     rule) and writes the pair total to d_total (device int64) and, when host_total != NULL (pinned or pageable
- *     host int64), copies it there and SYNCHRONISES the stream — the one optional host sync of the forward.
+ *     host int64), copies it there (cudaMemcpyAsync on `stream`) and, when sync_host != 0, SYNCHRONISES the stream —
+ *     the one optional host sync of the forward.  With sync_host == 0 the caller records its own event and reads
+ *     host_total later (capacity mode of phase B).
  *     workspace_a must stay untouched until phase B has been enqueued.
  * b200gs_bin_sort: phase B. Emits pairs, partitions by tile, writes sorted_ids[total] (Gaussian ids, front to back
- *     inside each tile) and tile_ranges[n_tiles,2] (int32 [start,end)).  `total` must be the value phase A produced;
- *     returns B200GS_ENOSPACE if total > max_pairs. */
+ *     inside each tile) and tile_ranges[n_tiles,2] (int32 [start,end)).  d_total = the device counter phase A wrote.
+ *     total >= 0 (exact mode): the host copy of that counter; returns B200GS_ENOSPACE if total > max_pairs.
+ *     total < 0 (capacity mode, no host sync): the count is read on the device only; all max_pairs slots are sorted
+ *     (unused ones padded behind the last tile) and pairs beyond max_pairs are DROPPED — the caller must compare the
+ *     counter with max_pairs afterwards (it is copied to host_total asynchronously by phase A) and redo the phase with
+ *     a larger buffer if it overflowed. */
 B200GS_API size_t b200gs_bin_count_workspace_bytes(int64_t n);
 B200GS_API size_t b200gs_bin_sort_workspace_bytes(int64_t n, int64_t max_pairs, int32_t width, int32_t height);
 B200GS_API int b200gs_bin_count(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const float* depth,
                      const int32_t* radii, const float* cull_conic, const float* cull_opacity, void* workspace_a, size_t workspace_a_bytes, int64_t* d_total,
-                     int64_t* host_total, void* stream);
+                     int64_t* host_total, int32_t sync_host, void* stream);
 B200GS_API int b200gs_bin_sort(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const int32_t* radii,
-                    const float* cull_conic, const float* cull_opacity, int64_t total, int64_t max_pairs, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes,
+                    const float* cull_conic, const float* cull_opacity, int64_t total, const int64_t* d_total, int64_t max_pairs, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes,
                     int32_t* sorted_ids, int32_t* tile_ranges, void* stream);
 
 /* ---- K6: blend forward ---------------------------------------------------------------------------------------------

@@ -346,6 +346,29 @@ def test_fused_activation_path(n, W, H, seed, pose, ms):
         assert _rel(model.gaussians[k].grad, g_fused[k]) < 2e-3, k
 
 
+def test_lazy_binning_overflow_falls_back():
+    """The sync-free forward sizes its pair buffers from the previous view; when a view needs more than that capacity
+    the forward must detect it and redo the binning exactly — same image, same gradients."""
+    from b200gs import ops
+    from b200gs.renderers import B200VanillaRenderer
+    raw, model, cam = _model_and_cam(4096, 256, 256, 5, 3, 0.05)
+    cam_d = cam.to_device(DEV)
+    bg = torch.tensor([0.3, 0.1, 0.7], device=DEV)
+    R = B200VanillaRenderer().to(DEV)
+    ops._last_total.clear()
+    a = R(cam_d, model, bg)["render"].detach().clone()         # first call: exact (no history)
+    b = R(cam_d, model, bg)["render"].detach().clone()         # second call: lazy, capacity from history
+    assert torch.equal(a, b)
+    assert len(ops._last_total) > 0
+    for k in list(ops._last_total):
+        ops._last_total[k] = 100                                # pretend the previous view was almost empty
+    out = R(cam_d, model, bg)
+    assert torch.equal(a, out["render"].detach())
+    out["render"].sum().backward()
+    assert bool(torch.isfinite(model.gaussians["means"].grad).all())
+    assert all(v > 100 for v in ops._last_total.values())       # history repaired by the fallback
+
+
 def test_edge_cases():
     """empty scene, everything behind the camera, one huge splat covering all tiles, opaque stack, sh degrees 0..3."""
     from b200gs.renderers import B200VanillaRenderer, B200GSplatRenderer
