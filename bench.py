@@ -110,7 +110,23 @@ class ClockSampler:
 # CPU arm: the reference's own CPU-runnable part of the path: projection + SH, forward + autograd
 # backward, as restated (and pinned against the reference) in oracle/gs_oracle.py
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_projection_views_per_sec(n, width, height, mode_name, iters, warm=2):
+def _reference_modules():
+    """internal/utils/gaussian_projection.py and sh_utils.py of the UNMODIFIED reference, from baseline/_ref (the offline
+    pip --target install of /root/reference; git-ignored, shipped to the GPU box).  None when it is not there."""
+    base = os.path.join(ROOT, "baseline", "_ref", "internal", "utils")
+    if not os.path.exists(os.path.join(base, "gaussian_projection.py")):
+        return None
+    import importlib.util
+    mods = []
+    for name in ("gaussian_projection", "sh_utils"):
+        spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(base, name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        mods.append(m)
+    return tuple(mods)
+
+
+def cpu_projection_views_per_sec(n, width, height, mode_name, iters, warm=2, prefer_reference=True):
     from oracle import gs_oracle as O
     from b200gs.scene import activate, make_ring_cameras, make_scene
     mode = O.MODE_GSPLAT if mode_name == "gsplat" else O.MODE_VANILLA
@@ -118,10 +134,25 @@ def cpu_projection_views_per_sec(n, width, height, mode_name, iters, warm=2):
     cams = make_ring_cameras(width, height)
     g = torch.Generator().manual_seed(1)
     c_xy, c_con, c_rgb = torch.randn(n, 2, generator=g), torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
+    ref = _reference_modules() if prefer_reference else None
+
     def one(it):
         cam = cams[it % len(cams)]
-        ov = O.make_view(cam.R, cam.T, float(cam.fx), float(cam.fy), float(cam.cx), float(cam.cy), width, height)
         ins = {k: sc[k].clone().requires_grad_(True) for k in ("means", "scales", "rotations", "shs")}
+        if ref is not None:
+            # the UNMODIFIED reference code (baseline/_ref): PythonPreprocessGSplatRenderer's projection + SH
+            # (internal/renderers/pypreprocess_gsplat_renderer.py:20-38), forward + autograd backward, on the CPU
+            gp, shu = ref
+            t0 = time.perf_counter()
+            out = gp.project_gaussians(means_3d=ins["means"], scales=ins["scales"], scale_modifier=1.0, quaternions=ins["rotations"],
+                                       world_to_camera=cam.world_to_camera, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy,
+                                       img_height=cam.height, img_width=cam.width, block_width=16)
+            dirs = ins["means"].detach() - cam.camera_center
+            dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+            col = torch.clamp_min(shu.eval_sh(3, ins["shs"].transpose(1, 2), dirs) + 0.5, 0.0)
+            ((out[0] * c_xy).sum() + (out[3] * c_con).sum() + (col * c_rgb).sum()).backward()
+            return time.perf_counter() - t0
+        ov = O.make_view(cam.R, cam.T, float(cam.fx), float(cam.fy), float(cam.cx), float(cam.cy), width, height)
         t0 = time.perf_counter()
         p = O.project(mode, ins["means"], ins["scales"], ins["rotations"], ov)
         col = O.sh_colors(3, ins["shs"], ins["means"], cam.camera_center, detach_dir=(mode == O.MODE_GSPLAT))
@@ -141,21 +172,22 @@ def cpu_projection_views_per_sec(n, width, height, mode_name, iters, warm=2):
     times = [one(it) for it in range(warm + iters)][warm:]
     times.sort()
     med = times[len(times) // 2]
-    return 1.0 / med, med, best_threads
+    return 1.0 / med, med, best_threads, ("reference" if ref is not None else "port")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 12))
-    vps, med, cores = cpu_projection_views_per_sec(args.n, args.width, args.height, args.mode, steps, warm=max(1, min(args.warmup, 3)))
-    sample = (f"projection+SH forward + autograd backward only (the reference has no CPU blend/sort: BASELINE.md §3), "
-              f"{steps} views of the same workload, median")
+    vps, med, cores, kind = cpu_projection_views_per_sec(args.n, args.width, args.height, args.mode, steps, warm=max(1, min(args.warmup, 3)))
+    sample = (f"the reference's CPU-runnable part of the path (pypreprocess projection + SH, forward + autograd backward; it has no "
+              f"CPU blend/sort: BASELINE.md §3), {steps} views of the same workload, median; "
+              + ("unmodified reference code from baseline/_ref" if kind == "reference" else "oracle port (baseline/_ref absent)"))
     line = {
         "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
         "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, "cpu"),
-        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -310,9 +342,10 @@ def main():
         "scene": {"N": N, "V": V, "I": I, "I_after_exact_culling": I_culled, "P": P, "stage_sum_ms": round(sum(stage_ms.values()), 4)},
     }
     if not args.no_cpu_baseline and world == 1:
-        vps, med, cores = cpu_projection_views_per_sec(N, W, H, args.mode, args.cpu_sample_iters)
-        line["cpu_baseline"] = {"value": vps, "unit": UNIT, "cores": cores, "kind": "port", "host_cpus": os.cpu_count() or 1,
-                                "sample": f"oracle projection+SH fwd+autograd bwd (reference has no CPU blend), {args.cpu_sample_iters} views, median"}
+        vps, med, cores, kind = cpu_projection_views_per_sec(N, W, H, args.mode, args.cpu_sample_iters)
+        line["cpu_baseline"] = {"value": vps, "unit": UNIT, "cores": cores, "kind": kind, "host_cpus": os.cpu_count() or 1,
+                                "sample": f"reference CPU path (pypreprocess projection + SH, fwd + autograd bwd; no CPU blend exists), "
+                                          f"{args.cpu_sample_iters} views, median; " + ("baseline/_ref code" if kind == "reference" else "oracle port")}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,157 @@
+"""Drop-in evidence: the reference's UNMODIFIED classes — ``internal.renderers.vanilla_renderer.VanillaRenderer``,
+``internal.renderers.gsplat_renderer.GSPlatRenderer``, ``internal.models.vanilla_gaussian.VanillaGaussianModel``,
+``internal.cameras.cameras.Cameras`` — imported from ``baseline/_ref`` (the offline ``pip install --target`` of
+/root/reference, git-ignored, shipped to the GPU box) run on the b200gs kernels once ``b200gs.compat.install()`` has
+aliased ``diff_gaussian_rasterization`` / ``gsplat`` in ``sys.modules``; and the b200gs plug-in renderers give the same
+image and gradients for the reference's own model object.
+
+Skipped when ``baseline/_ref`` is absent.  ``lightning`` (not installed here) is only needed for a type annotation at
+import time and is stubbed with an empty module."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+REF = os.path.join(ROOT, "baseline", "_ref")
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.isdir(os.path.join(REF, "internal")):
+        pytest.skip("baseline/_ref not present")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    if "lightning" not in sys.modules:
+        stub = types.ModuleType("lightning")
+        stub.LightningModule = type("LightningModule", (), {})
+        sys.modules["lightning"] = stub
+    import b200gs.compat
+    b200gs.compat.install()
+    from internal.cameras.cameras import Cameras
+    from internal.models.vanilla_gaussian import VanillaGaussian
+    from internal.renderers.gsplat_renderer import GSPlatRenderer
+    from internal.renderers.vanilla_renderer import VanillaRenderer
+    return types.SimpleNamespace(Cameras=Cameras, VanillaGaussian=VanillaGaussian, VanillaRenderer=VanillaRenderer,
+                                 GSPlatRenderer=GSPlatRenderer)
+
+
+def _setup(ref, n=6000, W=320, H=240, pose=2):
+    from b200gs.scene import make_scene, ring_pose
+    import math
+    raw = make_scene(n, 9, mean_scale=0.04)
+    model = ref.VanillaGaussian(sh_degree=3).instantiate()
+    model.setup_from_tensors({k: v.clone() for k, v in raw.items()})
+    model.active_sh_degree = 3
+    model = model.to(DEV)
+    R, T = ring_pose(pose)
+    fx = 0.5 * W / math.tan(math.radians(39.6) * 0.5)
+    cams = ref.Cameras(R=R[None], T=T[None], fx=torch.tensor([fx]), fy=torch.tensor([fx]), cx=torch.tensor([W / 2.0]),
+                       cy=torch.tensor([H / 2.0]), width=torch.tensor([W], dtype=torch.int32),
+                       height=torch.tensor([H], dtype=torch.int32), appearance_id=torch.zeros(1, dtype=torch.int32),
+                       normalized_appearance_id=torch.zeros(1), distortion_params=None,
+                       camera_type=torch.zeros(1, dtype=torch.int32))
+    return raw, model, cams[0].to_device(DEV), W, H
+
+
+def _grads(model):
+    return {k: p.grad.detach().clone() for k, p in model.gaussians.items()}
+
+
+def _zero(model):
+    for p in model.gaussians.values():
+        p.grad = None
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def test_reference_vanilla_renderer_runs_on_b200gs(ref):
+    from b200gs.renderers import B200VanillaRenderer
+    raw, model, cam, W, H = _setup(ref)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=DEV)
+    cot = (torch.rand(3, H, W, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(DEV)
+
+    out_ref = ref.VanillaRenderer()(cam, model, bg)              # the reference's class, our kernels underneath
+    out_ref["viewspace_points"].retain_grad()
+    (out_ref["render"] * cot).sum().backward()
+    g_ref, vs_ref = _grads(model), out_ref["viewspace_points"].grad.clone()
+    assert out_ref["render"].shape == (3, H, W) and out_ref["radii"].dtype == torch.int32
+    assert torch.equal(out_ref["visibility_filter"], out_ref["radii"] > 0)
+    assert float(vs_ref[:, 2].abs().max()) == 0 and float(vs_ref[:, :2].abs().max()) > 0
+
+    _zero(model)
+    out = B200VanillaRenderer().to(DEV)(cam, model, bg)           # our plug-in (fused-activation path: it IS the vanilla model)
+    out["viewspace_points"].retain_grad()
+    (out["render"] * cot).sum().backward()
+    assert set(out.keys()) == set(out_ref.keys())
+    assert float((out["render"] - out_ref["render"]).abs().max()) < 2e-4
+    assert torch.equal(out["radii"], out_ref["radii"])
+    g = _grads(model)
+    for k in g:
+        assert _rel(g[k], g_ref[k]) < 2e-3, k
+    assert _rel(out["viewspace_points"].grad, vs_ref) < 2e-3
+
+
+def test_reference_gsplat_renderer_runs_on_b200gs(ref):
+    from b200gs.renderers import B200GSplatRenderer
+    raw, model, cam, W, H = _setup(ref)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=DEV)
+    cot = (torch.rand(3, H, W, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(DEV)
+
+    out_ref = ref.GSPlatRenderer()(cam, model, bg, render_types=["rgb", "alpha", "acc_depth"])
+    out_ref["viewspace_points"].retain_grad()
+    ((out_ref["render"] * cot).sum() + out_ref["alpha"].sum() + out_ref["acc_depth"].sum()).backward()
+    g_ref, vs_ref = _grads(model), out_ref["viewspace_points"].grad.clone()
+    assert out_ref["render"].shape == (3, H, W) and out_ref["alpha"].shape == (1, H, W)
+
+    _zero(model)
+    out = B200GSplatRenderer().to(DEV)(cam, model, bg, render_types=["rgb", "alpha", "acc_depth"])
+    out["viewspace_points"].retain_grad()
+    ((out["render"] * cot).sum() + out["alpha"].sum() + out["acc_depth"].sum()).backward()
+    assert set(out.keys()) == set(out_ref.keys())
+    for key in ("render", "alpha", "acc_depth"):
+        assert float((out[key] - out_ref[key]).abs().max()) < 2e-4 * max(1.0, float(out_ref[key].abs().max())), key
+    assert torch.equal(out["radii"], out_ref["radii"])
+    assert torch.equal(out["viewspace_points_grad_scale"], out_ref["viewspace_points_grad_scale"])
+    g = _grads(model)
+    for k in g:
+        assert _rel(g[k], g_ref[k]) < 2e-3, k
+    assert _rel(out["viewspace_points"].grad, vs_ref) < 2e-3
+
+
+def test_training_step_shape_with_reference_objects(ref):
+    """The sequence GaussianSplatting.training_step performs around the renderer (internal/gaussian_splatting.py:341-397):
+    forward -> L1 + (1 - SSIM) loss with the reference's own ssim -> retain_grad -> backward -> the density controller's
+    read of viewspace_points.grad[visibility_filter, :2] / radii (vanilla_density_controller.py:101-123) -> Adam step."""
+    from internal.utils.ssim import ssim
+    from b200gs.renderers import B200VanillaRenderer
+    raw, model, cam, W, H = _setup(ref)
+    bg = torch.tensor([0.0, 0.0, 0.0], device=DEV)
+    renderer = B200VanillaRenderer().to(DEV)
+    with torch.no_grad():
+        target = renderer(cam, model, bg)["render"].clone()
+        model.gaussians["means"].add_(0.003 * torch.randn_like(model.gaussians["means"]))
+    opt = torch.optim.Adam(model.gaussians.values(), lr=1e-3)
+    losses = []
+    max_radii = torch.zeros(model.gaussians["means"].shape[0], device=DEV)
+    for step in range(4):
+        out = renderer(cam, model, bg)
+        loss = 0.8 * (out["render"] - target).abs().mean() + 0.2 * (1 - ssim(out["render"], target))
+        out["viewspace_points"].retain_grad()
+        loss.backward()
+        vis, radii = out["visibility_filter"], out["radii"]
+        grad_norm = out["viewspace_points"].grad[vis, :2].norm(dim=-1)
+        assert bool(torch.isfinite(grad_norm).all()) and grad_norm.numel() == int(vis.sum())
+        max_radii[vis] = torch.max(max_radii[vis], radii[vis].float())
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(float(loss))
+    assert losses[-1] < losses[0]
