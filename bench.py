@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--cpu-sample-iters", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="sharded", choices=["sharded", "replicas"],
+                    help="N>1 only. sharded: the reference's Gaussian-sharded scheme (gsplat_distributed_renderer.py): scene split by "
+                         "index across ranks, one camera per rank, all-to-all of the visible projected splats, gsplat semantics. "
+                         "replicas: every rank holds the whole scene (configs/ddp.yaml style), no data-path collective.")
     return ap.parse_args()
 
 
@@ -237,9 +241,17 @@ def main():
 
     N, W, H = args.n, args.width, args.height
     raw = make_scene(N, 0)
-    model = SyntheticGaussians(raw).to(dev)
+    sharded = world > 1 and args.parallelism == "sharded"
     cams = [c.to_device(dev) for c in make_ring_cameras(W, H)]
-    renderer = (B200VanillaRenderer() if args.mode == "vanilla" else B200GSplatRenderer()).to(dev)
+    if sharded:
+        from b200gs.distributed import B200DistributedRenderer, shard_range
+        lo, hi = shard_range(N, world, rank)
+        model = SyntheticGaussians({k: v[lo:hi].contiguous() for k, v in raw.items()}).to(dev)
+        renderer = B200DistributedRenderer().to(dev)
+        args.mode = "gsplat"    # the sharded renderer has gsplat semantics, like the reference's
+    else:
+        model = SyntheticGaussians(raw).to(dev)
+        renderer = (B200VanillaRenderer() if args.mode == "vanilla" else B200GSplatRenderer()).to(dev)
     bg = torch.zeros(3, device=dev)
     gen = torch.Generator().manual_seed(1)
     cot_host = (torch.rand(3, H, W, generator=gen) * 2 - 1).pin_memory()
@@ -302,7 +314,10 @@ def main():
             dist.destroy_process_group()
         return
 
-    # workload statistics of pose 0 for the algorithmic byte counts
+    # workload statistics of pose 0 for the algorithmic byte counts (full scene on this GPU, no collectives)
+    if sharded:
+        model = SyntheticGaussians(raw).to(dev)
+        renderer = B200GSplatRenderer().to(dev)
     with torch.no_grad():
         out = renderer(cams[0], model, bg)
         V = int((out["radii"] > 0).sum())
@@ -331,7 +346,7 @@ def main():
     line = {
         "metric": METRIC, "value": views_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, "replicas" if world > 1 else "single"),
+        "data": "synthetic", "config": workload_config(args, ("sharded-by-gaussian-index+all-to-all" if sharded else "replicas") if world > 1 else "single"),
         "e2e": {"value": e2e_vps, "unit": UNIT, "h2d_bytes_per_step": int(cot_host.numel() * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "clocks": clocks,
