@@ -139,7 +139,7 @@ int b200gs_bin_count(int32_t mode, int32_t width, int32_t height, int64_t n, con
     B200GS_CHECK_ARG(n == 0 || (xy && depth && radii), "NULL pointer");
     B200GS_CHECK_ARG(n < (int64_t(1) << 31), "n >= 2^31");
     B200GS_CHECK_ARG((cull_conic == nullptr) == (cull_opacity == nullptr), "cull_conic and cull_opacity go together");
-    return bin_count(mode, width, height, n, xy, depth, radii, cull_conic, cull_opacity, workspace, workspace_bytes, d_total,
+    return bin_count(mode, width, height, n, 0, xy, depth, radii, cull_conic, cull_opacity, workspace, workspace_bytes, d_total,
                      host_total, sync_host, (cudaStream_t)stream);
 }
 
@@ -152,7 +152,7 @@ int b200gs_bin_sort(int32_t mode, int32_t width, int32_t height, int64_t n, cons
     B200GS_CHECK_ARG(workspace_a && workspace_b && tile_ranges, "workspace/tile_ranges must not be NULL");
     B200GS_CHECK_ARG(total == 0 || (xy && radii && sorted_ids), "NULL pointer");
     B200GS_CHECK_ARG((cull_conic == nullptr) == (cull_opacity == nullptr), "cull_conic and cull_opacity go together");
-    return bin_sort(mode, width, height, n, xy, radii, cull_conic, cull_opacity, total, d_total, max_pairs, workspace_a, workspace_b, workspace_b_bytes, sorted_ids,
+    return bin_sort(mode, width, height, n, 0, xy, radii, cull_conic, cull_opacity, total, d_total, max_pairs, workspace_a, workspace_b, workspace_b_bytes, sorted_ids,
                     tile_ranges, (cudaStream_t)stream);
 }
 
@@ -163,7 +163,7 @@ int b200gs_blend_fwd(int32_t mode, int32_t width, int32_t height, int32_t channe
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
     B200GS_CHECK_ARG(width > 0 && height > 0, "bad size");
     B200GS_CHECK_ARG(tile_ranges && image && final_T && n_contrib, "NULL output/range pointer");
-    return launch_blend_fwd(mode, width, height, channels, tile_ranges, sorted_ids, xy, conic, opacity, colors, bg, image,
+    return launch_blend_fwd(mode, width, height, channels, tile_ranges, sorted_ids, 0, xy, conic, opacity, colors, bg, image,
                             pix_stride, ch_stride, final_T, n_contrib, alpha, (cudaStream_t)stream);
 }
 
@@ -177,9 +177,73 @@ int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int32_t channe
     B200GS_CHECK_ARG(width > 0 && height > 0, "bad size");
     B200GS_CHECK_ARG(tile_ranges && final_T && n_contrib && v_image, "NULL input pointer");
     B200GS_CHECK_ARG(v_xy && v_conic && v_opacity && v_colors, "NULL output pointer");
-    return launch_blend_bwd(mode, width, height, channels, tile_ranges, sorted_ids, xy, conic, opacity, colors, bg, final_T,
+    return launch_blend_bwd(mode, width, height, channels, tile_ranges, sorted_ids, 0, xy, conic, opacity, colors, bg, final_T,
                             n_contrib, v_image, pix_stride, ch_stride, v_alpha, xy_scale_x, xy_scale_y, v_xy, v_conic,
                             v_opacity, v_colors, v_xy_abs, (cudaStream_t)stream);
+}
+
+// ---- [n,12] row layout (the exchange format of the Gaussian-sharded renderer) -------------------------------------------
+size_t b200gs_pack_rows_workspace_bytes(int64_t n) { return n < 0 ? 0 : pack_rows_workspace_bytes(n); }
+
+int b200gs_pack_rows(int64_t n, const float* xy, const float* depth, const float* conic, const float* comp, const float* opacity,
+                     const float* rgb, const int32_t* radii, void* workspace, size_t workspace_bytes, int32_t* offsets, float* rows,
+                     int64_t* d_count, void* stream) {
+    B200GS_CHECK_ARG(n >= 0 && n < (int64_t(1) << 31), "bad n");
+    B200GS_CHECK_ARG(d_count != nullptr, "d_count must not be NULL");
+    B200GS_CHECK_ARG(n == 0 || (xy && depth && conic && opacity && rgb && radii && workspace && offsets && rows), "NULL pointer");
+    B200GS_CHECK_ARG(n == 0 || workspace_bytes >= pack_rows_workspace_bytes(n), "workspace too small");
+    return pack_rows(n, xy, depth, conic, comp, opacity, rgb, radii, workspace, workspace_bytes, offsets, rows, d_count,
+                     (cudaStream_t)stream);
+}
+
+int b200gs_unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offsets, const float* v_rows, float* v_xy, float* v_depth,
+                            float* v_conic, float* v_comp, float* v_opacity, float* v_rgb, void* stream) {
+    B200GS_CHECK_ARG(n >= 0, "bad n");
+    B200GS_CHECK_ARG(n == 0 || (radii && offsets && v_xy && v_depth && v_conic && v_opacity && v_rgb), "NULL pointer");
+    return unpack_rows_grad(n, radii, offsets, v_rows, v_xy, v_depth, v_conic, v_comp, v_opacity, v_rgb, (cudaStream_t)stream);
+}
+
+int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull, void* workspace,
+                          size_t workspace_bytes, int64_t* d_total, int64_t* host_total, int32_t sync_host, void* stream) {
+    B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
+    B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0 && n < (int64_t(1) << 31), "bad size");
+    B200GS_CHECK_ARG(workspace && d_total && (n == 0 || rows), "NULL pointer");
+    return bin_count(mode, width, height, n, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY, rows + B200GS_ROW_DEPTH,
+                     (const int32_t*)(rows + B200GS_ROW_RADIUS), cull ? rows + B200GS_ROW_CONIC : nullptr,
+                     cull ? rows + B200GS_ROW_OPACITY : nullptr, workspace, workspace_bytes, d_total, host_total, sync_host,
+                     (cudaStream_t)stream);
+}
+
+int b200gs_bin_sort_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull, int64_t total,
+                         const int64_t* d_total, int64_t max_pairs, const void* workspace_a, void* workspace_b,
+                         size_t workspace_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges, void* stream) {
+    B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
+    B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0 && max_pairs >= 0, "bad size");
+    B200GS_CHECK_ARG(d_total && workspace_a && workspace_b && tile_ranges && (n == 0 || rows), "NULL pointer");
+    return bin_sort(mode, width, height, n, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY, (const int32_t*)(rows + B200GS_ROW_RADIUS),
+                    cull ? rows + B200GS_ROW_CONIC : nullptr, cull ? rows + B200GS_ROW_OPACITY : nullptr, total, d_total, max_pairs,
+                    workspace_a, workspace_b, workspace_b_bytes, sorted_ids, tile_ranges, (cudaStream_t)stream);
+}
+
+int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
+                          const float* rows, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride, float* final_T,
+                          int32_t* n_contrib, float* alpha, void* stream) {
+    B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
+    B200GS_CHECK_ARG(width > 0 && height > 0 && tile_ranges && image && final_T && n_contrib, "bad argument");
+    return launch_blend_fwd(mode, width, height, 3, tile_ranges, sorted_ids, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY,
+                            rows + B200GS_ROW_CONIC, rows + B200GS_ROW_OPACITY, rows + B200GS_ROW_RGB, bg, image, pix_stride,
+                            ch_stride, final_T, n_contrib, alpha, (cudaStream_t)stream);
+}
+
+int b200gs_blend_bwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
+                          const float* rows, const float* bg, const float* final_T, const int32_t* n_contrib, const float* v_image,
+                          int64_t pix_stride, int64_t ch_stride, const float* v_alpha, float* v_rows, void* stream) {
+    B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
+    B200GS_CHECK_ARG(width > 0 && height > 0 && tile_ranges && final_T && n_contrib && v_image && v_rows, "bad argument");
+    return launch_blend_bwd(mode, width, height, 3, tile_ranges, sorted_ids, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY,
+                            rows + B200GS_ROW_CONIC, rows + B200GS_ROW_OPACITY, rows + B200GS_ROW_RGB, bg, final_T, n_contrib, v_image,
+                            pix_stride, ch_stride, v_alpha, 1.0f, 1.0f, v_rows + B200GS_ROW_XY, v_rows + B200GS_ROW_CONIC,
+                            v_rows + B200GS_ROW_OPACITY, v_rows + B200GS_ROW_RGB, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

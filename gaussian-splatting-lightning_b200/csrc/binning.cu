@@ -106,19 +106,31 @@ LayoutB make_layout_b(int64_t max_pairs) {
 // blend evaluations) shrinks ~1.8x on the benchmark scene.  The threshold carries a margin for the fp32 / ex2.approx
 // rounding of the blend loop, the interval a 0.01 px slack; round-to-nearest intrinsics pin the arithmetic so that the
 // counting and the emitting kernel agree on every pair.
+// Per-Gaussian inputs of the binning kernels, with element strides: separate contiguous arrays ({2,1,1,3,1}) or columns
+// of one [n,12] row buffer ({12,12,12,12,12}).
+struct BinSrc {
+    const float* xy; const float* depth; const int32_t* radii; const float* conic; const float* opacity;
+    int xs, ds, rs, cs, os;
+    __device__ __forceinline__ float2 get_xy(int64_t i) const { return *reinterpret_cast<const float2*>(xy + i * xs); }
+    __device__ __forceinline__ float get_depth(int64_t i) const { return depth[i * ds]; }
+    __device__ __forceinline__ int get_radius(int64_t i) const { return radii[i * rs]; }
+};
+
 struct CullE {
     float mx, my, A, B, iA, two_tA, det, ymax, yR;
     int mode;  // 0: full rect (culling off / degenerate conic), 1: spans, 2: nothing visible (opacity <= 1/255)
 };
 
-__device__ __forceinline__ CullE load_cull(const float2 p, const float* __restrict__ conic, const float* __restrict__ opacity, int64_t g) {
+__device__ __forceinline__ CullE load_cull(const float2 p, const BinSrc& src, int64_t g) {
+    const float* conic = src.conic ? src.conic + g * src.cs : nullptr;
+    const float* opacity = src.opacity ? src.opacity + g * src.os : nullptr;
     CullE e;
     e.mx = p.x; e.my = p.y;
     e.A = 1.f; e.B = 0.f; e.iA = 1.f; e.two_tA = 0.f; e.det = 1.f; e.ymax = 0.f; e.yR = 0.f;
     e.mode = 0;
     if (conic == nullptr) return e;
-    const float A = __ldg(conic + 3 * g), B = __ldg(conic + 3 * g + 1), C = __ldg(conic + 3 * g + 2);
-    const float o255 = 255.0f * __ldg(opacity + g);
+    const float A = __ldg(conic), B = __ldg(conic + 1), C = __ldg(conic + 2);
+    const float o255 = 255.0f * __ldg(opacity);
     if (o255 <= 1.0f) { e.mode = 2; return e; }
     // alpha >= 1/255  <=>  q <= ln(255 o); margin covers the fp32 / ex2.approx rounding of the blend loop
     const float t = __fmaf_rn(__logf(o255), 1.0001f, 1e-3f);
@@ -219,9 +231,7 @@ __device__ __forceinline__ int walk_rect(unsigned lane, bool active, int g, cons
 }
 
 template <bool GSPLAT>
-__global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, int grid_y, const float2* __restrict__ xy,
-                                                         const float* __restrict__ depth, const int32_t* __restrict__ radii,
-                                                         const float* __restrict__ conic, const float* __restrict__ opacity,
+__global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, int grid_y, const BinSrc src,
                                                          uint32_t* __restrict__ keys, int32_t* __restrict__ ids,
                                                          int32_t* __restrict__ tiles) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -230,17 +240,17 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
     bool active = false;
     CullE e{};
     if (i < n) {
-        const int r = radii[i];
+        const int r = src.get_radius(i);
         if (r > 0) {
-            const float2 p = xy[i];
+            const float2 p = src.get_xy(i);
             tile_rect<GSPLAT>(p.x, p.y, (float)r, grid_x, grid_y, x0, y0, x1, y1);
-            e = load_cull(p, conic, opacity, i);
+            e = load_cull(p, src, i);
             active = (x1 - x0) * (y1 - y0) > 0;
         }
     }
     const int t = walk_rect<GSPLAT, false>(lane, active, (int)i, e, x0, y0, x1, y1, grid_x, 0, 0, nullptr, nullptr);
     if (i < n) {
-        keys[i] = t > 0 ? __float_as_uint(depth[i]) : 0xFFFFFFFFu;
+        keys[i] = t > 0 ? __float_as_uint(src.get_depth(i)) : 0xFFFFFFFFu;
         ids[i] = (int32_t)i;
         tiles[i] = t;
     }
@@ -252,9 +262,7 @@ __global__ void write_total_kernel(int64_t n, const int64_t* __restrict__ offset
 
 // One lane per depth-ranked Gaussian; Gaussians with very large rects are written by the whole warp.
 template <bool GSPLAT>
-__global__ void __launch_bounds__(256) emit_pairs_kernel(int64_t n, int grid_x, int grid_y, int64_t max_pairs,
-                                                         const float2* __restrict__ xy, const int32_t* __restrict__ radii,
-                                                         const float* __restrict__ conic, const float* __restrict__ opacity,
+__global__ void __launch_bounds__(256) emit_pairs_kernel(int64_t n, int grid_x, int grid_y, int64_t max_pairs, const BinSrc src,
                                                          const int32_t* __restrict__ order, const int32_t* __restrict__ tiles,
                                                          const int64_t* __restrict__ offsets, uint32_t* __restrict__ pkeys,
                                                          int32_t* __restrict__ pvals) {
@@ -268,9 +276,9 @@ __global__ void __launch_bounds__(256) emit_pairs_kernel(int64_t n, int grid_x, 
         g = order[rnk];
         const int t = tiles[g];
         if (t > 0) {
-            const float2 p = xy[g];
-            tile_rect<GSPLAT>(p.x, p.y, (float)radii[g], grid_x, grid_y, x0, y0, x1, y1);
-            e = load_cull(p, conic, opacity, g);
+            const float2 p = src.get_xy(g);
+            tile_rect<GSPLAT>(p.x, p.y, (float)src.get_radius(g), grid_x, grid_y, x0, y0, x1, y1);
+            e = load_cull(p, src, g);
             start = offsets[rnk] - t;
             active = true;
         }
@@ -308,7 +316,12 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t cap, const int
 size_t bin_count_workspace_bytes(int64_t n) { return make_layout_a(n).total; }
 size_t bin_sort_workspace_bytes(int64_t, int64_t max_pairs, int, int) { return make_layout_b(max_pairs).total; }
 
-int bin_count(int mode, int width, int height, int64_t n, const float* xy, const float* depth, const int32_t* radii,
+static BinSrc make_src(int row_stride, const float* xy, const float* depth, const int32_t* radii, const float* conic, const float* opacity) {
+    if (row_stride > 0) return BinSrc{xy, depth, radii, conic, opacity, row_stride, row_stride, row_stride, row_stride, row_stride};
+    return BinSrc{xy, depth, radii, conic, opacity, 2, 1, 1, 3, 1};
+}
+
+int bin_count(int mode, int width, int height, int64_t n, int row_stride, const float* xy, const float* depth, const int32_t* radii,
               const float* conic, const float* opacity, void* ws, size_t ws_bytes, int64_t* d_total, int64_t* host_total,
               int sync_host, cudaStream_t s) {
     const LayoutA L = make_layout_a(n);
@@ -326,10 +339,11 @@ int bin_count(int mode, int width, int height, int64_t n, const float* xy, const
     const int grid_x = div_up(width, TILE), grid_y = div_up(height, TILE);
     if (n > 0) {
         const unsigned blocks = (unsigned)div_up64(n, 256);
+        const BinSrc src = make_src(row_stride, xy, depth, radii, conic, opacity);
         if (mode == B200GS_MODE_GSPLAT)
-            depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, (const float2*)xy, depth, radii, conic, opacity, keys_in, ids_in, tiles);
+            depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, keys_in, ids_in, tiles);
         else
-            depth_keys_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, (const float2*)xy, depth, radii, conic, opacity, keys_in, ids_in, tiles);
+            depth_keys_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, keys_in, ids_in, tiles);
         B200GS_LAUNCH_CHECK();
         size_t tb = L.temp_bytes;
         B200GS_CUDA(cub::DeviceRadixSort::SortPairs(w + L.temp, tb, keys_in, keys_out, ids_in, order, (int)n, 0, 32, s));
@@ -346,7 +360,7 @@ int bin_count(int mode, int width, int height, int64_t n, const float* xy, const
     return B200GS_OK;
 }
 
-int bin_sort(int mode, int width, int height, int64_t n, const float* xy, const int32_t* radii, const float* conic,
+int bin_sort(int mode, int width, int height, int64_t n, int row_stride, const float* xy, const int32_t* radii, const float* conic,
              const float* opacity, int64_t total, const int64_t* d_total, int64_t max_pairs, const void* ws_a, void* ws_b,
              size_t ws_bytes, int32_t* sorted_ids, int32_t* tile_ranges, cudaStream_t s) {
     const int grid_x = div_up(width, TILE), grid_y = div_up(height, TILE);
@@ -378,10 +392,11 @@ int bin_sort(int mode, int width, int height, int64_t n, const float* xy, const 
     uint32_t* pkeys_out = (uint32_t*)(w + L.pkeys_out);
     int32_t* pvals_in = (int32_t*)(w + L.pvals_in);
     const unsigned blocks = (unsigned)div_up64(n, 256);
+    const BinSrc src = make_src(row_stride, xy, nullptr, radii, conic, opacity);
     if (mode == B200GS_MODE_GSPLAT)
-        emit_pairs_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, (const float2*)xy, radii, conic, opacity, order, tiles, offsets, pkeys_in, pvals_in);
+        emit_pairs_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, src, order, tiles, offsets, pkeys_in, pvals_in);
     else
-        emit_pairs_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, (const float2*)xy, radii, conic, opacity, order, tiles, offsets, pkeys_in, pvals_in);
+        emit_pairs_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, src, order, tiles, offsets, pkeys_in, pvals_in);
     B200GS_LAUNCH_CHECK();
     int bits = tile_bits_for(n_tiles);
     if (capacity_mode) {
@@ -393,6 +408,89 @@ int bin_sort(int mode, int width, int height, int64_t n, const float* xy, const 
     // temp was sized for max_pairs items; cub's requirement is monotone in the item count
     B200GS_CUDA(cub::DeviceRadixSort::SortPairs(w + L.temp, tb, pkeys_in, pkeys_out, pvals_in, sorted_ids, (int)items, 0, bits, s));
     tile_ranges_kernel<<<(unsigned)div_up64(items, 256), 256, 0, s>>>(items, d_total, pkeys_out, (int2*)tile_ranges);
+    B200GS_LAUNCH_CHECK();
+    return B200GS_OK;
+}
+
+
+// ---- row packing for the Gaussian-sharded exchange -------------------------------------------------------------------
+namespace {
+
+struct VisibleFlag {
+    const int32_t* radii;
+    __host__ __device__ int32_t operator()(int32_t i) const { return radii[i] > 0 ? 1 : 0; }
+};
+
+__global__ void __launch_bounds__(256) pack_rows_kernel(int64_t n, const float2* __restrict__ xy, const float* __restrict__ depth,
+                                                        const float* __restrict__ conic, const float* __restrict__ comp,
+                                                        const float* __restrict__ opacity, const float* __restrict__ rgb,
+                                                        const int32_t* __restrict__ radii, const int32_t* __restrict__ offsets,
+                                                        float* __restrict__ rows, int64_t* __restrict__ d_count) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = radii[i];
+    const int o = offsets[i];
+    if (i == n - 1) *d_count = o + (r > 0 ? 1 : 0);
+    if (r <= 0) return;
+    float4* out = reinterpret_cast<float4*>(rows + int64_t(o) * B200GS_ROW_FLOATS);
+    const float2 p = xy[i];
+    out[0] = make_float4(p.x, p.y, depth[i], conic[3 * i]);
+    out[1] = make_float4(conic[3 * i + 1], conic[3 * i + 2], comp ? comp[i] : 1.0f, opacity[i]);
+    out[2] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], __int_as_float(r));
+}
+
+__global__ void __launch_bounds__(256) unpack_rows_grad_kernel(int64_t n, const int32_t* __restrict__ radii,
+                                                               const int32_t* __restrict__ offsets, const float* __restrict__ v_rows,
+                                                               float2* __restrict__ v_xy, float* __restrict__ v_depth,
+                                                               float* __restrict__ v_conic, float* __restrict__ v_comp,
+                                                               float* __restrict__ v_opacity, float* __restrict__ v_rgb) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+    if (radii[i] > 0) {
+        const float4* in = reinterpret_cast<const float4*>(v_rows + int64_t(offsets[i]) * B200GS_ROW_FLOATS);
+        a = in[0]; b = in[1]; c = in[2];
+    }
+    v_xy[i] = make_float2(a.x, a.y);
+    v_depth[i] = a.z;
+    v_conic[3 * i] = a.w; v_conic[3 * i + 1] = b.x; v_conic[3 * i + 2] = b.y;
+    if (v_comp) v_comp[i] = b.z;
+    v_opacity[i] = b.w;
+    v_rgb[3 * i] = c.x; v_rgb[3 * i + 1] = c.y; v_rgb[3 * i + 2] = c.z;
+}
+
+}  // namespace
+
+size_t pack_rows_workspace_bytes(int64_t n) {
+    size_t t = 0;
+    cub::TransformInputIterator<int32_t, VisibleFlag, cub::CountingInputIterator<int32_t>> it(cub::CountingInputIterator<int32_t>(0),
+                                                                                                VisibleFlag{nullptr});
+    cub::DeviceScan::ExclusiveSum(nullptr, t, it, (int32_t*)nullptr, (int)(n > 0 ? n : 1));
+    return align_up(t, 256);
+}
+
+int pack_rows(int64_t n, const float* xy, const float* depth, const float* conic, const float* comp, const float* opacity,
+              const float* rgb, const int32_t* radii, void* ws, size_t ws_bytes, int32_t* offsets, float* rows, int64_t* d_count,
+              cudaStream_t s) {
+    if (n == 0) {
+        B200GS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), s));
+        return B200GS_OK;
+    }
+    cub::TransformInputIterator<int32_t, VisibleFlag, cub::CountingInputIterator<int32_t>> it(cub::CountingInputIterator<int32_t>(0),
+                                                                                                VisibleFlag{radii});
+    size_t tb = ws_bytes;
+    B200GS_CUDA(cub::DeviceScan::ExclusiveSum(ws, tb, it, offsets, (int)n, s));
+    pack_rows_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(n, (const float2*)xy, depth, conic, comp, opacity, rgb, radii, offsets,
+                                                               rows, d_count);
+    B200GS_LAUNCH_CHECK();
+    return B200GS_OK;
+}
+
+int unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offsets, const float* v_rows, float* v_xy, float* v_depth,
+                     float* v_conic, float* v_comp, float* v_opacity, float* v_rgb, cudaStream_t s) {
+    if (n == 0) return B200GS_OK;
+    unpack_rows_grad_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(n, radii, offsets, v_rows, (float2*)v_xy, v_depth, v_conic, v_comp,
+                                                                      v_opacity, v_rgb);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }

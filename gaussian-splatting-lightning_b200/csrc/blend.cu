@@ -32,6 +32,12 @@ constexpr float T_STOP = 1e-4f;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr unsigned FULL = 0xffffffffu;
 
+// Element strides of the per-splat arrays: {2,3,1,CH} for separate contiguous arrays; {12,12,12,12} when all four
+// pointers address columns of one [n,12] row buffer (the exchange format of the Gaussian-sharded renderer).
+struct SplatStrides {
+    int xs, cs, os, ks;
+};
+
 __device__ __forceinline__ void pixel_of_thread(int tid, int& lx, int& ly) {
     const int w = tid >> 5, l = tid & 31;
     lx = ((w & 1) << 3) + (l & 7);
@@ -97,7 +103,7 @@ __device__ __forceinline__ int build_list(const unsigned char* __restrict__ s_ma
 
 template <int CH, bool GSPLAT>
 __global__ void __launch_bounds__(BLOCK_PIX) blend_fwd_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
-                                                              const int32_t* __restrict__ ids, const float2* __restrict__ xy,
+                                                              const int32_t* __restrict__ ids, const SplatStrides st, const float* __restrict__ xy,
                                                               const float* __restrict__ conic, const float* __restrict__ opacity,
                                                               const float* __restrict__ colors, const float* __restrict__ bg,
                                                               float* __restrict__ image, int64_t pix_stride, int64_t ch_stride,
@@ -136,14 +142,15 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_fwd_kernel(int width, int hei
         const int cnt = min(BLOCK_PIX, todo);
         if (tid < cnt) {
             const int g = __ldg(ids + range.x + base + tid);
-            const float2 m = __ldg(xy + g);
-            const float A = __ldg(conic + 3 * g), B = __ldg(conic + 3 * g + 1), Cc = __ldg(conic + 3 * g + 2);
-            const float o = __ldg(opacity + g);
+            const float2 m = __ldg(reinterpret_cast<const float2*>(xy + int64_t(g) * st.xs));
+            const float* cq = conic + int64_t(g) * st.cs;
+            const float A = __ldg(cq), B = __ldg(cq + 1), Cc = __ldg(cq + 2);
+            const float o = __ldg(opacity + int64_t(g) * st.os);
             s_g1[tid] = make_float4(m.x, m.y, (-0.5f * LOG2E) * A, -LOG2E * B);
             s_g2[tid] = make_float2((-0.5f * LOG2E) * Cc, o);
             float col[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * CH + c);
+            for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * st.ks + c);
             s_col[tid] = make_float4(col[0], col[1], col[2], col[3]);
             s_mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
         }
@@ -235,7 +242,7 @@ __device__ __forceinline__ float reduce_scatter<4>(const float* p, unsigned lane
 
 template <int CH, bool GSPLAT, bool ABS, int RB>
 __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
-                                                              const int32_t* __restrict__ ids, const float2* __restrict__ xy,
+                                                              const int32_t* __restrict__ ids, const SplatStrides st, const float* __restrict__ xy,
                                                               const float* __restrict__ conic, const float* __restrict__ opacity,
                                                               const float* __restrict__ colors, const float* __restrict__ bg,
                                                               const float* __restrict__ final_T, const int32_t* __restrict__ n_contrib,
@@ -302,14 +309,15 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
         if (tid < cnt) {
             const int g = __ldg(ids + range.x + lo + tid);
             s_id[tid] = g;
-            const float2 m = __ldg(xy + g);
-            const float A = __ldg(conic + 3 * g), B = __ldg(conic + 3 * g + 1), Cc = __ldg(conic + 3 * g + 2);
-            const float o = __ldg(opacity + g);
+            const float2 m = __ldg(reinterpret_cast<const float2*>(xy + int64_t(g) * st.xs));
+            const float* cq = conic + int64_t(g) * st.cs;
+            const float A = __ldg(cq), B = __ldg(cq + 1), Cc = __ldg(cq + 2);
+            const float o = __ldg(opacity + int64_t(g) * st.os);
             s_g1[tid] = make_float4(m.x, m.y, A, B);
             s_g2[tid] = make_float2(Cc, o);
             float col[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * CH + c);
+            for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * st.ks + c);
             s_col[tid] = make_float4(col[0], col[1], col[2], col[3]);
             s_mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
         }
@@ -376,14 +384,16 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
             for (int k = 0; k < NT; ++k) tot[k] = reduce_scatter<RB>(part[k], lane);
             if (writer && ((present >> my_slot) & 1u)) {
                 const int g = s_id[my_list[ii - my_slot]];
-                atomicAdd(v_xy + 2 * g, tot[0] * sx);
-                atomicAdd(v_xy + 2 * g + 1, tot[1] * sy);
-                atomicAdd(v_conic + 3 * g, tot[2]);
-                atomicAdd(v_conic + 3 * g + 1, tot[3]);
-                atomicAdd(v_conic + 3 * g + 2, tot[4]);
-                atomicAdd(v_opacity + g, tot[5]);
+                float* vx = v_xy + int64_t(g) * st.xs;
+                float* vc = v_conic + int64_t(g) * st.cs;
+                atomicAdd(vx, tot[0] * sx);
+                atomicAdd(vx + 1, tot[1] * sy);
+                atomicAdd(vc, tot[2]);
+                atomicAdd(vc + 1, tot[3]);
+                atomicAdd(vc + 2, tot[4]);
+                atomicAdd(v_opacity + int64_t(g) * st.os, tot[5]);
 #pragma unroll
-                for (int c = 0; c < CH; ++c) atomicAdd(v_colors + int64_t(g) * CH + c, tot[6 + c]);
+                for (int c = 0; c < CH; ++c) atomicAdd(v_colors + int64_t(g) * st.ks + c, tot[6 + c]);
                 if (ABS) {
                     atomicAdd(v_xy_abs + 2 * g, tot[6 + CH]);
                     atomicAdd(v_xy_abs + 2 * g + 1, tot[(7 + CH) % NT]);
@@ -394,16 +404,17 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
 }
 
 template <int CH>
-int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const int32_t* ids, const float* xy, const float* conic,
+int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy, const float* conic,
                  const float* opacity, const float* colors, const float* bg, float* image, int64_t ps, int64_t cs, float* final_T,
                  int32_t* n_contrib, float* alpha, cudaStream_t s) {
     const int gx = div_up(width, TILE), gy = div_up(height, TILE);
     dim3 grid(gx, gy);
+    const SplatStrides st = row_stride > 0 ? SplatStrides{row_stride, row_stride, row_stride, row_stride} : SplatStrides{2, 3, 1, CH};
     if (mode == B200GS_MODE_GSPLAT)
-        blend_fwd_kernel<CH, true><<<grid, BLOCK_PIX, 0, s>>>(width, height, gx, (const int2*)ranges, ids, (const float2*)xy, conic,
+        blend_fwd_kernel<CH, true><<<grid, BLOCK_PIX, 0, s>>>(width, height, gx, (const int2*)ranges, ids, st, xy, conic,
                                                               opacity, colors, bg, image, ps, cs, final_T, n_contrib, alpha);
     else
-        blend_fwd_kernel<CH, false><<<grid, BLOCK_PIX, 0, s>>>(width, height, gx, (const int2*)ranges, ids, (const float2*)xy, conic,
+        blend_fwd_kernel<CH, false><<<grid, BLOCK_PIX, 0, s>>>(width, height, gx, (const int2*)ranges, ids, st, xy, conic,
                                                                opacity, colors, bg, image, ps, cs, final_T, n_contrib, alpha);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
@@ -414,14 +425,15 @@ int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
 #endif
 
 template <int CH>
-int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const int32_t* ids, const float* xy, const float* conic,
+int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy, const float* conic,
                  const float* opacity, const float* colors, const float* bg, const float* final_T, const int32_t* n_contrib,
                  const float* v_image, int64_t ps, int64_t cs, const float* v_alpha, float sx, float sy, float* v_xy, float* v_conic,
                  float* v_opacity, float* v_colors, float* v_xy_abs, cudaStream_t s) {
     const int gx = div_up(width, TILE), gy = div_up(height, TILE);
     dim3 grid(gx, gy);
     constexpr int RB = B200GS_BWD_RB;
-#define B200GS_BWD_ARGS width, height, gx, (const int2*)ranges, ids, (const float2*)xy, conic, opacity, colors, bg, final_T, n_contrib, \
+    const SplatStrides st = row_stride > 0 ? SplatStrides{row_stride, row_stride, row_stride, row_stride} : SplatStrides{2, 3, 1, CH};
+#define B200GS_BWD_ARGS width, height, gx, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, final_T, n_contrib, \
                         v_image, ps, cs, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs
     if (mode == B200GS_MODE_GSPLAT) {
         if (v_xy_abs)
@@ -441,29 +453,29 @@ int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
 
 }  // namespace
 
-int launch_blend_fwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids, const float* xy,
+int launch_blend_fwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy,
                      const float* conic, const float* opacity, const float* colors, const float* bg, float* image,
                      int64_t pix_stride, int64_t ch_stride, float* final_T, int32_t* n_contrib, float* alpha, cudaStream_t s) {
     switch (channels) {
-        case 1: return fwd_dispatch<1>(mode, width, height, ranges, ids, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
-        case 2: return fwd_dispatch<2>(mode, width, height, ranges, ids, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
-        case 3: return fwd_dispatch<3>(mode, width, height, ranges, ids, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
-        case 4: return fwd_dispatch<4>(mode, width, height, ranges, ids, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
+        case 1: return fwd_dispatch<1>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
+        case 2: return fwd_dispatch<2>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
+        case 3: return fwd_dispatch<3>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
+        case 4: return fwd_dispatch<4>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
     }
     set_error("blend_fwd: unsupported channel count %d (1..4)", channels);
     return B200GS_EINVAL;
 }
 
-int launch_blend_bwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids, const float* xy,
+int launch_blend_bwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy,
                      const float* conic, const float* opacity, const float* colors, const float* bg, const float* final_T,
                      const int32_t* n_contrib, const float* v_image, int64_t pix_stride, int64_t ch_stride, const float* v_alpha,
                      float sx, float sy, float* v_xy, float* v_conic, float* v_opacity, float* v_colors, float* v_xy_abs,
                      cudaStream_t s) {
     switch (channels) {
-        case 1: return bwd_dispatch<1>(mode, width, height, ranges, ids, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
-        case 2: return bwd_dispatch<2>(mode, width, height, ranges, ids, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
-        case 3: return bwd_dispatch<3>(mode, width, height, ranges, ids, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
-        case 4: return bwd_dispatch<4>(mode, width, height, ranges, ids, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
+        case 1: return bwd_dispatch<1>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
+        case 2: return bwd_dispatch<2>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
+        case 3: return bwd_dispatch<3>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
+        case 4: return bwd_dispatch<4>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
     }
     set_error("blend_bwd: unsupported channel count %d (1..4)", channels);
     return B200GS_EINVAL;

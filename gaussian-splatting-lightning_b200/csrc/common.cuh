@@ -93,19 +93,25 @@ int launch_sh_bwd(int degree, int stride, int64_t n, const float* dirs, const fl
 
 size_t bin_count_workspace_bytes(int64_t n);
 size_t bin_sort_workspace_bytes(int64_t n, int64_t max_pairs, int width, int height);
-int bin_count(int mode, int width, int height, int64_t n, const float* xy, const float* depth, const int32_t* radii,
+int bin_count(int mode, int width, int height, int64_t n, int row_stride, const float* xy, const float* depth, const int32_t* radii,
               const float* conic, const float* opacity, void* ws, size_t ws_bytes, int64_t* d_total, int64_t* host_total,
               int sync_host, cudaStream_t s);
-int bin_sort(int mode, int width, int height, int64_t n, const float* xy, const int32_t* radii, const float* conic,
+size_t pack_rows_workspace_bytes(int64_t n);
+int pack_rows(int64_t n, const float* xy, const float* depth, const float* conic, const float* comp, const float* opacity,
+              const float* rgb, const int32_t* radii, void* ws, size_t ws_bytes, int32_t* offsets, float* rows, int64_t* d_count,
+              cudaStream_t s);
+int unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offsets, const float* v_rows, float* v_xy, float* v_depth,
+                     float* v_conic, float* v_comp, float* v_opacity, float* v_rgb, cudaStream_t s);
+int bin_sort(int mode, int width, int height, int64_t n, int row_stride, const float* xy, const int32_t* radii, const float* conic,
              const float* opacity, int64_t total, const int64_t* d_total, int64_t max_pairs, const void* ws_a, void* ws_b,
              size_t ws_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges, cudaStream_t s);
 
 int launch_blend_fwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids,
-                     const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
+                     int row_stride, const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
                      float* image, int64_t pix_stride, int64_t ch_stride, float* final_T, int32_t* n_contrib,
                      float* alpha, cudaStream_t s);
 int launch_blend_bwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids,
-                     const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
+                     int row_stride, const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
                      const float* final_T, const int32_t* n_contrib, const float* v_image, int64_t pix_stride,
                      int64_t ch_stride, const float* v_alpha, float sx, float sy, float* v_xy, float* v_conic,
                      float* v_opacity, float* v_colors, float* v_xy_abs, cudaStream_t s);

@@ -108,19 +108,178 @@ class GatheredView:
         self.camera_center = flat[22:25].to(device)
 
 
+class _ShardedRasterize(torch.autograd.Function):
+    """The whole sharded step as ONE autograd node, everything between the raw shard parameters and this rank's image:
+    K1 (fused activations, gsplat constants) per camera -> pack visible rows (device-side compaction) -> count exchange
+    (the step's single host sync) -> all_to_all_single of [V,12] rows -> K2-K7 reading the received rows in place.
+    Backward: K7 accumulates straight into a [R,12] gradient row buffer -> mirrored all_to_all_single -> unpack -> K8
+    (fused activation chain) per camera, summed over cameras."""
+
+    @staticmethod
+    def forward(ctx, means, log_scales, raw_quats, opac_logits, shs_dc, shs_rest, bg, views, rank, group, anti_aliased, sh_degree):
+        import ctypes
+        from . import ops
+        from ._lib import MODE_GSPLAT, check, lib, ptr
+        L = lib()
+        dev = means.device
+        n = means.shape[0]
+        world = len(views)
+        st = torch.cuda.current_stream().cuda_stream
+        means, log_scales, raw_quats = means.contiguous(), log_scales.contiguous(), raw_quats.contiguous()
+        ol = opac_logits.contiguous().reshape(-1)
+        shs_dc, shs_rest, bg = shs_dc.contiguous(), shs_rest.contiguous(), bg.contiguous()
+        counts = torch.zeros(2 * world, dtype=torch.int64, device=dev)   # [send | recv]
+        ws = torch.empty(max(int(L.b200gs_pack_rows_workspace_bytes(n)), 256), dtype=torch.uint8, device=dev)
+        per_cam = []
+        for j, view in enumerate(views):
+            v = ops._copy_view(view, sh_degree=int(sh_degree), sh_stride=int(shs_dc.shape[1] + shs_rest.shape[1]))
+            xy, depth, radii, conic, comp, tiles, rgb, clamped, opac = ops.project_forward_raw(
+                v, means, log_scales, raw_quats, ol, shs_dc, shs_rest, anti_aliased, want_comp=True)
+            rows = torch.empty(n, ROW_FLOATS, dtype=torch.float32, device=dev)
+            offsets = torch.empty(n, dtype=torch.int32, device=dev)
+            check(L.b200gs_pack_rows(n, ptr(xy), ptr(depth), ptr(conic), ptr(comp), ptr(opac), ptr(rgb), ptr(radii), ptr(ws), ws.numel(),
+                                     ptr(offsets), ptr(rows), counts.data_ptr() + 8 * j, st), "b200gs_pack_rows")
+            per_cam.append((v, rows, offsets, radii, clamped, xy))
+        dist.all_to_all_single(counts[world:], counts[:world], group=group)
+        host_counts = counts.cpu().tolist()                                 # the step's host sync
+        send_counts, recv_counts = host_counts[:world], host_counts[world:]
+        send = torch.cat([per_cam[j][1][:send_counts[j]] for j in range(world)], dim=0)
+        recv = torch.empty(sum(recv_counts), ROW_FLOATS, dtype=torch.float32, device=dev)
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
+        del send
+
+        gv = views[rank]
+        W, H = gv.width, gv.height
+        R = recv.shape[0]
+        gx, gy = (W + 15) // 16, (H + 15) // 16
+        ws_a = torch.empty(L.b200gs_bin_count_workspace_bytes(R), dtype=torch.uint8, device=dev)
+        d_total = torch.empty(1, dtype=torch.int64, device=dev)
+        host_total = torch.zeros(1, dtype=torch.int64).pin_memory()
+        check(L.b200gs_bin_count_rows(MODE_GSPLAT, W, H, R, ptr(recv), 1, ptr(ws_a), ws_a.numel(), ptr(d_total), host_total.data_ptr(), 1, st),
+              "b200gs_bin_count_rows")
+        total = int(host_total[0])
+        sorted_ids = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
+        ws_b = torch.empty(L.b200gs_bin_sort_workspace_bytes(R, total, W, H), dtype=torch.uint8, device=dev)
+        check(L.b200gs_bin_sort_rows(MODE_GSPLAT, W, H, R, ptr(recv), 1, total, ptr(d_total), total, ptr(ws_a), ptr(ws_b), ws_b.numel(),
+                                     ptr(sorted_ids), ptr(ranges), st), "b200gs_bin_sort_rows")
+        image = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
+        final_T = torch.empty(H, W, dtype=torch.float32, device=dev)
+        n_contrib = torch.empty(H, W, dtype=torch.int32, device=dev)
+        check(L.b200gs_blend_fwd_rows(MODE_GSPLAT, W, H, ptr(ranges), ptr(sorted_ids), ptr(recv), ptr(bg), ptr(image), 3, 1, ptr(final_T),
+                                      ptr(n_contrib), None, st), "b200gs_blend_fwd_rows")
+        ctx.per_cam, ctx.views, ctx.rank, ctx.group = per_cam, views, rank, group
+        ctx.counts = (send_counts, recv_counts)
+        ctx.aa = bool(anti_aliased)
+        ctx.hw = (H, W)
+        ctx.opac_shape = tuple(opac_logits.shape)
+        ctx.save_for_backward(means, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, recv, sorted_ids, ranges, final_T, n_contrib)
+        ctx.xy_grads = None
+        return image
+
+    @staticmethod
+    def backward(ctx, v_image):
+        from ._lib import MODE_GSPLAT, check, lib, ptr
+        from . import ops
+        L = lib()
+        means, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, recv, sorted_ids, ranges, final_T, n_contrib = ctx.saved_tensors
+        dev = means.device
+        n = means.shape[0]
+        st = torch.cuda.current_stream().cuda_stream
+        H, W = ctx.hw
+        send_counts, recv_counts = ctx.counts
+        v_image = v_image.contiguous()
+        v_recv = torch.zeros_like(recv)
+        check(L.b200gs_blend_bwd_rows(MODE_GSPLAT, W, H, ptr(ranges), ptr(sorted_ids), ptr(recv), ptr(bg), ptr(final_T), ptr(n_contrib),
+                                      ptr(v_image), 3, 1, None, ptr(v_recv), st), "b200gs_blend_bwd_rows")
+        v_send = torch.empty(sum(send_counts), ROW_FLOATS, dtype=torch.float32, device=dev)
+        dist.all_to_all_single(v_send, v_recv, output_split_sizes=send_counts, input_split_sizes=recv_counts, group=ctx.group)
+        grads = None
+        xy_grads = []
+        off = 0
+        for j, (view, rows, offsets, radii, clamped, xy) in enumerate(ctx.per_cam):
+            v_rows = v_send[off:off + send_counts[j]]
+            off += send_counts[j]
+            v_xy = torch.empty(n, 2, dtype=torch.float32, device=dev)
+            v_depth = torch.empty(n, dtype=torch.float32, device=dev)
+            v_conic = torch.empty(n, 3, dtype=torch.float32, device=dev)
+            v_opac = torch.empty(n, dtype=torch.float32, device=dev)
+            v_rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+            check(L.b200gs_unpack_rows_grad(n, ptr(radii), ptr(offsets), ptr(v_rows) if v_rows.numel() else None, ptr(v_xy), ptr(v_depth),
+                                            ptr(v_conic), None, ptr(v_opac), ptr(v_rgb), st), "b200gs_unpack_rows_grad")
+            g = ops.project_backward_raw(view, means, log_scales, raw_quats, ol, shs_dc, shs_rest, ctx.aa, radii, clamped, v_xy, v_depth,
+                                         v_conic, v_rgb, v_opac)
+            xy_grads.append(v_xy)
+            if grads is None:
+                grads = list(g)
+            else:
+                for a, b in zip(grads, g):
+                    a.add_(b)
+        ctx.xy_grads_out.extend(xy_grads)
+        v_means, v_ls, v_q, v_ol, v_dc, v_rest = grads
+        return v_means, v_ls, v_q, v_ol.reshape(ctx.opac_shape), v_dc, v_rest, None, None, None, None, None, None
+
+
+def _sharded_apply(fn, xy_grads_out, *args):
+    """apply() with a side list that backward fills with the per-camera mean2D gradients"""
+    class _Bound(fn):
+        @staticmethod
+        def forward(ctx, *a):
+            ctx.xy_grads_out = xy_grads_out
+            return fn.forward(ctx, *a)
+    return _Bound.apply(*args)
+
+
 class B200DistributedRenderer(torch.nn.Module):
     """Drop-in for ``GSplatDistributedRendererImpl.forward`` (gsplat_distributed_renderer.py:313-414): `pc` holds THIS rank's
     shard; returns this rank's image plus the per-camera projection results the distributed density controller reads
     (``distributed_vanilla_density_controller.py:16-47``)."""
 
-    def __init__(self, anti_aliased: bool = True, group=None):
+    def __init__(self, anti_aliased: bool = True, group=None, fused: bool = True):
+        """fused: when `pc` is the vanilla Gaussian model, run the whole step as one autograd node on the raw parameters
+        (_ShardedRasterize: device-side packing, rows consumed in place, one host sync); otherwise the generic path
+        below, built from the same ops the single-GPU renderers use."""
         super().__init__()
         self.anti_aliased = anti_aliased
         self.group = group
+        self.fused = fused
+
+    def _forward_fused(self, raw, viewpoint_camera, pc, bg_color, scaling_modifier):
+        from . import ops
+        from ._lib import MODE_GSPLAT
+        world = dist.get_world_size(self.group)
+        rank = dist.get_rank(self.group)
+        dev = bg_color.device
+        gathered = torch.empty(world * VIEW_FLOATS, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gathered, pack_view(viewpoint_camera), group=self.group)
+        flat = gathered.reshape(world, VIEW_FLOATS).cpu()
+        cams = [GatheredView(flat[j], dev) for j in range(world)]
+        views = []
+        for gv in cams:
+            v = ops.make_view(MODE_GSPLAT, gv.width, gv.height, fx=gv.fx, fy=gv.fy, cx=gv.cx, cy=gv.cy, viewmatrix=gv.world_to_camera,
+                              campos=gv.camera_center, scale_modifier=scaling_modifier)
+            views.append(v)
+        xy_grads: List[torch.Tensor] = []
+        fn = _ShardedRasterize
+        # the per-camera mean2D gradients (what the distributed density controller reads) are appended to this list by backward
+        _ShardedRasterize_ctx_hook = xy_grads
+        img = _sharded_apply(fn, _ShardedRasterize_ctx_hook, raw["means"], raw["scales"], raw["rotations"], raw["opacities"], raw["shs_dc"],
+                             raw["shs_rest"], bg_color, views, rank, self.group, self.anti_aliased, int(pc.active_sh_degree))
+        return {
+            "render": img.permute(2, 0, 1),
+            "cameras": cams,
+            "viewspace_points_grads": xy_grads,     # filled by backward: one [n,2] pixel-unit gradient per camera
+            "xys_grad_scale_required": True,
+        }
 
     def forward(self, viewpoint_camera, pc, bg_color: torch.Tensor, scaling_modifier=1.0, render_types: list = None, **kwargs):
         from . import ops
         from ._lib import MODE_GSPLAT
+        if self.fused:
+            from .renderers import _raw_parameters
+            raw = _raw_parameters(pc)
+            if raw is not None:
+                return self._forward_fused(raw, viewpoint_camera, pc, bg_color, scaling_modifier)
         world = dist.get_world_size(self.group)
         rank = dist.get_rank(self.group)
         dev = bg_color.device

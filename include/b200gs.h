@@ -182,6 +182,45 @@ B200GS_API int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int
                      float xy_scale_x, float xy_scale_y, float* v_xy, float* v_conic, float* v_opacity,
                      float* v_colors, float* v_xy_abs, void* stream);
 
+/* ---- [n,12] splat rows: the exchange format of the Gaussian-sharded multi-GPU renderer ------------------------------
+ * replaces the packing / splitting around the reference's all-to-all of projected splats
+ * (internal/renderers/gsplat_distributed_renderer.py:127-217): one fp32 row per VISIBLE Gaussian,
+ *   col 0-1 xy | 2 depth | 3-5 conic | 6 compensation | 7 opacity | 8-10 rgb | 11 radius (int32 bit pattern).
+ * b200gs_pack_rows: compacts the visible (radii > 0) entries of K1's outputs into rows, in index order; offsets[n] (int32,
+ *     exclusive scan of the visibility flags) is kept for the backward; d_count <- number of rows.
+ * b200gs_unpack_rows_grad: the backward of that gather: full-length per-Gaussian cotangents for b200gs_project_bwd*
+ *     (zeros for culled Gaussians).
+ * b200gs_bin_count_rows / bin_sort_rows / blend_fwd_rows / blend_bwd_rows: K2-K7 reading the rows IN PLACE (strided
+ *     access, no split copies); blend_bwd_rows accumulates into a zero-filled [n,12] gradient row buffer that goes
+ *     straight back through the all-to-all.  3 colour channels; cull != 0 enables exact tile culling. */
+#define B200GS_ROW_FLOATS 12
+#define B200GS_ROW_XY 0
+#define B200GS_ROW_DEPTH 2
+#define B200GS_ROW_CONIC 3
+#define B200GS_ROW_COMP 6
+#define B200GS_ROW_OPACITY 7
+#define B200GS_ROW_RGB 8
+#define B200GS_ROW_RADIUS 11
+B200GS_API size_t b200gs_pack_rows_workspace_bytes(int64_t n);
+B200GS_API int b200gs_pack_rows(int64_t n, const float* xy, const float* depth, const float* conic, const float* comp,
+                                const float* opacity, const float* rgb, const int32_t* radii, void* workspace, size_t workspace_bytes,
+                                int32_t* offsets, float* rows, int64_t* d_count, void* stream);
+B200GS_API int b200gs_unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offsets, const float* v_rows, float* v_xy,
+                                       float* v_depth, float* v_conic, float* v_comp, float* v_opacity, float* v_rgb, void* stream);
+B200GS_API int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull,
+                                     void* workspace_a, size_t workspace_a_bytes, int64_t* d_total, int64_t* host_total,
+                                     int32_t sync_host, void* stream);
+B200GS_API int b200gs_bin_sort_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull,
+                                    int64_t total, const int64_t* d_total, int64_t max_pairs, const void* workspace_a,
+                                    void* workspace_b, size_t workspace_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges, void* stream);
+B200GS_API int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
+                                     const float* rows, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride,
+                                     float* final_T, int32_t* n_contrib, float* alpha, void* stream);
+B200GS_API int b200gs_blend_bwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
+                                     const float* rows, const float* bg, const float* final_T, const int32_t* n_contrib,
+                                     const float* v_image, int64_t pix_stride, int64_t ch_stride, const float* v_alpha, float* v_rows,
+                                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,15 +47,22 @@ def _worker(rank, world, port, q):
         loss.backward()
 
         lo, hi = shard_range(n, world, rank)
-        shard = SyntheticGaussians({k: v[lo:hi] for k, v in raw.items()}).to(dev)
-        out = B200DistributedRenderer().to(dev)(cams[3 * rank].to_device(dev), shard, bg)
-        assert torch.equal(out["render"].detach(), imgs[rank]), float((out["render"].detach() - imgs[rank]).abs().max())
-        (out["render"] * cots[rank]).sum().backward()
-        for k, p in shard.gaussians.items():
-            ref = full.gaussians[k].grad[lo:hi]
-            err = float((p.grad - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
-            assert err < 1e-4, (k, err)
-        assert len(out["projection_results_list"]) == world and sum(out["n_received"]) > 0
+        for fused in (True, False):     # one-node fused path (raw parameters, rows consumed in place) and the generic op-by-op path
+            shard = SyntheticGaussians({k: v[lo:hi] for k, v in raw.items()}).to(dev)
+            out = B200DistributedRenderer(fused=fused).to(dev)(cams[3 * rank].to_device(dev), shard, bg)
+            if fused:
+                assert float((out["render"].detach() - imgs[rank]).abs().max()) < 2e-4   # in-kernel vs torch activations: ulps
+            else:
+                assert torch.equal(out["render"].detach(), imgs[rank]), float((out["render"].detach() - imgs[rank]).abs().max())
+            (out["render"] * cots[rank]).sum().backward()
+            for k, p in shard.gaussians.items():
+                ref = full.gaussians[k].grad[lo:hi]
+                err = float((p.grad - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+                assert err < (2e-3 if fused else 1e-4), (fused, k, err)
+            if fused:
+                assert len(out["viewspace_points_grads"]) == world and out["viewspace_points_grads"][0].shape == (hi - lo, 2)
+            else:
+                assert len(out["projection_results_list"]) == world and sum(out["n_received"]) > 0
         q.put((rank, "ok"))
     except Exception:
         import traceback
