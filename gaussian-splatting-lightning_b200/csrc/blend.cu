@@ -84,19 +84,28 @@ __device__ __forceinline__ unsigned block_mask(float mx, float my, float A, floa
     return m;
 }
 
-// Every warp compacts the staged slab [0,cnt) into the ascending list of entries whose mask has its bit set (and whose
-// index is below `limit`).  Returns the list length.  s_list[w] is private to warp w.
-__device__ __forceinline__ int build_list(const unsigned char* __restrict__ s_mask, unsigned char* __restrict__ my_list, int cnt, int limit,
-                                          int warp, unsigned lane) {
+// Staged splats live in shared memory as 48-byte records (3 x float4): one base address per splat, immediate offsets.
+//   forward : {x, y, a', b'} {c', opacity, col0, col1} {col2, col3, -, -}     (a',b',c' = conic pre-scaled by -0.5*log2e / -log2e)
+//   backward: {x, y, A, B}   {C, opacity, col0, col1}  {col2, col3, id, -}
+// Record DUMMY (index 256) has opacity 0: it fails the alpha test in every lane and pads the per-warp lists to a
+// multiple of the unroll factor, so the pixel loops are straight-line code.
+constexpr int DUMMY = BLOCK_PIX;
+constexpr int LIST_PAD = 8;
+
+// Every warp compacts the staged slab [0,top) into the ascending list of entries whose mask has its bit set.
+// my_list[LIST_PAD + k] = k-th entry; the LIST_PAD slots in front and the slots after the end hold DUMMY.
+__device__ __forceinline__ int build_list(const unsigned char* __restrict__ s_mask, unsigned short* __restrict__ my_list, int top, int warp,
+                                          unsigned lane) {
     int n = 0;
-    const int top = min(cnt, limit);
+    if (lane < LIST_PAD) my_list[lane] = (unsigned short)DUMMY;
     for (int c = 0; c < top; c += 32) {
         const int j = c + (int)lane;
         const bool hit = (j < top) && ((s_mask[j] >> warp) & 1u);
         const unsigned b = __ballot_sync(FULL, hit);
-        if (hit) my_list[n + __popc(b & ((1u << lane) - 1u))] = (unsigned char)j;
+        if (hit) my_list[LIST_PAD + n + __popc(b & ((1u << lane) - 1u))] = (unsigned short)j;
         n += __popc(b);
     }
+    if (lane < LIST_PAD) my_list[LIST_PAD + n + lane] = (unsigned short)DUMMY;
     __syncwarp();
     return n;
 }
@@ -109,11 +118,9 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_fwd_kernel(int width, int hei
                                                               float* __restrict__ image, int64_t pix_stride, int64_t ch_stride,
                                                               float* __restrict__ final_T, int32_t* __restrict__ n_contrib,
                                                               float* __restrict__ alpha_out) {
-    __shared__ float4 s_g1[BLOCK_PIX];  // x, y, -0.5*log2e*A, -log2e*B
-    __shared__ float2 s_g2[BLOCK_PIX];  // -0.5*log2e*C, opacity
-    __shared__ float4 s_col[BLOCK_PIX];
+    __shared__ float4 s_rec[(BLOCK_PIX + 1) * 3];
     __shared__ unsigned char s_mask[BLOCK_PIX];
-    __shared__ unsigned char s_list[NWARP][BLOCK_PIX];
+    __shared__ unsigned short s_list[NWARP][BLOCK_PIX + 2 * LIST_PAD];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -127,15 +134,14 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_fwd_kernel(int width, int hei
     const float pxf = float(px) + off, pyf = float(py) + off;
     const float ox = float(blockIdx.x * TILE) + off, oy = float(blockIdx.y * TILE) + off;
     const float amax = GSPLAT ? 0.999f : 0.99f;
+    if (tid < 3) s_rec[DUMMY * 3 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     const int2 range = ranges[tile];
     int todo = range.y - range.x;
     bool done = !inside;
     float T = 1.0f;
     int last = 0;
-    float C[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) C[c] = 0.f;
+    float C[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (int base = 0; todo > 0; base += BLOCK_PIX, todo -= BLOCK_PIX) {
         if (__syncthreads_and(done)) break;
@@ -146,47 +152,44 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_fwd_kernel(int width, int hei
             const float* cq = conic + int64_t(g) * st.cs;
             const float A = __ldg(cq), B = __ldg(cq + 1), Cc = __ldg(cq + 2);
             const float o = __ldg(opacity + int64_t(g) * st.os);
-            s_g1[tid] = make_float4(m.x, m.y, (-0.5f * LOG2E) * A, -LOG2E * B);
-            s_g2[tid] = make_float2((-0.5f * LOG2E) * Cc, o);
             float col[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * st.ks + c);
-            s_col[tid] = make_float4(col[0], col[1], col[2], col[3]);
+            s_rec[tid * 3 + 0] = make_float4(m.x, m.y, (-0.5f * LOG2E) * A, -LOG2E * B);
+            s_rec[tid * 3 + 1] = make_float4((-0.5f * LOG2E) * Cc, o, col[0], col[1]);
+            if (CH > 2) s_rec[tid * 3 + 2] = make_float4(col[2], col[3], 0.f, 0.f);
             s_mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
         }
         __syncthreads();
         if (__all_sync(FULL, done)) continue;  // warp finished: only keeps the block barriers company
-        const unsigned char* my_list = s_list[warp];
-        const int nl = build_list(s_mask, s_list[warp], cnt, cnt, warp, lane);
+        const unsigned short* my_list = s_list[warp] + LIST_PAD;
+        const int nl = build_list(s_mask, s_list[warp], cnt, warp, lane);
         for (int i0 = 0; i0 < nl; i0 += 4) {
             if (__all_sync(FULL, done)) break;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u;
-                if (i < nl && !done) {
-                    const int j = my_list[i];
-                    const float4 g1 = s_g1[j];
-                    const float2 g2 = s_g2[j];
-                    const float dx = g1.x - pxf, dy = g1.y - pyf;
-                    // power * log2(e) = a' dx^2 + b' dx dy + c' dy^2
-                    const float p2 = fmaf(g2.x * dy, dy, fmaf(g1.w, dy, g1.z * dx) * dx);
-                    const float a = fminf(amax, g2.y * ex2_approx(p2));
-                    if (!(p2 > 0.0f) && !(a < ALPHA_MIN)) {
-                        const float nT = fmaf(-a, T, T);
-                        if (GSPLAT ? (nT <= T_STOP) : (nT < T_STOP)) {
-                            done = true;
-                        } else {
-                            const float w = a * T;
-                            const float4 col = s_col[j];
-                            C[0] = fmaf(col.x, w, C[0]);
-                            if (CH > 1) C[1 % CH] = fmaf(col.y, w, C[1 % CH]);
-                            if (CH > 2) C[2 % CH] = fmaf(col.z, w, C[2 % CH]);
-                            if (CH > 3) C[3 % CH] = fmaf(col.w, w, C[3 % CH]);
-                            T = nT;
-                            last = base + j + 1;
-                        }
-                    }
+                const int j = my_list[i0 + u];                 // entries past nl are DUMMY (alpha 0)
+                const float4 r0 = s_rec[j * 3 + 0];
+                const float4 r1 = s_rec[j * 3 + 1];
+                const float dx = r0.x - pxf, dy = r0.y - pyf;
+                // power * log2(e) = a' dx^2 + b' dx dy + c' dy^2
+                const float p2 = fmaf(r1.x * dy, dy, fmaf(r0.w, dy, r0.z * dx) * dx);
+                const float a = fminf(amax, r1.y * ex2_approx(p2));
+                const float nT = fmaf(-a, T, T);
+                const bool ok = !done && !(p2 > 0.0f) && !(a < ALPHA_MIN);
+                const bool stop = ok && (GSPLAT ? (nT <= T_STOP) : (nT < T_STOP));
+                const bool take = ok && !stop;
+                const float w = take ? a * T : 0.f;
+                C[0] = fmaf(r1.z, w, C[0]);
+                if (CH > 1) C[1] = fmaf(r1.w, w, C[1]);
+                if (CH > 2) {
+                    const float2 r2 = *reinterpret_cast<const float2*>(&s_rec[j * 3 + 2]);
+                    C[2] = fmaf(r2.x, w, C[2]);
+                    if (CH > 3) C[3] = fmaf(r2.y, w, C[3]);
                 }
+                T = take ? nT : T;
+                last = take ? base + j + 1 : last;
+                done = done || stop;
             }
         }
     }
@@ -251,13 +254,13 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
                                                               float* __restrict__ v_xy, float* __restrict__ v_conic,
                                                               float* __restrict__ v_opacity, float* __restrict__ v_colors,
                                                               float* __restrict__ v_xy_abs) {
-    constexpr int NT = 6 + CH + (ABS ? 2 : 0);  // x y a b c o colours [|x| |y|]
-    __shared__ float4 s_g1[BLOCK_PIX];  // x, y, A, B
-    __shared__ float2 s_g2[BLOCK_PIX];  // C, opacity
-    __shared__ float4 s_col[BLOCK_PIX];
-    __shared__ int s_id[BLOCK_PIX];
+    // reduced per splat: the six moments  sum(go), sum(vs dx), sum(vs dy), sum(vs dx^2), sum(vs dx dy), sum(vs dy^2)  (vs = dL/dsigma,
+    // go = dL/dopacity) — the conic/mean gradients are linear in them, so the writer lane finishes the products once per
+    // splat instead of every lane per sample — plus the colour sums, plus |grad xy| when the absgrad side channel is on.
+    constexpr int NT = 6 + CH + (ABS ? 2 : 0);
+    __shared__ float4 s_rec[(BLOCK_PIX + 1) * 3];
     __shared__ unsigned char s_mask[BLOCK_PIX];
-    __shared__ unsigned char s_list[NWARP][BLOCK_PIX];
+    __shared__ unsigned short s_list[NWARP][BLOCK_PIX + 2 * LIST_PAD];
     __shared__ int s_wmax[NWARP];
 
     const int tid = threadIdx.x;
@@ -273,11 +276,12 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
     const float ox = float(blockIdx.x * TILE) + off, oy = float(blockIdx.y * TILE) + off;
     const float amax = GSPLAT ? 0.999f : 0.99f;
     const int64_t pix = int64_t(py) * width + px;
+    if (tid < 3) s_rec[DUMMY * 3 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     const int2 range = ranges[tile];
     const float Tf = inside ? final_T[pix] : 0.f;
     const int last = inside ? n_contrib[pix] : 0;
-    float vo[CH];
+    float vo[4] = {0.f, 0.f, 0.f, 0.f};
     float bg_dot = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -296,9 +300,7 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
     if (max_last == 0) return;
 
     float T = Tf;
-    float buf[CH];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) buf[c] = 0.f;
+    float buf[4] = {0.f, 0.f, 0.f, 0.f};
     const int my_slot = rs_slot<RB>(lane);
     const bool writer = (lane & (32 / RB - 1)) == 0;
 
@@ -308,74 +310,69 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
         __syncthreads();
         if (tid < cnt) {
             const int g = __ldg(ids + range.x + lo + tid);
-            s_id[tid] = g;
             const float2 m = __ldg(reinterpret_cast<const float2*>(xy + int64_t(g) * st.xs));
             const float* cq = conic + int64_t(g) * st.cs;
             const float A = __ldg(cq), B = __ldg(cq + 1), Cc = __ldg(cq + 2);
             const float o = __ldg(opacity + int64_t(g) * st.os);
-            s_g1[tid] = make_float4(m.x, m.y, A, B);
-            s_g2[tid] = make_float2(Cc, o);
             float col[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * st.ks + c);
-            s_col[tid] = make_float4(col[0], col[1], col[2], col[3]);
+            s_rec[tid * 3 + 0] = make_float4(m.x, m.y, A, B);
+            s_rec[tid * 3 + 1] = make_float4(Cc, o, col[0], col[1]);
+            s_rec[tid * 3 + 2] = make_float4(col[2], col[3], __int_as_float(g), 0.f);
             s_mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
         }
         __syncthreads();
         if (wmax <= lo) continue;  // this warp has no contributor in the batch
-        const unsigned char* my_list = s_list[warp];
-        const int nl = build_list(s_mask, s_list[warp], cnt, wmax - lo, warp, lane);
+        const unsigned short* my_list = s_list[warp] + LIST_PAD;   // my_list[-LIST_PAD..-1] are DUMMY
+        const int nl = build_list(s_mask, s_list[warp], min(cnt, wmax - lo), warp, lane);
         for (int ii = nl - 1; ii >= 0; ii -= RB) {
             float part[NT][RB];
             unsigned present = 0;  // bit u set when any lane of the warp has a valid sample of list entry ii-u
 #pragma unroll
             for (int u = 0; u < RB; ++u) {
-                const int i = ii - u;
-                float vs = 0.f, fac = 0.f, go = 0.f, dx = 0.f, dy = 0.f;
-                float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                float2 g2 = make_float2(0.f, 0.f);
-                bool valid = false;
-                if (i >= 0) {  // warp-uniform
-                    const int j = my_list[i];
-                    g1 = s_g1[j];
-                    g2 = s_g2[j];
-                    dx = g1.x - pxf; dy = g1.y - pyf;
-                    const float power = -0.5f * (g1.z * dx * dx + g2.x * dy * dy) - g1.w * dx * dy;
-                    const float G = __expf(power);
-                    const float a = fminf(amax, g2.y * G);
-                    valid = ((lo + j) < last) && !(power > 0.0f) && (a >= ALPHA_MIN);
-                    if (valid) {
-                        const float ra = 1.0f / (1.0f - a);
-                        T *= ra;
-                        fac = a * T;
-                        const float4 col4 = s_col[j];
-                        const float col[4] = {col4.x, col4.y, col4.z, col4.w};
-                        float v_al = tail * ra;
+                const int j = my_list[ii - u];
+                const float4 r0 = s_rec[j * 3 + 0];
+                const float4 r1 = s_rec[j * 3 + 1];
+                const float dx = r0.x - pxf, dy = r0.y - pyf;
+                const float power = -0.5f * (r0.z * dx * dx + r1.x * dy * dy) - r0.w * dx * dy;
+                const float G = __expf(power);
+                const float a = fminf(amax, r1.y * G);
+                const bool valid = ((lo + j) < last) && !(power > 0.0f) && (a >= ALPHA_MIN);
+                present |= (__ballot_sync(FULL, valid) != 0u) ? (1u << u) : 0u;
+                float vs = 0.f, fac = 0.f, go = 0.f;
+                if (valid) {
+                    const float ra = 1.0f / (1.0f - a);
+                    T *= ra;
+                    fac = a * T;
+                    float col[4] = {r1.z, r1.w, 0.f, 0.f};
+                    if (CH > 2) {
+                        const float2 r2 = *reinterpret_cast<const float2*>(&s_rec[j * 3 + 2]);
+                        col[2] = r2.x; col[3] = r2.y;
+                    }
+                    float v_al = tail * ra;
 #pragma unroll
-                        for (int c = 0; c < CH; ++c) {
-                            v_al += (col[c] * T - buf[c] * ra) * vo[c];
-                            buf[c] += col[c] * fac;
-                        }
-                        if (!GSPLAT || (g2.y * G <= 0.999f)) {
-                            vs = -g2.y * G * v_al;
-                            go = G * v_al;
-                        }
+                    for (int c = 0; c < CH; ++c) {
+                        v_al += (col[c] * T - buf[c] * ra) * vo[c];
+                        buf[c] += col[c] * fac;
+                    }
+                    if (!GSPLAT || (r1.y * G <= 0.999f)) {
+                        go = G * v_al;
+                        vs = -r1.y * go;
                     }
                 }
-                present |= (__ballot_sync(FULL, valid) != 0u) ? (1u << u) : 0u;
-                const float gx = vs * (g1.z * dx + g1.w * dy);
-                const float gy = vs * (g1.w * dx + g2.x * dy);
-                part[0][u] = gx;
-                part[1][u] = gy;
-                part[2][u] = 0.5f * vs * dx * dx;
-                part[3][u] = vs * dx * dy;
-                part[4][u] = 0.5f * vs * dy * dy;
-                part[5][u] = go;
+                const float t1 = vs * dx, t2 = vs * dy;
+                part[0][u] = go;
+                part[1][u] = t1;
+                part[2][u] = t2;
+                part[3][u] = t1 * dx;
+                part[4][u] = t1 * dy;
+                part[5][u] = t2 * dy;
 #pragma unroll
                 for (int c = 0; c < CH; ++c) part[6 + c][u] = fac * vo[c];
                 if (ABS) {
-                    part[6 + CH][u] = fabsf(gx);
-                    part[(7 + CH) % NT][u] = fabsf(gy);
+                    part[6 + CH][u] = fabsf(r0.z * t1 + r0.w * t2);
+                    part[(7 + CH) % NT][u] = fabsf(r0.w * t1 + r1.x * t2);
                 }
             }
             if (present == 0u) continue;
@@ -383,15 +380,18 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
 #pragma unroll
             for (int k = 0; k < NT; ++k) tot[k] = reduce_scatter<RB>(part[k], lane);
             if (writer && ((present >> my_slot) & 1u)) {
-                const int g = s_id[my_list[ii - my_slot]];
+                const int j = my_list[ii - my_slot];
+                const float4 r0 = s_rec[j * 3 + 0];
+                const float Cc = s_rec[j * 3 + 1].x;
+                const int g = __float_as_int(s_rec[j * 3 + 2].z);
                 float* vx = v_xy + int64_t(g) * st.xs;
                 float* vc = v_conic + int64_t(g) * st.cs;
-                atomicAdd(vx, tot[0] * sx);
-                atomicAdd(vx + 1, tot[1] * sy);
-                atomicAdd(vc, tot[2]);
-                atomicAdd(vc + 1, tot[3]);
-                atomicAdd(vc + 2, tot[4]);
-                atomicAdd(v_opacity + int64_t(g) * st.os, tot[5]);
+                atomicAdd(vx, (r0.z * tot[1] + r0.w * tot[2]) * sx);
+                atomicAdd(vx + 1, (r0.w * tot[1] + Cc * tot[2]) * sy);
+                atomicAdd(vc, 0.5f * tot[3]);
+                atomicAdd(vc + 1, tot[4]);
+                atomicAdd(vc + 2, 0.5f * tot[5]);
+                atomicAdd(v_opacity + int64_t(g) * st.os, tot[0]);
 #pragma unroll
                 for (int c = 0; c < CH; ++c) atomicAdd(v_colors + int64_t(g) * st.ks + c, tot[6 + c]);
                 if (ABS) {
