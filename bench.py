@@ -206,6 +206,7 @@ def workload_config(args, parallelism):
 
 # bytes per view, SURVEY.md §8(d) / BASELINE.md §5 (V visible, I pairs, P pixels, N total; SH degree 3)
 def algorithmic_bytes(stage, N, V, I, P, n_tiles):
+    """I = (tile, Gaussian) pairs the stage actually processes (after exact tile culling)."""
     return {
         "project_fwd": V * 268 + N * 16,
         "bin_count": N * (16 + 4 * 16 + 8 + 12),      # keys+ids+tiles write, 4 radix passes of 8 B pairs (r+w), scan
@@ -335,7 +336,7 @@ def main():
     hbm_peak, peak_src = peaks()
     kernels = {}
     for k, ms in stage_ms.items():
-        b = algorithmic_bytes(k, N, V, I, P, gx * gy)
+        b = algorithmic_bytes(k, N, V, I_culled, P, gx * gy)
         kernels[k] = {"ms": round(ms, 4), "alg_bytes": b, "gbs": round(b / (ms * 1e-3) / 1e9, 1), "launches": LAUNCHES_PER_STEP.get(k, 1)}
     top = max(stage_ms, key=stage_ms.get)
     ach = kernels[top]["gbs"]

@@ -155,19 +155,22 @@ class _ShardedRasterize(torch.autograd.Function):
         ws_a = torch.empty(L.b200gs_bin_count_workspace_bytes(R), dtype=torch.uint8, device=dev)
         d_total = torch.empty(1, dtype=torch.int64, device=dev)
         host_total = torch.zeros(1, dtype=torch.int64).pin_memory()
-        check(L.b200gs_bin_count_rows(MODE_GSPLAT, W, H, R, ptr(recv), 1, ptr(ws_a), ws_a.numel(), ptr(d_total), host_total.data_ptr(), 1, st),
-              "b200gs_bin_count_rows")
+        with ops._stage("bin_count"):
+            check(L.b200gs_bin_count_rows(MODE_GSPLAT, W, H, R, ptr(recv), 1, ptr(ws_a), ws_a.numel(), ptr(d_total), host_total.data_ptr(), 1, st),
+                  "b200gs_bin_count_rows")
         total = int(host_total[0])
         sorted_ids = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
         ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
         ws_b = torch.empty(L.b200gs_bin_sort_workspace_bytes(R, total, W, H), dtype=torch.uint8, device=dev)
-        check(L.b200gs_bin_sort_rows(MODE_GSPLAT, W, H, R, ptr(recv), 1, total, ptr(d_total), total, ptr(ws_a), ptr(ws_b), ws_b.numel(),
-                                     ptr(sorted_ids), ptr(ranges), st), "b200gs_bin_sort_rows")
+        with ops._stage("bin_sort"):
+            check(L.b200gs_bin_sort_rows(MODE_GSPLAT, W, H, R, ptr(recv), 1, total, ptr(d_total), total, ptr(ws_a), ptr(ws_b), ws_b.numel(),
+                                         ptr(sorted_ids), ptr(ranges), st), "b200gs_bin_sort_rows")
         image = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
         final_T = torch.empty(H, W, dtype=torch.float32, device=dev)
         n_contrib = torch.empty(H, W, dtype=torch.int32, device=dev)
-        check(L.b200gs_blend_fwd_rows(MODE_GSPLAT, W, H, ptr(ranges), ptr(sorted_ids), ptr(recv), ptr(bg), ptr(image), 3, 1, ptr(final_T),
-                                      ptr(n_contrib), None, st), "b200gs_blend_fwd_rows")
+        with ops._stage("blend_fwd"):
+            check(L.b200gs_blend_fwd_rows(MODE_GSPLAT, W, H, ptr(ranges), ptr(sorted_ids), ptr(recv), ptr(bg), ptr(image), 3, 1, ptr(final_T),
+                                          ptr(n_contrib), None, st), "b200gs_blend_fwd_rows")
         ctx.per_cam, ctx.views, ctx.rank, ctx.group = per_cam, views, rank, group
         ctx.counts = (send_counts, recv_counts)
         ctx.aa = bool(anti_aliased)
@@ -190,8 +193,9 @@ class _ShardedRasterize(torch.autograd.Function):
         send_counts, recv_counts = ctx.counts
         v_image = v_image.contiguous()
         v_recv = torch.zeros_like(recv)
-        check(L.b200gs_blend_bwd_rows(MODE_GSPLAT, W, H, ptr(ranges), ptr(sorted_ids), ptr(recv), ptr(bg), ptr(final_T), ptr(n_contrib),
-                                      ptr(v_image), 3, 1, None, ptr(v_recv), st), "b200gs_blend_bwd_rows")
+        with ops._stage("blend_bwd"):
+            check(L.b200gs_blend_bwd_rows(MODE_GSPLAT, W, H, ptr(ranges), ptr(sorted_ids), ptr(recv), ptr(bg), ptr(final_T), ptr(n_contrib),
+                                          ptr(v_image), 3, 1, None, ptr(v_recv), st), "b200gs_blend_bwd_rows")
         v_send = torch.empty(sum(send_counts), ROW_FLOATS, dtype=torch.float32, device=dev)
         dist.all_to_all_single(v_send, v_recv, output_split_sizes=send_counts, input_split_sizes=recv_counts, group=ctx.group)
         grads = None
