@@ -85,9 +85,12 @@ LayoutB make_layout_b(int64_t max_pairs) {
     L.pkeys_in = take(pp * 4);
     L.pkeys_out = take(pp * 4);
     L.pvals_in = take(pp * 4);
-    size_t t_psort = 0;
+    size_t t_psort = 0, t_psort16 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t_psort, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
                                     (int32_t*)nullptr, (int)pp, 0, 16);
+    cub::DeviceRadixSort::SortPairs(nullptr, t_psort16, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int)pp, 0, 16);
+    if (t_psort16 > t_psort) t_psort = t_psort16;
     L.temp_bytes = t_psort;
     L.temp = take(t_psort);
     L.total = take.off;
@@ -179,10 +182,26 @@ constexpr int BIG_RECT = 512;   // Gaussians covering more tiles than this are w
 
 // Shared walk over the rect of one Gaussian per lane.  EMIT=false: returns the number of kept tiles.
 // EMIT=true: writes (tile id, g) pairs from `start`, row-major like the reference's emission order.
-template <bool GSPLAT, bool EMIT>
+// Sinks for walk_rect: count only, or stage (tile id, g) pairs of the output window [lo, lo+n) in shared memory.
+struct CountSink {
+    static constexpr bool kWrites = false;
+    __device__ __forceinline__ void put(int64_t, int, int) const {}
+};
+template <typename KT>
+struct StageSink {
+    static constexpr bool kWrites = true;
+    KT* k; int32_t* v; int64_t lo; int n;
+    __device__ __forceinline__ void put(int64_t o, int tile, int g) const {
+        const int64_t r = o - lo;
+        if (r >= 0 && r < n) { k[r] = (KT)tile; v[r] = g; }
+    }
+};
+
+// Shared walk over the rect of one Gaussian per lane.  Returns the number of kept tiles; a writing sink receives the
+// (tile id, g) pairs at output offsets start, start+1, ... in row-major order (the reference's emission order).
+template <bool GSPLAT, typename Sink>
 __device__ __forceinline__ int walk_rect(unsigned lane, bool active, int g, const CullE& e, int x0, int y0, int x1, int y1,
-                                         int grid_x, int64_t start, int64_t max_pairs, uint32_t* __restrict__ pkeys,
-                                         int32_t* __restrict__ pvals) {
+                                         int grid_x, int64_t start, const Sink& sink) {
     const int t_rect = active ? (x1 - x0) * (y1 - y0) : 0;
     const bool none = (e.mode == 2);
     int kept = 0;
@@ -190,11 +209,8 @@ __device__ __forceinline__ int walk_rect(unsigned lane, bool active, int g, cons
         for (int ty = y0; ty < y1; ++ty) {
             int a, b;
             if (!row_span<GSPLAT>(e, ty, x0, x1, a, b)) continue;
-            if (EMIT) {
-                for (int tx = a; tx < b; ++tx) {
-                    const int64_t o = start + kept + (tx - a);
-                    if (o < max_pairs) { pkeys[o] = (uint32_t)(ty * grid_x + tx); pvals[o] = g; }
-                }
+            if (Sink::kWrites) {
+                for (int tx = a; tx < b; ++tx) sink.put(start + kept + (tx - a), ty * grid_x + tx, g);
             }
             kept += b - a;
         }
@@ -217,11 +233,8 @@ __device__ __forceinline__ int walk_rect(unsigned lane, bool active, int g, cons
         for (int ty = by0; ty < by1; ++ty) {
             int a, b;
             if (!row_span<GSPLAT>(be, ty, bx0, bx1, a, b)) continue;
-            if (EMIT) {
-                for (int tx = a + (int)lane; tx < b; tx += 32) {
-                    const int64_t o = bstart + bkept + (tx - a);
-                    if (o < max_pairs) { pkeys[o] = (uint32_t)(ty * grid_x + tx); pvals[o] = bg; }
-                }
+            if (Sink::kWrites) {
+                for (int tx = a + (int)lane; tx < b; tx += 32) sink.put(bstart + bkept + (tx - a), ty * grid_x + tx, bg);
             }
             bkept += b - a;
         }
@@ -248,7 +261,7 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
             active = (x1 - x0) * (y1 - y0) > 0;
         }
     }
-    const int t = walk_rect<GSPLAT, false>(lane, active, (int)i, e, x0, y0, x1, y1, grid_x, 0, 0, nullptr, nullptr);
+    const int t = walk_rect<GSPLAT>(lane, active, (int)i, e, x0, y0, x1, y1, grid_x, 0, CountSink{});
     if (i < n) {
         keys[i] = t > 0 ? __float_as_uint(src.get_depth(i)) : 0xFFFFFFFFu;
         ids[i] = (int32_t)i;
@@ -260,40 +273,59 @@ __global__ void write_total_kernel(int64_t n, const int64_t* __restrict__ offset
     *d_total = n > 0 ? offsets[n - 1] : 0;
 }
 
-// One lane per depth-ranked Gaussian; Gaussians with very large rects are written by the whole warp.
-template <bool GSPLAT>
+// One lane per depth-ranked Gaussian.  The 256 consecutive ranks of a block own one contiguous window of the pair arrays
+// (offsets are an inclusive scan in depth order), so the pairs are staged in shared memory and written back with
+// coalesced stores, EMIT_CHUNK entries at a time (one chunk covers a typical block: 256 x ~13 pairs).
+constexpr int EMIT_CHUNK = 4096;
+
+template <bool GSPLAT, typename KT>
 __global__ void __launch_bounds__(256) emit_pairs_kernel(int64_t n, int grid_x, int grid_y, int64_t max_pairs, const BinSrc src,
                                                          const int32_t* __restrict__ order, const int32_t* __restrict__ tiles,
-                                                         const int64_t* __restrict__ offsets, uint32_t* __restrict__ pkeys,
+                                                         const int64_t* __restrict__ offsets, KT* __restrict__ pkeys,
                                                          int32_t* __restrict__ pvals) {
-    const int64_t rnk = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    __shared__ KT s_k[EMIT_CHUNK];
+    __shared__ int32_t s_v[EMIT_CHUNK];
+    const int64_t rank0 = int64_t(blockIdx.x) * blockDim.x;
+    const int64_t rnk = rank0 + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
-    int g = -1, x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    int g = -1, x0 = 0, y0 = 0, x1 = 0, y1 = 0, t = 0;
     int64_t start = 0;
-    bool active = false;
     CullE e{};
     if (rnk < n) {
         g = order[rnk];
-        const int t = tiles[g];
+        t = tiles[g];
         if (t > 0) {
             const float2 p = src.get_xy(g);
             tile_rect<GSPLAT>(p.x, p.y, (float)src.get_radius(g), grid_x, grid_y, x0, y0, x1, y1);
             e = load_cull(p, src, g);
             start = offsets[rnk] - t;
-            active = true;
         }
     }
-    walk_rect<GSPLAT, true>(lane, active, g, e, x0, y0, x1, y1, grid_x, start, max_pairs, pkeys, pvals);
+    const int64_t last_rank = min(rank0 + (int64_t)blockDim.x, n) - 1;
+    const int64_t block_lo = offsets[rank0] - tiles[order[rank0]];
+    const int64_t block_hi = min(offsets[last_rank], max_pairs);
+    for (int64_t lo = block_lo; lo < block_hi; lo += EMIT_CHUNK) {
+        const int cn = (int)min((int64_t)EMIT_CHUNK, block_hi - lo);
+        const bool active = (t > 0) && (start < lo + cn) && (start + t > lo);
+        walk_rect<GSPLAT>(lane, active, g, e, x0, y0, x1, y1, grid_x, start, StageSink<KT>{s_k, s_v, lo, cn});
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn; i += blockDim.x) {
+            pkeys[lo + i] = s_k[i];
+            pvals[lo + i] = s_v[i];
+        }
+        __syncthreads();
+    }
 }
 
 // capacity mode: entries [total, cap) of the key buffer get a key above every tile id so they sort to the end
-__global__ void __launch_bounds__(256) pad_keys_kernel(int64_t cap, const int64_t* __restrict__ d_total, uint32_t* __restrict__ keys,
-                                                       uint32_t pad) {
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < cap && i >= *d_total) keys[i] = pad;
+template <typename KT>
+__global__ void __launch_bounds__(256) pad_keys_kernel(int64_t cap, const int64_t* __restrict__ d_total, KT* __restrict__ keys, KT pad) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = *d_total + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < cap; i += stride) keys[i] = pad;
 }
 
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t cap, const int64_t* __restrict__ d_total, const uint32_t* __restrict__ keys,
+template <typename KT>
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t cap, const int64_t* __restrict__ d_total, const KT* __restrict__ keys,
                                                           int2* __restrict__ ranges) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = min(cap, *d_total);
@@ -309,6 +341,33 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t cap, const int
         }
     }
     if (i == total - 1) ranges[cur].y = (int)total;
+}
+
+template <typename KT>
+int emit_sort_ranges(int mode, int64_t n, int grid_x, int grid_y, int n_tiles, const BinSrc& src, bool capacity_mode, int64_t items,
+                     const int64_t* d_total, int64_t max_pairs, const int32_t* order, const int32_t* tiles, const int64_t* offsets,
+                     void* keys_in, void* keys_out, int32_t* pvals_in, void* temp, size_t temp_bytes, int32_t* sorted_ids,
+                     int32_t* tile_ranges, cudaStream_t s) {
+    KT* kin = (KT*)keys_in;
+    KT* kout = (KT*)keys_out;
+    const unsigned blocks = (unsigned)div_up64(n, 256);
+    if (mode == B200GS_MODE_GSPLAT)
+        emit_pairs_kernel<true, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, src, order, tiles, offsets, kin, pvals_in);
+    else
+        emit_pairs_kernel<false, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, src, order, tiles, offsets, kin, pvals_in);
+    B200GS_LAUNCH_CHECK();
+    int bits = tile_bits_for(n_tiles);
+    if (capacity_mode) {
+        pad_keys_kernel<KT><<<512, 256, 0, s>>>(items, d_total, kin, (KT)(1u << bits));
+        B200GS_LAUNCH_CHECK();
+        bits += 1;
+    }
+    size_t tb = temp_bytes;
+    // temp was sized for max_pairs 32-bit keys; cub's requirement is monotone in the item count and key width
+    B200GS_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, kin, kout, pvals_in, sorted_ids, (int)items, 0, bits, s));
+    tile_ranges_kernel<KT><<<(unsigned)div_up64(items, 256), 256, 0, s>>>(items, d_total, kout, (int2*)tile_ranges);
+    B200GS_LAUNCH_CHECK();
+    return B200GS_OK;
 }
 
 }  // namespace
@@ -393,25 +452,13 @@ int bin_sort(int mode, int width, int height, int64_t n, int row_stride, const f
     int32_t* pvals_in = (int32_t*)(w + L.pvals_in);
     const unsigned blocks = (unsigned)div_up64(n, 256);
     const BinSrc src = make_src(row_stride, xy, nullptr, radii, conic, opacity);
-    if (mode == B200GS_MODE_GSPLAT)
-        emit_pairs_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, src, order, tiles, offsets, pkeys_in, pvals_in);
-    else
-        emit_pairs_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, src, order, tiles, offsets, pkeys_in, pvals_in);
-    B200GS_LAUNCH_CHECK();
-    int bits = tile_bits_for(n_tiles);
-    if (capacity_mode) {
-        pad_keys_kernel<<<(unsigned)div_up64(items, 256), 256, 0, s>>>(items, d_total, pkeys_in, 1u << bits);
-        B200GS_LAUNCH_CHECK();
-        bits += 1;
-    }
-    size_t tb = L.temp_bytes;
-    // temp was sized for max_pairs items; cub's requirement is monotone in the item count
-    B200GS_CUDA(cub::DeviceRadixSort::SortPairs(w + L.temp, tb, pkeys_in, pkeys_out, pvals_in, sorted_ids, (int)items, 0, bits, s));
-    tile_ranges_kernel<<<(unsigned)div_up64(items, 256), 256, 0, s>>>(items, d_total, pkeys_out, (int2*)tile_ranges);
-    B200GS_LAUNCH_CHECK();
-    return B200GS_OK;
+    const int bits = tile_bits_for(n_tiles) + (capacity_mode ? 1 : 0);
+    if (bits <= 16)   // every image up to ~4K: 16-bit tile keys -> 12 B instead of 16 B per pair and radix pass
+        return emit_sort_ranges<uint16_t>(mode, n, grid_x, grid_y, n_tiles, src, capacity_mode, items, d_total, max_pairs, order, tiles,
+                                          offsets, pkeys_in, pkeys_out, pvals_in, w + L.temp, L.temp_bytes, sorted_ids, tile_ranges, s);
+    return emit_sort_ranges<uint32_t>(mode, n, grid_x, grid_y, n_tiles, src, capacity_mode, items, d_total, max_pairs, order, tiles,
+                                      offsets, pkeys_in, pkeys_out, pvals_in, w + L.temp, L.temp_bytes, sorted_ids, tile_ranges, s);
 }
-
 
 // ---- row packing for the Gaussian-sharded exchange -------------------------------------------------------------------
 namespace {

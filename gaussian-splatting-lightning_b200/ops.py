@@ -146,7 +146,7 @@ _host_total = None
 _last_total = {}       # (mode, width, height, n) -> pair count of the previous view: sizes the next view's buffers
 
 TILE_CULLING = True    # exact (tile, splat) culling in K2/K3; False reproduces the reference's full 3-sigma-rect pair list
-LAZY_SLACK = 1.25      # lazy mode: capacity = slack x previous pair count
+LAZY_SLACK = 1.15      # lazy mode: capacity = slack x previous pair count
 
 
 def bin_gaussians(mode: int, width: int, height: int, xy: torch.Tensor, depth: torch.Tensor, radii: torch.Tensor,
