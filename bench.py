@@ -340,6 +340,14 @@ def main():
         kernels[k] = {"ms": round(ms, 4), "alg_bytes": b, "gbs": round(b / (ms * 1e-3) / 1e9, 1), "launches": LAUNCHES_PER_STEP.get(k, 1)}
     top = max(stage_ms, key=stage_ms.get)
     ach = kernels[top]["gbs"]
+    traffic = None
+    try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/summarize.py)
+        prof = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
+        if prof:
+            with open(os.path.join(ROOT, "profiles", prof[-1])) as f:
+                traffic = json.load(f).get(top)
+    except Exception:
+        traffic = None
     views_per_s = args.steps * world / (ms_total * 1e-3)
     e2e_vps = args.steps * world / (ms_e2e * 1e-3)
     launches = sum(LAUNCHES_PER_STEP.values()) * args.steps
@@ -352,7 +360,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "peak_source": peak_src,
                      "note": "blend kernels are SM-issue (FP32+MUFU) bound, not HBM bound (SURVEY §8d); HBM fraction reported as asked"},
         "kernels": kernels,
         "scene": {"N": N, "V": V, "I": I, "I_after_exact_culling": I_culled, "P": P, "stage_sum_ms": round(sum(stage_ms.values()), 4)},
