@@ -244,7 +244,7 @@ __device__ __forceinline__ float reduce_scatter<4>(const float* p, unsigned lane
 }
 
 template <int CH, bool GSPLAT, bool ABS, int RB>
-__global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
+__global__ void __launch_bounds__(BLOCK_PIX, (RB == 4 && !ABS) ? 4 : 1) blend_bwd_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
                                                               const int32_t* __restrict__ ids, const SplatStrides st, const float* __restrict__ xy,
                                                               const float* __restrict__ conic, const float* __restrict__ opacity,
                                                               const float* __restrict__ colors, const float* __restrict__ bg,
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
     if (max_last == 0) return;
 
     float T = Tf;
-    float buf[4] = {0.f, 0.f, 0.f, 0.f};
+    float D = 0.f;   // <colour accumulated behind the current splat, v_image> for this pixel
     const int my_slot = rs_slot<RB>(lane);
     const bool writer = (lane & (32 / RB - 1)) == 0;
 
@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
             float col[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * st.ks + c);
-            s_rec[tid * 3 + 0] = make_float4(m.x, m.y, A, B);
-            s_rec[tid * 3 + 1] = make_float4(Cc, o, col[0], col[1]);
+            s_rec[tid * 3 + 0] = make_float4(m.x, m.y, (-0.5f * LOG2E) * A, -LOG2E * B);
+            s_rec[tid * 3 + 1] = make_float4((-0.5f * LOG2E) * Cc, o, col[0], col[1]);
             s_rec[tid * 3 + 2] = make_float4(col[2], col[3], __int_as_float(g), 0.f);
             s_mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
         }
@@ -335,27 +335,27 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
                 const float4 r0 = s_rec[j * 3 + 0];
                 const float4 r1 = s_rec[j * 3 + 1];
                 const float dx = r0.x - pxf, dy = r0.y - pyf;
-                const float power = -0.5f * (r0.z * dx * dx + r1.x * dy * dy) - r0.w * dx * dy;
-                const float G = __expf(power);
+                // same arithmetic as the forward: power * log2(e) = a' dx^2 + b' dx dy + c' dy^2
+                const float p2 = fmaf(r1.x * dy, dy, fmaf(r0.w, dy, r0.z * dx) * dx);
+                const float G = ex2_approx(p2);
                 const float a = fminf(amax, r1.y * G);
-                const bool valid = ((lo + j) < last) && !(power > 0.0f) && (a >= ALPHA_MIN);
+                const bool valid = ((lo + j) < last) && !(p2 > 0.0f) && (a >= ALPHA_MIN);
                 present |= (__ballot_sync(FULL, valid) != 0u) ? (1u << u) : 0u;
                 float vs = 0.f, fac = 0.f, go = 0.f;
                 if (valid) {
                     const float ra = 1.0f / (1.0f - a);
                     T *= ra;
                     fac = a * T;
-                    float col[4] = {r1.z, r1.w, 0.f, 0.f};
+                    float S = r1.z * vo[0];
+                    if (CH > 1) S = fmaf(r1.w, vo[1], S);
                     if (CH > 2) {
                         const float2 r2 = *reinterpret_cast<const float2*>(&s_rec[j * 3 + 2]);
-                        col[2] = r2.x; col[3] = r2.y;
+                        S = fmaf(r2.x, vo[2], S);
+                        if (CH > 3) S = fmaf(r2.y, vo[3], S);
                     }
-                    float v_al = tail * ra;
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                        v_al += (col[c] * T - buf[c] * ra) * vo[c];
-                        buf[c] += col[c] * fac;
-                    }
+                    // dL/dalpha = T <c, v> - (<colour behind, v> + T_final (bg.v - v_alpha)) / (1 - alpha);  D = <colour behind, v>
+                    const float v_al = fmaf(T, S, ra * (tail - D));
+                    D = fmaf(fac, S, D);
                     if (!GSPLAT || (r1.y * G <= 0.999f)) {
                         go = G * v_al;
                         vs = -r1.y * go;
@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
 #pragma unroll
                 for (int c = 0; c < CH; ++c) part[6 + c][u] = fac * vo[c];
                 if (ABS) {
-                    part[6 + CH][u] = fabsf(r0.z * t1 + r0.w * t2);
-                    part[(7 + CH) % NT][u] = fabsf(r0.w * t1 + r1.x * t2);
+                    part[6 + CH][u] = fabsf(r0.z * t1 + 0.5f * r0.w * t2) * (2.0f / LOG2E);
+                    part[(7 + CH) % NT][u] = fabsf(0.5f * r0.w * t1 + r1.x * t2) * (2.0f / LOG2E);
                 }
             }
             if (present == 0u) continue;
@@ -382,12 +382,12 @@ __global__ void __launch_bounds__(BLOCK_PIX) blend_bwd_kernel(int width, int hei
             if (writer && ((present >> my_slot) & 1u)) {
                 const int j = my_list[ii - my_slot];
                 const float4 r0 = s_rec[j * 3 + 0];
-                const float Cc = s_rec[j * 3 + 1].x;
+                const float A = r0.z * (-2.0f / LOG2E), B = r0.w * (-1.0f / LOG2E), Cc = s_rec[j * 3 + 1].x * (-2.0f / LOG2E);
                 const int g = __float_as_int(s_rec[j * 3 + 2].z);
                 float* vx = v_xy + int64_t(g) * st.xs;
                 float* vc = v_conic + int64_t(g) * st.cs;
-                atomicAdd(vx, (r0.z * tot[1] + r0.w * tot[2]) * sx);
-                atomicAdd(vx + 1, (r0.w * tot[1] + Cc * tot[2]) * sy);
+                atomicAdd(vx, (A * tot[1] + B * tot[2]) * sx);
+                atomicAdd(vx + 1, (B * tot[1] + Cc * tot[2]) * sy);
                 atomicAdd(vc, 0.5f * tot[3]);
                 atomicAdd(vc + 1, tot[4]);
                 atomicAdd(vc + 2, 0.5f * tot[5]);
