@@ -468,6 +468,45 @@ class _ProjectGaussians(torch.autograd.Function):
         return v_means, v_scales, v_quats, None
 
 
+class _ProjectGaussiansRaw(torch.autograd.Function):
+    """gsplat-mode K1 / K8 on the model's RAW parameters (activations, compensation-scaled opacity and SH colours fused):
+    -> xys, depths, radii, conics, tiles, opacity_for_blend [N], rgbs [N,3].  `xys` stays a graph tensor so the
+    renderer's ``viewspace_points.retain_grad()`` contract holds."""
+
+    @staticmethod
+    def forward(ctx, means, log_scales, raw_quats, opac_logits, shs_dc, shs_rest, view: B200gsView, anti_aliased: bool):
+        means = _f32c(means, "means")
+        log_scales = _f32c(log_scales, "scales")
+        raw_quats = _f32c(raw_quats, "rotations")
+        ol = _f32c(opac_logits, "opacities").reshape(-1)
+        shs_dc = _f32c(shs_dc, "shs_dc")
+        shs_rest = _f32c(shs_rest, "shs_rest")
+        view = _copy_view(view, sh_stride=int(shs_dc.shape[1] + shs_rest.shape[1]))
+        xy, depth, radii, conic, _, tiles, rgb, clamped, opac = project_forward_raw(view, means, log_scales, raw_quats, ol, shs_dc, shs_rest,
+                                                                                  anti_aliased)
+        ctx.view, ctx.aa, ctx.opac_shape = view, bool(anti_aliased), tuple(opac_logits.shape)
+        ctx.save_for_backward(means, log_scales, raw_quats, ol, shs_dc, shs_rest, radii, clamped)
+        ctx.mark_non_differentiable(radii, tiles)
+        return xy, depth, radii, conic, tiles, opac, rgb
+
+    @staticmethod
+    def backward(ctx, v_xy, v_depth, _v_radii, v_conic, _v_tiles, v_opac, v_rgb):
+        means, log_scales, raw_quats, ol, shs_dc, shs_rest, radii, clamped = ctx.saved_tensors
+        n, dev = means.shape[0], means.device
+
+        def z(t, shape):
+            return torch.zeros(shape, dtype=torch.float32, device=dev) if t is None else _f32c(t, "grad")
+
+        v_means, v_ls, v_q, v_ol, v_dc, v_rest = project_backward_raw(
+            ctx.view, means, log_scales, raw_quats, ol, shs_dc, shs_rest, ctx.aa, radii, clamped, z(v_xy, (n, 2)),
+            None if v_depth is None else _f32c(v_depth, "grad"), z(v_conic, (n, 3)), z(v_rgb, (n, 3)), z(v_opac, (n,)))
+        return v_means, v_ls, v_q, v_ol.reshape(ctx.opac_shape), v_dc, v_rest, None, None
+
+
+def project_gaussians_raw(means, log_scales, raw_quats, opacity_logits, shs_dc, shs_rest, view: B200gsView, anti_aliased: bool = True):
+    return _ProjectGaussiansRaw.apply(means, log_scales, raw_quats, opacity_logits, shs_dc, shs_rest, view, anti_aliased)
+
+
 def project_gaussians(means3d, scales, glob_scale, quats, viewmat, fx, fy, cx, cy, img_height, img_width, block_width=16,
                       clip_thresh=0.01, filter_2d_kernel_size=0.3, view: Optional[B200gsView] = None):
     """gsplat v0 ``project_gaussians``: -> (xys [N,2], depths [N], radii int32 [N], conics [N,3], compensation [N],

@@ -237,7 +237,7 @@ class B200GSplatRenderer(Renderer):
     }
 
     def __init__(self, block_size: int = DEFAULT_BLOCK_SIZE, anti_aliased: bool = DEFAULT_ANTI_ALIASED_STATUS,
-                 kernel_size: float = 0.3, cache_cameras: bool = True) -> None:
+                 kernel_size: float = 0.3, cache_cameras: bool = True, fused_activations: bool = True) -> None:
         super().__init__()
         if block_size != DEFAULT_BLOCK_SIZE:
             raise ValueError("b200gs supports block_size 16 only")
@@ -245,6 +245,7 @@ class B200GSplatRenderer(Renderer):
         self.anti_aliased = anti_aliased
         self.filter_2d_kernel_size = kernel_size
         self.cache_cameras = cache_cameras
+        self.fused_activations = fused_activations   # rgb-only renders of a vanilla Gaussian model: activations + SH inside K1/K8
 
     def parse_render_types(self, render_types: list) -> int:
         if render_types is None:
@@ -268,6 +269,24 @@ class B200GSplatRenderer(Renderer):
     def forward(self, viewpoint_camera, pc, bg_color: torch.Tensor, scaling_modifier=1.0, render_types: list = None, **kwargs):
         bits = self.parse_render_types(render_types)
         img_height, img_width = int(viewpoint_camera.height), int(viewpoint_camera.width)
+        raw = _raw_parameters(pc) if (self.fused_activations and bits == self._RGB_REQUIRED) else None
+        if raw is not None:
+            view = camera_view(viewpoint_camera, MODE_GSPLAT, self.cache_cameras)
+            view = _view_with(view, scale_modifier=float(scaling_modifier), eps2d=float(getattr(self, "filter_2d_kernel_size", 0.3)),
+                              sh_degree=int(pc.active_sh_degree))
+            xys, depths, radii, conics, tiles, opac, rgbs = ops.project_gaussians_raw(
+                raw["means"], raw["scales"], raw["rotations"], raw["opacities"], raw["shs_dc"], raw["shs_rest"], view, self.anti_aliased)
+            rgb = ops.rasterize_gaussians(xys, depths, radii, conics, tiles, rgbs, opac, img_height, img_width, self.block_size,
+                                          bg_color, False).permute(2, 0, 1)
+            none = None
+            return {
+                "render": rgb, "alpha": none, "acc_depth": none, "acc_depth_inverted": none, "exp_depth": none,
+                "exp_depth_inverted": none, "inverse_depth": none, "hard_depth": none, "hard_inverse_depth": none,
+                "viewspace_points": xys,
+                "viewspace_points_grad_scale": 0.5 * torch.tensor([[img_width, img_height]]).to(xys),
+                "visibility_filter": radii > 0,
+                "radii": radii,
+            }
         quats = pc.get_rotation
         quats = quats / quats.norm(dim=-1, keepdim=True)  # gsplat_renderer.py:68
         xys, depths, radii, conics, comp, num_tiles_hit, cov3d = self._project(
