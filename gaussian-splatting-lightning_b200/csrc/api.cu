@@ -106,6 +106,26 @@ int b200gs_project_bwd_raw(const B200gsView* view, int64_t n, const float* means
                                   v_opacity_logits, v_shs_dc, v_shs_rest, (cudaStream_t)stream);
 }
 
+int b200gs_project_bwd_rows(const B200gsView* view, int64_t n, const float* means, const float* log_scales, const float* raw_quats,
+                            const float* opacity_logits, const float* shs_dc, const float* shs_rest, int32_t anti_aliased,
+                            const int32_t* radii, const uint8_t* clamped, const int32_t* row_offsets, const float* v_rows,
+                            int32_t accumulate, float* v_means, float* v_log_scales, float* v_raw_quats, float* v_opacity_logits,
+                            float* v_shs_dc, float* v_shs_rest, void* stream) {
+    int rc = check_view(view, true);
+    if (rc) return rc;
+    B200GS_CHECK_ARG(n >= 0, "n < 0");
+    if (n > 0) {
+        B200GS_CHECK_ARG(means && log_scales && raw_quats && opacity_logits && shs_dc && radii && clamped && row_offsets, "NULL input pointer");
+        B200GS_CHECK_ARG(view->sh_stride == 1 || (shs_rest && v_shs_rest), "shs_rest / v_shs_rest required when sh_stride > 1");
+        B200GS_CHECK_ARG(v_means && v_log_scales && v_raw_quats && v_opacity_logits && v_shs_dc, "NULL output pointer");
+    }
+    static const float dummy = 0.f;   // v_rows may be NULL when no Gaussian of the shard is visible: never dereferenced then
+    return launch_project_bwd_raw(*view, n, means, log_scales, raw_quats, opacity_logits, shs_dc, shs_rest, anti_aliased, radii,
+                                  clamped, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v_means, v_log_scales, v_raw_quats,
+                                  v_opacity_logits, v_shs_dc, v_shs_rest, (cudaStream_t)stream, v_rows ? v_rows : &dummy, row_offsets,
+                                  accumulate);
+}
+
 int b200gs_sh_fwd(int32_t degree, int32_t sh_stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, void* stream) {
     B200GS_CHECK_ARG(degree >= 0 && degree <= 3, "degree must be 0..3");
     B200GS_CHECK_ARG(sh_stride >= (degree + 1) * (degree + 1), "sh_stride < (degree+1)^2");

@@ -86,7 +86,7 @@ int launch_project_bwd_raw(const B200gsView& v, int64_t n, const float* means, c
                            const int32_t* radii, const uint8_t* clamped, const float* v_xy, const float* v_depth,
                            const float* v_conic, const float* v_comp, const float* v_rgb, const float* v_opac, float* v_means,
                            float* v_scales, float* v_quats, float* v_opac_logit, float* v_shs_dc, float* v_shs_rest,
-                           cudaStream_t s);
+                           cudaStream_t s, const float* v_rows = nullptr, const int32_t* row_offsets = nullptr, int accumulate = 0);
 int launch_sh_fwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, cudaStream_t s);
 int launch_sh_bwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, const float* v_rgb,
                   float* v_coeffs, float* v_dirs, cudaStream_t s);

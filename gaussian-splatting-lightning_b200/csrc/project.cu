@@ -188,6 +188,11 @@ struct RawIO {
     float* v_opac_logit;     // [n]
     float* v_shs_rest;       // [n, sh_stride-1, 3]; `v_shs` then receives the dc gradient [n,1,3]
     int anti_aliased;
+    // backward of the sharded renderer: cotangents come as compacted [V,12] rows (b200gs.h row layout) addressed through
+    // row_offsets[n] (exclusive scan of the visibility flags), and gradients are ACCUMULATED over the W cameras of a step
+    const float* v_rows;
+    const int32_t* row_offsets;
+    int accumulate;
 };
 
 template <bool RAW, typename R>
@@ -363,6 +368,9 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
     const int stride3 = v.sh_stride * 3;
     float p[3] = {0.f, 0.f, 0.f};
     if (vis) { p[0] = __ldg(means + 3 * i); p[1] = __ldg(means + 3 * i + 1); p[2] = __ldg(means + 3 * i + 2); }
+    const bool ROWS = RAW && (raw.v_rows != nullptr);
+    const bool ACC = RAW && (raw.accumulate != 0);
+    const float* vrow = (ROWS && vis) ? raw.v_rows + int64_t(raw.row_offsets[i]) * B200GS_ROW_FLOATS : nullptr;
 
     float dmx = 0.f, dmy = 0.f, dmz = 0.f;  // dL/dmean (world)
     float dtx = 0.f, dty = 0.f, dtz = 0.f;  // dL/dt (camera)
@@ -377,9 +385,10 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
         for (int k = 0; k < MAX_COEFFS * 3; ++k) out[k] = 0.f;
         if (vis) {
             const uint8_t cl = clamped[i];
-            gr = (cl & 1) ? 0.f : __ldg(v_rgb + 3 * i + 0);
-            gg = (cl & 2) ? 0.f : __ldg(v_rgb + 3 * i + 1);
-            gb = (cl & 4) ? 0.f : __ldg(v_rgb + 3 * i + 2);
+            const float* crgb = ROWS ? vrow + B200GS_ROW_RGB : v_rgb + 3 * i;
+            gr = (cl & 1) ? 0.f : __ldg(crgb + 0);
+            gg = (cl & 2) ? 0.f : __ldg(crgb + 1);
+            gb = (cl & 4) ? 0.f : __ldg(crgb + 2);
             dx = p[0] - v.campos[0]; dy = p[1] - v.campos[1]; dz = p[2] - v.campos[2];
             inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
             dx *= inv_len; dy *= inv_len; dz *= inv_len;
@@ -393,7 +402,10 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
         }
         const int rw = RAW ? stride3 - 3 : stride3;          // floats per output row
         float* dst_base = RAW ? raw.v_shs_rest : v_shs;
-        if (RAW && in_range) { v_shs[3 * i] = out[0]; v_shs[3 * i + 1] = out[1]; v_shs[3 * i + 2] = out[2]; }
+        if (RAW && in_range) {
+            if (ACC) { out[0] += v_shs[3 * i]; out[1] += v_shs[3 * i + 1]; out[2] += v_shs[3 * i + 2]; }
+            v_shs[3 * i] = out[0]; v_shs[3 * i + 1] = out[1]; v_shs[3 * i + 2] = out[2];
+        }
         if (rw <= 48) {
             const int rwp = rw | 1;
             float* row = s_rows[warp] + lane * rwp;
@@ -417,11 +429,15 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
                         t[e] = sw[r * rwp + c];
                         if (++c == rw) { c = 0; ++r; }
                     }
+                    if (ACC) {
+                        const float4 old = reinterpret_cast<const float4*>(dst)[idx];
+                        t[0] += old.x; t[1] += old.y; t[2] += old.z; t[3] += old.w;
+                    }
                     reinterpret_cast<float4*>(dst)[idx] = make_float4(t[0], t[1], t[2], t[3]);
                 }
-                for (int f = (total & ~3) + lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw];
+                for (int f = (total & ~3) + lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw] + (ACC ? dst[f] : 0.f);
             } else {
-                for (int f = lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw];
+                for (int f = lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw] + (ACC ? dst[f] : 0.f);
             }
         } else if (in_range) {  // wider coefficient storage than the kernel evaluates: plain per-thread rows
             float* o = dst_base + i * int64_t(rw);
@@ -451,10 +467,12 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
     }
     if (!in_range) return;
     if (!vis) {
-        v_means[3 * i] = 0.f; v_means[3 * i + 1] = 0.f; v_means[3 * i + 2] = 0.f;
-        v_scales[3 * i] = 0.f; v_scales[3 * i + 1] = 0.f; v_scales[3 * i + 2] = 0.f;
-        v_quats[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (RAW) raw.v_opac_logit[i] = 0.f;
+        if (!ACC) {
+            v_means[3 * i] = 0.f; v_means[3 * i + 1] = 0.f; v_means[3 * i + 2] = 0.f;
+            v_scales[3 * i] = 0.f; v_scales[3 * i + 1] = 0.f; v_scales[3 * i + 2] = 0.f;
+            v_quats[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (RAW) raw.v_opac_logit[i] = 0.f;
+        }
         return;
     }
     float sc[3], q[4], inv_qn;
@@ -466,7 +484,8 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
     // ---- conic (+ compensation) -> blurred cov2D (a, b, c) ----------------------------------------------------
     const float inv_det = 1.0f / g.det;
     const float A = g.c * inv_det, B = -g.b * inv_det, C = g.a * inv_det;
-    const float vA = __ldg(v_conic + 3 * i), vB = __ldg(v_conic + 3 * i + 1), vC = __ldg(v_conic + 3 * i + 2);
+    const float* ccon = ROWS ? vrow + B200GS_ROW_CONIC : v_conic + 3 * i;
+    const float vA = __ldg(ccon), vB = __ldg(ccon + 1), vC = __ldg(ccon + 2);
     // X = -Q G Q, Q = [[A,B],[B,C]], G = [[vA, vB/2],[vB/2, vC]]
     const float hB = 0.5f * vB;
     const float m00 = A * vA + B * hB, m01 = A * hB + B * vC;
@@ -479,14 +498,14 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
     if (RAW) {
         // blend opacity = sigmoid(logit) [* compensation]: split dL/d(opac_out) between the logit and the compensation
         const float o = 1.0f / (1.0f + expf(-__ldg(raw.opac_in + i)));
-        const float vo = __ldg(raw.v_opac + i);
+        const float vo = ROWS ? __ldg(vrow + B200GS_ROW_OPACITY) : __ldg(raw.v_opac + i);
         float v_sig = vo;
         if (GSPLAT && raw.anti_aliased) {
             const float comp = sqrtf(fmaxf(g.det0 / g.det, 0.f));
             v_sig = vo * comp;
             vc_total += vo * o;
         }
-        raw.v_opac_logit[i] = v_sig * o * (1.0f - o);
+        raw.v_opac_logit[i] = v_sig * o * (1.0f - o) + (ACC ? raw.v_opac_logit[i] : 0.f);
     }
     if (GSPLAT && (v_comp != nullptr || RAW)) {
         const float vc = vc_total;
@@ -538,13 +557,14 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
     if (!g.cly) dty += dcy; else if (GSPLAT) dtz += dcy * g.cyp * itz;
 
     // ---- mean2D / depth --------------------------------------------------------------------------------------
-    const float2 vxy = v_xy[i];
+    const float2 vxy = ROWS ? make_float2(__ldg(vrow), __ldg(vrow + 1)) : v_xy[i];
     if (GSPLAT) {
         const float iz = 1.0f / (g.tz + 1e-6f);
         dtx += v.fx * iz * vxy.x;
         dty += v.fy * iz * vxy.y;
         dtz += (-v.fx * g.tx * iz * iz + v.cx * 1e-6f * iz * iz) * vxy.x + (-v.fy * g.ty * iz * iz + v.cy * 1e-6f * iz * iz) * vxy.y;
-        if (v_depth) dtz += __ldg(v_depth + i);
+        if (ROWS) dtz += __ldg(vrow + B200GS_ROW_DEPTH);
+        else if (v_depth) dtz += __ldg(v_depth + i);
     } else {
         // v_xy is dL/d(ndc) (pixel gradient x 0.5 W/H), straight through the 4x4 full projection
         const float* P = v.projmatrix;
@@ -560,6 +580,7 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
     dmx += V[0] * dtx + V[1] * dty + V[2] * dtz;
     dmy += V[4] * dtx + V[5] * dty + V[6] * dtz;
     dmz += V[8] * dtx + V[9] * dty + V[10] * dtz;
+    if (ACC) { dmx += v_means[3 * i]; dmy += v_means[3 * i + 1]; dmz += v_means[3 * i + 2]; }
     v_means[3 * i] = dmx; v_means[3 * i + 1] = dmy; v_means[3 * i + 2] = dmz;
 
     // ---- Sigma3 = M M^T, M = R diag(s) ------------------------------------------------------------------------
@@ -577,7 +598,7 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float vs_k = v.scale_modifier * (g.Rm[k] * dM[k] + g.Rm[3 + k] * dM[3 + k] + g.Rm[6 + k] * dM[6 + k]);
-        v_scales[3 * i + k] = RAW ? vs_k * sc[k] : vs_k;   // d exp(x) = exp(x)
+        v_scales[3 * i + k] = (RAW ? vs_k * sc[k] : vs_k) + (ACC ? v_scales[3 * i + k] : 0.f);   // d exp(x) = exp(x)
 #pragma unroll
         for (int r = 0; r < 3; ++r) dR[r * 3 + k] = dM[r * 3 + k] * g.s[k];
     }
@@ -591,6 +612,10 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
         const float dot = dq.x * q[0] + dq.y * q[1] + dq.z * q[2] + dq.w * q[3];
         dq.x = (dq.x - q[0] * dot) * inv_qn; dq.y = (dq.y - q[1] * dot) * inv_qn;
         dq.z = (dq.z - q[2] * dot) * inv_qn; dq.w = (dq.w - q[3] * dot) * inv_qn;
+    }
+    if (ACC) {
+        const float4 old = v_quats[i];
+        dq.x += old.x; dq.y += old.y; dq.z += old.z; dq.w += old.w;
     }
     v_quats[i] = dq;
 }
@@ -673,7 +698,7 @@ int launch_project_fwd_raw(const B200gsView& v, int64_t n, const float* means, c
     const int threads = 256;
     const unsigned blocks = (unsigned)div_up64(n, threads);
     const bool raw_mode = opac_out != nullptr;
-    RawIO raw{opac_logits, shs_rest, opac_out, nullptr, nullptr, nullptr, anti_aliased};
+    RawIO raw{opac_logits, shs_rest, opac_out, nullptr, nullptr, nullptr, anti_aliased, nullptr, nullptr, 0};
 #define B200GS_PF_ARGS v, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth, radii, conic, comp, tiles, cov3d, rgb, clamped
     if (v.mode == B200GS_MODE_GSPLAT) {
         if (raw_mode) project_fwd_kernel<true, true><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);
@@ -700,12 +725,12 @@ int launch_project_bwd_raw(const B200gsView& v, int64_t n, const float* means, c
                            const int32_t* radii, const uint8_t* clamped, const float* v_xy, const float* v_depth,
                            const float* v_conic, const float* v_comp, const float* v_rgb, const float* v_opac, float* v_means,
                            float* v_scales, float* v_quats, float* v_opac_logit, float* v_shs_dc, float* v_shs_rest,
-                           cudaStream_t s) {
+                           cudaStream_t s, const float* v_rows, const int32_t* row_offsets, int accumulate) {
     if (n == 0) return B200GS_OK;
     const int threads = BWD_THREADS;
     const unsigned blocks = (unsigned)div_up64(n, threads);
     const bool raw_mode = v_opac_logit != nullptr;
-    RawIO raw{opac_logits, shs_rest, nullptr, v_opac, v_opac_logit, v_shs_rest, anti_aliased};
+    RawIO raw{opac_logits, shs_rest, nullptr, v_opac, v_opac_logit, v_shs_rest, anti_aliased, v_rows, row_offsets, accumulate};
 #define B200GS_PB_ARGS v, raw, n, means, scales, quats, shs_dc, radii, clamped, (const float2*)v_xy, v_depth, v_conic, v_comp, v_rgb, \
                        v_means, v_scales, (float4*)v_quats, v_shs_dc
     if (v.mode == B200GS_MODE_GSPLAT) {

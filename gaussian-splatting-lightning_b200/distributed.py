@@ -109,11 +109,14 @@ class GatheredView:
 
 
 class _ShardedRasterize(torch.autograd.Function):
-    """The whole sharded step as ONE autograd node, everything between the raw shard parameters and this rank's image:
-    K1 (fused activations, gsplat constants) per camera -> pack visible rows (device-side compaction) -> count exchange
-    (the step's single host sync) -> all_to_all_single of [V,12] rows -> K2-K7 reading the received rows in place.
-    Backward: K7 accumulates straight into a [R,12] gradient row buffer -> mirrored all_to_all_single -> unpack -> K8
-    (fused activation chain) per camera, summed over cameras."""
+    """The whole sharded step as ONE autograd node, everything between the raw shard parameters and this rank's image.
+    forward : K1 (fused activations, gsplat constants) per camera into camera-major SoA buffers -> ONE b200gs_pack_rows over all
+              W*n entries (device-side stable compaction; its output IS the all-to-all send buffer, camera-major) -> count
+              exchange (the step's host sync) -> all_to_all_single of [V,12] rows -> K2-K7 reading the received rows in
+              place, pair buffers sized lazily from the previous step.
+    backward: K7 accumulates into a [R,12] gradient row buffer -> mirrored all_to_all_single -> K8 (fused activation
+              chain) per camera reading its cotangents straight from the returned rows and ACCUMULATING into one set of
+              gradient buffers (b200gs_project_bwd_rows): no unpack copies, no separate sum kernels."""
 
     @staticmethod
     def forward(ctx, means, log_scales, raw_quats, opac_logits, shs_dc, shs_rest, bg, views, rank, group, anti_aliased, sh_degree):
@@ -124,103 +127,94 @@ class _ShardedRasterize(torch.autograd.Function):
         dev = means.device
         n = means.shape[0]
         world = len(views)
-        st = torch.cuda.current_stream().cuda_stream
+        st = ops._stream()
         means, log_scales, raw_quats = means.contiguous(), log_scales.contiguous(), raw_quats.contiguous()
         ol = opac_logits.contiguous().reshape(-1)
         shs_dc, shs_rest, bg = shs_dc.contiguous(), shs_rest.contiguous(), bg.contiguous()
-        counts = torch.zeros(2 * world, dtype=torch.int64, device=dev)   # [send | recv]
-        ws = torch.empty(max(int(L.b200gs_pack_rows_workspace_bytes(n)), 256), dtype=torch.uint8, device=dev)
-        per_cam = []
-        for j, view in enumerate(views):
-            v = ops._copy_view(view, sh_degree=int(sh_degree), sh_stride=int(shs_dc.shape[1] + shs_rest.shape[1]))
-            xy, depth, radii, conic, comp, tiles, rgb, clamped, opac = ops.project_forward_raw(
-                v, means, log_scales, raw_quats, ol, shs_dc, shs_rest, anti_aliased, want_comp=True)
-            rows = torch.empty(n, ROW_FLOATS, dtype=torch.float32, device=dev)
-            offsets = torch.empty(n, dtype=torch.int32, device=dev)
-            check(L.b200gs_pack_rows(n, ptr(xy), ptr(depth), ptr(conic), ptr(comp), ptr(opac), ptr(rgb), ptr(radii), ptr(ws), ws.numel(),
-                                     ptr(offsets), ptr(rows), counts.data_ptr() + 8 * j, st), "b200gs_pack_rows")
-            per_cam.append((v, rows, offsets, radii, clamped, xy))
+        wn = world * n
+        f32 = dict(dtype=torch.float32, device=dev)
+        xy, depth, conic, comp = torch.empty(wn, 2, **f32), torch.empty(wn, **f32), torch.empty(wn, 3, **f32), torch.empty(wn, **f32)
+        rgb, opac = torch.empty(wn, 3, **f32), torch.empty(wn, **f32)
+        radii = torch.empty(wn, dtype=torch.int32, device=dev)
+        tiles = torch.empty(n, dtype=torch.int32, device=dev)
+        clamped = torch.empty(wn, dtype=torch.uint8, device=dev)
+        cam_views = []
+        with ops._stage("project_fwd"):
+            for j, view in enumerate(views):
+                v = ops._copy_view(view, sh_degree=int(sh_degree), sh_stride=int(shs_dc.shape[1] + shs_rest.shape[1]))
+                cam_views.append(v)
+                o = j * n
+                check(L.b200gs_project_fwd_raw(ctypes.byref(v), n, ptr(means), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc),
+                                               ptr(shs_rest), int(bool(anti_aliased)), xy.data_ptr() + 8 * o, depth.data_ptr() + 4 * o,
+                                               radii.data_ptr() + 4 * o, conic.data_ptr() + 12 * o, comp.data_ptr() + 4 * o, ptr(tiles),
+                                               rgb.data_ptr() + 12 * o, clamped.data_ptr() + o, opac.data_ptr() + 4 * o, st),
+                      "b200gs_project_fwd_raw")
+        rows = torch.empty(wn, ROW_FLOATS, **f32)          # upper bound; the first sum(V_j) rows are the send buffer
+        offsets = torch.empty(wn, dtype=torch.int32, device=dev)
+        ws = torch.empty(max(int(L.b200gs_pack_rows_workspace_bytes(wn)), 256), dtype=torch.uint8, device=dev)
+        d_count = torch.empty(1, dtype=torch.int64, device=dev)
+        with ops._stage("pack"):
+            check(L.b200gs_pack_rows(wn, ptr(xy), ptr(depth), ptr(conic), ptr(comp), ptr(opac), ptr(rgb), ptr(radii), ptr(ws), ws.numel(),
+                                     ptr(offsets), ptr(rows), ptr(d_count), st), "b200gs_pack_rows")
+        last = torch.arange(1, world + 1, device=dev, dtype=torch.int64) * n - 1
+        ends = offsets[last].to(torch.int64) + (radii[last] > 0).to(torch.int64)          # cumulative visible counts per camera
+        counts = torch.empty(2 * world, dtype=torch.int64, device=dev)                       # [send | recv]
+        counts[:world] = ends - torch.cat([ends.new_zeros(1), ends[:-1]])
         dist.all_to_all_single(counts[world:], counts[:world], group=group)
-        host_counts = counts.cpu().tolist()                                 # the step's host sync
+        host_counts = counts.cpu().tolist()                                                  # the step's host sync
         send_counts, recv_counts = host_counts[:world], host_counts[world:]
-        send = torch.cat([per_cam[j][1][:send_counts[j]] for j in range(world)], dim=0)
-        recv = torch.empty(sum(recv_counts), ROW_FLOATS, dtype=torch.float32, device=dev)
-        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
-        del send
+        recv = torch.empty(sum(recv_counts), ROW_FLOATS, **f32)
+        dist.all_to_all_single(recv, rows[:sum(send_counts)], output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
+        del rows, xy, depth, conic, comp, rgb, opac
 
         gv = views[rank]
         W, H = gv.width, gv.height
-        R = recv.shape[0]
-        gx, gy = (W + 15) // 16, (H + 15) // 16
-        ws_a = torch.empty(L.b200gs_bin_count_workspace_bytes(R), dtype=torch.uint8, device=dev)
-        d_total = torch.empty(1, dtype=torch.int64, device=dev)
-        host_total = torch.zeros(1, dtype=torch.int64).pin_memory()
-        with ops._stage("bin_count"):
-            check(L.b200gs_bin_count_rows(MODE_GSPLAT, W, H, R, ptr(recv), 1, ptr(ws_a), ws_a.numel(), ptr(d_total), host_total.data_ptr(), 1, st),
-                  "b200gs_bin_count_rows")
-        total = int(host_total[0])
-        sorted_ids = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-        ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
-        ws_b = torch.empty(L.b200gs_bin_sort_workspace_bytes(R, total, W, H), dtype=torch.uint8, device=dev)
-        with ops._stage("bin_sort"):
-            check(L.b200gs_bin_sort_rows(MODE_GSPLAT, W, H, R, ptr(recv), 1, total, ptr(d_total), total, ptr(ws_a), ptr(ws_b), ws_b.numel(),
-                                         ptr(sorted_ids), ptr(ranges), st), "b200gs_bin_sort_rows")
-        image = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
-        final_T = torch.empty(H, W, dtype=torch.float32, device=dev)
-        n_contrib = torch.empty(H, W, dtype=torch.int32, device=dev)
-        with ops._stage("blend_fwd"):
-            check(L.b200gs_blend_fwd_rows(MODE_GSPLAT, W, H, ptr(ranges), ptr(sorted_ids), ptr(recv), ptr(bg), ptr(image), 3, 1, ptr(final_T),
-                                          ptr(n_contrib), None, st), "b200gs_blend_fwd_rows")
-        ctx.per_cam, ctx.views, ctx.rank, ctx.group = per_cam, views, rank, group
+        binning, (image, final_T, n_contrib) = ops.bin_and_blend_rows(MODE_GSPLAT, W, H, recv, bg, True)
+        ctx.cam_views, ctx.group, ctx.n = cam_views, group, n
         ctx.counts = (send_counts, recv_counts)
         ctx.aa = bool(anti_aliased)
         ctx.hw = (H, W)
+        ctx.binning = binning
         ctx.opac_shape = tuple(opac_logits.shape)
-        ctx.save_for_backward(means, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, recv, sorted_ids, ranges, final_T, n_contrib)
-        ctx.xy_grads = None
+        ctx.save_for_backward(means, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, recv, final_T, n_contrib, radii, clamped, offsets)
         return image
 
     @staticmethod
     def backward(ctx, v_image):
+        import ctypes
         from ._lib import MODE_GSPLAT, check, lib, ptr
         from . import ops
         L = lib()
-        means, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, recv, sorted_ids, ranges, final_T, n_contrib = ctx.saved_tensors
+        means, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, recv, final_T, n_contrib, radii, clamped, offsets = ctx.saved_tensors
         dev = means.device
-        n = means.shape[0]
-        st = torch.cuda.current_stream().cuda_stream
+        n = ctx.n
+        st = ops._stream()
         H, W = ctx.hw
         send_counts, recv_counts = ctx.counts
         v_image = v_image.contiguous()
         v_recv = torch.zeros_like(recv)
         with ops._stage("blend_bwd"):
-            check(L.b200gs_blend_bwd_rows(MODE_GSPLAT, W, H, ptr(ranges), ptr(sorted_ids), ptr(recv), ptr(bg), ptr(final_T), ptr(n_contrib),
-                                          ptr(v_image), 3, 1, None, ptr(v_recv), st), "b200gs_blend_bwd_rows")
-        v_send = torch.empty(sum(send_counts), ROW_FLOATS, dtype=torch.float32, device=dev)
-        dist.all_to_all_single(v_send, v_recv, output_split_sizes=send_counts, input_split_sizes=recv_counts, group=ctx.group)
-        grads = None
-        xy_grads = []
-        off = 0
-        for j, (view, rows, offsets, radii, clamped, xy) in enumerate(ctx.per_cam):
-            v_rows = v_send[off:off + send_counts[j]]
-            off += send_counts[j]
-            v_xy = torch.empty(n, 2, dtype=torch.float32, device=dev)
-            v_depth = torch.empty(n, dtype=torch.float32, device=dev)
-            v_conic = torch.empty(n, 3, dtype=torch.float32, device=dev)
-            v_opac = torch.empty(n, dtype=torch.float32, device=dev)
-            v_rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
-            check(L.b200gs_unpack_rows_grad(n, ptr(radii), ptr(offsets), ptr(v_rows) if v_rows.numel() else None, ptr(v_xy), ptr(v_depth),
-                                            ptr(v_conic), None, ptr(v_opac), ptr(v_rgb), st), "b200gs_unpack_rows_grad")
-            g = ops.project_backward_raw(view, means, log_scales, raw_quats, ol, shs_dc, shs_rest, ctx.aa, radii, clamped, v_xy, v_depth,
-                                         v_conic, v_rgb, v_opac)
-            xy_grads.append(v_xy)
-            if grads is None:
-                grads = list(g)
-            else:
-                for a, b in zip(grads, g):
-                    a.add_(b)
-        ctx.xy_grads_out.extend(xy_grads)
-        v_means, v_ls, v_q, v_ol, v_dc, v_rest = grads
+            check(L.b200gs_blend_bwd_rows(MODE_GSPLAT, W, H, ptr(ctx.binning.tile_ranges), ptr(ctx.binning.sorted_ids), ptr(recv), ptr(bg),
+                                          ptr(final_T), ptr(n_contrib), ptr(v_image), 3, 1, None, ptr(v_recv), st), "b200gs_blend_bwd_rows")
+        v_send = torch.empty(max(sum(send_counts), 1), ROW_FLOATS, dtype=torch.float32, device=dev)
+        dist.all_to_all_single(v_send[:sum(send_counts)], v_recv, output_split_sizes=send_counts, input_split_sizes=recv_counts,
+                               group=ctx.group)
+        f32 = dict(dtype=torch.float32, device=dev)
+        v_means, v_ls, v_q = torch.empty(n, 3, **f32), torch.empty(n, 3, **f32), torch.empty(n, 4, **f32)
+        v_ol, v_dc, v_rest = torch.empty(n, **f32), torch.empty_like(shs_dc), torch.empty_like(shs_rest)
+        with ops._stage("project_bwd"):
+            for j, view in enumerate(ctx.cam_views):
+                check(L.b200gs_project_bwd_rows(ctypes.byref(view), n, ptr(means), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc),
+                                                ptr(shs_rest), int(ctx.aa), radii.data_ptr() + 4 * j * n, clamped.data_ptr() + j * n,
+                                                offsets.data_ptr() + 4 * j * n, ptr(v_send), 1 if j > 0 else 0, ptr(v_means), ptr(v_ls),
+                                                ptr(v_q), ptr(v_ol), ptr(v_dc), ptr(v_rest), st), "b200gs_project_bwd_rows")
+        if ctx.xy_grads_out is not None:
+            # per-camera mean2D gradients for the distributed density controller (distributed_vanilla_density_controller.py:16-47)
+            for j in range(len(ctx.cam_views)):
+                g = torch.zeros(n, 2, **f32)
+                vis = radii[j * n:(j + 1) * n] > 0
+                g[vis] = v_send[offsets[j * n:(j + 1) * n][vis].long(), 0:2]
+                ctx.xy_grads_out.append(g)
         return v_means, v_ls, v_q, v_ol.reshape(ctx.opac_shape), v_dc, v_rest, None, None, None, None, None, None
 
 
@@ -239,7 +233,7 @@ class B200DistributedRenderer(torch.nn.Module):
     shard; returns this rank's image plus the per-camera projection results the distributed density controller reads
     (``distributed_vanilla_density_controller.py:16-47``)."""
 
-    def __init__(self, anti_aliased: bool = True, group=None, fused: bool = True):
+    def __init__(self, anti_aliased: bool = True, group=None, fused: bool = True, want_xy_grads: bool = False):
         """fused: when `pc` is the vanilla Gaussian model, run the whole step as one autograd node on the raw parameters
         (_ShardedRasterize: device-side packing, rows consumed in place, one host sync); otherwise the generic path
         below, built from the same ops the single-GPU renderers use."""
@@ -247,6 +241,7 @@ class B200DistributedRenderer(torch.nn.Module):
         self.anti_aliased = anti_aliased
         self.group = group
         self.fused = fused
+        self.want_xy_grads = want_xy_grads   # fused path: also materialise per-camera dL/d(mean2D) for the density controller
 
     def _forward_fused(self, raw, viewpoint_camera, pc, bg_color, scaling_modifier):
         from . import ops
@@ -263,11 +258,9 @@ class B200DistributedRenderer(torch.nn.Module):
             v = ops.make_view(MODE_GSPLAT, gv.width, gv.height, fx=gv.fx, fy=gv.fy, cx=gv.cx, cy=gv.cy, viewmatrix=gv.world_to_camera,
                               campos=gv.camera_center, scale_modifier=scaling_modifier)
             views.append(v)
-        xy_grads: List[torch.Tensor] = []
-        fn = _ShardedRasterize
         # the per-camera mean2D gradients (what the distributed density controller reads) are appended to this list by backward
-        _ShardedRasterize_ctx_hook = xy_grads
-        img = _sharded_apply(fn, _ShardedRasterize_ctx_hook, raw["means"], raw["scales"], raw["rotations"], raw["opacities"], raw["shs_dc"],
+        xy_grads: Optional[List[torch.Tensor]] = [] if self.want_xy_grads else None
+        img = _sharded_apply(_ShardedRasterize, xy_grads, raw["means"], raw["scales"], raw["rotations"], raw["opacities"], raw["shs_dc"],
                              raw["shs_rest"], bg_color, views, rank, self.group, self.anti_aliased, int(pc.active_sh_degree))
         return {
             "render": img.permute(2, 0, 1),

@@ -200,6 +200,65 @@ def bin_gaussians(mode: int, width: int, height: int, xy: torch.Tensor, depth: t
     return Binning(sorted_ids, ranges, None if pending else total, pending)
 
 
+def bin_rows(mode: int, width: int, height: int, rows: torch.Tensor, cull: bool = True, lazy: bool = False) -> Binning:
+    """K2-K5 on a [n,12] splat-row buffer read in place (b200gs_bin_*_rows); same lazy protocol as bin_gaussians."""
+    L = lib()
+    n = rows.shape[0]
+    dev = rows.device
+    st = _stream()
+    gx, gy = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+    ws_a = torch.empty(L.b200gs_bin_count_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    d_total = torch.empty(1, dtype=torch.int64, device=dev)
+    ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
+    global _host_total
+    if _host_total is None:
+        _host_total = torch.zeros(1, dtype=torch.int64).pin_memory()
+    key = ("rows", mode, width, height, bool(cull))
+    prev = _last_total.get(key) if lazy else None
+    sync = prev is None
+    with _stage("bin_count"):
+        check(L.b200gs_bin_count_rows(mode, width, height, n, ptr(rows), int(cull), ptr(ws_a), ws_a.numel(), ptr(d_total),
+                                      _host_total.data_ptr(), 1 if sync else 0, st), "b200gs_bin_count_rows")
+    if sync:
+        total = capacity = int(_host_total[0])
+        _last_total[key] = total
+        pending = None
+    else:
+        event = torch.cuda.Event()
+        event.record()
+        total = -1
+        capacity = int(prev * LAZY_SLACK) + 4096
+        pending = (event, key, capacity)
+    sorted_ids = torch.empty(max(capacity, 1), dtype=torch.int32, device=dev)
+    ws_b = torch.empty(L.b200gs_bin_sort_workspace_bytes(n, capacity, width, height), dtype=torch.uint8, device=dev)
+    with _stage("bin_sort"):
+        check(L.b200gs_bin_sort_rows(mode, width, height, n, ptr(rows), int(cull), total, ptr(d_total), capacity, ptr(ws_a), ptr(ws_b),
+                                     ws_b.numel(), ptr(sorted_ids), ptr(ranges), st), "b200gs_bin_sort_rows")
+    return Binning(sorted_ids, ranges, None if pending else total, pending)
+
+
+def blend_forward_rows(mode, width, height, binning: Binning, rows, bg):
+    """K6 on rows -> image [H,W,3], final_T, n_contrib."""
+    L = lib()
+    dev = rows.device
+    image = torch.empty(height, width, 3, dtype=torch.float32, device=dev)
+    final_T = torch.empty(height, width, dtype=torch.float32, device=dev)
+    n_contrib = torch.empty(height, width, dtype=torch.int32, device=dev)
+    with _stage("blend_fwd"):
+        check(L.b200gs_blend_fwd_rows(mode, width, height, ptr(binning.tile_ranges), ptr(binning.sorted_ids), ptr(rows), ptr(bg), ptr(image),
+                                      3, 1, ptr(final_T), ptr(n_contrib), None, _stream()), "b200gs_blend_fwd_rows")
+    return image, final_T, n_contrib
+
+
+def bin_and_blend_rows(mode, width, height, rows, bg, cull=True):
+    binning = bin_rows(mode, width, height, rows, cull, lazy=True)
+    out = blend_forward_rows(mode, width, height, binning, rows, bg)
+    if not binning.resolve():
+        binning = bin_rows(mode, width, height, rows, cull, lazy=False)
+        out = blend_forward_rows(mode, width, height, binning, rows, bg)
+    return binning, out
+
+
 def bin_and_blend(mode, width, height, xy, depth, radii, conic, opacity, colors, bg, planar, want_alpha):
     """Forward binning + blend with the lazy (sync-free) pair count; falls back to an exact re-run on overflow."""
     binning = bin_gaussians(mode, width, height, xy, depth, radii, conic, opacity, lazy=True)

@@ -201,6 +201,14 @@ B200GS_API int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int
 #define B200GS_ROW_OPACITY 7
 #define B200GS_ROW_RGB 8
 #define B200GS_ROW_RADIUS 11
+/* b200gs_project_bwd_rows: K8 (fused activations) taking its cotangents straight from compacted [V,12] gradient rows
+ *     (v_rows[row_offsets[i]] for visible i) and, when accumulate != 0, ADDING to the gradient buffers — the sharded
+ *     renderer calls it once per camera of the step without unpack copies or separate sum kernels. */
+B200GS_API int b200gs_project_bwd_rows(const B200gsView* view, int64_t n, const float* means, const float* log_scales,
+                                       const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
+                                       int32_t anti_aliased, const int32_t* radii, const uint8_t* clamped, const int32_t* row_offsets,
+                                       const float* v_rows, int32_t accumulate, float* v_means, float* v_log_scales, float* v_raw_quats,
+                                       float* v_opacity_logits, float* v_shs_dc, float* v_shs_rest, void* stream);
 B200GS_API size_t b200gs_pack_rows_workspace_bytes(int64_t n);
 B200GS_API int b200gs_pack_rows(int64_t n, const float* xy, const float* depth, const float* conic, const float* comp,
                                 const float* opacity, const float* rgb, const int32_t* radii, void* workspace, size_t workspace_bytes,

@@ -49,7 +49,7 @@ def _worker(rank, world, port, q):
         lo, hi = shard_range(n, world, rank)
         for fused in (True, False):     # one-node fused path (raw parameters, rows consumed in place) and the generic op-by-op path
             shard = SyntheticGaussians({k: v[lo:hi] for k, v in raw.items()}).to(dev)
-            out = B200DistributedRenderer(fused=fused).to(dev)(cams[3 * rank].to_device(dev), shard, bg)
+            out = B200DistributedRenderer(fused=fused, want_xy_grads=True).to(dev)(cams[3 * rank].to_device(dev), shard, bg)
             if fused:
                 assert float((out["render"].detach() - imgs[rank]).abs().max()) < 2e-4   # in-kernel vs torch activations: ulps
             else:
