@@ -214,7 +214,8 @@ def algorithmic_bytes(stage, N, V, I, P, n_tiles):
         "blend_fwd": I * 40 + P * 20,
         "blend_bwd": I * 76 + P * 20,
         "project_bwd": V * 552,
-    }[stage]
+        "pack": N * 57 + V * 48,                       # sharded path: visibility scan + SoA read + [V,12] row write
+    }.get(stage, 0)
 
 
 LAUNCHES_PER_STEP = {"project_fwd": 1, "bin_count": 1 + 6 + 2 + 1, "bin_sort": 1 + 4 + 1, "blend_fwd": 1, "blend_bwd": 1, "project_bwd": 1}
