@@ -324,23 +324,34 @@ __global__ void __launch_bounds__(256) pad_keys_kernel(int64_t cap, const int64_
     for (int64_t i = *d_total + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < cap; i += stride) keys[i] = pad;
 }
 
+// ranges[t] = [first, last+1) of tile t in the partitioned key array; RV keys per thread (one 8/16-byte load).
 template <typename KT>
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t cap, const int64_t* __restrict__ d_total, const KT* __restrict__ keys,
                                                           int2* __restrict__ ranges) {
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    constexpr int RV = 16 / sizeof(KT) >= 8 ? 8 : 4;   // 8 x u16 = 16 B, 4 x u32 = 16 B
     const int64_t total = min(cap, *d_total);
-    if (i >= total) return;
-    const uint32_t cur = keys[i];
-    if (i == 0) {
-        ranges[cur].x = 0;
+    const int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * RV;
+    if (i0 >= total) return;
+    KT k[RV];
+    if (i0 + RV <= total) {
+        *reinterpret_cast<uint4*>(k) = *reinterpret_cast<const uint4*>(keys + i0);   // keys is 256 B aligned, i0 multiple of RV
     } else {
-        const uint32_t prev = keys[i - 1];
-        if (prev != cur) {
-            ranges[prev].y = (int)i;
+#pragma unroll
+        for (int e = 0; e < RV; ++e) k[e] = (i0 + e < total) ? keys[i0 + e] : KT(0);
+    }
+    uint32_t prev = (i0 == 0) ? 0xFFFFFFFFu : (uint32_t)keys[i0 - 1];
+#pragma unroll
+    for (int e = 0; e < RV; ++e) {
+        const int64_t i = i0 + e;
+        if (i >= total) break;
+        const uint32_t cur = k[e];
+        if (cur != prev) {
+            if (i > 0) ranges[prev].y = (int)i;
             ranges[cur].x = (int)i;
         }
+        if (i == total - 1) ranges[cur].y = (int)total;
+        prev = cur;
     }
-    if (i == total - 1) ranges[cur].y = (int)total;
 }
 
 template <typename KT>
@@ -365,7 +376,8 @@ int emit_sort_ranges(int mode, int64_t n, int grid_x, int grid_y, int n_tiles, c
     size_t tb = temp_bytes;
     // temp was sized for max_pairs 32-bit keys; cub's requirement is monotone in the item count and key width
     B200GS_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, kin, kout, pvals_in, sorted_ids, (int)items, 0, bits, s));
-    tile_ranges_kernel<KT><<<(unsigned)div_up64(items, 256), 256, 0, s>>>(items, d_total, kout, (int2*)tile_ranges);
+    constexpr int RV = 16 / sizeof(KT) >= 8 ? 8 : 4;
+    tile_ranges_kernel<KT><<<(unsigned)div_up64(div_up64(items, RV), 256), 256, 0, s>>>(items, d_total, kout, (int2*)tile_ranges);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }
