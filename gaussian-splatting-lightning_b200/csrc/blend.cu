@@ -19,6 +19,8 @@
 // consecutive list entries and keeps their 9 partial derivatives in registers; the warp then reduces them with a
 // reduce-SCATTER butterfly (halving exchanges: RB -> RB/2 -> ... -> 1 value per lane) and one lane per splat issues
 // the atomics: 32x fewer L2 atomics than the reference's per-pixel atomicAdd.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200gs {
@@ -403,6 +405,240 @@ __global__ void __launch_bounds__(BLOCK_PIX, (RB == 4 && !ABS) ? 4 : 1) blend_bw
     }
 }
 
+// ---- backward, tensor-core reduction variant -------------------------------------------------------------------------
+// The cross-lane reduction of the backward IS a small dense contraction: for the 8 list entries of a group, every
+// output is  sum_over_the_32_pixel_lanes( weight[row][lane] * value[lane][entry] )  with weights that are FIXED for the warp:
+//   rows 0..5  : 1, cx, cy, cx^2, cx*cy, cy^2   (pixel coordinates relative to the centre of the warp's 8x4 block)   x  g = dL/d(opacity)
+//   rows 8..8+CH-1 : v_image[channel] of the lane's pixel                                                             x  f = alpha*T
+// (the mean/conic gradients are linear in the six pixel-coordinate moments of g, see the writer below).  That is a
+// [16 x 64] x [64 x 8] GEMM per group: mma.sync.m16n8k8 TF32 with the 3xTF32 split (hi*hi + hi*lo + lo*hi; the coordinate
+// weights are exact in TF32) -> fp32-level accuracy, ~23 issue slots per splat for reduction + writer instead of ~58 with
+// the shuffle butterfly.  Values go lane -> fragment through a 2 KB per-warp shared-memory tile (XOR-swizzled: both the
+// stores and the fragment loads are bank-conflict free).
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int CH, bool GSPLAT>
+__global__ void __launch_bounds__(BLOCK_PIX, 3) blend_bwd_mma_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
+                                                                     const int32_t* __restrict__ ids, const SplatStrides st,
+                                                                     const float* __restrict__ xy, const float* __restrict__ conic,
+                                                                     const float* __restrict__ opacity, const float* __restrict__ colors,
+                                                                     const float* __restrict__ bg, const float* __restrict__ final_T,
+                                                                     const int32_t* __restrict__ n_contrib, const float* __restrict__ v_image,
+                                                                     int64_t pix_stride, int64_t ch_stride, const float* __restrict__ v_alpha,
+                                                                     float sx, float sy, float* __restrict__ v_xy, float* __restrict__ v_conic,
+                                                                     float* __restrict__ v_opacity, float* __restrict__ v_colors) {
+    constexpr int GB = 8;  // list entries per group = N of the MMA tile
+    __shared__ float4 s_rec[(BLOCK_PIX + 1) * 3];
+    __shared__ unsigned char s_mask[BLOCK_PIX];
+    __shared__ unsigned short s_list[NWARP][BLOCK_PIX + 2 * LIST_PAD];
+    __shared__ float s_b[NWARP][2][GB][32];
+    __shared__ int s_wmax[NWARP];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const unsigned lane = tid & 31u;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int tile = blockIdx.y * grid_x + blockIdx.x;
+    int lx, ly;
+    pixel_of_thread(tid, lx, ly);
+    const int px = blockIdx.x * TILE + lx, py = blockIdx.y * TILE + ly;
+    const bool inside = (px < width) && (py < height);
+    const float off = GSPLAT ? 0.5f : 0.0f;
+    const float pxf = float(px) + off, pyf = float(py) + off;
+    const float ox = float(blockIdx.x * TILE) + off, oy = float(blockIdx.y * TILE) + off;
+    // centre of this warp's 8x4 block of pixel samples
+    const float bcx = ox + float((warp & 1) << 3) + 3.5f, bcy = oy + float((warp >> 1) << 2) + 1.5f;
+    const float amax = GSPLAT ? 0.999f : 0.99f;
+    const int64_t pix = int64_t(py) * width + px;
+    if (tid < 3) s_rec[DUMMY * 3 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const int2 range = ranges[tile];
+    const float Tf = inside ? final_T[pix] : 0.f;
+    const int last = inside ? n_contrib[pix] : 0;
+    float vo[4] = {0.f, 0.f, 0.f, 0.f};
+    float bg_dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        vo[c] = inside ? __ldg(v_image + pix * pix_stride + c * ch_stride) : 0.f;
+        if (bg) bg_dot += __ldg(bg + c) * vo[c];
+    }
+    const float va = (v_alpha && inside) ? __ldg(v_alpha + pix) : 0.f;
+    const float tail = Tf * (va - bg_dot);
+
+    // fixed A fragments.  G part (k-steps 0..3): rows 0..5 in a0/a2;  F part (k-steps 4..7): rows 8..8+CH-1 in a1/a3 (hi + lo)
+    uint32_t aG0[4], aG2[4], aF1h[4], aF1l[4], aF3h[4], aF3l[4];
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 8 * s4 + tig + 4 * h;                 // pixel lane this fragment element multiplies
+            const float cx = float(k & 7) - 3.5f, cy = float(k >> 3) - 1.5f;
+            float w = 0.f;
+            if (gid == 0) w = 1.0f;
+            else if (gid == 1) w = cx;
+            else if (gid == 2) w = cy;
+            else if (gid == 3) w = cx * cx;
+            else if (gid == 4) w = cx * cy;
+            else if (gid == 5) w = cy * cy;
+            float v = 0.f;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const float t = __shfl_sync(FULL, vo[c], k);
+                if (gid == c) v = t;
+            }
+            const uint32_t vh = to_tf32(v);
+            const uint32_t vl = to_tf32(v - __uint_as_float(vh));
+            if (h == 0) { aG0[s4] = to_tf32(w); aF1h[s4] = vh; aF1l[s4] = vl; }
+            else { aG2[s4] = to_tf32(w); aF3h[s4] = vh; aF3l[s4] = vl; }
+        }
+    }
+
+    const int wmax = __reduce_max_sync(FULL, last);
+    if (lane == 0) s_wmax[warp] = wmax;
+    __syncthreads();
+    int max_last = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) max_last = max(max_last, s_wmax[w]);
+    if (max_last == 0) return;
+
+    float T = Tf;
+    float D = 0.f;
+    float* sbG = &s_b[warp][0][0][0];
+    float* sbF = &s_b[warp][1][0][0];
+
+    for (int hi = max_last; hi > 0; hi -= BLOCK_PIX) {
+        const int lo = max(0, hi - BLOCK_PIX);
+        const int cnt = hi - lo;
+        __syncthreads();
+        if (tid < cnt) {
+            const int g = __ldg(ids + range.x + lo + tid);
+            const float2 m = __ldg(reinterpret_cast<const float2*>(xy + int64_t(g) * st.xs));
+            const float* cq = conic + int64_t(g) * st.cs;
+            const float A = __ldg(cq), B = __ldg(cq + 1), Cc = __ldg(cq + 2);
+            const float o = __ldg(opacity + int64_t(g) * st.os);
+            float col[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * st.ks + c);
+            s_rec[tid * 3 + 0] = make_float4(m.x, m.y, (-0.5f * LOG2E) * A, -LOG2E * B);
+            s_rec[tid * 3 + 1] = make_float4((-0.5f * LOG2E) * Cc, o, col[0], col[1]);
+            s_rec[tid * 3 + 2] = make_float4(col[2], col[3], __int_as_float(g), 0.f);
+            s_mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
+        }
+        __syncthreads();
+        if (wmax <= lo) continue;
+        const unsigned short* my_list = s_list[warp] + LIST_PAD;
+        const int nl = build_list(s_mask, s_list[warp], min(cnt, wmax - lo), warp, lane);
+        for (int ii = nl - 1; ii >= 0; ii -= GB) {
+            unsigned present = 0;
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+                const int j = my_list[ii - u];
+                const float4 r0 = s_rec[j * 3 + 0];
+                const float4 r1 = s_rec[j * 3 + 1];
+                const float dx = r0.x - pxf, dy = r0.y - pyf;
+                const float p2 = fmaf(r1.x * dy, dy, fmaf(r0.w, dy, r0.z * dx) * dx);
+                const float G = ex2_approx(p2);
+                const float a = fminf(amax, r1.y * G);
+                const bool valid = ((lo + j) < last) && !(p2 > 0.0f) && (a >= ALPHA_MIN);
+                present |= (__ballot_sync(FULL, valid) != 0u) ? (1u << u) : 0u;
+                float fac = 0.f, go = 0.f;
+                if (valid) {
+                    const float ra = 1.0f / (1.0f - a);
+                    T *= ra;
+                    fac = a * T;
+                    float S = r1.z * vo[0];
+                    if (CH > 1) S = fmaf(r1.w, vo[1], S);
+                    if (CH > 2) {
+                        const float2 r2 = *reinterpret_cast<const float2*>(&s_rec[j * 3 + 2]);
+                        S = fmaf(r2.x, vo[2], S);
+                        if (CH > 3) S = fmaf(r2.y, vo[3], S);
+                    }
+                    const float v_al = fmaf(T, S, ra * (tail - D));
+                    D = fmaf(fac, S, D);
+                    if (!GSPLAT || (r1.y * G <= 0.999f)) go = G * v_al;
+                }
+                sbG[u * 32 + (lane ^ (4 * u))] = go;
+                sbF[u * 32 + (lane ^ (4 * u))] = fac;
+            }
+            if (present == 0u) continue;
+            __syncwarp();
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const int k0 = (8 * s4 + tig) ^ (4 * gid), k1 = (8 * s4 + tig + 4) ^ (4 * gid);
+                {
+                    const float b0 = sbG[gid * 32 + k0], b1 = sbG[gid * 32 + k1];
+                    const uint32_t b0h = to_tf32(b0), b1h = to_tf32(b1);
+                    const uint32_t b0l = to_tf32(b0 - __uint_as_float(b0h)), b1l = to_tf32(b1 - __uint_as_float(b1h));
+                    mma_tf32(acc, aG0[s4], 0u, aG2[s4], 0u, b0h, b1h);
+                    mma_tf32(acc, aG0[s4], 0u, aG2[s4], 0u, b0l, b1l);
+                }
+                {
+                    const float b0 = sbF[gid * 32 + k0], b1 = sbF[gid * 32 + k1];
+                    const uint32_t b0h = to_tf32(b0), b1h = to_tf32(b1);
+                    const uint32_t b0l = to_tf32(b0 - __uint_as_float(b0h)), b1l = to_tf32(b1 - __uint_as_float(b1h));
+                    mma_tf32(acc, 0u, aF1h[s4], 0u, aF3h[s4], b0h, b1h);
+                    mma_tf32(acc, 0u, aF1l[s4], 0u, aF3l[s4], b0h, b1h);
+                    mma_tf32(acc, 0u, aF1h[s4], 0u, aF3h[s4], b0l, b1l);
+                }
+            }
+            __syncwarp();
+            // acc[0], acc[1]: row gid (moment gid), entries 2*tig, 2*tig+1;  acc[2], acc[3]: row 8+gid (colour gid), same entries.
+            // Collect the six moments and the colour sums of entries 2*tig+e in the gid==0 lane of each tig.
+            float mom[2][6], csum[2][4];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                mom[0][r] = __shfl_sync(FULL, acc[0], (r << 2) | tig);
+                mom[1][r] = __shfl_sync(FULL, acc[1], (r << 2) | tig);
+            }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                csum[0][c] = __shfl_sync(FULL, acc[2], (c << 2) | tig);
+                csum[1][c] = __shfl_sync(FULL, acc[3], (c << 2) | tig);
+            }
+            if (gid == 0) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = 2 * tig + e;
+                    if (!((present >> n) & 1u)) continue;
+                    const int j = my_list[ii - n];
+                    const float4 r0 = s_rec[j * 3 + 0];
+                    const float4 r1 = s_rec[j * 3 + 1];
+                    const float A = r0.z * (-2.0f / LOG2E), B = r0.w * (-1.0f / LOG2E), Cc = r1.x * (-2.0f / LOG2E);
+                    const int g = __float_as_int(s_rec[j * 3 + 2].z);
+                    const float ex = r0.x - bcx, ey = r0.y - bcy;   // splat centre relative to the block centre; dx = ex - cx
+                    const float S0 = mom[e][0], Sx = mom[e][1], Sy = mom[e][2], Sxx = mom[e][3], Sxy = mom[e][4], Syy = mom[e][5];
+                    const float no = -r1.y;                          // v_sigma = -opacity * g
+                    const float M1 = no * (ex * S0 - Sx), M2 = no * (ey * S0 - Sy);
+                    const float M3 = no * (ex * ex * S0 - 2.0f * ex * Sx + Sxx);
+                    const float M4 = no * (ex * ey * S0 - ex * Sy - ey * Sx + Sxy);
+                    const float M5 = no * (ey * ey * S0 - 2.0f * ey * Sy + Syy);
+                    float* vx = v_xy + int64_t(g) * st.xs;
+                    float* vc = v_conic + int64_t(g) * st.cs;
+                    atomicAdd(vx, (A * M1 + B * M2) * sx);
+                    atomicAdd(vx + 1, (B * M1 + Cc * M2) * sy);
+                    atomicAdd(vc, 0.5f * M3);
+                    atomicAdd(vc + 1, M4);
+                    atomicAdd(vc + 2, 0.5f * M5);
+                    atomicAdd(v_opacity + int64_t(g) * st.os, S0);
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) atomicAdd(v_colors + int64_t(g) * st.ks + c, csum[e][c]);
+                }
+            }
+        }
+    }
+}
+
 template <int CH>
 int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy, const float* conic,
                  const float* opacity, const float* colors, const float* bg, float* image, int64_t ps, int64_t cs, float* final_T,
@@ -435,17 +671,25 @@ int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
     const SplatStrides st = row_stride > 0 ? SplatStrides{row_stride, row_stride, row_stride, row_stride} : SplatStrides{2, 3, 1, CH};
 #define B200GS_BWD_ARGS width, height, gx, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, final_T, n_contrib, \
                         v_image, ps, cs, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs
+#define B200GS_BWD_MMA_ARGS width, height, gx, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, final_T, n_contrib, \
+                            v_image, ps, cs, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors
+    static const bool use_mma = []() { const char* e = getenv("B200GS_BWD_MMA"); return !(e && e[0] == '0'); }();
     if (mode == B200GS_MODE_GSPLAT) {
         if (v_xy_abs)
             blend_bwd_kernel<CH, true, true, RB><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
+        else if (use_mma)
+            blend_bwd_mma_kernel<CH, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_MMA_ARGS);
         else
             blend_bwd_kernel<CH, true, false, RB><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
     } else {
         if (v_xy_abs)
             blend_bwd_kernel<CH, false, true, RB><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
+        else if (use_mma)
+            blend_bwd_mma_kernel<CH, false><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_MMA_ARGS);
         else
             blend_bwd_kernel<CH, false, false, RB><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
     }
+#undef B200GS_BWD_MMA_ARGS
 #undef B200GS_BWD_ARGS
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
