@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(BLOCK_PIX, 3) blend_bwd_mma_kernel(int width, 
             }
             if (present == 0u) continue;
             __syncwarp();
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f}, acc3[4] = {0.f, 0.f, 0.f, 0.f};   // independent MMA chains
 #pragma unroll
             for (int s4 = 0; s4 < 4; ++s4) {
                 const int k0 = (8 * s4 + tig) ^ (4 * gid), k1 = (8 * s4 + tig + 4) ^ (4 * gid);
@@ -581,17 +581,19 @@ __global__ void __launch_bounds__(BLOCK_PIX, 3) blend_bwd_mma_kernel(int width, 
                     const uint32_t b0h = to_tf32(b0), b1h = to_tf32(b1);
                     const uint32_t b0l = to_tf32(b0 - __uint_as_float(b0h)), b1l = to_tf32(b1 - __uint_as_float(b1h));
                     mma_tf32(acc, aG0[s4], 0u, aG2[s4], 0u, b0h, b1h);
-                    mma_tf32(acc, aG0[s4], 0u, aG2[s4], 0u, b0l, b1l);
+                    mma_tf32(acc2, aG0[s4], 0u, aG2[s4], 0u, b0l, b1l);
                 }
                 {
                     const float b0 = sbF[gid * 32 + k0], b1 = sbF[gid * 32 + k1];
                     const uint32_t b0h = to_tf32(b0), b1h = to_tf32(b1);
                     const uint32_t b0l = to_tf32(b0 - __uint_as_float(b0h)), b1l = to_tf32(b1 - __uint_as_float(b1h));
-                    mma_tf32(acc, 0u, aF1h[s4], 0u, aF3h[s4], b0h, b1h);
-                    mma_tf32(acc, 0u, aF1l[s4], 0u, aF3l[s4], b0h, b1h);
+                    mma_tf32(acc3, 0u, aF1h[s4], 0u, aF3h[s4], b0h, b1h);
+                    mma_tf32(acc2, 0u, aF1l[s4], 0u, aF3l[s4], b0h, b1h);
                     mma_tf32(acc, 0u, aF1h[s4], 0u, aF3h[s4], b0l, b1l);
                 }
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] += acc2[q] + acc3[q];
             __syncwarp();
             // acc[0], acc[1]: row gid (moment gid), entries 2*tig, 2*tig+1;  acc[2], acc[3]: row 8+gid (colour gid), same entries.
             // Collect the six moments and the colour sums of entries 2*tig+e in the gid==0 lane of each tig.
@@ -673,7 +675,10 @@ int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
                         v_image, ps, cs, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs
 #define B200GS_BWD_MMA_ARGS width, height, gx, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, final_T, n_contrib, \
                             v_image, ps, cs, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors
-    static const bool use_mma = []() { const char* e = getenv("B200GS_BWD_MMA"); return !(e && e[0] == '0'); }();
+    // opt-in (B200GS_BWD_MMA=1): measured 0.89 ms vs 0.69 ms for the shuffle butterfly at 1 M Gaussians / 1080p — the TF32 hi/lo
+    // splits, the lane->fragment staging and the writer algebra cost as many issue slots as the butterfly saves (677 M vs
+    // ~620 M warp instructions, ncu), so the shuffle kernel stays the default.
+    static const bool use_mma = []() { const char* e = getenv("B200GS_BWD_MMA"); return e && e[0] == '1'; }();
     if (mode == B200GS_MODE_GSPLAT) {
         if (v_xy_abs)
             blend_bwd_kernel<CH, true, true, RB><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
