@@ -228,40 +228,13 @@ __device__ __forceinline__ void load_sh_any(const float* __restrict__ shs, const
     }
 }
 
-// Warp-cooperative load of 32 consecutive rows of a row-major [*, rw] fp32 array (rw <= 48) into shared memory (row stride
-// rw|1: conflict-free per-lane row reads) with fully coalesced 128-bit loads.  A thread reading its own 180/192-byte row
-// directly touches 32 different sectors per load instruction; this touches each sector once.
-__device__ __forceinline__ void warp_load_rows(const float* __restrict__ src, int64_t i0, int rw, float* __restrict__ sw, unsigned lane) {
-    const int rwp = rw | 1;
-    const float* base = src + i0 * rw;
-    const int total = 32 * rw;
-    if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
-        for (int idx = lane; idx * 4 + 3 < total; idx += 32) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(base) + idx);
-            const float tv[4] = {t.x, t.y, t.z, t.w};
-            int f = idx * 4, r = f / rw, c = f - r * rw;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                sw[r * rwp + c] = tv[e];
-                if (++c == rw) { c = 0; ++r; }
-            }
-        }
-        for (int f = (total & ~3) + lane; f < total; f += 32) sw[(f / rw) * rwp + f % rw] = __ldg(base + f);
-    } else {
-        for (int f = lane; f < total; f += 32) sw[(f / rw) * rwp + f % rw] = __ldg(base + f);
-    }
-    __syncwarp();
-}
-
-constexpr int PROJ_THREADS = 128;
-
 template <bool GSPLAT>
 __device__ __forceinline__ float near_of(const B200gsView& v) {
     return v.near_plane > 0.f ? v.near_plane : (GSPLAT ? 0.01f : 0.2f);
 }
 
 template <bool GSPLAT, bool RAW>
-__global__ void __launch_bounds__(PROJ_THREADS) project_fwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
+__global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
                                                           const float* __restrict__ means, const float* __restrict__ scales,
                                                           const float* __restrict__ quats, const float* __restrict__ shs,
                                                           float2* __restrict__ xy_out, float* __restrict__ depth_out,
@@ -340,33 +313,11 @@ __global__ void __launch_bounds__(PROJ_THREADS) project_fwd_kernel(const __grid_
     if (shs != nullptr) {
         float r = 0.f, gc = 0.f, bc = 0.f;
         uint8_t cl = 0;
-        const int deg = v.sh_degree;
-        const int ncoef = (deg + 1) * (deg + 1);
-        // full warps stage their 32 SH rows through shared memory with coalesced loads (when most of a row is needed)
-        __shared__ float s_rows[PROJ_THREADS / 32][32 * 49];
-        const unsigned lane = threadIdx.x & 31u;
-        const int rw = (RAW ? v.sh_stride - 1 : v.sh_stride) * 3;
-        const int need = ncoef * 3 - (RAW ? 3 : 0);
-        bool staged = false;
-        if ((i - lane + 31) < n && rw <= 48 && need * 2 > rw) {      // warp-uniform
-            if (__ballot_sync(0xffffffffu, vis) != 0u) {
-                warp_load_rows(RAW ? raw.shs_rest : shs, i - lane, rw, s_rows[threadIdx.x >> 5], lane);
-                staged = true;
-            }
-        }
         if (vis) {
+            const int deg = v.sh_degree;
+            const int ncoef = (deg + 1) * (deg + 1);
             float sh[MAX_COEFFS * 3];
-            if (staged) {
-                const float* row = s_rows[threadIdx.x >> 5] + lane * (rw | 1);
-                if (RAW) { sh[0] = __ldg(shs + 3 * i); sh[1] = __ldg(shs + 3 * i + 1); sh[2] = __ldg(shs + 3 * i + 2); }
-#pragma unroll
-                for (int q = 0; q < MAX_COEFFS * 3; ++q) {
-                    const int c = RAW ? q - 3 : q;
-                    if (c >= 0 && q < ncoef * 3) sh[q] = row[c];
-                }
-            } else {
-                load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
-            }
+            load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
             float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
             const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
             dx *= inv_len; dy *= inv_len; dz *= inv_len;
@@ -497,7 +448,7 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
         if (vis && !GSPLAT && deg > 0) {
             // view direction -> mean (dgr back-propagates it; gsplat renderers detach the direction)
             float sh[MAX_COEFFS * 3];
-            load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);   // (cooperative staging is done by K1; here the rows are L2-warm)
+            load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
             float bx[MAX_COEFFS], by[MAX_COEFFS], bz[MAX_COEFFS];
             sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
@@ -744,7 +695,7 @@ int launch_project_fwd_raw(const B200gsView& v, int64_t n, const float* means, c
                            float* depth, int32_t* radii, float* conic, float* comp, int32_t* tiles, float* cov3d, float* rgb,
                            uint8_t* clamped, float* opac_out, cudaStream_t s) {
     if (n == 0) return B200GS_OK;
-    const int threads = PROJ_THREADS;
+    const int threads = 256;
     const unsigned blocks = (unsigned)div_up64(n, threads);
     const bool raw_mode = opac_out != nullptr;
     RawIO raw{opac_logits, shs_rest, opac_out, nullptr, nullptr, nullptr, anti_aliased, nullptr, nullptr, 0};
