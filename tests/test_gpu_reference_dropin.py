@@ -127,6 +127,27 @@ def test_reference_gsplat_renderer_runs_on_b200gs(ref):
     assert _rel(out["viewspace_points"].grad, vs_ref) < 2e-3
 
 
+def test_reference_python_preprocess_renderer_agrees(ref):
+    """configs[0] of BASELINE.json names the reference's PythonPreprocessGSplatRenderer (its own torch projection,
+    internal/utils/gaussian_projection.py, feeding the gsplat rasterizer) as the CPU-runnable reference path.  Run THAT class
+    unmodified (torch projection on the GPU, our SH + binning + blend underneath through the aliased gsplat modules) and compare
+    the picture with B200GSplatRenderer, whose K1 restates the same projection: the two images must agree to fp32-projection
+    noise (the python projection is fp32; K1 evaluates the same formulas in fp64)."""
+    from internal.renderers.pypreprocess_gsplat_renderer import PythonPreprocessGSplatRenderer
+    from b200gs.renderers import B200GSplatRenderer
+    raw, model, cam, W, H = _setup(ref)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=DEV)
+    with torch.no_grad():
+        out_py = PythonPreprocessGSplatRenderer()(cam, model, bg)
+        out = B200GSplatRenderer().to(DEV)(cam, model, bg)
+    assert out_py["render"].shape == out["render"].shape == (3, H, W)
+    diff = (out_py["render"] - out["render"]).abs()
+    assert float(diff.mean()) < 2e-5 and float(diff.max()) < 2e-2      # isolated radius/threshold flips of the fp32 python projection
+    assert int((diff > 1e-3).sum()) < 0.002 * diff.numel()
+    same_vis = (out_py["visibility_filter"] == out["visibility_filter"]).float().mean()
+    assert float(same_vis) > 0.999
+
+
 def test_training_step_shape_with_reference_objects(ref):
     """The sequence GaussianSplatting.training_step performs around the renderer (internal/gaussian_splatting.py:341-397):
     forward -> L1 + (1 - SSIM) loss with the reference's own ssim -> retain_grad -> backward -> the density controller's
