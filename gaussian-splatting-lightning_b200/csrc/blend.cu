@@ -112,8 +112,12 @@ __device__ __forceinline__ int build_list(const unsigned char* __restrict__ s_ma
     return n;
 }
 
+#ifndef B200GS_FWD_MINBLOCKS
+#define B200GS_FWD_MINBLOCKS 1
+#endif
+
 template <int CH, bool GSPLAT>
-__global__ void __launch_bounds__(BLOCK_PIX) blend_fwd_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
+__global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
                                                               const int32_t* __restrict__ ids, const SplatStrides st, const float* __restrict__ xy,
                                                               const float* __restrict__ conic, const float* __restrict__ opacity,
                                                               const float* __restrict__ colors, const float* __restrict__ bg,
