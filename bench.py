@@ -205,12 +205,17 @@ def workload_config(args, parallelism):
 
 
 # bytes per view, SURVEY.md §8(d) / BASELINE.md §5 (V visible, I pairs, P pixels, N total; SH degree 3)
-def algorithmic_bytes(stage, N, V, I, P, n_tiles):
+def algorithmic_bytes(stage, N, V, I, P, n_tiles, C=None):
     """I = (tile, Gaussian) pairs the stage actually processes (after exact tile culling)."""
     return {
         "project_fwd": V * 268 + N * 16,
-        "bin_count": N * (16 + 4 * 16 + 8 + 12),      # keys+ids+tiles write, 4 radix passes of 8 B pairs (r+w), scan
-        "bin_sort": V * 24 + I * 8 + I * (4 + 2 * 16) + I * 4 + n_tiles * 8,  # emit, 2-pass 8 B pair partition, ranges
+        # xy/depth/radius/conic/opacity read, keys+ids+cells+32 B record write, 4 radix passes of 8 B pairs (r+w), scan (id, gathered
+        # cell count, 8 B offset)
+        "bin_count": N * (32 + 44 + 4 * 16 + 16),
+        # C = (8x8-tile cell, Gaussian) pairs (~2.5 per visible splat).  emit: order + 32 B record + offset per splat, 18 B
+        # (key + {mask, id}) per coarse pair; one radix pass over them (18 B r+w) + histogram read; ranges 2 B; chunk counts 8 B;
+        # scatter 16 B; every fine pair's id written ONCE (4 B); tile starts / ranges 24 B per tile
+        "bin_sort": V * 44 + (C if C is not None else int(2.5 * V)) * (18 + 2 + 36 + 2 + 8 + 16) + I * 4 + n_tiles * 24,
         "blend_fwd": I * 40 + P * 20,
         "blend_bwd": I * 76 + P * 20,
         "project_bwd": V * 552,
@@ -218,7 +223,7 @@ def algorithmic_bytes(stage, N, V, I, P, n_tiles):
     }.get(stage, 0)
 
 
-LAUNCHES_PER_STEP = {"project_fwd": 1, "bin_count": 1 + 6 + 2 + 1, "bin_sort": 1 + 4 + 1, "blend_fwd": 1, "blend_bwd": 1, "project_bwd": 1}
+LAUNCHES_PER_STEP = {"project_fwd": 1, "bin_count": 1 + 1 + 6 + 2, "bin_sort": 1 + 1 + 1 + 3 + 1 + 1 + 1 + 1 + 1, "blend_fwd": 1, "blend_bwd": 1, "project_bwd": 1}
 
 
 def main():
@@ -362,12 +367,13 @@ def main():
                                                                             model.get_rotation.detach().contiguous(), None, True)
         I = int(tiles.sum())
         opac_act = model.get_opacity.detach().reshape(-1).contiguous() * (comp if args.mode == "gsplat" else 1.0)
-        I_culled = ops.bin_gaussians(mode_id, W, H, xy, depth, radii, conic, opac_act.contiguous()).total
+        binned = ops.bin_gaussians(mode_id, W, H, xy, depth, radii, conic, opac_act.contiguous())
+        I_culled, C_coarse = binned.total, binned.coarse_pairs
     P = W * H
     hbm_peak, peak_src = peaks()
     kernels = {}
     for k, ms in stage_ms.items():
-        b = algorithmic_bytes(k, N, V, I_culled, P, gx * gy)
+        b = algorithmic_bytes(k, N, V, I_culled, P, gx * gy, C_coarse)
         kernels[k] = {"ms": round(ms, 4), "alg_bytes": b, "gbs": round(b / (ms * 1e-3) / 1e9, 1), "launches": LAUNCHES_PER_STEP.get(k, 1)}
     top = max(stage_ms, key=stage_ms.get)
     ach = kernels[top]["gbs"]
@@ -394,7 +400,7 @@ def main():
                      "traffic": traffic, "peak_source": peak_src,
                      "note": "blend kernels are SM-issue (FP32+MUFU) bound, not HBM bound (SURVEY §8d); HBM fraction reported as asked"},
         "kernels": kernels,
-        "scene": {"N": N, "V": V, "I": I, "I_after_exact_culling": I_culled, "P": P, "stage_sum_ms": round(sum(stage_ms.values()), 4)},
+        "scene": {"N": N, "V": V, "I": I, "I_after_exact_culling": I_culled, "coarse_pairs": C_coarse, "P": P, "stage_sum_ms": round(sum(stage_ms.values()), 4)},
     }
     if not args.no_cpu_baseline and world == 1:
         vps, med, cores, kind = cpu_projection_views_per_sec(N, W, H, args.mode, args.cpu_sample_iters)

@@ -36,7 +36,7 @@ using namespace b200gs;
 extern "C" {
 
 const char* b200gs_last_error(void) { return g_error; }
-int b200gs_version(void) { return 100; }
+int b200gs_version(void) { return 200; }
 
 int b200gs_project_fwd(const B200gsView* view, int64_t n, const float* means, const float* scales, const float* quats,
                        const float* shs, float* xy, float* depth, int32_t* radii, float* conic, float* comp,
@@ -145,35 +145,34 @@ int b200gs_sh_bwd(int32_t degree, int32_t sh_stride, int64_t n, const float* dir
 
 size_t b200gs_bin_count_workspace_bytes(int64_t n) { return n < 0 ? 0 : bin_count_workspace_bytes(n); }
 
-size_t b200gs_bin_sort_workspace_bytes(int64_t n, int64_t max_pairs, int32_t width, int32_t height) {
-    if (n < 0 || max_pairs < 0) return 0;
-    return bin_sort_workspace_bytes(n, max_pairs, width, height);
+size_t b200gs_bin_sort_workspace_bytes(int64_t n, int64_t max_coarse, int32_t width, int32_t height) {
+    if (n < 0 || max_coarse < 0 || width <= 0 || height <= 0) return 0;
+    return bin_sort_workspace_bytes(n, max_coarse, width, height);
 }
 
 int b200gs_bin_count(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const float* depth,
-                     const int32_t* radii, const float* cull_conic, const float* cull_opacity, void* workspace,
-                     size_t workspace_bytes, int64_t* d_total, int64_t* host_total, int32_t sync_host, void* stream) {
+                     const int32_t* radii, const float* cull_conic, const float* cull_opacity, void* workspace, size_t workspace_bytes,
+                     int64_t* d_counts, int64_t* host_counts, int32_t sync_host, void* stream) {
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
     B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0, "bad size");
-    B200GS_CHECK_ARG(workspace && d_total, "workspace/d_total must not be NULL");
+    B200GS_CHECK_ARG(workspace && d_counts, "workspace/d_counts must not be NULL");
     B200GS_CHECK_ARG(n == 0 || (xy && depth && radii), "NULL pointer");
     B200GS_CHECK_ARG(n < (int64_t(1) << 31), "n >= 2^31");
     B200GS_CHECK_ARG((cull_conic == nullptr) == (cull_opacity == nullptr), "cull_conic and cull_opacity go together");
-    return bin_count(mode, width, height, n, 0, xy, depth, radii, cull_conic, cull_opacity, workspace, workspace_bytes, d_total,
-                     host_total, sync_host, (cudaStream_t)stream);
+    return bin_count(mode, width, height, n, 0, xy, depth, radii, cull_conic, cull_opacity, workspace, workspace_bytes, d_counts,
+                     host_counts, sync_host, (cudaStream_t)stream);
 }
 
-int b200gs_bin_sort(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const int32_t* radii,
-                    const float* cull_conic, const float* cull_opacity, int64_t total, const int64_t* d_total, int64_t max_pairs, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes,
-                    int32_t* sorted_ids, int32_t* tile_ranges, void* stream) {
+int b200gs_bin_sort(int32_t mode, int32_t width, int32_t height, int64_t n, int32_t cull, int64_t max_coarse, int64_t max_pairs,
+                    int64_t* d_counts, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes, int32_t* sorted_ids,
+                    int32_t* tile_ranges, int64_t* host_counts, int32_t sync_host, void* stream) {
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
-    B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0 && max_pairs >= 0, "bad size");
-    B200GS_CHECK_ARG(d_total != nullptr, "d_total must not be NULL");
+    B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0 && max_pairs >= 0 && max_coarse >= 0, "bad size");
+    B200GS_CHECK_ARG(d_counts != nullptr, "d_counts must not be NULL");
     B200GS_CHECK_ARG(workspace_a && workspace_b && tile_ranges, "workspace/tile_ranges must not be NULL");
-    B200GS_CHECK_ARG(total == 0 || (xy && radii && sorted_ids), "NULL pointer");
-    B200GS_CHECK_ARG((cull_conic == nullptr) == (cull_opacity == nullptr), "cull_conic and cull_opacity go together");
-    return bin_sort(mode, width, height, n, 0, xy, radii, cull_conic, cull_opacity, total, d_total, max_pairs, workspace_a, workspace_b, workspace_b_bytes, sorted_ids,
-                    tile_ranges, (cudaStream_t)stream);
+    B200GS_CHECK_ARG(n == 0 || max_coarse == 0 || sorted_ids, "NULL pointer");
+    return bin_sort(mode, width, height, n, cull, max_coarse, max_pairs, d_counts, workspace_a, workspace_b, workspace_b_bytes,
+                    sorted_ids, tile_ranges, host_counts, sync_host, (cudaStream_t)stream);
 }
 
 int b200gs_blend_fwd(int32_t mode, int32_t width, int32_t height, int32_t channels, const int32_t* tile_ranges,
@@ -224,25 +223,14 @@ int b200gs_unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offs
 }
 
 int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull, void* workspace,
-                          size_t workspace_bytes, int64_t* d_total, int64_t* host_total, int32_t sync_host, void* stream) {
+                          size_t workspace_bytes, int64_t* d_counts, int64_t* host_counts, int32_t sync_host, void* stream) {
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
     B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0 && n < (int64_t(1) << 31), "bad size");
-    B200GS_CHECK_ARG(workspace && d_total && (n == 0 || rows), "NULL pointer");
+    B200GS_CHECK_ARG(workspace && d_counts && (n == 0 || rows), "NULL pointer");
     return bin_count(mode, width, height, n, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY, rows + B200GS_ROW_DEPTH,
                      (const int32_t*)(rows + B200GS_ROW_RADIUS), cull ? rows + B200GS_ROW_CONIC : nullptr,
-                     cull ? rows + B200GS_ROW_OPACITY : nullptr, workspace, workspace_bytes, d_total, host_total, sync_host,
+                     cull ? rows + B200GS_ROW_OPACITY : nullptr, workspace, workspace_bytes, d_counts, host_counts, sync_host,
                      (cudaStream_t)stream);
-}
-
-int b200gs_bin_sort_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull, int64_t total,
-                         const int64_t* d_total, int64_t max_pairs, const void* workspace_a, void* workspace_b,
-                         size_t workspace_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges, void* stream) {
-    B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
-    B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0 && max_pairs >= 0, "bad size");
-    B200GS_CHECK_ARG(d_total && workspace_a && workspace_b && tile_ranges && (n == 0 || rows), "NULL pointer");
-    return bin_sort(mode, width, height, n, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY, (const int32_t*)(rows + B200GS_ROW_RADIUS),
-                    cull ? rows + B200GS_ROW_CONIC : nullptr, cull ? rows + B200GS_ROW_OPACITY : nullptr, total, d_total, max_pairs,
-                    workspace_a, workspace_b, workspace_b_bytes, sorted_ids, tile_ranges, (cudaStream_t)stream);
 }
 
 int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,

@@ -1,19 +1,23 @@
 // K2-K5: tile binning.
 //
 // The reference backends sort I (tile,Gaussian) pairs on a 64-bit (tile | depth-bits) key: ~6 radix passes over
-// 12 B pairs (I*152 B, the largest pure-bandwidth term of the forward).  The same total order — tile
-// major, then depth bits, ties in Gaussian-id order (radix sort is stable and pairs are emitted Gaussian-major) — is
-// produced here with ~4x less traffic:
-//   A. stable radix sort of the N per-Gaussian depth keys (32-bit float bits; culled -> 0xFFFFFFFF)      [N * 16 B * 4 passes]
-//   B. scan of tiles-per-Gaussian in depth order -> pair offsets, total I
-//   C. emit pairs in depth order: key = tile id (needs only ceil(log2 tiles) bits), value = Gaussian id   [I * 8 B]
-//   D. stable radix partition of the pairs by tile id (2 passes at <= 16 bits)                            [I * ~36 B]
-//   E. tile ranges from the partitioned keys                                                              [I * 4 B]
-// Stable(depth) followed by stable(tile) == stable sort on (tile, depth) — tests compare against the oracle's
-// torch.sort(stable) of the 64-bit keys, element for element.
+// 12 B pairs (I*152 B, the largest pure-bandwidth term of their forward).  The same total order — tile
+// major, then depth bits, ties in Gaussian-id order — is produced here hierarchically, and the fine pairs are written
+// exactly once, already in place:
+//   A. depth keys (32-bit float bits; off-screen -> 0xFFFFFFFF), stable radix sort of the N keys, scan of the
+//      per-Gaussian COARSE cell counts in depth order (a coarse cell = 8x8 tiles = 128x128 px)
+//   B. emit (coarse cell, Gaussian) pairs in depth order and stable-partition them by cell: ONE 8-bit radix pass over
+//      ~2.5 pairs per visible Gaussian for every image up to 2048x2048 (<= 256 cells)
+//   C. per 256-entry chunk of a cell's list: the exact 64-bit mask of the cell's tiles each splat can reach (row spans
+//      of the alpha >= 1/255 ellipse, or the plain 3-sigma rect with culling off) and the chunk's per-tile counts
+//   D. per cell: prefix of the chunk counts; one scan over the tiles -> tile_ranges and the pair total
+//   E. every chunk writes its splat ids to sorted_ids at (tile start + chunk prefix + rank inside the chunk), ranks
+//      from warp ballots in list order
+// A stable multi-split keeps the depth order inside every tile, so the result equals the oracle's torch.sort(stable)
+// of the 64-bit keys element for element (tests/test_gpu_parity.py::test_binning_exact).
 //
-// Round 1: the device-wide scan and the two radix sorts are cub:: primitives (header library compiled into this .so);
-// the emit / key / range kernels are ours.  Replacing D by a fused emit+partition kernel is the next step.
+// cub:: provides the device-wide scan and the two radix sorts (header library compiled into this .so); everything else
+// is ours.
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -22,21 +26,38 @@ namespace b200gs {
 
 namespace {
 
+constexpr int SUPER_SHIFT = 3;             // coarse cell = 8 x 8 tiles
+constexpr int SUPER = 1 << SUPER_SHIFT;
+constexpr int CELL_TILES = SUPER * SUPER;  // 64: one bit per tile in a uint64_t mask
+constexpr int CHUNK = 256;                 // list entries per block of the count / scatter kernels
+
+// What phase B needs to know about a Gaussian, packed by phase A into ONE 32-byte L2 sector (phase B visits the
+// Gaussians in depth order, i.e. at random addresses).
+struct __align__(16) SplatRec {
+    float x, y, A, B, C, opacity;
+    int32_t radius, ncells;
+};
+static_assert(sizeof(SplatRec) == 32, "SplatRec must be one sector");
+
+// value type of the coarse partition: {tile mask lo, tile mask hi, Gaussian id, unused}
+typedef uint4 CellEntry;
+
 struct LayoutA {
-    size_t keys_in, keys_out, ids_in, order, tiles, offsets, temp, temp_bytes, total;
+    size_t keys_in, keys_out, ids_in, order, cells, offsets, recs, temp, temp_bytes, total;
 };
 struct LayoutB {
-    size_t pkeys_in, pkeys_out, pvals_in, temp, temp_bytes, total;
+    size_t ckeys_in, ckeys_out, cvals_in, entries, temp, temp_bytes, cell_ranges, chunk_base, chunk_cell, chunk_cnt, chunk_pre, tile_start, total;
+    int64_t max_chunks;
 };
 
-struct TilesOfOrder {
-    const int32_t* tiles;
-    __host__ __device__ int64_t operator()(int32_t g) const { return (int64_t)tiles[g]; }
+struct CellsOfOrder {
+    const int32_t* cells;
+    __host__ __device__ int64_t operator()(int32_t g) const { return (int64_t)cells[g]; }
 };
 
-inline int tile_bits_for(int n_tiles) {
+inline int bits_for(int n_values) {
     int b = 1;
-    while ((1 << b) < n_tiles) ++b;
+    while ((1 << b) < n_values) ++b;
     return b;
 }
 
@@ -60,12 +81,13 @@ LayoutA make_layout_a(int64_t n) {
     L.keys_out = take(nn * 4);
     L.ids_in = take(nn * 4);
     L.order = take(nn * 4);
-    L.tiles = take(nn * 4);
+    L.cells = take(nn * 4);
     L.offsets = take(nn * 8);
+    L.recs = take(nn * sizeof(SplatRec));
     size_t t_sort = 0, t_scan = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, t_sort, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
                                     (int32_t*)nullptr, (int)nn, 0, 32);
-    cub::TransformInputIterator<int64_t, TilesOfOrder, const int32_t*> it(nullptr, TilesOfOrder{nullptr});
+    cub::TransformInputIterator<int64_t, CellsOfOrder, const int32_t*> it(nullptr, CellsOfOrder{nullptr});
     cub::DeviceScan::InclusiveSum(nullptr, t_scan, it, (int64_t*)nullptr, (int)nn);
     L.temp_bytes = t_sort > t_scan ? t_sort : t_scan;
     L.temp = take(L.temp_bytes);
@@ -75,28 +97,48 @@ LayoutA make_layout_a(int64_t n) {
     return L;
 }
 
-LayoutB make_layout_b(int64_t max_pairs) {
+inline void cell_grid(int width, int height, int& grid_x, int& grid_y, int& cgrid_x, int& cgrid_y) {
+    grid_x = div_up(width, TILE);
+    grid_y = div_up(height, TILE);
+    cgrid_x = div_up(grid_x, SUPER);
+    cgrid_y = div_up(grid_y, SUPER);
+}
+
+LayoutB make_layout_b(int64_t max_coarse, int width, int height) {
     static thread_local int64_t cached_p = -1;
+    static thread_local int cached_w = -1, cached_h = -1;
     static thread_local LayoutB cached{};
-    if (max_pairs == cached_p) return cached;
+    if (max_coarse == cached_p && width == cached_w && height == cached_h) return cached;
+    int grid_x, grid_y, cgrid_x, cgrid_y;
+    cell_grid(width, height, grid_x, grid_y, cgrid_x, cgrid_y);
+    const size_t n_cells = (size_t)cgrid_x * cgrid_y, n_tiles = (size_t)grid_x * grid_y;
     LayoutB L{};
     Taker take;
-    const size_t pp = (size_t)(max_pairs > 0 ? max_pairs : 1);
-    L.pkeys_in = take(pp * 4);
-    L.pkeys_out = take(pp * 4);
-    L.pvals_in = take(pp * 4);
-    size_t t_psort = 0, t_psort16 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t_psort, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
-                                    (int32_t*)nullptr, (int)pp, 0, 16);
-    cub::DeviceRadixSort::SortPairs(nullptr, t_psort16, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const int32_t*)nullptr,
-                                    (int32_t*)nullptr, (int)pp, 0, 16);
-    if (t_psort16 > t_psort) t_psort = t_psort16;
-    L.temp_bytes = t_psort;
-    L.temp = take(t_psort);
+    const size_t pp = (size_t)(max_coarse > 0 ? max_coarse : 1);
+    L.max_chunks = (int64_t)(pp / CHUNK + n_cells + 1);
+    L.ckeys_in = take(pp * 4);
+    L.ckeys_out = take(pp * 4);
+    L.cvals_in = take(pp * sizeof(CellEntry));
+    L.entries = take(pp * sizeof(CellEntry));
+    size_t t32 = 0, t16 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t32, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const CellEntry*)nullptr,
+                                    (CellEntry*)nullptr, (int)pp, 0, 32);
+    cub::DeviceRadixSort::SortPairs(nullptr, t16, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const CellEntry*)nullptr,
+                                    (CellEntry*)nullptr, (int)pp, 0, 16);
+    L.temp_bytes = t32 > t16 ? t32 : t16;
+    L.temp = take(L.temp_bytes);
+    L.cell_ranges = take(n_cells * 8);
+    L.chunk_base = take((n_cells + 1) * 4);
+    L.chunk_cell = take((size_t)L.max_chunks * 4);
+    L.chunk_cnt = take((size_t)L.max_chunks * CELL_TILES * 2);
+    L.chunk_pre = take((size_t)L.max_chunks * CELL_TILES * 4);
+    L.tile_start = take(n_tiles * 8);
     L.total = take.off;
     cached = L;
-    cached_p = max_pairs;
-    return L;
+    cached_p = max_coarse;
+    cached_w = width;
+    cached_h = height;
+    return cached;
 }
 
 // ---- exact tile culling ------------------------------------------------------------------------------------------------
@@ -105,12 +147,13 @@ LayoutB make_layout_b(int64_t max_pairs) {
 // E and a tile ROW (a band of 16 sample rows) are convex, so the tiles of that row that meet E are exactly those whose
 // sample columns meet the x-extent of (E ∩ band): one interval per row, from two clamped evaluations of the ellipse's
 // left/right boundary.  Cost O(rows) per Gaussian instead of O(tiles); every pair dropped would have been skipped by
-// the blend loop at all 256 pixels, so images and gradients are bit-identical while the pair list (sort, staging,
-// blend evaluations) shrinks ~1.8x on the benchmark scene.  The threshold carries a margin for the fp32 / ex2.approx
-// rounding of the blend loop, the interval a 0.01 px slack; round-to-nearest intrinsics pin the arithmetic so that the
-// counting and the emitting kernel agree on every pair.
-// Per-Gaussian inputs of the binning kernels, with element strides: separate contiguous arrays ({2,1,1,3,1}) or columns
-// of one [n,12] row buffer ({12,12,12,12,12}).
+// the blend loop at all 256 pixels, so images and gradients are bit-identical while the pair list (staging, blend
+// evaluations) shrinks ~1.8x on the benchmark scene.  The test only has to be conservative: the threshold carries a
+// relative margin of 1e-4 (+1e-3), the interval a 0.01 px slack — orders of magnitude above the error of the
+// approximate sqrt used here and of the fp32 / ex2.approx rounding of the blend loop.  Each pair's verdict is computed
+// exactly once (emit_cells_kernel) and travels with the pair, so no two kernels ever have to agree on it.
+// Per-Gaussian inputs of phase A, with element strides: separate contiguous arrays ({2,1,1,3,1}) or columns of one
+// [n,12] row buffer ({12,12,12,12,12}).
 struct BinSrc {
     const float* xy; const float* depth; const int32_t* radii; const float* conic; const float* opacity;
     int xs, ds, rs, cs, os;
@@ -120,34 +163,38 @@ struct BinSrc {
 };
 
 struct CullE {
-    float mx, my, A, B, iA, two_tA, det, ymax, yR;
+    float mx, my, B, iA, two_tA, det, ymax, yR;
     int mode;  // 0: full rect (culling off / degenerate conic), 1: spans, 2: nothing visible (opacity <= 1/255)
 };
 
-__device__ __forceinline__ CullE load_cull(const float2 p, const BinSrc& src, int64_t g) {
-    const float* conic = src.conic ? src.conic + g * src.cs : nullptr;
-    const float* opacity = src.opacity ? src.opacity + g * src.os : nullptr;
+__device__ __forceinline__ CullE make_cull(const SplatRec& r, bool cull) {
     CullE e;
-    e.mx = p.x; e.my = p.y;
-    e.A = 1.f; e.B = 0.f; e.iA = 1.f; e.two_tA = 0.f; e.det = 1.f; e.ymax = 0.f; e.yR = 0.f;
+    e.mx = r.x; e.my = r.y;
+    e.B = 0.f; e.iA = 1.f; e.two_tA = 0.f; e.det = 1.f; e.ymax = 0.f; e.yR = 0.f;
     e.mode = 0;
-    if (conic == nullptr) return e;
-    const float A = __ldg(conic), B = __ldg(conic + 1), C = __ldg(conic + 2);
-    const float o255 = 255.0f * __ldg(opacity);
+    if (!cull) return e;
+    const float A = r.A, B = r.B, C = r.C;
+    const float o255 = 255.0f * r.opacity;
     if (o255 <= 1.0f) { e.mode = 2; return e; }
-    // alpha >= 1/255  <=>  q <= ln(255 o); margin covers the fp32 / ex2.approx rounding of the blend loop
-    const float t = __fmaf_rn(__logf(o255), 1.0001f, 1e-3f);
-    const float det = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, B));
+    // alpha >= 1/255  <=>  q <= ln(255 o); margin covers every rounding here and in the blend loop
+    const float t = __logf(o255) * 1.0001f + 1e-3f;
+    const float det = A * C - B * B;
     if (!(det > 0.f) || !(A > 0.f) || !(C > 0.f) || !(t < 3.0e38f)) return e;  // degenerate / NaN: keep the full rect
     const float idet = __frcp_rn(det);
-    e.A = A; e.B = B; e.iA = __frcp_rn(A);
-    e.two_tA = __fmul_rn(__fmul_rn(2.0f, t), A);
+    e.B = B; e.iA = __frcp_rn(A);
+    e.two_tA = 2.0f * t * A;
     e.det = det;
-    e.ymax = __fsqrt_rn(__fmul_rn(e.two_tA, idet));
-    const float xext = __fsqrt_rn(__fmul_rn(__fmul_rn(__fmul_rn(2.0f, t), C), idet));
-    e.yR = __fmul_rn(__fmul_rn(-B, xext), __frcp_rn(C));  // the ellipse's rightmost point sits at y = yR, leftmost at -yR
+    e.ymax = __fsqrt_rn(e.two_tA * idet);
+    const float xext = __fsqrt_rn(2.0f * t * C * idet);
+    e.yR = -B * xext * __frcp_rn(C);  // the ellipse's rightmost point sits at y = yR, leftmost at -yR
     e.mode = 1;
     return e;
+}
+
+__device__ __forceinline__ float sqrt_fast(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // tiles [a, b) of tile row ty (clipped to [x0, x1)) whose pixel samples can meet the ellipse
@@ -156,18 +203,18 @@ __device__ __forceinline__ bool row_span(const CullE& e, int ty, int x0, int x1,
     a = x0; b = x1;
     if (e.mode == 0) return true;
     const float off = GSPLAT ? 0.5f : 0.0f;
-    const float Y0 = __fsub_rn(__fadd_rn(float(ty * TILE), off), e.my);
-    const float ya = fmaxf(Y0, -e.ymax), yb = fminf(__fadd_rn(Y0, float(TILE - 1)), e.ymax);
+    const float Y0 = float(ty * TILE) + off - e.my;
+    const float ya = fmaxf(Y0, -e.ymax), yb = fminf(Y0 + float(TILE - 1), e.ymax);
     if (ya > yb) { b = a; return false; }
     const float yr = fminf(yb, fmaxf(ya, e.yR)), yl = fminf(yb, fmaxf(ya, -e.yR));
-    const float dr = __fsqrt_rn(fmaxf(0.f, __fmaf_rn(-e.det, __fmul_rn(yr, yr), e.two_tA)));
-    const float dl = __fsqrt_rn(fmaxf(0.f, __fmaf_rn(-e.det, __fmul_rn(yl, yl), e.two_tA)));
-    const float xr = __fmul_rn(__fadd_rn(__fmul_rn(-e.B, yr), dr), e.iA);   // right end of E ∩ band (relative to mu)
-    const float xl = __fmul_rn(__fsub_rn(__fmul_rn(-e.B, yl), dl), e.iA);   // left end
+    const float dr = sqrt_fast(fmaxf(0.f, e.two_tA - e.det * yr * yr));
+    const float dl = sqrt_fast(fmaxf(0.f, e.two_tA - e.det * yl * yl));
+    const float xr = (dr - e.B * yr) * e.iA;    // right end of E ∩ band (relative to mu)
+    const float xl = (-e.B * yl - dl) * e.iA;   // left end
     // tile tx holds sample columns [16 tx + off, 16 tx + off + 15]
     const float inv = 1.0f / float(TILE);
-    const float fa = ceilf(__fmul_rn(__fsub_rn(__fadd_rn(xl, e.mx), off + float(TILE - 1) + 0.01f), inv));
-    const float fb = floorf(__fmul_rn(__fadd_rn(__fsub_rn(__fadd_rn(xr, e.mx), off), 0.01f), inv));
+    const float fa = ceilf((xl + e.mx - (off + float(TILE - 1) + 0.01f)) * inv);
+    const float fb = floorf((xr + e.mx - off + 0.01f) * inv);
     if (!(fa <= fb)) {  // also catches NaN
         if (fa == fa && fb == fb) { b = a; return false; }
         return true;    // NaN: keep the whole row
@@ -178,155 +225,221 @@ __device__ __forceinline__ bool row_span(const CullE& e, int ty, int x0, int x1,
     return true;
 }
 
-constexpr int BIG_RECT = 512;   // Gaussians covering more tiles than this are walked by the whole warp
-
-// Shared walk over the rect of one Gaussian per lane.  EMIT=false: returns the number of kept tiles.
-// EMIT=true: writes (tile id, g) pairs from `start`, row-major like the reference's emission order.
-// Sinks for walk_rect: count only, or stage (tile id, g) pairs of the output window [lo, lo+n) in shared memory.
-struct CountSink {
-    static constexpr bool kWrites = false;
-    __device__ __forceinline__ void put(int64_t, int, int) const {}
-};
-template <typename KT>
-struct StageSink {
-    static constexpr bool kWrites = true;
-    KT* k; int32_t* v; int64_t lo; int n;
-    __device__ __forceinline__ void put(int64_t o, int tile, int g) const {
-        const int64_t r = o - lo;
-        if (r >= 0 && r < n) { k[r] = (KT)tile; v[r] = g; }
+// the tiles of coarse cell (cx, cy) a splat with tile rect [x0,x1) x [y0,y1) can reach, bit (ty_local * 8 + tx_local)
+template <bool GSPLAT>
+__device__ __forceinline__ uint64_t cell_tile_mask(const CullE& e, int x0, int y0, int x1, int y1, int cx, int cy) {
+    if (e.mode == 2) return 0;
+    const int wx0 = cx << SUPER_SHIFT, wy0 = cy << SUPER_SHIFT;
+    x0 = max(x0, wx0); x1 = min(x1, wx0 + SUPER);
+    y0 = max(y0, wy0); y1 = min(y1, wy0 + SUPER);
+    uint64_t mask = 0;
+    for (int ty = y0; ty < y1; ++ty) {
+        int a, b;
+        if (!row_span<GSPLAT>(e, ty, x0, x1, a, b)) continue;   // clipping the span to the window == intersecting it
+        const uint64_t bits = ((1ull << (b - a)) - 1ull) << (a - wx0);
+        mask |= bits << ((ty - wy0) * SUPER);
     }
-};
-
-// Shared walk over the rect of one Gaussian per lane.  Returns the number of kept tiles; a writing sink receives the
-// (tile id, g) pairs at output offsets start, start+1, ... in row-major order (the reference's emission order).
-template <bool GSPLAT, typename Sink>
-__device__ __forceinline__ int walk_rect(unsigned lane, bool active, int g, const CullE& e, int x0, int y0, int x1, int y1,
-                                         int grid_x, int64_t start, const Sink& sink) {
-    const int t_rect = active ? (x1 - x0) * (y1 - y0) : 0;
-    const bool none = (e.mode == 2);
-    int kept = 0;
-    if (t_rect > 0 && t_rect <= BIG_RECT && !none) {
-        for (int ty = y0; ty < y1; ++ty) {
-            int a, b;
-            if (!row_span<GSPLAT>(e, ty, x0, x1, a, b)) continue;
-            if (Sink::kWrites) {
-                for (int tx = a; tx < b; ++tx) sink.put(start + kept + (tx - a), ty * grid_x + tx, g);
-            }
-            kept += b - a;
-        }
-    }
-    unsigned big = __ballot_sync(0xffffffffu, t_rect > BIG_RECT && !none);
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        CullE be;
-        be.mx = __shfl_sync(0xffffffffu, e.mx, src); be.my = __shfl_sync(0xffffffffu, e.my, src);
-        be.A = __shfl_sync(0xffffffffu, e.A, src); be.B = __shfl_sync(0xffffffffu, e.B, src);
-        be.iA = __shfl_sync(0xffffffffu, e.iA, src); be.two_tA = __shfl_sync(0xffffffffu, e.two_tA, src);
-        be.det = __shfl_sync(0xffffffffu, e.det, src); be.ymax = __shfl_sync(0xffffffffu, e.ymax, src);
-        be.yR = __shfl_sync(0xffffffffu, e.yR, src); be.mode = __shfl_sync(0xffffffffu, e.mode, src);
-        const int bg = __shfl_sync(0xffffffffu, g, src);
-        const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-        const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
-        const int64_t bstart = __shfl_sync(0xffffffffu, start, src);
-        int bkept = 0;
-        for (int ty = by0; ty < by1; ++ty) {
-            int a, b;
-            if (!row_span<GSPLAT>(be, ty, bx0, bx1, a, b)) continue;
-            if (Sink::kWrites) {
-                for (int tx = a + (int)lane; tx < b; tx += 32) sink.put(bstart + bkept + (tx - a), ty * grid_x + tx, bg);
-            }
-            bkept += b - a;
-        }
-        if ((int)lane == src) kept = bkept;
-    }
-    return kept;
+    return mask;
 }
 
+// tile rect -> rect of coarse cells
+__device__ __forceinline__ void coarsen_rect(int x0, int y0, int x1, int y1, int& cx0, int& cy0, int& cx1, int& cy1) {
+    cx0 = x0 >> SUPER_SHIFT;
+    cy0 = y0 >> SUPER_SHIFT;
+    cx1 = ((x1 - 1) >> SUPER_SHIFT) + 1;
+    cy1 = ((y1 - 1) >> SUPER_SHIFT) + 1;
+}
+
+// Phase A, one lane per Gaussian: depth key, identity id, number of coarse cells of its tile rect and the 32-byte record
+// phase B works from.  counts[0] += tiles of the rect (the reference's pair count I: an upper bound of the culled
+// count, exact without culling), counts[1] += cells.
 template <bool GSPLAT>
 __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, int grid_y, const BinSrc src,
                                                          uint32_t* __restrict__ keys, int32_t* __restrict__ ids,
-                                                         int32_t* __restrict__ tiles) {
+                                                         int32_t* __restrict__ cells, SplatRec* __restrict__ recs,
+                                                         unsigned long long* __restrict__ counts) {
+    __shared__ unsigned long long s_area[8], s_cells[8];
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
-    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    bool active = false;
-    CullE e{};
+    int area = 0, nc = 0;
     if (i < n) {
         const int r = src.get_radius(i);
+        SplatRec rec;
+        rec.x = rec.y = 0.f; rec.A = rec.C = 1.f; rec.B = 0.f; rec.opacity = 1.f; rec.radius = r;
         if (r > 0) {
             const float2 p = src.get_xy(i);
+            rec.x = p.x; rec.y = p.y;
+            int x0, y0, x1, y1;
             tile_rect<GSPLAT>(p.x, p.y, (float)r, grid_x, grid_y, x0, y0, x1, y1);
-            e = load_cull(p, src, i);
-            active = (x1 - x0) * (y1 - y0) > 0;
+            area = max(0, x1 - x0) * max(0, y1 - y0);
+            if (area > 0) {
+                int cx0, cy0, cx1, cy1;
+                coarsen_rect(x0, y0, x1, y1, cx0, cy0, cx1, cy1);
+                nc = (cx1 - cx0) * (cy1 - cy0);
+                if (src.conic != nullptr) {
+                    const float* q = src.conic + i * src.cs;
+                    rec.A = q[0]; rec.B = q[1]; rec.C = q[2];
+                    rec.opacity = src.opacity[i * src.os];
+                }
+            }
         }
-    }
-    const int t = walk_rect<GSPLAT>(lane, active, (int)i, e, x0, y0, x1, y1, grid_x, 0, CountSink{});
-    if (i < n) {
-        keys[i] = t > 0 ? __float_as_uint(src.get_depth(i)) : 0xFFFFFFFFu;
+        rec.ncells = nc;
+        keys[i] = area > 0 ? __float_as_uint(src.get_depth(i)) : 0xFFFFFFFFu;
         ids[i] = (int32_t)i;
-        tiles[i] = t;
+        cells[i] = nc;
+        float4* out = reinterpret_cast<float4*>(recs + i);
+        out[0] = make_float4(rec.x, rec.y, rec.A, rec.B);
+        out[1] = make_float4(rec.C, rec.opacity, __int_as_float(rec.radius), __int_as_float(rec.ncells));
+    }
+    unsigned long long a = (unsigned long long)area, c = (unsigned long long)nc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_area[threadIdx.x >> 5] = a; s_cells[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long ta = 0, tc = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { ta += s_area[w]; tc += s_cells[w]; }
+        if (ta) atomicAdd(counts, ta);
+        if (tc) atomicAdd(counts + 1, tc);
     }
 }
 
-__global__ void write_total_kernel(int64_t n, const int64_t* __restrict__ offsets, int64_t* __restrict__ d_total) {
-    *d_total = n > 0 ? offsets[n - 1] : 0;
-}
-
-// One lane per depth-ranked Gaussian.  The 256 consecutive ranks of a block own one contiguous window of the pair arrays
-// (offsets are an inclusive scan in depth order), so the pairs are staged in shared memory and written back with
-// coalesced stores, EMIT_CHUNK entries at a time (one chunk covers a typical block: 256 x ~13 pairs).
-constexpr int EMIT_CHUNK = 4096;
+// Phase B, one block per 256 depth-ranked Gaussians: emits their (coarse cell, {tile mask, id}) pairs, cells in row-major
+// order.  The block's ranks own one contiguous window of the pair arrays (offsets are an inclusive scan in depth order),
+// so the pairs are assembled in shared memory and written back with coalesced stores.  The expensive part — one
+// ellipse/row-band intersection per tile row of every rect — is spread over the block as (rank, row) work items, so a
+// warp never waits for the one lane that owns a large splat.
+constexpr int EMIT_SLOTS = 2048;
 
 template <bool GSPLAT, typename KT>
-__global__ void __launch_bounds__(256) emit_pairs_kernel(int64_t n, int grid_x, int grid_y, int64_t max_pairs, const BinSrc src,
-                                                         const int32_t* __restrict__ order, const int32_t* __restrict__ tiles,
-                                                         const int64_t* __restrict__ offsets, KT* __restrict__ pkeys,
-                                                         int32_t* __restrict__ pvals) {
-    __shared__ KT s_k[EMIT_CHUNK];
-    __shared__ int32_t s_v[EMIT_CHUNK];
+__global__ void __launch_bounds__(256) emit_cells_kernel(int64_t n, int grid_x, int grid_y, int cgrid_x, int cull, int64_t max_coarse,
+                                                         const int32_t* __restrict__ order, const SplatRec* __restrict__ recs,
+                                                         const int64_t* __restrict__ offsets, KT* __restrict__ ckeys,
+                                                         CellEntry* __restrict__ cvals) {
+    __shared__ KT s_k[EMIT_SLOTS];
+    __shared__ int32_t s_id[EMIT_SLOTS];
+    __shared__ unsigned long long s_mask[EMIT_SLOTS];
+    __shared__ float s_f[8][256];        // mx, my, B, iA, two_tA, det, ymax, yR
+    __shared__ int s_mode[256], s_xr[256], s_yr[256], s_start[256];   // x0 | x1 << 16, y0 | y1 << 16, first slot - block_lo
+    __shared__ int s_rowoff[257];
+    __shared__ int s_warp[8];
+    __shared__ int64_t s_lo;
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, w = tid >> 5;
     const int64_t rank0 = int64_t(blockIdx.x) * blockDim.x;
-    const int64_t rnk = rank0 + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
-    int g = -1, x0 = 0, y0 = 0, x1 = 0, y1 = 0, t = 0;
+    const int64_t rnk = rank0 + tid;
+    int g = -1, x0 = 0, y0 = 0, x1 = 0, y1 = 0, t = 0, nrows = 0;
     int64_t start = 0;
     CullE e{};
     if (rnk < n) {
         g = order[rnk];
-        t = tiles[g];
+        const float4* rp = reinterpret_cast<const float4*>(recs + g);
+        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        SplatRec rec;
+        rec.x = r0.x; rec.y = r0.y; rec.A = r0.z; rec.B = r0.w; rec.C = r1.x; rec.opacity = r1.y;
+        rec.radius = __float_as_int(r1.z); rec.ncells = __float_as_int(r1.w);
+        t = rec.ncells;
         if (t > 0) {
-            const float2 p = src.get_xy(g);
-            tile_rect<GSPLAT>(p.x, p.y, (float)src.get_radius(g), grid_x, grid_y, x0, y0, x1, y1);
-            e = load_cull(p, src, g);
-            start = offsets[rnk] - t;
+            tile_rect<GSPLAT>(rec.x, rec.y, (float)rec.radius, grid_x, grid_y, x0, y0, x1, y1);
+            e = make_cull(rec, cull != 0);
+            nrows = (e.mode == 2) ? 0 : y1 - y0;
         }
+        start = offsets[rnk] - t;
     }
+    if (tid == 0) s_lo = start;
+    // exclusive scan of the row counts
+    int inc = nrows;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += v;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    int wbase = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wbase += (k < (int)w) ? s_warp[k] : 0;
+    const int64_t block_lo = s_lo;
+    s_rowoff[tid] = wbase + inc - nrows;
+    if (tid == 255) s_rowoff[256] = wbase + inc;
+    s_f[0][tid] = e.mx; s_f[1][tid] = e.my; s_f[2][tid] = e.B; s_f[3][tid] = e.iA;
+    s_f[4][tid] = e.two_tA; s_f[5][tid] = e.det; s_f[6][tid] = e.ymax; s_f[7][tid] = e.yR;
+    s_mode[tid] = e.mode;
+    s_xr[tid] = x0 | (x1 << 16);
+    s_yr[tid] = y0 | (y1 << 16);
+    s_start[tid] = (int)(start - block_lo);
+    const int cx0 = x0 >> SUPER_SHIFT, cy0 = y0 >> SUPER_SHIFT;
+    const int cw = t > 0 ? ((x1 - 1) >> SUPER_SHIFT) - cx0 + 1 : 1;
+    __syncthreads();
+    const int total_rows = s_rowoff[256];
     const int64_t last_rank = min(rank0 + (int64_t)blockDim.x, n) - 1;
-    const int64_t block_lo = offsets[rank0] - tiles[order[rank0]];
-    const int64_t block_hi = min(offsets[last_rank], max_pairs);
-    for (int64_t lo = block_lo; lo < block_hi; lo += EMIT_CHUNK) {
-        const int cn = (int)min((int64_t)EMIT_CHUNK, block_hi - lo);
-        const bool active = (t > 0) && (start < lo + cn) && (start + t > lo);
-        walk_rect<GSPLAT>(lane, active, g, e, x0, y0, x1, y1, grid_x, start, StageSink<KT>{s_k, s_v, lo, cn});
+    const int64_t block_hi = min(offsets[last_rank], max_coarse);
+    for (int64_t lo = block_lo; lo < block_hi; lo += EMIT_SLOTS) {
+        const int cn = (int)min((int64_t)EMIT_SLOTS, block_hi - lo);
+        const int wlo = (int)(lo - block_lo);       // window = local slots [wlo, wlo + cn)
+        for (int i = tid; i < cn; i += 256) s_mask[i] = 0ull;
+        // keys and ids of this rank's slots
+        {
+            const int ls = (int)(start - block_lo);
+            int k = max(0, wlo - ls);
+            const int kend = min(t, wlo + cn - ls);
+            int cy = cy0 + k / cw, cx = cx0 + k % cw;
+            for (; k < kend; ++k) {
+                s_k[ls + k - wlo] = (KT)(cy * cgrid_x + cx);
+                s_id[ls + k - wlo] = g;
+                if (++cx == cx0 + cw) { cx = cx0; ++cy; }
+            }
+        }
         __syncthreads();
-        for (int i = threadIdx.x; i < cn; i += blockDim.x) {
-            pkeys[lo + i] = s_k[i];
-            pvals[lo + i] = s_v[i];
+        // (rank, row) work items
+        for (int it = tid; it < total_rows; it += 256) {
+            int r = 0;
+#pragma unroll
+            for (int step = 128; step >= 1; step >>= 1)
+                if (s_rowoff[r + step] <= it) r += step;
+            CullE q;
+            q.mx = s_f[0][r]; q.my = s_f[1][r]; q.B = s_f[2][r]; q.iA = s_f[3][r];
+            q.two_tA = s_f[4][r]; q.det = s_f[5][r]; q.ymax = s_f[6][r]; q.yR = s_f[7][r];
+            q.mode = s_mode[r];
+            const int xr = s_xr[r], yr = s_yr[r];
+            const int rx0 = xr & 0xffff, rx1 = xr >> 16, ry0 = yr & 0xffff;
+            const int ty = ry0 + (it - s_rowoff[r]);
+            int a, b;
+            if (!row_span<GSPLAT>(q, ty, rx0, rx1, a, b)) continue;
+            const int rcx0 = rx0 >> SUPER_SHIFT, rcw = ((rx1 - 1) >> SUPER_SHIFT) - rcx0 + 1;
+            const int row_slot = s_start[r] + ((ty >> SUPER_SHIFT) - (ry0 >> SUPER_SHIFT)) * rcw - rcx0 - wlo;
+            for (int cx = a >> SUPER_SHIFT; cx <= (b - 1) >> SUPER_SHIFT; ++cx) {
+                const int slot = row_slot + cx;
+                if (slot < 0 || slot >= cn) continue;
+                const int wx0 = cx << SUPER_SHIFT;
+                const int ca = max(a, wx0) - wx0, cb = min(b, wx0 + SUPER) - wx0;
+                const unsigned bits = ((1u << (cb - ca)) - 1u) << ca;
+                reinterpret_cast<unsigned char*>(s_mask)[slot * 8 + (ty & (SUPER - 1))] = (unsigned char)bits;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < cn; i += 256) {
+            const unsigned long long m = s_mask[i];
+            ckeys[lo + i] = s_k[i];
+            cvals[lo + i] = make_uint4((uint32_t)m, (uint32_t)(m >> 32), (uint32_t)s_id[i], 0u);
         }
         __syncthreads();
     }
 }
 
-// capacity mode: entries [total, cap) of the key buffer get a key above every tile id so they sort to the end
+// entries [total, cap) of the key buffer get a key above every cell id so they sort to the end
 template <typename KT>
 __global__ void __launch_bounds__(256) pad_keys_kernel(int64_t cap, const int64_t* __restrict__ d_total, KT* __restrict__ keys, KT pad) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = *d_total + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < cap; i += stride) keys[i] = pad;
 }
 
-// ranges[t] = [first, last+1) of tile t in the partitioned key array; RV keys per thread (one 8/16-byte load).
+// ranges[c] = [first, last+1) of cell c in the partitioned key array; RV keys per thread (one 16-byte load).
 template <typename KT>
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t cap, const int64_t* __restrict__ d_total, const KT* __restrict__ keys,
+__global__ void __launch_bounds__(256) cell_ranges_kernel(int64_t cap, const int64_t* __restrict__ d_total, const KT* __restrict__ keys,
                                                           int2* __restrict__ ranges) {
     constexpr int RV = 16 / sizeof(KT) >= 8 ? 8 : 4;   // 8 x u16 = 16 B, 4 x u32 = 16 B
     const int64_t total = min(cap, *d_total);
@@ -354,30 +467,303 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t cap, const int
     }
 }
 
+// chunk_base[c] = number of CHUNK-entry chunks of the cells before c; chunk_cell[chunk] = its cell (one block; n_cells is small)
+__global__ void __launch_bounds__(1024) chunk_table_kernel(int n_cells, const int2* __restrict__ cell_ranges, int32_t* __restrict__ chunk_base,
+                                                           int32_t* __restrict__ chunk_cell) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_cells; base += 1024) {
+        const int i = base + tid;
+        int v = 0;
+        if (i < n_cells) {
+            const int2 r = cell_ranges[i];
+            v = (r.y - r.x + CHUNK - 1) / CHUNK;
+        }
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            int ws = s_warp[lane], winc = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_warp[lane] = winc - ws;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + s_warp[w] + inc - v;
+        if (i < n_cells) {
+            chunk_base[i] = excl;
+            for (int k = 0; k < v; ++k) chunk_cell[excl + k] = i;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) chunk_base[n_cells] = s_carry;
+}
+
+// 32x32 bit-matrix transpose across a warp: lane l passes row l, lane t receives column t
+// (bit l of the result = bit t of lane l's input).
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, unsigned lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = (j == 16) ? 0x0000FFFFu : (j == 8) ? 0x00FF00FFu : (j == 4) ? 0x0F0F0F0Fu : (j == 2) ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+    }
+    return x;
+}
+
+// Phase C: one block per chunk (256 consecutive entries of one cell's depth-ordered list): per-tile entry counts.
+// Each warp transposes the masks of its 32 entries: lane t then holds, for tiles t and t+32, the bit set of the warp's
+// entries that reach the tile.
+__global__ void __launch_bounds__(CHUNK) chunk_counts_kernel(int n_cells, const int2* __restrict__ cell_ranges,
+                                                             const int32_t* __restrict__ chunk_base, const int32_t* __restrict__ chunk_cell,
+                                                             const CellEntry* __restrict__ entries, uint16_t* __restrict__ chunk_cnt) {
+    __shared__ uint16_t s_cnt[CHUNK / 32][CELL_TILES];
+    const int c = blockIdx.x;
+    if (c >= __ldg(chunk_base + n_cells)) return;
+    const int cell = __ldg(chunk_cell + c);
+    const int2 r = cell_ranges[cell];
+    const int e = r.x + (c - __ldg(chunk_base + cell)) * CHUNK + (int)threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    uint32_t lo = 0, hi = 0;
+    if (e < r.y) {
+        const uint2 m = __ldg(reinterpret_cast<const uint2*>(entries + e));
+        lo = m.x; hi = m.y;
+    }
+    s_cnt[w][lane] = (uint16_t)__popc(transpose32(lo, lane));
+    s_cnt[w][lane + 32] = (uint16_t)__popc(transpose32(hi, lane));
+    __syncthreads();
+    if (threadIdx.x < CELL_TILES) {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < CHUNK / 32; ++k) sum += s_cnt[k][threadIdx.x];
+        chunk_cnt[int64_t(c) * CELL_TILES + threadIdx.x] = (uint16_t)sum;
+    }
+}
+
+// Phase D, one block per cell, thread (j, t): prefix over the cell's chunks of tile t's counts, the chunk list split
+// into 16 contiguous parts j so that the sequential walks stay short; the tile's total goes to tile_start (tile-id
+// order).  The LAST block to finish then scans the tile totals in place -> tile starts, tile_ranges (clamped to the
+// capacity of sorted_ids; empty tiles (0,0) like dgr's zero-filled ranges) and the pair total.
+__global__ void __launch_bounds__(1024) chunk_prefix_kernel(int cgrid_x, int grid_x, int grid_y, const int32_t* __restrict__ chunk_base,
+                                                            const uint16_t* __restrict__ chunk_cnt, uint32_t* __restrict__ chunk_pre,
+                                                            int64_t* __restrict__ tile_start, int64_t max_pairs,
+                                                            int2* __restrict__ tile_ranges, int64_t* __restrict__ d_counts) {
+    __shared__ uint32_t s_part[16][CELL_TILES];
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    __shared__ int s_last;
+    const int cell = blockIdx.x;
+    const int tid = threadIdx.x;
+    {
+        const int t = tid & (CELL_TILES - 1), j = tid >> 6;
+        const int c0 = chunk_base[cell], c1 = chunk_base[cell + 1];
+        const int per = (c1 - c0 + 15) >> 4;
+        const int a = min(c1, c0 + j * per), b = min(c1, a + per);
+        uint32_t sum = 0;
+#pragma unroll 4
+        for (int c = a; c < b; ++c) sum += chunk_cnt[int64_t(c) * CELL_TILES + t];
+        s_part[j][t] = sum;
+        __syncthreads();
+        uint32_t run = 0;
+        for (int k = 0; k < j; ++k) run += s_part[k][t];
+#pragma unroll 4
+        for (int c = a; c < b; ++c) {
+            const uint32_t v = chunk_cnt[int64_t(c) * CELL_TILES + t];
+            chunk_pre[int64_t(c) * CELL_TILES + t] = run;
+            run += v;
+        }
+        if (j == 15) {
+            const int tx = ((cell % cgrid_x) << SUPER_SHIFT) + (t & (SUPER - 1));
+            const int ty = ((cell / cgrid_x) << SUPER_SHIFT) + (t >> SUPER_SHIFT);
+            if (tx < grid_x && ty < grid_y) tile_start[int64_t(ty) * grid_x + tx] = run;
+        }
+    }
+    // ticket: d_counts[3] is zero on entry (phase A memset) and reset by the last block
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long ticket = atomicAdd(reinterpret_cast<unsigned long long*>(d_counts + 3), 1ull);
+        s_last = (ticket == (unsigned long long)(gridDim.x - 1));
+        s_carry = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int n_tiles = grid_x * grid_y;
+    const int lane = tid & 31, w = tid >> 5;
+    for (int base = 0; base < n_tiles; base += 8192) {
+        const int i0 = base + tid * 8;
+        int64_t v[8];
+        if (i0 + 8 <= n_tiles) {
+            const longlong2* p = reinterpret_cast<const longlong2*>(tile_start + i0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const longlong2 q = __ldcg(p + k);
+                v[2 * k] = q.x; v[2 * k + 1] = q.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (i0 + k < n_tiles) ? __ldcg(tile_start + i0 + k) : 0;
+        }
+        int64_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += v[k];
+        int64_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            const int64_t ws = s_warp[lane];
+            int64_t winc = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_warp[lane] = winc - ws;
+        }
+        __syncthreads();
+        int64_t run = s_carry + s_warp[w] + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (i0 + k < n_tiles) {
+                tile_start[i0 + k] = run;
+                tile_ranges[i0 + k] = v[k] > 0 ? make_int2((int)min(run, max_pairs), (int)min(run + v[k], max_pairs)) : make_int2(0, 0);
+            }
+            run += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = run;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        d_counts[2] = s_carry;
+        d_counts[3] = 0;
+    }
+}
+
+// Phase E: one block per chunk; sorted_ids[tile start + chunk prefix + rank in chunk] = id.  After the warp transpose,
+// lane t owns the bit sets of tiles t / t+32 over the warp's 32 entries; walking their set bits in order yields the
+// tile's ids in list order.  The chunk's output is first laid out in shared memory in (tile, rank) order — the order it
+// has in global memory, where tile t's part is one contiguous run — so each run leaves the SM as one coalesced store
+// instead of one partial-sector write per id.
+constexpr int SCATTER_STAGE = 4096;
+
+__global__ void __launch_bounds__(CHUNK) scatter_ids_kernel(int n_cells, int cgrid_x, int grid_x, int grid_y, int64_t max_pairs,
+                                                            const int2* __restrict__ cell_ranges, const int32_t* __restrict__ chunk_base,
+                                                            const int32_t* __restrict__ chunk_cell, const CellEntry* __restrict__ entries,
+                                                            const uint32_t* __restrict__ chunk_pre, const int64_t* __restrict__ tile_start,
+                                                            int32_t* __restrict__ sorted_ids) {
+    constexpr int WARPS = CHUNK / 32;
+    __shared__ uint16_t s_cnt[WARPS][CELL_TILES];
+    __shared__ int s_wbase[WARPS][CELL_TILES];    // offset of (warp, tile) inside the tile's run of this chunk
+    __shared__ int s_off[CELL_TILES + 1];         // offset of tile t's run inside the staged output
+    __shared__ int64_t s_gbase[CELL_TILES];       // global position of tile t's run
+    __shared__ int32_t s_id[CHUNK];
+    __shared__ int32_t s_out[SCATTER_STAGE];
+    const int c = blockIdx.x;
+    if (c >= __ldg(chunk_base + n_cells)) return;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const int cell = __ldg(chunk_cell + c);
+    const int2 r = cell_ranges[cell];
+    const int e = r.x + (c - __ldg(chunk_base + cell)) * CHUNK + (int)threadIdx.x;
+    uint32_t mlo = 0, mhi = 0;
+    if (e < r.y) {
+        const uint4 v = __ldg(entries + e);
+        mlo = v.x; mhi = v.y;
+        s_id[threadIdx.x] = (int)v.z;
+    }
+    uint32_t wlo = transpose32(mlo, lane), whi = transpose32(mhi, lane);   // entries of this warp reaching tile lane / lane + 32
+    s_cnt[w][lane] = (uint16_t)__popc(wlo);
+    s_cnt[w][lane + 32] = (uint16_t)__popc(whi);
+    __syncthreads();
+    if (threadIdx.x < CELL_TILES) {
+        const int t = threadIdx.x;
+        const int tx = ((cell % cgrid_x) << SUPER_SHIFT) + (t & (SUPER - 1));
+        const int ty = ((cell / cgrid_x) << SUPER_SHIFT) + (t >> SUPER_SHIFT);
+        s_gbase[t] = (tx < grid_x && ty < grid_y) ? tile_start[int64_t(ty) * grid_x + tx] + chunk_pre[int64_t(c) * CELL_TILES + t] : 0;
+        int run = 0;
+#pragma unroll
+        for (int k = 0; k < WARPS; ++k) {
+            s_wbase[k][t] = run;
+            run += s_cnt[k][t];
+        }
+        int inc = run;   // inclusive scan of the tile totals inside each of the two warps
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)lane >= o) inc += v;
+        }
+        s_off[t + 1] = inc;
+    }
+    __syncthreads();
+    const int half = s_off[32];       // total of tiles 0..31
+    __syncthreads();
+    if (threadIdx.x >= 32 && threadIdx.x < CELL_TILES) s_off[threadIdx.x + 1] += half;
+    if (threadIdx.x == 0) s_off[0] = 0;
+    __syncthreads();
+    const int total = s_off[CELL_TILES];
+    const int32_t* ids = s_id + w * 32;
+    if (total <= SCATTER_STAGE) {
+        int p = s_off[lane] + s_wbase[w][lane];
+        for (; wlo; wlo &= wlo - 1) s_out[p++] = ids[__ffs(wlo) - 1];
+        p = s_off[lane + 32] + s_wbase[w][lane + 32];
+        for (; whi; whi &= whi - 1) s_out[p++] = ids[__ffs(whi) - 1];
+        __syncthreads();
+        for (int t = (int)w; t < CELL_TILES; t += WARPS) {     // warp w flushes the runs of tiles w, w+8, ...
+            const int o = s_off[t], len = s_off[t + 1] - o;
+            const int64_t gb = s_gbase[t];
+            for (int k = (int)lane; k < len; k += 32)
+                if (gb + k < max_pairs) sorted_ids[gb + k] = s_out[o + k];
+        }
+    } else {   // a chunk of very large splats: write straight to global memory
+        int64_t p = s_gbase[lane] + s_wbase[w][lane];
+        for (; wlo; wlo &= wlo - 1, ++p)
+            if (p < max_pairs) sorted_ids[p] = ids[__ffs(wlo) - 1];
+        p = s_gbase[lane + 32] + s_wbase[w][lane + 32];
+        for (; whi; whi &= whi - 1, ++p)
+            if (p < max_pairs) sorted_ids[p] = ids[__ffs(whi) - 1];
+    }
+}
+
 template <typename KT>
-int emit_sort_ranges(int mode, int64_t n, int grid_x, int grid_y, int n_tiles, const BinSrc& src, bool capacity_mode, int64_t items,
-                     const int64_t* d_total, int64_t max_pairs, const int32_t* order, const int32_t* tiles, const int64_t* offsets,
-                     void* keys_in, void* keys_out, int32_t* pvals_in, void* temp, size_t temp_bytes, int32_t* sorted_ids,
-                     int32_t* tile_ranges, cudaStream_t s) {
+int partition_cells(int mode, int64_t n, int grid_x, int grid_y, int cgrid_x, int n_cells, int cull, const int64_t* d_coarse,
+                    int64_t max_coarse, const int32_t* order, const SplatRec* recs, const int64_t* offsets, void* keys_in,
+                    void* keys_out, CellEntry* cvals_in, void* temp, size_t temp_bytes, CellEntry* entries, int2* cell_ranges,
+                    cudaStream_t s) {
     KT* kin = (KT*)keys_in;
     KT* kout = (KT*)keys_out;
     const unsigned blocks = (unsigned)div_up64(n, 256);
     if (mode == B200GS_MODE_GSPLAT)
-        emit_pairs_kernel<true, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, src, order, tiles, offsets, kin, pvals_in);
+        emit_cells_kernel<true, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, kin, cvals_in);
     else
-        emit_pairs_kernel<false, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, max_pairs, src, order, tiles, offsets, kin, pvals_in);
+        emit_cells_kernel<false, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, kin, cvals_in);
     B200GS_LAUNCH_CHECK();
-    int bits = tile_bits_for(n_tiles);
-    if (capacity_mode) {
-        pad_keys_kernel<KT><<<512, 256, 0, s>>>(items, d_total, kin, (KT)(1u << bits));
-        B200GS_LAUNCH_CHECK();
-        bits += 1;
-    }
+    const int bits = bits_for(n_cells + 1);   // + the pad key n_cells
+    pad_keys_kernel<KT><<<64, 256, 0, s>>>(max_coarse, d_coarse, kin, (KT)n_cells);
+    B200GS_LAUNCH_CHECK();
     size_t tb = temp_bytes;
-    // temp was sized for max_pairs 32-bit keys; cub's requirement is monotone in the item count and key width
-    B200GS_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, kin, kout, pvals_in, sorted_ids, (int)items, 0, bits, s));
+    B200GS_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, kin, kout, cvals_in, entries, (int)max_coarse, 0, bits, s));
     constexpr int RV = 16 / sizeof(KT) >= 8 ? 8 : 4;
-    tile_ranges_kernel<KT><<<(unsigned)div_up64(div_up64(items, RV), 256), 256, 0, s>>>(items, d_total, kout, (int2*)tile_ranges);
+    cell_ranges_kernel<KT><<<(unsigned)div_up64(div_up64(max_coarse, RV), 256), 256, 0, s>>>(max_coarse, d_coarse, kout, cell_ranges);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }
@@ -385,15 +771,23 @@ int emit_sort_ranges(int mode, int64_t n, int grid_x, int grid_y, int n_tiles, c
 }  // namespace
 
 size_t bin_count_workspace_bytes(int64_t n) { return make_layout_a(n).total; }
-size_t bin_sort_workspace_bytes(int64_t, int64_t max_pairs, int, int) { return make_layout_b(max_pairs).total; }
+size_t bin_sort_workspace_bytes(int64_t, int64_t max_coarse, int width, int height) { return make_layout_b(max_coarse, width, height).total; }
 
 static BinSrc make_src(int row_stride, const float* xy, const float* depth, const int32_t* radii, const float* conic, const float* opacity) {
     if (row_stride > 0) return BinSrc{xy, depth, radii, conic, opacity, row_stride, row_stride, row_stride, row_stride, row_stride};
     return BinSrc{xy, depth, radii, conic, opacity, 2, 1, 1, 3, 1};
 }
 
+static int copy_counts(const int64_t* d_counts, int64_t* host_counts, int sync_host, cudaStream_t s) {
+    if (host_counts != nullptr) {
+        B200GS_CUDA(cudaMemcpyAsync(host_counts, d_counts, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        if (sync_host) B200GS_CUDA(cudaStreamSynchronize(s));
+    }
+    return B200GS_OK;
+}
+
 int bin_count(int mode, int width, int height, int64_t n, int row_stride, const float* xy, const float* depth, const int32_t* radii,
-              const float* conic, const float* opacity, void* ws, size_t ws_bytes, int64_t* d_total, int64_t* host_total,
+              const float* conic, const float* opacity, void* ws, size_t ws_bytes, int64_t* d_counts, int64_t* host_counts,
               int sync_host, cudaStream_t s) {
     const LayoutA L = make_layout_a(n);
     if (ws_bytes < L.total) {
@@ -405,51 +799,44 @@ int bin_count(int mode, int width, int height, int64_t n, int row_stride, const 
     uint32_t* keys_out = (uint32_t*)(w + L.keys_out);
     int32_t* ids_in = (int32_t*)(w + L.ids_in);
     int32_t* order = (int32_t*)(w + L.order);
-    int32_t* tiles = (int32_t*)(w + L.tiles);
+    int32_t* cells = (int32_t*)(w + L.cells);
     int64_t* offsets = (int64_t*)(w + L.offsets);
+    SplatRec* recs = (SplatRec*)(w + L.recs);
     const int grid_x = div_up(width, TILE), grid_y = div_up(height, TILE);
+    B200GS_CUDA(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int64_t), s));
     if (n > 0) {
         const unsigned blocks = (unsigned)div_up64(n, 256);
         const BinSrc src = make_src(row_stride, xy, depth, radii, conic, opacity);
         if (mode == B200GS_MODE_GSPLAT)
-            depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, keys_in, ids_in, tiles);
+            depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, keys_in, ids_in, cells, recs, (unsigned long long*)d_counts);
         else
-            depth_keys_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, keys_in, ids_in, tiles);
+            depth_keys_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, keys_in, ids_in, cells, recs, (unsigned long long*)d_counts);
         B200GS_LAUNCH_CHECK();
         size_t tb = L.temp_bytes;
         B200GS_CUDA(cub::DeviceRadixSort::SortPairs(w + L.temp, tb, keys_in, keys_out, ids_in, order, (int)n, 0, 32, s));
-        cub::TransformInputIterator<int64_t, TilesOfOrder, const int32_t*> it(order, TilesOfOrder{tiles});
+        cub::TransformInputIterator<int64_t, CellsOfOrder, const int32_t*> it(order, CellsOfOrder{cells});
         tb = L.temp_bytes;
         B200GS_CUDA(cub::DeviceScan::InclusiveSum(w + L.temp, tb, it, offsets, (int)n, s));
     }
-    write_total_kernel<<<1, 1, 0, s>>>(n, offsets, d_total);
-    B200GS_LAUNCH_CHECK();
-    if (host_total != nullptr) {
-        B200GS_CUDA(cudaMemcpyAsync(host_total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        if (sync_host) B200GS_CUDA(cudaStreamSynchronize(s));
-    }
-    return B200GS_OK;
+    return copy_counts(d_counts, host_counts, sync_host, s);
 }
 
-int bin_sort(int mode, int width, int height, int64_t n, int row_stride, const float* xy, const int32_t* radii, const float* conic,
-             const float* opacity, int64_t total, const int64_t* d_total, int64_t max_pairs, const void* ws_a, void* ws_b,
-             size_t ws_bytes, int32_t* sorted_ids, int32_t* tile_ranges, cudaStream_t s) {
-    const int grid_x = div_up(width, TILE), grid_y = div_up(height, TILE);
-    const int n_tiles = grid_x * grid_y;
-    const bool capacity_mode = total < 0;   // pair count known on the device only: sort the whole capacity, padded
-    B200GS_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(int32_t) * 2 * (size_t)n_tiles, s));
-    if (!capacity_mode && total > max_pairs) {
-        set_error("bin_sort: %lld pairs exceed capacity %lld", (long long)total, (long long)max_pairs);
+int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_coarse, int64_t max_pairs, int64_t* d_counts,
+             const void* ws_a, void* ws_b, size_t ws_bytes, int32_t* sorted_ids, int32_t* tile_ranges, int64_t* host_counts,
+             int sync_host, cudaStream_t s) {
+    int grid_x, grid_y, cgrid_x, cgrid_y;
+    cell_grid(width, height, grid_x, grid_y, cgrid_x, cgrid_y);
+    const int n_tiles = grid_x * grid_y, n_cells = cgrid_x * cgrid_y;
+    if (max_pairs >= (int64_t(1) << 31) || max_coarse >= (int64_t(1) << 31)) {
+        set_error("bin_sort: capacity %lld / %lld exceeds 2^31", (long long)max_coarse, (long long)max_pairs);
         return B200GS_ENOSPACE;
     }
-    const int64_t items = capacity_mode ? max_pairs : total;
-    if (items >= (int64_t(1) << 31)) {
-        set_error("bin_sort: %lld pairs exceed 2^31", (long long)items);
-        return B200GS_ENOSPACE;
+    if (max_coarse == 0 || n == 0) {   // nothing on screen (or nothing can be stored): empty lists; counts[2] stays 0
+        B200GS_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(int32_t) * 2 * (size_t)n_tiles, s));
+        return copy_counts(d_counts, host_counts, sync_host, s);
     }
-    if (items == 0 || n == 0) return B200GS_OK;
     const LayoutA LA = make_layout_a(n);
-    const LayoutB L = make_layout_b(max_pairs);
+    const LayoutB L = make_layout_b(max_coarse, width, height);
     if (ws_bytes < L.total) {
         set_error("bin_sort: workspace too small (%zu < %zu)", ws_bytes, L.total);
         return B200GS_ENOSPACE;
@@ -457,19 +844,41 @@ int bin_sort(int mode, int width, int height, int64_t n, int row_stride, const f
     const char* wa = (const char*)ws_a;
     char* w = (char*)ws_b;
     const int32_t* order = (const int32_t*)(wa + LA.order);
-    const int32_t* tiles = (const int32_t*)(wa + LA.tiles);
     const int64_t* offsets = (const int64_t*)(wa + LA.offsets);
-    uint32_t* pkeys_in = (uint32_t*)(w + L.pkeys_in);
-    uint32_t* pkeys_out = (uint32_t*)(w + L.pkeys_out);
-    int32_t* pvals_in = (int32_t*)(w + L.pvals_in);
-    const unsigned blocks = (unsigned)div_up64(n, 256);
-    const BinSrc src = make_src(row_stride, xy, nullptr, radii, conic, opacity);
-    const int bits = tile_bits_for(n_tiles) + (capacity_mode ? 1 : 0);
-    if (bits <= 16)   // every image up to ~4K: 16-bit tile keys -> 12 B instead of 16 B per pair and radix pass
-        return emit_sort_ranges<uint16_t>(mode, n, grid_x, grid_y, n_tiles, src, capacity_mode, items, d_total, max_pairs, order, tiles,
-                                          offsets, pkeys_in, pkeys_out, pvals_in, w + L.temp, L.temp_bytes, sorted_ids, tile_ranges, s);
-    return emit_sort_ranges<uint32_t>(mode, n, grid_x, grid_y, n_tiles, src, capacity_mode, items, d_total, max_pairs, order, tiles,
-                                      offsets, pkeys_in, pkeys_out, pvals_in, w + L.temp, L.temp_bytes, sorted_ids, tile_ranges, s);
+    const SplatRec* recs = (const SplatRec*)(wa + LA.recs);
+    CellEntry* cvals_in = (CellEntry*)(w + L.cvals_in);
+    CellEntry* entries = (CellEntry*)(w + L.entries);
+    int2* cell_ranges = (int2*)(w + L.cell_ranges);
+    int32_t* chunk_base = (int32_t*)(w + L.chunk_base);
+    int32_t* chunk_cell = (int32_t*)(w + L.chunk_cell);
+    uint16_t* chunk_cnt = (uint16_t*)(w + L.chunk_cnt);
+    uint32_t* chunk_pre = (uint32_t*)(w + L.chunk_pre);
+    int64_t* tile_start = (int64_t*)(w + L.tile_start);
+
+    // B: coarse pairs with their tile masks, partitioned by cell
+    B200GS_CUDA(cudaMemsetAsync(cell_ranges, 0, sizeof(int2) * (size_t)n_cells, s));
+    int rc;
+    if (bits_for(n_cells + 1) <= 16)
+        rc = partition_cells<uint16_t>(mode, n, grid_x, grid_y, cgrid_x, n_cells, cull, d_counts + 1, max_coarse, order, recs, offsets,
+                                       w + L.ckeys_in, w + L.ckeys_out, cvals_in, w + L.temp, L.temp_bytes, entries, cell_ranges, s);
+    else
+        rc = partition_cells<uint32_t>(mode, n, grid_x, grid_y, cgrid_x, n_cells, cull, d_counts + 1, max_coarse, order, recs, offsets,
+                                       w + L.ckeys_in, w + L.ckeys_out, cvals_in, w + L.temp, L.temp_bytes, entries, cell_ranges, s);
+    if (rc != B200GS_OK) return rc;
+    chunk_table_kernel<<<1, 1024, 0, s>>>(n_cells, cell_ranges, chunk_base, chunk_cell);
+    B200GS_LAUNCH_CHECK();
+
+    // C: per-chunk tile counts;  D: chunk prefixes, tile starts / ranges / total;  E: ids in place
+    const unsigned chunks = (unsigned)L.max_chunks;
+    chunk_counts_kernel<<<chunks, CHUNK, 0, s>>>(n_cells, cell_ranges, chunk_base, chunk_cell, entries, chunk_cnt);
+    B200GS_LAUNCH_CHECK();
+    chunk_prefix_kernel<<<(unsigned)n_cells, 1024, 0, s>>>(cgrid_x, grid_x, grid_y, chunk_base, chunk_cnt, chunk_pre, tile_start, max_pairs,
+                                                           (int2*)tile_ranges, d_counts);
+    B200GS_LAUNCH_CHECK();
+    scatter_ids_kernel<<<chunks, CHUNK, 0, s>>>(n_cells, cgrid_x, grid_x, grid_y, max_pairs, cell_ranges, chunk_base, chunk_cell, entries, chunk_pre,
+                                                tile_start, sorted_ids);
+    B200GS_LAUNCH_CHECK();
+    return copy_counts(d_counts, host_counts, sync_host, s);
 }
 
 // ---- row packing for the Gaussian-sharded exchange -------------------------------------------------------------------

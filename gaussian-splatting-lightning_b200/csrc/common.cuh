@@ -92,9 +92,9 @@ int launch_sh_bwd(int degree, int stride, int64_t n, const float* dirs, const fl
                   float* v_coeffs, float* v_dirs, cudaStream_t s);
 
 size_t bin_count_workspace_bytes(int64_t n);
-size_t bin_sort_workspace_bytes(int64_t n, int64_t max_pairs, int width, int height);
+size_t bin_sort_workspace_bytes(int64_t n, int64_t max_coarse, int width, int height);
 int bin_count(int mode, int width, int height, int64_t n, int row_stride, const float* xy, const float* depth, const int32_t* radii,
-              const float* conic, const float* opacity, void* ws, size_t ws_bytes, int64_t* d_total, int64_t* host_total,
+              const float* conic, const float* opacity, void* ws, size_t ws_bytes, int64_t* d_counts, int64_t* host_counts,
               int sync_host, cudaStream_t s);
 size_t pack_rows_workspace_bytes(int64_t n);
 int pack_rows(int64_t n, const float* xy, const float* depth, const float* conic, const float* comp, const float* opacity,
@@ -102,9 +102,9 @@ int pack_rows(int64_t n, const float* xy, const float* depth, const float* conic
               cudaStream_t s);
 int unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offsets, const float* v_rows, float* v_xy, float* v_depth,
                      float* v_conic, float* v_comp, float* v_opacity, float* v_rgb, cudaStream_t s);
-int bin_sort(int mode, int width, int height, int64_t n, int row_stride, const float* xy, const int32_t* radii, const float* conic,
-             const float* opacity, int64_t total, const int64_t* d_total, int64_t max_pairs, const void* ws_a, void* ws_b,
-             size_t ws_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges, cudaStream_t s);
+int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_coarse, int64_t max_pairs, int64_t* d_counts,
+             const void* ws_a, void* ws_b, size_t ws_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges, int64_t* host_counts,
+             int sync_host, cudaStream_t s);
 
 int launch_blend_fwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids,
                      int row_stride, const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,

@@ -128,113 +128,125 @@ def _copy_view(v: B200gsView, **updates) -> B200gsView:
 # binning helper (no autograd)
 # ----------------------------------------------------------------------------------------------------------------------
 class Binning:
-    """Result of K2-K5 for one view: depth-sorted per-tile Gaussian id lists.  In lazy mode `total` is None until
-    resolve() has read the pair counter back (see bin_gaussians)."""
-    __slots__ = ("sorted_ids", "tile_ranges", "total", "_pending")
+    """Result of K2-K5 for one view: depth-sorted per-tile Gaussian id lists.  `rect_pairs` = the reference's pair count
+    (every tile of the 3-sigma rects; bounds `total`), `coarse_pairs` = (8x8-tile cell, Gaussian) pairs of the first
+    binning level, `total` = number of listed pairs.  In lazy mode the counters arrive asynchronously: rect/coarse are
+    None until resolve(), `total` waits for its own copy when first read (see bin_gaussians)."""
+    __slots__ = ("sorted_ids", "tile_ranges", "rect_pairs", "coarse_pairs", "_total", "_pending", "_host", "_event_b")
 
-    def __init__(self, sorted_ids, tile_ranges, total, pending=None):
-        self.sorted_ids, self.tile_ranges, self.total, self._pending = sorted_ids, tile_ranges, total, pending
+    def __init__(self, sorted_ids, tile_ranges, total=None, host=None, pending=None, event_b=None):
+        self.sorted_ids, self.tile_ranges, self._total = sorted_ids, tile_ranges, total
+        self.rect_pairs = self.coarse_pairs = None
+        self._host, self._pending, self._event_b = host, pending, event_b
+        if host is not None and pending is None:
+            self.rect_pairs, self.coarse_pairs = int(host[0]), int(host[1])
+
+    @property
+    def total(self):
+        if self._total is None and self._host is not None:
+            if self._event_b is not None:
+                self._event_b.synchronize()
+            self._total = int(self._host[6])
+        return self._total
 
     def resolve(self) -> bool:
-        """Lazy mode: wait for the asynchronous copy of the pair counter.  Returns False when the counter exceeded
-        the capacity the lists were built with (pairs were dropped: the caller must re-bin in exact mode)."""
+        """Lazy mode: wait for phase A's counters (the GPU is far past that point when this is called after the blend has
+        been enqueued).  Returns False when a counter exceeds the capacity the lists were built with — pairs were
+        dropped and the caller must re-bin in exact mode.  The check uses the RECT pair count, which bounds the listed
+        pairs and is known right after phase A, so it never waits for the binning itself."""
         if self._pending is None:
             return True
-        event, key, capacity = self._pending
+        event_a, key, cap_coarse, cap_pairs = self._pending
         self._pending = None
-        event.synchronize()
-        self.total = int(_host_total[0])
-        _last_total[key] = self.total
-        return self.total <= capacity
+        event_a.synchronize()
+        self.rect_pairs, self.coarse_pairs = int(self._host[0]), int(self._host[1])
+        _last_total[key] = (self.coarse_pairs, self.rect_pairs)
+        return self.coarse_pairs <= cap_coarse and self.rect_pairs <= cap_pairs
+
+    def __del__(self):
+        try:
+            if self._host is not None and len(_host_counts_pool) < 32:
+                _host_counts_pool.append(self._host)
+        except Exception:      # interpreter shutdown
+            pass
 
 
-_host_total = None
-_last_total = {}       # (mode, width, height, n) -> pair count of the previous view: sizes the next view's buffers
+_host_counts_pool = []  # pinned int64[8] buffers: [0:4] phase A's copy of the counters, [4:8] phase B's
+_last_total = {}       # key -> (coarse pairs, rect pairs) of the previous view: sizes the next view's buffers in lazy mode
 
-TILE_CULLING = True    # exact (tile, splat) culling in K2/K3; False reproduces the reference's full 3-sigma-rect pair list
-LAZY_SLACK = 1.15      # lazy mode: capacity = slack x previous pair count
+TILE_CULLING = True    # exact (tile, splat) culling in K3; False reproduces the reference's full 3-sigma-rect pair list
+LAZY_SLACK = 1.15      # lazy mode: capacity = slack x previous count
+
+
+def _host_counts():
+    return _host_counts_pool.pop() if _host_counts_pool else torch.zeros(8, dtype=torch.int64).pin_memory()
+
+
+def _bin(key, mode, width, height, n, dev, cull, lazy, count_call) -> Binning:
+    L = lib()
+    st = _stream()
+    gx, gy = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
+    ws_a = torch.empty(L.b200gs_bin_count_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    d_counts = torch.empty(4, dtype=torch.int64, device=dev)
+    ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
+    host = _host_counts()
+    prev = _last_total.get(key) if lazy else None
+    sync = prev is None
+    with _stage("bin_count"):
+        count_call(ptr(ws_a), ws_a.numel(), ptr(d_counts), host.data_ptr(), 1 if sync else 0, st)
+    if sync:
+        cap_coarse, cap_pairs = int(host[1]), int(host[0])    # exact / an upper bound: cannot overflow
+        _last_total[key] = (cap_coarse, cap_pairs)
+        pending = None
+    else:
+        event_a = torch.cuda.Event()
+        event_a.record()
+        cap_coarse = int(prev[0] * LAZY_SLACK) + 4096
+        cap_pairs = int(prev[1] * LAZY_SLACK) + 4096
+        pending = (event_a, key, cap_coarse, cap_pairs)
+    sorted_ids = torch.empty(max(cap_pairs, 1), dtype=torch.int32, device=dev)
+    ws_b = torch.empty(L.b200gs_bin_sort_workspace_bytes(n, cap_coarse, width, height), dtype=torch.uint8, device=dev)
+    with _stage("bin_sort"):
+        check(L.b200gs_bin_sort(mode, width, height, n, 1 if cull else 0, cap_coarse, cap_pairs, ptr(d_counts), ptr(ws_a), ptr(ws_b),
+                                ws_b.numel(), ptr(sorted_ids), ptr(ranges), host.data_ptr() + 32, 1 if sync else 0, st), "b200gs_bin_sort")
+    if sync:
+        return Binning(sorted_ids, ranges, int(host[6]), host)
+    event_b = torch.cuda.Event()
+    event_b.record()
+    return Binning(sorted_ids, ranges, None, host, pending, event_b)
 
 
 def bin_gaussians(mode: int, width: int, height: int, xy: torch.Tensor, depth: torch.Tensor, radii: torch.Tensor,
                   conic: Optional[torch.Tensor] = None, opacity: Optional[torch.Tensor] = None, lazy: bool = False) -> Binning:
     """K2-K5.  Passing conic+opacity enables exact tile culling (see include/b200gs.h).
 
-    lazy=False: the pair count is read back synchronously (one host sync, like the reference backends) and the lists
-    are allocated exactly.  lazy=True: buffers are sized from the previous view's count (x LAZY_SLACK), nothing blocks
-    here; call Binning.resolve() once the rest of the forward is enqueued — it returns False in the rare case the
-    capacity was exceeded and the forward has to be redone with lazy=False."""
+    lazy=False: the counters are read back synchronously (host syncs, like the reference backends) and the buffers can
+    never overflow.  lazy=True: buffers are sized from the previous view's counts (x LAZY_SLACK), nothing blocks here;
+    call Binning.resolve() once the rest of the forward is enqueued — it returns False in the rare case a capacity was
+    exceeded and the forward has to be redone with lazy=False."""
     L = lib()
     if not TILE_CULLING or conic is None or opacity is None:
         conic = opacity = None
     n = xy.shape[0]
-    dev = xy.device
-    st = _stream()
-    gx, gy = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
-    ws_a = torch.empty(L.b200gs_bin_count_workspace_bytes(n), dtype=torch.uint8, device=dev)
-    d_total = torch.empty(1, dtype=torch.int64, device=dev)
-    ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
-    global _host_total
-    if _host_total is None:
-        _host_total = torch.zeros(1, dtype=torch.int64).pin_memory()
-    key = (mode, width, height, n, conic is not None)
-    prev = _last_total.get(key) if lazy else None
-    sync = prev is None
-    with _stage("bin_count"):
-        check(L.b200gs_bin_count(mode, width, height, n, ptr(xy), ptr(depth), ptr(radii), ptr(conic), ptr(opacity), ptr(ws_a),
-                                 ws_a.numel(), ptr(d_total), _host_total.data_ptr(), 1 if sync else 0, st), "b200gs_bin_count")
-    if sync:
-        total = capacity = int(_host_total[0])
-        _last_total[key] = total
-        pending = None
-    else:
-        event = torch.cuda.Event()
-        event.record()
-        total = -1
-        capacity = int(prev * LAZY_SLACK) + 4096
-        pending = (event, key, capacity)
-    sorted_ids = torch.empty(max(capacity, 1), dtype=torch.int32, device=dev)
-    ws_b = torch.empty(L.b200gs_bin_sort_workspace_bytes(n, capacity, width, height), dtype=torch.uint8, device=dev)
-    with _stage("bin_sort"):
-        check(L.b200gs_bin_sort(mode, width, height, n, ptr(xy), ptr(radii), ptr(conic), ptr(opacity), total, ptr(d_total), capacity,
-                                ptr(ws_a), ptr(ws_b), ws_b.numel(), ptr(sorted_ids), ptr(ranges), st), "b200gs_bin_sort")
-    return Binning(sorted_ids, ranges, None if pending else total, pending)
+
+    def count_call(ws_a, ws_a_bytes, d_counts, host, sync, st):
+        check(L.b200gs_bin_count(mode, width, height, n, ptr(xy), ptr(depth), ptr(radii), ptr(conic), ptr(opacity), ws_a, ws_a_bytes,
+                                 d_counts, host, sync, st), "b200gs_bin_count")
+
+    cull = conic is not None
+    return _bin((mode, width, height, n, cull), mode, width, height, n, xy.device, cull, lazy, count_call)
 
 
 def bin_rows(mode: int, width: int, height: int, rows: torch.Tensor, cull: bool = True, lazy: bool = False) -> Binning:
-    """K2-K5 on a [n,12] splat-row buffer read in place (b200gs_bin_*_rows); same lazy protocol as bin_gaussians."""
+    """K2-K5 on a [n,12] splat-row buffer read in place (b200gs_bin_count_rows); same lazy protocol as bin_gaussians."""
     L = lib()
     n = rows.shape[0]
-    dev = rows.device
-    st = _stream()
-    gx, gy = (width + TILE - 1) // TILE, (height + TILE - 1) // TILE
-    ws_a = torch.empty(L.b200gs_bin_count_workspace_bytes(n), dtype=torch.uint8, device=dev)
-    d_total = torch.empty(1, dtype=torch.int64, device=dev)
-    ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
-    global _host_total
-    if _host_total is None:
-        _host_total = torch.zeros(1, dtype=torch.int64).pin_memory()
-    key = ("rows", mode, width, height, bool(cull))
-    prev = _last_total.get(key) if lazy else None
-    sync = prev is None
-    with _stage("bin_count"):
-        check(L.b200gs_bin_count_rows(mode, width, height, n, ptr(rows), int(cull), ptr(ws_a), ws_a.numel(), ptr(d_total),
-                                      _host_total.data_ptr(), 1 if sync else 0, st), "b200gs_bin_count_rows")
-    if sync:
-        total = capacity = int(_host_total[0])
-        _last_total[key] = total
-        pending = None
-    else:
-        event = torch.cuda.Event()
-        event.record()
-        total = -1
-        capacity = int(prev * LAZY_SLACK) + 4096
-        pending = (event, key, capacity)
-    sorted_ids = torch.empty(max(capacity, 1), dtype=torch.int32, device=dev)
-    ws_b = torch.empty(L.b200gs_bin_sort_workspace_bytes(n, capacity, width, height), dtype=torch.uint8, device=dev)
-    with _stage("bin_sort"):
-        check(L.b200gs_bin_sort_rows(mode, width, height, n, ptr(rows), int(cull), total, ptr(d_total), capacity, ptr(ws_a), ptr(ws_b),
-                                     ws_b.numel(), ptr(sorted_ids), ptr(ranges), st), "b200gs_bin_sort_rows")
-    return Binning(sorted_ids, ranges, None if pending else total, pending)
+
+    def count_call(ws_a, ws_a_bytes, d_counts, host, sync, st):
+        check(L.b200gs_bin_count_rows(mode, width, height, n, ptr(rows), int(cull), ws_a, ws_a_bytes, d_counts, host, sync, st),
+              "b200gs_bin_count_rows")
+
+    return _bin(("rows", mode, width, height, bool(cull)), mode, width, height, n, rows.device, bool(cull), lazy, count_call)
 
 
 def blend_forward_rows(mode, width, height, binning: Binning, rows, bg):

@@ -128,36 +128,41 @@ B200GS_API int b200gs_sh_bwd(int32_t degree, int32_t sh_stride, int64_t n, const
 /* ---- K2-K5: tile binning ------------------------------------------------------------------------------------------
  * replaces dgr InclusiveSum + duplicateWithKeys + SortPairs + identifyTileRanges / gsplat isect_tiles + isect_offset_encode.
  * Result order is exactly that of a stable sort of (tile_id << 32 | float_bits(depth)) keys emitted Gaussian-major:
- * implemented as a stable depth sort of the visible Gaussians followed by a stable tile-id partition of the pairs.
+ * implemented as a stable depth sort of the Gaussians, a stable partition of (coarse cell, Gaussian) pairs (a cell =
+ * 8x8 tiles) and an order-preserving multi-split of every cell's list into its 64 tiles that writes each id once.
  *
- * cull_conic[n,3] / cull_opacity[n] (both NULL, or both given — and then the SAME arrays in phase A and B): exact tile
- *     culling.  A (tile, Gaussian) pair is dropped when no pixel sample of the tile can reach alpha >= 1/255 for that
- *     Gaussian (minimum of the conic's quadratic over the tile box > ln(255*opacity)); the blend loop would have skipped
- *     it at every pixel, so images and gradients do not change while the pair list shrinks ~2x.  With NULL the pair
- *     list is exactly the reference's (every tile of the 3-sigma bounding rect).
+ * Counters: d_counts = device int64[4], host_counts = host int64[4] (pinned or pageable; nullable):
+ *     [0] number of (tile, Gaussian) pairs of the 3-sigma bounding rects — the reference's pair count, an upper bound
+ *         of [2] and equal to it without culling                                              (written by phase A)
+ *     [1] number of (coarse cell, Gaussian) pairs                                              (written by phase A)
+ *     [2] number of pairs actually listed in sorted_ids / tile_ranges                          (written by phase B)
+ *     [3] reserved (0)
+ *   Each phase ends with cudaMemcpyAsync(host_counts <- d_counts) on `stream` when host_counts != NULL and, when
+ *   sync_host != 0, SYNCHRONISES the stream.  Sync-free use: size max_coarse / max_pairs from the previous view's
+ *   counters, pass sync_host = 0, record an event, and check counts[1] <= max_coarse && counts[2] <= max_pairs later.
+ * cull_conic[n,3] / cull_opacity[n] (both NULL, or both given): exact tile culling.  A (tile, Gaussian) pair is dropped
+ *     when no pixel sample of the tile can reach alpha >= 1/255 for that Gaussian (minimum of the conic's quadratic
+ *     over the tile box > ln(255*opacity)); the blend loop would have skipped it at every pixel, so images and
+ *     gradients do not change while the pair list shrinks ~2x.  With NULL the pair list is exactly the reference's
+ *     (every tile of the 3-sigma bounding rect).
  * b200gs_bin_count_workspace_bytes / b200gs_bin_sort_workspace_bytes: bytes of scratch for phase A (n Gaussians) and
- *     phase B (up to max_pairs (tile,Gaussian) pairs).  Two buffers because the pair count is only known after phase A.
- * b200gs_bin_count: phase A. Depth-sorts, scans tiles-per-Gaussian (recomputed from xy/radii with the mode's rect
- *     rule) and writes the pair total to d_total (device int64) and, when host_total != NULL (pinned or pageable
- *     host int64), copies it there (cudaMemcpyAsync on `stream`) and, when sync_host != 0, SYNCHRONISES the stream —
- *     the one optional host sync of the forward.  With sync_host == 0 the caller records its own event and reads
- *     host_total later (capacity mode of phase B).
- *     workspace_a must stay untouched until phase B has been enqueued.
- * b200gs_bin_sort: phase B. Emits pairs, partitions by tile, writes sorted_ids[total] (Gaussian ids, front to back
- *     inside each tile) and tile_ranges[n_tiles,2] (int32 [start,end)).  d_total = the device counter phase A wrote.
- *     total >= 0 (exact mode): the host copy of that counter; returns B200GS_ENOSPACE if total > max_pairs.
- *     total < 0 (capacity mode, no host sync): the count is read on the device only; all max_pairs slots are sorted
- *     (unused ones padded behind the last tile) and pairs beyond max_pairs are DROPPED — the caller must compare the
- *     counter with max_pairs afterwards (it is copied to host_total asynchronously by phase A) and redo the phase with
- *     a larger buffer if it overflowed. */
+ *     phase B (up to max_coarse coarse pairs).  Two buffers because counts[1] is only known after phase A.
+ * b200gs_bin_count: phase A.  Depth keys, stable depth sort, scan of cells-per-Gaussian; counts[0], counts[1].  Everything
+ *     phase B needs to know about a Gaussian (xy, radius, cull_conic, cull_opacity) is packed into workspace_a, which
+ *     must stay untouched until phase B has been enqueued.
+ * b200gs_bin_sort: phase B (reads workspace_a only; cull = whether phase A was given the cull arrays).  Writes sorted_ids (Gaussian ids, front to back inside each tile; capacity max_pairs),
+ *     tile_ranges[n_tiles,2] (int32 [start,end), clamped to max_pairs) and counts[2].  Coarse pairs beyond max_coarse
+ *     and ids beyond max_pairs are DROPPED (never written out of bounds): the caller compares the counters with the
+ *     capacities and redoes the phase with larger buffers if either overflowed.  max_pairs = counts[0] and
+ *     max_coarse = counts[1] can never overflow. */
 B200GS_API size_t b200gs_bin_count_workspace_bytes(int64_t n);
-B200GS_API size_t b200gs_bin_sort_workspace_bytes(int64_t n, int64_t max_pairs, int32_t width, int32_t height);
+B200GS_API size_t b200gs_bin_sort_workspace_bytes(int64_t n, int64_t max_coarse, int32_t width, int32_t height);
 B200GS_API int b200gs_bin_count(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const float* depth,
-                     const int32_t* radii, const float* cull_conic, const float* cull_opacity, void* workspace_a, size_t workspace_a_bytes, int64_t* d_total,
-                     int64_t* host_total, int32_t sync_host, void* stream);
-B200GS_API int b200gs_bin_sort(int32_t mode, int32_t width, int32_t height, int64_t n, const float* xy, const int32_t* radii,
-                    const float* cull_conic, const float* cull_opacity, int64_t total, const int64_t* d_total, int64_t max_pairs, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes,
-                    int32_t* sorted_ids, int32_t* tile_ranges, void* stream);
+                     const int32_t* radii, const float* cull_conic, const float* cull_opacity, void* workspace_a, size_t workspace_a_bytes,
+                     int64_t* d_counts, int64_t* host_counts, int32_t sync_host, void* stream);
+B200GS_API int b200gs_bin_sort(int32_t mode, int32_t width, int32_t height, int64_t n, int32_t cull, int64_t max_coarse, int64_t max_pairs,
+                    int64_t* d_counts, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes, int32_t* sorted_ids,
+                    int32_t* tile_ranges, int64_t* host_counts, int32_t sync_host, void* stream);
 
 /* ---- K6: blend forward ---------------------------------------------------------------------------------------------
  * replaces dgr renderCUDA fwd / gsplat rasterize_to_pixels fwd.  channels in {1,2,3,4}.
@@ -190,7 +195,7 @@ B200GS_API int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int
  *     exclusive scan of the visibility flags) is kept for the backward; d_count <- number of rows.
  * b200gs_unpack_rows_grad: the backward of that gather: full-length per-Gaussian cotangents for b200gs_project_bwd*
  *     (zeros for culled Gaussians).
- * b200gs_bin_count_rows / bin_sort_rows / blend_fwd_rows / blend_bwd_rows: K2-K7 reading the rows IN PLACE (strided
+ * b200gs_bin_count_rows (then b200gs_bin_sort) / blend_fwd_rows / blend_bwd_rows: K2-K7 reading the rows IN PLACE (strided
  *     access, no split copies); blend_bwd_rows accumulates into a zero-filled [n,12] gradient row buffer that goes
  *     straight back through the all-to-all.  3 colour channels; cull != 0 enables exact tile culling. */
 #define B200GS_ROW_FLOATS 12
@@ -216,11 +221,8 @@ B200GS_API int b200gs_pack_rows(int64_t n, const float* xy, const float* depth, 
 B200GS_API int b200gs_unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offsets, const float* v_rows, float* v_xy,
                                        float* v_depth, float* v_conic, float* v_comp, float* v_opacity, float* v_rgb, void* stream);
 B200GS_API int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull,
-                                     void* workspace_a, size_t workspace_a_bytes, int64_t* d_total, int64_t* host_total,
+                                     void* workspace_a, size_t workspace_a_bytes, int64_t* d_counts, int64_t* host_counts,
                                      int32_t sync_host, void* stream);
-B200GS_API int b200gs_bin_sort_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull,
-                                    int64_t total, const int64_t* d_total, int64_t max_pairs, const void* workspace_a,
-                                    void* workspace_b, size_t workspace_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges, void* stream);
 B200GS_API int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                                      const float* rows, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride,
                                      float* final_T, int32_t* n_contrib, float* alpha, void* stream);
