@@ -318,7 +318,7 @@ template <bool GSPLAT, typename KT>
 __global__ void __launch_bounds__(256) emit_cells_kernel(int64_t n, int grid_x, int grid_y, int cgrid_x, int cull, int64_t max_coarse,
                                                          const int32_t* __restrict__ order, const SplatRec* __restrict__ recs,
                                                          const int64_t* __restrict__ offsets, KT* __restrict__ ckeys,
-                                                         CellEntry* __restrict__ cvals) {
+                                                         CellEntry* __restrict__ cvals, KT pad_key) {
     __shared__ KT s_k[EMIT_SLOTS];
     __shared__ int32_t s_id[EMIT_SLOTS];
     __shared__ unsigned long long s_mask[EMIT_SLOTS];
@@ -331,6 +331,12 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(int64_t n, int grid_x, 
     const unsigned lane = tid & 31u, w = tid >> 5;
     const int64_t rank0 = int64_t(blockIdx.x) * blockDim.x;
     const int64_t rnk = rank0 + tid;
+    {   // slots [total, capacity) are sorted too: give them a key above every cell id (a slice per block)
+        const int64_t total = n > 0 ? offsets[n - 1] : 0;
+        const int64_t per = (max(max_coarse - total, (int64_t)0) + gridDim.x - 1) / gridDim.x;
+        const int64_t p0 = total + per * blockIdx.x, p1 = min(max_coarse, p0 + per);
+        for (int64_t i = p0 + tid; i < p1; i += 256) ckeys[i] = pad_key;
+    }
     int g = -1, x0 = 0, y0 = 0, x1 = 0, y1 = 0, t = 0, nrows = 0;
     int64_t start = 0;
     CullE e{};
@@ -430,13 +436,6 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(int64_t n, int grid_x, 
     }
 }
 
-// entries [total, cap) of the key buffer get a key above every cell id so they sort to the end
-template <typename KT>
-__global__ void __launch_bounds__(256) pad_keys_kernel(int64_t cap, const int64_t* __restrict__ d_total, KT* __restrict__ keys, KT pad) {
-    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    for (int64_t i = *d_total + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < cap; i += stride) keys[i] = pad;
-}
-
 // ranges[c] = [first, last+1) of cell c in the partitioned key array; RV keys per thread (one 16-byte load).
 template <typename KT>
 __global__ void __launch_bounds__(256) cell_ranges_kernel(int64_t cap, const int64_t* __restrict__ d_total, const KT* __restrict__ keys,
@@ -469,7 +468,7 @@ __global__ void __launch_bounds__(256) cell_ranges_kernel(int64_t cap, const int
 
 // chunk_base[c] = number of CHUNK-entry chunks of the cells before c; chunk_cell[chunk] = its cell (one block; n_cells is small)
 __global__ void __launch_bounds__(1024) chunk_table_kernel(int n_cells, const int2* __restrict__ cell_ranges, int32_t* __restrict__ chunk_base,
-                                                           int32_t* __restrict__ chunk_cell) {
+                                                           int32_t* __restrict__ chunk_cell, int n_tiles, int64_t* __restrict__ tile_total) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -502,15 +501,23 @@ __global__ void __launch_bounds__(1024) chunk_table_kernel(int n_cells, const in
         __syncthreads();
         const int carry = s_carry;
         const int excl = carry + s_warp[w] + inc - v;
-        if (i < n_cells) {
-            chunk_base[i] = excl;
-            for (int k = 0; k < v; ++k) chunk_cell[excl + k] = i;
-        }
+        if (i < n_cells) chunk_base[i] = excl;
         __syncthreads();
         if (tid == 1023) s_carry = excl + v;
         __syncthreads();
     }
-    if (tid == 0) chunk_base[n_cells] = s_carry;
+    const int total = s_carry;
+    if (tid == 0) chunk_base[n_cells] = total;
+    for (int i = tid; i < n_tiles; i += 1024) tile_total[i] = 0;    // accumulated by chunk_counts_kernel
+    __syncthreads();                                                // chunk_base (written by this block) is visible
+    for (int c = tid; c < total; c += 1024) {
+        int lo = 0, hi = n_cells;   // invariant: chunk_base[lo] <= c < chunk_base[hi]; cells without entries own no chunk
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (chunk_base[mid] <= c) lo = mid; else hi = mid;
+        }
+        chunk_cell[c] = lo;
+    }
 }
 
 // 32x32 bit-matrix transpose across a warp: lane l passes row l, lane t receives column t
@@ -528,9 +535,10 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, unsigned lane) {
 // Phase C: one block per chunk (256 consecutive entries of one cell's depth-ordered list): per-tile entry counts.
 // Each warp transposes the masks of its 32 entries: lane t then holds, for tiles t and t+32, the bit set of the warp's
 // entries that reach the tile.
-__global__ void __launch_bounds__(CHUNK) chunk_counts_kernel(int n_cells, const int2* __restrict__ cell_ranges,
+__global__ void __launch_bounds__(CHUNK) chunk_counts_kernel(int n_cells, int cgrid_x, int grid_x, int grid_y, const int2* __restrict__ cell_ranges,
                                                              const int32_t* __restrict__ chunk_base, const int32_t* __restrict__ chunk_cell,
-                                                             const CellEntry* __restrict__ entries, uint16_t* __restrict__ chunk_cnt) {
+                                                             const CellEntry* __restrict__ entries, uint16_t* __restrict__ chunk_cnt,
+                                                             int64_t* __restrict__ tile_total) {
     __shared__ uint16_t s_cnt[CHUNK / 32][CELL_TILES];
     const int c = blockIdx.x;
     if (c >= __ldg(chunk_base + n_cells)) return;
@@ -551,24 +559,28 @@ __global__ void __launch_bounds__(CHUNK) chunk_counts_kernel(int n_cells, const 
 #pragma unroll
         for (int k = 0; k < CHUNK / 32; ++k) sum += s_cnt[k][threadIdx.x];
         chunk_cnt[int64_t(c) * CELL_TILES + threadIdx.x] = (uint16_t)sum;
+        const int t = threadIdx.x;
+        const int tx = ((cell % cgrid_x) << SUPER_SHIFT) + (t & (SUPER - 1));
+        const int ty = ((cell / cgrid_x) << SUPER_SHIFT) + (t >> SUPER_SHIFT);
+        if (sum > 0 && tx < grid_x && ty < grid_y)
+            atomicAdd(reinterpret_cast<unsigned long long*>(tile_total + int64_t(ty) * grid_x + tx), (unsigned long long)sum);
     }
 }
 
-// Phase D, one block per cell, thread (j, t): prefix over the cell's chunks of tile t's counts, the chunk list split
-// into 16 contiguous parts j so that the sequential walks stay short; the tile's total goes to tile_start (tile-id
-// order).  The LAST block to finish then scans the tile totals in place -> tile starts, tile_ranges (clamped to the
-// capacity of sorted_ids; empty tiles (0,0) like dgr's zero-filled ranges) and the pair total.
-__global__ void __launch_bounds__(1024) chunk_prefix_kernel(int cgrid_x, int grid_x, int grid_y, const int32_t* __restrict__ chunk_base,
+// Phase D.  Blocks [0, n_cells): thread (j, t) of a cell's block computes the prefix over the cell's chunks of tile t's
+// counts, the chunk list split into 16 contiguous parts j so that the sequential walks stay short.  Block n_cells, at the
+// same time: exclusive scan of the tile totals (accumulated by chunk_counts_kernel) in tile-id order, in place -> tile
+// starts; tile_ranges (clamped to the capacity of sorted_ids; empty tiles (0,0) like dgr's zero-filled ranges); counts[2].
+__global__ void __launch_bounds__(1024) chunk_prefix_kernel(int n_cells, int n_tiles, const int32_t* __restrict__ chunk_base,
                                                             const uint16_t* __restrict__ chunk_cnt, uint32_t* __restrict__ chunk_pre,
                                                             int64_t* __restrict__ tile_start, int64_t max_pairs,
                                                             int2* __restrict__ tile_ranges, int64_t* __restrict__ d_counts) {
     __shared__ uint32_t s_part[16][CELL_TILES];
     __shared__ int64_t s_warp[32];
     __shared__ int64_t s_carry;
-    __shared__ int s_last;
-    const int cell = blockIdx.x;
     const int tid = threadIdx.x;
-    {
+    if ((int)blockIdx.x < n_cells) {
+        const int cell = blockIdx.x;
         const int t = tid & (CELL_TILES - 1), j = tid >> 6;
         const int c0 = chunk_base[cell], c1 = chunk_base[cell + 1];
         const int per = (c1 - c0 + 15) >> 4;
@@ -586,24 +598,10 @@ __global__ void __launch_bounds__(1024) chunk_prefix_kernel(int cgrid_x, int gri
             chunk_pre[int64_t(c) * CELL_TILES + t] = run;
             run += v;
         }
-        if (j == 15) {
-            const int tx = ((cell % cgrid_x) << SUPER_SHIFT) + (t & (SUPER - 1));
-            const int ty = ((cell / cgrid_x) << SUPER_SHIFT) + (t >> SUPER_SHIFT);
-            if (tx < grid_x && ty < grid_y) tile_start[int64_t(ty) * grid_x + tx] = run;
-        }
+        return;
     }
-    // ticket: d_counts[3] is zero on entry (phase A memset) and reset by the last block
-    __threadfence();
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    if (tid == 0) {
-        const unsigned long long ticket = atomicAdd(reinterpret_cast<unsigned long long*>(d_counts + 3), 1ull);
-        s_last = (ticket == (unsigned long long)(gridDim.x - 1));
-        s_carry = 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int n_tiles = grid_x * grid_y;
     const int lane = tid & 31, w = tid >> 5;
     for (int base = 0; base < n_tiles; base += 8192) {
         const int i0 = base + tid * 8;
@@ -612,12 +610,12 @@ __global__ void __launch_bounds__(1024) chunk_prefix_kernel(int cgrid_x, int gri
             const longlong2* p = reinterpret_cast<const longlong2*>(tile_start + i0);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const longlong2 q = __ldcg(p + k);
+                const longlong2 q = p[k];
                 v[2 * k] = q.x; v[2 * k + 1] = q.y;
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = (i0 + k < n_tiles) ? __ldcg(tile_start + i0 + k) : 0;
+            for (int k = 0; k < 8; ++k) v[k] = (i0 + k < n_tiles) ? tile_start[i0 + k] : 0;
         }
         int64_t sum = 0;
 #pragma unroll
@@ -654,10 +652,7 @@ __global__ void __launch_bounds__(1024) chunk_prefix_kernel(int cgrid_x, int gri
         if (tid == 1023) s_carry = run;
         __syncthreads();
     }
-    if (tid == 0) {
-        d_counts[2] = s_carry;
-        d_counts[3] = 0;
-    }
+    if (tid == 0) d_counts[2] = s_carry;
 }
 
 // Phase E: one block per chunk; sorted_ids[tile start + chunk prefix + rank in chunk] = id.  After the warp transpose,
@@ -753,13 +748,13 @@ int partition_cells(int mode, int64_t n, int grid_x, int grid_y, int cgrid_x, in
     KT* kout = (KT*)keys_out;
     const unsigned blocks = (unsigned)div_up64(n, 256);
     if (mode == B200GS_MODE_GSPLAT)
-        emit_cells_kernel<true, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, kin, cvals_in);
+        emit_cells_kernel<true, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, kin, cvals_in,
+                                                             (KT)n_cells);
     else
-        emit_cells_kernel<false, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, kin, cvals_in);
+        emit_cells_kernel<false, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, kin, cvals_in,
+                                                              (KT)n_cells);
     B200GS_LAUNCH_CHECK();
     const int bits = bits_for(n_cells + 1);   // + the pad key n_cells
-    pad_keys_kernel<KT><<<64, 256, 0, s>>>(max_coarse, d_coarse, kin, (KT)n_cells);
-    B200GS_LAUNCH_CHECK();
     size_t tb = temp_bytes;
     B200GS_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, kin, kout, cvals_in, entries, (int)max_coarse, 0, bits, s));
     constexpr int RV = 16 / sizeof(KT) >= 8 ? 8 : 4;
@@ -865,15 +860,15 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
         rc = partition_cells<uint32_t>(mode, n, grid_x, grid_y, cgrid_x, n_cells, cull, d_counts + 1, max_coarse, order, recs, offsets,
                                        w + L.ckeys_in, w + L.ckeys_out, cvals_in, w + L.temp, L.temp_bytes, entries, cell_ranges, s);
     if (rc != B200GS_OK) return rc;
-    chunk_table_kernel<<<1, 1024, 0, s>>>(n_cells, cell_ranges, chunk_base, chunk_cell);
+    chunk_table_kernel<<<1, 1024, 0, s>>>(n_cells, cell_ranges, chunk_base, chunk_cell, n_tiles, tile_start);
     B200GS_LAUNCH_CHECK();
 
     // C: per-chunk tile counts;  D: chunk prefixes, tile starts / ranges / total;  E: ids in place
     const unsigned chunks = (unsigned)L.max_chunks;
-    chunk_counts_kernel<<<chunks, CHUNK, 0, s>>>(n_cells, cell_ranges, chunk_base, chunk_cell, entries, chunk_cnt);
+    chunk_counts_kernel<<<chunks, CHUNK, 0, s>>>(n_cells, cgrid_x, grid_x, grid_y, cell_ranges, chunk_base, chunk_cell, entries, chunk_cnt, tile_start);
     B200GS_LAUNCH_CHECK();
-    chunk_prefix_kernel<<<(unsigned)n_cells, 1024, 0, s>>>(cgrid_x, grid_x, grid_y, chunk_base, chunk_cnt, chunk_pre, tile_start, max_pairs,
-                                                           (int2*)tile_ranges, d_counts);
+    chunk_prefix_kernel<<<(unsigned)n_cells + 1, 1024, 0, s>>>(n_cells, n_tiles, chunk_base, chunk_cnt, chunk_pre, tile_start, max_pairs,
+                                                               (int2*)tile_ranges, d_counts);
     B200GS_LAUNCH_CHECK();
     scatter_ids_kernel<<<chunks, CHUNK, 0, s>>>(n_cells, cgrid_x, grid_x, grid_y, max_pairs, cell_ranges, chunk_base, chunk_cell, entries, chunk_pre,
                                                 tile_start, sorted_ids);
