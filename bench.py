@@ -270,10 +270,13 @@ def main():
     # computes (double buffer), and every step's scalar result is read back (its D2H lands one step later, so the host
     # never stalls the GPU).  Every byte is moved inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
+    read_stream = torch.cuda.Stream(device=dev)   # the result read-back never sits in the compute stream
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
     in_bufs = [torch.empty_like(cot), torch.empty_like(cot)]
     in_ready = [torch.cuda.Event(), torch.cuda.Event()]
     loss_hosts = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
     loss_done = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_dev = [torch.zeros(1, device=dev), torch.zeros(1, device=dev)]
     results = []
 
     def prefetch(i):
@@ -295,8 +298,12 @@ def main():
         loss = (out["render"] * c).sum()
         loss.backward()
         if e2e:
-            loss_hosts[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)
-            loss_done[i & 1].record()
+            loss_dev[i & 1].copy_(loss.detach().reshape(1))
+            loss_ready[i & 1].record()
+            read_stream.wait_event(loss_ready[i & 1])
+            with torch.cuda.stream(read_stream):
+                loss_hosts[i & 1].copy_(loss_dev[i & 1], non_blocking=True)
+                loss_done[i & 1].record(read_stream)
         return out
 
     def barrier():

@@ -318,7 +318,8 @@ template <bool GSPLAT, typename KT>
 __global__ void __launch_bounds__(256) emit_cells_kernel(int64_t n, int grid_x, int grid_y, int cgrid_x, int cull, int64_t max_coarse,
                                                          const int32_t* __restrict__ order, const SplatRec* __restrict__ recs,
                                                          const int64_t* __restrict__ offsets, KT* __restrict__ ckeys,
-                                                         CellEntry* __restrict__ cvals, KT pad_key) {
+                                                         CellEntry* __restrict__ cvals, KT pad_key, int n_cells,
+                                                         int2* __restrict__ cell_ranges) {
     __shared__ KT s_k[EMIT_SLOTS];
     __shared__ int32_t s_id[EMIT_SLOTS];
     __shared__ unsigned long long s_mask[EMIT_SLOTS];
@@ -336,6 +337,8 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(int64_t n, int grid_x, 
         const int64_t per = (max(max_coarse - total, (int64_t)0) + gridDim.x - 1) / gridDim.x;
         const int64_t p0 = total + per * blockIdx.x, p1 = min(max_coarse, p0 + per);
         for (int64_t i = p0 + tid; i < p1; i += 256) ckeys[i] = pad_key;
+        if (blockIdx.x == 0)   // cells without entries keep the empty range (filled in by cell_ranges_kernel otherwise)
+            for (int i = tid; i < n_cells; i += 256) cell_ranges[i] = make_int2(0, 0);
     }
     int g = -1, x0 = 0, y0 = 0, x1 = 0, y1 = 0, t = 0, nrows = 0;
     int64_t start = 0;
@@ -749,10 +752,10 @@ int partition_cells(int mode, int64_t n, int grid_x, int grid_y, int cgrid_x, in
     const unsigned blocks = (unsigned)div_up64(n, 256);
     if (mode == B200GS_MODE_GSPLAT)
         emit_cells_kernel<true, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, kin, cvals_in,
-                                                             (KT)n_cells);
+                                                             (KT)n_cells, n_cells, cell_ranges);
     else
         emit_cells_kernel<false, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, kin, cvals_in,
-                                                              (KT)n_cells);
+                                                              (KT)n_cells, n_cells, cell_ranges);
     B200GS_LAUNCH_CHECK();
     const int bits = bits_for(n_cells + 1);   // + the pad key n_cells
     size_t tb = temp_bytes;
@@ -773,9 +776,30 @@ static BinSrc make_src(int row_stride, const float* xy, const float* depth, cons
     return BinSrc{xy, depth, radii, conic, opacity, 2, 1, 1, 3, 1};
 }
 
+// Counter read-back.  For pinned (mapped) host memory the counters are PUBLISHED by a kernel with system-scope stores
+// instead of a cudaMemcpyAsync: an in-stream D2H copy is serviced by a copy engine, and queues behind whatever bulk
+// transfer the application has in flight on it (e.g. the H2D prefetch of the next training image) — which would stall
+// the whole forward behind a 32-byte copy.  Pageable host memory falls back to the copy.
+__global__ void publish_counts_kernel(const int64_t* __restrict__ d_counts, volatile int64_t* __restrict__ host_counts) {
+    if (threadIdx.x < 4) host_counts[threadIdx.x] = d_counts[threadIdx.x];
+    __threadfence_system();
+}
+
+__global__ void zero_counts_kernel(int64_t* __restrict__ d_counts) {
+    if (threadIdx.x < 4) d_counts[threadIdx.x] = 0;
+}
+
 static int copy_counts(const int64_t* d_counts, int64_t* host_counts, int sync_host, cudaStream_t s) {
     if (host_counts != nullptr) {
-        B200GS_CUDA(cudaMemcpyAsync(host_counts, d_counts, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        cudaPointerAttributes attr{};
+        const cudaError_t e = cudaPointerGetAttributes(&attr, host_counts);
+        if (e == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr) {
+            publish_counts_kernel<<<1, 32, 0, s>>>(d_counts, (volatile int64_t*)attr.devicePointer);
+            B200GS_LAUNCH_CHECK();
+        } else {
+            (void)cudaGetLastError();
+            B200GS_CUDA(cudaMemcpyAsync(host_counts, d_counts, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        }
         if (sync_host) B200GS_CUDA(cudaStreamSynchronize(s));
     }
     return B200GS_OK;
@@ -798,7 +822,8 @@ int bin_count(int mode, int width, int height, int64_t n, int row_stride, const 
     int64_t* offsets = (int64_t*)(w + L.offsets);
     SplatRec* recs = (SplatRec*)(w + L.recs);
     const int grid_x = div_up(width, TILE), grid_y = div_up(height, TILE);
-    B200GS_CUDA(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int64_t), s));
+    zero_counts_kernel<<<1, 32, 0, s>>>(d_counts);
+    B200GS_LAUNCH_CHECK();
     if (n > 0) {
         const unsigned blocks = (unsigned)div_up64(n, 256);
         const BinSrc src = make_src(row_stride, xy, depth, radii, conic, opacity);
@@ -851,7 +876,6 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
     int64_t* tile_start = (int64_t*)(w + L.tile_start);
 
     // B: coarse pairs with their tile masks, partitioned by cell
-    B200GS_CUDA(cudaMemsetAsync(cell_ranges, 0, sizeof(int2) * (size_t)n_cells, s));
     int rc;
     if (bits_for(n_cells + 1) <= 16)
         rc = partition_cells<uint16_t>(mode, n, grid_x, grid_y, cgrid_x, n_cells, cull, d_counts + 1, max_coarse, order, recs, offsets,
