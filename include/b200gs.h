@@ -137,9 +137,12 @@ B200GS_API int b200gs_sh_bwd(int32_t degree, int32_t sh_stride, int64_t n, const
  *     [1] number of (coarse cell, Gaussian) pairs                                              (written by phase A)
  *     [2] number of pairs actually listed in sorted_ids / tile_ranges                          (written by phase B)
  *     [3] reserved (0)
- *   Each phase ends with cudaMemcpyAsync(host_counts <- d_counts) on `stream` when host_counts != NULL and, when
- *   sync_host != 0, SYNCHRONISES the stream.  Sync-free use: size max_coarse / max_pairs from the previous view's
- *   counters, pass sync_host = 0, record an event, and check counts[1] <= max_coarse && counts[2] <= max_pairs later.
+ *   Each phase ends by delivering d_counts to host_counts (when != NULL) in stream order — pinned/mapped host memory is
+ *   written by a tiny kernel with system-scope stores (a D2H copy would queue on a copy engine behind the application's
+ *   bulk transfers), pageable memory by cudaMemcpyAsync — and, when sync_host != 0, SYNCHRONISES the stream.
+ *   Sync-free use: size max_coarse from the previous view's counts[1] and max_pairs from its counts[0] (the bound is known
+ *   after phase A already), pass sync_host = 0, record an event after phase A and check
+ *   counts[1] <= max_coarse && counts[0] <= max_pairs once the rest of the forward has been enqueued.
  * cull_conic[n,3] / cull_opacity[n] (both NULL, or both given): exact tile culling.  A (tile, Gaussian) pair is dropped
  *     when no pixel sample of the tile can reach alpha >= 1/255 for that Gaussian (minimum of the conic's quadratic
  *     over the tile box > ln(255*opacity)); the blend loop would have skipped it at every pixel, so images and

@@ -1,6 +1,6 @@
 """Which part of the end-to-end loop costs time: H2D prefetch, D2H loss read, or the lagged host sync."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from b200gs.renderers import B200VanillaRenderer
 from b200gs.scene import SyntheticGaussians, make_ring_cameras, make_scene

@@ -1,6 +1,6 @@
 """Host-side cost of one training step: (a) pure enqueue time with the GPU far behind, (b) cProfile of the step loop."""
 import cProfile, pstats, sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from b200gs.renderers import B200VanillaRenderer
 from b200gs.scene import SyntheticGaussians, make_ring_cameras, make_scene
