@@ -279,13 +279,20 @@ def main():
     loss_dev = [torch.zeros(1, device=dev), torch.zeros(1, device=dev)]
     results = []
 
+    fwd_done = torch.cuda.Event()
+    step_done = [torch.cuda.Event(), torch.cuda.Event()]
+
     def prefetch(i):
-        copy_stream.wait_stream(torch.cuda.current_stream())     # the buffer's previous consumer has been enqueued
+        # called right after step i-1's forward has been enqueued: the upload overlaps that step's backward (compute-bound
+        # kernels) instead of the next forward's projection/binning (bandwidth- and latency-bound: measured 1.68 vs 1.58
+        # ms/step, profiles/tools/e2e_probe.py).  The buffer's previous consumer (step i-2) precedes the event in stream order.
+        fwd_done.record()
+        copy_stream.wait_event(fwd_done)
         with torch.cuda.stream(copy_stream):
             in_bufs[i & 1].copy_(cot_host, non_blocking=True)
             in_ready[i & 1].record(copy_stream)
 
-    def step(i, e2e=False):
+    def step(i, e2e=False, more=False):
         cam = cams[(i * world + rank) % len(cams)]   # each rank renders a different pose
         for p in model.parameters():
             p.grad = None
@@ -295,6 +302,8 @@ def main():
         else:
             c = cot
         out = renderer(cam, model, bg)
+        if e2e and more:
+            prefetch(i + 1)
         loss = (out["render"] * c).sum()
         loss.backward()
         if e2e:
@@ -318,12 +327,15 @@ def main():
         if e2e:
             prefetch(0)
         for i in range(k):
-            if e2e and i + 1 < k:
-                prefetch(i + 1)
-            step(i, e2e)
-            if e2e and i > 0:                                   # the user reads the previous step's result
-                loss_done[(i - 1) & 1].synchronize()
-                results.append(float(loss_hosts[(i - 1) & 1][0]))
+            step(i, e2e, i + 1 < k)
+            if not e2e:
+                step_done[i & 1].record()
+            if i > 0:   # the host stays at most one step ahead in both loops, like a training loop that logs its loss
+                if e2e:                                         # the user reads the previous step's result
+                    loss_done[(i - 1) & 1].synchronize()
+                    results.append(float(loss_hosts[(i - 1) & 1][0]))
+                else:
+                    step_done[(i - 1) & 1].synchronize()
         if e2e:
             loss_done[(k - 1) & 1].synchronize()
             results.append(float(loss_hosts[(k - 1) & 1][0]))

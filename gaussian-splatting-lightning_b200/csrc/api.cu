@@ -201,18 +201,25 @@ int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int32_t channe
                             v_opacity, v_colors, v_xy_abs, (cudaStream_t)stream);
 }
 
+int b200gs_publish_i64(const int64_t* d_values, int64_t* host_values, int32_t n, void* stream) {
+    B200GS_CHECK_ARG(d_values && host_values && n > 0, "bad argument");
+    return publish_i64(d_values, host_values, n, (cudaStream_t)stream);
+}
+
 // ---- [n,12] row layout (the exchange format of the Gaussian-sharded renderer) -------------------------------------------
 size_t b200gs_pack_rows_workspace_bytes(int64_t n) { return n < 0 ? 0 : pack_rows_workspace_bytes(n); }
 
-int b200gs_pack_rows(int64_t n, const float* xy, const float* depth, const float* conic, const float* comp, const float* opacity,
-                     const float* rgb, const int32_t* radii, void* workspace, size_t workspace_bytes, int32_t* offsets, float* rows,
-                     int64_t* d_count, void* stream) {
+int b200gs_pack_rows(int64_t n, int64_t segment_len, int64_t segment_cap, const float* xy, const float* depth, const float* conic,
+                     const float* comp, const float* opacity, const float* rgb, const int32_t* radii, void* workspace,
+                     size_t workspace_bytes, int32_t* row_index, float* rows, int64_t* d_count, void* stream) {
     B200GS_CHECK_ARG(n >= 0 && n < (int64_t(1) << 31), "bad n");
+    B200GS_CHECK_ARG(segment_cap >= 0 && (segment_cap == 0 || segment_len > 0), "bad segment_len / segment_cap");
+    B200GS_CHECK_ARG(segment_cap == 0 || (n + segment_len - 1) / segment_len * segment_cap < (int64_t(1) << 31), "segments * segment_cap >= 2^31");
     B200GS_CHECK_ARG(d_count != nullptr, "d_count must not be NULL");
-    B200GS_CHECK_ARG(n == 0 || (xy && depth && conic && opacity && rgb && radii && workspace && offsets && rows), "NULL pointer");
+    B200GS_CHECK_ARG(n == 0 || (xy && depth && conic && opacity && rgb && radii && workspace && row_index && rows), "NULL pointer");
     B200GS_CHECK_ARG(n == 0 || workspace_bytes >= pack_rows_workspace_bytes(n), "workspace too small");
-    return pack_rows(n, xy, depth, conic, comp, opacity, rgb, radii, workspace, workspace_bytes, offsets, rows, d_count,
-                     (cudaStream_t)stream);
+    return pack_rows(n, segment_len, segment_cap, xy, depth, conic, comp, opacity, rgb, radii, workspace, workspace_bytes, row_index, rows,
+                     d_count, (cudaStream_t)stream);
 }
 
 int b200gs_unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offsets, const float* v_rows, float* v_xy, float* v_depth,

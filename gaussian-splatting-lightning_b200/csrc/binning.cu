@@ -785,6 +785,11 @@ __global__ void publish_counts_kernel(const int64_t* __restrict__ d_counts, vola
     __threadfence_system();
 }
 
+__global__ void publish_i64_kernel(const int64_t* __restrict__ src, volatile int64_t* __restrict__ dst, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+
 __global__ void zero_counts_kernel(int64_t* __restrict__ d_counts) {
     if (threadIdx.x < 4) d_counts[threadIdx.x] = 0;
 }
@@ -801,6 +806,19 @@ static int copy_counts(const int64_t* d_counts, int64_t* host_counts, int sync_h
             B200GS_CUDA(cudaMemcpyAsync(host_counts, d_counts, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         }
         if (sync_host) B200GS_CUDA(cudaStreamSynchronize(s));
+    }
+    return B200GS_OK;
+}
+
+int publish_i64(const int64_t* d_values, int64_t* host_values, int n, cudaStream_t s) {
+    cudaPointerAttributes attr{};
+    const cudaError_t e = cudaPointerGetAttributes(&attr, host_values);
+    if (e == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr) {
+        publish_i64_kernel<<<1, 64, 0, s>>>(d_values, (volatile int64_t*)attr.devicePointer, n);
+        B200GS_LAUNCH_CHECK();
+    } else {
+        (void)cudaGetLastError();
+        B200GS_CUDA(cudaMemcpyAsync(host_values, d_values, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
     }
     return B200GS_OK;
 }
@@ -908,22 +926,46 @@ struct VisibleFlag {
     __host__ __device__ int32_t operator()(int32_t i) const { return radii[i] > 0 ? 1 : 0; }
 };
 
-__global__ void __launch_bounds__(256) pack_rows_kernel(int64_t n, const float2* __restrict__ xy, const float* __restrict__ depth,
-                                                        const float* __restrict__ conic, const float* __restrict__ comp,
-                                                        const float* __restrict__ opacity, const float* __restrict__ rgb,
-                                                        const int32_t* __restrict__ radii, const int32_t* __restrict__ offsets,
+// scan[i] = number of visible entries before i.  Plain layout (seg_cap == 0): row index = scan[i], d_count[0] = total.
+// Segmented layout (seg_cap > 0; a segment = the seg_len entries of one camera = the rows for one destination rank):
+// segment j owns rows [j*seg_cap, (j+1)*seg_cap) — a fixed-size send block, so the all-to-all needs no size exchange;
+// rows past the capacity are dropped and reported through d_count[j] = visible entries of segment j (the caller compares
+// with seg_cap); unused rows of a block are zero-filled (radius 0 = culled for the binning that reads them in place).
+// row_index[i] is what the backward uses to find entry i's gradient row.
+__global__ void __launch_bounds__(256) pack_rows_kernel(int64_t n, int64_t seg_len, int64_t seg_cap, const float2* __restrict__ xy,
+                                                        const float* __restrict__ depth, const float* __restrict__ conic,
+                                                        const float* __restrict__ comp, const float* __restrict__ opacity,
+                                                        const float* __restrict__ rgb, const int32_t* __restrict__ radii,
+                                                        const int32_t* __restrict__ scan, int32_t* __restrict__ row_index,
                                                         float* __restrict__ rows, int64_t* __restrict__ d_count) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int r = radii[i];
-    const int o = offsets[i];
-    if (i == n - 1) *d_count = o + (r > 0 ? 1 : 0);
-    if (r <= 0) return;
-    float4* out = reinterpret_cast<float4*>(rows + int64_t(o) * B200GS_ROW_FLOATS);
+    int64_t o = scan[i];
+    if (seg_cap > 0) {
+        const int64_t seg = i / seg_len, first = seg * seg_len;
+        const int64_t k = o - scan[first];
+        if (i == min(n, first + seg_len) - 1) d_count[seg] = k + (r > 0 ? 1 : 0);
+        o = (k < seg_cap) ? seg * seg_cap + k : -1;
+    } else if (i == n - 1) {
+        *d_count = o + (r > 0 ? 1 : 0);
+    }
+    row_index[i] = (int32_t)o;
+    if (r <= 0 || o < 0) return;
+    float4* out = reinterpret_cast<float4*>(rows + o * B200GS_ROW_FLOATS);
     const float2 p = xy[i];
     out[0] = make_float4(p.x, p.y, depth[i], conic[3 * i]);
     out[1] = make_float4(conic[3 * i + 1], conic[3 * i + 2], comp ? comp[i] : 1.0f, opacity[i]);
     out[2] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], __int_as_float(r));
+}
+
+// zero the unused tail of every fixed-size block
+__global__ void __launch_bounds__(256) pad_rows_kernel(int64_t segments, int64_t seg_cap, const int64_t* __restrict__ d_count,
+                                                       float* __restrict__ rows) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;    // one float4 per thread, 3 per row
+    if (i >= segments * seg_cap * 3) return;
+    const int64_t row = i / 3, seg = row / seg_cap;
+    if (row - seg * seg_cap >= d_count[seg]) reinterpret_cast<float4*>(rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 __global__ void __launch_bounds__(256) unpack_rows_grad_kernel(int64_t n, const int32_t* __restrict__ radii,
@@ -948,7 +990,7 @@ __global__ void __launch_bounds__(256) unpack_rows_grad_kernel(int64_t n, const 
 
 }  // namespace
 
-size_t pack_rows_workspace_bytes(int64_t n) {
+static size_t pack_scan_temp_bytes(int64_t n) {
     size_t t = 0;
     cub::TransformInputIterator<int32_t, VisibleFlag, cub::CountingInputIterator<int32_t>> it(cub::CountingInputIterator<int32_t>(0),
                                                                                                 VisibleFlag{nullptr});
@@ -956,20 +998,30 @@ size_t pack_rows_workspace_bytes(int64_t n) {
     return align_up(t, 256);
 }
 
-int pack_rows(int64_t n, const float* xy, const float* depth, const float* conic, const float* comp, const float* opacity,
-              const float* rgb, const int32_t* radii, void* ws, size_t ws_bytes, int32_t* offsets, float* rows, int64_t* d_count,
-              cudaStream_t s) {
+size_t pack_rows_workspace_bytes(int64_t n) { return pack_scan_temp_bytes(n) + align_up((size_t)(n > 0 ? n : 1) * 4, 256); }
+
+int pack_rows(int64_t n, int64_t seg_len, int64_t seg_cap, const float* xy, const float* depth, const float* conic, const float* comp,
+              const float* opacity, const float* rgb, const int32_t* radii, void* ws, size_t ws_bytes, int32_t* row_index, float* rows,
+              int64_t* d_count, cudaStream_t s) {
+    const int64_t segments = seg_cap > 0 ? div_up64(n, seg_len) : 1;
     if (n == 0) {
-        B200GS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), s));
+        B200GS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t) * (size_t)segments, s));
         return B200GS_OK;
     }
+    const size_t temp = pack_scan_temp_bytes(n);
+    int32_t* scan = (int32_t*)((char*)ws + temp);
     cub::TransformInputIterator<int32_t, VisibleFlag, cub::CountingInputIterator<int32_t>> it(cub::CountingInputIterator<int32_t>(0),
                                                                                                 VisibleFlag{radii});
-    size_t tb = ws_bytes;
-    B200GS_CUDA(cub::DeviceScan::ExclusiveSum(ws, tb, it, offsets, (int)n, s));
-    pack_rows_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(n, (const float2*)xy, depth, conic, comp, opacity, rgb, radii, offsets,
-                                                               rows, d_count);
+    size_t tb = temp;
+    (void)ws_bytes;
+    B200GS_CUDA(cub::DeviceScan::ExclusiveSum(ws, tb, it, scan, (int)n, s));
+    pack_rows_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(n, seg_cap > 0 ? seg_len : n, seg_cap, (const float2*)xy, depth, conic, comp,
+                                                               opacity, rgb, radii, scan, row_index, rows, d_count);
     B200GS_LAUNCH_CHECK();
+    if (seg_cap > 0) {
+        pad_rows_kernel<<<(unsigned)div_up64(segments * seg_cap * 3, 256), 256, 0, s>>>(segments, seg_cap, d_count, rows);
+        B200GS_LAUNCH_CHECK();
+    }
     return B200GS_OK;
 }
 

@@ -96,10 +96,11 @@ size_t bin_sort_workspace_bytes(int64_t n, int64_t max_coarse, int width, int he
 int bin_count(int mode, int width, int height, int64_t n, int row_stride, const float* xy, const float* depth, const int32_t* radii,
               const float* conic, const float* opacity, void* ws, size_t ws_bytes, int64_t* d_counts, int64_t* host_counts,
               int sync_host, cudaStream_t s);
+int publish_i64(const int64_t* d_values, int64_t* host_values, int n, cudaStream_t s);
 size_t pack_rows_workspace_bytes(int64_t n);
-int pack_rows(int64_t n, const float* xy, const float* depth, const float* conic, const float* comp, const float* opacity,
-              const float* rgb, const int32_t* radii, void* ws, size_t ws_bytes, int32_t* offsets, float* rows, int64_t* d_count,
-              cudaStream_t s);
+int pack_rows(int64_t n, int64_t seg_len, int64_t seg_cap, const float* xy, const float* depth, const float* conic, const float* comp,
+              const float* opacity, const float* rgb, const int32_t* radii, void* ws, size_t ws_bytes, int32_t* row_index, float* rows,
+              int64_t* d_count, cudaStream_t s);
 int unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offsets, const float* v_rows, float* v_xy, float* v_depth,
                      float* v_conic, float* v_comp, float* v_opacity, float* v_rgb, cudaStream_t s);
 int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_coarse, int64_t max_pairs, int64_t* d_counts,

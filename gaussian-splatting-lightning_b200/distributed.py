@@ -97,6 +97,48 @@ def pack_view(camera) -> torch.Tensor:
     return v
 
 
+def pack_view_host(camera, cache: bool = True) -> torch.Tensor:
+    """pack_view on the host (pinned-free CPU tensor), cached on the camera object: reading a camera's device tensors costs a
+    device sync, and a training set revisits the same camera objects every epoch."""
+    v = getattr(camera, "_b200gs_packed_view", None) if cache else None
+    if v is None:
+        v = pack_view(camera).detach().cpu()
+        if cache:
+            try:
+                setattr(camera, "_b200gs_packed_view", v)
+            except Exception:
+                pass
+    return v
+
+
+_HOST_GROUPS = {}
+
+
+def _host_group(group):
+    """A gloo twin of `group` for the per-step camera exchange: 40 floats per rank travel host to host, so the exchange
+    neither waits for the GPU nor makes the GPU wait for the host (an NCCL all_gather followed by .cpu() drains the
+    device queue at the start of every step).  Created collectively on first use."""
+    key = id(group) if group is not None else None
+    g = _HOST_GROUPS.get(key)
+    if g is None:
+        if dist.get_backend(group) == "gloo":
+            g = group if group is not None else dist.group.WORLD
+        else:
+            ranks = dist.get_process_group_ranks(group) if group is not None else None
+            g = dist.new_group(ranks=ranks, backend="gloo")
+        _HOST_GROUPS[key] = g
+    return g
+
+
+def gather_views_host(camera, group=None) -> torch.Tensor:
+    """[world, VIEW_FLOATS] CPU tensor with every rank's camera, no device synchronisation."""
+    world = dist.get_world_size(group)
+    mine = pack_view_host(camera)
+    out = torch.empty(world * VIEW_FLOATS, dtype=torch.float32)
+    dist.all_gather_into_tensor(out, mine.contiguous(), group=_host_group(group))
+    return out.reshape(world, VIEW_FLOATS)
+
+
 class GatheredView:
     """Host-side view of one gathered camera (what ``cameras`` in the return dict holds)."""
 
@@ -105,15 +147,24 @@ class GatheredView:
         self.width, self.height = int(f[0]), int(f[1])
         self.fx, self.fy, self.cx, self.cy = f[2], f[3], f[4], f[5]
         self.world_to_camera = flat[6:22].reshape(4, 4)
-        self.camera_center = flat[22:25].to(device)
+        self.camera_center_host = flat[22:25]
+        self.camera_center = flat[22:25].to(device, non_blocking=True)
+
+
+_EXCHANGE_CAP = {}      # (group id, world, n) -> rows per fixed-size send block, agreed by all ranks (from the previous step's global max)
+EXCHANGE_SLACK = 1.15
 
 
 class _ShardedRasterize(torch.autograd.Function):
     """The whole sharded step as ONE autograd node, everything between the raw shard parameters and this rank's image.
     forward : K1 (fused activations, gsplat constants) per camera into camera-major SoA buffers -> ONE b200gs_pack_rows over all
-              W*n entries (device-side stable compaction; its output IS the all-to-all send buffer, camera-major) -> count
-              exchange (the step's host sync) -> all_to_all_single of [V,12] rows -> K2-K7 reading the received rows in
-              place, pair buffers sized lazily from the previous step.
+              W*n entries (device-side stable compaction straight into the all-to-all send buffer) -> all_to_all_single of
+              [.,12] rows -> K2-K7 reading the received rows in place, pair buffers sized lazily from the previous step.
+              Steady state has NO host sync: every destination gets a fixed-size block of rows (capacity = 1.15 x the
+              previous step's global maximum, identical on all ranks; unused rows are zero = culled), so the all-to-all
+              needs no size exchange; this step's global maximum (one 8-byte all_reduce) is read back after the rest of the
+              forward has been enqueued and, if it exceeded the capacity on ANY rank, all ranks redo the forward with the
+              exact, synchronising exchange (first step, or a >15 % jump of the visible count).
     backward: K7 accumulates into a [R,12] gradient row buffer -> mirrored all_to_all_single -> K8 (fused activation
               chain) per camera reading its cotangents straight from the returned rows and ACCUMULATING into one set of
               gradient buffers (b200gs_project_bwd_rows): no unpack copies, no separate sum kernels."""
@@ -149,34 +200,72 @@ class _ShardedRasterize(torch.autograd.Function):
                                                radii.data_ptr() + 4 * o, conic.data_ptr() + 12 * o, comp.data_ptr() + 4 * o, ptr(tiles),
                                                rgb.data_ptr() + 12 * o, clamped.data_ptr() + o, opac.data_ptr() + 4 * o, st),
                       "b200gs_project_fwd_raw")
-        rows = torch.empty(wn, ROW_FLOATS, **f32)          # upper bound; the first sum(V_j) rows are the send buffer
-        offsets = torch.empty(wn, dtype=torch.int32, device=dev)
+        row_index = torch.empty(wn, dtype=torch.int32, device=dev)
         ws = torch.empty(max(int(L.b200gs_pack_rows_workspace_bytes(wn)), 256), dtype=torch.uint8, device=dev)
-        d_count = torch.empty(1, dtype=torch.int64, device=dev)
-        with ops._stage("pack"):
-            check(L.b200gs_pack_rows(wn, ptr(xy), ptr(depth), ptr(conic), ptr(comp), ptr(opac), ptr(rgb), ptr(radii), ptr(ws), ws.numel(),
-                                     ptr(offsets), ptr(rows), ptr(d_count), st), "b200gs_pack_rows")
-        last = torch.arange(1, world + 1, device=dev, dtype=torch.int64) * n - 1
-        ends = offsets[last].to(torch.int64) + (radii[last] > 0).to(torch.int64)          # cumulative visible counts per camera
-        counts = torch.empty(2 * world, dtype=torch.int64, device=dev)                       # [send | recv]
-        counts[:world] = ends - torch.cat([ends.new_zeros(1), ends[:-1]])
-        dist.all_to_all_single(counts[world:], counts[:world], group=group)
-        host_counts = counts.cpu().tolist()                                                  # the step's host sync
-        send_counts, recv_counts = host_counts[:world], host_counts[world:]
-        recv = torch.empty(sum(recv_counts), ROW_FLOATS, **f32)
-        dist.all_to_all_single(recv, rows[:sum(send_counts)], output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
-        del rows, xy, depth, conic, comp, rgb, opac
-
         gv = views[rank]
         W, H = gv.width, gv.height
-        binning, (image, final_T, n_contrib) = ops.bin_and_blend_rows(MODE_GSPLAT, W, H, recv, bg, True)
+        key = (id(group) if group is not None else None, world, n)
+
+        def pack(seg_cap, rows, d_count):
+            with ops._stage("pack"):
+                check(L.b200gs_pack_rows(wn, n, seg_cap, ptr(xy), ptr(depth), ptr(conic), ptr(comp), ptr(opac), ptr(rgb), ptr(radii), ptr(ws),
+                                         ws.numel(), ptr(row_index), ptr(rows), ptr(d_count), st), "b200gs_pack_rows")
+
+        def exact():
+            """size exchange + host syncs: first step and overflow fallback"""
+            rows = torch.empty(wn, ROW_FLOATS, **f32)          # upper bound; the first sum(V_j) rows are the send buffer
+            d_count = torch.empty(1, dtype=torch.int64, device=dev)
+            pack(0, rows, d_count)
+            last = torch.arange(1, world + 1, device=dev, dtype=torch.int64) * n - 1
+            ends = row_index[last].to(torch.int64) + (radii[last] > 0).to(torch.int64)          # cumulative visible counts per camera
+            counts = torch.empty(2 * world + 1, dtype=torch.int64, device=dev)                   # [send | recv | global max]
+            counts[:world] = ends - torch.cat([ends.new_zeros(1), ends[:-1]])
+            dist.all_to_all_single(counts[world:2 * world], counts[:world], group=group)
+            counts[2 * world] = counts[:world].max()
+            dist.all_reduce(counts[2 * world:], op=dist.ReduceOp.MAX, group=group)
+            host_counts = counts.cpu().tolist()                                                  # host sync
+            send_counts, recv_counts, gmax = host_counts[:world], host_counts[world:2 * world], host_counts[2 * world]
+            recv = torch.empty(sum(recv_counts), ROW_FLOATS, **f32)
+            dist.all_to_all_single(recv, rows[:sum(send_counts)], output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
+            binning, out = ops.bin_and_blend_rows(MODE_GSPLAT, W, H, recv, bg, True)
+            _EXCHANGE_CAP[key] = int(gmax * EXCHANGE_SLACK) + 1024
+            return (send_counts, recv_counts), recv, binning, out
+
+        cap = _EXCHANGE_CAP.get(key)
+        result = None
+        if cap is not None:
+            rows = torch.empty(world * cap, ROW_FLOATS, **f32)
+            d_count = torch.empty(world, dtype=torch.int64, device=dev)
+            pack(cap, rows, d_count)
+            gmax_dev = d_count.max().reshape(1)
+            dist.all_reduce(gmax_dev, op=dist.ReduceOp.MAX, group=group)
+            gmax_host = ops._host_counts()
+            check(L.b200gs_publish_i64(ptr(gmax_dev), gmax_host.data_ptr(), 1, st), "b200gs_publish_i64")
+            published = torch.cuda.Event()
+            published.record()
+            recv = torch.empty(world * cap, ROW_FLOATS, **f32)
+            dist.all_to_all_single(recv, rows, group=group)
+            binning, out = ops.bin_and_blend_rows(MODE_GSPLAT, W, H, recv, bg, True)
+            published.synchronize()                           # long past: the blend has been enqueued behind it
+            gmax = int(gmax_host[0])
+            ops._host_counts_pool.append(gmax_host)
+            if gmax <= cap:                                   # same verdict on every rank: gmax is global
+                _EXCHANGE_CAP[key] = int(gmax * EXCHANGE_SLACK) + 1024
+                result = (None, recv, binning, out)
+                ctx.fixed_cap = cap
+            del rows
+        if result is None:
+            ctx.fixed_cap = 0
+            result = exact()
+        counts, recv, binning, (image, final_T, n_contrib) = result
+        del xy, depth, conic, comp, rgb, opac
         ctx.cam_views, ctx.group, ctx.n = cam_views, group, n
-        ctx.counts = (send_counts, recv_counts)
+        ctx.counts = counts
         ctx.aa = bool(anti_aliased)
         ctx.hw = (H, W)
         ctx.binning = binning
         ctx.opac_shape = tuple(opac_logits.shape)
-        ctx.save_for_backward(means, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, recv, final_T, n_contrib, radii, clamped, offsets)
+        ctx.save_for_backward(means, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, recv, final_T, n_contrib, radii, clamped, row_index)
         return image
 
     @staticmethod
@@ -190,15 +279,19 @@ class _ShardedRasterize(torch.autograd.Function):
         n = ctx.n
         st = ops._stream()
         H, W = ctx.hw
-        send_counts, recv_counts = ctx.counts
         v_image = v_image.contiguous()
         v_recv = torch.zeros_like(recv)
         with ops._stage("blend_bwd"):
             check(L.b200gs_blend_bwd_rows(MODE_GSPLAT, W, H, ptr(ctx.binning.tile_ranges), ptr(ctx.binning.sorted_ids), ptr(recv), ptr(bg),
                                           ptr(final_T), ptr(n_contrib), ptr(v_image), 3, 1, None, ptr(v_recv), st), "b200gs_blend_bwd_rows")
-        v_send = torch.empty(max(sum(send_counts), 1), ROW_FLOATS, dtype=torch.float32, device=dev)
-        dist.all_to_all_single(v_send[:sum(send_counts)], v_recv, output_split_sizes=send_counts, input_split_sizes=recv_counts,
-                               group=ctx.group)
+        if ctx.fixed_cap:
+            v_send = torch.empty_like(v_recv)
+            dist.all_to_all_single(v_send, v_recv, group=ctx.group)
+        else:
+            send_counts, recv_counts = ctx.counts
+            v_send = torch.empty(max(sum(send_counts), 1), ROW_FLOATS, dtype=torch.float32, device=dev)
+            dist.all_to_all_single(v_send[:sum(send_counts)], v_recv, output_split_sizes=send_counts, input_split_sizes=recv_counts,
+                                   group=ctx.group)
         f32 = dict(dtype=torch.float32, device=dev)
         v_means, v_ls, v_q = torch.empty(n, 3, **f32), torch.empty(n, 3, **f32), torch.empty(n, 4, **f32)
         v_ol, v_dc, v_rest = torch.empty(n, **f32), torch.empty_like(shs_dc), torch.empty_like(shs_rest)
@@ -249,14 +342,12 @@ class B200DistributedRenderer(torch.nn.Module):
         world = dist.get_world_size(self.group)
         rank = dist.get_rank(self.group)
         dev = bg_color.device
-        gathered = torch.empty(world * VIEW_FLOATS, dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(gathered, pack_view(viewpoint_camera), group=self.group)
-        flat = gathered.reshape(world, VIEW_FLOATS).cpu()
+        flat = gather_views_host(viewpoint_camera, self.group)
         cams = [GatheredView(flat[j], dev) for j in range(world)]
         views = []
         for gv in cams:
             v = ops.make_view(MODE_GSPLAT, gv.width, gv.height, fx=gv.fx, fy=gv.fy, cx=gv.cx, cy=gv.cy, viewmatrix=gv.world_to_camera,
-                              campos=gv.camera_center, scale_modifier=scaling_modifier)
+                              campos=gv.camera_center_host, scale_modifier=scaling_modifier)
             views.append(v)
         # the per-camera mean2D gradients (what the distributed density controller reads) are appended to this list by backward
         xy_grads: Optional[List[torch.Tensor]] = [] if self.want_xy_grads else None
@@ -282,10 +373,7 @@ class B200DistributedRenderer(torch.nn.Module):
         dev = bg_color.device
 
         # 1. every rank learns all W cameras
-        mine = pack_view(viewpoint_camera)
-        gathered = torch.empty(world * VIEW_FLOATS, dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(gathered, mine, group=self.group)
-        flat = gathered.reshape(world, VIEW_FLOATS).cpu()
+        flat = gather_views_host(viewpoint_camera, self.group)
         views = [GatheredView(flat[j], dev) for j in range(world)]
 
         # 2. project my shard to every camera, colours for every camera

@@ -167,6 +167,11 @@ B200GS_API int b200gs_bin_sort(int32_t mode, int32_t width, int32_t height, int6
                     int64_t* d_counts, const void* workspace_a, void* workspace_b, size_t workspace_b_bytes, int32_t* sorted_ids,
                     int32_t* tile_ranges, int64_t* host_counts, int32_t sync_host, void* stream);
 
+/* b200gs_publish_i64: deliver n device int64 counters to host memory in stream order, the way the binning phases do
+ *     (kernel with system-scope stores for pinned/mapped memory, cudaMemcpyAsync for pageable): for callers that run their
+ *     own sync-free capacity protocol (the sharded renderer's row exchange). */
+B200GS_API int b200gs_publish_i64(const int64_t* d_values, int64_t* host_values, int32_t n, void* stream);
+
 /* ---- K6: blend forward ---------------------------------------------------------------------------------------------
  * replaces dgr renderCUDA fwd / gsplat rasterize_to_pixels fwd.  channels in {1,2,3,4}.
  * in : xy[n,2] conic[n,3] opacity[n] colors[n,channels]; bg[channels] or NULL.
@@ -194,8 +199,12 @@ B200GS_API int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int
  * replaces the packing / splitting around the reference's all-to-all of projected splats
  * (internal/renderers/gsplat_distributed_renderer.py:127-217): one fp32 row per VISIBLE Gaussian,
  *   col 0-1 xy | 2 depth | 3-5 conic | 6 compensation | 7 opacity | 8-10 rgb | 11 radius (int32 bit pattern).
- * b200gs_pack_rows: compacts the visible (radii > 0) entries of K1's outputs into rows, in index order; offsets[n] (int32,
- *     exclusive scan of the visibility flags) is kept for the backward; d_count <- number of rows.
+ * b200gs_pack_rows: compacts the visible (radii > 0) entries of K1's outputs into rows, in index order; row_index[n] (int32)
+ *     = the row of entry i, kept for the backward.  segment_cap == 0: one dense block, d_count[0] <- number of rows.
+ *     segment_cap > 0: entries [j*segment_len, (j+1)*segment_len) (one camera = one destination rank) fill the fixed-size
+ *     block rows[j*segment_cap, (j+1)*segment_cap) — the all-to-all then needs no size exchange (no host sync); unused
+ *     rows are zero (radius 0: ignored by the binning that reads them in place); entries that do not fit are DROPPED
+ *     (row_index -1) and d_count[j] <- visible entries of segment j, for the caller to compare with segment_cap.
  * b200gs_unpack_rows_grad: the backward of that gather: full-length per-Gaussian cotangents for b200gs_project_bwd*
  *     (zeros for culled Gaussians).
  * b200gs_bin_count_rows (then b200gs_bin_sort) / blend_fwd_rows / blend_bwd_rows: K2-K7 reading the rows IN PLACE (strided
@@ -218,9 +227,9 @@ B200GS_API int b200gs_project_bwd_rows(const B200gsView* view, int64_t n, const 
                                        const float* v_rows, int32_t accumulate, float* v_means, float* v_log_scales, float* v_raw_quats,
                                        float* v_opacity_logits, float* v_shs_dc, float* v_shs_rest, void* stream);
 B200GS_API size_t b200gs_pack_rows_workspace_bytes(int64_t n);
-B200GS_API int b200gs_pack_rows(int64_t n, const float* xy, const float* depth, const float* conic, const float* comp,
-                                const float* opacity, const float* rgb, const int32_t* radii, void* workspace, size_t workspace_bytes,
-                                int32_t* offsets, float* rows, int64_t* d_count, void* stream);
+B200GS_API int b200gs_pack_rows(int64_t n, int64_t segment_len, int64_t segment_cap, const float* xy, const float* depth,
+                                const float* conic, const float* comp, const float* opacity, const float* rgb, const int32_t* radii,
+                                void* workspace, size_t workspace_bytes, int32_t* row_index, float* rows, int64_t* d_count, void* stream);
 B200GS_API int b200gs_unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offsets, const float* v_rows, float* v_xy,
                                        float* v_depth, float* v_conic, float* v_comp, float* v_opacity, float* v_rgb, void* stream);
 B200GS_API int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull,

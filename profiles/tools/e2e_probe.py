@@ -19,7 +19,10 @@ consumed = [torch.cuda.Event(), torch.cuda.Event()]
 loss_hosts = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
 loss_done = [torch.cuda.Event(), torch.cuda.Event()]
 
-def run(k, h2d, d2h, lag_sync, fine_dep):
+fwd_done = torch.cuda.Event()
+
+
+def run(k, h2d, d2h, lag_sync, fine_dep, late=False):
     def prefetch(i):
         if fine_dep:
             copy_stream.wait_event(consumed[i & 1])
@@ -36,6 +39,12 @@ def run(k, h2d, d2h, lag_sync, fine_dep):
         else:
             c = cot
         out = renderer(cams[i % len(cams)], model, bg)
+        if h2d and late and i + 1 < k:      # upload the next image while THIS step's backward runs (compute-bound kernels)
+            fwd_done.record()
+            copy_stream.wait_event(fwd_done)
+            with torch.cuda.stream(copy_stream):
+                in_bufs[(i + 1) & 1].copy_(cot_host, non_blocking=True)
+                in_ready[(i + 1) & 1].record(copy_stream)
         loss = (out["render"] * c).sum()
         loss.backward()
         consumed[i & 1].record()
@@ -48,7 +57,7 @@ def run(k, h2d, d2h, lag_sync, fine_dep):
     e0.record()
     if h2d: prefetch(0)
     for i in range(k):
-        if h2d and i + 1 < k: prefetch(i + 1)
+        if h2d and not late and i + 1 < k: prefetch(i + 1)
         step(i)
         if lag_sync and i > 0: loss_done[(i - 1) & 1].synchronize()
     e1.record(); torch.cuda.synchronize()
@@ -57,5 +66,6 @@ def run(k, h2d, d2h, lag_sync, fine_dep):
 for i in range(3): run(16, False, False, False, False)
 for name, cfg in [("resident", (False, False, False, False)), ("resident+lagsync", (False, False, True, False)), ("d2h+lagsync", (False, True, True, False)),
                   ("h2d", (True, False, False, False)), ("h2d fine dep", (True, False, False, True)), ("full e2e", (True, True, True, False)),
-                  ("full e2e fine dep", (True, True, True, True)), ("resident again", (False, False, False, False))]:
+                  ("full e2e fine dep", (True, True, True, True)), ("full e2e late upload", (True, True, True, False, True)),
+                  ("h2d late upload", (True, False, False, False, True)), ("resident again", (False, False, False, False))]:
     print(f"{name:22s} {run(64, *cfg):.4f} ms/step")

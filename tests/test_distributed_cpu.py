@@ -58,6 +58,17 @@ def _worker(rank, world, port, q):
             exp = rows_src[start:start + cnts[rank]]
             assert torch.equal(got.detach()[off:off + cnts[rank]].view(torch.int32), exp.view(torch.int32))  # bit-exact incl. radius bits
             off += cnts[rank]
+        # host-side camera exchange (gloo): every rank ends up with every rank's camera, in rank order, without device tensors
+        from b200gs.distributed import VIEW_FLOATS, GatheredView, gather_views_host
+        from b200gs.scene import make_ring_cameras
+        cams = make_ring_cameras(64, 48)
+        flat = gather_views_host(cams[3 + rank])
+        assert flat.shape == (world, VIEW_FLOATS) and flat.device.type == "cpu"
+        for src in range(world):
+            gv = GatheredView(flat[src], "cpu")
+            ref = cams[3 + src]
+            assert (gv.width, gv.height) == (64, 48) and abs(gv.fx - float(ref.fx)) < 1e-4
+            assert torch.equal(gv.world_to_camera, ref.world_to_camera.float()) and torch.equal(gv.camera_center_host, ref.camera_center.float())
         # sharding
         tot = 0
         for r in range(world):

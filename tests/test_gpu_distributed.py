@@ -60,6 +60,34 @@ def _worker(rank, world, port, q):
                 assert err < 1e-4, (fused, k, err)
             if fused:
                 assert len(out["viewspace_points_grads"]) == world and out["viewspace_points_grads"][0].shape == (hi - lo, 2)
+                # The first step used the exact (synchronising) exchange; the following ones the sync-free fixed-size blocks
+                # sized from the previous step.  Different poses per step; then a capacity that is far too small (every rank
+                # must fall back to the exact exchange together); results stay bit-identical to the single-GPU render.
+                import b200gs.distributed as D
+                renderer = B200DistributedRenderer(fused=True).to(dev)
+                for step, cap in enumerate([None, None, 64, None]):
+                    if cap is not None:
+                        assert len(D._EXCHANGE_CAP) > 0
+                        for key in list(D._EXCHANGE_CAP):
+                            D._EXCHANGE_CAP[key] = cap
+                    pose = [3 * j + 1 + step for j in range(world)]
+                    with torch.no_grad():
+                        want = single(cams[pose[rank]].to_device(dev), full, bg)["render"]
+                    for p in shard.gaussians.values():
+                        p.grad = None
+                    got = renderer(cams[pose[rank]].to_device(dev), shard, bg)
+                    assert torch.equal(got["render"].detach(), want), (step, float((got["render"].detach() - want).abs().max()))
+                    (got["render"] * cots[rank]).sum().backward()
+                    assert all(bool(torch.isfinite(p.grad).all()) for p in shard.gaussians.values())
+                    if step == 1:      # gradients of a sync-free step against the single-GPU gradients of the summed loss
+                        for p in full.gaussians.values():
+                            p.grad = None
+                        sum((single(cams[pose[j]].to_device(dev), full, bg)["render"] * cots[j]).sum() for j in range(world)).backward()
+                        for k, p in shard.gaussians.items():
+                            ref = full.gaussians[k].grad[lo:hi]
+                            err = float((p.grad - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+                            assert err < 1e-4, ("sync-free", k, err)
+                    assert all(v > 64 for v in D._EXCHANGE_CAP.values())
             else:
                 assert len(out["projection_results_list"]) == world and sum(out["n_received"]) > 0
         q.put((rank, "ok"))

@@ -133,8 +133,42 @@ def test_binning_exact(mode, n, W, H, seed, pose, ms):
     assert torch.equal(b.tile_ranges.cpu().long(), ranges)
 
 
+# Shapes that drive the hierarchical binning off its common path: huge splats (rects of many coarse cells -> long (rank,row)
+# item lists in the emit kernel; 256-entry chunks whose output exceeds the shared-memory staging buffer -> direct-write
+# path of the scatter kernel) and an image with more than 256 coarse cells (two radix passes over the cell keys).
+STRESS = [(1500, 512, 384, 7, 1, 1.0), (2500, 2304, 2304, 9, 4, 0.06)]
+
+
 @pytest.mark.parametrize("mode", [O.MODE_VANILLA, O.MODE_GSPLAT])
-@pytest.mark.parametrize("n,W,H,seed,pose,ms", CASES[:3])
+@pytest.mark.parametrize("n,W,H,seed,pose,ms", STRESS)
+def test_binning_exact_stress(mode, n, W, H, seed, pose, ms):
+    from b200gs import ops
+    ref, colors, op, sids, ranges = _projected_inputs(mode, n, W, H, seed, pose, ms)
+    dxy, ddep, drad, dcon, dop = (t.detach().to(DEV).contiguous() for t in (ref["xy"], ref["depth"], ref["radii"], ref["conic"], op))
+    full = ops.bin_gaussians(mode, W, H, dxy, ddep, drad)
+    assert full.total == int(ref["tiles"].sum()) == full.rect_pairs
+    assert torch.equal(full.sorted_ids[:full.total].cpu(), sids)
+    assert torch.equal(full.tile_ranges.cpu().long(), ranges)
+    cul = ops.bin_gaussians(mode, W, H, dxy, ddep, drad, dcon, dop)
+    assert 0 < cul.total <= full.total and cul.rect_pairs == full.rect_pairs and cul.coarse_pairs == full.coarse_pairs
+    # every tile's culled list is an order-preserving subsequence of the full list
+    fr, cr = full.tile_ranges.cpu().tolist(), cul.tile_ranges.cpu().tolist()
+    fi, ci = full.sorted_ids.cpu().tolist(), cul.sorted_ids.cpu().tolist()
+    for (fs, fe), (cs, ce) in zip(fr, cr):
+        it = iter(fi[fs:fe])
+        assert all(any(x == y for y in it) for x in ci[cs:ce])
+    # the capacity protocol: too small a buffer must be reported, never overrun
+    ops._last_total[(mode, W, H, dxy.shape[0], True)] = (max(1, cul.coarse_pairs // 2), max(1, cul.rect_pairs // 2))
+    lazy = ops.bin_gaussians(mode, W, H, dxy, ddep, drad, dcon, dop, lazy=True)
+    assert lazy.resolve() is False
+    ops._last_total[(mode, W, H, dxy.shape[0], True)] = (cul.coarse_pairs, cul.rect_pairs)
+    lazy = ops.bin_gaussians(mode, W, H, dxy, ddep, drad, dcon, dop, lazy=True)
+    assert lazy.resolve() is True and lazy.total == cul.total
+    assert torch.equal(lazy.sorted_ids[:lazy.total], cul.sorted_ids[:cul.total]) and torch.equal(lazy.tile_ranges, cul.tile_ranges)
+
+
+@pytest.mark.parametrize("mode", [O.MODE_VANILLA, O.MODE_GSPLAT])
+@pytest.mark.parametrize("n,W,H,seed,pose,ms", CASES[:3] + STRESS[:1])
 def test_tile_culling_is_exact(mode, n, W, H, seed, pose, ms):
     """Exact tile culling drops only pairs no pixel of the tile would have used: per tile the culled list is an
     order-preserving subsequence of the reference list, and the blended image / saved state are BIT-identical."""
