@@ -223,7 +223,7 @@ def algorithmic_bytes(stage, N, V, I, P, n_tiles, C=None):
     }.get(stage, 0)
 
 
-LAUNCHES_PER_STEP = {"project_fwd": 1, "bin_count": 1 + 1 + 6 + 2, "bin_sort": 1 + 1 + 1 + 3 + 1 + 1 + 1 + 1 + 1, "blend_fwd": 1, "blend_bwd": 1, "project_bwd": 1}
+LAUNCHES_PER_STEP = {"project_fwd": 1, "bin_count": 1 + 1 + 6 + 2 + 1, "bin_sort": 1 + 3 + 1 + 1 + 1 + 1 + 1 + 1, "blend_fwd": 1, "blend_bwd": 1, "project_bwd": 1}
 
 
 def main():
