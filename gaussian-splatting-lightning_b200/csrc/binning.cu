@@ -5,14 +5,16 @@
 // major, then depth bits, ties in Gaussian-id order — is produced here hierarchically, and the fine pairs are written
 // exactly once, already in place:
 //   A. depth keys (32-bit float bits; off-screen -> 0xFFFFFFFF), stable radix sort of the N keys, scan of the
-//      per-Gaussian COARSE cell counts in depth order (a coarse cell = 8x8 tiles = 128x128 px)
-//   B. emit (coarse cell, Gaussian) pairs in depth order and stable-partition them by cell: ONE 8-bit radix pass over
-//      ~2.5 pairs per visible Gaussian for every image up to 2048x2048 (<= 256 cells)
-//   C. per 256-entry chunk of a cell's list: the exact 64-bit mask of the cell's tiles each splat can reach (row spans
-//      of the alpha >= 1/255 ellipse, or the plain 3-sigma rect with culling off) and the chunk's per-tile counts
+//      per-Gaussian COARSE cell counts in depth order (a coarse cell = 8x8 tiles = 128x128 px); a 32-byte record per
+//      Gaussian (one L2 sector) holds everything phase B needs
+//   B. emit (coarse cell, {64-bit tile mask, id}) pairs in depth order — the mask = which of the cell's 64 tiles the splat
+//      can reach (row spans of the alpha >= 1/255 ellipse, or the plain 3-sigma rect with culling off) — and
+//      stable-partition them by cell: ONE 8-bit radix pass over ~2 pairs per visible Gaussian for every image up to
+//      2048x2048 (<= 256 cells)
+//   C. per 256-entry chunk of a cell's list: per-tile counts (warp bit-matrix transpose + popcount)
 //   D. per cell: prefix of the chunk counts; one scan over the tiles -> tile_ranges and the pair total
 //   E. every chunk writes its splat ids to sorted_ids at (tile start + chunk prefix + rank inside the chunk), ranks
-//      from warp ballots in list order
+//      from the transposed bit sets in list order, staged so that every run is one coalesced store
 // A stable multi-split keeps the depth order inside every tile, so the result equals the oracle's torch.sort(stable)
 // of the 64-bit keys element for element (tests/test_gpu_parity.py::test_binning_exact).
 //
@@ -223,23 +225,6 @@ __device__ __forceinline__ bool row_span(const CullE& e, int ty, int x0, int x1,
     b = min(x1, (int)fminf(fb, 1.0e9f) + 1);
     if (a >= b) { b = a; return false; }
     return true;
-}
-
-// the tiles of coarse cell (cx, cy) a splat with tile rect [x0,x1) x [y0,y1) can reach, bit (ty_local * 8 + tx_local)
-template <bool GSPLAT>
-__device__ __forceinline__ uint64_t cell_tile_mask(const CullE& e, int x0, int y0, int x1, int y1, int cx, int cy) {
-    if (e.mode == 2) return 0;
-    const int wx0 = cx << SUPER_SHIFT, wy0 = cy << SUPER_SHIFT;
-    x0 = max(x0, wx0); x1 = min(x1, wx0 + SUPER);
-    y0 = max(y0, wy0); y1 = min(y1, wy0 + SUPER);
-    uint64_t mask = 0;
-    for (int ty = y0; ty < y1; ++ty) {
-        int a, b;
-        if (!row_span<GSPLAT>(e, ty, x0, x1, a, b)) continue;   // clipping the span to the window == intersecting it
-        const uint64_t bits = ((1ull << (b - a)) - 1ull) << (a - wx0);
-        mask |= bits << ((ty - wy0) * SUPER);
-    }
-    return mask;
 }
 
 // tile rect -> rect of coarse cells
