@@ -249,7 +249,11 @@ __device__ __forceinline__ float reduce_scatter<4>(const float* p, unsigned lane
     return s;
 }
 
-template <int CH, bool GSPLAT, bool ABS, int RB>
+// VS ("value scatter", experimental, opt-in with B200GS_BWD_VS=1, CH == 3, RB == 4, no absgrad): after the two entry-splitting
+// steps of the reduce-scatter the nine totals of an entry are reduced over the remaining 8 lanes with a reduce-scatter over
+// the VALUES (5 + 3 + 3 shuffles instead of 27), so each of the 8 lanes ends up owning one total (lane 0 of the group owns
+// the coupled pair sum(vs dx), sum(vs dy)) and issues its own atomic: two lane-parallel REDs instead of nine serial ones.
+template <int CH, bool GSPLAT, bool ABS, int RB, bool VS = false>
 __global__ void __launch_bounds__(BLOCK_PIX, (RB == 4 && !ABS) ? 4 : 1) blend_bwd_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
                                                               const int32_t* __restrict__ ids, const SplatStrides st, const float* __restrict__ xy,
                                                               const float* __restrict__ conic, const float* __restrict__ opacity,
@@ -264,6 +268,7 @@ __global__ void __launch_bounds__(BLOCK_PIX, (RB == 4 && !ABS) ? 4 : 1) blend_bw
     // go = dL/dopacity) — the conic/mean gradients are linear in them, so the writer lane finishes the products once per
     // splat instead of every lane per sample — plus the colour sums, plus |grad xy| when the absgrad side channel is on.
     constexpr int NT = 6 + CH + (ABS ? 2 : 0);
+    static_assert(!VS || (CH == 3 && RB == 4 && !ABS), "value-scatter variant: 3 channels, RB 4, no absgrad");
     __shared__ float4 s_rec[(BLOCK_PIX + 1) * 3];
     __shared__ unsigned char s_mask[BLOCK_PIX];
     __shared__ unsigned short s_list[NWARP][BLOCK_PIX + 2 * LIST_PAD];
@@ -272,6 +277,22 @@ __global__ void __launch_bounds__(BLOCK_PIX, (RB == 4 && !ABS) ? 4 : 1) blend_bw
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const unsigned lane = tid & 31u;
+    // VS: which total lane (lane & 7) of an 8-lane group owns, and where it goes
+    float* vs_base = nullptr;
+    int vs_stride = 0;
+    float vs_scale = 1.0f;
+    if (VS) {
+        switch (lane & 7u) {
+            case 0: vs_base = v_xy; vs_stride = st.xs; vs_scale = sx; break;              // + the y component, see the writer
+            case 1: vs_base = v_opacity; vs_stride = st.os; break;
+            case 2: vs_base = v_conic; vs_stride = st.cs; vs_scale = 0.5f; break;
+            case 3: vs_base = v_conic + 1; vs_stride = st.cs; break;
+            case 4: vs_base = v_conic + 2; vs_stride = st.cs; vs_scale = 0.5f; break;
+            case 5: vs_base = v_colors; vs_stride = st.ks; break;
+            case 6: vs_base = v_colors + 1; vs_stride = st.ks; break;
+            default: vs_base = v_colors + 2; vs_stride = st.ks; break;
+        }
+    }
     const int tile = blockIdx.y * grid_x + blockIdx.x;
     int lx, ly;
     pixel_of_thread(tid, lx, ly);
@@ -382,6 +403,39 @@ __global__ void __launch_bounds__(BLOCK_PIX, (RB == 4 && !ABS) ? 4 : 1) blend_bw
                 }
             }
             if (present == 0u) continue;
+            if (VS) {
+                const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+                float sv[NT];      // entry split: this lane's entry (slot my_slot), summed over the lanes that differ in bits 16 and 8
+#pragma unroll
+                for (int k = 0; k < NT; ++k)
+                    sv[k] = rs_step(rs_step(part[k][0], part[k][2], b16, 16), rs_step(part[k][1], part[k][3], b16, 16), b8, 8);
+                // value split over the 8 lanes of the group.  sv: 0 go, 1 t1, 2 t2, 3..5 conic moments, 6..8 colours
+                const float r0 = rs_step(sv[1], sv[5], b4, 4), r1 = rs_step(sv[2], sv[6], b4, 4);
+                const float r3 = rs_step(sv[3], sv[7], b4, 4), r4 = rs_step(sv[4], sv[8], b4, 4);
+                const float r2 = sv[0] + __shfl_xor_sync(FULL, sv[0], 4);
+                const float u0 = rs_step(r0, r3, b2, 2), u1 = rs_step(r1, r4, b2, 2);
+                const float u2 = r2 + __shfl_xor_sync(FULL, r2, 2);
+                const float w = rs_step(u0, u1, b1, 1);                     // lane&7: 0 t1, 2 m3, 3 m4, 4 m5, 5 c0, 6 c1, 7 c2
+                const float t2tot = u1 + __shfl_xor_sync(FULL, u1, 1);      // valid on lanes 0/1 of the group
+                const float gotot = u2 + __shfl_xor_sync(FULL, u2, 1);      // valid on lanes 0/1 of the group
+                if ((present >> my_slot) & 1u) {
+                    const int j = my_list[ii - my_slot];
+                    const int g = __float_as_int(s_rec[j * 3 + 2].z);
+                    const unsigned l8 = lane & 7u;
+                    float outv = vs_scale * (l8 == 1u ? gotot : w);
+                    float outy = 0.f;
+                    if (l8 == 0u) {
+                        const float4 r0c = s_rec[j * 3 + 0];
+                        const float A = r0c.z * (-2.0f / LOG2E), B = r0c.w * (-1.0f / LOG2E), Cc = s_rec[j * 3 + 1].x * (-2.0f / LOG2E);
+                        outv = (A * w + B * t2tot) * sx;
+                        outy = (B * w + Cc * t2tot) * sy;
+                    }
+                    float* dst = vs_base + int64_t(g) * vs_stride;
+                    atomicAdd(dst, outv);
+                    if (l8 == 0u) atomicAdd(dst + 1, outy);
+                }
+                continue;
+            }
             float tot[NT];
 #pragma unroll
             for (int k = 0; k < NT; ++k) tot[k] = reduce_scatter<RB>(part[k], lane);
@@ -683,6 +737,19 @@ int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
     // splits, the lane->fragment staging and the writer algebra cost as many issue slots as the butterfly saves (677 M vs
     // ~620 M warp instructions, ncu), so the shuffle kernel stays the default.
     static const bool use_mma = []() { const char* e = getenv("B200GS_BWD_MMA"); return e && e[0] == '1'; }();
+    // opt-in (B200GS_BWD_VS=1): value-scatter reduction, see blend_bwd_kernel.  Written from the ncu instruction breakdown of
+    // the default kernel at the end of round 1; NOT yet run on hardware — the default path does not use it.
+    static const bool use_vs = []() { const char* e = getenv("B200GS_BWD_VS"); return e && e[0] == '1'; }();
+    if (CH == 3 && RB == 4 && use_vs && !v_xy_abs) {
+        if constexpr (CH == 3 && RB == 4) {
+            if (mode == B200GS_MODE_GSPLAT)
+                blend_bwd_kernel<CH, true, false, RB, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
+            else
+                blend_bwd_kernel<CH, false, false, RB, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
+            B200GS_LAUNCH_CHECK();
+            return B200GS_OK;
+        }
+    }
     if (mode == B200GS_MODE_GSPLAT) {
         if (v_xy_abs)
             blend_bwd_kernel<CH, true, true, RB><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
