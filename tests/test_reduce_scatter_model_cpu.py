@@ -58,3 +58,18 @@ def test_value_scatter_variant():
             assert np.isclose(w[lane], tot[owner_value[l8], u])
         if l8 == 0:
             assert np.isclose(t2[lane], tot[2, u])                 # the coupled pair lives on one lane
+
+
+def test_bit_matrix_transpose32():
+    """csrc/binning.cu: transpose32 — five xor-shuffle stages; lane t must end with bit l = bit t of lane l's input."""
+    rng = np.random.default_rng(2)
+    x = rng.integers(0, 2 ** 32, size=32, dtype=np.uint64).astype(np.uint32)
+    orig = x.copy()
+    for j, m in ((16, 0x0000FFFF), (8, 0x00FF00FF), (4, 0x0F0F0F0F), (2, 0x33333333), (1, 0x55555555)):
+        m = np.uint32(m)
+        y = x[LANES ^ j]
+        hi = (LANES & j) != 0
+        x = np.where(hi, (x & ~m) | ((y >> np.uint32(j)) & m), (x & m) | ((y << np.uint32(j)) & ~m)).astype(np.uint32)
+    for t in range(32):
+        for l in range(32):
+            assert ((int(x[t]) >> l) & 1) == ((int(orig[l]) >> t) & 1)
