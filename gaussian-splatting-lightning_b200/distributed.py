@@ -130,10 +130,11 @@ def _host_group(group):
     return g
 
 
-def gather_views_host(camera, group=None) -> torch.Tensor:
-    """[world, VIEW_FLOATS] CPU tensor with every rank's camera, no device synchronisation."""
+def gather_views_host(camera, group=None, cache: bool = True) -> torch.Tensor:
+    """[world, VIEW_FLOATS] CPU tensor with every rank's camera, no device synchronisation (cache=False re-reads the camera's
+    device tensors every call — one sync — for cameras whose pose is being optimised)."""
     world = dist.get_world_size(group)
-    mine = pack_view_host(camera)
+    mine = pack_view_host(camera, cache)
     out = torch.empty(world * VIEW_FLOATS, dtype=torch.float32)
     dist.all_gather_into_tensor(out, mine.contiguous(), group=_host_group(group))
     return out.reshape(world, VIEW_FLOATS)
@@ -326,7 +327,8 @@ class B200DistributedRenderer(torch.nn.Module):
     shard; returns this rank's image plus the per-camera projection results the distributed density controller reads
     (``distributed_vanilla_density_controller.py:16-47``)."""
 
-    def __init__(self, anti_aliased: bool = True, group=None, fused: bool = True, want_xy_grads: bool = False):
+    def __init__(self, anti_aliased: bool = True, group=None, fused: bool = True, want_xy_grads: bool = False,
+                 cache_cameras: bool = True):
         """fused: when `pc` is the vanilla Gaussian model, run the whole step as one autograd node on the raw parameters
         (_ShardedRasterize: device-side packing, rows consumed in place, one host sync); otherwise the generic path
         below, built from the same ops the single-GPU renderers use."""
@@ -335,6 +337,7 @@ class B200DistributedRenderer(torch.nn.Module):
         self.group = group
         self.fused = fused
         self.want_xy_grads = want_xy_grads   # fused path: also materialise per-camera dL/d(mean2D) for the density controller
+        self.cache_cameras = cache_cameras   # False when camera poses are optimised (the packed host view is cached on the camera)
 
     def _forward_fused(self, raw, viewpoint_camera, pc, bg_color, scaling_modifier):
         from . import ops
@@ -342,7 +345,7 @@ class B200DistributedRenderer(torch.nn.Module):
         world = dist.get_world_size(self.group)
         rank = dist.get_rank(self.group)
         dev = bg_color.device
-        flat = gather_views_host(viewpoint_camera, self.group)
+        flat = gather_views_host(viewpoint_camera, self.group, self.cache_cameras)
         cams = [GatheredView(flat[j], dev) for j in range(world)]
         views = []
         for gv in cams:
@@ -373,7 +376,7 @@ class B200DistributedRenderer(torch.nn.Module):
         dev = bg_color.device
 
         # 1. every rank learns all W cameras
-        flat = gather_views_host(viewpoint_camera, self.group)
+        flat = gather_views_host(viewpoint_camera, self.group, self.cache_cameras)
         views = [GatheredView(flat[j], dev) for j in range(world)]
 
         # 2. project my shard to every camera, colours for every camera
