@@ -47,6 +47,9 @@ _SIGNATURES = {
     "b200gs_bin_sort_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32]),
     "b200gs_bin_count": (c_int32, [c_int32, c_int32, c_int32, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P, _P, c_int32, _P]),
     "b200gs_bin_sort": (c_int32, [c_int32, c_int32, c_int32, c_int64, c_int32, c_int64, c_int64, _P, _P, _P, c_size_t, _P, _P, _P, c_int32, _P]),
+    "b200gs_loss_blocks": (c_int64, [c_int32, c_int32, c_int32]),
+    "b200gs_loss_fwd": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
+    "b200gs_loss_bwd": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, ctypes.c_float, _P, _P, _P]),
     "b200gs_publish_i64": (c_int32, [_P, _P, c_int32, _P]),
     "b200gs_blend_fwd": (c_int32, [c_int32] * 4 + [_P] * 7 + [_P, c_int64, c_int64, _P, _P, _P, _P]),
     "b200gs_blend_bwd": (c_int32, [c_int32] * 4 + [_P] * 7 + [_P, _P, _P, c_int64, c_int64, _P, c_float, c_float]

@@ -206,6 +206,26 @@ int b200gs_publish_i64(const int64_t* d_values, int64_t* host_values, int32_t n,
     return publish_i64(d_values, host_values, n, (cudaStream_t)stream);
 }
 
+// ---- fused L1 + SSIM loss (experimental) ----------------------------------------------------------------------------------
+int64_t b200gs_loss_blocks(int32_t channels, int32_t width, int32_t height) {
+    if (channels <= 0 || width <= 0 || height <= 0) return 0;
+    return loss_blocks(channels, width, height);
+}
+
+int b200gs_loss_fwd(int32_t channels, int32_t width, int32_t height, const float* image, const float* target, float* dmaps,
+                    float* partials, void* stream) {
+    B200GS_CHECK_ARG(channels > 0 && width > 0 && height > 0, "bad size");
+    B200GS_CHECK_ARG(image && target && dmaps && partials, "NULL pointer");
+    return launch_loss_fwd(channels, width, height, image, target, dmaps, partials, (cudaStream_t)stream);
+}
+
+int b200gs_loss_bwd(int32_t channels, int32_t width, int32_t height, const float* image, const float* target, const float* dmaps,
+                    float lambda_dssim, const float* v_loss, float* v_image, void* stream) {
+    B200GS_CHECK_ARG(channels > 0 && width > 0 && height > 0, "bad size");
+    B200GS_CHECK_ARG(image && target && dmaps && v_image, "NULL pointer");
+    return launch_loss_bwd(channels, width, height, image, target, dmaps, lambda_dssim, v_loss, v_image, (cudaStream_t)stream);
+}
+
 // ---- [n,12] row layout (the exchange format of the Gaussian-sharded renderer) -------------------------------------------
 size_t b200gs_pack_rows_workspace_bytes(int64_t n) { return n < 0 ? 0 : pack_rows_workspace_bytes(n); }
 

@@ -107,6 +107,11 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
              const void* ws_a, void* ws_b, size_t ws_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges, int64_t* host_counts,
              int sync_host, cudaStream_t s);
 
+int64_t loss_blocks(int channels, int width, int height);
+int launch_loss_fwd(int channels, int width, int height, const float* img, const float* gt, float* dmaps, float* partials, cudaStream_t s);
+int launch_loss_bwd(int channels, int width, int height, const float* img, const float* gt, const float* dmaps, float lambda_dssim,
+                    const float* v_loss, float* v_img, cudaStream_t s);
+
 int launch_blend_fwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids,
                      int row_stride, const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
                      float* image, int64_t pix_stride, int64_t ch_stride, float* final_T, int32_t* n_contrib,

@@ -676,3 +676,46 @@ def rasterize_gaussians(xys, depths, radii, conics, num_tiles_hit, colors, opaci
     image, alpha = _RasterizeGaussians.apply(xys, depths, radii, conics, colors, opacity, img_height, img_width, background,
                                              return_alpha, absgrad)
     return (image, alpha) if return_alpha else image
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fused L1 + SSIM loss (EXPERIMENTAL: csrc/loss.cu compiles but has not been validated on hardware; not used by the renderers)
+# ----------------------------------------------------------------------------------------------------------------------
+class _L1SSIMLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, target, lambda_dssim):
+        L = lib()
+        image, target = _f32c(image, "image"), _f32c(target, "target")
+        if image.dim() != 3 or image.shape != target.shape:
+            raise ValueError("image and target must both be [C,H,W]")
+        C, H, W = image.shape
+        dev = image.device
+        blocks = int(L.b200gs_loss_blocks(C, W, H))
+        dmaps = torch.empty(3, C, H, W, dtype=torch.float32, device=dev)
+        partials = torch.empty(blocks, 2, dtype=torch.float32, device=dev)
+        with _stage("loss_fwd"):
+            check(L.b200gs_loss_fwd(C, W, H, ptr(image), ptr(target), ptr(dmaps), ptr(partials), _stream()), "b200gs_loss_fwd")
+        sums = partials.sum(dim=0) / float(C * H * W)                   # [mean |a-b|, mean SSIM]; fixed summation order
+        loss = (1.0 - lambda_dssim) * sums[0] + lambda_dssim * (1.0 - sums[1])
+        ctx.save_for_backward(image, target, dmaps)
+        ctx.lambda_dssim = float(lambda_dssim)
+        ctx.mark_non_differentiable(sums)
+        return loss, sums
+
+    @staticmethod
+    def backward(ctx, v_loss, _v_sums):
+        L = lib()
+        image, target, dmaps = ctx.saved_tensors
+        C, H, W = image.shape
+        v_image = torch.empty_like(image)
+        v = _f32c(v_loss.reshape(1), "grad_loss")
+        with _stage("loss_bwd"):
+            check(L.b200gs_loss_bwd(C, W, H, ptr(image), ptr(target), ptr(dmaps), ctx.lambda_dssim, ptr(v), ptr(v_image), _stream()),
+                  "b200gs_loss_bwd")
+        return v_image, None, None
+
+
+def l1_ssim_loss(image: torch.Tensor, target: torch.Tensor, lambda_dssim: float = 0.2):
+    """(1 - lambda) * L1 + lambda * (1 - SSIM) of `VanillaMetricsImpl._get_basic_metrics` (vanilla_metrics.py:57-74) in two
+    kernels; returns (loss, stats) with stats = [mean |image - target|, mean SSIM].  image/target: [C,H,W] fp32 CUDA."""
+    return _L1SSIMLoss.apply(image, target, float(lambda_dssim))

@@ -195,6 +195,18 @@ B200GS_API int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int
                      float xy_scale_x, float xy_scale_y, float* v_xy, float* v_conic, float* v_opacity,
                      float* v_colors, float* v_xy_abs, void* stream);
 
+/* ---- fused L1 + SSIM training loss on the rendered image (EXPERIMENTAL: compiles, not yet validated on hardware) ------------
+ * replaces  loss = (1-lambda) * l1_loss(image, gt) + lambda * (1 - ssim(image, gt))   (internal/metrics/vanilla_metrics.py:57-74,
+ * internal/utils/ssim.py:17-63: 11-tap Gaussian window sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2).  image/target [C,H,W].
+ * b200gs_loss_fwd: partials[b200gs_loss_blocks(...)][2] <- per-CTA sums of |image-target| and of the SSIM map (the caller sums them
+ *     and divides by C*H*W); dmaps[3][C][H][W] <- partial derivatives of the SSIM map, kept for the backward.
+ * b200gs_loss_bwd: v_image[C,H,W] <- (*v_loss or 1) * dloss/dimage. */
+B200GS_API int64_t b200gs_loss_blocks(int32_t channels, int32_t width, int32_t height);
+B200GS_API int b200gs_loss_fwd(int32_t channels, int32_t width, int32_t height, const float* image, const float* target, float* dmaps,
+                               float* partials, void* stream);
+B200GS_API int b200gs_loss_bwd(int32_t channels, int32_t width, int32_t height, const float* image, const float* target, const float* dmaps,
+                               float lambda_dssim, const float* v_loss, float* v_image, void* stream);
+
 /* ---- [n,12] splat rows: the exchange format of the Gaussian-sharded multi-GPU renderer ------------------------------
  * replaces the packing / splitting around the reference's all-to-all of projected splats
  * (internal/renderers/gsplat_distributed_renderer.py:127-217): one fp32 row per VISIBLE Gaussian,

@@ -49,3 +49,30 @@ def test_ssim_properties():
     assert abs(float(L.ssim(img, gt)) - float(L.ssim(gt, img))) < 1e-7   # symmetric
     w = L.window_1d()
     assert abs(float(w.sum()) - 1.0) < 1e-6 and w.numel() == 11 and float(w[5]) == float(w.max())
+
+
+def test_fused_kernel_formulas_match_autograd():
+    """The closed-form pieces the fused kernels (csrc/loss.cu) evaluate — the three partial-derivative maps of the SSIM map
+    w.r.t. the blurred moments mu1, E[a^2], E[ab], and  v_img = ((1-l) sign(a-b) - l (blur(d_mu1) + 2 a blur(d_e11) + b blur(d_e12))) / n
+    — restated with torch ops and compared with autograd through the oracle loss.  Pins the math of K9/K10 on CPU."""
+    g = torch.Generator().manual_seed(7)
+    gt = torch.rand(3, 45, 61, generator=g, dtype=torch.float64)
+    a = (gt + 0.15 * torch.randn(3, 45, 61, generator=g, dtype=torch.float64)).clamp(0, 1)
+    lam = 0.2
+    ar = a.clone().requires_grad_(True)
+    loss, _, _ = L.training_loss(ar, gt, lam)
+    loss.backward()
+
+    w = L.window_1d(torch.float64)
+    mu1, mu2 = L._blur(a, w), L._blur(gt, w)
+    e11, e22, e12 = L._blur(a * a, w), L._blur(gt * gt, w), L._blur(a * gt, w)
+    s1, s2, s12 = e11 - mu1 * mu1, e22 - mu2 * mu2, e12 - mu1 * mu2
+    A1, A2 = 2 * mu1 * mu2 + L.C1, 2 * s12 + L.C2
+    B1, B2 = mu1 * mu1 + mu2 * mu2 + L.C1, s1 + s2 + L.C2
+    ss = A1 * A2 / (B1 * B2)
+    d_mu1 = (2 * mu2 * A2 - 2 * mu2 * A1) / (B1 * B2) - ss * (2 * mu1 / B1 - 2 * mu1 / B2)
+    d_e11 = -ss / B2
+    d_e12 = 2 * A1 / (B1 * B2)
+    n = a.numel()
+    v_img = ((1 - lam) * torch.sign(a - gt) - lam * (L._blur(d_mu1, w) + 2 * a * L._blur(d_e11, w) + gt * L._blur(d_e12, w))) / n
+    assert float((v_img - ar.grad).abs().max() / ar.grad.abs().max()) < 1e-9
