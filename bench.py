@@ -4,9 +4,15 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200gs|reference] [--mode vanilla|gsplat]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload = BASELINE.json configs[1] shape ("Mip-NeRF360 garden, 1920x1080, ~1M Gaussians, SH deg 3, fwd+bwd") with the
-deterministic synthetic scene of SURVEY.md §8(d): G(1 000 000, seed 0) in [-1.3,1.3]^3, 32-pose camera ring, one
-camera per step (a fresh pose every step: 236 MB of parameters + ~180 MB of per-view buffers > L2, no L2 flush needed).
+Workloads are the BASELINE.json config shapes on the deterministic synthetic scene of SURVEY.md §8(d) (G(N, seed 0) in
+[-1.3,1.3]^3, 32-pose camera ring, a fresh pose every step: parameters + per-view buffers > L2, no L2 flush needed):
+  N = 1 (default)   configs[1] "Mip-NeRF360 garden, 1920x1080, ~1M Gaussians, SH deg 3, 1xB200 fwd+bwd" — the metric's config
+  N = 2, 4, 8       configs[3] "bicycle, ~3M Gaussians, 1600x1063, Gaussian-sharded across 2/4/8 GPUs" (gsplat semantics, like the
+                    reference's distributed renderer); at N = 8 configs[4] (10M, 1920x1080, tile culling on) is measured too and
+                    reported under "other_workloads"
+  --config K / --n --width --height select any other shape (configs[0] 30k/800x800, configs[2] 5M/1080p, ...).
+The N = 1 line also carries "scaling_base": configs[3] on ONE GPU in gsplat mode — the like-for-like denominator of the
+multi-GPU lines (same workload, same kernels); the N > 1 lines repeat it as measured on rank 0 alone in the same run.
 
 One "step" = what `GaussianSplatting.training_step` asks of the renderer (internal/gaussian_splatting.py:344,380):
 renderer.forward(camera, model, bg) from RAW parameters (activations included) and backward of a fixed random
@@ -34,6 +40,15 @@ import torch  # noqa: E402
 METRIC = "train-views/sec (fwd+bwd) @ N Gaussians, 1080p"
 UNIT = "views/s"
 
+# BASELINE.json "configs", as (label, N Gaussians, width, height)
+CONFIGS = {
+    0: ("configs[0] shape: nerf_synthetic/lego, 30k Gaussians, 800x800", 30_000, 800, 800),
+    1: ("configs[1] shape: Mip-NeRF360 garden, ~1M Gaussians, 1920x1080", 1_000_000, 1920, 1080),
+    2: ("configs[2] shape: synthetic 5M Gaussians, 1920x1080", 5_000_000, 1920, 1080),
+    3: ("configs[3] shape: Mip-NeRF360 bicycle, ~3M Gaussians, 1600x1063", 3_000_000, 1600, 1063),
+    4: ("configs[4] shape: MatrixCity aerial block, 10M Gaussians, 1920x1080", 10_000_000, 1920, 1080),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -41,17 +56,31 @@ def parse():
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200gs", choices=["b200gs", "reference"])
-    ap.add_argument("--mode", default="vanilla", choices=["vanilla", "gsplat"])
-    ap.add_argument("--n", type=int, default=1_000_000)
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--mode", default=None, choices=["vanilla", "gsplat"], help="default: vanilla on one GPU, gsplat when sharded")
+    ap.add_argument("--config", type=int, default=None, choices=sorted(CONFIGS), help="BASELINE.json configs[K] shape; default 1 (N=1) / 3 (N>1)")
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--no-extras", action="store_true", help="skip the scaling_base / single-GPU / configs[4] side measurements")
     ap.add_argument("--cpu-sample-iters", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parallelism", default="sharded", choices=["sharded", "replicas"],
                     help="N>1 only. sharded: the reference's Gaussian-sharded scheme (gsplat_distributed_renderer.py): scene split by "
                          "index across ranks, one camera per rank, all-to-all of the visible projected splats, gsplat semantics. "
                          "replicas: every rank holds the whole scene (configs/ddp.yaml style), no data-path collective.")
-    return ap.parse_args()
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.config is None:
+        args.config = 1 if world == 1 else 3
+    label, n, w, h = CONFIGS[args.config]
+    custom = any(v is not None for v in (args.n, args.width, args.height))
+    args.n = n if args.n is None else args.n
+    args.width = w if args.width is None else args.width
+    args.height = h if args.height is None else args.height
+    args.workload_label = label if not custom else f"custom shape ({args.n} Gaussians, {args.width}x{args.height})"
+    if args.mode is None:
+        args.mode = "gsplat" if (world > 1 and args.parallelism == "sharded") else "vanilla"
+    return args
 
 
 def peaks():
@@ -182,15 +211,15 @@ def cpu_projection_views_per_sec(n, width, height, mode_name, iters, warm=2, pre
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 12))
-    vps, med, cores, kind = cpu_projection_views_per_sec(args.n, args.width, args.height, args.mode, steps, warm=max(1, min(args.warmup, 3)))
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    vps, med, cores, kind = cpu_projection_views_per_sec(args.n, args.width, args.height, args.mode, steps, warm=warm)
     sample = (f"the reference's CPU-runnable part of the path (pypreprocess projection + SH, forward + autograd backward; it has no "
               f"CPU blend/sort: BASELINE.md §3), {steps} views of the same workload, median; "
               + ("unmodified reference code from baseline/_ref" if kind == "reference" else "oracle port (baseline/_ref absent)"))
     line = {
-        "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
+        "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, "cpu"),
+        "config": workload_config(args, "single" if world == 1 else "sharded-by-gaussian-index+all-to-all"),
         "cpu_baseline": {"value": vps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -198,7 +227,7 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, parallelism):
-    return {"workload": f"configs[1]: synthetic G({args.n}, seed 0) SH deg 3, {args.width}x{args.height}, 32-pose ring, "
+    return {"workload": f"{args.workload_label}: synthetic G({args.n}, seed 0) SH deg 3, {args.width}x{args.height}, 32-pose ring, "
                         f"{args.mode} semantics, fwd+bwd from raw parameters",
             "n_gaussians": args.n, "width": args.width, "height": args.height, "mode": args.mode, "parallelism": parallelism,
             "l2": "inputs larger than L2 (236 MB parameters + fresh camera every step); no explicit flush"}
@@ -207,15 +236,16 @@ def workload_config(args, parallelism):
 # bytes per view, SURVEY.md §8(d) / BASELINE.md §5 (V visible, I pairs, P pixels, N total; SH degree 3)
 def algorithmic_bytes(stage, N, V, I, P, n_tiles, C=None):
     """I = (tile, Gaussian) pairs the stage actually processes (after exact tile culling)."""
+    C = C if C is not None else int(2.5 * V)
     return {
         "project_fwd": V * 268 + N * 16,
-        # xy/depth/radius/conic/opacity read, keys+ids+cells+32 B record write, 4 radix passes of 8 B pairs (r+w), scan (id, gathered
-        # cell count, 8 B offset)
-        "bin_count": N * (32 + 44 + 4 * 16 + 16),
-        # C = (8x8-tile cell, Gaussian) pairs (~2.5 per visible splat).  emit: order + 32 B record + offset per splat, 18 B
-        # (key + {mask, id}) per coarse pair; one radix pass over them (18 B r+w) + histogram read; ranges 2 B; chunk counts 8 B;
-        # scatter 16 B; every fine pair's id written ONCE (4 B); tile starts / ranges 24 B per tile
-        "bin_sort": V * 44 + (C if C is not None else int(2.5 * V)) * (18 + 2 + 36 + 2 + 8 + 16) + I * 4 + n_tiles * 24,
+        # phase A: xy/depth/radius/conic/opacity read (36 B per Gaussian, 24 more per visible one), {key, id} + 32 B record per
+        # visible Gaussian, histogram read (8 B), 4 radix passes over the V records (8 B read + 8 B write each)
+        "bin_count": N * 12 + V * (24 + 8 + 32 + 8 + 4 * 16),
+        # phase B, C = (8x8-tile cell, Gaussian) entries (~2 per visible splat): emit reads {key,id} 8 B + the 32 B record per
+        # visible Gaussian and writes 16 B per entry; one partition pass (16 B read + 16 B write); chunk counts read 8 B, write
+        # 2 B x 64 tiles per 256-entry chunk; scatter reads 16 B; every fine pair's id written ONCE (4 B); tile starts / ranges
+        "bin_sort": V * 40 + C * (16 + 32 + 8 + 16) + I * 4 + n_tiles * 24,
         "blend_fwd": I * 40 + P * 20,
         "blend_bwd": I * 76 + P * 20,
         "project_bwd": V * 552,
@@ -223,7 +253,161 @@ def algorithmic_bytes(stage, N, V, I, P, n_tiles, C=None):
     }.get(stage, 0)
 
 
-LAUNCHES_PER_STEP = {"project_fwd": 1, "bin_count": 1 + 1 + 6 + 2 + 1, "bin_sort": 1 + 3 + 1 + 1 + 1 + 1 + 1 + 1, "blend_fwd": 1, "blend_bwd": 1, "project_bwd": 1}
+def _launch_count():
+    """Number of kernels libb200gs.so has launched so far in this process (counted inside the library at every launch)."""
+    from b200gs._lib import lib
+    fn = getattr(lib(), "b200gs_launch_count", None)
+    return int(fn()) if fn is not None else None
+
+
+class Workload:
+    """One (shape, mode, parallelism) measurement on the current process group."""
+
+    def __init__(self, n, width, height, mode, rank, world, local, sharded):
+        from b200gs.renderers import B200GSplatRenderer, B200VanillaRenderer
+        from b200gs.scene import SyntheticGaussians, make_ring_cameras, make_scene
+        self.N, self.W, self.H, self.mode, self.rank, self.world, self.sharded = n, width, height, mode, rank, world, sharded
+        self.dev = dev = torch.device("cuda", local)
+        raw = make_scene(n, 0)
+        self.cams = [c.to_device(dev) for c in make_ring_cameras(width, height)]
+        if sharded:
+            from b200gs.distributed import B200DistributedRenderer, shard_range
+            lo, hi = shard_range(n, world, rank)
+            self.model = SyntheticGaussians({k: v[lo:hi].contiguous() for k, v in raw.items()}).to(dev)
+            self.renderer = B200DistributedRenderer().to(dev)
+        else:
+            self.model = SyntheticGaussians(raw).to(dev)
+            self.renderer = (B200VanillaRenderer() if mode == "vanilla" else B200GSplatRenderer()).to(dev)
+        del raw
+        self.bg = torch.zeros(3, device=dev)
+        gen = torch.Generator().manual_seed(1)
+        self.cot_host = (torch.rand(3, height, width, generator=gen) * 2 - 1).pin_memory()
+        self.cot = self.cot_host.to(dev)
+        # e2e pipeline, the shape of the reference's training input path (dataset.py:150-305 prefetches, gaussian_splatting.py:
+        # 250-264 copies to the device): step i's input image is uploaded from pinned memory on a copy stream while step i-1
+        # computes (double buffer), and every step's scalar result is read back (its D2H lands one step later, so the host
+        # never stalls the GPU).  Every byte is moved inside the timed region.  (The 32 camera poses — 40 floats each — are
+        # device-resident before the loop, as a training set's cameras are.)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.read_stream = torch.cuda.Stream(device=dev)   # the result read-back never sits in the compute stream
+        self.loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.in_bufs = [torch.empty_like(self.cot), torch.empty_like(self.cot)]
+        self.in_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.loss_hosts = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
+        self.loss_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.loss_dev = [torch.zeros(1, device=dev), torch.zeros(1, device=dev)]
+        self.results = []
+        self.fwd_done = torch.cuda.Event()
+        self.step_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(self, i):
+        # called right after step i-1's forward has been enqueued: the upload overlaps that step's backward (compute-bound
+        # kernels) instead of the next forward's projection/binning (bandwidth- and latency-bound: measured 1.68 vs 1.58
+        # ms/step, profiles/tools/e2e_probe.py).  The buffer's previous consumer (step i-2) precedes the event in stream order.
+        self.fwd_done.record()
+        self.copy_stream.wait_event(self.fwd_done)
+        with torch.cuda.stream(self.copy_stream):
+            self.in_bufs[i & 1].copy_(self.cot_host, non_blocking=True)
+            self.in_ready[i & 1].record(self.copy_stream)
+
+    def step(self, i, e2e=False, more=False):
+        cam = self.cams[(i * self.world + self.rank) % len(self.cams)]   # each rank renders a different pose
+        for p in self.model.parameters():
+            p.grad = None
+        if e2e:
+            torch.cuda.current_stream().wait_event(self.in_ready[i & 1])
+            c = self.in_bufs[i & 1]
+        else:
+            c = self.cot
+        out = self.renderer(cam, self.model, self.bg)
+        if e2e and more:
+            self.prefetch(i + 1)
+        loss = (out["render"] * c).sum()
+        loss.backward()
+        if e2e:
+            self.loss_dev[i & 1].copy_(loss.detach().reshape(1))
+            self.loss_ready[i & 1].record()
+            self.read_stream.wait_event(self.loss_ready[i & 1])
+            with torch.cuda.stream(self.read_stream):
+                self.loss_hosts[i & 1].copy_(self.loss_dev[i & 1], non_blocking=True)
+                self.loss_done[i & 1].record(self.read_stream)
+        return out
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, k, e2e):
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if e2e:
+            self.prefetch(0)
+        for i in range(k):
+            self.step(i, e2e, i + 1 < k)
+            if not e2e:
+                self.step_done[i & 1].record()
+            if i > 0:   # the host stays at most one step ahead in both loops, like a training loop that logs its loss
+                if e2e:                                         # the user reads the previous step's result
+                    self.loss_done[(i - 1) & 1].synchronize()
+                    self.results.append(float(self.loss_hosts[(i - 1) & 1][0]))
+                else:
+                    self.step_done[(i - 1) & 1].synchronize()
+        if e2e:
+            self.loss_done[(k - 1) & 1].synchronize()
+            self.results.append(float(self.loss_hosts[(k - 1) & 1][0]))
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    def run(self, steps, warmup, e2e=True, stages=True):
+        """-> dict(ms_total, ms_e2e, launches, stage_ms).  W untimed warm-up steps, then EXACTLY `steps` timed steps."""
+        from b200gs import ops
+        for i in range(max(warmup, 3)):
+            self.step(i)
+        self.timed(min(steps, 16), False)      # untimed: lets the caching allocator settle into the timed loop's pattern
+        l0 = _launch_count()
+        ms_total = self.timed(steps, False)
+        l1 = _launch_count()
+        ms_e2e = self.timed(steps, True) if e2e else None
+        stage_ms = {}
+        if stages:    # per-stage timing (CUDA events on the launching stream) for the roofline numbers
+            timer = ops.StageTimer()
+            ops.set_stage_timer(timer)
+            for i in range(min(steps, 32)):
+                self.step(i)
+            stage_ms, _ = timer.summary_ms()
+            ops.set_stage_timer(None)
+        return {"ms_total": ms_total, "ms_e2e": ms_e2e, "launches": (l1 - l0) if l0 is not None else None, "stage_ms": stage_ms}
+
+    def views_per_s(self, ms, steps):
+        return steps * self.world / (ms * 1e-3)
+
+
+def scene_statistics(n, width, height, mode, dev):
+    """V, I (rect pairs), I after exact culling, coarse pairs of pose 0 on the full scene (one GPU, no collectives)."""
+    from b200gs import ops
+    from b200gs.renderers import camera_view
+    from b200gs.scene import SyntheticGaussians, make_ring_cameras, make_scene
+    model = SyntheticGaussians(make_scene(n, 0)).to(dev)
+    cam = make_ring_cameras(width, height)[0].to_device(dev)
+    mode_id = 0 if mode == "vanilla" else 1
+    view = camera_view(cam, mode_id)
+    with torch.no_grad():
+        xy, depth, radii, conic, comp, tiles, _, _, _ = ops.project_forward(view, model.get_xyz.detach(), model.get_scaling.detach().contiguous(),
+                                                                            model.get_rotation.detach().contiguous(), None, True)
+        V, I = int((radii > 0).sum()), int(tiles.sum())
+        opac_act = model.get_opacity.detach().reshape(-1).contiguous() * (comp if mode == "gsplat" else 1.0)
+        binned = ops.bin_gaussians(mode_id, width, height, xy, depth, radii, conic, opac_act.contiguous())
+        return V, I, binned.total, binned.coarse_pairs
 
 
 def main():
@@ -236,9 +420,6 @@ def main():
         return
 
     import torch.distributed as dist
-    from b200gs import ops
-    from b200gs.renderers import B200GSplatRenderer, B200VanillaRenderer
-    from b200gs.scene import SyntheticGaussians, make_ring_cameras, make_scene
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (b200gs has no CPU path)"
     torch.cuda.set_device(local)
@@ -247,124 +428,53 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     N, W, H = args.n, args.width, args.height
-    raw = make_scene(N, 0)
     sharded = world > 1 and args.parallelism == "sharded"
-    cams = [c.to_device(dev) for c in make_ring_cameras(W, H)]
-    if sharded:
-        from b200gs.distributed import B200DistributedRenderer, shard_range
-        lo, hi = shard_range(N, world, rank)
-        model = SyntheticGaussians({k: v[lo:hi].contiguous() for k, v in raw.items()}).to(dev)
-        renderer = B200DistributedRenderer().to(dev)
-        args.mode = "gsplat"    # the sharded renderer has gsplat semantics, like the reference's
-    else:
-        model = SyntheticGaussians(raw).to(dev)
-        renderer = (B200VanillaRenderer() if args.mode == "vanilla" else B200GSplatRenderer()).to(dev)
-    bg = torch.zeros(3, device=dev)
-    gen = torch.Generator().manual_seed(1)
-    cot_host = (torch.rand(3, H, W, generator=gen) * 2 - 1).pin_memory()
-    cot = cot_host.to(dev)
-    loss_host = torch.zeros(1).pin_memory()
+    extras = {}
 
-    # e2e pipeline, the shape of the reference's training input path (dataset.py:150-305 prefetches, gaussian_splatting.py:
-    # 250-264 copies to the device): step i's input image is uploaded from pinned memory on a copy stream while step i-1
-    # computes (double buffer), and every step's scalar result is read back (its D2H lands one step later, so the host
-    # never stalls the GPU).  Every byte is moved inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
-    read_stream = torch.cuda.Stream(device=dev)   # the result read-back never sits in the compute stream
-    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
-    in_bufs = [torch.empty_like(cot), torch.empty_like(cot)]
-    in_ready = [torch.cuda.Event(), torch.cuda.Event()]
-    loss_hosts = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
-    loss_done = [torch.cuda.Event(), torch.cuda.Event()]
-    loss_dev = [torch.zeros(1, device=dev), torch.zeros(1, device=dev)]
-    results = []
-
-    fwd_done = torch.cuda.Event()
-    step_done = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def prefetch(i):
-        # called right after step i-1's forward has been enqueued: the upload overlaps that step's backward (compute-bound
-        # kernels) instead of the next forward's projection/binning (bandwidth- and latency-bound: measured 1.68 vs 1.58
-        # ms/step, profiles/tools/e2e_probe.py).  The buffer's previous consumer (step i-2) precedes the event in stream order.
-        fwd_done.record()
-        copy_stream.wait_event(fwd_done)
-        with torch.cuda.stream(copy_stream):
-            in_bufs[i & 1].copy_(cot_host, non_blocking=True)
-            in_ready[i & 1].record(copy_stream)
-
-    def step(i, e2e=False, more=False):
-        cam = cams[(i * world + rank) % len(cams)]   # each rank renders a different pose
-        for p in model.parameters():
-            p.grad = None
-        if e2e:
-            torch.cuda.current_stream().wait_event(in_ready[i & 1])
-            c = in_bufs[i & 1]
-        else:
-            c = cot
-        out = renderer(cam, model, bg)
-        if e2e and more:
-            prefetch(i + 1)
-        loss = (out["render"] * c).sum()
-        loss.backward()
-        if e2e:
-            loss_dev[i & 1].copy_(loss.detach().reshape(1))
-            loss_ready[i & 1].record()
-            read_stream.wait_event(loss_ready[i & 1])
-            with torch.cuda.stream(read_stream):
-                loss_hosts[i & 1].copy_(loss_dev[i & 1], non_blocking=True)
-                loss_done[i & 1].record(read_stream)
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(k, e2e):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        if e2e:
-            prefetch(0)
-        for i in range(k):
-            step(i, e2e, i + 1 < k)
-            if not e2e:
-                step_done[i & 1].record()
-            if i > 0:   # the host stays at most one step ahead in both loops, like a training loop that logs its loss
-                if e2e:                                         # the user reads the previous step's result
-                    loss_done[(i - 1) & 1].synchronize()
-                    results.append(float(loss_hosts[(i - 1) & 1][0]))
-                else:
-                    step_done[(i - 1) & 1].synchronize()
-        if e2e:
-            loss_done[(k - 1) & 1].synchronize()
-            results.append(float(loss_hosts[(k - 1) & 1][0]))
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t[0])
-        return ms
+    # like-for-like single-GPU number of the same workload and mode (rank 0 alone; the other ranks wait): the denominator
+    # the multi-GPU value should be read against
+    if sharded and not args.no_extras:
+        if rank == 0:
+            solo = Workload(N, W, H, args.mode, 0, 1, local, False)
+            r = solo.run(min(args.steps, 24), 3, e2e=False, stages=False)
+            extras["single_gpu_same_workload"] = {"value": solo.views_per_s(r["ms_total"], min(args.steps, 24)), "unit": UNIT, "mode": args.mode,
+                                                  "note": "the whole scene on rank 0 alone, same shape/mode/kernels, measured in this run"}
+            del solo
+            torch.cuda.empty_cache()
+        dist.barrier()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    timed(min(args.steps, 16), False)      # untimed: lets the caching allocator settle into the timed loop's pattern
-    ms_total = timed(args.steps, False)
-    ms_e2e = timed(args.steps, True)
+    wl = Workload(N, W, H, args.mode, rank, world, local, sharded)
+    res = wl.run(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    ms_total, ms_e2e, stage_ms = res["ms_total"], res["ms_e2e"], res["stage_ms"]
+    cot_bytes = int(wl.cot_host.numel() * 4)
+    del wl
+    torch.cuda.empty_cache()
 
-    # per-stage timing (CUDA events on the launching stream) for the roofline numbers
-    timer = ops.StageTimer()
-    ops.set_stage_timer(timer)
-    for i in range(min(args.steps, 32)):
-        step(i)
-    stage_ms, stage_calls = timer.summary_ms()
-    ops.set_stage_timer(None)
+    # side measurements: configs[4] on 8 GPUs; the scaling base (configs[3], one GPU, gsplat mode) on the single-GPU line
+    if not args.no_extras and args.config in (1, 3):
+        if sharded and world == 8 and args.config == 3:
+            label, n4, w4, h4 = CONFIGS[4]
+            w4l = Workload(n4, w4, h4, "gsplat", rank, world, local, True)
+            k4 = min(args.steps, 16)
+            r4 = w4l.run(k4, 3, e2e=False, stages=False)
+            extras["other_workloads"] = [{"workload": f"{label}: synthetic G({n4}, seed 0) SH deg 3, {w4}x{h4}, gsplat semantics, exact tile culling on, "
+                                                      f"sharded by Gaussian index over {world} GPUs", "value": w4l.views_per_s(r4["ms_total"], k4),
+                                          "unit": UNIT, "steps": k4, "ms_per_step": r4["ms_total"] / k4}]
+            del w4l
+            torch.cuda.empty_cache()
+        elif world == 1 and args.config == 1:
+            label, n3, w3, h3 = CONFIGS[3]
+            w3l = Workload(n3, w3, h3, "gsplat", 0, 1, local, False)
+            k3 = min(args.steps, 24)
+            r3 = w3l.run(k3, 3, e2e=False, stages=False)
+            extras["scaling_base"] = {"workload": f"{label}: synthetic G({n3}, seed 0), {w3}x{h3}, gsplat semantics, ONE GPU", "value": w3l.views_per_s(r3["ms_total"], k3),
+                                      "unit": UNIT, "steps": k3, "note": "denominator for the N = 2/4/8 lines, which run this workload sharded"}
+            del w3l
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -372,56 +482,53 @@ def main():
         return
 
     # workload statistics of pose 0 for the algorithmic byte counts (full scene on this GPU, no collectives)
-    if sharded:
-        model = SyntheticGaussians(raw).to(dev)
-        renderer = B200GSplatRenderer().to(dev)
-    with torch.no_grad():
-        out = renderer(cams[0], model, bg)
-        V = int((out["radii"] > 0).sum())
+    V, I, I_culled, C_coarse = scene_statistics(N, W, H, args.mode, dev)
     gx, gy = (W + 15) // 16, (H + 15) // 16
-    from b200gs.renderers import camera_view
-    mode_id = 0 if args.mode == "vanilla" else 1
-    view = camera_view(cams[0], mode_id)
-    with torch.no_grad():
-        xy, depth, radii, conic, comp, tiles, _, _, _ = ops.project_forward(view, model.get_xyz.detach(), model.get_scaling.detach().contiguous(),
-                                                                            model.get_rotation.detach().contiguous(), None, True)
-        I = int(tiles.sum())
-        opac_act = model.get_opacity.detach().reshape(-1).contiguous() * (comp if args.mode == "gsplat" else 1.0)
-        binned = ops.bin_gaussians(mode_id, W, H, xy, depth, radii, conic, opac_act.contiguous())
-        I_culled, C_coarse = binned.total, binned.coarse_pairs
     P = W * H
     hbm_peak, peak_src = peaks()
     kernels = {}
     for k, ms in stage_ms.items():
         b = algorithmic_bytes(k, N, V, I_culled, P, gx * gy, C_coarse)
-        kernels[k] = {"ms": round(ms, 4), "alg_bytes": b, "gbs": round(b / (ms * 1e-3) / 1e9, 1), "launches": LAUNCHES_PER_STEP.get(k, 1)}
+        kernels[k] = {"ms": round(ms, 4), "alg_bytes": b, "gbs": round(b / (ms * 1e-3) / 1e9, 1)}
     top = max(stage_ms, key=stage_ms.get)
     ach = kernels[top]["gbs"]
-    traffic = None
-    try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/summarize.py)
+    traffic, traffic_src, issue = None, None, None
+    try:   # DRAM bytes / executed warp instructions per launch of that kernel from the committed ncu --set full capture
         prof = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
         if prof:
             with open(os.path.join(ROOT, "profiles", prof[-1])) as f:
-                traffic = json.load(f).get(top)
+                pj = json.load(f)
+            traffic = pj.get(top)
+            traffic_src = f"static: profiles/{prof[-1]} (ncu --set full capture of this command, configs[1]); not re-measured in this run"
+            inst = pj.get(top + "_warp_instructions")
+            if inst and clocks and clocks.get("sm_mhz"):
+                peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6            # warp instructions per second: 4 schedulers per SM, 1 per clock
+                issue = {"kernel": top, "bound": "issue", "achieved": round(inst / (stage_ms[top] * 1e-3) / 1e9, 1), "peak": round(peak_issue / 1e9, 1),
+                         "unit": "G warp-inst/s", "frac": round(inst / (stage_ms[top] * 1e-3) / peak_issue, 4),
+                         "source": f"executed warp instructions per launch from profiles/{prof[-1]} / live kernel time"}
     except Exception:
         traffic = None
     views_per_s = args.steps * world / (ms_total * 1e-3)
     e2e_vps = args.steps * world / (ms_e2e * 1e-3)
-    launches = sum(LAUNCHES_PER_STEP.values()) * args.steps
 
     line = {
         "metric": METRIC, "value": views_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args, ("sharded-by-gaussian-index+all-to-all" if sharded else "replicas") if world > 1 else "single"),
-        "e2e": {"value": e2e_vps, "unit": UNIT, "h2d_bytes_per_step": int(cot_host.numel() * 4), "d2h_bytes_per_step": 4},
-        "gpu_launches": launches,
+        "e2e": {"value": e2e_vps, "unit": UNIT, "h2d_bytes_per_step": cot_bytes, "d2h_bytes_per_step": 4,
+                "note": "per step: the [3,H,W] input image pinned-host->device and the scalar result device->host, inside the timed region; "
+                        "the 32 camera poses (40 floats each) are device-resident before the loop, as a training set's cameras are"},
+        "gpu_launches": res["launches"],
+        "gpu_launches_note": "kernels launched by libb200gs.so inside the timed region, counted by the library at every launch (b200gs_launch_count)",
         "clocks": clocks,
         "roofline": {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4),
-                     "traffic": traffic, "peak_source": peak_src,
-                     "note": "blend kernels are SM-issue (FP32+MUFU) bound, not HBM bound (SURVEY §8d); HBM fraction reported as asked"},
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "note": "blend kernels are SM-issue (FP32+MUFU) bound, not HBM bound (SURVEY §8d): see roofline_issue; HBM fraction reported as asked"},
+        "roofline_issue": issue,
         "kernels": kernels,
         "scene": {"N": N, "V": V, "I": I, "I_after_exact_culling": I_culled, "coarse_pairs": C_coarse, "P": P, "stage_sum_ms": round(sum(stage_ms.values()), 4)},
     }
+    line.update(extras)
     if not args.no_cpu_baseline and world == 1:
         vps, med, cores, kind = cpu_projection_views_per_sec(N, W, H, args.mode, args.cpu_sample_iters)
         line["cpu_baseline"] = {"value": vps, "unit": UNIT, "cores": cores, "kind": kind, "host_cpus": os.cpu_count() or 1,

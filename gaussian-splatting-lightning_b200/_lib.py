@@ -37,6 +37,7 @@ _P = c_void_p  # every device pointer is passed as an integer address
 _SIGNATURES = {
     "b200gs_last_error": (c_char_p, []),
     "b200gs_version": (c_int32, []),
+    "b200gs_launch_count": (c_int64, []),
     "b200gs_project_fwd": (c_int32, [POINTER(B200gsView), c_int64] + [_P] * 4 + [_P] * 9 + [_P]),
     "b200gs_project_bwd": (c_int32, [POINTER(B200gsView), c_int64] + [_P] * 4 + [_P] * 2 + [_P] * 5 + [_P] * 4 + [_P]),
     "b200gs_project_fwd_raw": (c_int32, [POINTER(B200gsView), c_int64] + [_P] * 6 + [c_int32] + [_P] * 9 + [_P]),

@@ -18,11 +18,14 @@
 // A stable multi-split keeps the depth order inside every tile, so the result equals the oracle's torch.sort(stable)
 // of the 64-bit keys element for element (tests/test_gpu_parity.py::test_binning_exact).
 //
-// cub:: provides the device-wide scan and the two radix sorts (header library compiled into this .so); everything else
-// is ours.
-#include <cub/cub.cuh>
-
+// Every kernel here is ours, including the device-wide primitives (onesweep.cuh: chained scan, onesweep radix passes):
+//   phase A  depth_keys (order-preserving compaction of the visible Gaussians through a chained scan; {depth key, id} records
+//            + the 32-byte record)  ->  hist4  ->  4 onesweep passes over the V visible records
+//   phase B  emit_cells (chained scan of the coarse-cell counts in depth order; per-cell histogram)  ->  cell_table (cell
+//            ranges, chunk table, digit histograms)  ->  1 onesweep pass by cell (2 above 256 cells)  ->  chunk_counts  ->
+//            chunk_prefix  ->  scatter_ids
 #include "common.cuh"
+#include "onesweep.cuh"
 
 namespace b200gs {
 
@@ -44,17 +47,19 @@ static_assert(sizeof(SplatRec) == 32, "SplatRec must be one sector");
 // value type of the coarse partition: {tile mask lo, tile mask hi, Gaussian id, unused}
 typedef uint4 CellEntry;
 
+constexpr int DEPTH_IPT = 16;                        // records per thread of a depth-sort tile (uint2: 32 KB of staging)
+constexpr int CELL_IPT = 8;                          // records per thread of a cell-partition tile (uint4: 32 KB of staging)
+constexpr int DEPTH_TILE = sweep::THREADS * DEPTH_IPT;
+constexpr int CELL_TILE = sweep::THREADS * CELL_IPT;
+
 struct LayoutA {
-    size_t keys_in, keys_out, ids_in, order, cells, offsets, recs, temp, temp_bytes, total;
+    size_t rec_a, rec_b, recs, zero, zero_bytes, hist, tickets, scan_state, lookback, total;
+    int64_t tiles, blocks;
 };
 struct LayoutB {
-    size_t ckeys_in, ckeys_out, cvals_in, entries, temp, temp_bytes, cell_ranges, chunk_base, chunk_cell, chunk_cnt, chunk_pre, tile_start, total;
-    int64_t max_chunks;
-};
-
-struct CellsOfOrder {
-    const int32_t* cells;
-    __host__ __device__ int64_t operator()(int32_t g) const { return (int64_t)cells[g]; }
+    size_t entries_in, entries, zero, zero_bytes, cell_hist, tickets, scan_state, lookback, digit_hist, cell_ranges, chunk_base, chunk_cell,
+        chunk_cnt, chunk_pre, tile_start, total;
+    int64_t max_chunks, tiles, blocks;
 };
 
 inline int bits_for(int n_values) {
@@ -79,20 +84,18 @@ LayoutA make_layout_a(int64_t n) {
     LayoutA L{};
     Taker take;
     const size_t nn = (size_t)(n > 0 ? n : 1);
-    L.keys_in = take(nn * 4);
-    L.keys_out = take(nn * 4);
-    L.ids_in = take(nn * 4);
-    L.order = take(nn * 4);
-    L.cells = take(nn * 4);
-    L.offsets = take(nn * 8);
+    L.tiles = (int64_t)div_up64((int64_t)nn, DEPTH_TILE);
+    L.blocks = (int64_t)div_up64((int64_t)nn, 256);
+    L.rec_a = take(nn * 8);
+    L.rec_b = take(nn * 8);
     L.recs = take(nn * sizeof(SplatRec));
-    size_t t_sort = 0, t_scan = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t_sort, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
-                                    (int32_t*)nullptr, (int)nn, 0, 32);
-    cub::TransformInputIterator<int64_t, CellsOfOrder, const int32_t*> it(nullptr, CellsOfOrder{nullptr});
-    cub::DeviceScan::InclusiveSum(nullptr, t_scan, it, (int64_t*)nullptr, (int)nn);
-    L.temp_bytes = t_sort > t_scan ? t_sort : t_scan;
-    L.temp = take(L.temp_bytes);
+    // one contiguous zero-initialised region: digit histograms, tickets, chained-scan state, look-back words of the 4 passes
+    L.zero = take(0);
+    L.hist = take(4 * sweep::RADIX * 4);
+    L.tickets = take(16 * 4);
+    L.scan_state = take((size_t)L.blocks * 4);
+    L.lookback = take((size_t)4 * L.tiles * sweep::RADIX * 4);
+    L.zero_bytes = take.off - L.zero;
     L.total = take.off;
     cached = L;
     cached_n = n;
@@ -106,11 +109,11 @@ inline void cell_grid(int width, int height, int& grid_x, int& grid_y, int& cgri
     cgrid_y = div_up(grid_y, SUPER);
 }
 
-LayoutB make_layout_b(int64_t max_coarse, int width, int height) {
-    static thread_local int64_t cached_p = -1;
+LayoutB make_layout_b(int64_t n, int64_t max_coarse, int width, int height) {
+    static thread_local int64_t cached_p = -1, cached_n = -1;
     static thread_local int cached_w = -1, cached_h = -1;
     static thread_local LayoutB cached{};
-    if (max_coarse == cached_p && width == cached_w && height == cached_h) return cached;
+    if (max_coarse == cached_p && n == cached_n && width == cached_w && height == cached_h) return cached;
     int grid_x, grid_y, cgrid_x, cgrid_y;
     cell_grid(width, height, grid_x, grid_y, cgrid_x, cgrid_y);
     const size_t n_cells = (size_t)cgrid_x * cgrid_y, n_tiles = (size_t)grid_x * grid_y;
@@ -118,17 +121,17 @@ LayoutB make_layout_b(int64_t max_coarse, int width, int height) {
     Taker take;
     const size_t pp = (size_t)(max_coarse > 0 ? max_coarse : 1);
     L.max_chunks = (int64_t)(pp / CHUNK + n_cells + 1);
-    L.ckeys_in = take(pp * 4);
-    L.ckeys_out = take(pp * 4);
-    L.cvals_in = take(pp * sizeof(CellEntry));
+    L.tiles = (int64_t)div_up64((int64_t)pp, CELL_TILE);
+    L.blocks = (int64_t)div_up64(n > 0 ? n : 1, 256);
+    L.entries_in = take(pp * sizeof(CellEntry));
     L.entries = take(pp * sizeof(CellEntry));
-    size_t t32 = 0, t16 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, t32, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const CellEntry*)nullptr,
-                                    (CellEntry*)nullptr, (int)pp, 0, 32);
-    cub::DeviceRadixSort::SortPairs(nullptr, t16, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const CellEntry*)nullptr,
-                                    (CellEntry*)nullptr, (int)pp, 0, 16);
-    L.temp_bytes = t32 > t16 ? t32 : t16;
-    L.temp = take(L.temp_bytes);
+    L.zero = take(0);
+    L.cell_hist = take(n_cells * 4);
+    L.tickets = take(16 * 4);
+    L.scan_state = take((size_t)L.blocks * 4);
+    L.lookback = take((size_t)2 * L.tiles * sweep::RADIX * 4);
+    L.zero_bytes = take.off - L.zero;
+    L.digit_hist = take(2 * sweep::RADIX * 4);
     L.cell_ranges = take(n_cells * 8);
     L.chunk_base = take((n_cells + 1) * 4);
     L.chunk_cell = take((size_t)L.max_chunks * 4);
@@ -138,6 +141,7 @@ LayoutB make_layout_b(int64_t max_coarse, int width, int height) {
     L.total = take.off;
     cached = L;
     cached_p = max_coarse;
+    cached_n = n;
     cached_w = width;
     cached_h = height;
     return cached;
@@ -235,21 +239,29 @@ __device__ __forceinline__ void coarsen_rect(int x0, int y0, int x1, int y1, int
     cy1 = ((y1 - 1) >> SUPER_SHIFT) + 1;
 }
 
-// Phase A, one lane per Gaussian: depth key, identity id, number of coarse cells of its tile rect and the 32-byte record
-// phase B works from.  counts[0] += tiles of the rect (the reference's pair count I: an upper bound of the culled
-// count, exact without culling), counts[1] += cells.
+// Phase A, one lane per Gaussian, blocks in ticket order: the visible Gaussians (non-empty tile rect) are compacted in index
+// order (block scan + chained scan over the blocks) into {depth key, id} records; each gets the 32-byte record phase B
+// works from.  counts[0] += tiles of the rect (the reference's pair count I: an upper bound of the culled count, exact
+// without culling), counts[1] += coarse cells, counts[3] = V.
 template <bool GSPLAT>
-__global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, int grid_y, const BinSrc src,
-                                                         uint32_t* __restrict__ keys, int32_t* __restrict__ ids,
-                                                         int32_t* __restrict__ cells, SplatRec* __restrict__ recs,
-                                                         unsigned long long* __restrict__ counts) {
+__global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, int grid_y, const BinSrc src, uint2* __restrict__ keyrec,
+                                                         SplatRec* __restrict__ recs, uint32_t* __restrict__ ticket,
+                                                         uint32_t* __restrict__ scan_state, unsigned long long* __restrict__ counts) {
     __shared__ unsigned long long s_area[8], s_cells[8];
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    __shared__ int s_scan[sweep::WARPS + 1];
+    __shared__ int s_tile;
+    __shared__ uint32_t s_excl;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int t = s_tile;
+    const int64_t i = int64_t(t) * blockDim.x + threadIdx.x;
     int area = 0, nc = 0;
+    SplatRec rec;
+    rec.x = rec.y = 0.f; rec.A = rec.C = 1.f; rec.B = 0.f; rec.opacity = 1.f; rec.radius = 0; rec.ncells = 0;
+    uint32_t key = 0xFFFFFFFFu;
     if (i < n) {
         const int r = src.get_radius(i);
-        SplatRec rec;
-        rec.x = rec.y = 0.f; rec.A = rec.C = 1.f; rec.B = 0.f; rec.opacity = 1.f; rec.radius = r;
+        rec.radius = r;
         if (r > 0) {
             const float2 p = src.get_xy(i);
             rec.x = p.x; rec.y = p.y;
@@ -265,12 +277,22 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
                     rec.A = q[0]; rec.B = q[1]; rec.C = q[2];
                     rec.opacity = src.opacity[i * src.os];
                 }
+                key = __float_as_uint(src.get_depth(i));
             }
         }
         rec.ncells = nc;
-        keys[i] = area > 0 ? __float_as_uint(src.get_depth(i)) : 0xFFFFFFFFu;
-        ids[i] = (int32_t)i;
-        cells[i] = nc;
+    }
+    const bool vis = area > 0;
+    int block_vis;
+    const int local = sweep::block_exclusive(vis ? 1 : 0, s_scan, &block_vis);
+    if (threadIdx.x == 0) {
+        const uint32_t excl = sweep::chained_exclusive(scan_state, t, (uint32_t)block_vis);
+        s_excl = excl;
+        if (t == (int)gridDim.x - 1) counts[3] = (unsigned long long)(excl + (uint32_t)block_vis);
+    }
+    __syncthreads();
+    if (vis) {
+        keyrec[s_excl + (uint32_t)local] = make_uint2(key, (uint32_t)i);
         float4* out = reinterpret_cast<float4*>(recs + i);
         out[0] = make_float4(rec.x, rec.y, rec.A, rec.B);
         out[1] = make_float4(rec.C, rec.opacity, __int_as_float(rec.radius), __int_as_float(rec.ncells));
@@ -292,44 +314,47 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
     }
 }
 
-// Phase B, one block per 256 depth-ranked Gaussians: emits their (coarse cell, {tile mask, id}) pairs, cells in row-major
-// order.  The block's ranks own one contiguous window of the pair arrays (offsets are an inclusive scan in depth order),
-// so the pairs are assembled in shared memory and written back with coalesced stores.  The expensive part — one
-// ellipse/row-band intersection per tile row of every rect — is spread over the block as (rank, row) work items, so a
-// warp never waits for the one lane that owns a large splat.
+// Phase B, one block (in ticket order) per 256 depth-ranked Gaussians: emits their (coarse cell, {tile mask, id}) entries, cells
+// in row-major order.  The first slot of a rank is the exclusive prefix of the cell counts in depth order: block scan +
+// chained scan over the blocks, so the block's ranks own one contiguous window of the entry array; the entries are
+// assembled in shared memory and written back with coalesced stores.  The expensive part — one ellipse/row-band
+// intersection per tile row of every rect — is spread over the block as (rank, row) work items, so a warp never waits
+// for the one lane that owns a large splat.  The block also counts its entries per cell (the histogram the partition and
+// the cell ranges are derived from).
 constexpr int EMIT_SLOTS = 2048;
+constexpr int EMIT_HIST = 1024;   // cells counted in shared memory (images up to 4096 x 4096); larger grids count straight in global memory
 
-template <bool GSPLAT, typename KT>
-__global__ void __launch_bounds__(256) emit_cells_kernel(int64_t n, int grid_x, int grid_y, int cgrid_x, int cull, int64_t max_coarse,
-                                                         const int32_t* __restrict__ order, const SplatRec* __restrict__ recs,
-                                                         const int64_t* __restrict__ offsets, KT* __restrict__ ckeys,
-                                                         CellEntry* __restrict__ cvals, KT pad_key, int n_cells,
-                                                         int2* __restrict__ cell_ranges) {
-    __shared__ KT s_k[EMIT_SLOTS];
+template <bool GSPLAT>
+__global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restrict__ d_visible, int grid_x, int grid_y, int cgrid_x, int cull,
+                                                         int64_t max_coarse, const uint2* __restrict__ order, const SplatRec* __restrict__ recs,
+                                                         CellEntry* __restrict__ entries, int n_cells, uint32_t* __restrict__ cell_hist,
+                                                         uint32_t* __restrict__ ticket, uint32_t* __restrict__ scan_state) {
+    __shared__ unsigned short s_k[EMIT_SLOTS];
     __shared__ int32_t s_id[EMIT_SLOTS];
     __shared__ unsigned long long s_mask[EMIT_SLOTS];
     __shared__ float s_f[8][256];        // mx, my, B, iA, two_tA, det, ymax, yR
     __shared__ int s_mode[256], s_xr[256], s_yr[256], s_start[256];   // x0 | x1 << 16, y0 | y1 << 16, first slot - block_lo
     __shared__ int s_rowoff[257];
     __shared__ int s_warp[8];
+    __shared__ int s_scan[sweep::WARPS + 1];
+    __shared__ uint32_t s_hist[EMIT_HIST];
     __shared__ int64_t s_lo;
+    __shared__ int s_tile;
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u, w = tid >> 5;
-    const int64_t rank0 = int64_t(blockIdx.x) * blockDim.x;
+    if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int64_t n = *d_visible;
+    const int64_t rank0 = int64_t(s_tile) * blockDim.x;
+    if (rank0 >= n) return;
+    const bool smem_hist = n_cells <= EMIT_HIST;
+    if (smem_hist)
+        for (int i = tid; i < n_cells; i += 256) s_hist[i] = 0;
     const int64_t rnk = rank0 + tid;
-    {   // slots [total, capacity) are sorted too: give them a key above every cell id (a slice per block)
-        const int64_t total = n > 0 ? offsets[n - 1] : 0;
-        const int64_t per = (max(max_coarse - total, (int64_t)0) + gridDim.x - 1) / gridDim.x;
-        const int64_t p0 = total + per * blockIdx.x, p1 = min(max_coarse, p0 + per);
-        for (int64_t i = p0 + tid; i < p1; i += 256) ckeys[i] = pad_key;
-        if (blockIdx.x == 0)   // cells without entries keep the empty range (filled in by cell_ranges_kernel otherwise)
-            for (int i = tid; i < n_cells; i += 256) cell_ranges[i] = make_int2(0, 0);
-    }
     int g = -1, x0 = 0, y0 = 0, x1 = 0, y1 = 0, t = 0, nrows = 0;
-    int64_t start = 0;
     CullE e{};
     if (rnk < n) {
-        g = order[rnk];
+        g = (int)order[rnk].y;
         const float4* rp = reinterpret_cast<const float4*>(recs + g);
         const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
         SplatRec rec;
@@ -341,9 +366,11 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(int64_t n, int grid_x, 
             e = make_cull(rec, cull != 0);
             nrows = (e.mode == 2) ? 0 : y1 - y0;
         }
-        start = offsets[rnk] - t;
     }
-    if (tid == 0) s_lo = start;
+    // first slot of this rank: cells of the ranks before it (this block: scan; the blocks before: chained scan)
+    int block_cells;
+    const int local_start = sweep::block_exclusive(t, s_scan, &block_cells);
+    if (tid == 0) s_lo = (int64_t)sweep::chained_exclusive(scan_state, s_tile, (uint32_t)block_cells);
     // exclusive scan of the row counts
     int inc = nrows;
 #pragma unroll
@@ -364,26 +391,27 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(int64_t n, int grid_x, 
     s_mode[tid] = e.mode;
     s_xr[tid] = x0 | (x1 << 16);
     s_yr[tid] = y0 | (y1 << 16);
-    s_start[tid] = (int)(start - block_lo);
+    s_start[tid] = local_start;
     const int cx0 = x0 >> SUPER_SHIFT, cy0 = y0 >> SUPER_SHIFT;
     const int cw = t > 0 ? ((x1 - 1) >> SUPER_SHIFT) - cx0 + 1 : 1;
     __syncthreads();
     const int total_rows = s_rowoff[256];
-    const int64_t last_rank = min(rank0 + (int64_t)blockDim.x, n) - 1;
-    const int64_t block_hi = min(offsets[last_rank], max_coarse);
+    const int64_t block_hi = min(block_lo + block_cells, max_coarse);
     for (int64_t lo = block_lo; lo < block_hi; lo += EMIT_SLOTS) {
         const int cn = (int)min((int64_t)EMIT_SLOTS, block_hi - lo);
         const int wlo = (int)(lo - block_lo);       // window = local slots [wlo, wlo + cn)
         for (int i = tid; i < cn; i += 256) s_mask[i] = 0ull;
-        // keys and ids of this rank's slots
+        // cells and ids of this rank's slots
         {
-            const int ls = (int)(start - block_lo);
+            const int ls = local_start;
             int k = max(0, wlo - ls);
             const int kend = min(t, wlo + cn - ls);
             int cy = cy0 + k / cw, cx = cx0 + k % cw;
             for (; k < kend; ++k) {
-                s_k[ls + k - wlo] = (KT)(cy * cgrid_x + cx);
+                const int cell = cy * cgrid_x + cx;
+                s_k[ls + k - wlo] = (unsigned short)cell;
                 s_id[ls + k - wlo] = g;
+                if (smem_hist) atomicAdd(&s_hist[cell], 1u); else atomicAdd(cell_hist + cell, 1u);
                 if (++cx == cx0 + cw) { cx = cx0; ++cy; }
             }
         }
@@ -417,85 +445,72 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(int64_t n, int grid_x, 
         __syncthreads();
         for (int i = tid; i < cn; i += 256) {
             const unsigned long long m = s_mask[i];
-            ckeys[lo + i] = s_k[i];
-            cvals[lo + i] = make_uint4((uint32_t)m, (uint32_t)(m >> 32), (uint32_t)s_id[i], 0u);
+            entries[lo + i] = make_uint4((uint32_t)m, (uint32_t)(m >> 32), (uint32_t)s_id[i], (uint32_t)s_k[i]);
         }
         __syncthreads();
     }
-}
-
-// ranges[c] = [first, last+1) of cell c in the partitioned key array; RV keys per thread (one 16-byte load).
-template <typename KT>
-__global__ void __launch_bounds__(256) cell_ranges_kernel(int64_t cap, const int64_t* __restrict__ d_total, const KT* __restrict__ keys,
-                                                          int2* __restrict__ ranges) {
-    constexpr int RV = 16 / sizeof(KT) >= 8 ? 8 : 4;   // 8 x u16 = 16 B, 4 x u32 = 16 B
-    const int64_t total = min(cap, *d_total);
-    const int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * RV;
-    if (i0 >= total) return;
-    KT k[RV];
-    if (i0 + RV <= total) {
-        *reinterpret_cast<uint4*>(k) = *reinterpret_cast<const uint4*>(keys + i0);   // keys is 256 B aligned, i0 multiple of RV
-    } else {
-#pragma unroll
-        for (int e = 0; e < RV; ++e) k[e] = (i0 + e < total) ? keys[i0 + e] : KT(0);
-    }
-    uint32_t prev = (i0 == 0) ? 0xFFFFFFFFu : (uint32_t)keys[i0 - 1];
-#pragma unroll
-    for (int e = 0; e < RV; ++e) {
-        const int64_t i = i0 + e;
-        if (i >= total) break;
-        const uint32_t cur = k[e];
-        if (cur != prev) {
-            if (i > 0) ranges[prev].y = (int)i;
-            ranges[cur].x = (int)i;
+    if (smem_hist)
+        for (int i = tid; i < n_cells; i += 256) {
+            const uint32_t c = s_hist[i];
+            if (c) atomicAdd(cell_hist + i, c);
         }
-        if (i == total - 1) ranges[cur].y = (int)total;
-        prev = cur;
-    }
 }
 
-// chunk_base[c] = number of CHUNK-entry chunks of the cells before c; chunk_cell[chunk] = its cell (one block; n_cells is small)
-__global__ void __launch_bounds__(1024) chunk_table_kernel(int n_cells, const int2* __restrict__ cell_ranges, int32_t* __restrict__ chunk_base,
-                                                           int32_t* __restrict__ chunk_cell, int n_tiles, int64_t* __restrict__ tile_total) {
-    __shared__ int s_warp[32];
-    __shared__ int s_carry;
+// One block, after the emit: from the per-cell entry counts -> cell ranges (exclusive scan), the chunk table
+// (chunk_base[c] = number of CHUNK-entry chunks of the cells before c; chunk_cell[chunk] = its cell), the digit histograms
+// of the partition passes (low / high byte of the cell id), zeroed tile totals.
+__global__ void __launch_bounds__(1024) cell_table_kernel(int n_cells, const uint32_t* __restrict__ cell_hist, int2* __restrict__ cell_ranges,
+                                                          int32_t* __restrict__ chunk_base, int32_t* __restrict__ chunk_cell,
+                                                          uint32_t* __restrict__ digit_hist, int n_tiles, int64_t* __restrict__ tile_total) {
+    __shared__ int s_warp[32], s_warp2[32];
+    __shared__ int s_carry, s_carry2;
+    __shared__ uint32_t s_dh[2][sweep::RADIX];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) { s_carry = 0; s_carry2 = 0; }
+    for (int i = tid; i < 2 * sweep::RADIX; i += 1024) (&s_dh[0][0])[i] = 0;
     __syncthreads();
     for (int base = 0; base < n_cells; base += 1024) {
         const int i = base + tid;
-        int v = 0;
+        int cnt = 0, v = 0;
         if (i < n_cells) {
-            const int2 r = cell_ranges[i];
-            v = (r.y - r.x + CHUNK - 1) / CHUNK;
+            cnt = (int)cell_hist[i];
+            v = (cnt + CHUNK - 1) / CHUNK;
+            if (cnt) { atomicAdd(&s_dh[0][i & 255], (uint32_t)cnt); atomicAdd(&s_dh[1][(i >> 8) & 255], (uint32_t)cnt); }
         }
-        int inc = v;
+        int inc = v, inc2 = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+            const int t2 = __shfl_up_sync(0xffffffffu, inc2, o);
+            if (lane >= o) { inc += t; inc2 += t2; }
         }
-        if (lane == 31) s_warp[w] = inc;
+        if (lane == 31) { s_warp[w] = inc; s_warp2[w] = inc2; }
         __syncthreads();
         if (w == 0) {
-            int ws = s_warp[lane], winc = ws;
+            int ws = s_warp[lane], winc = ws, ws2 = s_warp2[lane], winc2 = ws2;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
+                const int t2 = __shfl_up_sync(0xffffffffu, winc2, o);
+                if (lane >= o) { winc += t; winc2 += t2; }
             }
             s_warp[lane] = winc - ws;
+            s_warp2[lane] = winc2 - ws2;
         }
         __syncthreads();
-        const int carry = s_carry;
-        const int excl = carry + s_warp[w] + inc - v;
-        if (i < n_cells) chunk_base[i] = excl;
+        const int excl = s_carry + s_warp[w] + inc - v;
+        const int excl2 = s_carry2 + s_warp2[w] + inc2 - cnt;
+        if (i < n_cells) {
+            chunk_base[i] = excl;
+            cell_ranges[i] = cnt > 0 ? make_int2(excl2, excl2 + cnt) : make_int2(0, 0);
+        }
         __syncthreads();
-        if (tid == 1023) s_carry = excl + v;
+        if (tid == 1023) { s_carry = excl + v; s_carry2 = excl2 + cnt; }
         __syncthreads();
     }
     const int total = s_carry;
     if (tid == 0) chunk_base[n_cells] = total;
+    for (int i = tid; i < 2 * sweep::RADIX; i += 1024) digit_hist[i] = (&s_dh[0][0])[i];
     for (int i = tid; i < n_tiles; i += 1024) tile_total[i] = 0;    // accumulated by chunk_counts_kernel
     __syncthreads();                                                // chunk_base (written by this block) is visible
     for (int c = tid; c < total; c += 1024) {
@@ -727,34 +742,10 @@ __global__ void __launch_bounds__(CHUNK) scatter_ids_kernel(int n_cells, int cgr
     }
 }
 
-template <typename KT>
-int partition_cells(int mode, int64_t n, int grid_x, int grid_y, int cgrid_x, int n_cells, int cull, const int64_t* d_coarse,
-                    int64_t max_coarse, const int32_t* order, const SplatRec* recs, const int64_t* offsets, void* keys_in,
-                    void* keys_out, CellEntry* cvals_in, void* temp, size_t temp_bytes, CellEntry* entries, int2* cell_ranges,
-                    cudaStream_t s) {
-    KT* kin = (KT*)keys_in;
-    KT* kout = (KT*)keys_out;
-    const unsigned blocks = (unsigned)div_up64(n, 256);
-    if (mode == B200GS_MODE_GSPLAT)
-        emit_cells_kernel<true, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, kin, cvals_in,
-                                                             (KT)n_cells, n_cells, cell_ranges);
-    else
-        emit_cells_kernel<false, KT><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, kin, cvals_in,
-                                                              (KT)n_cells, n_cells, cell_ranges);
-    B200GS_LAUNCH_CHECK();
-    const int bits = bits_for(n_cells + 1);   // + the pad key n_cells
-    size_t tb = temp_bytes;
-    B200GS_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, kin, kout, cvals_in, entries, (int)max_coarse, 0, bits, s));
-    constexpr int RV = 16 / sizeof(KT) >= 8 ? 8 : 4;
-    cell_ranges_kernel<KT><<<(unsigned)div_up64(div_up64(max_coarse, RV), 256), 256, 0, s>>>(max_coarse, d_coarse, kout, cell_ranges);
-    B200GS_LAUNCH_CHECK();
-    return B200GS_OK;
-}
-
 }  // namespace
 
 size_t bin_count_workspace_bytes(int64_t n) { return make_layout_a(n).total; }
-size_t bin_sort_workspace_bytes(int64_t, int64_t max_coarse, int width, int height) { return make_layout_b(max_coarse, width, height).total; }
+size_t bin_sort_workspace_bytes(int64_t n, int64_t max_coarse, int width, int height) { return make_layout_b(n, max_coarse, width, height).total; }
 
 static BinSrc make_src(int row_stride, const float* xy, const float* depth, const int32_t* radii, const float* conic, const float* opacity) {
     if (row_stride > 0) return BinSrc{xy, depth, radii, conic, opacity, row_stride, row_stride, row_stride, row_stride, row_stride};
@@ -773,10 +764,6 @@ __global__ void publish_counts_kernel(const int64_t* __restrict__ d_counts, vola
 __global__ void publish_i64_kernel(const int64_t* __restrict__ src, volatile int64_t* __restrict__ dst, int n) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
     __threadfence_system();
-}
-
-__global__ void zero_counts_kernel(int64_t* __restrict__ d_counts) {
-    if (threadIdx.x < 4) d_counts[threadIdx.x] = 0;
 }
 
 static int copy_counts(const int64_t* d_counts, int64_t* host_counts, int sync_host, cudaStream_t s) {
@@ -816,30 +803,42 @@ int bin_count(int mode, int width, int height, int64_t n, int row_stride, const 
         set_error("bin_count: workspace too small (%zu < %zu)", ws_bytes, L.total);
         return B200GS_ENOSPACE;
     }
+    if (n >= (int64_t(1) << 30)) {
+        set_error("bin_count: %lld Gaussians exceed the 2^30 limit of the look-back words", (long long)n);
+        return B200GS_ENOSPACE;
+    }
     char* w = (char*)ws;
-    uint32_t* keys_in = (uint32_t*)(w + L.keys_in);
-    uint32_t* keys_out = (uint32_t*)(w + L.keys_out);
-    int32_t* ids_in = (int32_t*)(w + L.ids_in);
-    int32_t* order = (int32_t*)(w + L.order);
-    int32_t* cells = (int32_t*)(w + L.cells);
-    int64_t* offsets = (int64_t*)(w + L.offsets);
+    uint2* rec_a = (uint2*)(w + L.rec_a);
+    uint2* rec_b = (uint2*)(w + L.rec_b);
     SplatRec* recs = (SplatRec*)(w + L.recs);
+    uint32_t* hist = (uint32_t*)(w + L.hist);
+    uint32_t* tickets = (uint32_t*)(w + L.tickets);
+    uint32_t* scan_state = (uint32_t*)(w + L.scan_state);
+    uint32_t* lookback = (uint32_t*)(w + L.lookback);
     const int grid_x = div_up(width, TILE), grid_y = div_up(height, TILE);
-    zero_counts_kernel<<<1, 32, 0, s>>>(d_counts);
-    B200GS_LAUNCH_CHECK();
+    B200GS_CUDA(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int64_t), s));
     if (n > 0) {
-        const unsigned blocks = (unsigned)div_up64(n, 256);
+        B200GS_CUDA(cudaMemsetAsync(w + L.zero, 0, L.zero_bytes, s));
+        const unsigned blocks = (unsigned)L.blocks;
         const BinSrc src = make_src(row_stride, xy, depth, radii, conic, opacity);
         if (mode == B200GS_MODE_GSPLAT)
-            depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, keys_in, ids_in, cells, recs, (unsigned long long*)d_counts);
+            depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, rec_a, recs, tickets, scan_state, (unsigned long long*)d_counts);
         else
-            depth_keys_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, keys_in, ids_in, cells, recs, (unsigned long long*)d_counts);
+            depth_keys_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, rec_a, recs, tickets, scan_state, (unsigned long long*)d_counts);
         B200GS_LAUNCH_CHECK();
-        size_t tb = L.temp_bytes;
-        B200GS_CUDA(cub::DeviceRadixSort::SortPairs(w + L.temp, tb, keys_in, keys_out, ids_in, order, (int)n, 0, 32, s));
-        cub::TransformInputIterator<int64_t, CellsOfOrder, const int32_t*> it(order, CellsOfOrder{cells});
-        tb = L.temp_bytes;
-        B200GS_CUDA(cub::DeviceScan::InclusiveSum(w + L.temp, tb, it, offsets, (int)n, s));
+        // stable LSD sort of the V visible {depth key, id} records (V = d_counts[3], known on the device only)
+        const int64_t* d_visible = d_counts + 3;
+        sweep::hist4_kernel<<<(unsigned)min((int64_t)592, L.blocks), sweep::THREADS, 0, s>>>(rec_a, d_visible, n, hist);
+        B200GS_LAUNCH_CHECK();
+        uint2* src_rec = rec_a;
+        uint2* dst_rec = rec_b;
+        for (int pass = 0; pass < 4; ++pass) {
+            sweep::onesweep_pass_kernel<uint2, DEPTH_IPT><<<(unsigned)L.tiles, sweep::THREADS, 0, s>>>(
+                src_rec, dst_rec, d_visible, n, 8 * pass, hist + pass * sweep::RADIX, lookback + (size_t)pass * L.tiles * sweep::RADIX, tickets + 1 + pass);
+            B200GS_LAUNCH_CHECK();
+            uint2* tmp = src_rec; src_rec = dst_rec; dst_rec = tmp;
+        }
+        // 4 passes: the sorted records are back in rec_a
     }
     return copy_counts(d_counts, host_counts, sync_host, s);
 }
@@ -850,8 +849,12 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
     int grid_x, grid_y, cgrid_x, cgrid_y;
     cell_grid(width, height, grid_x, grid_y, cgrid_x, cgrid_y);
     const int n_tiles = grid_x * grid_y, n_cells = cgrid_x * cgrid_y;
-    if (max_pairs >= (int64_t(1) << 31) || max_coarse >= (int64_t(1) << 31)) {
-        set_error("bin_sort: capacity %lld / %lld exceeds 2^31", (long long)max_coarse, (long long)max_pairs);
+    if (max_pairs >= (int64_t(1) << 30) || max_coarse >= (int64_t(1) << 30)) {
+        set_error("bin_sort: capacity %lld / %lld exceeds 2^30", (long long)max_coarse, (long long)max_pairs);
+        return B200GS_ENOSPACE;
+    }
+    if (n_cells > 65536) {
+        set_error("bin_sort: %d coarse cells exceed 65536 (image too large)", n_cells);
         return B200GS_ENOSPACE;
     }
     if (max_coarse == 0 || n == 0) {   // nothing on screen (or nothing can be stored): empty lists; counts[2] stays 0
@@ -859,35 +862,55 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
         return copy_counts(d_counts, host_counts, sync_host, s);
     }
     const LayoutA LA = make_layout_a(n);
-    const LayoutB L = make_layout_b(max_coarse, width, height);
+    const LayoutB L = make_layout_b(n, max_coarse, width, height);
     if (ws_bytes < L.total) {
         set_error("bin_sort: workspace too small (%zu < %zu)", ws_bytes, L.total);
         return B200GS_ENOSPACE;
     }
     const char* wa = (const char*)ws_a;
     char* w = (char*)ws_b;
-    const int32_t* order = (const int32_t*)(wa + LA.order);
-    const int64_t* offsets = (const int64_t*)(wa + LA.offsets);
+    const uint2* order = (const uint2*)(wa + LA.rec_a);
     const SplatRec* recs = (const SplatRec*)(wa + LA.recs);
-    CellEntry* cvals_in = (CellEntry*)(w + L.cvals_in);
+    CellEntry* entries_in = (CellEntry*)(w + L.entries_in);
     CellEntry* entries = (CellEntry*)(w + L.entries);
+    uint32_t* cell_hist = (uint32_t*)(w + L.cell_hist);
+    uint32_t* tickets = (uint32_t*)(w + L.tickets);
+    uint32_t* scan_state = (uint32_t*)(w + L.scan_state);
+    uint32_t* lookback = (uint32_t*)(w + L.lookback);
+    uint32_t* digit_hist = (uint32_t*)(w + L.digit_hist);
     int2* cell_ranges = (int2*)(w + L.cell_ranges);
     int32_t* chunk_base = (int32_t*)(w + L.chunk_base);
     int32_t* chunk_cell = (int32_t*)(w + L.chunk_cell);
     uint16_t* chunk_cnt = (uint16_t*)(w + L.chunk_cnt);
     uint32_t* chunk_pre = (uint32_t*)(w + L.chunk_pre);
     int64_t* tile_start = (int64_t*)(w + L.tile_start);
+    const int64_t* d_visible = d_counts + 3;
+    const int64_t* d_coarse = d_counts + 1;
 
-    // B: coarse pairs with their tile masks, partitioned by cell
-    int rc;
-    if (bits_for(n_cells + 1) <= 16)
-        rc = partition_cells<uint16_t>(mode, n, grid_x, grid_y, cgrid_x, n_cells, cull, d_counts + 1, max_coarse, order, recs, offsets,
-                                       w + L.ckeys_in, w + L.ckeys_out, cvals_in, w + L.temp, L.temp_bytes, entries, cell_ranges, s);
+    // B: coarse entries with their tile masks in depth order; per-cell counts
+    B200GS_CUDA(cudaMemsetAsync(w + L.zero, 0, L.zero_bytes, s));
+    const bool two_pass = n_cells > sweep::RADIX;
+    CellEntry* emit_dst = two_pass ? entries : entries_in;   // one pass: in -> entries; two passes: entries -> in -> entries
+    if (mode == B200GS_MODE_GSPLAT)
+        emit_cells_kernel<true><<<(unsigned)L.blocks, 256, 0, s>>>(d_visible, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, emit_dst, n_cells,
+                                                                    cell_hist, tickets, scan_state);
     else
-        rc = partition_cells<uint32_t>(mode, n, grid_x, grid_y, cgrid_x, n_cells, cull, d_counts + 1, max_coarse, order, recs, offsets,
-                                       w + L.ckeys_in, w + L.ckeys_out, cvals_in, w + L.temp, L.temp_bytes, entries, cell_ranges, s);
-    if (rc != B200GS_OK) return rc;
-    chunk_table_kernel<<<1, 1024, 0, s>>>(n_cells, cell_ranges, chunk_base, chunk_cell, n_tiles, tile_start);
+        emit_cells_kernel<false><<<(unsigned)L.blocks, 256, 0, s>>>(d_visible, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, emit_dst, n_cells,
+                                                                     cell_hist, tickets, scan_state);
+    B200GS_LAUNCH_CHECK();
+    cell_table_kernel<<<1, 1024, 0, s>>>(n_cells, cell_hist, cell_ranges, chunk_base, chunk_cell, digit_hist, n_tiles, tile_start);
+    B200GS_LAUNCH_CHECK();
+    // stable partition by cell: one onesweep pass per byte of the cell id (the entry carries its cell in .w)
+    if (two_pass) {
+        sweep::onesweep_pass_kernel<CellEntry, CELL_IPT><<<(unsigned)L.tiles, sweep::THREADS, 0, s>>>(entries, entries_in, d_coarse, max_coarse, 0, digit_hist,
+                                                                                                      lookback, tickets + 1);
+        B200GS_LAUNCH_CHECK();
+        sweep::onesweep_pass_kernel<CellEntry, CELL_IPT><<<(unsigned)L.tiles, sweep::THREADS, 0, s>>>(
+            entries_in, entries, d_coarse, max_coarse, 8, digit_hist + sweep::RADIX, lookback + (size_t)L.tiles * sweep::RADIX, tickets + 2);
+    } else {
+        sweep::onesweep_pass_kernel<CellEntry, CELL_IPT><<<(unsigned)L.tiles, sweep::THREADS, 0, s>>>(entries_in, entries, d_coarse, max_coarse, 0, digit_hist,
+                                                                                                      lookback, tickets + 1);
+    }
     B200GS_LAUNCH_CHECK();
 
     // C: per-chunk tile counts;  D: chunk prefixes, tile starts / ranges / total;  E: ids in place
@@ -906,10 +929,23 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
 // ---- row packing for the Gaussian-sharded exchange -------------------------------------------------------------------
 namespace {
 
-struct VisibleFlag {
-    const int32_t* radii;
-    __host__ __device__ int32_t operator()(int32_t i) const { return radii[i] > 0 ? 1 : 0; }
-};
+// scan[i] = number of entries with radius > 0 before i: block scan + chained scan over the blocks (ticket order)
+__global__ void __launch_bounds__(256) visible_scan_kernel(int64_t n, const int32_t* __restrict__ radii, int32_t* __restrict__ scan,
+                                                           uint32_t* __restrict__ ticket, uint32_t* __restrict__ state) {
+    __shared__ int s_scan[sweep::WARPS + 1];
+    __shared__ int s_tile;
+    __shared__ uint32_t s_excl;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int t = s_tile;
+    const int64_t i = int64_t(t) * blockDim.x + threadIdx.x;
+    const int v = (i < n && radii[i] > 0) ? 1 : 0;
+    int block_total;
+    const int local = sweep::block_exclusive(v, s_scan, &block_total);
+    if (threadIdx.x == 0) s_excl = sweep::chained_exclusive(state, t, (uint32_t)block_total);
+    __syncthreads();
+    if (i < n) scan[i] = (int32_t)(s_excl + (uint32_t)local);
+}
 
 // scan[i] = number of visible entries before i.  Plain layout (seg_cap == 0): row index = scan[i], d_count[0] = total.
 // Segmented layout (seg_cap > 0; a segment = the seg_len entries of one camera = the rows for one destination rank):
@@ -975,15 +1011,9 @@ __global__ void __launch_bounds__(256) unpack_rows_grad_kernel(int64_t n, const 
 
 }  // namespace
 
-static size_t pack_scan_temp_bytes(int64_t n) {
-    size_t t = 0;
-    cub::TransformInputIterator<int32_t, VisibleFlag, cub::CountingInputIterator<int32_t>> it(cub::CountingInputIterator<int32_t>(0),
-                                                                                                VisibleFlag{nullptr});
-    cub::DeviceScan::ExclusiveSum(nullptr, t, it, (int32_t*)nullptr, (int)(n > 0 ? n : 1));
-    return align_up(t, 256);
-}
+static size_t pack_scan_state_bytes(int64_t n) { return align_up((size_t)div_up64(n > 0 ? n : 1, 256) * 4 + 64, 256); }
 
-size_t pack_rows_workspace_bytes(int64_t n) { return pack_scan_temp_bytes(n) + align_up((size_t)(n > 0 ? n : 1) * 4, 256); }
+size_t pack_rows_workspace_bytes(int64_t n) { return pack_scan_state_bytes(n) + align_up((size_t)(n > 0 ? n : 1) * 4, 256); }
 
 int pack_rows(int64_t n, int64_t seg_len, int64_t seg_cap, const float* xy, const float* depth, const float* conic, const float* comp,
               const float* opacity, const float* rgb, const int32_t* radii, void* ws, size_t ws_bytes, int32_t* row_index, float* rows,
@@ -993,13 +1023,14 @@ int pack_rows(int64_t n, int64_t seg_len, int64_t seg_cap, const float* xy, cons
         B200GS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t) * (size_t)segments, s));
         return B200GS_OK;
     }
-    const size_t temp = pack_scan_temp_bytes(n);
-    int32_t* scan = (int32_t*)((char*)ws + temp);
-    cub::TransformInputIterator<int32_t, VisibleFlag, cub::CountingInputIterator<int32_t>> it(cub::CountingInputIterator<int32_t>(0),
-                                                                                                VisibleFlag{radii});
-    size_t tb = temp;
+    const size_t state_bytes = pack_scan_state_bytes(n);
     (void)ws_bytes;
-    B200GS_CUDA(cub::DeviceScan::ExclusiveSum(ws, tb, it, scan, (int)n, s));
+    uint32_t* ticket = (uint32_t*)ws;               // [0]: ticket, [16..]: chained-scan state of the blocks
+    uint32_t* state = ticket + 16;
+    int32_t* scan = (int32_t*)((char*)ws + state_bytes);
+    B200GS_CUDA(cudaMemsetAsync(ws, 0, state_bytes, s));
+    visible_scan_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(n, radii, scan, ticket, state);
+    B200GS_LAUNCH_CHECK();
     pack_rows_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(n, seg_cap > 0 ? seg_len : n, seg_cap, (const float2*)xy, depth, conic, comp,
                                                                opacity, rgb, radii, scan, row_index, rows, d_count);
     B200GS_LAUNCH_CHECK();

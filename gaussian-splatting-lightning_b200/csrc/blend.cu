@@ -96,18 +96,19 @@ constexpr int LIST_PAD = 8;
 
 // Every warp compacts the staged slab [0,top) into the ascending list of entries whose mask has its bit set.
 // my_list[LIST_PAD + k] = k-th entry; the LIST_PAD slots in front and the slots after the end hold DUMMY.
+template <int FRONT = LIST_PAD>
 __device__ __forceinline__ int build_list(const unsigned char* __restrict__ s_mask, unsigned short* __restrict__ my_list, int top, int warp,
                                           unsigned lane) {
     int n = 0;
-    if (lane < LIST_PAD) my_list[lane] = (unsigned short)DUMMY;
+    if (lane < FRONT) my_list[lane] = (unsigned short)DUMMY;
     for (int c = 0; c < top; c += 32) {
         const int j = c + (int)lane;
         const bool hit = (j < top) && ((s_mask[j] >> warp) & 1u);
         const unsigned b = __ballot_sync(FULL, hit);
-        if (hit) my_list[LIST_PAD + n + __popc(b & ((1u << lane) - 1u))] = (unsigned short)j;
+        if (hit) my_list[FRONT + n + __popc(b & ((1u << lane) - 1u))] = (unsigned short)j;
         n += __popc(b);
     }
-    if (lane < LIST_PAD) my_list[LIST_PAD + n + lane] = (unsigned short)DUMMY;
+    if (lane < LIST_PAD) my_list[FRONT + n + lane] = (unsigned short)DUMMY;
     __syncwarp();
     return n;
 }
@@ -199,6 +200,153 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_ker
             }
         }
     }
+    if (inside) {
+        const int64_t pix = int64_t(py) * width + px;
+        final_T[pix] = T;
+        n_contrib[pix] = last;
+        if (alpha_out) alpha_out[pix] = 1.0f - T;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) image[pix * pix_stride + c * ch_stride] = C[c] + (bg ? T * __ldg(bg + c) : 0.f);
+    }
+}
+
+// ---- forward with asynchronous slab staging -----------------------------------------------------------------------------
+// Same arithmetic and the same per-warp lists as blend_fwd_kernel; what changes is how a batch reaches shared memory.
+// The tile's slab is an indirection (sorted ids -> records scattered over the splat arrays), so every thread copies
+// "its" splat of the NEXT batch with cp.async (LDGSTS: global -> shared without a register round trip, 8 B + 7 x 4 B from the
+// separate arrays, or 3 x 16 B from a [n,12] row buffer) into the second of two staging buffers while the warps blend the current
+// batch; the ids are prefetched two batches ahead in a register.  When a batch starts, its copies have landed long
+// ago (cp.async.wait_all + barrier), each thread post-processes its own record in place (conic pre-scaling, 8-bit block
+// mask) and the warps go on to the list compaction: the two dependent L2 round trips of the synchronous version
+// (id -> record) are off the critical path of the tile.
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// raw slot layout (floats): separate arrays -> {x, y, A, B | C, o, c0, c1 | c2, c3, -, -};  rows -> the 12 floats of the row
+// {x, y, depth, A | B, C, comp, o | r, g, b, radius}
+template <int CH, bool ROWS>
+__device__ __forceinline__ void stage_async(float4* slot, int g, const SplatStrides& st, const float* __restrict__ xy,
+                                            const float* __restrict__ conic, const float* __restrict__ opacity,
+                                            const float* __restrict__ colors) {
+    if (ROWS) {
+        const float* row = xy + int64_t(g) * st.xs;     // xy points at column 0 of the row buffer
+        cp_async16(slot, row);
+        cp_async16(slot + 1, row + 4);
+        cp_async16(slot + 2, row + 8);
+    } else {
+        float* f = reinterpret_cast<float*>(slot);
+        cp_async8(f, xy + int64_t(g) * st.xs);
+        const float* cq = conic + int64_t(g) * st.cs;
+        cp_async4(f + 2, cq);
+        cp_async4(f + 3, cq + 1);
+        cp_async4(f + 4, cq + 2);
+        cp_async4(f + 5, opacity + int64_t(g) * st.os);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) cp_async4(f + 6 + c, colors + int64_t(g) * st.ks + c);
+    }
+}
+
+template <int CH, bool GSPLAT, bool ROWS>
+__global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_async_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
+                                                              const int32_t* __restrict__ ids, const SplatStrides st, const float* __restrict__ xy,
+                                                              const float* __restrict__ conic, const float* __restrict__ opacity,
+                                                              const float* __restrict__ colors, const float* __restrict__ bg,
+                                                              float* __restrict__ image, int64_t pix_stride, int64_t ch_stride,
+                                                              float* __restrict__ final_T, int32_t* __restrict__ n_contrib,
+                                                              float* __restrict__ alpha_out) {
+    __shared__ float4 s_buf[2][(BLOCK_PIX + 1) * 3];
+    __shared__ unsigned char s_mask[BLOCK_PIX];
+    __shared__ unsigned short s_list[NWARP][BLOCK_PIX + 2 * LIST_PAD];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const unsigned lane = tid & 31u;
+    const int tile = blockIdx.y * grid_x + blockIdx.x;
+    int lx, ly;
+    pixel_of_thread(tid, lx, ly);
+    const int px = blockIdx.x * TILE + lx, py = blockIdx.y * TILE + ly;
+    const bool inside = (px < width) && (py < height);
+    const float off = GSPLAT ? 0.5f : 0.0f;
+    const float pxf = float(px) + off, pyf = float(py) + off;
+    const float ox = float(blockIdx.x * TILE) + off, oy = float(blockIdx.y * TILE) + off;
+    const float amax = GSPLAT ? 0.999f : 0.99f;
+    if (tid < 6) s_buf[tid / 3][DUMMY * 3 + tid % 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const int2 range = ranges[tile];
+    const int total = range.y - range.x;
+    bool done = !inside;
+    float T = 1.0f;
+    int last = 0;
+    float C[4] = {0.f, 0.f, 0.f, 0.f};
+
+    // prologue: batch 0 in flight, ids of batch 1 in a register
+    if (tid < total) stage_async<CH, ROWS>(&s_buf[0][tid * 3], __ldg(ids + range.x + tid), st, xy, conic, opacity, colors);
+    int next_id = (BLOCK_PIX + tid < total) ? __ldg(ids + range.x + BLOCK_PIX + tid) : 0;
+
+    int buf = 0;
+    for (int base = 0; base < total; base += BLOCK_PIX, buf ^= 1) {
+        cp_async_wait_all();
+        if (__syncthreads_and(done)) break;          // also: every thread's copies of this batch are visible
+        const int cnt = min(BLOCK_PIX, total - base);
+        float4* s_rec = s_buf[buf];
+        if (tid < cnt) {
+            const float4 q0 = s_rec[tid * 3 + 0], q1 = s_rec[tid * 3 + 1], q2 = s_rec[tid * 3 + 2];
+            float mx, my, A, B, Cc, o, c0, c1, c2, c3;
+            if (ROWS) { mx = q0.x; my = q0.y; A = q0.w; B = q1.x; Cc = q1.y; o = q1.w; c0 = q2.x; c1 = q2.y; c2 = q2.z; c3 = 0.f; }
+            else      { mx = q0.x; my = q0.y; A = q0.z; B = q0.w; Cc = q1.x; o = q1.y; c0 = q1.z; c1 = q1.w; c2 = q2.x; c3 = q2.y; }
+            s_rec[tid * 3 + 0] = make_float4(mx, my, (-0.5f * LOG2E) * A, -LOG2E * B);
+            s_rec[tid * 3 + 1] = make_float4((-0.5f * LOG2E) * Cc, o, c0, CH > 1 ? c1 : 0.f);
+            if (CH > 2) s_rec[tid * 3 + 2] = make_float4(c2, CH > 3 ? c3 : 0.f, 0.f, 0.f);
+            s_mask[tid] = (unsigned char)block_mask(mx, my, A, B, Cc, o, ox, oy);
+        }
+        // next batch: the other buffer was last read by the blend loop of the previous iteration, which every warp left
+        // before the barrier above
+        if (base + BLOCK_PIX + tid < total) stage_async<CH, ROWS>(&s_buf[buf ^ 1][tid * 3], next_id, st, xy, conic, opacity, colors);
+        next_id = (base + 2 * BLOCK_PIX + tid < total) ? __ldg(ids + range.x + base + 2 * BLOCK_PIX + tid) : 0;
+        __syncthreads();
+        if (__all_sync(FULL, done)) continue;  // warp finished: only keeps the block barriers company
+        const unsigned short* my_list = s_list[warp] + LIST_PAD;
+        const int nl = build_list(s_mask, s_list[warp], cnt, warp, lane);
+        for (int i0 = 0; i0 < nl; i0 += 4) {
+            if (__all_sync(FULL, done)) break;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = my_list[i0 + u];                 // entries past nl are DUMMY (alpha 0)
+                const float4 r0 = s_rec[j * 3 + 0];
+                const float4 r1 = s_rec[j * 3 + 1];
+                const float dx = r0.x - pxf, dy = r0.y - pyf;
+                const float p2 = fmaf(r1.x * dy, dy, fmaf(r0.w, dy, r0.z * dx) * dx);
+                const float a = fminf(amax, r1.y * ex2_approx(p2));
+                const float nT = fmaf(-a, T, T);
+                const bool ok = !done && !(p2 > 0.0f) && !(a < ALPHA_MIN);
+                const bool stop = ok && (GSPLAT ? (nT <= T_STOP) : (nT < T_STOP));
+                const bool take = ok && !stop;
+                const float w = take ? a * T : 0.f;
+                C[0] = fmaf(r1.z, w, C[0]);
+                if (CH > 1) C[1] = fmaf(r1.w, w, C[1]);
+                if (CH > 2) {
+                    const float2 r2 = *reinterpret_cast<const float2*>(&s_rec[j * 3 + 2]);
+                    C[2] = fmaf(r2.x, w, C[2]);
+                    if (CH > 3) C[3] = fmaf(r2.y, w, C[3]);
+                }
+                T = take ? nT : T;
+                last = take ? base + j + 1 : last;
+                done = done || stop;
+            }
+        }
+    }
+    cp_async_wait_all();
     if (inside) {
         const int64_t pix = int64_t(py) * width + px;
         final_T[pix] = T;
@@ -463,6 +611,216 @@ __global__ void __launch_bounds__(BLOCK_PIX, (RB == 4 && !ABS) ? 4 : 1) blend_bw
     }
 }
 
+// ---- backward, transpose-reduce variant (default) -----------------------------------------------------------------------
+// The butterfly above spends 63 of its 119 warp instructions per (warp, list entry) on moving nine partial sums between
+// lanes (SHFL issues at one warp instruction per clock per SM) and on a single writer lane.  Here each pixel lane only
+// produces TWO numbers per entry —  go = dL/d(opacity-weighted Gaussian)  and  fac = alpha*T  — and stores them as one
+// float2 into a per-warp shared-memory tile [GE entries][32 lanes].  After GE = 16 entries the roles flip: lane (e, h)
+// owns entry e and the 16 pixels of half h of the warp's 8x4 block, reads its row with 128-bit loads (rows are padded by
+// 16 B: conflict-free in both directions) and accumulates, in registers and with compile-time pixel coordinates as FFMA
+// immediates, the six coordinate moments of go (the mean/conic gradients are linear in them) and the colour sums
+// sum(fac * v_image[pixel]) (v_image of the warp's 32 pixels sits in shared memory, read as broadcasts).  One xor-16
+// exchange combines the halves; then lane (e, 0) finishes the mean/conic algebra of entry e and issues its 5 atomics
+// while lane (e, 1) issues opacity + colours: 16 entries are written by 32 lanes in parallel.  No shuffles in the
+// reduction, no serial writer: ~12 instead of 63 instructions per (warp, entry) after the evaluation.
+constexpr int GE = 16;                          // list entries per reduction group
+constexpr int VAL_ROW = 32 * 8 + 16;            // bytes per entry row of the value tile: 32 x {go, fac} + pad
+constexpr int BWD_LIST = BLOCK_PIX + GE + 8;    // per-warp list: GE dummies in front (reverse walk), 8 behind
+
+struct TrSmem {
+    float4 rec[(BLOCK_PIX + 1) * 3];
+    float4 vo[NWARP][32];
+    unsigned char val[NWARP][GE * VAL_ROW];
+    unsigned short list[NWARP][BWD_LIST];
+    unsigned char mask[BLOCK_PIX];
+    int wmax[NWARP];
+};
+static_assert(sizeof(TrSmem) <= 57344, "4 CTAs per SM need <= 56 KB each");
+
+template <int CH, bool GSPLAT>
+__global__ void __launch_bounds__(BLOCK_PIX, 4) blend_bwd_tr_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
+                                                                    const int32_t* __restrict__ ids, const SplatStrides st,
+                                                                    const float* __restrict__ xy, const float* __restrict__ conic,
+                                                                    const float* __restrict__ opacity, const float* __restrict__ colors,
+                                                                    const float* __restrict__ bg, const float* __restrict__ final_T,
+                                                                    const int32_t* __restrict__ n_contrib, const float* __restrict__ v_image,
+                                                                    int64_t pix_stride, int64_t ch_stride, const float* __restrict__ v_alpha,
+                                                                    float sx, float sy, float* __restrict__ v_xy, float* __restrict__ v_conic,
+                                                                    float* __restrict__ v_opacity, float* __restrict__ v_colors) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TrSmem& sm = *reinterpret_cast<TrSmem*>(smem_raw);
+    float4* s_rec = sm.rec;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const unsigned lane = tid & 31u;
+    const int tile = blockIdx.y * grid_x + blockIdx.x;
+    int lx, ly;
+    pixel_of_thread(tid, lx, ly);
+    const int px = blockIdx.x * TILE + lx, py = blockIdx.y * TILE + ly;
+    const bool inside = (px < width) && (py < height);
+    const float off = GSPLAT ? 0.5f : 0.0f;
+    const float pxf = float(px) + off, pyf = float(py) + off;
+    const float ox = float(blockIdx.x * TILE) + off, oy = float(blockIdx.y * TILE) + off;
+    const float amax = GSPLAT ? 0.999f : 0.99f;
+    const int64_t pix = int64_t(py) * width + px;
+    if (tid < 3) s_rec[DUMMY * 3 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const int2 range = ranges[tile];
+    const float Tf = inside ? final_T[pix] : 0.f;
+    const int last = inside ? n_contrib[pix] : 0;
+    float vo[4] = {0.f, 0.f, 0.f, 0.f};
+    float bg_dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        vo[c] = inside ? __ldg(v_image + pix * pix_stride + c * ch_stride) : 0.f;
+        if (bg) bg_dot += __ldg(bg + c) * vo[c];
+    }
+    sm.vo[warp][lane] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+    const float va = (v_alpha && inside) ? __ldg(v_alpha + pix) : 0.f;
+    const float tail = Tf * (va - bg_dot);  // d(out)/d(alpha_i) through everything behind the last contributor
+
+    const int wmax = __reduce_max_sync(FULL, last);
+    if (lane == 0) sm.wmax[warp] = wmax;
+    __syncthreads();
+    int max_last = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) max_last = max(max_last, sm.wmax[w]);
+    if (max_last == 0) return;
+
+    float T = Tf;
+    float D = 0.f;   // <colour accumulated behind the current splat, v_image> for this pixel
+    unsigned char* my_val = sm.val[warp] + lane * 8;              // eval phase: this pixel's {go, fac} column
+    const int re = lane & (GE - 1), rh = lane >> 4;               // reduce phase: entry and pixel half of this lane
+    const float4* my_row = reinterpret_cast<const float4*>(sm.val[warp] + re * VAL_ROW + rh * 128);
+    const float4* my_vo = sm.vo[warp] + rh * 16;
+    // origin of the warp's 8x4 block of pixel samples; the reduce lane's pixels are rows 2 rh, 2 rh + 1 of it
+    const float bx0 = ox + float((warp & 1) << 3), by0 = oy + float((warp >> 1) << 2);
+    const float hh = float(2 * rh);
+
+    for (int hi = max_last; hi > 0; hi -= BLOCK_PIX) {
+        const int lo = max(0, hi - BLOCK_PIX);
+        const int cnt = hi - lo;
+        __syncthreads();
+        if (tid < cnt) {
+            const int g = __ldg(ids + range.x + lo + tid);
+            const float2 m = __ldg(reinterpret_cast<const float2*>(xy + int64_t(g) * st.xs));
+            const float* cq = conic + int64_t(g) * st.cs;
+            const float A = __ldg(cq), B = __ldg(cq + 1), Cc = __ldg(cq + 2);
+            const float o = __ldg(opacity + int64_t(g) * st.os);
+            float col[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * st.ks + c);
+            s_rec[tid * 3 + 0] = make_float4(m.x, m.y, (-0.5f * LOG2E) * A, -LOG2E * B);
+            s_rec[tid * 3 + 1] = make_float4((-0.5f * LOG2E) * Cc, o, col[0], col[1]);
+            s_rec[tid * 3 + 2] = make_float4(col[2], col[3], __int_as_float(g), 0.f);
+            sm.mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
+        }
+        __syncthreads();
+        if (wmax <= lo) continue;  // this warp has no contributor in the batch
+        const unsigned short* my_list = sm.list[warp] + GE;   // my_list[-GE..-1] are DUMMY
+        const int nl = build_list<GE>(sm.mask, sm.list[warp], min(cnt, wmax - lo), warp, lane);
+        const int rel_last = last - lo;                        // entry j of this batch is in front of the pixel's last contributor iff j < rel_last
+        for (int ii = nl - 1; ii >= 0; ii -= GE) {
+            unsigned vm = 0;   // bit u: this pixel has a valid sample of list entry ii-u
+#pragma unroll
+            for (int u = 0; u < GE; ++u) {
+                const int j = my_list[ii - u];
+                const float4 r0 = s_rec[j * 3 + 0];
+                const float4 r1 = s_rec[j * 3 + 1];
+                const float dx = r0.x - pxf, dy = r0.y - pyf;
+                // same arithmetic as the forward: power * log2(e) = a' dx^2 + b' dx dy + c' dy^2
+                const float p2 = fmaf(r1.x * dy, dy, fmaf(r0.w, dy, r0.z * dx) * dx);
+                const float G = ex2_approx(p2);
+                const float oG = r1.y * G;
+                const float a = fminf(amax, oG);
+                const bool valid = (j < rel_last) && !(p2 > 0.0f) && (a >= ALPHA_MIN);
+                float go = 0.f, fac = 0.f;
+                if (valid) {
+                    const float ra = 1.0f / (1.0f - a);
+                    T *= ra;
+                    fac = a * T;
+                    float S = r1.z * vo[0];
+                    if (CH > 1) S = fmaf(r1.w, vo[1], S);
+                    if (CH > 2) {
+                        const float2 r2 = *reinterpret_cast<const float2*>(&s_rec[j * 3 + 2]);
+                        S = fmaf(r2.x, vo[2], S);
+                        if (CH > 3) S = fmaf(r2.y, vo[3], S);
+                    }
+                    // dL/dalpha = T <c, v> - (<colour behind, v> + T_final (bg.v - v_alpha)) / (1 - alpha);  D = <colour behind, v>
+                    const float v_al = fmaf(T, S, ra * (tail - D));
+                    D = fmaf(fac, S, D);
+                    if (!GSPLAT || (oG <= 0.999f)) go = G * v_al;
+                    vm |= 1u << u;
+                }
+                *reinterpret_cast<float2*>(my_val + u * VAL_ROW) = make_float2(go, fac);
+            }
+            const unsigned present = __reduce_or_sync(FULL, vm);
+            __syncwarp();   // the tile stores of all lanes are visible to the row loads below
+            if (present != 0u) {
+                // ---- reduce: lane (re, rh) sums entry ii-re over pixels 16 rh .. 16 rh + 15 (local x = k & 7, local row = k >> 3)
+                float R0 = 0.f, R0x = 0.f, R0xx = 0.f, R1 = 0.f, R1x = 0.f, R1xx = 0.f;
+                float Cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) {
+                    const float4 v = my_row[k2];          // {go, fac} of pixels 2 k2, 2 k2 + 1
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int k = 2 * k2 + e;
+                        const float gk = e ? v.z : v.x, fk = e ? v.w : v.y;
+                        const float x = float(k & 7);
+                        if (k < 8) { R0 += gk; if (k & 7) { R0x = fmaf(gk, x, R0x); R0xx = fmaf(gk, x * x, R0xx); } }
+                        else       { R1 += gk; if (k & 7) { R1x = fmaf(gk, x, R1x); R1xx = fmaf(gk, x * x, R1xx); } }
+                        const float4 w = my_vo[k];
+                        Cs[0] = fmaf(fk, w.x, Cs[0]);
+                        if (CH > 1) Cs[1] = fmaf(fk, w.y, Cs[1]);
+                        if (CH > 2) Cs[2] = fmaf(fk, w.z, Cs[2]);
+                        if (CH > 3) Cs[3] = fmaf(fk, w.w, Cs[3]);
+                    }
+                }
+                // moments in block coordinates (x = 0..7, y = 2 rh + {0, 1}), then both halves
+                float S0 = R0 + R1, Sx = R0x + R1x, Sxx = R0xx + R1xx;
+                float Sy = fmaf(hh, S0, R1), Sxy = fmaf(hh, Sx, R1x), Syy = fmaf(hh * hh, S0, fmaf(2.0f * hh, R1, R1));
+                S0 += __shfl_xor_sync(FULL, S0, 16);
+                Sx += __shfl_xor_sync(FULL, Sx, 16);
+                Sy += __shfl_xor_sync(FULL, Sy, 16);
+                Sxx += __shfl_xor_sync(FULL, Sxx, 16);
+                Sxy += __shfl_xor_sync(FULL, Sxy, 16);
+                Syy += __shfl_xor_sync(FULL, Syy, 16);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) Cs[c] += __shfl_xor_sync(FULL, Cs[c], 16);
+                if ((present >> re) & 1u) {
+                    const int j = my_list[ii - re];
+                    const int g = __float_as_int(s_rec[j * 3 + 2].z);
+                    if (rh == 0) {
+                        const float4 r0 = s_rec[j * 3 + 0];
+                        const float4 r1 = s_rec[j * 3 + 1];
+                        const float A = r0.z * (-2.0f / LOG2E), B = r0.w * (-1.0f / LOG2E), Cc = r1.x * (-2.0f / LOG2E);
+                        const float ex = r0.x - bx0, ey = r0.y - by0;   // dx = ex - x, dy = ey - y
+                        const float no = -r1.y;                        // dL/dsigma = -opacity * go
+                        const float M1 = no * fmaf(ex, S0, -Sx), M2 = no * fmaf(ey, S0, -Sy);
+                        const float M3 = no * fmaf(ex, fmaf(ex, S0, -2.0f * Sx), Sxx);
+                        const float M4 = no * (fmaf(ex, fmaf(ey, S0, -Sy), Sxy) - ey * Sx);
+                        const float M5 = no * fmaf(ey, fmaf(ey, S0, -2.0f * Sy), Syy);
+                        float* vx = v_xy + int64_t(g) * st.xs;
+                        float* vc = v_conic + int64_t(g) * st.cs;
+                        atomicAdd(vx, (A * M1 + B * M2) * sx);
+                        atomicAdd(vx + 1, (B * M1 + Cc * M2) * sy);
+                        atomicAdd(vc, 0.5f * M3);
+                        atomicAdd(vc + 1, M4);
+                        atomicAdd(vc + 2, 0.5f * M5);
+                    } else {
+                        atomicAdd(v_opacity + int64_t(g) * st.os, S0);
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) atomicAdd(v_colors + int64_t(g) * st.ks + c, Cs[c]);
+                    }
+                }
+            }
+            __syncwarp();   // the rows are read: the next group may overwrite the tile
+        }
+    }
+}
+
 // ---- backward, tensor-core reduction variant -------------------------------------------------------------------------
 // The cross-lane reduction of the backward IS a small dense contraction: for the 8 list entries of a group, every
 // output is  sum_over_the_32_pixel_lanes( weight[row][lane] * value[lane][entry] )  with weights that are FIXED for the warp:
@@ -706,6 +1064,25 @@ int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
     const int gx = div_up(width, TILE), gy = div_up(height, TILE);
     dim3 grid(gx, gy);
     const SplatStrides st = row_stride > 0 ? SplatStrides{row_stride, row_stride, row_stride, row_stride} : SplatStrides{2, 3, 1, CH};
+    // default: asynchronous (cp.async, double-buffered) slab staging; B200GS_FWD_SYNC=1 selects the synchronous kernel for A/B runs
+    static const bool use_sync = []() { const char* e = getenv("B200GS_FWD_SYNC"); return e && e[0] == '1'; }();
+    // the row layout is [x, y, depth, A, B, C, comp, opacity, r, g, b, radius] (include/b200gs.h); 16-byte copies need 16-byte aligned rows
+    const bool rows16 = row_stride == 12 && CH == 3 && conic == xy + 3 && opacity == xy + 7 && colors == xy + 8 && (reinterpret_cast<uintptr_t>(xy) & 15) == 0;
+    if (!use_sync) {
+#define B200GS_FWD_ARGS width, height, gx, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, image, ps, cs, final_T, n_contrib, alpha
+        if (rows16) {
+            if constexpr (CH == 3) {
+                if (mode == B200GS_MODE_GSPLAT) blend_fwd_async_kernel<CH, true, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_FWD_ARGS);
+                else blend_fwd_async_kernel<CH, false, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_FWD_ARGS);
+            }
+        } else {
+            if (mode == B200GS_MODE_GSPLAT) blend_fwd_async_kernel<CH, true, false><<<grid, BLOCK_PIX, 0, s>>>(B200GS_FWD_ARGS);
+            else blend_fwd_async_kernel<CH, false, false><<<grid, BLOCK_PIX, 0, s>>>(B200GS_FWD_ARGS);
+        }
+#undef B200GS_FWD_ARGS
+        B200GS_LAUNCH_CHECK();
+        return B200GS_OK;
+    }
     if (mode == B200GS_MODE_GSPLAT)
         blend_fwd_kernel<CH, true><<<grid, BLOCK_PIX, 0, s>>>(width, height, gx, (const int2*)ranges, ids, st, xy, conic,
                                                               opacity, colors, bg, image, ps, cs, final_T, n_contrib, alpha);
@@ -749,6 +1126,27 @@ int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
             B200GS_LAUNCH_CHECK();
             return B200GS_OK;
         }
+    }
+    // default: transpose-reduce kernel (no absgrad side channel); B200GS_BWD_BUTTERFLY=1 selects the shuffle butterfly for A/B runs
+    static const bool use_butterfly = []() { const char* e = getenv("B200GS_BWD_BUTTERFLY"); return e && e[0] == '1'; }();
+    if (!v_xy_abs && !use_butterfly && !use_mma) {
+        static const cudaError_t attr_rc = []() {
+            cudaError_t e = cudaFuncSetAttribute(blend_bwd_tr_kernel<CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrSmem));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(blend_bwd_tr_kernel<CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrSmem));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(blend_bwd_tr_kernel<CH, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(blend_bwd_tr_kernel<CH, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            return e;
+        }();
+        if (attr_rc != cudaSuccess) {
+            set_error("blend_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_rc));
+            return B200GS_ECUDA;
+        }
+        if (mode == B200GS_MODE_GSPLAT)
+            blend_bwd_tr_kernel<CH, true><<<grid, BLOCK_PIX, sizeof(TrSmem), s>>>(B200GS_BWD_MMA_ARGS);
+        else
+            blend_bwd_tr_kernel<CH, false><<<grid, BLOCK_PIX, sizeof(TrSmem), s>>>(B200GS_BWD_MMA_ARGS);
+        B200GS_LAUNCH_CHECK();
+        return B200GS_OK;
     }
     if (mode == B200GS_MODE_GSPLAT) {
         if (v_xy_abs)

@@ -9,6 +9,7 @@
 namespace b200gs {
 
 void set_error(const char* fmt, ...);
+void count_launch();   // every kernel launch of the library is counted (b200gs_launch_count): B200GS_LAUNCH_CHECK follows each <<<>>>
 
 #define B200GS_CHECK_ARG(cond, msg)                                  \
     do {                                                              \
@@ -29,6 +30,7 @@ void set_error(const char* fmt, ...);
 
 #define B200GS_LAUNCH_CHECK()                                                                  \
     do {                                                                                       \
+        b200gs::count_launch();                                                                \
         cudaError_t _e = cudaGetLastError();                                                   \
         if (_e != cudaSuccess) {                                                               \
             b200gs::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(_e)); \

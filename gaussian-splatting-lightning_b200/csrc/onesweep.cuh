@@ -1,0 +1,186 @@
+// Hand-written device-wide primitives of the tile binning (no cub): a single-pass chained scan (decoupled look-back on
+// one value per block) and a stable LSD radix sort in the onesweep style — one histogram kernel for all digits, then one
+// kernel per 8-bit digit in which every tile ranks its records with warp match/ballot, publishes its digit counts,
+// obtains its global offsets by looking back over the preceding tiles' counts, and scatters through a shared-memory
+// staging area so that the global writes are runs of consecutive addresses.
+//
+// Records carry their key inside (a uint2 {depth key, Gaussian id} for the depth sort, a uint4 {tile mask lo, hi, id,
+// coarse cell} for the partition by cell), so keys and payload move as one 8- or 16-byte vector.
+// The number of records may be known only on the device (`d_n`): grids are sized for the capacity and surplus tiles exit.
+#pragma once
+#include "common.cuh"
+
+namespace b200gs {
+namespace sweep {
+
+constexpr int RADIX = 256;
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr uint32_t FLAG_AGG = 1u << 30, FLAG_PREFIX = 2u << 30, VALUE_MASK = (1u << 30) - 1u;
+
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// Wait until a look-back word has been published.  Tiles take tickets in launch order, so the tile that owns the word is
+// already running; the bound only turns a logic error (a word that is never published) into a trap instead of a hang.
+__device__ __forceinline__ uint32_t wait_published(const uint32_t* p) {
+    uint32_t v = ld_volatile(p);
+    for (unsigned spins = 0; (v >> 30) == 0u; ++spins) {
+        if (spins > (1u << 27)) asm volatile("trap;");
+        v = ld_volatile(p);
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint32_t key_of(const uint2& r) { return r.x; }
+__device__ __forceinline__ uint32_t key_of(const uint4& r) { return r.w; }
+
+// ---- chained scan --------------------------------------------------------------------------------------------------
+// Exclusive prefix of one 30-bit value per tile over the tiles in ticket order.  `state[t]` must be zero before the launch.
+// Called by one thread; returns the sum of the values of tiles 0..t-1.
+__device__ __forceinline__ uint32_t chained_exclusive(uint32_t* state, int t, uint32_t value) {
+    st_volatile(state + t, (value & VALUE_MASK) | (t == 0 ? FLAG_PREFIX : FLAG_AGG));
+    uint32_t excl = 0;
+    for (int p = t - 1; p >= 0; --p) {
+        const uint32_t v = wait_published(state + p);
+        excl += v & VALUE_MASK;
+        if (v & FLAG_PREFIX) break;
+    }
+    if (t > 0) st_volatile(state + t, ((excl + value) & VALUE_MASK) | FLAG_PREFIX);
+    return excl;
+}
+
+// block-wide exclusive scan of one int per thread (THREADS threads); returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ int block_exclusive(int v, int* s_warp /*[WARPS + 1]*/, int* total) {
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < WARPS; ++k) {
+        const int c = s_warp[k];
+        base += (k < (int)w) ? c : 0;
+        tot += c;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+// ---- histogram of the four digits of uint2 records ------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) hist4_kernel(const uint2* __restrict__ recs, const int64_t* __restrict__ d_n, int64_t cap,
+                                                       uint32_t* __restrict__ hist /*[4][RADIX]*/) {
+    __shared__ uint32_t s_h[4][RADIX];
+    const int64_t n = d_n ? min(cap, *d_n) : cap;
+    for (int i = threadIdx.x; i < 4 * RADIX; i += THREADS) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    for (int64_t i = int64_t(blockIdx.x) * THREADS + threadIdx.x; i < n; i += int64_t(gridDim.x) * THREADS) {
+        const uint32_t k = recs[i].x;
+        atomicAdd(&s_h[0][k & 255u], 1u);
+        atomicAdd(&s_h[1][(k >> 8) & 255u], 1u);
+        atomicAdd(&s_h[2][(k >> 16) & 255u], 1u);
+        atomicAdd(&s_h[3][k >> 24], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * RADIX; i += THREADS) {
+        const uint32_t c = (&s_h[0][0])[i];
+        if (c) atomicAdd(hist + i, c);
+    }
+}
+
+// ---- one digit pass ----------------------------------------------------------------------------------------------------
+// hist[RADIX]: global count of every digit value of this pass; lookback[tiles][RADIX] and *ticket zero before the launch.
+template <typename Rec, int IPT>
+__global__ void __launch_bounds__(THREADS) onesweep_pass_kernel(const Rec* __restrict__ in, Rec* __restrict__ out, const int64_t* __restrict__ d_n,
+                                                               int64_t cap, int shift, const uint32_t* __restrict__ hist,
+                                                               uint32_t* __restrict__ lookback, uint32_t* __restrict__ ticket) {
+    constexpr int TILE_ITEMS = THREADS * IPT;
+    __shared__ uint32_t s_cnt[WARPS][RADIX];     // per-warp digit counts -> exclusive offsets of the warp inside the tile's digit run
+    __shared__ int s_base[RADIX];                // global index of the tile's first record of a digit, minus its slot in the tile
+    __shared__ int s_scan[WARPS + 1];
+    __shared__ int s_tile;
+    __shared__ Rec s_stage[TILE_ITEMS];
+    const int64_t n = d_n ? min(cap, *d_n) : cap;
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, w = tid >> 5;
+    if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    for (int i = tid; i < WARPS * RADIX; i += THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int t = s_tile;
+    const int64_t tile_lo = int64_t(t) * TILE_ITEMS;
+    if (tile_lo >= n) return;
+    const int tile_n = (int)min((int64_t)TILE_ITEMS, n - tile_lo);
+
+    Rec rec[IPT];
+    int dig[IPT];      // 0..255, or 256 for the slots past the end
+    int rank[IPT];
+    uint32_t* my_cnt = s_cnt[w];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const int local = (int)w * (32 * IPT) + i * 32 + (int)lane;
+        const bool valid = local < tile_n;
+        if (valid) rec[i] = in[tile_lo + local];
+        dig[i] = valid ? (int)((key_of(rec[i]) >> shift) & 255u) : 256;
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const unsigned peers = __match_any_sync(0xffffffffu, dig[i]);
+        const int lt = __popc(peers & ((1u << lane) - 1u));
+        uint32_t before = 0;
+        if (dig[i] < 256) before = my_cnt[dig[i]];
+        __syncwarp();
+        if (dig[i] < 256 && lt == 0) my_cnt[dig[i]] = before + __popc(peers);
+        __syncwarp();
+        rank[i] = (int)before + lt;
+    }
+    __syncthreads();
+    // thread d owns digit d: offsets of the warps inside the digit's run, the tile's count, the look-back
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < WARPS; ++k) {
+        const uint32_t c = s_cnt[k][tid];
+        s_cnt[k][tid] = run;
+        run += c;
+    }
+    uint32_t before_tiles = 0;
+    {
+        uint32_t* col = lookback + tid;                                    // lookback[p * RADIX + d]
+        st_volatile(col + int64_t(t) * RADIX, (run & VALUE_MASK) | (t == 0 ? FLAG_PREFIX : FLAG_AGG));
+        for (int p = t - 1; p >= 0; --p) {
+            const uint32_t v = wait_published(col + int64_t(p) * RADIX);
+            before_tiles += v & VALUE_MASK;
+            if (v & FLAG_PREFIX) break;
+        }
+        if (t > 0) st_volatile(col + int64_t(t) * RADIX, ((before_tiles + run) & VALUE_MASK) | FLAG_PREFIX);
+    }
+    int tot;
+    const int digit_start = block_exclusive((int)hist[tid], s_scan, &tot);   // first global index of digit d
+    const int tile_start = block_exclusive((int)run, s_scan, &tot);          // first slot of digit d in the staged tile
+    s_base[tid] = digit_start + (int)before_tiles - tile_start;
+    // slot of a record = tile_start[d] + warp offset + rank; fold tile_start into the warp offsets
+#pragma unroll
+    for (int k = 0; k < WARPS; ++k) s_cnt[k][tid] += (uint32_t)tile_start;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+        if (dig[i] < 256) s_stage[my_cnt[dig[i]] + rank[i]] = rec[i];
+    __syncthreads();
+    for (int s = tid; s < tile_n; s += THREADS) {
+        const Rec r = s_stage[s];
+        const int d = (int)((key_of(r) >> shift) & 255u);
+        out[s_base[d] + s] = r;
+    }
+}
+
+}  // namespace sweep
+}  // namespace b200gs

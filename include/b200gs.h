@@ -75,6 +75,8 @@ typedef struct B200gsView {
 
 B200GS_API const char* b200gs_last_error(void);
 B200GS_API int b200gs_version(void);
+/* number of CUDA kernels this library has launched in this process (monotonic; every launch site increments it) */
+B200GS_API int64_t b200gs_launch_count(void);
 
 /* ---- K1: per-Gaussian projection (+ optional fused SH colour) ------------------------------------------------
  * replaces dgr preprocessCUDA / gsplat project_gaussians (+ spherical_harmonics when shs != NULL).
@@ -128,15 +130,16 @@ B200GS_API int b200gs_sh_bwd(int32_t degree, int32_t sh_stride, int64_t n, const
 /* ---- K2-K5: tile binning ------------------------------------------------------------------------------------------
  * replaces dgr InclusiveSum + duplicateWithKeys + SortPairs + identifyTileRanges / gsplat isect_tiles + isect_offset_encode.
  * Result order is exactly that of a stable sort of (tile_id << 32 | float_bits(depth)) keys emitted Gaussian-major:
- * implemented as a stable depth sort of the Gaussians, a stable partition of (coarse cell, Gaussian) pairs (a cell =
- * 8x8 tiles) and an order-preserving multi-split of every cell's list into its 64 tiles that writes each id once.
+ * implemented as a stable depth sort of the visible Gaussians, a stable partition of (coarse cell, Gaussian) pairs (a
+ * cell = 8x8 tiles) and an order-preserving multi-split of every cell's list into its 64 tiles that writes each id
+ * once.  Both sorts are hand-written onesweep-style radix passes (decoupled look-back); no library sort is involved.
  *
  * Counters: d_counts = device int64[4], host_counts = host int64[4] (pinned or pageable; nullable):
  *     [0] number of (tile, Gaussian) pairs of the 3-sigma bounding rects — the reference's pair count, an upper bound
  *         of [2] and equal to it without culling                                              (written by phase A)
  *     [1] number of (coarse cell, Gaussian) pairs                                              (written by phase A)
  *     [2] number of pairs actually listed in sorted_ids / tile_ranges                          (written by phase B)
- *     [3] reserved (0)
+ *     [3] number of visible Gaussians (non-empty tile rect)                                    (written by phase A)
  *   Each phase ends by delivering d_counts to host_counts (when != NULL) in stream order — pinned/mapped host memory is
  *   written by a tiny kernel with system-scope stores (a D2H copy would queue on a copy engine behind the application's
  *   bulk transfers), pageable memory by cudaMemcpyAsync — and, when sync_host != 0, SYNCHRONISES the stream.
@@ -150,7 +153,7 @@ B200GS_API int b200gs_sh_bwd(int32_t degree, int32_t sh_stride, int64_t n, const
  *     (every tile of the 3-sigma bounding rect).
  * b200gs_bin_count_workspace_bytes / b200gs_bin_sort_workspace_bytes: bytes of scratch for phase A (n Gaussians) and
  *     phase B (up to max_coarse coarse pairs).  Two buffers because counts[1] is only known after phase A.
- * b200gs_bin_count: phase A.  Depth keys, stable depth sort, scan of cells-per-Gaussian; counts[0], counts[1].  Everything
+ * b200gs_bin_count: phase A.  Compaction of the visible Gaussians, depth keys, stable depth sort; counts[0], [1], [3].  Everything
  *     phase B needs to know about a Gaussian (xy, radius, cull_conic, cull_opacity) is packed into workspace_a, which
  *     must stay untouched until phase B has been enqueued.
  * b200gs_bin_sort: phase B (reads workspace_a only; cull = whether phase A was given the cull arrays).  Writes sorted_ids (Gaussian ids, front to back inside each tile; capacity max_pairs),
