@@ -132,6 +132,104 @@ int b200gs_project_bwd_rows(const B200gsView* view, int64_t n, const float* mean
                                   accumulate);
 }
 
+static int check_views(const B200gsView* views, int32_t n_views) {
+    if (views == nullptr) { set_error("views is NULL"); return B200GS_EINVAL; }
+    if (n_views < 1 || n_views > B200GS_MAX_VIEWS) { set_error("n_views %d out of range (1..%d)", n_views, B200GS_MAX_VIEWS); return B200GS_EINVAL; }
+    for (int j = 0; j < n_views; ++j) {
+        int rc = check_view(views + j, true);
+        if (rc) return rc;
+        if (views[j].mode != B200GS_MODE_GSPLAT) { set_error("multi-view projection supports gsplat constants only"); return B200GS_EINVAL; }
+        if (views[j].sh_degree != views[0].sh_degree || views[j].sh_stride != views[0].sh_stride) {
+            set_error("all views of a multi-view launch must share sh_degree / sh_stride");
+            return B200GS_EINVAL;
+        }
+    }
+    return B200GS_OK;
+}
+
+int b200gs_project_fwd_raw_multi(const B200gsView* views, int32_t n_views, int64_t n, const float* means, const float* log_scales,
+                                 const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
+                                 int32_t anti_aliased, float* xy, float* depth, int32_t* radii, float* conic, float* rgb, uint8_t* clamped,
+                                 float* opacity_out, void* stream) {
+    int rc = check_views(views, n_views);
+    if (rc) return rc;
+    B200GS_CHECK_ARG(n >= 0, "n < 0");
+    if (n > 0) {
+        B200GS_CHECK_ARG(means && log_scales && raw_quats && opacity_logits && shs_dc, "NULL input pointer");
+        B200GS_CHECK_ARG(views[0].sh_stride == 1 || shs_rest, "shs_rest required when sh_stride > 1");
+        B200GS_CHECK_ARG(xy && depth && radii && conic && rgb && clamped && opacity_out, "NULL output pointer");
+    }
+    return launch_project_fwd_multi(views, n_views, n, means, log_scales, raw_quats, opacity_logits, shs_dc, shs_rest, anti_aliased, xy, depth,
+                                    radii, conic, rgb, clamped, opacity_out, (cudaStream_t)stream);
+}
+
+int b200gs_project_bwd_rows_multi(const B200gsView* views, int32_t n_views, int64_t n, const float* means, const float* log_scales,
+                                  const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
+                                  int32_t anti_aliased, const int32_t* radii, const uint8_t* clamped, const int32_t* row_index,
+                                  const float* const* v_rows, float* v_means, float* v_log_scales, float* v_raw_quats,
+                                  float* v_opacity_logits, float* v_shs_dc, float* v_shs_rest, void* stream) {
+    int rc = check_views(views, n_views);
+    if (rc) return rc;
+    B200GS_CHECK_ARG(n >= 0, "n < 0");
+    if (n > 0) {
+        B200GS_CHECK_ARG(means && log_scales && raw_quats && opacity_logits && shs_dc && radii && clamped && row_index && v_rows, "NULL input pointer");
+        B200GS_CHECK_ARG(views[0].sh_stride == 1 || (shs_rest && v_shs_rest), "shs_rest / v_shs_rest required when sh_stride > 1");
+        B200GS_CHECK_ARG(v_means && v_log_scales && v_raw_quats && v_opacity_logits && v_shs_dc, "NULL output pointer");
+    }
+    return launch_project_bwd_multi(views, n_views, n, means, log_scales, raw_quats, opacity_logits, shs_dc, shs_rest, anti_aliased, radii, clamped,
+                                    row_index, v_rows, v_means, v_log_scales, v_raw_quats, v_opacity_logits, v_shs_dc, v_shs_rest,
+                                    (cudaStream_t)stream);
+}
+
+int b200gs_pack_rows_peer(int64_t n, int64_t segment_len, int64_t segment_cap, const float* xy, const float* depth, const float* conic,
+                          const float* comp, const float* opacity, const float* rgb, const int32_t* radii, void* workspace, size_t workspace_bytes,
+                          int32_t* row_index, float* const* peer_rows, int64_t peer_block, int64_t* d_count, void* stream) {
+    B200GS_CHECK_ARG(n >= 0 && segment_len > 0 && segment_cap > 0 && peer_block >= 0, "bad sizes");
+    B200GS_CHECK_ARG(peer_rows != nullptr && d_count != nullptr, "peer_rows / d_count must not be NULL");
+    if (n > 0) {
+        B200GS_CHECK_ARG(xy && depth && conic && opacity && rgb && radii && row_index && workspace, "NULL pointer");
+        B200GS_CHECK_ARG(workspace_bytes >= pack_rows_workspace_bytes(n), "workspace too small");
+        for (int64_t j = 0; j < (n + segment_len - 1) / segment_len; ++j) B200GS_CHECK_ARG(j >= B200GS_MAX_VIEWS || peer_rows[j] != nullptr, "NULL peer buffer");
+    }
+    return pack_rows(n, segment_len, segment_cap, xy, depth, conic, comp, opacity, rgb, radii, workspace, workspace_bytes, row_index, nullptr,
+                     d_count, (cudaStream_t)stream, peer_rows, peer_block);
+}
+
+int b200gs_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+    B200GS_CHECK_ARG(dev_ptr != nullptr && handle64 != nullptr && bytes > 0, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    void* p = nullptr;
+    B200GS_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("b200gs_ipc_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return B200GS_ECUDA;
+    }
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return B200GS_OK;
+}
+
+int b200gs_ipc_open(const unsigned char* handle64, void** dev_ptr) {
+    B200GS_CHECK_ARG(dev_ptr != nullptr && handle64 != nullptr, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    B200GS_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200GS_OK;
+}
+
+int b200gs_ipc_close(void* dev_ptr) {
+    if (dev_ptr) B200GS_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return B200GS_OK;
+}
+
+int b200gs_ipc_free(void* dev_ptr) {
+    if (dev_ptr) B200GS_CUDA(cudaFree(dev_ptr));
+    return B200GS_OK;
+}
+
 int b200gs_sh_fwd(int32_t degree, int32_t sh_stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, void* stream) {
     B200GS_CHECK_ARG(degree >= 0 && degree <= 3, "degree must be 0..3");
     B200GS_CHECK_ARG(sh_stride >= (degree + 1) * (degree + 1), "sh_stride < (degree+1)^2");

@@ -89,6 +89,13 @@ int launch_project_bwd_raw(const B200gsView& v, int64_t n, const float* means, c
                            const float* v_conic, const float* v_comp, const float* v_rgb, const float* v_opac, float* v_means,
                            float* v_scales, float* v_quats, float* v_opac_logit, float* v_shs_dc, float* v_shs_rest,
                            cudaStream_t s, const float* v_rows = nullptr, const int32_t* row_offsets = nullptr, int accumulate = 0);
+int launch_project_fwd_multi(const B200gsView* views, int n_views, int64_t n, const float* means, const float* scales, const float* quats,
+                             const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased, float* xy, float* depth,
+                             int32_t* radii, float* conic, float* rgb, uint8_t* clamped, float* opac_out, cudaStream_t s);
+int launch_project_bwd_multi(const B200gsView* views, int n_views, int64_t n, const float* means, const float* scales, const float* quats,
+                             const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased, const int32_t* radii,
+                             const uint8_t* clamped, const int32_t* row_index, const float* const* v_rows, float* v_means, float* v_scales,
+                             float* v_quats, float* v_opac_logit, float* v_shs_dc, float* v_shs_rest, cudaStream_t s);
 int launch_sh_fwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, cudaStream_t s);
 int launch_sh_bwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, const float* v_rgb,
                   float* v_coeffs, float* v_dirs, cudaStream_t s);
@@ -102,7 +109,7 @@ int publish_i64(const int64_t* d_values, int64_t* host_values, int n, cudaStream
 size_t pack_rows_workspace_bytes(int64_t n);
 int pack_rows(int64_t n, int64_t seg_len, int64_t seg_cap, const float* xy, const float* depth, const float* conic, const float* comp,
               const float* opacity, const float* rgb, const int32_t* radii, void* ws, size_t ws_bytes, int32_t* row_index, float* rows,
-              int64_t* d_count, cudaStream_t s);
+              int64_t* d_count, cudaStream_t s, float* const* peer_rows = nullptr, int64_t peer_block = 0);
 int unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offsets, const float* v_rows, float* v_xy, float* v_depth,
                      float* v_conic, float* v_comp, float* v_opacity, float* v_rgb, cudaStream_t s);
 int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_coarse, int64_t max_pairs, int64_t* d_counts,

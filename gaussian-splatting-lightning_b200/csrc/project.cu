@@ -104,6 +104,7 @@ struct Proj {
     R T[6];              // T = J * Rw, rows 0,1 (2x3)
     R a, b, c, det;      // blurred cov2D and determinant
     R a0, c0, det0;      // un-blurred diag and determinant (gsplat compensation)
+    R qr, qx, qy, qz;    // the unit quaternion Rm was built from (filled by the backward kernels)
 };
 
 template <typename R>
@@ -233,21 +234,16 @@ __device__ __forceinline__ float near_of(const B200gsView& v) {
     return v.near_plane > 0.f ? v.near_plane : (GSPLAT ? 0.01f : 0.2f);
 }
 
+// Destination of one view's projection outputs (element index `o` of every array).
+struct ProjOut {
+    float2* xy; float* depth; int32_t* radii; float* conic; float* comp; int32_t* tiles; float* cov3d; float* rgb; uint8_t* clamped;
+};
+
+// Projection of Gaussian (p, sc, q) into view v; writes the outputs at index o and returns the visibility.
 template <bool GSPLAT, bool RAW>
-__global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
-                                                          const float* __restrict__ means, const float* __restrict__ scales,
-                                                          const float* __restrict__ quats, const float* __restrict__ shs,
-                                                          float2* __restrict__ xy_out, float* __restrict__ depth_out,
-                                                          int32_t* __restrict__ radii_out, float* __restrict__ conic_out,
-                                                          float* __restrict__ comp_out, int32_t* __restrict__ tiles_out,
-                                                          float* __restrict__ cov3d_out, float* __restrict__ rgb_out,
-                                                          uint8_t* __restrict__ clamped_out) {
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
+__device__ __forceinline__ bool project_one(const B200gsView& v, const RawIO& raw, int64_t i, int64_t o, const float* p, const double* sc,
+                                            const double* q, const ProjOut& out, float* opac_out) {
     typedef double R;
-    R sc[3], q[4], inv_qn;
-    load_scale_quat<RAW, R>(scales, quats, i, sc, q, &inv_qn);
     Proj<R> g;
     project_geometry<GSPLAT, R>(v, p, sc, q, g);
 
@@ -284,60 +280,126 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant_
     vis = vis && (ntiles > 0) && (radius > 0.f);  // NaN radius compares false
 
     if (vis) {
-        xy_out[i] = make_float2(px, py);
-        depth_out[i] = float(g.tz);
-        radii_out[i] = (int32_t)radius;
-        conic_out[3 * i + 0] = float(g.c * inv_det);
-        conic_out[3 * i + 1] = float(-g.b * inv_det);
-        conic_out[3 * i + 2] = float(g.a * inv_det);
-        tiles_out[i] = ntiles;
+        out.xy[o] = make_float2(px, py);
+        out.depth[o] = float(g.tz);
+        out.radii[o] = (int32_t)radius;
+        out.conic[3 * o + 0] = float(g.c * inv_det);
+        out.conic[3 * o + 1] = float(-g.b * inv_det);
+        out.conic[3 * o + 2] = float(g.a * inv_det);
+        if (out.tiles) out.tiles[o] = ntiles;
         const float comp = GSPLAT ? float(sqrt(fmax(g.det0 * inv_det, R(0)))) : 1.0f;
-        if (comp_out) comp_out[i] = comp;
+        if (out.comp) out.comp[o] = comp;
         if (RAW) {
-            const float o = 1.0f / (1.0f + expf(-__ldg(raw.opac_in + i)));
-            raw.opac_out[i] = (GSPLAT && raw.anti_aliased) ? o * comp : o;
+            const float op = 1.0f / (1.0f + expf(-__ldg(raw.opac_in + i)));
+            opac_out[o] = (GSPLAT && raw.anti_aliased) ? op * comp : op;
         }
     } else {
-        if (RAW) raw.opac_out[i] = 0.f;
-        xy_out[i] = make_float2(0.f, 0.f);
-        depth_out[i] = 0.f;
-        radii_out[i] = 0;
-        conic_out[3 * i + 0] = 0.f; conic_out[3 * i + 1] = 0.f; conic_out[3 * i + 2] = 0.f;
-        tiles_out[i] = 0;
-        if (comp_out) comp_out[i] = 0.f;
+        if (RAW) opac_out[o] = 0.f;
+        out.xy[o] = make_float2(0.f, 0.f);
+        out.depth[o] = 0.f;
+        out.radii[o] = 0;
+        out.conic[3 * o + 0] = 0.f; out.conic[3 * o + 1] = 0.f; out.conic[3 * o + 2] = 0.f;
+        if (out.tiles) out.tiles[o] = 0;
+        if (out.comp) out.comp[o] = 0.f;
     }
-    if (cov3d_out) {
+    if (out.cov3d) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) cov3d_out[6 * i + k] = vis ? float(g.S3[k]) : 0.f;
+        for (int k = 0; k < 6; ++k) out.cov3d[6 * o + k] = vis ? float(g.S3[k]) : 0.f;
     }
+    return vis;
+}
+
+// max(SH colour + 0.5, 0) of a visible Gaussian seen from v.campos; bit c of *cl set where channel c was clamped
+__device__ __forceinline__ void sh_color_one(const B200gsView& v, const float* p, const float* sh, float& r, float& gc, float& bc, uint8_t& cl) {
+    const int deg = v.sh_degree;
+    const int ncoef = (deg + 1) * (deg + 1);
+    float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
+    const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= inv_len; dy *= inv_len; dz *= inv_len;
+    float bs[MAX_COEFFS];
+    sh_basis(deg, dx, dy, dz, bs);
+    r = gc = bc = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAX_COEFFS; ++k) {
+        if (k < ncoef) {
+            r += bs[k] * sh[3 * k + 0];
+            gc += bs[k] * sh[3 * k + 1];
+            bc += bs[k] * sh[3 * k + 2];
+        }
+    }
+    r += 0.5f; gc += 0.5f; bc += 0.5f;
+    cl = 0;
+    if (r < 0.f) { r = 0.f; cl |= 1; }
+    if (gc < 0.f) { gc = 0.f; cl |= 2; }
+    if (bc < 0.f) { bc = 0.f; cl |= 4; }
+}
+
+template <bool GSPLAT, bool RAW>
+__global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
+                                                          const float* __restrict__ means, const float* __restrict__ scales,
+                                                          const float* __restrict__ quats, const float* __restrict__ shs,
+                                                          float2* __restrict__ xy_out, float* __restrict__ depth_out,
+                                                          int32_t* __restrict__ radii_out, float* __restrict__ conic_out,
+                                                          float* __restrict__ comp_out, int32_t* __restrict__ tiles_out,
+                                                          float* __restrict__ cov3d_out, float* __restrict__ rgb_out,
+                                                          uint8_t* __restrict__ clamped_out) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
+    double sc[3], q[4], inv_qn;
+    load_scale_quat<RAW, double>(scales, quats, i, sc, q, &inv_qn);
+    const ProjOut out{xy_out, depth_out, radii_out, conic_out, comp_out, tiles_out, cov3d_out, rgb_out, clamped_out};
+    const bool vis = project_one<GSPLAT, RAW>(v, raw, i, i, p, sc, q, out, raw.opac_out);
     if (shs != nullptr) {
         float r = 0.f, gc = 0.f, bc = 0.f;
         uint8_t cl = 0;
         if (vis) {
             const int deg = v.sh_degree;
-            const int ncoef = (deg + 1) * (deg + 1);
             float sh[MAX_COEFFS * 3];
-            load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
-            float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
-            const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-            dx *= inv_len; dy *= inv_len; dz *= inv_len;
-            float bs[MAX_COEFFS];
-            sh_basis(deg, dx, dy, dz, bs);
-#pragma unroll
-            for (int k = 0; k < MAX_COEFFS; ++k) {
-                if (k < ncoef) {
-                    r += bs[k] * sh[3 * k + 0];
-                    gc += bs[k] * sh[3 * k + 1];
-                    bc += bs[k] * sh[3 * k + 2];
-                }
-            }
-            r += 0.5f; gc += 0.5f; bc += 0.5f;
-            if (r < 0.f) { r = 0.f; cl |= 1; }
-            if (gc < 0.f) { gc = 0.f; cl |= 2; }
-            if (bc < 0.f) { bc = 0.f; cl |= 4; }
+            load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, (deg + 1) * (deg + 1), sh);
+            sh_color_one(v, p, sh, r, gc, bc, cl);
         }
         rgb_out[3 * i + 0] = r; rgb_out[3 * i + 1] = gc; rgb_out[3 * i + 2] = bc;
         clamped_out[i] = cl;
+    }
+}
+
+// The sharded renderer projects ONE shard into the W cameras of a step: one launch, the parameters (and the SH block, if any view
+// sees the Gaussian) are read once per Gaussian instead of once per camera.  gsplat constants, raw parameters.  View j's outputs
+// live at elements [j*n, (j+1)*n) of camera-major arrays.
+struct ViewPack {
+    B200gsView v[B200GS_MAX_VIEWS];
+};
+
+__global__ void __launch_bounds__(256) project_fwd_multi_kernel(const __grid_constant__ ViewPack vp, int nviews, const RawIO raw, int64_t n,
+                                                                const float* __restrict__ means, const float* __restrict__ scales,
+                                                                const float* __restrict__ quats, const float* __restrict__ shs_dc,
+                                                                float2* __restrict__ xy_out, float* __restrict__ depth_out,
+                                                                int32_t* __restrict__ radii_out, float* __restrict__ conic_out,
+                                                                float* __restrict__ rgb_out, uint8_t* __restrict__ clamped_out) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
+    double sc[3], q[4], inv_qn;
+    load_scale_quat<true, double>(scales, quats, i, sc, q, &inv_qn);
+    const ProjOut out{xy_out, depth_out, radii_out, conic_out, nullptr, nullptr, nullptr, rgb_out, clamped_out};
+    unsigned vismask = 0;
+#pragma unroll 1
+    for (int j = 0; j < nviews; ++j)
+        if (project_one<true, true>(vp.v[j], raw, i, int64_t(j) * n + i, p, sc, q, out, raw.opac_out)) vismask |= 1u << j;
+    float sh[MAX_COEFFS * 3];
+    if (vismask) {
+        const int deg = vp.v[0].sh_degree;
+        load_sh_any<true>(shs_dc, raw.shs_rest, i, vp.v[0].sh_stride, (deg + 1) * (deg + 1), sh);
+    }
+#pragma unroll 1
+    for (int j = 0; j < nviews; ++j) {
+        float r = 0.f, gc = 0.f, bc = 0.f;
+        uint8_t cl = 0;
+        if ((vismask >> j) & 1u) sh_color_one(vp.v[j], p, sh, r, gc, bc, cl);
+        const int64_t o = int64_t(j) * n + i;
+        rgb_out[3 * o + 0] = r; rgb_out[3 * o + 1] = gc; rgb_out[3 * o + 2] = bc;
+        clamped_out[o] = cl;
     }
 }
 
@@ -346,170 +408,33 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int BWD_THREADS = 128;
 
-template <bool GSPLAT, bool RAW>
-__global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
-                                                          const float* __restrict__ means, const float* __restrict__ scales,
-                                                          const float* __restrict__ quats, const float* __restrict__ shs,
-                                                          const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
-                                                          const float2* __restrict__ v_xy, const float* __restrict__ v_depth,
-                                                          const float* __restrict__ v_conic, const float* __restrict__ v_comp,
-                                                          const float* __restrict__ v_rgb, float* __restrict__ v_means,
-                                                          float* __restrict__ v_scales, float4* __restrict__ v_quats,
-                                                          float* __restrict__ v_shs) {
-    // SH-gradient rows are staged per warp in shared memory (odd row stride: conflict-free) and written back with
-    // fully coalesced 128-bit stores: every row must be written (zeros for culled Gaussians), so the warp's 32 rows are
-    // one contiguous 5.6-6 KB span of the output.
-    __shared__ float s_rows[BWD_THREADS / 32][32 * 49];
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
-    const int warp = threadIdx.x >> 5;
-    const bool in_range = i < n;
-    const bool ROWS = RAW && (raw.v_rows != nullptr);
-    const bool ACC = RAW && (raw.accumulate != 0);
-    // a negative row index = the entry did not fit its fixed-size block (the caller redoes such a step): treated as culled
-    const bool vis = in_range && (radii[i] > 0) && !(ROWS && raw.row_offsets[i] < 0);
-    const int stride3 = v.sh_stride * 3;
-    float p[3] = {0.f, 0.f, 0.f};
-    if (vis) { p[0] = __ldg(means + 3 * i); p[1] = __ldg(means + 3 * i + 1); p[2] = __ldg(means + 3 * i + 2); }
-    const float* vrow = (ROWS && vis) ? raw.v_rows + int64_t(raw.row_offsets[i]) * B200GS_ROW_FLOATS : nullptr;
+// Cotangents of one view's projection outputs for one Gaussian
+struct ProjCot {
+    float vA, vB, vC;      // dL/dconic
+    float2 vxy;            // dL/dmean2D (vanilla: NDC-scaled units)
+    float vdepth;          // dL/ddepth (gsplat)
+    float vcomp;           // dL/dcompensation (gsplat), incl. the part that reaches it through the blend opacity
+};
 
-    float dmx = 0.f, dmy = 0.f, dmz = 0.f;  // dL/dmean (world)
-    float dtx = 0.f, dty = 0.f, dtz = 0.f;  // dL/dt (camera)
-
-    // ---- SH colour -------------------------------------------------------------------------------------------
-    if (v_shs != nullptr) {
-        const int deg = v.sh_degree;
-        const int ncoef = (deg + 1) * (deg + 1);
-        float gr = 0.f, gg = 0.f, gb = 0.f, dx = 0.f, dy = 0.f, dz = 1.f, inv_len = 0.f;
-        float out[MAX_COEFFS * 3];
-#pragma unroll
-        for (int k = 0; k < MAX_COEFFS * 3; ++k) out[k] = 0.f;
-        if (vis) {
-            const uint8_t cl = clamped[i];
-            const float* crgb = ROWS ? vrow + B200GS_ROW_RGB : v_rgb + 3 * i;
-            gr = (cl & 1) ? 0.f : __ldg(crgb + 0);
-            gg = (cl & 2) ? 0.f : __ldg(crgb + 1);
-            gb = (cl & 4) ? 0.f : __ldg(crgb + 2);
-            dx = p[0] - v.campos[0]; dy = p[1] - v.campos[1]; dz = p[2] - v.campos[2];
-            inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-            dx *= inv_len; dy *= inv_len; dz *= inv_len;
-            float bs[MAX_COEFFS];
-            sh_basis(deg, dx, dy, dz, bs);
-#pragma unroll
-            for (int k = 0; k < MAX_COEFFS; ++k) {
-                const float bk = (k < ncoef) ? bs[k] : 0.f;
-                out[3 * k + 0] = bk * gr; out[3 * k + 1] = bk * gg; out[3 * k + 2] = bk * gb;
-            }
-        }
-        const int rw = RAW ? stride3 - 3 : stride3;          // floats per output row
-        float* dst_base = RAW ? raw.v_shs_rest : v_shs;
-        if (RAW && in_range) {
-            if (ACC) { out[0] += v_shs[3 * i]; out[1] += v_shs[3 * i + 1]; out[2] += v_shs[3 * i + 2]; }
-            v_shs[3 * i] = out[0]; v_shs[3 * i + 1] = out[1]; v_shs[3 * i + 2] = out[2];
-        }
-        if (rw <= 48) {
-            const int rwp = rw | 1;
-            float* row = s_rows[warp] + lane * rwp;
-#pragma unroll
-            for (int k = 0; k < MAX_COEFFS * 3; ++k) {
-                const int c = RAW ? k - 3 : k;
-                if (c >= 0 && c < rw) row[c] = out[k];
-            }
-            __syncwarp();
-            const int64_t i0 = i - lane;
-            const int rows_valid = (i0 < n) ? (int)min((int64_t)32, n - i0) : 0;
-            const int total = rows_valid * rw;
-            float* dst = dst_base + i0 * rw;
-            const float* sw = s_rows[warp];
-            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                for (int idx = lane; idx * 4 + 3 < total; idx += 32) {
-                    int f = idx * 4, r = f / rw, c = f - r * rw;
-                    float t[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        t[e] = sw[r * rwp + c];
-                        if (++c == rw) { c = 0; ++r; }
-                    }
-                    if (ACC) {
-                        const float4 old = reinterpret_cast<const float4*>(dst)[idx];
-                        t[0] += old.x; t[1] += old.y; t[2] += old.z; t[3] += old.w;
-                    }
-                    reinterpret_cast<float4*>(dst)[idx] = make_float4(t[0], t[1], t[2], t[3]);
-                }
-                for (int f = (total & ~3) + lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw] + (ACC ? dst[f] : 0.f);
-            } else {
-                for (int f = lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw] + (ACC ? dst[f] : 0.f);
-            }
-        } else if (in_range) {  // wider coefficient storage than the kernel evaluates: plain per-thread rows
-            float* o = dst_base + i * int64_t(rw);
-#pragma unroll
-            for (int k = RAW ? 3 : 0; k < MAX_COEFFS * 3; ++k) o[RAW ? k - 3 : k] = out[k];
-            for (int c = MAX_COEFFS * 3 - (RAW ? 3 : 0); c < rw; ++c) o[c] = 0.f;
-        }
-        if (vis && !GSPLAT && deg > 0) {
-            // view direction -> mean (dgr back-propagates it; gsplat renderers detach the direction)
-            float sh[MAX_COEFFS * 3];
-            load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
-            float bx[MAX_COEFFS], by[MAX_COEFFS], bz[MAX_COEFFS];
-            sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
-            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-#pragma unroll
-            for (int k = 1; k < MAX_COEFFS; ++k) {
-                if (k < ncoef) {
-                    const float w = sh[3 * k] * gr + sh[3 * k + 1] * gg + sh[3 * k + 2] * gb;
-                    ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
-                }
-            }
-            const float dot = dx * ddx + dy * ddy + dz * ddz;
-            dmx += (ddx - dx * dot) * inv_len;
-            dmy += (ddy - dy * dot) * inv_len;
-            dmz += (ddz - dz * dot) * inv_len;
-        }
-    }
-    if (!in_range) return;
-    if (!vis) {
-        if (!ACC) {
-            v_means[3 * i] = 0.f; v_means[3 * i + 1] = 0.f; v_means[3 * i + 2] = 0.f;
-            v_scales[3 * i] = 0.f; v_scales[3 * i + 1] = 0.f; v_scales[3 * i + 2] = 0.f;
-            v_quats[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (RAW) raw.v_opac_logit[i] = 0.f;
-        }
-        return;
-    }
-    float sc[3], q[4], inv_qn;
-    load_scale_quat<RAW, float>(scales, quats, i, sc, q, &inv_qn);
-    Proj<float> g;
-    project_geometry<GSPLAT, float>(v, p, sc, q, g);
+// Adds view v's contribution to dL/dmean (dm), dL/dM-chain outputs: dL/dscale (activated scale, before the exp chain) and dL/dq
+// (unit quaternion, before the normalisation chain).  g = project_geometry<GSPLAT, float>(v, p, sc, q).
+template <bool GSPLAT>
+__device__ __forceinline__ void geometry_backward(const B200gsView& v, const float* p, const Proj<float>& g, const ProjCot& c, float* dm,
+                                                  float* dscale, float4& dq) {
     const float* V = v.viewmatrix;
-
+    float dtx = 0.f, dty = 0.f, dtz = 0.f;  // dL/dt (camera)
     // ---- conic (+ compensation) -> blurred cov2D (a, b, c) ----------------------------------------------------
     const float inv_det = 1.0f / g.det;
     const float A = g.c * inv_det, B = -g.b * inv_det, C = g.a * inv_det;
-    const float* ccon = ROWS ? vrow + B200GS_ROW_CONIC : v_conic + 3 * i;
-    const float vA = __ldg(ccon), vB = __ldg(ccon + 1), vC = __ldg(ccon + 2);
     // X = -Q G Q, Q = [[A,B],[B,C]], G = [[vA, vB/2],[vB/2, vC]]
-    const float hB = 0.5f * vB;
-    const float m00 = A * vA + B * hB, m01 = A * hB + B * vC;
-    const float m10 = B * vA + C * hB, m11 = B * hB + C * vC;
+    const float hB = 0.5f * c.vB;
+    const float m00 = A * c.vA + B * hB, m01 = A * hB + B * c.vC;
+    const float m10 = B * c.vA + C * hB, m11 = B * hB + C * c.vC;
     float da = -(m00 * A + m01 * B);
     float db = -2.0f * (m00 * B + m01 * C);
     float dc = -(m10 * B + m11 * C);
-    (void)m10;
-    float vc_total = (GSPLAT && v_comp != nullptr) ? __ldg(v_comp + i) : 0.f;
-    if (RAW) {
-        // blend opacity = sigmoid(logit) [* compensation]: split dL/d(opac_out) between the logit and the compensation
-        const float o = 1.0f / (1.0f + expf(-__ldg(raw.opac_in + i)));
-        const float vo = ROWS ? __ldg(vrow + B200GS_ROW_OPACITY) : __ldg(raw.v_opac + i);
-        float v_sig = vo;
-        if (GSPLAT && raw.anti_aliased) {
-            const float comp = sqrtf(fmaxf(g.det0 / g.det, 0.f));
-            v_sig = vo * comp;
-            vc_total += vo * o;
-        }
-        raw.v_opac_logit[i] = v_sig * o * (1.0f - o) + (ACC ? raw.v_opac_logit[i] : 0.f);
-    }
-    if (GSPLAT && (v_comp != nullptr || RAW)) {
-        const float vc = vc_total;
+    if (GSPLAT) {
+        const float vc = c.vcomp;
         if (g.det0 > 0.f && vc != 0.f) {
             const float comp = sqrtf(g.det0 * inv_det);
             const float d_det0 = vc * 0.5f * comp / g.det0;
@@ -545,7 +470,6 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
         dT1[k] = 2.0f * (g01 * TS0[k] + g11 * TS1[k]);
     }
     // T = J Rw -> dL/dJ = dL/dT Rw^T ; Rw[j][i] = V[i*4+j]
-    // dJ00 = sum_i dT0[i] Rw[0][i], dJ02 = sum_i dT0[i] Rw[2][i], dJ11 = sum_i dT1[i] Rw[1][i], dJ12 = sum_i dT1[i] Rw[2][i]
     const float dJ00 = dT0[0] * V[0] + dT0[1] * V[4] + dT0[2] * V[8];
     const float dJ02 = dT0[0] * V[2] + dT0[1] * V[6] + dT0[2] * V[10];
     const float dJ11 = dT1[0] * V[1] + dT1[1] * V[5] + dT1[2] * V[9];
@@ -558,14 +482,12 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
     if (!g.cly) dty += dcy; else if (GSPLAT) dtz += dcy * g.cyp * itz;
 
     // ---- mean2D / depth --------------------------------------------------------------------------------------
-    const float2 vxy = ROWS ? make_float2(__ldg(vrow), __ldg(vrow + 1)) : v_xy[i];
     if (GSPLAT) {
         const float iz = 1.0f / (g.tz + 1e-6f);
-        dtx += v.fx * iz * vxy.x;
-        dty += v.fy * iz * vxy.y;
-        dtz += (-v.fx * g.tx * iz * iz + v.cx * 1e-6f * iz * iz) * vxy.x + (-v.fy * g.ty * iz * iz + v.cy * 1e-6f * iz * iz) * vxy.y;
-        if (ROWS) dtz += __ldg(vrow + B200GS_ROW_DEPTH);
-        else if (v_depth) dtz += __ldg(v_depth + i);
+        dtx += v.fx * iz * c.vxy.x;
+        dty += v.fy * iz * c.vxy.y;
+        dtz += (-v.fx * g.tx * iz * iz + v.cx * 1e-6f * iz * iz) * c.vxy.x + (-v.fy * g.ty * iz * iz + v.cy * 1e-6f * iz * iz) * c.vxy.y;
+        dtz += c.vdepth;
     } else {
         // v_xy is dL/d(ndc) (pixel gradient x 0.5 W/H), straight through the 4x4 full projection
         const float* P = v.projmatrix;
@@ -573,16 +495,14 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
         const float mw = 1.0f / (hw + 0.0000001f);
         const float mul1 = (p[0] * P[0] + p[1] * P[4] + p[2] * P[8] + P[12]) * mw * mw;
         const float mul2 = (p[0] * P[1] + p[1] * P[5] + p[2] * P[9] + P[13]) * mw * mw;
-        dmx += (P[0] * mw - P[3] * mul1) * vxy.x + (P[1] * mw - P[3] * mul2) * vxy.y;
-        dmy += (P[4] * mw - P[7] * mul1) * vxy.x + (P[5] * mw - P[7] * mul2) * vxy.y;
-        dmz += (P[8] * mw - P[11] * mul1) * vxy.x + (P[9] * mw - P[11] * mul2) * vxy.y;
+        dm[0] += (P[0] * mw - P[3] * mul1) * c.vxy.x + (P[1] * mw - P[3] * mul2) * c.vxy.y;
+        dm[1] += (P[4] * mw - P[7] * mul1) * c.vxy.x + (P[5] * mw - P[7] * mul2) * c.vxy.y;
+        dm[2] += (P[8] * mw - P[11] * mul1) * c.vxy.x + (P[9] * mw - P[11] * mul2) * c.vxy.y;
     }
     // t = p * V[:3,:3] + V[3,:3]  ->  dL/dp_i = sum_j V[i][j] dt_j
-    dmx += V[0] * dtx + V[1] * dty + V[2] * dtz;
-    dmy += V[4] * dtx + V[5] * dty + V[6] * dtz;
-    dmz += V[8] * dtx + V[9] * dty + V[10] * dtz;
-    if (ACC) { dmx += v_means[3 * i]; dmy += v_means[3 * i + 1]; dmz += v_means[3 * i + 2]; }
-    v_means[3 * i] = dmx; v_means[3 * i + 1] = dmy; v_means[3 * i + 2] = dmz;
+    dm[0] += V[0] * dtx + V[1] * dty + V[2] * dtz;
+    dm[1] += V[4] * dtx + V[5] * dty + V[6] * dtz;
+    dm[2] += V[8] * dtx + V[9] * dty + V[10] * dtz;
 
     // ---- Sigma3 = M M^T, M = R diag(s) ------------------------------------------------------------------------
     float M[9], dM[9];
@@ -598,17 +518,187 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
     float dR[9];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float vs_k = v.scale_modifier * (g.Rm[k] * dM[k] + g.Rm[3 + k] * dM[3 + k] + g.Rm[6 + k] * dM[6 + k]);
-        v_scales[3 * i + k] = (RAW ? vs_k * sc[k] : vs_k) + (ACC ? v_scales[3 * i + k] : 0.f);   // d exp(x) = exp(x)
+        dscale[k] += v.scale_modifier * (g.Rm[k] * dM[k] + g.Rm[3 + k] * dM[3 + k] + g.Rm[6 + k] * dM[6 + k]);
 #pragma unroll
         for (int r = 0; r < 3; ++r) dR[r * 3 + k] = dM[r * 3 + k] * g.s[k];
     }
-    const float r = q[0], x = q[1], y = q[2], z = q[3];
-    float4 dq;
-    dq.x = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
-    dq.y = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
-    dq.z = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
-    dq.w = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+    // Rm was built from the (unit) quaternion (r, x, y, z): recover it from the caller
+    const float r = g.qr, x = g.qx, y = g.qy, z = g.qz;
+    dq.x += 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+    dq.y += 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
+    dq.z += 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
+    dq.w += 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+}
+
+// SH-gradient rows of a warp's 32 Gaussians: staged in shared memory (odd row stride: conflict-free) and written back with
+// fully coalesced 128-bit stores: every row must be written (zeros for culled Gaussians), so the warp's 32 rows are one
+// contiguous 5.6-6 KB span of the output.  out[] holds this lane's 48 values (dc first); RAW: dc goes to v_shs, rest to dst_base.
+template <bool RAW>
+__device__ __forceinline__ void store_sh_rows(float* s_rows_warp, const float* out, int64_t i, int64_t n, bool in_range, int stride3, unsigned lane,
+                                              float* __restrict__ v_shs, float* __restrict__ v_shs_rest, bool ACC) {
+    const int rw = RAW ? stride3 - 3 : stride3;          // floats per output row
+    float* dst_base = RAW ? v_shs_rest : v_shs;
+    if (RAW && in_range) {
+        float o0 = out[0], o1 = out[1], o2 = out[2];
+        if (ACC) { o0 += v_shs[3 * i]; o1 += v_shs[3 * i + 1]; o2 += v_shs[3 * i + 2]; }
+        v_shs[3 * i] = o0; v_shs[3 * i + 1] = o1; v_shs[3 * i + 2] = o2;
+    }
+    if (rw <= 48) {
+        const int rwp = rw | 1;
+        float* row = s_rows_warp + lane * rwp;
+#pragma unroll
+        for (int k = 0; k < MAX_COEFFS * 3; ++k) {
+            const int c = RAW ? k - 3 : k;
+            if (c >= 0 && c < rw) row[c] = out[k];
+        }
+        __syncwarp();
+        const int64_t i0 = i - lane;
+        const int rows_valid = (i0 < n) ? (int)min((int64_t)32, n - i0) : 0;
+        const int total = rows_valid * rw;
+        float* dst = dst_base + i0 * rw;
+        const float* sw = s_rows_warp;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            for (int idx = lane; idx * 4 + 3 < total; idx += 32) {
+                int f = idx * 4, r = f / rw, c = f - r * rw;
+                float t[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    t[e] = sw[r * rwp + c];
+                    if (++c == rw) { c = 0; ++r; }
+                }
+                if (ACC) {
+                    const float4 old = reinterpret_cast<const float4*>(dst)[idx];
+                    t[0] += old.x; t[1] += old.y; t[2] += old.z; t[3] += old.w;
+                }
+                reinterpret_cast<float4*>(dst)[idx] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+            for (int f = (total & ~3) + lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw] + (ACC ? dst[f] : 0.f);
+        } else {
+            for (int f = lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw] + (ACC ? dst[f] : 0.f);
+        }
+    } else if (in_range) {  // wider coefficient storage than the kernel evaluates: plain per-thread rows
+        float* o = dst_base + i * int64_t(rw);
+#pragma unroll
+        for (int k = RAW ? 3 : 0; k < MAX_COEFFS * 3; ++k) o[RAW ? k - 3 : k] = out[k];
+        for (int c = MAX_COEFFS * 3 - (RAW ? 3 : 0); c < rw; ++c) o[c] = 0.f;
+    }
+}
+
+template <bool GSPLAT, bool RAW>
+__global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
+                                                          const float* __restrict__ means, const float* __restrict__ scales,
+                                                          const float* __restrict__ quats, const float* __restrict__ shs,
+                                                          const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
+                                                          const float2* __restrict__ v_xy, const float* __restrict__ v_depth,
+                                                          const float* __restrict__ v_conic, const float* __restrict__ v_comp,
+                                                          const float* __restrict__ v_rgb, float* __restrict__ v_means,
+                                                          float* __restrict__ v_scales, float4* __restrict__ v_quats,
+                                                          float* __restrict__ v_shs) {
+    __shared__ float s_rows[BWD_THREADS / 32][32 * 49];
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const int warp = threadIdx.x >> 5;
+    const bool in_range = i < n;
+    const bool ROWS = RAW && (raw.v_rows != nullptr);
+    const bool ACC = RAW && (raw.accumulate != 0);
+    // a negative row index = the entry did not fit its fixed-size block (the caller redoes such a step): treated as culled
+    const bool vis = in_range && (radii[i] > 0) && !(ROWS && raw.row_offsets[i] < 0);
+    const int stride3 = v.sh_stride * 3;
+    float p[3] = {0.f, 0.f, 0.f};
+    if (vis) { p[0] = __ldg(means + 3 * i); p[1] = __ldg(means + 3 * i + 1); p[2] = __ldg(means + 3 * i + 2); }
+    const float* vrow = (ROWS && vis) ? raw.v_rows + int64_t(raw.row_offsets[i]) * B200GS_ROW_FLOATS : nullptr;
+
+    float dm[3] = {0.f, 0.f, 0.f};  // dL/dmean (world)
+
+    // ---- SH colour -------------------------------------------------------------------------------------------
+    if (v_shs != nullptr) {
+        const int deg = v.sh_degree;
+        const int ncoef = (deg + 1) * (deg + 1);
+        float gr = 0.f, gg = 0.f, gb = 0.f, dx = 0.f, dy = 0.f, dz = 1.f, inv_len = 0.f;
+        float out[MAX_COEFFS * 3];
+#pragma unroll
+        for (int k = 0; k < MAX_COEFFS * 3; ++k) out[k] = 0.f;
+        if (vis) {
+            const uint8_t cl = clamped[i];
+            const float* crgb = ROWS ? vrow + B200GS_ROW_RGB : v_rgb + 3 * i;
+            gr = (cl & 1) ? 0.f : __ldg(crgb + 0);
+            gg = (cl & 2) ? 0.f : __ldg(crgb + 1);
+            gb = (cl & 4) ? 0.f : __ldg(crgb + 2);
+            dx = p[0] - v.campos[0]; dy = p[1] - v.campos[1]; dz = p[2] - v.campos[2];
+            inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            dx *= inv_len; dy *= inv_len; dz *= inv_len;
+            float bs[MAX_COEFFS];
+            sh_basis(deg, dx, dy, dz, bs);
+#pragma unroll
+            for (int k = 0; k < MAX_COEFFS; ++k) {
+                const float bk = (k < ncoef) ? bs[k] : 0.f;
+                out[3 * k + 0] = bk * gr; out[3 * k + 1] = bk * gg; out[3 * k + 2] = bk * gb;
+            }
+        }
+        store_sh_rows<RAW>(s_rows[warp], out, i, n, in_range, stride3, lane, v_shs, raw.v_shs_rest, ACC);
+        if (vis && !GSPLAT && deg > 0) {
+            // view direction -> mean (dgr back-propagates it; gsplat renderers detach the direction)
+            float sh[MAX_COEFFS * 3];
+            load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
+            float bx[MAX_COEFFS], by[MAX_COEFFS], bz[MAX_COEFFS];
+            sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
+            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+#pragma unroll
+            for (int k = 1; k < MAX_COEFFS; ++k) {
+                if (k < ncoef) {
+                    const float w = sh[3 * k] * gr + sh[3 * k + 1] * gg + sh[3 * k + 2] * gb;
+                    ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
+                }
+            }
+            const float dot = dx * ddx + dy * ddy + dz * ddz;
+            dm[0] += (ddx - dx * dot) * inv_len;
+            dm[1] += (ddy - dy * dot) * inv_len;
+            dm[2] += (ddz - dz * dot) * inv_len;
+        }
+    }
+    if (!in_range) return;
+    if (!vis) {
+        if (!ACC) {
+            v_means[3 * i] = 0.f; v_means[3 * i + 1] = 0.f; v_means[3 * i + 2] = 0.f;
+            v_scales[3 * i] = 0.f; v_scales[3 * i + 1] = 0.f; v_scales[3 * i + 2] = 0.f;
+            v_quats[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (RAW) raw.v_opac_logit[i] = 0.f;
+        }
+        return;
+    }
+    float sc[3], q[4], inv_qn;
+    load_scale_quat<RAW, float>(scales, quats, i, sc, q, &inv_qn);
+    Proj<float> g;
+    project_geometry<GSPLAT, float>(v, p, sc, q, g);
+    g.qr = q[0]; g.qx = q[1]; g.qy = q[2]; g.qz = q[3];
+
+    ProjCot c;
+    const float* ccon = ROWS ? vrow + B200GS_ROW_CONIC : v_conic + 3 * i;
+    c.vA = __ldg(ccon); c.vB = __ldg(ccon + 1); c.vC = __ldg(ccon + 2);
+    c.vxy = ROWS ? make_float2(__ldg(vrow), __ldg(vrow + 1)) : v_xy[i];
+    c.vdepth = 0.f;
+    if (GSPLAT) c.vdepth = ROWS ? __ldg(vrow + B200GS_ROW_DEPTH) : (v_depth ? __ldg(v_depth + i) : 0.f);
+    c.vcomp = (GSPLAT && v_comp != nullptr) ? __ldg(v_comp + i) : 0.f;
+    if (RAW) {
+        // blend opacity = sigmoid(logit) [* compensation]: split dL/d(opac_out) between the logit and the compensation
+        const float o = 1.0f / (1.0f + expf(-__ldg(raw.opac_in + i)));
+        const float vo = ROWS ? __ldg(vrow + B200GS_ROW_OPACITY) : __ldg(raw.v_opac + i);
+        float v_sig = vo;
+        if (GSPLAT && raw.anti_aliased) {
+            const float comp = sqrtf(fmaxf(g.det0 / g.det, 0.f));
+            v_sig = vo * comp;
+            c.vcomp += vo * o;
+        }
+        raw.v_opac_logit[i] = v_sig * o * (1.0f - o) + (ACC ? raw.v_opac_logit[i] : 0.f);
+    }
+    float dscale[3] = {0.f, 0.f, 0.f};
+    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+    geometry_backward<GSPLAT>(v, p, g, c, dm, dscale, dq);
+
+    if (ACC) { dm[0] += v_means[3 * i]; dm[1] += v_means[3 * i + 1]; dm[2] += v_means[3 * i + 2]; }
+    v_means[3 * i] = dm[0]; v_means[3 * i + 1] = dm[1]; v_means[3 * i + 2] = dm[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v_scales[3 * i + k] = (RAW ? dscale[k] * sc[k] : dscale[k]) + (ACC ? v_scales[3 * i + k] : 0.f);   // d exp(x) = exp(x)
     if (RAW) {  // through q / |q|
         const float dot = dq.x * q[0] + dq.y * q[1] + dq.z * q[2] + dq.w * q[3];
         dq.x = (dq.x - q[0] * dot) * inv_qn; dq.y = (dq.y - q[1] * dot) * inv_qn;
@@ -619,6 +709,97 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
         dq.x += old.x; dq.y += old.y; dq.z += old.z; dq.w += old.w;
     }
     v_quats[i] = dq;
+}
+
+// Backward of project_fwd_multi_kernel: every thread walks the W cameras of the step, accumulates the parameter gradients of
+// its Gaussian in registers and writes them ONCE (the per-camera launches read-modify-wrote 236 B per Gaussian and camera).
+// Cotangents are [.,12] gradient rows (b200gs.h row layout); view j's rows start at v_rows[j] (possibly a peer GPU's buffer
+// mapped over NVLink), entry (j, i) uses row row_index[j*n + i] of it.
+struct RowSources {
+    const float* rows[B200GS_MAX_VIEWS];
+};
+
+__global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __grid_constant__ ViewPack vp, int nviews, const RawIO raw,
+                                                                       const __grid_constant__ RowSources src, int64_t n,
+                                                                       const float* __restrict__ means, const float* __restrict__ scales,
+                                                                       const float* __restrict__ quats, const int32_t* __restrict__ radii,
+                                                                       const uint8_t* __restrict__ clamped, const int32_t* __restrict__ row_index,
+                                                                       float* __restrict__ v_means, float* __restrict__ v_scales,
+                                                                       float4* __restrict__ v_quats, float* __restrict__ v_shs_dc) {
+    __shared__ float s_rows[BWD_THREADS / 32][32 * 49];
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const int warp = threadIdx.x >> 5;
+    const bool in_range = i < n;
+    const int stride3 = vp.v[0].sh_stride * 3;
+    const int deg = vp.v[0].sh_degree;
+    const int ncoef = (deg + 1) * (deg + 1);
+    float out[MAX_COEFFS * 3];
+#pragma unroll
+    for (int k = 0; k < MAX_COEFFS * 3; ++k) out[k] = 0.f;
+    float dm[3] = {0.f, 0.f, 0.f}, dscale[3] = {0.f, 0.f, 0.f}, dlogit = 0.f;
+    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
+    float p[3] = {0.f, 0.f, 0.f}, sc[3] = {1.f, 1.f, 1.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, inv_qn = 1.f, o = 0.f;
+    bool loaded = false;
+#pragma unroll 1
+    for (int j = 0; j < nviews; ++j) {
+        const int64_t e = int64_t(j) * n + i;
+        if (!in_range || radii[e] <= 0) continue;
+        const int ri = row_index[e];
+        if (ri < 0) continue;     // did not fit its fixed-size block: the caller redoes such a step
+        const float* vrow = src.rows[j] + int64_t(ri) * B200GS_ROW_FLOATS;
+        const float4 w0 = *reinterpret_cast<const float4*>(vrow), w1 = *reinterpret_cast<const float4*>(vrow + 4),
+                     w2 = *reinterpret_cast<const float4*>(vrow + 8);
+        if (!loaded) {
+            p[0] = __ldg(means + 3 * i); p[1] = __ldg(means + 3 * i + 1); p[2] = __ldg(means + 3 * i + 2);
+            load_scale_quat<true, float>(scales, quats, i, sc, q, &inv_qn);
+            o = 1.0f / (1.0f + expf(-__ldg(raw.opac_in + i)));
+            loaded = true;
+        }
+        const B200gsView& v = vp.v[j];
+        // SH colour
+        {
+            const uint8_t cl = clamped[e];
+            const float gr = (cl & 1) ? 0.f : w2.x, gg = (cl & 2) ? 0.f : w2.y, gb = (cl & 4) ? 0.f : w2.z;
+            float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
+            const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            dx *= inv_len; dy *= inv_len; dz *= inv_len;
+            float bs[MAX_COEFFS];
+            sh_basis(deg, dx, dy, dz, bs);
+#pragma unroll
+            for (int k = 0; k < MAX_COEFFS; ++k) {
+                const float bk = (k < ncoef) ? bs[k] : 0.f;
+                out[3 * k + 0] = fmaf(bk, gr, out[3 * k + 0]);
+                out[3 * k + 1] = fmaf(bk, gg, out[3 * k + 1]);
+                out[3 * k + 2] = fmaf(bk, gb, out[3 * k + 2]);
+            }
+        }
+        Proj<float> g;
+        project_geometry<true, float>(v, p, sc, q, g);
+        g.qr = q[0]; g.qx = q[1]; g.qy = q[2]; g.qz = q[3];
+        ProjCot c;
+        c.vxy = make_float2(w0.x, w0.y);
+        c.vdepth = w0.z;
+        c.vA = w0.w; c.vB = w1.x; c.vC = w1.y;
+        c.vcomp = 0.f;
+        const float vo = w1.w;
+        float v_sig = vo;
+        if (raw.anti_aliased) {
+            const float comp = sqrtf(fmaxf(g.det0 / g.det, 0.f));
+            v_sig = vo * comp;
+            c.vcomp = vo * o;
+        }
+        dlogit += v_sig * o * (1.0f - o);
+        geometry_backward<true>(v, p, g, c, dm, dscale, dq);
+    }
+    store_sh_rows<true>(s_rows[warp], out, i, n, in_range, stride3, lane, v_shs_dc, raw.v_shs_rest, false);
+    if (!in_range) return;
+    v_means[3 * i] = dm[0]; v_means[3 * i + 1] = dm[1]; v_means[3 * i + 2] = dm[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v_scales[3 * i + k] = dscale[k] * sc[k];
+    const float dot = dq.x * q[0] + dq.y * q[1] + dq.z * q[2] + dq.w * q[3];
+    v_quats[i] = make_float4((dq.x - q[0] * dot) * inv_qn, (dq.y - q[1] * dot) * inv_qn, (dq.z - q[2] * dot) * inv_qn, (dq.w - q[3] * dot) * inv_qn);
+    raw.v_opac_logit[i] = dlogit;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -742,6 +923,40 @@ int launch_project_bwd_raw(const B200gsView& v, int64_t n, const float* means, c
         else project_bwd_kernel<false, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);
     }
 #undef B200GS_PB_ARGS
+    B200GS_LAUNCH_CHECK();
+    return B200GS_OK;
+}
+
+int launch_project_fwd_multi(const B200gsView* views, int n_views, int64_t n, const float* means, const float* scales, const float* quats,
+                             const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased, float* xy, float* depth,
+                             int32_t* radii, float* conic, float* rgb, uint8_t* clamped, float* opac_out, cudaStream_t s) {
+    if (n == 0 || n_views == 0) return B200GS_OK;
+    ViewPack vp;
+    for (int j = 0; j < n_views; ++j) vp.v[j] = views[j];
+    for (int j = n_views; j < B200GS_MAX_VIEWS; ++j) vp.v[j] = views[0];
+    RawIO raw{opac_logits, shs_rest, opac_out, nullptr, nullptr, nullptr, anti_aliased, nullptr, nullptr, 0};
+    project_fwd_multi_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(vp, n_views, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth, radii,
+                                                                        conic, rgb, clamped);
+    B200GS_LAUNCH_CHECK();
+    return B200GS_OK;
+}
+
+int launch_project_bwd_multi(const B200gsView* views, int n_views, int64_t n, const float* means, const float* scales, const float* quats,
+                             const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased, const int32_t* radii,
+                             const uint8_t* clamped, const int32_t* row_index, const float* const* v_rows, float* v_means, float* v_scales,
+                             float* v_quats, float* v_opac_logit, float* v_shs_dc, float* v_shs_rest, cudaStream_t s) {
+    if (n == 0 || n_views == 0) return B200GS_OK;
+    (void)shs_dc;
+    ViewPack vp;
+    RowSources src;
+    static const float dummy[B200GS_ROW_FLOATS] = {0.f};
+    for (int j = 0; j < B200GS_MAX_VIEWS; ++j) {
+        vp.v[j] = views[j < n_views ? j : 0];
+        src.rows[j] = (j < n_views && v_rows[j]) ? v_rows[j] : dummy;   // NULL only when no row of that view is ever read
+    }
+    RawIO raw{opac_logits, shs_rest, nullptr, nullptr, v_opac_logit, v_shs_rest, anti_aliased, nullptr, nullptr, 0};
+    project_bwd_multi_kernel<<<(unsigned)div_up64(n, BWD_THREADS), BWD_THREADS, 0, s>>>(vp, n_views, raw, src, n, means, scales, quats, radii, clamped,
+                                                                                        row_index, v_means, v_scales, (float4*)v_quats, v_shs_dc);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }

@@ -18,10 +18,14 @@ Mirrors ``internal/renderers/gsplat_distributed_renderer.py`` (SURVEY.md Â§3d, Â
 The distributed image is bit-identical to the single-GPU gsplat-mode render of the unsharded model
 (tests/test_gpu_distributed.py).  A per-pixel reduce of partial images would NOT be (SURVEY Â§0.4).
 """
+import threading
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+from .renderers import Renderer, RendererOutputInfo
 
 ROW_FLOATS = 12  # xy(2) depth(1) conic(3) comp(1) opacity(1) rgb(3) radius-bits(1)
 VIEW_FLOATS = 40  # width height fx fy cx cy | world_to_camera 16 | camera_center 3 | pad
@@ -119,14 +123,16 @@ def _host_group(group):
     neither waits for the GPU nor makes the GPU wait for the host (an NCCL all_gather followed by .cpu() drains the
     device queue at the start of every step).  Created collectively on first use."""
     key = id(group) if group is not None else None
-    g = _HOST_GROUPS.get(key)
+    with _STATE_LOCK:
+        g = _HOST_GROUPS.get(key)
     if g is None:
         if dist.get_backend(group) == "gloo":
             g = group if group is not None else dist.group.WORLD
         else:
             ranks = dist.get_process_group_ranks(group) if group is not None else None
             g = dist.new_group(ranks=ranks, backend="gloo")
-        _HOST_GROUPS[key] = g
+        with _STATE_LOCK:
+            _HOST_GROUPS[key] = g
     return g
 
 
@@ -152,73 +158,252 @@ class GatheredView:
         self.camera_center = flat[22:25].to(device, non_blocking=True)
 
 
-_EXCHANGE_CAP = {}      # (group id, world, n) -> rows per fixed-size send block, agreed by all ranks (from the previous step's global max)
+_EXCHANGE_CAP = {}      # (group id, world) -> rows per fixed-size block, agreed by all ranks (from the previous step's GLOBAL max)
 EXCHANGE_SLACK = 1.15
+_STATE_LOCK = threading.RLock()   # guards _EXCHANGE_CAP / _HOST_GROUPS / _PEERS (a viewer thread may render beside the trainer)
 
 
-class _ShardedRasterize(torch.autograd.Function):
-    """The whole sharded step as ONE autograd node, everything between the raw shard parameters and this rank's image.
-    forward : K1 (fused activations, gsplat constants) per camera into camera-major SoA buffers -> ONE b200gs_pack_rows over all
-              W*n entries (device-side stable compaction straight into the all-to-all send buffer) -> all_to_all_single of
-              [.,12] rows -> K2-K7 reading the received rows in place, pair buffers sized lazily from the previous step.
-              Steady state has NO host sync: every destination gets a fixed-size block of rows (capacity = 1.15 x the
-              previous step's global maximum, identical on all ranks; unused rows are zero = culled), so the all-to-all
-              needs no size exchange; this step's global maximum (one 8-byte all_reduce) is read back after the rest of the
-              forward has been enqueued and, if it exceeded the capacity on ANY rank, all ranks redo the forward with the
-              exact, synchronising exchange (first step, or a >15 % jump of the visible count).
-    backward: K7 accumulates into a [R,12] gradient row buffer -> mirrored all_to_all_single -> K8 (fused activation
-              chain) per camera reading its cotangents straight from the returned rows and ACCUMULATING into one set of
-              gradient buffers (b200gs_project_bwd_rows): no unpack copies, no separate sum kernels."""
+def _group_key(group, world):
+    return (id(group) if group is not None else None, world)
 
-    @staticmethod
-    def forward(ctx, means, log_scales, raw_quats, opac_logits, shs_dc, shs_rest, bg, views, rank, group, anti_aliased, sh_degree):
+
+class _RawDevice:
+    """Device memory that was not allocated by torch, exposed through __cuda_array_interface__ (fp32, 1-D)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """Exchange buffers every rank of the box can address: each rank owns two receive buffers for splat rows (alternating by
+    step) and one for gradient rows, `world * rows_per_block` rows of 12 floats each, allocated with cudaMalloc and mapped into
+    the peers with CUDA IPC (b200gs_ipc_*).  Producers store rows straight into the owner's buffer from their pack kernel
+    (b200gs_pack_rows_peer) and consumers pull gradient rows straight out of the owner's buffer in K8 â€” NVLink loads/stores from
+    our own kernels, no all-to-all.  All methods are collective."""
+
+    def __init__(self, group, device):
+        self.group, self.device = group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.rows_per_block = 0
+        self.enabled = True
+        self.own = {}          # name -> device pointer of my buffer
+        self.peers = {}        # name -> [device pointer on rank j for j in range(world)] (own pointer at j == rank)
+        self._opened = []
+        self.step = 0
+
+    NAMES = ("recv0", "recv1", "vrecv")
+
+    def ensure(self, rows_per_block: int) -> bool:
+        """Make room for `rows_per_block` rows per (source, destination) block.  Returns False (on every rank) when peer
+        mapping is unavailable on any rank; the caller then keeps the NCCL all-to-all."""
         import ctypes
-        from . import ops
-        from ._lib import MODE_GSPLAT, check, lib, ptr
-        L = lib()
-        dev = means.device
-        n = means.shape[0]
-        world = len(views)
-        st = ops._stream()
-        means, log_scales, raw_quats = means.contiguous(), log_scales.contiguous(), raw_quats.contiguous()
-        ol = opac_logits.contiguous().reshape(-1)
-        shs_dc, shs_rest, bg = shs_dc.contiguous(), shs_rest.contiguous(), bg.contiguous()
-        wn = world * n
-        f32 = dict(dtype=torch.float32, device=dev)
-        xy, depth, conic, comp = torch.empty(wn, 2, **f32), torch.empty(wn, **f32), torch.empty(wn, 3, **f32), torch.empty(wn, **f32)
-        rgb, opac = torch.empty(wn, 3, **f32), torch.empty(wn, **f32)
-        radii = torch.empty(wn, dtype=torch.int32, device=dev)
-        tiles = torch.empty(n, dtype=torch.int32, device=dev)
-        clamped = torch.empty(wn, dtype=torch.uint8, device=dev)
-        cam_views = []
-        with ops._stage("project_fwd"):
-            for j, view in enumerate(views):
-                v = ops._copy_view(view, sh_degree=int(sh_degree), sh_stride=int(shs_dc.shape[1] + shs_rest.shape[1]))
-                cam_views.append(v)
+        from . import _lib
+        if not self.enabled or self.world > 8:
+            return False
+        if rows_per_block <= self.rows_per_block:
+            return True
+        L = _lib.lib()
+        self.release()
+        want = int(rows_per_block * 1.25) + 4096
+        nbytes = self.world * want * ROW_FLOATS * 4
+        handles, ok = {}, True
+        try:
+            for name in self.NAMES:
+                ptr_, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+                _lib.check(L.b200gs_ipc_alloc(nbytes, ctypes.byref(ptr_), h), "b200gs_ipc_alloc")
+                self.own[name] = int(ptr_.value)
+                handles[name] = bytes(h.raw)
+        except Exception:
+            ok = False
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (ok, handles), group=_host_group(self.group))
+        ok = all(g[0] for g in gathered)
+        if ok:
+            try:
+                for name in self.NAMES:
+                    ptrs = []
+                    for j in range(self.world):
+                        if j == self.rank:
+                            ptrs.append(self.own[name])
+                            continue
+                        ptr_ = ctypes.c_void_p()
+                        _lib.check(L.b200gs_ipc_open(gathered[j][1][name], ctypes.byref(ptr_)), "b200gs_ipc_open")
+                        self._opened.append(int(ptr_.value))
+                        ptrs.append(int(ptr_.value))
+                    self.peers[name] = ptrs
+            except Exception:
+                ok = False
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=_host_group(self.group))
+        if not all(flags):
+            self.release()
+            self.enabled = False
+            return False
+        self.rows_per_block = want
+        return True
+
+    def tensor(self, name: str, rows: int) -> torch.Tensor:
+        """My own buffer `name` as a [rows, 12] fp32 tensor."""
+        return torch.as_tensor(_RawDevice(self.own[name], rows * ROW_FLOATS), device=self.device).view(rows, ROW_FLOATS)
+
+    def peer_tensor(self, name: str, j: int, rows: int) -> torch.Tensor:
+        return torch.as_tensor(_RawDevice(self.peers[name][j], rows * ROW_FLOATS), device=self.device).view(rows, ROW_FLOATS)
+
+    def release(self):
+        from . import _lib
+        L = _lib.lib()
+        torch.cuda.synchronize(self.device)
+        for p in self._opened:
+            L.b200gs_ipc_close(p)
+        for p in self.own.values():
+            L.b200gs_ipc_free(p)
+        self._opened, self.own, self.peers, self.rows_per_block = [], {}, {}, 0
+
+
+_PEERS = {}
+
+
+def _peer_exchange(group, device) -> PeerExchange:
+    key = (id(group) if group is not None else None, str(device))
+    with _STATE_LOCK:
+        pe = _PEERS.get(key)
+        if pe is None:
+            pe = _PEERS[key] = PeerExchange(group, device)
+    return pe
+
+
+class _ShardStep:
+    """What the two autograd nodes of one sharded step share (buffers of the projection, the exchange and the raster)."""
+    __slots__ = ("views", "cam_views", "rank", "world", "group", "n", "aa", "sh_degree", "peer", "xy", "depth", "conic", "rgb", "opac", "radii",
+                 "clamped", "row_index", "fixed_cap", "counts", "recv", "binning", "final_T", "n_contrib", "hw", "v_rows", "v_send", "parity",
+                 "peer_mode")
+
+
+def _project_shard(st: _ShardStep, means, log_scales, raw_quats, ol, shs_dc, shs_rest):
+    """K1 of the shard for all cameras of the step: one multi-view launch (<= 8 cameras), else one launch per camera."""
+    import ctypes
+    from . import ops
+    from ._lib import B200gsView, check, lib, ptr
+    L = lib()
+    dev, n, world = means.device, st.n, st.world
+    wn = world * n
+    f32 = dict(dtype=torch.float32, device=dev)
+    st.xy, st.depth, st.conic = torch.empty(wn, 2, **f32), torch.empty(wn, **f32), torch.empty(wn, 3, **f32)
+    st.rgb, st.opac = torch.empty(wn, 3, **f32), torch.empty(wn, **f32)
+    st.radii = torch.empty(wn, dtype=torch.int32, device=dev)
+    st.clamped = torch.empty(wn, dtype=torch.uint8, device=dev)
+    st.cam_views = [ops._copy_view(v, sh_degree=int(st.sh_degree), sh_stride=int(shs_dc.shape[1] + shs_rest.shape[1])) for v in st.views]
+    stream = ops._stream()
+    with ops._stage("project_fwd"):
+        if world <= 8:
+            arr = (B200gsView * world)(*st.cam_views)
+            check(L.b200gs_project_fwd_raw_multi(arr, world, n, ptr(means), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc), ptr(shs_rest),
+                                                 int(st.aa), ptr(st.xy), ptr(st.depth), ptr(st.radii), ptr(st.conic), ptr(st.rgb), ptr(st.clamped),
+                                                 ptr(st.opac), stream), "b200gs_project_fwd_raw_multi")
+        else:
+            tiles = torch.empty(n, dtype=torch.int32, device=dev)
+            comp = torch.empty(n, **f32)
+            for j, v in enumerate(st.cam_views):
                 o = j * n
                 check(L.b200gs_project_fwd_raw(ctypes.byref(v), n, ptr(means), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc),
-                                               ptr(shs_rest), int(bool(anti_aliased)), xy.data_ptr() + 8 * o, depth.data_ptr() + 4 * o,
-                                               radii.data_ptr() + 4 * o, conic.data_ptr() + 12 * o, comp.data_ptr() + 4 * o, ptr(tiles),
-                                               rgb.data_ptr() + 12 * o, clamped.data_ptr() + o, opac.data_ptr() + 4 * o, st),
+                                               ptr(shs_rest), int(st.aa), st.xy.data_ptr() + 8 * o, st.depth.data_ptr() + 4 * o,
+                                               st.radii.data_ptr() + 4 * o, st.conic.data_ptr() + 12 * o, ptr(comp), ptr(tiles),
+                                               st.rgb.data_ptr() + 12 * o, st.clamped.data_ptr() + o, st.opac.data_ptr() + 4 * o, stream),
                       "b200gs_project_fwd_raw")
-        row_index = torch.empty(wn, dtype=torch.int32, device=dev)
-        ws = torch.empty(max(int(L.b200gs_pack_rows_workspace_bytes(wn)), 256), dtype=torch.uint8, device=dev)
-        gv = views[rank]
-        W, H = gv.width, gv.height
-        key = (id(group) if group is not None else None, world, n)
 
-        def pack(seg_cap, rows, d_count):
-            with ops._stage("pack"):
-                check(L.b200gs_pack_rows(wn, n, seg_cap, ptr(xy), ptr(depth), ptr(conic), ptr(comp), ptr(opac), ptr(rgb), ptr(radii), ptr(ws),
-                                         ws.numel(), ptr(row_index), ptr(rows), ptr(d_count), st), "b200gs_pack_rows")
+
+class _ProjectShard(torch.autograd.Function):
+    """Node A of a sharded step: raw shard parameters -> the mean2D of every (camera, Gaussian) pair, one [n,2] tensor per camera
+    (graph tensors: the distributed density controller calls retain_grad() on them, distributed_vanilla_density_controller.py:
+    16-22).  Everything else the projection produces travels to node B through the shared _ShardStep.  backward = K8 for all
+    cameras in one launch, reading its cotangents straight from the gradient rows node B's backward obtained (local buffer
+    after the return all-to-all, or the camera owners' buffers over NVLink)."""
+
+    @staticmethod
+    def forward(ctx, means, log_scales, raw_quats, opac_logits, shs_dc, shs_rest, st: _ShardStep):
+        means, log_scales, raw_quats = means.contiguous(), log_scales.contiguous(), raw_quats.contiguous()
+        ol = opac_logits.contiguous().reshape(-1)
+        shs_dc, shs_rest = shs_dc.contiguous(), shs_rest.contiguous()
+        _project_shard(st, means, log_scales, raw_quats, ol, shs_dc, shs_rest)
+        ctx.st = st
+        ctx.opac_shape = tuple(opac_logits.shape)
+        ctx.save_for_backward(means, log_scales, raw_quats, ol, shs_dc, shs_rest)
+        return tuple(st.xy[j * st.n:(j + 1) * st.n] for j in range(st.world))
+
+    @staticmethod
+    def backward(ctx, *_grad_xys):
+        # the mean2D cotangents are columns 0..1 of the gradient rows already (node B handed them to autograd only so that
+        # `.grad` of the per-camera tensors gets populated); K8 reads the full rows
+        import ctypes
+        from . import ops
+        from ._lib import B200gsView, check, lib, ptr
+        L = lib()
+        st = ctx.st
+        means, log_scales, raw_quats, ol, shs_dc, shs_rest = ctx.saved_tensors
+        dev, n, world = means.device, st.n, st.world
+        if st.v_rows is None:
+            raise RuntimeError("b200gs sharded renderer: backward of the projection ran before the rasterization's backward")
+        f32 = dict(dtype=torch.float32, device=dev)
+        v_means, v_ls, v_q = torch.empty(n, 3, **f32), torch.empty(n, 3, **f32), torch.empty(n, 4, **f32)
+        v_ol, v_dc, v_rest = torch.empty(n, **f32), torch.empty_like(shs_dc), torch.empty_like(shs_rest)
+        stream = ops._stream()
+        with ops._stage("project_bwd"):
+            if world <= 8:
+                arr = (B200gsView * world)(*st.cam_views)
+                rows = (ctypes.c_void_p * world)(*[int(p) for p in st.v_rows])
+                check(L.b200gs_project_bwd_rows_multi(arr, world, n, ptr(means), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc), ptr(shs_rest),
+                                                      int(st.aa), ptr(st.radii), ptr(st.clamped), ptr(st.row_index), rows, ptr(v_means), ptr(v_ls),
+                                                      ptr(v_q), ptr(v_ol), ptr(v_dc), ptr(v_rest), stream), "b200gs_project_bwd_rows_multi")
+            else:
+                for j, view in enumerate(st.cam_views):
+                    check(L.b200gs_project_bwd_rows(ctypes.byref(view), n, ptr(means), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc),
+                                                    ptr(shs_rest), int(st.aa), st.radii.data_ptr() + 4 * j * n, st.clamped.data_ptr() + j * n,
+                                                    st.row_index.data_ptr() + 4 * j * n, int(st.v_rows[j]), 1 if j > 0 else 0, ptr(v_means),
+                                                    ptr(v_ls), ptr(v_q), ptr(v_ol), ptr(v_dc), ptr(v_rest), stream), "b200gs_project_bwd_rows")
+        st.v_send = None
+        return v_means, v_ls, v_q, v_ol.reshape(ctx.opac_shape), v_dc, v_rest, None
+
+
+class _ExchangeRasterize(torch.autograd.Function):
+    """Node B of a sharded step: (projected shard of every camera) -> this rank's image.
+    forward : device-side stable compaction of the visible splats into [.,12] rows, written either into a local send buffer
+              (-> ONE all_to_all_single) or â€” peer mode â€” straight into the camera owners' receive buffers over NVLink by the pack
+              kernel itself; K2-K7 read the received rows in place, pair buffers sized lazily from the previous step.
+              Steady state has NO host sync: every destination gets a fixed-size block of rows (capacity = 1.15 x the previous
+              step's GLOBAL maximum, identical on all ranks; unused rows are zero = culled), so no size exchange is needed; this
+              step's global maximum (one 8-byte all_reduce, which in peer mode is also the barrier that tells a rank its receive
+              buffer is complete) is read back after the rest of the forward has been enqueued and, if it exceeded the capacity
+              on ANY rank, ALL ranks redo the forward with the exact, synchronising exchange (first step, or a > 15 % jump).
+    backward: K7 accumulates into a [R,12] gradient row buffer; the rows return through the mirrored all_to_all_single, or â€”
+              peer mode â€” stay where they are and node A's K8 pulls them from the owners after one barrier."""
+
+    @staticmethod
+    def forward(ctx, bg, st: _ShardStep, *xys):
+        from . import ops
+        from ._lib import MODE_GSPLAT, check, lib, ptr
+        import ctypes
+        L = lib()
+        dev = bg.device
+        n, world, rank, group = st.n, st.world, st.rank, st.group
+        wn = world * n
+        stream = ops._stream()
+        bg = bg.contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        st.row_index = torch.empty(wn, dtype=torch.int32, device=dev)
+        ws = torch.empty(max(int(L.b200gs_pack_rows_workspace_bytes(wn)), 256), dtype=torch.uint8, device=dev)
+        gv = st.views[rank]
+        W, H = gv.width, gv.height
+        key = _group_key(group, world)
 
         def exact():
             """size exchange + host syncs: first step and overflow fallback"""
             rows = torch.empty(wn, ROW_FLOATS, **f32)          # upper bound; the first sum(V_j) rows are the send buffer
             d_count = torch.empty(1, dtype=torch.int64, device=dev)
-            pack(0, rows, d_count)
+            with ops._stage("pack"):
+                check(L.b200gs_pack_rows(wn, n, 0, ptr(st.xy), ptr(st.depth), ptr(st.conic), None, ptr(st.opac), ptr(st.rgb), ptr(st.radii),
+                                         ptr(ws), ws.numel(), ptr(st.row_index), ptr(rows), ptr(d_count), stream), "b200gs_pack_rows")
             last = torch.arange(1, world + 1, device=dev, dtype=torch.int64) * n - 1
-            ends = row_index[last].to(torch.int64) + (radii[last] > 0).to(torch.int64)          # cumulative visible counts per camera
+            ends = st.row_index[last].to(torch.int64) + (st.radii[last] > 0).to(torch.int64)     # cumulative visible counts per camera
             counts = torch.empty(2 * world + 1, dtype=torch.int64, device=dev)                   # [send | recv | global max]
             counts[:world] = ends - torch.cat([ends.new_zeros(1), ends[:-1]])
             dist.all_to_all_single(counts[world:2 * world], counts[:world], group=group)
@@ -229,116 +414,277 @@ class _ShardedRasterize(torch.autograd.Function):
             recv = torch.empty(sum(recv_counts), ROW_FLOATS, **f32)
             dist.all_to_all_single(recv, rows[:sum(send_counts)], output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
             binning, out = ops.bin_and_blend_rows(MODE_GSPLAT, W, H, recv, bg, True)
-            _EXCHANGE_CAP[key] = int(gmax * EXCHANGE_SLACK) + 1024
+            cap = int(gmax * EXCHANGE_SLACK) + 1024
+            with _STATE_LOCK:
+                _EXCHANGE_CAP[key] = cap
+            if st.peer is not None:
+                st.peer.ensure(cap)                      # collective: every rank takes this branch in the same step
             return (send_counts, recv_counts), recv, binning, out
 
-        cap = _EXCHANGE_CAP.get(key)
+        with _STATE_LOCK:
+            cap = _EXCHANGE_CAP.get(key)
         result = None
+        st.fixed_cap, st.parity, st.peer_mode = 0, 0, False
         if cap is not None:
-            rows = torch.empty(world * cap, ROW_FLOATS, **f32)
+            use_peer = st.peer is not None and st.peer.ensure(cap)
             d_count = torch.empty(world, dtype=torch.int64, device=dev)
-            pack(cap, rows, d_count)
+            if use_peer:
+                pe = st.peer
+                pe.step += 1
+                st.parity = pe.step & 1
+                name = "recv1" if st.parity else "recv0"
+                dst = (ctypes.c_void_p * world)(*pe.peers[name])
+                with ops._stage("pack"):
+                    check(L.b200gs_pack_rows_peer(wn, n, cap, ptr(st.xy), ptr(st.depth), ptr(st.conic), None, ptr(st.opac), ptr(st.rgb),
+                                                  ptr(st.radii), ptr(ws), ws.numel(), ptr(st.row_index), dst, rank * cap, ptr(d_count), stream),
+                          "b200gs_pack_rows_peer")
+                recv = pe.tensor(name, world * cap)
+            else:
+                rows = torch.empty(world * cap, ROW_FLOATS, **f32)
+                with ops._stage("pack"):
+                    check(L.b200gs_pack_rows(wn, n, cap, ptr(st.xy), ptr(st.depth), ptr(st.conic), None, ptr(st.opac), ptr(st.rgb), ptr(st.radii),
+                                             ptr(ws), ws.numel(), ptr(st.row_index), ptr(rows), ptr(d_count), stream), "b200gs_pack_rows")
             gmax_dev = d_count.max().reshape(1)
+            # global maximum of the block fill; in peer mode ALSO the barrier: when it completes on this rank, every rank's
+            # pack kernel (which precedes its all_reduce in stream order) has finished storing into this rank's buffer
             dist.all_reduce(gmax_dev, op=dist.ReduceOp.MAX, group=group)
             gmax_host = ops._host_counts()
-            check(L.b200gs_publish_i64(ptr(gmax_dev), gmax_host.data_ptr(), 1, st), "b200gs_publish_i64")
+            check(L.b200gs_publish_i64(ptr(gmax_dev), gmax_host.data_ptr(), 1, stream), "b200gs_publish_i64")
             published = torch.cuda.Event()
             published.record()
-            recv = torch.empty(world * cap, ROW_FLOATS, **f32)
-            dist.all_to_all_single(recv, rows, group=group)
+            if not use_peer:
+                recv = torch.empty(world * cap, ROW_FLOATS, **f32)
+                dist.all_to_all_single(recv, rows, group=group)
+                del rows
             binning, out = ops.bin_and_blend_rows(MODE_GSPLAT, W, H, recv, bg, True)
             published.synchronize()                           # long past: the blend has been enqueued behind it
             gmax = int(gmax_host[0])
-            ops._host_counts_pool.append(gmax_host)
+            ops._return_host_counts(gmax_host)
             if gmax <= cap:                                   # same verdict on every rank: gmax is global
-                _EXCHANGE_CAP[key] = int(gmax * EXCHANGE_SLACK) + 1024
+                with _STATE_LOCK:
+                    _EXCHANGE_CAP[key] = int(gmax * EXCHANGE_SLACK) + 1024
                 result = (None, recv, binning, out)
-                ctx.fixed_cap = cap
-            del rows
+                st.fixed_cap, st.peer_mode = cap, use_peer
         if result is None:
-            ctx.fixed_cap = 0
+            st.fixed_cap, st.peer_mode = 0, False             # the exact step exchanges through NCCL in both directions
             result = exact()
-        counts, recv, binning, (image, final_T, n_contrib) = result
-        del xy, depth, conic, comp, rgb, opac
-        ctx.cam_views, ctx.group, ctx.n = cam_views, group, n
-        ctx.counts = counts
-        ctx.aa = bool(anti_aliased)
-        ctx.hw = (H, W)
-        ctx.binning = binning
-        ctx.opac_shape = tuple(opac_logits.shape)
-        ctx.save_for_backward(means, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, recv, final_T, n_contrib, radii, clamped, row_index)
+        st.counts, st.recv, st.binning, (image, st.final_T, st.n_contrib) = result
+        st.hw = (H, W)
+        st.xy = st.depth = st.conic = st.rgb = st.opac = None      # consumed: the rows hold everything from here on
+        st.v_rows = None
+        ctx.st = st
+        ctx.save_for_backward(bg)
         return image
 
     @staticmethod
     def backward(ctx, v_image):
-        import ctypes
         from ._lib import MODE_GSPLAT, check, lib, ptr
         from . import ops
         L = lib()
-        means, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, recv, final_T, n_contrib, radii, clamped, offsets = ctx.saved_tensors
-        dev = means.device
-        n = ctx.n
-        st = ops._stream()
-        H, W = ctx.hw
+        st = ctx.st
+        (bg,) = ctx.saved_tensors
+        dev = bg.device
+        n, world, rank, group = st.n, st.world, st.rank, st.group
+        stream = ops._stream()
+        H, W = st.hw
         v_image = v_image.contiguous()
-        v_recv = torch.zeros_like(recv)
-        with ops._stage("blend_bwd"):
-            check(L.b200gs_blend_bwd_rows(MODE_GSPLAT, W, H, ptr(ctx.binning.tile_ranges), ptr(ctx.binning.sorted_ids), ptr(recv), ptr(bg),
-                                          ptr(final_T), ptr(n_contrib), ptr(v_image), 3, 1, None, ptr(v_recv), st), "b200gs_blend_bwd_rows")
-        if ctx.fixed_cap:
-            v_send = torch.empty_like(v_recv)
-            dist.all_to_all_single(v_send, v_recv, group=ctx.group)
+        cap = st.fixed_cap
+        peer_mode = st.peer_mode
+        if peer_mode:
+            v_recv = st.peer.tensor("vrecv", world * cap)
+            v_recv.zero_()
         else:
-            send_counts, recv_counts = ctx.counts
-            v_send = torch.empty(max(sum(send_counts), 1), ROW_FLOATS, dtype=torch.float32, device=dev)
-            dist.all_to_all_single(v_send[:sum(send_counts)], v_recv, output_split_sizes=send_counts, input_split_sizes=recv_counts,
-                                   group=ctx.group)
-        f32 = dict(dtype=torch.float32, device=dev)
-        v_means, v_ls, v_q = torch.empty(n, 3, **f32), torch.empty(n, 3, **f32), torch.empty(n, 4, **f32)
-        v_ol, v_dc, v_rest = torch.empty(n, **f32), torch.empty_like(shs_dc), torch.empty_like(shs_rest)
-        with ops._stage("project_bwd"):
-            for j, view in enumerate(ctx.cam_views):
-                check(L.b200gs_project_bwd_rows(ctypes.byref(view), n, ptr(means), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc),
-                                                ptr(shs_rest), int(ctx.aa), radii.data_ptr() + 4 * j * n, clamped.data_ptr() + j * n,
-                                                offsets.data_ptr() + 4 * j * n, ptr(v_send), 1 if j > 0 else 0, ptr(v_means), ptr(v_ls),
-                                                ptr(v_q), ptr(v_ol), ptr(v_dc), ptr(v_rest), st), "b200gs_project_bwd_rows")
-        if ctx.xy_grads_out is not None:
-            # per-camera mean2D gradients for the distributed density controller (distributed_vanilla_density_controller.py:16-47)
-            for j in range(len(ctx.cam_views)):
-                g = torch.zeros(n, 2, **f32)
-                vis = radii[j * n:(j + 1) * n] > 0
-                g[vis] = v_send[offsets[j * n:(j + 1) * n][vis].long(), 0:2]
-                ctx.xy_grads_out.append(g)
-        return v_means, v_ls, v_q, v_ol.reshape(ctx.opac_shape), v_dc, v_rest, None, None, None, None, None, None
+            v_recv = torch.zeros_like(st.recv)
+        with ops._stage("blend_bwd"):
+            check(L.b200gs_blend_bwd_rows(MODE_GSPLAT, W, H, ptr(st.binning.tile_ranges), ptr(st.binning.sorted_ids), ptr(st.recv), ptr(bg),
+                                          ptr(st.final_T), ptr(st.n_contrib), ptr(v_image), 3, 1, None, ptr(v_recv), stream), "b200gs_blend_bwd_rows")
+        grads = []
+        if peer_mode:
+            # one barrier: every camera owner's K7 is done.  Entry (j, i) with row_index = j*cap + k lives at row rank*cap + k of owner
+            # j's buffer: shift each base pointer so that K8 can index it with row_index directly.
+            token = torch.zeros(1, dtype=torch.int32, device=dev)
+            dist.all_reduce(token, group=group)
+            pe = st.peer
+            st.v_rows = [pe.peers["vrecv"][j] + (rank * cap - j * cap) * ROW_FLOATS * 4 for j in range(world)]
+            st.v_send = v_recv
+            for j in range(world):
+                g = torch.zeros(n, 2, dtype=torch.float32, device=dev)
+                vis = st.radii[j * n:(j + 1) * n] > 0
+                k = st.row_index[j * n:(j + 1) * n][vis].long() - j * cap
+                ok = k >= 0
+                src = pe.peer_tensor("vrecv", j, world * cap)
+                sel = torch.nonzero(vis).reshape(-1)[ok]
+                g[sel] = src[rank * cap + k[ok], 0:2]
+                grads.append(g)
+        else:
+            if cap:
+                v_send = torch.empty_like(v_recv)
+                dist.all_to_all_single(v_send, v_recv, group=group)
+            else:
+                send_counts, recv_counts = st.counts
+                v_send = torch.empty(max(sum(send_counts), 1), ROW_FLOATS, dtype=torch.float32, device=dev)
+                dist.all_to_all_single(v_send[:sum(send_counts)], v_recv, output_split_sizes=send_counts, input_split_sizes=recv_counts, group=group)
+            st.v_send = v_send
+            st.v_rows = [v_send.data_ptr()] * world
+            for j in range(world):
+                g = torch.zeros(n, 2, dtype=torch.float32, device=dev)
+                idx = st.row_index[j * n:(j + 1) * n]
+                vis = (st.radii[j * n:(j + 1) * n] > 0) & (idx >= 0)
+                g[vis] = v_send[idx[vis].long(), 0:2]
+                grads.append(g)
+        st.recv = st.binning = st.final_T = st.n_contrib = None
+        return (None, None) + tuple(grads)
 
 
-def _sharded_apply(fn, xy_grads_out, *args):
-    """apply() with a side list that backward fills with the per-camera mean2D gradients"""
-    class _Bound(fn):
-        @staticmethod
-        def forward(ctx, *a):
-            ctx.xy_grads_out = xy_grads_out
-            return fn.forward(ctx, *a)
-    return _Bound.apply(*args)
+@dataclass
+class B200DistributedRendererConfig:
+    """YAML-selectable config, the fields of `GSplatDistributedRenderer` (gsplat_distributed_renderer.py:16-38)."""
+    block_size: int = 16
+    anti_aliased: bool = True
+    filter_2d_kernel_size: float = 0.3
+    tile_based_culling: bool = True
+    redistribute_interval: int = 1000
+    redistribute_until: int = 15_000
+    redistribute_threshold: float = 1.1
+    fused: bool = True
+    peer_exchange: bool = True
+
+    def instantiate(self, *args, **kwargs):
+        return B200DistributedRenderer(config=self)
 
 
-class B200DistributedRenderer(torch.nn.Module):
-    """Drop-in for ``GSplatDistributedRendererImpl.forward`` (gsplat_distributed_renderer.py:313-414): `pc` holds THIS rank's
-    shard; returns this rank's image plus the per-camera projection results the distributed density controller reads
-    (``distributed_vanilla_density_controller.py:16-47``)."""
+def replace_tensors_to_properties(tensors: Dict[str, torch.Tensor], optimizers) -> Dict[str, torch.nn.Parameter]:
+    """New parameter tensors into the optimizers' single-tensor param groups, optimizer state reset; properties that no optimizer
+    holds become frozen Parameters.  Same contract as DensityControllerUtils.replace_tensors_to_properties with selector=None
+    (internal/density_controllers/density_controller.py:148-209), which the reference's training_setup uses for sharding."""
+    new_parameters = {}
+    for opt in optimizers:
+        for group in opt.param_groups:
+            tensor = tensors.get(group["name"], None)
+            if tensor is None:
+                continue
+            assert len(group["params"]) == 1
+            assert group["name"] not in new_parameters, "parameter `{}` appears in multiple optimizers".format(group["name"])
+            stored_state = opt.state.get(group["params"][0], None)
+            new_param = torch.nn.Parameter(tensor.requires_grad_(True))
+            if stored_state is not None:
+                stored_state["exp_avg"] = torch.zeros_like(tensor)
+                stored_state["exp_avg_sq"] = torch.zeros_like(tensor)
+                del opt.state[group["params"][0]]
+                group["params"][0] = new_param
+                opt.state[new_param] = stored_state
+            else:
+                group["params"][0] = new_param
+            new_parameters[group["name"]] = new_param
+    for k, v in tensors.items():
+        if k not in new_parameters:
+            new_parameters[k] = torch.nn.Parameter(v, requires_grad=False)
+    return new_parameters
 
-    def __init__(self, anti_aliased: bool = True, group=None, fused: bool = True, want_xy_grads: bool = False,
-                 cache_cameras: bool = True):
-        """fused: when `pc` is the vanilla Gaussian model, run the whole step as one autograd node on the raw parameters
-        (_ShardedRasterize: device-side packing, rows consumed in place, one host sync); otherwise the generic path
-        below, built from the same ops the single-GPU renderers use."""
+
+def all_to_all_rows_by_destination(local: torch.Tensor, destination: torch.Tensor, recv_counts: List[int], world: int, group=None) -> torch.Tensor:
+    """Rows of `local` go to rank destination[i]; returns the rows this rank receives, concatenated in source-rank order
+    (gsplat_distributed_renderer.py:464-479, with one all_to_all_single instead of the list form)."""
+    order = torch.argsort(destination, stable=True)
+    send = local[order].contiguous()
+    send_counts = torch.bincount(destination, minlength=world).tolist()
+    out = local.new_empty((int(sum(recv_counts)),) + tuple(local.shape[1:]))
+    dist.all_to_all_single(out, send, output_split_sizes=[int(c) for c in recv_counts], input_split_sizes=[int(c) for c in send_counts], group=group)
+    return out
+
+
+class B200DistributedRenderer(Renderer):
+    """Drop-in for ``GSplatDistributedRendererImpl`` (gsplat_distributed_renderer.py:41-516): `pc` holds THIS rank's shard;
+    ``training_setup`` shards the model and its optimizers by contiguous index ranges (:63-118), ``forward`` returns this rank's
+    image plus what the distributed density controller reads â€” ``projection_results_list`` (per camera: radii, xys (graph tensor:
+    ``retain_grad()`` / ``.grad`` work), depths, conics, compensation), ``visible_mask_list``, ``cameras``,
+    ``xys_grad_scale_required`` (:407-414; distributed_vanilla_density_controller.py:16-47) â€” and ``after_training_step``
+    rebalances the shards incl. the Adam moments (:416-510)."""
+
+    def __init__(self, anti_aliased: bool = True, group=None, fused: bool = True, want_xy_grads: bool = False, cache_cameras: bool = True,
+                 config: Optional[B200DistributedRendererConfig] = None, peer_exchange: bool = True):
+        """fused: when `pc` is the vanilla Gaussian model, run the step as two autograd nodes on the raw parameters (multi-view K1 /
+        K8, device-side packing, rows consumed in place, no host sync in the steady state); otherwise the generic path below,
+        built from the same ops the single-GPU renderers use.  peer_exchange: store / pull the rows through peer-mapped buffers
+        over NVLink instead of NCCL all-to-alls (falls back to NCCL when CUDA IPC is unavailable or the group has > 8 ranks)."""
         super().__init__()
-        self.anti_aliased = anti_aliased
+        self.config = config if config is not None else B200DistributedRendererConfig(anti_aliased=anti_aliased, fused=fused,
+                                                                                        peer_exchange=peer_exchange)
+        self.anti_aliased = self.config.anti_aliased
         self.group = group
-        self.fused = fused
-        self.want_xy_grads = want_xy_grads   # fused path: also materialise per-camera dL/d(mean2D) for the density controller
+        self.fused = self.config.fused
+        self.peer_exchange = self.config.peer_exchange
+        self.want_xy_grads = want_xy_grads   # kept for callers of the previous interface: the per-camera gradients are `.grad` of the xys now
         self.cache_cameras = cache_cameras   # False when camera poses are optimised (the packed host view is cached on the camera)
+        self.world_size, self.global_rank = 1, 0
+        self.on_density_changed = None
 
+    # ---- lifecycle (renderer.py:90-100; gaussian_splatting.py:657) ------------------------------------------------------
+    def training_setup(self, module):
+        self.world_size = module.trainer.world_size
+        self.global_rank = module.trainer.global_rank
+        n_gaussians = module.gaussian_model.n_gaussians
+        lo, hi = shard_range(n_gaussians, self.world_size, self.global_rank)
+        new_param_tensors = {name: value[lo:hi] for name, value in module.gaussian_model.properties.items()}
+        module.gaussian_model.properties = replace_tensors_to_properties(new_param_tensors, module.gaussian_optimizers)
+        self.on_density_changed = module.density_updated_by_renderer
+        self.on_density_changed()
+        print(f"rank={self.global_rank}, l={lo}, r={hi}")
+        return None, None
+
+    def after_training_step(self, step: int, module):
+        c = self.config
+        if c.redistribute_interval < 0 or step >= c.redistribute_until or step % c.redistribute_interval != 0:
+            return
+        self.redistribute(module)
+
+    def redistribute(self, module):
+        with torch.no_grad():
+            counts = [0 for _ in range(self.world_size)]
+            dist.all_gather_object(counts, int(module.gaussian_model.get_xyz.shape[0]), group=self.group)
+            if min(counts) * self.config.redistribute_threshold >= max(counts):
+                return
+            self.random_redistribute(module)
+
+    def random_redistribute(self, module):
+        """Every Gaussian (parameters AND Adam moments) moves to a uniformly random rank (gsplat_distributed_renderer.py:447-510)."""
+        model, optimizers = module.gaussian_model, module.gaussian_optimizers
+        world = self.world_size
+        dev = model.get_xyz.device
+        destination = torch.randint(0, world, (model.get_xyz.shape[0],), device=dev)
+        send_counts = torch.bincount(destination, minlength=world)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        recv_counts = recv_counts.tolist()
+
+        def move(t):
+            return all_to_all_rows_by_destination(t, destination, recv_counts, world, self.group)
+
+        new_tensors = {}
+        for opt in optimizers:
+            for group in opt.param_groups:
+                assert len(group["params"]) == 1
+                old = group["params"][0]
+                state = opt.state.get(old, None)
+                new_param = torch.nn.Parameter(move(old.detach()).requires_grad_(True))
+                if state is not None:
+                    state["exp_avg"] = move(state["exp_avg"])
+                    state["exp_avg_sq"] = move(state["exp_avg_sq"])
+                    del opt.state[old]
+                    opt.state[new_param] = state
+                group["params"][0] = new_param
+                new_tensors[group["name"]] = new_param
+        for name in model.get_property_names():
+            if name not in new_tensors:
+                new_tensors[name] = move(model.get_property(name))
+        model.properties = new_tensors
+        if self.on_density_changed is not None:
+            self.on_density_changed()
+
+    def get_available_outputs(self):
+        return {"rgb": RendererOutputInfo("render")}
+
+    # ---- forward ---------------------------------------------------------------------------------------------------------
     def _forward_fused(self, raw, viewpoint_camera, pc, bg_color, scaling_modifier):
         from . import ops
         from ._lib import MODE_GSPLAT
@@ -347,19 +693,25 @@ class B200DistributedRenderer(torch.nn.Module):
         dev = bg_color.device
         flat = gather_views_host(viewpoint_camera, self.group, self.cache_cameras)
         cams = [GatheredView(flat[j], dev) for j in range(world)]
-        views = []
-        for gv in cams:
-            v = ops.make_view(MODE_GSPLAT, gv.width, gv.height, fx=gv.fx, fy=gv.fy, cx=gv.cx, cy=gv.cy, viewmatrix=gv.world_to_camera,
-                              campos=gv.camera_center_host, scale_modifier=scaling_modifier)
-            views.append(v)
-        # the per-camera mean2D gradients (what the distributed density controller reads) are appended to this list by backward
-        xy_grads: Optional[List[torch.Tensor]] = [] if self.want_xy_grads else None
-        img = _sharded_apply(_ShardedRasterize, xy_grads, raw["means"], raw["scales"], raw["rotations"], raw["opacities"], raw["shs_dc"],
-                             raw["shs_rest"], bg_color, views, rank, self.group, self.anti_aliased, int(pc.active_sh_degree))
+        st = _ShardStep()
+        st.views = [ops.make_view(MODE_GSPLAT, gv.width, gv.height, fx=gv.fx, fy=gv.fy, cx=gv.cx, cy=gv.cy, viewmatrix=gv.world_to_camera,
+                                  campos=gv.camera_center_host, scale_modifier=scaling_modifier, eps2d=self.config.filter_2d_kernel_size)
+                    for gv in cams]
+        st.rank, st.world, st.group, st.n = rank, world, self.group, int(raw["means"].shape[0])
+        st.aa, st.sh_degree = bool(self.anti_aliased), int(pc.active_sh_degree)
+        st.peer = _peer_exchange(self.group, dev) if (self.peer_exchange and bg_color.is_cuda and dist.get_backend(self.group) == "nccl") else None
+        st.v_rows = st.v_send = None
+        xys = _ProjectShard.apply(raw["means"], raw["scales"], raw["rotations"], raw["opacities"], raw["shs_dc"], raw["shs_rest"], st)
+        n = st.n
+        projection_results_list = [(st.radii[j * n:(j + 1) * n], xys[j], st.depth[j * n:(j + 1) * n], st.conic[j * n:(j + 1) * n], None)
+                                   for j in range(world)]
+        visible_mask_list = [r[0] > 0 for r in projection_results_list]
+        img = _ExchangeRasterize.apply(bg_color, st, *xys)
         return {
             "render": img.permute(2, 0, 1),
             "cameras": cams,
-            "viewspace_points_grads": xy_grads,     # filled by backward: one [n,2] pixel-unit gradient per camera
+            "projection_results_list": projection_results_list,
+            "visible_mask_list": visible_mask_list,
             "xys_grad_scale_required": True,
         }
 

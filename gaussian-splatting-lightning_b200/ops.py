@@ -11,6 +11,7 @@ Functions
   rasterize_gaussians(...)    gsplat v0 ``rasterize_gaussians``        (gsplat_renderer.py:86-99)
 """
 import ctypes
+import threading
 from typing import Optional, Tuple
 
 import torch
@@ -160,26 +161,37 @@ class Binning:
         self._pending = None
         event_a.synchronize()
         self.rect_pairs, self.coarse_pairs = int(self._host[0]), int(self._host[1])
-        _last_total[key] = (self.coarse_pairs, self.rect_pairs)
+        with _state_lock:
+            _last_total[key] = (self.coarse_pairs, self.rect_pairs)
         return self.coarse_pairs <= cap_coarse and self.rect_pairs <= cap_pairs
 
     def __del__(self):
         try:
-            if self._host is not None and len(_host_counts_pool) < 32:
-                _host_counts_pool.append(self._host)
+            if self._host is not None:
+                _return_host_counts(self._host)
         except Exception:      # interpreter shutdown
             pass
 
 
 _host_counts_pool = []  # pinned int64[8] buffers: [0:4] phase A's copy of the counters, [4:8] phase B's
 _last_total = {}       # key -> (coarse pairs, rect pairs) of the previous view: sizes the next view's buffers in lazy mode
+_state_lock = threading.RLock()   # the two process-wide structures above are shared by every thread that renders (trainer + viewer threads)
 
 TILE_CULLING = True    # exact (tile, splat) culling in K3; False reproduces the reference's full 3-sigma-rect pair list
 LAZY_SLACK = 1.15      # lazy mode: capacity = slack x previous count
 
 
 def _host_counts():
-    return _host_counts_pool.pop() if _host_counts_pool else torch.zeros(8, dtype=torch.int64).pin_memory()
+    with _state_lock:
+        if _host_counts_pool:
+            return _host_counts_pool.pop()
+    return torch.zeros(8, dtype=torch.int64).pin_memory()
+
+
+def _return_host_counts(buf):
+    with _state_lock:
+        if len(_host_counts_pool) < 32:
+            _host_counts_pool.append(buf)
 
 
 def _bin(key, mode, width, height, n, dev, cull, lazy, count_call) -> Binning:
@@ -190,13 +202,15 @@ def _bin(key, mode, width, height, n, dev, cull, lazy, count_call) -> Binning:
     d_counts = torch.empty(4, dtype=torch.int64, device=dev)
     ranges = torch.empty(gx * gy, 2, dtype=torch.int32, device=dev)
     host = _host_counts()
-    prev = _last_total.get(key) if lazy else None
+    with _state_lock:
+        prev = _last_total.get(key) if lazy else None
     sync = prev is None
     with _stage("bin_count"):
         count_call(ptr(ws_a), ws_a.numel(), ptr(d_counts), host.data_ptr(), 1 if sync else 0, st)
     if sync:
         cap_coarse, cap_pairs = int(host[1]), int(host[0])    # exact / an upper bound: cannot overflow
-        _last_total[key] = (cap_coarse, cap_pairs)
+        with _state_lock:
+            _last_total[key] = (cap_coarse, cap_pairs)
         pending = None
     else:
         event_a = torch.cuda.Event()

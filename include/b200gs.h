@@ -225,6 +225,7 @@ B200GS_API int b200gs_loss_bwd(int32_t channels, int32_t width, int32_t height, 
  * b200gs_bin_count_rows (then b200gs_bin_sort) / blend_fwd_rows / blend_bwd_rows: K2-K7 reading the rows IN PLACE (strided
  *     access, no split copies); blend_bwd_rows accumulates into a zero-filled [n,12] gradient row buffer that goes
  *     straight back through the all-to-all.  3 colour channels; cull != 0 enables exact tile culling. */
+#define B200GS_MAX_VIEWS 8      /* cameras per multi-view launch / destination ranks per peer-mode pack (one NVSwitch box) */
 #define B200GS_ROW_FLOATS 12
 #define B200GS_ROW_XY 0
 #define B200GS_ROW_DEPTH 2
@@ -241,6 +242,35 @@ B200GS_API int b200gs_project_bwd_rows(const B200gsView* view, int64_t n, const 
                                        int32_t anti_aliased, const int32_t* radii, const uint8_t* clamped, const int32_t* row_offsets,
                                        const float* v_rows, int32_t accumulate, float* v_means, float* v_log_scales, float* v_raw_quats,
                                        float* v_opacity_logits, float* v_shs_dc, float* v_shs_rest, void* stream);
+/* b200gs_project_fwd_raw_multi / b200gs_project_bwd_rows_multi: K1 / K8 of one shard for ALL n_views (<= B200GS_MAX_VIEWS) cameras of a
+ *     step in one launch each (gsplat constants, raw parameters; sh_degree / sh_stride / scale_modifier of views[0] apply to all).
+ *     fwd: camera-major outputs, view j at elements [j*n, (j+1)*n); parameters and SH blocks are read once per Gaussian.
+ *     bwd: every thread accumulates its Gaussian's gradients over the cameras in registers and writes them once; cotangents are
+ *     [.,12] gradient rows, entry (j, i) reads row row_index[j*n+i] of v_rows[j] — a HOST array of n_views device pointers, each
+ *     of which may address a peer GPU's buffer (the camera owner's gradient rows are pulled over NVLink, no return all-to-all). */
+B200GS_API int b200gs_project_fwd_raw_multi(const B200gsView* views, int32_t n_views, int64_t n, const float* means, const float* log_scales,
+                                            const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
+                                            int32_t anti_aliased, float* xy, float* depth, int32_t* radii, float* conic, float* rgb,
+                                            uint8_t* clamped, float* opacity_out, void* stream);
+B200GS_API int b200gs_project_bwd_rows_multi(const B200gsView* views, int32_t n_views, int64_t n, const float* means, const float* log_scales,
+                                             const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
+                                             int32_t anti_aliased, const int32_t* radii, const uint8_t* clamped, const int32_t* row_index,
+                                             const float* const* v_rows, float* v_means, float* v_log_scales, float* v_raw_quats,
+                                             float* v_opacity_logits, float* v_shs_dc, float* v_shs_rest, void* stream);
+/* b200gs_pack_rows_peer: b200gs_pack_rows in the segmented layout, but segment j's rows (and the zero rows that pad its block) are
+ *     stored straight into peer_rows[j] — the receive buffer of the rank that owns camera j, possibly a peer GPU's memory — at
+ *     rows [peer_block, peer_block + segment_cap) of it; peer_rows is a HOST array of ceil(n/segment_len) device pointers.
+ *     `rows` is unused then (may be NULL); row_index keeps the send-layout numbering j*segment_cap + k.
+ * b200gs_ipc_alloc / _handle / _open / _close / _free: device buffers that peer processes of the same box can map (cudaMalloc +
+ *     CUDA IPC): the exchange buffers of the sharded renderer.  handle = 64 bytes to pass to the peers by any host channel. */
+B200GS_API int b200gs_pack_rows_peer(int64_t n, int64_t segment_len, int64_t segment_cap, const float* xy, const float* depth,
+                                     const float* conic, const float* comp, const float* opacity, const float* rgb, const int32_t* radii,
+                                     void* workspace, size_t workspace_bytes, int32_t* row_index, float* const* peer_rows, int64_t peer_block,
+                                     int64_t* d_count, void* stream);
+B200GS_API int b200gs_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+B200GS_API int b200gs_ipc_open(const unsigned char* handle64, void** dev_ptr);
+B200GS_API int b200gs_ipc_close(void* dev_ptr);
+B200GS_API int b200gs_ipc_free(void* dev_ptr);
 B200GS_API size_t b200gs_pack_rows_workspace_bytes(int64_t n);
 B200GS_API int b200gs_pack_rows(int64_t n, int64_t segment_len, int64_t segment_cap, const float* xy, const float* depth,
                                 const float* conic, const float* comp, const float* opacity, const float* rgb, const int32_t* radii,

@@ -99,6 +99,106 @@ def test_exchange_rows_world2_gloo():
         assert msg == "ok", f"rank {rank}: {msg}"
 
 
+class _FakeModel:
+    """The slice of the reference's GaussianModel interface the renderer's sharding code touches (gaussian.py: properties dict,
+    get_property_names / get_property, n_gaussians, get_xyz)."""
+
+    def __init__(self, props):
+        self.properties = props
+
+    @property
+    def n_gaussians(self):
+        return self.properties["means"].shape[0]
+
+    @property
+    def get_xyz(self):
+        return self.properties["means"]
+
+    def get_property_names(self):
+        return list(self.properties.keys())
+
+    def get_property(self, name):
+        return self.properties[name]
+
+
+class _FakeModule:
+    def __init__(self, model, optimizers, world, rank):
+        import types
+        self.gaussian_model, self.gaussian_optimizers = model, optimizers
+        self.trainer = types.SimpleNamespace(world_size=world, global_rank=rank)
+        self.density_changes = 0
+
+    def density_updated_by_renderer(self):
+        self.density_changes += 1
+
+
+def _shard_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from b200gs.distributed import B200DistributedRenderer, B200DistributedRendererConfig, shard_range
+        n = 101
+        ids = torch.arange(n, dtype=torch.float32)
+        props = {"means": torch.nn.Parameter(ids[:, None].repeat(1, 3).clone()), "opacities": torch.nn.Parameter(ids[:, None].clone()),
+                 "frozen": torch.nn.Parameter(ids[:, None].clone(), requires_grad=False)}
+        opts = [torch.optim.Adam([{"params": [props["means"]], "name": "means", "lr": 0.0}]),
+                torch.optim.Adam([{"params": [props["opacities"]], "name": "opacities", "lr": 0.0}])]
+        model = _FakeModel(dict(props))
+        module = _FakeModule(model, opts, world, rank)
+        r = B200DistributedRendererConfig(redistribute_interval=10, redistribute_until=100, redistribute_threshold=1.0).instantiate()
+        # training_setup: contiguous index shards (gsplat_distributed_renderer.py:63-118), optimizers follow, module notified
+        assert r.training_setup(module) == (None, None)
+        lo, hi = shard_range(n, world, rank)
+        assert model.n_gaussians == hi - lo and module.density_changes == 1
+        assert torch.equal(model.properties["means"][:, 0].detach(), ids[lo:hi]) and torch.equal(model.properties["frozen"][:, 0], ids[lo:hi])
+        assert opts[0].param_groups[0]["params"][0] is model.properties["means"] and model.properties["means"].requires_grad
+        assert not model.properties["frozen"].requires_grad
+        # give Adam a state whose rows are recognisable: exp_avg = 10 * id, exp_avg_sq = 100 * id
+        for name, opt in zip(("means", "opacities"), opts):
+            p_ = model.properties[name]
+            p_.grad = torch.zeros_like(p_)
+            opt.step()
+            st = opt.state[p_]
+            st["exp_avg"] = p_.detach() * 10
+            st["exp_avg_sq"] = p_.detach() * 100
+        torch.manual_seed(1234 + rank)
+        r.after_training_step(5, module)                # not a multiple of the interval: nothing happens
+        assert model.n_gaussians == hi - lo
+        r.after_training_step(10, module)               # threshold 1.0: shards of 50 / 51 are unbalanced enough
+        assert module.density_changes == 2
+        got = model.properties["means"].detach()
+        for name, opt in zip(("means", "opacities"), opts):
+            p_ = opt.param_groups[0]["params"][0]
+            assert p_ is model.properties[name] and p_.requires_grad
+            st = opt.state[p_]
+            assert torch.equal(st["exp_avg"], p_.detach() * 10) and torch.equal(st["exp_avg_sq"], p_.detach() * 100)   # rows moved together
+        assert torch.equal(model.properties["opacities"].detach()[:, 0], got[:, 0]) and torch.equal(model.properties["frozen"][:, 0], got[:, 0])
+        everyone = [None] * world
+        dist.all_gather_object(everyone, got[:, 0].tolist())
+        assert sorted(x for part in everyone for x in part) == ids.tolist()          # nothing lost, nothing duplicated
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_training_setup_sharding_and_redistribute_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", f"rank {rank}: {msg}"
+
+
 def test_shard_range_matches_reference_rule():
     from b200gs.distributed import shard_range
     # gsplat_distributed_renderer.py:76-83: per = round(n / W); l = per * rank; r = l + per, last rank takes the remainder
