@@ -290,6 +290,17 @@ int b200gs_blend_fwd(int32_t mode, int32_t width, int32_t height, int32_t channe
                             pix_stride, ch_stride, final_T, n_contrib, alpha, (cudaStream_t)stream);
 }
 
+int b200gs_blend_fwd_hits(int32_t mode, int32_t width, int32_t height, int32_t channels, const int32_t* tile_ranges,
+                          const int32_t* sorted_ids, const float* xy, const float* conic, const float* opacity,
+                          const float* colors, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride,
+                          float* final_T, int32_t* n_contrib, float* alpha, uint8_t* hit_any, void* stream) {
+    B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
+    B200GS_CHECK_ARG(width > 0 && height > 0, "bad size");
+    B200GS_CHECK_ARG(tile_ranges && image && final_T && n_contrib && hit_any, "NULL output/range pointer");
+    return launch_blend_fwd(mode, width, height, channels, tile_ranges, sorted_ids, 0, xy, conic, opacity, colors, bg, image,
+                            pix_stride, ch_stride, final_T, n_contrib, alpha, (cudaStream_t)stream, hit_any);
+}
+
 int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int32_t channels, const int32_t* tile_ranges,
                      const int32_t* sorted_ids, const float* xy, const float* conic, const float* opacity,
                      const float* colors, const float* bg, const float* final_T, const int32_t* n_contrib,

@@ -257,15 +257,18 @@ __device__ __forceinline__ void stage_async(float4* slot, int g, const SplatStri
     }
 }
 
-template <int CH, bool GSPLAT, bool ROWS>
+// HITS: also mark every splat that contributed to at least one pixel (gsplat's `means2d.has_hit_any_pixels`, read by
+// SelectiveAdam, optimizers.py:39, and exported as `acc_vis`, gsplat_v1_renderer.py:287): one byte store per (warp, contributing entry).
+template <int CH, bool GSPLAT, bool ROWS, bool HITS>
 __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_async_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
                                                               const int32_t* __restrict__ ids, const SplatStrides st, const float* __restrict__ xy,
                                                               const float* __restrict__ conic, const float* __restrict__ opacity,
                                                               const float* __restrict__ colors, const float* __restrict__ bg,
                                                               float* __restrict__ image, int64_t pix_stride, int64_t ch_stride,
                                                               float* __restrict__ final_T, int32_t* __restrict__ n_contrib,
-                                                              float* __restrict__ alpha_out) {
+                                                              float* __restrict__ alpha_out, uint8_t* __restrict__ hit_any) {
     __shared__ float4 s_buf[2][(BLOCK_PIX + 1) * 3];
+    __shared__ int32_t s_gid[HITS ? BLOCK_PIX + 1 : 1];
     __shared__ unsigned char s_mask[BLOCK_PIX];
     __shared__ unsigned short s_list[NWARP][BLOCK_PIX + 2 * LIST_PAD];
 
@@ -291,7 +294,8 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_asy
     float C[4] = {0.f, 0.f, 0.f, 0.f};
 
     // prologue: batch 0 in flight, ids of batch 1 in a register
-    if (tid < total) stage_async<CH, ROWS>(&s_buf[0][tid * 3], __ldg(ids + range.x + tid), st, xy, conic, opacity, colors);
+    int cur_id = (tid < total) ? __ldg(ids + range.x + tid) : 0;
+    if (tid < total) stage_async<CH, ROWS>(&s_buf[0][tid * 3], cur_id, st, xy, conic, opacity, colors);
     int next_id = (BLOCK_PIX + tid < total) ? __ldg(ids + range.x + BLOCK_PIX + tid) : 0;
 
     int buf = 0;
@@ -309,7 +313,9 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_asy
             s_rec[tid * 3 + 1] = make_float4((-0.5f * LOG2E) * Cc, o, c0, CH > 1 ? c1 : 0.f);
             if (CH > 2) s_rec[tid * 3 + 2] = make_float4(c2, CH > 3 ? c3 : 0.f, 0.f, 0.f);
             s_mask[tid] = (unsigned char)block_mask(mx, my, A, B, Cc, o, ox, oy);
+            if (HITS) s_gid[tid] = cur_id;
         }
+        cur_id = next_id;
         // next batch: the other buffer was last read by the blend loop of the previous iteration, which every warp left
         // before the barrier above
         if (base + BLOCK_PIX + tid < total) stage_async<CH, ROWS>(&s_buf[buf ^ 1][tid * 3], next_id, st, xy, conic, opacity, colors);
@@ -343,6 +349,9 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_asy
                 T = take ? nT : T;
                 last = take ? base + j + 1 : last;
                 done = done || stop;
+                if (HITS) {
+                    if (__any_sync(FULL, take) && lane == 0) hit_any[s_gid[j]] = 1;
+                }
             }
         }
     }
@@ -623,11 +632,16 @@ __global__ void __launch_bounds__(BLOCK_PIX, (RB == 4 && !ABS) ? 4 : 1) blend_bw
 // exchange combines the halves; then lane (e, 0) finishes the mean/conic algebra of entry e and issues its 5 atomics
 // while lane (e, 1) issues opacity + colours: 16 entries are written by 32 lanes in parallel.  No shuffles in the
 // reduction, no serial writer: ~12 instead of 63 instructions per (warp, entry) after the evaluation.
+// With the absgrad side channel (gsplat's `means2d.absgrad`, vanilla_density_controller.py:112-113) each pixel stores two more
+// values per entry, |dL/dmean2D.x| and |dL/dmean2D.y| of its own sample (they are summed without signs, so they cannot be
+// derived from the moments): float4 rows, 3 CTAs per SM instead of 4.
 constexpr int GE = 16;                          // list entries per reduction group
-constexpr int VAL_ROW = 32 * 8 + 16;            // bytes per entry row of the value tile: 32 x {go, fac} + pad
 constexpr int BWD_LIST = BLOCK_PIX + GE + 8;    // per-warp list: GE dummies in front (reverse walk), 8 behind
 
+template <bool ABS>
 struct TrSmem {
+    static constexpr int VAL_BYTES = ABS ? 16 : 8;              // per (entry, pixel): {go, fac} or {go, fac, |gx|, |gy|}
+    static constexpr int VAL_ROW = 32 * VAL_BYTES + 16;         // bytes per entry row of the value tile (+ pad)
     float4 rec[(BLOCK_PIX + 1) * 3];
     float4 vo[NWARP][32];
     unsigned char val[NWARP][GE * VAL_ROW];
@@ -635,10 +649,10 @@ struct TrSmem {
     unsigned char mask[BLOCK_PIX];
     int wmax[NWARP];
 };
-static_assert(sizeof(TrSmem) <= 57344, "4 CTAs per SM need <= 56 KB each");
+static_assert(sizeof(TrSmem<false>) <= 57344, "4 CTAs per SM need <= 56 KB each");
 
-template <int CH, bool GSPLAT>
-__global__ void __launch_bounds__(BLOCK_PIX, 4) blend_bwd_tr_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
+template <int CH, bool GSPLAT, bool ABS>
+__global__ void __launch_bounds__(BLOCK_PIX, ABS ? 3 : 4) blend_bwd_tr_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
                                                                     const int32_t* __restrict__ ids, const SplatStrides st,
                                                                     const float* __restrict__ xy, const float* __restrict__ conic,
                                                                     const float* __restrict__ opacity, const float* __restrict__ colors,
@@ -646,9 +660,12 @@ __global__ void __launch_bounds__(BLOCK_PIX, 4) blend_bwd_tr_kernel(int width, i
                                                                     const int32_t* __restrict__ n_contrib, const float* __restrict__ v_image,
                                                                     int64_t pix_stride, int64_t ch_stride, const float* __restrict__ v_alpha,
                                                                     float sx, float sy, float* __restrict__ v_xy, float* __restrict__ v_conic,
-                                                                    float* __restrict__ v_opacity, float* __restrict__ v_colors) {
+                                                                    float* __restrict__ v_opacity, float* __restrict__ v_colors,
+                                                                    float* __restrict__ v_xy_abs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TrSmem& sm = *reinterpret_cast<TrSmem*>(smem_raw);
+    typedef TrSmem<ABS> Smem;
+    constexpr int VAL_ROW = Smem::VAL_ROW, VAL_BYTES = Smem::VAL_BYTES;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     float4* s_rec = sm.rec;
 
     const int tid = threadIdx.x;
@@ -690,9 +707,9 @@ __global__ void __launch_bounds__(BLOCK_PIX, 4) blend_bwd_tr_kernel(int width, i
 
     float T = Tf;
     float D = 0.f;   // <colour accumulated behind the current splat, v_image> for this pixel
-    unsigned char* my_val = sm.val[warp] + lane * 8;              // eval phase: this pixel's {go, fac} column
+    unsigned char* my_val = sm.val[warp] + lane * VAL_BYTES;      // eval phase: this pixel's value column
     const int re = lane & (GE - 1), rh = lane >> 4;               // reduce phase: entry and pixel half of this lane
-    const float4* my_row = reinterpret_cast<const float4*>(sm.val[warp] + re * VAL_ROW + rh * 128);
+    const float4* my_row = reinterpret_cast<const float4*>(sm.val[warp] + re * VAL_ROW + rh * 16 * VAL_BYTES);
     const float4* my_vo = sm.vo[warp] + rh * 16;
     // origin of the warp's 8x4 block of pixel samples; the reduce lane's pixels are rows 2 rh, 2 rh + 1 of it
     const float bx0 = ox + float((warp & 1) << 3), by0 = oy + float((warp >> 1) << 2);
@@ -735,7 +752,7 @@ __global__ void __launch_bounds__(BLOCK_PIX, 4) blend_bwd_tr_kernel(int width, i
                 const float oG = r1.y * G;
                 const float a = fminf(amax, oG);
                 const bool valid = (j < rel_last) && !(p2 > 0.0f) && (a >= ALPHA_MIN);
-                float go = 0.f, fac = 0.f;
+                float go = 0.f, fac = 0.f, gax = 0.f, gay = 0.f;
                 if (valid) {
                     const float ra = 1.0f / (1.0f - a);
                     T *= ra;
@@ -752,8 +769,14 @@ __global__ void __launch_bounds__(BLOCK_PIX, 4) blend_bwd_tr_kernel(int width, i
                     D = fmaf(fac, S, D);
                     if (!GSPLAT || (oG <= 0.999f)) go = G * v_al;
                     vm |= 1u << u;
+                    if (ABS) {   // |dL/dmean2D| of this sample: |v_sigma (A dx + B dy)|, |v_sigma (B dx + C dy)|, v_sigma = -opacity * go
+                        const float vsg = r1.y * go * (2.0f / LOG2E);
+                        gax = fabsf(vsg * fmaf(r0.z, dx, 0.5f * r0.w * dy));
+                        gay = fabsf(vsg * fmaf(0.5f * r0.w, dx, r1.x * dy));
+                    }
                 }
-                *reinterpret_cast<float2*>(my_val + u * VAL_ROW) = make_float2(go, fac);
+                if (ABS) *reinterpret_cast<float4*>(my_val + u * VAL_ROW) = make_float4(go, fac, gax, gay);
+                else *reinterpret_cast<float2*>(my_val + u * VAL_ROW) = make_float2(go, fac);
             }
             const unsigned present = __reduce_or_sync(FULL, vm);
             __syncwarp();   // the tile stores of all lanes are visible to the row loads below
@@ -761,9 +784,18 @@ __global__ void __launch_bounds__(BLOCK_PIX, 4) blend_bwd_tr_kernel(int width, i
                 // ---- reduce: lane (re, rh) sums entry ii-re over pixels 16 rh .. 16 rh + 15 (local x = k & 7, local row = k >> 3)
                 float R0 = 0.f, R0x = 0.f, R0xx = 0.f, R1 = 0.f, R1x = 0.f, R1xx = 0.f;
                 float Cs[4] = {0.f, 0.f, 0.f, 0.f};
+                float Ax = 0.f, Ay = 0.f;
 #pragma unroll
                 for (int k2 = 0; k2 < 8; ++k2) {
-                    const float4 v = my_row[k2];          // {go, fac} of pixels 2 k2, 2 k2 + 1
+                    float4 v;                             // {go, fac} of pixels 2 k2, 2 k2 + 1
+                    if (ABS) {
+                        const float4 va = my_row[2 * k2], vb = my_row[2 * k2 + 1];
+                        v = make_float4(va.x, va.y, vb.x, vb.y);
+                        Ax += va.z + vb.z;
+                        Ay += va.w + vb.w;
+                    } else {
+                        v = my_row[k2];
+                    }
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int k = 2 * k2 + e;
@@ -789,6 +821,10 @@ __global__ void __launch_bounds__(BLOCK_PIX, 4) blend_bwd_tr_kernel(int width, i
                 Syy += __shfl_xor_sync(FULL, Syy, 16);
 #pragma unroll
                 for (int c = 0; c < CH; ++c) Cs[c] += __shfl_xor_sync(FULL, Cs[c], 16);
+                if (ABS) {
+                    Ax += __shfl_xor_sync(FULL, Ax, 16);
+                    Ay += __shfl_xor_sync(FULL, Ay, 16);
+                }
                 if ((present >> re) & 1u) {
                     const int j = my_list[ii - re];
                     const int g = __float_as_int(s_rec[j * 3 + 2].z);
@@ -813,6 +849,10 @@ __global__ void __launch_bounds__(BLOCK_PIX, 4) blend_bwd_tr_kernel(int width, i
                         atomicAdd(v_opacity + int64_t(g) * st.os, S0);
 #pragma unroll
                         for (int c = 0; c < CH; ++c) atomicAdd(v_colors + int64_t(g) * st.ks + c, Cs[c]);
+                        if (ABS) {
+                            atomicAdd(v_xy_abs + 2 * int64_t(g), Ax);
+                            atomicAdd(v_xy_abs + 2 * int64_t(g) + 1, Ay);
+                        }
                     }
                 }
             }
@@ -1060,7 +1100,7 @@ __global__ void __launch_bounds__(BLOCK_PIX, 3) blend_bwd_mma_kernel(int width, 
 template <int CH>
 int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy, const float* conic,
                  const float* opacity, const float* colors, const float* bg, float* image, int64_t ps, int64_t cs, float* final_T,
-                 int32_t* n_contrib, float* alpha, cudaStream_t s) {
+                 int32_t* n_contrib, float* alpha, uint8_t* hit_any, cudaStream_t s) {
     const int gx = div_up(width, TILE), gy = div_up(height, TILE);
     dim3 grid(gx, gy);
     const SplatStrides st = row_stride > 0 ? SplatStrides{row_stride, row_stride, row_stride, row_stride} : SplatStrides{2, 3, 1, CH};
@@ -1068,17 +1108,23 @@ int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
     static const bool use_sync = []() { const char* e = getenv("B200GS_FWD_SYNC"); return e && e[0] == '1'; }();
     // the row layout is [x, y, depth, A, B, C, comp, opacity, r, g, b, radius] (include/b200gs.h); 16-byte copies need 16-byte aligned rows
     const bool rows16 = row_stride == 12 && CH == 3 && conic == xy + 3 && opacity == xy + 7 && colors == xy + 8 && (reinterpret_cast<uintptr_t>(xy) & 15) == 0;
-    if (!use_sync) {
-#define B200GS_FWD_ARGS width, height, gx, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, image, ps, cs, final_T, n_contrib, alpha
+    if (!use_sync || hit_any != nullptr) {
+#define B200GS_FWD_ARGS width, height, gx, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, image, ps, cs, final_T, n_contrib, alpha, hit_any
+#define B200GS_FWD_LAUNCH(G, R)                                                                                                   \
+    do {                                                                                                                           \
+        if (hit_any) blend_fwd_async_kernel<CH, G, R, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_FWD_ARGS);                          \
+        else blend_fwd_async_kernel<CH, G, R, false><<<grid, BLOCK_PIX, 0, s>>>(B200GS_FWD_ARGS);                                 \
+    } while (0)
         if (rows16) {
             if constexpr (CH == 3) {
-                if (mode == B200GS_MODE_GSPLAT) blend_fwd_async_kernel<CH, true, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_FWD_ARGS);
-                else blend_fwd_async_kernel<CH, false, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_FWD_ARGS);
+                if (mode == B200GS_MODE_GSPLAT) B200GS_FWD_LAUNCH(true, true);
+                else B200GS_FWD_LAUNCH(false, true);
             }
         } else {
-            if (mode == B200GS_MODE_GSPLAT) blend_fwd_async_kernel<CH, true, false><<<grid, BLOCK_PIX, 0, s>>>(B200GS_FWD_ARGS);
-            else blend_fwd_async_kernel<CH, false, false><<<grid, BLOCK_PIX, 0, s>>>(B200GS_FWD_ARGS);
+            if (mode == B200GS_MODE_GSPLAT) B200GS_FWD_LAUNCH(true, false);
+            else B200GS_FWD_LAUNCH(false, false);
         }
+#undef B200GS_FWD_LAUNCH
 #undef B200GS_FWD_ARGS
         B200GS_LAUNCH_CHECK();
         return B200GS_OK;
@@ -1127,24 +1173,36 @@ int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
             return B200GS_OK;
         }
     }
-    // default: transpose-reduce kernel (no absgrad side channel); B200GS_BWD_BUTTERFLY=1 selects the shuffle butterfly for A/B runs
+    // default: transpose-reduce kernel; B200GS_BWD_BUTTERFLY=1 selects the shuffle butterfly for A/B runs
     static const bool use_butterfly = []() { const char* e = getenv("B200GS_BWD_BUTTERFLY"); return e && e[0] == '1'; }();
-    if (!v_xy_abs && !use_butterfly && !use_mma) {
+    if (!use_butterfly && !use_mma) {
         static const cudaError_t attr_rc = []() {
-            cudaError_t e = cudaFuncSetAttribute(blend_bwd_tr_kernel<CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrSmem));
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(blend_bwd_tr_kernel<CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrSmem));
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(blend_bwd_tr_kernel<CH, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(blend_bwd_tr_kernel<CH, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaError_t e = cudaSuccess;
+            auto set = [&e](const void* f, size_t bytes) {
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            };
+            set((const void*)blend_bwd_tr_kernel<CH, true, false>, sizeof(TrSmem<false>));
+            set((const void*)blend_bwd_tr_kernel<CH, false, false>, sizeof(TrSmem<false>));
+            set((const void*)blend_bwd_tr_kernel<CH, true, true>, sizeof(TrSmem<true>));
+            set((const void*)blend_bwd_tr_kernel<CH, false, true>, sizeof(TrSmem<true>));
             return e;
         }();
         if (attr_rc != cudaSuccess) {
             set_error("blend_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_rc));
             return B200GS_ECUDA;
         }
-        if (mode == B200GS_MODE_GSPLAT)
-            blend_bwd_tr_kernel<CH, true><<<grid, BLOCK_PIX, sizeof(TrSmem), s>>>(B200GS_BWD_MMA_ARGS);
-        else
-            blend_bwd_tr_kernel<CH, false><<<grid, BLOCK_PIX, sizeof(TrSmem), s>>>(B200GS_BWD_MMA_ARGS);
+        if (v_xy_abs) {
+            if (mode == B200GS_MODE_GSPLAT)
+                blend_bwd_tr_kernel<CH, true, true><<<grid, BLOCK_PIX, sizeof(TrSmem<true>), s>>>(B200GS_BWD_ARGS);
+            else
+                blend_bwd_tr_kernel<CH, false, true><<<grid, BLOCK_PIX, sizeof(TrSmem<true>), s>>>(B200GS_BWD_ARGS);
+        } else {
+            if (mode == B200GS_MODE_GSPLAT)
+                blend_bwd_tr_kernel<CH, true, false><<<grid, BLOCK_PIX, sizeof(TrSmem<false>), s>>>(B200GS_BWD_ARGS);
+            else
+                blend_bwd_tr_kernel<CH, false, false><<<grid, BLOCK_PIX, sizeof(TrSmem<false>), s>>>(B200GS_BWD_ARGS);
+        }
         B200GS_LAUNCH_CHECK();
         return B200GS_OK;
     }
@@ -1173,12 +1231,13 @@ int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
 
 int launch_blend_fwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy,
                      const float* conic, const float* opacity, const float* colors, const float* bg, float* image,
-                     int64_t pix_stride, int64_t ch_stride, float* final_T, int32_t* n_contrib, float* alpha, cudaStream_t s) {
+                     int64_t pix_stride, int64_t ch_stride, float* final_T, int32_t* n_contrib, float* alpha, cudaStream_t s,
+                     uint8_t* hit_any) {
     switch (channels) {
-        case 1: return fwd_dispatch<1>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
-        case 2: return fwd_dispatch<2>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
-        case 3: return fwd_dispatch<3>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
-        case 4: return fwd_dispatch<4>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, s);
+        case 1: return fwd_dispatch<1>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s);
+        case 2: return fwd_dispatch<2>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s);
+        case 3: return fwd_dispatch<3>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s);
+        case 4: return fwd_dispatch<4>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s);
     }
     set_error("blend_fwd: unsupported channel count %d (1..4)", channels);
     return B200GS_EINVAL;

@@ -335,8 +335,9 @@ def project_backward(view: B200gsView, means, scales, quats, shs, radii, clamped
     return v_means, v_scales, v_quats, v_shs
 
 
-def blend_forward(mode, width, height, binning: Binning, xy, conic, opacity, colors, bg, planar: bool, want_alpha: bool):
-    """planar=True -> image [C,H,W] (vanilla); else [H,W,C] (gsplat)."""
+def blend_forward(mode, width, height, binning: Binning, xy, conic, opacity, colors, bg, planar: bool, want_alpha: bool, hit_any=None):
+    """planar=True -> image [C,H,W] (vanilla); else [H,W,C] (gsplat).  hit_any: zero-filled uint8 [N] that receives 1 for every splat
+    that contributed to a pixel (b200gs_blend_fwd_hits)."""
     L = lib()
     ch = colors.shape[1]
     dev = xy.device
@@ -350,9 +351,14 @@ def blend_forward(mode, width, height, binning: Binning, xy, conic, opacity, col
     n_contrib = torch.empty(height, width, dtype=torch.int32, device=dev)
     alpha = torch.empty(height, width, dtype=torch.float32, device=dev) if want_alpha else None
     with _stage("blend_fwd"):
-        check(L.b200gs_blend_fwd(mode, width, height, ch, ptr(binning.tile_ranges), ptr(binning.sorted_ids), ptr(xy), ptr(conic),
-                                 ptr(opacity), ptr(colors), ptr(bg), ptr(image), ps, cs, ptr(final_T), ptr(n_contrib), ptr(alpha),
-                                 _stream()), "b200gs_blend_fwd")
+        if hit_any is None:
+            check(L.b200gs_blend_fwd(mode, width, height, ch, ptr(binning.tile_ranges), ptr(binning.sorted_ids), ptr(xy), ptr(conic),
+                                     ptr(opacity), ptr(colors), ptr(bg), ptr(image), ps, cs, ptr(final_T), ptr(n_contrib), ptr(alpha),
+                                     _stream()), "b200gs_blend_fwd")
+        else:
+            check(L.b200gs_blend_fwd_hits(mode, width, height, ch, ptr(binning.tile_ranges), ptr(binning.sorted_ids), ptr(xy), ptr(conic),
+                                          ptr(opacity), ptr(colors), ptr(bg), ptr(image), ps, cs, ptr(final_T), ptr(n_contrib), ptr(alpha),
+                                          ptr(hit_any), _stream()), "b200gs_blend_fwd_hits")
     return image, final_T, n_contrib, alpha
 
 
@@ -637,8 +643,9 @@ class _SphericalHarmonics(torch.autograd.Function):
         return None, v_dirs, v_coeffs
 
 
-def spherical_harmonics(degrees_to_use: int, dirs: torch.Tensor, coeffs: torch.Tensor) -> torch.Tensor:
-    """gsplat ``spherical_harmonics(deg, dirs[N,3], coeffs[N,K,3]) -> [N,3]`` (directions normalised inside)."""
+def spherical_harmonics(degrees_to_use: int, dirs: torch.Tensor, coeffs: torch.Tensor, masks: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gsplat ``spherical_harmonics(deg, dirs[N,3], coeffs[N,K,3], masks=None) -> [N,3]`` (directions normalised inside).  `masks`
+    (gsplat skips the masked-out rows) is accepted for call compatibility; every row is evaluated, the caller only reads the visible ones."""
     if coeffs.shape[-1] != 3 or coeffs.dim() != 3:
         raise ValueError("coeffs must be [N, K, 3]")
     return _SphericalHarmonics.apply(degrees_to_use, dirs, coeffs)
@@ -690,6 +697,61 @@ def rasterize_gaussians(xys, depths, radii, conics, num_tiles_hit, colors, opaci
     image, alpha = _RasterizeGaussians.apply(xys, depths, radii, conics, colors, opacity, img_height, img_width, background,
                                              return_alpha, absgrad)
     return (image, alpha) if return_alpha else image
+
+
+class _RasterizeBinned(torch.autograd.Function):
+    """K6 / K7 on a binning computed beforehand (gsplat v1: isect_tiles + isect_offset_encode once, rasterize_to_pixels several
+    times with different colour sets — gsplat_v1_renderer.py:176-196,326-352).  <= 4 channels per call."""
+
+    @staticmethod
+    def forward(ctx, xys, conics, colors, opacity, background, binning, hw, absgrad, want_hits):
+        xys = _f32c(xys, "means2d")
+        conics = _f32c(conics, "conics")
+        colors = _f32c(colors, "colors")
+        opac = _f32c(opacity, "opacities").reshape(-1)
+        bg = _f32c(background, "background") if background is not None else None
+        H, W = hw
+        hits = torch.zeros(xys.shape[0], dtype=torch.uint8, device=xys.device) if want_hits else None
+        image, final_T, n_contrib, alpha = blend_forward(MODE_GSPLAT, W, H, binning, xys, conics, opac, colors, bg, False, True, hits)
+        ctx.binning, ctx.hw, ctx.absgrad, ctx.opac_shape = binning, hw, bool(absgrad), tuple(opacity.shape)
+        ctx.save_for_backward(xys, conics, colors, opac, bg, final_T, n_contrib)
+        ctx.xys_ref = xys
+        ctx.mark_non_differentiable(*([hits] if hits is not None else []))
+        return (image, alpha, hits) if hits is not None else (image, alpha)
+
+    @staticmethod
+    def backward(ctx, v_image, v_alpha, *_):
+        xys, conics, colors, opac, bg, final_T, n_contrib = ctx.saved_tensors
+        H, W = ctx.hw
+        v_image = _f32c(v_image, "grad_image")
+        v_alpha = _f32c(v_alpha, "grad_alpha") if v_alpha is not None else None
+        v_xy, v_conic, v_opacity, v_colors, v_abs = blend_backward(MODE_GSPLAT, W, H, ctx.binning, xys, conics, opac, colors, bg, final_T,
+                                                                   n_contrib, v_image, v_alpha, False, (1.0, 1.0), ctx.absgrad)
+        if ctx.absgrad:   # channel groups of one render accumulate (|.| per group: an upper bound of gsplat's all-channel value when D > 4)
+            prev = getattr(ctx.xys_ref, "absgrad", None)
+            ctx.xys_ref.absgrad = v_abs if prev is None else prev + v_abs
+        return v_xy, v_conic, v_colors, v_opacity.reshape(ctx.opac_shape), None, None, None, None, None
+
+
+def rasterize_binned(means2d, conics, colors, opacities, binning: Binning, img_height: int, img_width: int, background=None,
+                     absgrad: bool = False, want_hits: bool = False):
+    """-> (image [H,W,D], alpha [H,W], hits uint8 [N] or None) for any D >= 1: the channels are composited in groups of <= 4 over the
+    same per-tile lists (alpha / hits come from the first group; `means2d.absgrad`, when requested, accumulates every group's)."""
+    if colors.dim() != 2 or colors.shape[1] < 1:
+        raise ValueError("colors must be [N, D] with D >= 1")
+    if background is not None and background.shape[0] != colors.shape[1]:
+        raise ValueError("background must have one entry per colour channel")
+    D = colors.shape[1]
+    images, alpha, hits, abs_total = [], None, None, None
+    for c0 in range(0, D, 4):
+        c1 = min(D, c0 + 4)
+        out = _RasterizeBinned.apply(means2d, conics, colors[:, c0:c1], opacities, None if background is None else background[c0:c1], binning,
+                                     (int(img_height), int(img_width)), absgrad, want_hits and c0 == 0)
+        images.append(out[0])
+        if c0 == 0:
+            alpha = out[1]
+            hits = out[2] if want_hits else None
+    return (images[0] if len(images) == 1 else torch.cat(images, dim=-1)), alpha, hits
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -92,3 +92,25 @@ class SyntheticGaussians(torch.nn.Module):
 
     def get_shs(self):
         return self.get_features
+
+    # the method-style getters of the reference's current GaussianModel API (internal/models/gaussian.py:122-254), read by
+    # the gsplat-v1 renderers
+    is_pre_activated = False
+
+    def get_means(self):
+        return self.gaussians["means"]
+
+    def get_scales(self):
+        return self.get_scaling
+
+    def get_rotations(self):
+        return self.get_rotation
+
+    def get_opacities(self):
+        return self.get_opacity
+
+    def get_shs_dc(self):
+        return self.gaussians["shs_dc"]
+
+    def get_shs_rest(self):
+        return self.gaussians["shs_rest"]

@@ -185,6 +185,12 @@ B200GS_API int b200gs_blend_fwd(int32_t mode, int32_t width, int32_t height, int
                      const int32_t* sorted_ids, const float* xy, const float* conic, const float* opacity,
                      const float* colors, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride,
                      float* final_T, int32_t* n_contrib, float* alpha, void* stream);
+/* b200gs_blend_fwd_hits: the same, and hit_any[g] = 1 for every splat g that contributed to at least one pixel (caller zero-fills
+ *     hit_any[n]): gsplat's `means2d.has_hit_any_pixels` (optimizers.py:39 SelectiveAdam; gsplat_v1_renderer.py:287 acc_vis). */
+B200GS_API int b200gs_blend_fwd_hits(int32_t mode, int32_t width, int32_t height, int32_t channels, const int32_t* tile_ranges,
+                     const int32_t* sorted_ids, const float* xy, const float* conic, const float* opacity,
+                     const float* colors, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride,
+                     float* final_T, int32_t* n_contrib, float* alpha, uint8_t* hit_any, void* stream);
 
 /* ---- K7: blend backward --------------------------------------------------------------------------------------------
  * replaces dgr renderCUDA bwd / gsplat rasterize_to_pixels bwd.
