@@ -25,7 +25,7 @@ static int check_view(const B200gsView* v, bool needs_sh) {
     if (v->width <= 0 || v->height <= 0) { set_error("bad image size %dx%d", v->width, v->height); return B200GS_EINVAL; }
     if (v->mode != B200GS_MODE_VANILLA && v->mode != B200GS_MODE_GSPLAT) { set_error("bad mode %d", v->mode); return B200GS_EINVAL; }
     if (needs_sh) {
-        if (v->sh_degree < 0 || v->sh_degree > 3) { set_error("sh_degree %d unsupported (0..3)", v->sh_degree); return B200GS_EINVAL; }
+        if (v->sh_degree < 0 || v->sh_degree > 4) { set_error("sh_degree %d unsupported (0..4)", v->sh_degree); return B200GS_EINVAL; }
         if (v->sh_stride < (v->sh_degree + 1) * (v->sh_degree + 1)) {
             set_error("sh_stride %d < (sh_degree+1)^2", v->sh_stride);
             return B200GS_EINVAL;
@@ -231,7 +231,7 @@ int b200gs_ipc_free(void* dev_ptr) {
 }
 
 int b200gs_sh_fwd(int32_t degree, int32_t sh_stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, void* stream) {
-    B200GS_CHECK_ARG(degree >= 0 && degree <= 3, "degree must be 0..3");
+    B200GS_CHECK_ARG(degree >= 0 && degree <= 4, "degree must be 0..4");
     B200GS_CHECK_ARG(sh_stride >= (degree + 1) * (degree + 1), "sh_stride < (degree+1)^2");
     B200GS_CHECK_ARG(n >= 0, "n < 0");
     B200GS_CHECK_ARG(n == 0 || (dirs && coeffs && rgb), "NULL pointer");
@@ -240,7 +240,7 @@ int b200gs_sh_fwd(int32_t degree, int32_t sh_stride, int64_t n, const float* dir
 
 int b200gs_sh_bwd(int32_t degree, int32_t sh_stride, int64_t n, const float* dirs, const float* coeffs, const float* v_rgb,
                   float* v_coeffs, float* v_dirs, void* stream) {
-    B200GS_CHECK_ARG(degree >= 0 && degree <= 3, "degree must be 0..3");
+    B200GS_CHECK_ARG(degree >= 0 && degree <= 4, "degree must be 0..4");
     B200GS_CHECK_ARG(sh_stride >= (degree + 1) * (degree + 1), "sh_stride < (degree+1)^2");
     B200GS_CHECK_ARG(n >= 0, "n < 0");
     B200GS_CHECK_ARG(n == 0 || (dirs && coeffs && v_rgb && v_coeffs), "NULL pointer");

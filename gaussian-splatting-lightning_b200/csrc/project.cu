@@ -20,16 +20,21 @@ __device__ constexpr float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f
                                        -1.0925484305920792f, 0.5462742152960396f};
 __device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
                                        -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+__device__ constexpr float SH_C4[9] = {2.5033429417967046f, -1.7701307697799304f, 0.9461746957575601f, -0.6690465435572892f,
+                                       0.10578554691520431f, -0.6690465435572892f, 0.47308734787878004f, -1.7701307697799304f,
+                                       0.6258357354491761f};
 
-constexpr int MAX_COEFFS = 16;
+// Every kernel that touches SH coefficients is instantiated for MC = 16 (degrees 0..3, the common case: 48 coefficient
+// registers) and MC = 25 (degree 4, sh_utils.py:102-111: 75 registers); the launchers pick by the view's sh_degree.
 
 // Loads the first ncoef*3 floats of one Gaussian's SH block into registers. 128-bit path when the block is 16B aligned.
+template <int MC>
 __device__ __forceinline__ void load_sh(const float* __restrict__ base, int ncoef, bool vec4, float* sh) {
     const int nf = ncoef * 3;
     if (vec4) {
         const float4* b4 = reinterpret_cast<const float4*>(base);
 #pragma unroll
-        for (int q = 0; q < MAX_COEFFS * 3 / 4; ++q) {
+        for (int q = 0; q < MC * 3 / 4; ++q) {
             if (q * 4 < nf) {
                 float4 t = __ldg(b4 + q);
                 sh[q * 4 + 0] = t.x; sh[q * 4 + 1] = t.y; sh[q * 4 + 2] = t.z; sh[q * 4 + 3] = t.w;
@@ -37,12 +42,13 @@ __device__ __forceinline__ void load_sh(const float* __restrict__ base, int ncoe
         }
     } else {
 #pragma unroll
-        for (int q = 0; q < MAX_COEFFS * 3; ++q)
+        for (int q = 0; q < MC * 3; ++q)
             if (q < nf) sh[q] = __ldg(base + q);
     }
 }
 
 // basis values for unit direction (x,y,z); writes (deg+1)^2 entries
+template <int MC>
 __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float* b) {
     b[0] = SH_C0;
     if (deg > 0) {
@@ -56,12 +62,20 @@ __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, flo
                 b[11] = SH_C3[2] * y * (4.0f * zz - xx - yy); b[12] = SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
                 b[13] = SH_C3[4] * x * (4.0f * zz - xx - yy); b[14] = SH_C3[5] * z * (xx - yy);
                 b[15] = SH_C3[6] * x * (xx - 3.0f * yy);
+                if (MC > 16 && deg > 3) {
+                    b[16] = SH_C4[0] * xy * (xx - yy); b[17] = SH_C4[1] * yz * (3.0f * xx - yy);
+                    b[18] = SH_C4[2] * xy * (7.0f * zz - 1.0f); b[19] = SH_C4[3] * yz * (7.0f * zz - 3.0f);
+                    b[20] = SH_C4[4] * (zz * (35.0f * zz - 30.0f) + 3.0f); b[21] = SH_C4[5] * xz * (7.0f * zz - 3.0f);
+                    b[22] = SH_C4[6] * (xx - yy) * (7.0f * zz - 1.0f); b[23] = SH_C4[7] * xz * (xx - 3.0f * yy);
+                    b[24] = SH_C4[8] * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy));
+                }
             }
         }
     }
 }
 
 // d(basis)/d(x,y,z)
+template <int MC>
 __device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z, float* bx, float* by, float* bz) {
     bx[0] = by[0] = bz[0] = 0.f;
     if (deg > 0) {
@@ -83,6 +97,18 @@ __device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z
                 bx[13] = SH_C3[4] * (4.f * zz - 3.f * xx - yy); by[13] = SH_C3[4] * -2.f * x * y; bz[13] = SH_C3[4] * 8.f * x * z;
                 bx[14] = SH_C3[5] * 2.f * x * z; by[14] = SH_C3[5] * -2.f * y * z; bz[14] = SH_C3[5] * (xx - yy);
                 bx[15] = SH_C3[6] * (3.f * xx - 3.f * yy); by[15] = SH_C3[6] * -6.f * x * y; bz[15] = 0.f;
+                if (MC > 16 && deg > 3) {
+                    const float xyz = x * y * z, s7 = 7.f * zz - 1.f, t7 = 7.f * zz - 3.f, u21 = 21.f * zz - 3.f;
+                    bx[16] = SH_C4[0] * y * (3.f * xx - yy); by[16] = SH_C4[0] * x * (xx - 3.f * yy); bz[16] = 0.f;
+                    bx[17] = SH_C4[1] * 6.f * xyz; by[17] = SH_C4[1] * 3.f * z * (xx - yy); bz[17] = SH_C4[1] * y * (3.f * xx - yy);
+                    bx[18] = SH_C4[2] * y * s7; by[18] = SH_C4[2] * x * s7; bz[18] = SH_C4[2] * 14.f * xyz;
+                    bx[19] = 0.f; by[19] = SH_C4[3] * z * t7; bz[19] = SH_C4[3] * y * u21;
+                    bx[20] = 0.f; by[20] = 0.f; bz[20] = SH_C4[4] * z * (140.f * zz - 60.f);
+                    bx[21] = SH_C4[5] * z * t7; by[21] = 0.f; bz[21] = SH_C4[5] * x * u21;
+                    bx[22] = SH_C4[6] * 2.f * x * s7; by[22] = SH_C4[6] * -2.f * y * s7; bz[22] = SH_C4[6] * 14.f * z * (xx - yy);
+                    bx[23] = SH_C4[7] * 3.f * z * (xx - yy); by[23] = SH_C4[7] * -6.f * xyz; bz[23] = SH_C4[7] * x * (xx - 3.f * yy);
+                    bx[24] = SH_C4[8] * 4.f * x * (xx - 3.f * yy); by[24] = SH_C4[8] * 4.f * y * (yy - 3.f * xx); bz[24] = 0.f;
+                }
             }
         }
     }
@@ -215,17 +241,17 @@ __device__ __forceinline__ void load_scale_quat(const float* __restrict__ scales
 }
 
 // SH block of Gaussian i into registers: [K,3] contiguous, or dc [1,3] + rest [K-1,3] when RAW
-template <bool RAW>
+template <bool RAW, int MC>
 __device__ __forceinline__ void load_sh_any(const float* __restrict__ shs, const float* __restrict__ shs_rest, int64_t i, int stride,
                                             int ncoef, float* sh) {
     if (RAW) {
         sh[0] = __ldg(shs + 3 * i); sh[1] = __ldg(shs + 3 * i + 1); sh[2] = __ldg(shs + 3 * i + 2);
         const float* r = shs_rest + i * int64_t(stride - 1) * 3;
 #pragma unroll
-        for (int q = 3; q < MAX_COEFFS * 3; ++q)
+        for (int q = 3; q < MC * 3; ++q)
             if (q < ncoef * 3) sh[q] = __ldg(r + q - 3);
     } else {
-        load_sh(shs + i * int64_t(stride) * 3, ncoef, ((stride * 3) & 3) == 0, sh);
+        load_sh<MC>(shs + i * int64_t(stride) * 3, ncoef, ((stride * 3) & 3) == 0, sh);
     }
 }
 
@@ -310,17 +336,18 @@ __device__ __forceinline__ bool project_one(const B200gsView& v, const RawIO& ra
 }
 
 // max(SH colour + 0.5, 0) of a visible Gaussian seen from v.campos; bit c of *cl set where channel c was clamped
+template <int MC>
 __device__ __forceinline__ void sh_color_one(const B200gsView& v, const float* p, const float* sh, float& r, float& gc, float& bc, uint8_t& cl) {
     const int deg = v.sh_degree;
     const int ncoef = (deg + 1) * (deg + 1);
     float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
     const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
     dx *= inv_len; dy *= inv_len; dz *= inv_len;
-    float bs[MAX_COEFFS];
-    sh_basis(deg, dx, dy, dz, bs);
+    float bs[MC];
+    sh_basis<MC>(deg, dx, dy, dz, bs);
     r = gc = bc = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAX_COEFFS; ++k) {
+    for (int k = 0; k < MC; ++k) {
         if (k < ncoef) {
             r += bs[k] * sh[3 * k + 0];
             gc += bs[k] * sh[3 * k + 1];
@@ -334,7 +361,7 @@ __device__ __forceinline__ void sh_color_one(const B200gsView& v, const float* p
     if (bc < 0.f) { bc = 0.f; cl |= 4; }
 }
 
-template <bool GSPLAT, bool RAW>
+template <bool GSPLAT, bool RAW, int MC>
 __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
                                                           const float* __restrict__ means, const float* __restrict__ scales,
                                                           const float* __restrict__ quats, const float* __restrict__ shs,
@@ -355,9 +382,9 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant_
         uint8_t cl = 0;
         if (vis) {
             const int deg = v.sh_degree;
-            float sh[MAX_COEFFS * 3];
-            load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, (deg + 1) * (deg + 1), sh);
-            sh_color_one(v, p, sh, r, gc, bc, cl);
+            float sh[MC * 3];
+            load_sh_any<RAW, MC>(shs, raw.shs_rest, i, v.sh_stride, (deg + 1) * (deg + 1), sh);
+            sh_color_one<MC>(v, p, sh, r, gc, bc, cl);
         }
         rgb_out[3 * i + 0] = r; rgb_out[3 * i + 1] = gc; rgb_out[3 * i + 2] = bc;
         clamped_out[i] = cl;
@@ -371,6 +398,7 @@ struct ViewPack {
     B200gsView v[B200GS_MAX_VIEWS];
 };
 
+template <int MC>
 __global__ void __launch_bounds__(256) project_fwd_multi_kernel(const __grid_constant__ ViewPack vp, int nviews, const RawIO raw, int64_t n,
                                                                 const float* __restrict__ means, const float* __restrict__ scales,
                                                                 const float* __restrict__ quats, const float* __restrict__ shs_dc,
@@ -387,16 +415,16 @@ __global__ void __launch_bounds__(256) project_fwd_multi_kernel(const __grid_con
 #pragma unroll 1
     for (int j = 0; j < nviews; ++j)
         if (project_one<true, true>(vp.v[j], raw, i, int64_t(j) * n + i, p, sc, q, out, raw.opac_out)) vismask |= 1u << j;
-    float sh[MAX_COEFFS * 3];
+    float sh[MC * 3];
     if (vismask) {
         const int deg = vp.v[0].sh_degree;
-        load_sh_any<true>(shs_dc, raw.shs_rest, i, vp.v[0].sh_stride, (deg + 1) * (deg + 1), sh);
+        load_sh_any<true, MC>(shs_dc, raw.shs_rest, i, vp.v[0].sh_stride, (deg + 1) * (deg + 1), sh);
     }
 #pragma unroll 1
     for (int j = 0; j < nviews; ++j) {
         float r = 0.f, gc = 0.f, bc = 0.f;
         uint8_t cl = 0;
-        if ((vismask >> j) & 1u) sh_color_one(vp.v[j], p, sh, r, gc, bc, cl);
+        if ((vismask >> j) & 1u) sh_color_one<MC>(vp.v[j], p, sh, r, gc, bc, cl);
         const int64_t o = int64_t(j) * n + i;
         rgb_out[3 * o + 0] = r; rgb_out[3 * o + 1] = gc; rgb_out[3 * o + 2] = bc;
         clamped_out[o] = cl;
@@ -533,7 +561,7 @@ __device__ __forceinline__ void geometry_backward(const B200gsView& v, const flo
 // SH-gradient rows of a warp's 32 Gaussians: staged in shared memory (odd row stride: conflict-free) and written back with
 // fully coalesced 128-bit stores: every row must be written (zeros for culled Gaussians), so the warp's 32 rows are one
 // contiguous 5.6-6 KB span of the output.  out[] holds this lane's 48 values (dc first); RAW: dc goes to v_shs, rest to dst_base.
-template <bool RAW>
+template <bool RAW, int MC>
 __device__ __forceinline__ void store_sh_rows(float* s_rows_warp, const float* out, int64_t i, int64_t n, bool in_range, int stride3, unsigned lane,
                                               float* __restrict__ v_shs, float* __restrict__ v_shs_rest, bool ACC) {
     const int rw = RAW ? stride3 - 3 : stride3;          // floats per output row
@@ -543,11 +571,11 @@ __device__ __forceinline__ void store_sh_rows(float* s_rows_warp, const float* o
         if (ACC) { o0 += v_shs[3 * i]; o1 += v_shs[3 * i + 1]; o2 += v_shs[3 * i + 2]; }
         v_shs[3 * i] = o0; v_shs[3 * i + 1] = o1; v_shs[3 * i + 2] = o2;
     }
-    if (rw <= 48) {
+    if (rw <= MC * 3) {
         const int rwp = rw | 1;
         float* row = s_rows_warp + lane * rwp;
 #pragma unroll
-        for (int k = 0; k < MAX_COEFFS * 3; ++k) {
+        for (int k = 0; k < MC * 3; ++k) {
             const int c = RAW ? k - 3 : k;
             if (c >= 0 && c < rw) row[c] = out[k];
         }
@@ -579,12 +607,12 @@ __device__ __forceinline__ void store_sh_rows(float* s_rows_warp, const float* o
     } else if (in_range) {  // wider coefficient storage than the kernel evaluates: plain per-thread rows
         float* o = dst_base + i * int64_t(rw);
 #pragma unroll
-        for (int k = RAW ? 3 : 0; k < MAX_COEFFS * 3; ++k) o[RAW ? k - 3 : k] = out[k];
-        for (int c = MAX_COEFFS * 3 - (RAW ? 3 : 0); c < rw; ++c) o[c] = 0.f;
+        for (int k = RAW ? 3 : 0; k < MC * 3; ++k) o[RAW ? k - 3 : k] = out[k];
+        for (int c = MC * 3 - (RAW ? 3 : 0); c < rw; ++c) o[c] = 0.f;
     }
 }
 
-template <bool GSPLAT, bool RAW>
+template <bool GSPLAT, bool RAW, int MC>
 __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
                                                           const float* __restrict__ means, const float* __restrict__ scales,
                                                           const float* __restrict__ quats, const float* __restrict__ shs,
@@ -594,7 +622,7 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
                                                           const float* __restrict__ v_rgb, float* __restrict__ v_means,
                                                           float* __restrict__ v_scales, float4* __restrict__ v_quats,
                                                           float* __restrict__ v_shs) {
-    __shared__ float s_rows[BWD_THREADS / 32][32 * 49];
+    __shared__ float s_rows[BWD_THREADS / 32][32 * (MC * 3 + 1)];
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const int warp = threadIdx.x >> 5;
@@ -615,9 +643,9 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
         const int deg = v.sh_degree;
         const int ncoef = (deg + 1) * (deg + 1);
         float gr = 0.f, gg = 0.f, gb = 0.f, dx = 0.f, dy = 0.f, dz = 1.f, inv_len = 0.f;
-        float out[MAX_COEFFS * 3];
+        float out[MC * 3];
 #pragma unroll
-        for (int k = 0; k < MAX_COEFFS * 3; ++k) out[k] = 0.f;
+        for (int k = 0; k < MC * 3; ++k) out[k] = 0.f;
         if (vis) {
             const uint8_t cl = clamped[i];
             const float* crgb = ROWS ? vrow + B200GS_ROW_RGB : v_rgb + 3 * i;
@@ -627,24 +655,24 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
             dx = p[0] - v.campos[0]; dy = p[1] - v.campos[1]; dz = p[2] - v.campos[2];
             inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
             dx *= inv_len; dy *= inv_len; dz *= inv_len;
-            float bs[MAX_COEFFS];
-            sh_basis(deg, dx, dy, dz, bs);
+            float bs[MC];
+            sh_basis<MC>(deg, dx, dy, dz, bs);
 #pragma unroll
-            for (int k = 0; k < MAX_COEFFS; ++k) {
+            for (int k = 0; k < MC; ++k) {
                 const float bk = (k < ncoef) ? bs[k] : 0.f;
                 out[3 * k + 0] = bk * gr; out[3 * k + 1] = bk * gg; out[3 * k + 2] = bk * gb;
             }
         }
-        store_sh_rows<RAW>(s_rows[warp], out, i, n, in_range, stride3, lane, v_shs, raw.v_shs_rest, ACC);
+        store_sh_rows<RAW, MC>(s_rows[warp], out, i, n, in_range, stride3, lane, v_shs, raw.v_shs_rest, ACC);
         if (vis && !GSPLAT && deg > 0) {
             // view direction -> mean (dgr back-propagates it; gsplat renderers detach the direction)
-            float sh[MAX_COEFFS * 3];
-            load_sh_any<RAW>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
-            float bx[MAX_COEFFS], by[MAX_COEFFS], bz[MAX_COEFFS];
-            sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
+            float sh[MC * 3];
+            load_sh_any<RAW, MC>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
+            float bx[MC], by[MC], bz[MC];
+            sh_basis_grad<MC>(deg, dx, dy, dz, bx, by, bz);
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
 #pragma unroll
-            for (int k = 1; k < MAX_COEFFS; ++k) {
+            for (int k = 1; k < MC; ++k) {
                 if (k < ncoef) {
                     const float w = sh[3 * k] * gr + sh[3 * k + 1] * gg + sh[3 * k + 2] * gb;
                     ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
@@ -719,6 +747,7 @@ struct RowSources {
     const float* rows[B200GS_MAX_VIEWS];
 };
 
+template <int MC>
 __global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __grid_constant__ ViewPack vp, int nviews, const RawIO raw,
                                                                        const __grid_constant__ RowSources src, int64_t n,
                                                                        const float* __restrict__ means, const float* __restrict__ scales,
@@ -726,7 +755,7 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __
                                                                        const uint8_t* __restrict__ clamped, const int32_t* __restrict__ row_index,
                                                                        float* __restrict__ v_means, float* __restrict__ v_scales,
                                                                        float4* __restrict__ v_quats, float* __restrict__ v_shs_dc) {
-    __shared__ float s_rows[BWD_THREADS / 32][32 * 49];
+    __shared__ float s_rows[BWD_THREADS / 32][32 * (MC * 3 + 1)];
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const int warp = threadIdx.x >> 5;
@@ -734,9 +763,9 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __
     const int stride3 = vp.v[0].sh_stride * 3;
     const int deg = vp.v[0].sh_degree;
     const int ncoef = (deg + 1) * (deg + 1);
-    float out[MAX_COEFFS * 3];
+    float out[MC * 3];
 #pragma unroll
-    for (int k = 0; k < MAX_COEFFS * 3; ++k) out[k] = 0.f;
+    for (int k = 0; k < MC * 3; ++k) out[k] = 0.f;
     float dm[3] = {0.f, 0.f, 0.f}, dscale[3] = {0.f, 0.f, 0.f}, dlogit = 0.f;
     float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
     float p[3] = {0.f, 0.f, 0.f}, sc[3] = {1.f, 1.f, 1.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, inv_qn = 1.f, o = 0.f;
@@ -764,10 +793,10 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __
             float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
             const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
             dx *= inv_len; dy *= inv_len; dz *= inv_len;
-            float bs[MAX_COEFFS];
-            sh_basis(deg, dx, dy, dz, bs);
+            float bs[MC];
+            sh_basis<MC>(deg, dx, dy, dz, bs);
 #pragma unroll
-            for (int k = 0; k < MAX_COEFFS; ++k) {
+            for (int k = 0; k < MC; ++k) {
                 const float bk = (k < ncoef) ? bs[k] : 0.f;
                 out[3 * k + 0] = fmaf(bk, gr, out[3 * k + 0]);
                 out[3 * k + 1] = fmaf(bk, gg, out[3 * k + 1]);
@@ -792,7 +821,7 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __
         dlogit += v_sig * o * (1.0f - o);
         geometry_backward<true>(v, p, g, c, dm, dscale, dq);
     }
-    store_sh_rows<true>(s_rows[warp], out, i, n, in_range, stride3, lane, v_shs_dc, raw.v_shs_rest, false);
+    store_sh_rows<true, MC>(s_rows[warp], out, i, n, in_range, stride3, lane, v_shs_dc, raw.v_shs_rest, false);
     if (!in_range) return;
     v_means[3 * i] = dm[0]; v_means[3 * i + 1] = dm[1]; v_means[3 * i + 2] = dm[2];
 #pragma unroll
@@ -805,6 +834,7 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __
 // ------------------------------------------------------------------------------------------------------------------
 // standalone SH (gsplat.sh.spherical_harmonics)
 // ------------------------------------------------------------------------------------------------------------------
+template <int MC>
 __global__ void __launch_bounds__(256) sh_fwd_kernel(int deg, int stride, int64_t n, const float* __restrict__ dirs,
                                                      const float* __restrict__ coeffs, float* __restrict__ rgb) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -813,17 +843,18 @@ __global__ void __launch_bounds__(256) sh_fwd_kernel(int deg, int stride, int64_
     float dx = __ldg(dirs + 3 * i), dy = __ldg(dirs + 3 * i + 1), dz = __ldg(dirs + 3 * i + 2);
     const float inv_len = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
     dx *= inv_len; dy *= inv_len; dz *= inv_len;
-    float sh[MAX_COEFFS * 3];
-    load_sh(coeffs + i * int64_t(stride) * 3, ncoef, ((stride * 3) & 3) == 0, sh);
-    float bs[MAX_COEFFS];
-    sh_basis(deg, dx, dy, dz, bs);
+    float sh[MC * 3];
+    load_sh<MC>(coeffs + i * int64_t(stride) * 3, ncoef, ((stride * 3) & 3) == 0, sh);
+    float bs[MC];
+    sh_basis<MC>(deg, dx, dy, dz, bs);
     float r = 0.f, g = 0.f, b = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAX_COEFFS; ++k)
+    for (int k = 0; k < MC; ++k)
         if (k < ncoef) { r += bs[k] * sh[3 * k]; g += bs[k] * sh[3 * k + 1]; b += bs[k] * sh[3 * k + 2]; }
     rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
 }
 
+template <int MC>
 __global__ void __launch_bounds__(256) sh_bwd_kernel(int deg, int stride, int64_t n, const float* __restrict__ dirs,
                                                      const float* __restrict__ coeffs, const float* __restrict__ v_rgb,
                                                      float* __restrict__ v_coeffs, float* __restrict__ v_dirs) {
@@ -836,8 +867,8 @@ __global__ void __launch_bounds__(256) sh_bwd_kernel(int deg, int stride, int64_
     const float inv_len = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
     dx *= inv_len; dy *= inv_len; dz *= inv_len;
     const float gr = __ldg(v_rgb + 3 * i), gg = __ldg(v_rgb + 3 * i + 1), gb = __ldg(v_rgb + 3 * i + 2);
-    float bs[MAX_COEFFS];
-    sh_basis(deg, dx, dy, dz, bs);
+    float bs[MC];
+    sh_basis<MC>(deg, dx, dy, dz, bs);
     float* o = v_coeffs + i * int64_t(stride3);
     for (int k = 0; k < stride; ++k) {
         const float bk = (k < ncoef) ? bs[k] : 0.f;
@@ -846,12 +877,12 @@ __global__ void __launch_bounds__(256) sh_bwd_kernel(int deg, int stride, int64_
     if (v_dirs != nullptr) {
         float ddx = 0.f, ddy = 0.f, ddz = 0.f;
         if (deg > 0) {
-            float sh[MAX_COEFFS * 3];
-            load_sh(coeffs + i * int64_t(stride3), ncoef, vec4, sh);
-            float bx[MAX_COEFFS], by[MAX_COEFFS], bz[MAX_COEFFS];
-            sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
+            float sh[MC * 3];
+            load_sh<MC>(coeffs + i * int64_t(stride3), ncoef, vec4, sh);
+            float bx[MC], by[MC], bz[MC];
+            sh_basis_grad<MC>(deg, dx, dy, dz, bx, by, bz);
 #pragma unroll
-            for (int k = 1; k < MAX_COEFFS; ++k)
+            for (int k = 1; k < MC; ++k)
                 if (k < ncoef) {
                     const float w = sh[3 * k] * gr + sh[3 * k + 1] * gg + sh[3 * k + 2] * gb;
                     ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
@@ -882,13 +913,19 @@ int launch_project_fwd_raw(const B200gsView& v, int64_t n, const float* means, c
     const bool raw_mode = opac_out != nullptr;
     RawIO raw{opac_logits, shs_rest, opac_out, nullptr, nullptr, nullptr, anti_aliased, nullptr, nullptr, 0};
 #define B200GS_PF_ARGS v, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth, radii, conic, comp, tiles, cov3d, rgb, clamped
-    if (v.mode == B200GS_MODE_GSPLAT) {
-        if (raw_mode) project_fwd_kernel<true, true><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);
-        else project_fwd_kernel<true, false><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);
-    } else {
-        if (raw_mode) project_fwd_kernel<false, true><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);
-        else project_fwd_kernel<false, false><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);
-    }
+#define B200GS_PF_LAUNCH(MC)                                                                                    \
+    do {                                                                                                         \
+        if (v.mode == B200GS_MODE_GSPLAT) {                                                                      \
+            if (raw_mode) project_fwd_kernel<true, true, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);         \
+            else project_fwd_kernel<true, false, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);                 \
+        } else {                                                                                                 \
+            if (raw_mode) project_fwd_kernel<false, true, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);        \
+            else project_fwd_kernel<false, false, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);                \
+        }                                                                                                        \
+    } while (0)
+    if (shs_dc != nullptr && v.sh_degree > 3) B200GS_PF_LAUNCH(25);
+    else B200GS_PF_LAUNCH(16);
+#undef B200GS_PF_LAUNCH
 #undef B200GS_PF_ARGS
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
@@ -915,13 +952,19 @@ int launch_project_bwd_raw(const B200gsView& v, int64_t n, const float* means, c
     RawIO raw{opac_logits, shs_rest, nullptr, v_opac, v_opac_logit, v_shs_rest, anti_aliased, v_rows, row_offsets, accumulate};
 #define B200GS_PB_ARGS v, raw, n, means, scales, quats, shs_dc, radii, clamped, (const float2*)v_xy, v_depth, v_conic, v_comp, v_rgb, \
                        v_means, v_scales, (float4*)v_quats, v_shs_dc
-    if (v.mode == B200GS_MODE_GSPLAT) {
-        if (raw_mode) project_bwd_kernel<true, true><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);
-        else project_bwd_kernel<true, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);
-    } else {
-        if (raw_mode) project_bwd_kernel<false, true><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);
-        else project_bwd_kernel<false, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);
-    }
+#define B200GS_PB_LAUNCH(MC)                                                                                    \
+    do {                                                                                                         \
+        if (v.mode == B200GS_MODE_GSPLAT) {                                                                      \
+            if (raw_mode) project_bwd_kernel<true, true, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);         \
+            else project_bwd_kernel<true, false, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);                 \
+        } else {                                                                                                 \
+            if (raw_mode) project_bwd_kernel<false, true, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);        \
+            else project_bwd_kernel<false, false, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);                \
+        }                                                                                                        \
+    } while (0)
+    if (v_shs_dc != nullptr && v.sh_degree > 3) B200GS_PB_LAUNCH(25);
+    else B200GS_PB_LAUNCH(16);
+#undef B200GS_PB_LAUNCH
 #undef B200GS_PB_ARGS
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
@@ -935,8 +978,12 @@ int launch_project_fwd_multi(const B200gsView* views, int n_views, int64_t n, co
     for (int j = 0; j < n_views; ++j) vp.v[j] = views[j];
     for (int j = n_views; j < B200GS_MAX_VIEWS; ++j) vp.v[j] = views[0];
     RawIO raw{opac_logits, shs_rest, opac_out, nullptr, nullptr, nullptr, anti_aliased, nullptr, nullptr, 0};
-    project_fwd_multi_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(vp, n_views, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth, radii,
-                                                                        conic, rgb, clamped);
+    if (views[0].sh_degree > 3)
+        project_fwd_multi_kernel<25><<<(unsigned)div_up64(n, 256), 256, 0, s>>>(vp, n_views, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth,
+                                                                                radii, conic, rgb, clamped);
+    else
+        project_fwd_multi_kernel<16><<<(unsigned)div_up64(n, 256), 256, 0, s>>>(vp, n_views, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth,
+                                                                                radii, conic, rgb, clamped);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }
@@ -955,15 +1002,22 @@ int launch_project_bwd_multi(const B200gsView* views, int n_views, int64_t n, co
         src.rows[j] = (j < n_views && v_rows[j]) ? v_rows[j] : dummy;   // NULL only when no row of that view is ever read
     }
     RawIO raw{opac_logits, shs_rest, nullptr, nullptr, v_opac_logit, v_shs_rest, anti_aliased, nullptr, nullptr, 0};
-    project_bwd_multi_kernel<<<(unsigned)div_up64(n, BWD_THREADS), BWD_THREADS, 0, s>>>(vp, n_views, raw, src, n, means, scales, quats, radii, clamped,
-                                                                                        row_index, v_means, v_scales, (float4*)v_quats, v_shs_dc);
+    if (views[0].sh_degree > 3)
+        project_bwd_multi_kernel<25><<<(unsigned)div_up64(n, BWD_THREADS), BWD_THREADS, 0, s>>>(vp, n_views, raw, src, n, means, scales, quats, radii,
+                                                                                                clamped, row_index, v_means, v_scales, (float4*)v_quats,
+                                                                                                v_shs_dc);
+    else
+        project_bwd_multi_kernel<16><<<(unsigned)div_up64(n, BWD_THREADS), BWD_THREADS, 0, s>>>(vp, n_views, raw, src, n, means, scales, quats, radii,
+                                                                                                clamped, row_index, v_means, v_scales, (float4*)v_quats,
+                                                                                                v_shs_dc);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }
 
 int launch_sh_fwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, cudaStream_t s) {
     if (n == 0) return B200GS_OK;
-    sh_fwd_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(degree, stride, n, dirs, coeffs, rgb);
+    if (degree > 3) sh_fwd_kernel<25><<<(unsigned)div_up64(n, 256), 256, 0, s>>>(degree, stride, n, dirs, coeffs, rgb);
+    else sh_fwd_kernel<16><<<(unsigned)div_up64(n, 256), 256, 0, s>>>(degree, stride, n, dirs, coeffs, rgb);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }
@@ -971,7 +1025,8 @@ int launch_sh_fwd(int degree, int stride, int64_t n, const float* dirs, const fl
 int launch_sh_bwd(int degree, int stride, int64_t n, const float* dirs, const float* coeffs, const float* v_rgb,
                   float* v_coeffs, float* v_dirs, cudaStream_t s) {
     if (n == 0) return B200GS_OK;
-    sh_bwd_kernel<<<(unsigned)div_up64(n, 256), 256, 0, s>>>(degree, stride, n, dirs, coeffs, v_rgb, v_coeffs, v_dirs);
+    if (degree > 3) sh_bwd_kernel<25><<<(unsigned)div_up64(n, 256), 256, 0, s>>>(degree, stride, n, dirs, coeffs, v_rgb, v_coeffs, v_dirs);
+    else sh_bwd_kernel<16><<<(unsigned)div_up64(n, 256), 256, 0, s>>>(degree, stride, n, dirs, coeffs, v_rgb, v_coeffs, v_dirs);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }

@@ -27,7 +27,10 @@ def make_scene(n: int, seed: int = 0, extent: float = 1.3, mean_scale: float = 0
     rotations = torch.randn(n, 4, generator=g)
     opacities = 1.5 * torch.randn(n, 1, generator=g)
     shs_dc = 0.5 * torch.randn(n, 1, 3, generator=g)
-    shs_rest = 0.1 * torch.randn(n, 15, 3, generator=g)[:, :k_rest, :].contiguous()
+    shs_rest = 0.1 * torch.randn(n, 15, 3, generator=g)
+    if k_rest > 15:   # degree 4: drawn after everything else, so the degree <= 3 scenes keep their law
+        shs_rest = torch.cat([shs_rest, 0.1 * torch.randn(n, k_rest - 15, 3, generator=g)], dim=1)
+    shs_rest = shs_rest[:, :k_rest, :].contiguous()
     return {"means": means, "scales": scales, "rotations": rotations, "opacities": opacities, "shs_dc": shs_dc,
             "shs_rest": shs_rest}
 

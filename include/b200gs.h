@@ -58,7 +58,7 @@ typedef struct B200gsView {
     int32_t width;
     int32_t height;
     int32_t mode;           /* B200GS_MODE_* */
-    int32_t sh_degree;      /* active degree 0..3 */
+    int32_t sh_degree;      /* active degree 0..4 */
     int32_t sh_stride;      /* coefficients stored per Gaussian (K of shs[N,K,3]); >= (sh_degree+1)^2 */
     int32_t reserved0;
     float fx, fy, cx, cy;   /* gsplat mode intrinsics (gsplat_renderer.py:70-73) */

@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
 B200GS_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_experimental.py -q -m gpu > gpurun_out/r2a_exp.log 2>&1; echo "exp rc=$?"
 timeout 1500 python -m pytest tests/test_gpu_parity.py -q -m gpu > gpurun_out/r2a_gpu_parity.log 2>&1; echo "parity rc=$?"
-timeout 900 python -m pytest tests/test_gpu_fullsize_parity.py tests/test_gpu_reference_dropin.py -q -m gpu > gpurun_out/r2a_gpu_full.log 2>&1; echo "full rc=$?"
+timeout 1200 python -m pytest tests/test_gpu_fullsize_parity.py tests/test_gpu_reference_dropin.py tests/test_gpu_v1_surface.py -q -m gpu > gpurun_out/r2a_gpu_full.log 2>&1; echo "full rc=$?"
 timeout 300 python bench.py --steps 48 --warmup 6 --no-cpu-baseline --no-extras > gpurun_out/r2a_bench_tr.log 2>&1
 B200GS_BWD_BUTTERFLY=1 timeout 300 python bench.py --steps 48 --warmup 6 --no-cpu-baseline --no-extras > gpurun_out/r2a_bench_bf.log 2>&1
 B200GS_FWD_SYNC=1 timeout 300 python bench.py --steps 48 --warmup 6 --no-cpu-baseline --no-extras > gpurun_out/r2a_bench_sync.log 2>&1

@@ -501,3 +501,56 @@ def test_full_size_properties(mode):
     for k in g1:                                        # backward is linear in the cotangent
         assert bool(torch.isfinite(g1[k]).all())
         assert _rel(g2[k], 2 * g1[k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("mode", [O.MODE_VANILLA, O.MODE_GSPLAT])
+@pytest.mark.parametrize("deg", [0, 1, 2, 3, 4])
+def test_sh_degrees_values_and_gradients(mode, deg):
+    """Every SH degree the reference evaluates (sh_utils.py:57-112, 0..4): colours from K1 and the standalone SH op against the
+    float64 oracle, K8 / SH-backward gradients against autograd through it (incl. the view-direction gradient of vanilla mode).
+    The coefficient storage is wider than the active degree (max degree 4 model), as during the reference's SH-degree schedule."""
+    from b200gs import ops
+    n, W, H, K = 1500, 160, 120, 25
+    g = torch.Generator().manual_seed(40 + deg)
+    from b200gs.scene import make_scene, activate
+    sc = activate(make_scene(n, 9, mean_scale=0.05))
+    shs = torch.cat([sc["shs"][:, :1], 0.2 * torch.randn(n, K - 1, 3, generator=g)], dim=1).contiguous()
+    cam = _cam(W, H, 2)
+    ncoef = (deg + 1) ** 2
+    ins = {"means": sc["means"].clone().double().requires_grad_(True), "shs": shs.clone().double().requires_grad_(True)}
+    ref_rgb = O.sh_colors(deg, ins["shs"][:, :ncoef], ins["means"], cam.camera_center.double(), detach_dir=(mode == O.MODE_GSPLAT))
+    c_rgb = torch.randn(n, 3, generator=g)
+    proj = O.project(mode, sc["means"].double(), sc["scales"].double(), sc["rotations"].double(), _oview(cam))
+    vis = proj["mask"]
+    (ref_rgb * (c_rgb * vis[:, None]).double()).sum().backward()
+
+    dev = {k: v.to(DEV) for k, v in sc.items()}
+    dshs = shs.to(DEV)
+    view = _cview(cam, mode, sh_degree=deg, sh_stride=K)
+    xy, depth, radii, conic, comp, tiles, _, rgb, clamped = ops.project_forward(view, dev["means"], dev["scales"], dev["rotations"], dshs, True)
+    same = (radii.cpu() > 0) == vis
+    ok = vis & same
+    assert int((~same).sum()) <= 1
+    assert torch.allclose(rgb.cpu().double()[ok], ref_rgb.detach()[ok], rtol=1e-4, atol=3e-5)
+    zeros2, zeros3 = torch.zeros(n, 2, device=DEV), torch.zeros(n, 3, device=DEV)
+    v_means, v_scales, v_quats, v_shs = ops.project_backward(view, dev["means"], dev["scales"], dev["rotations"], dshs, radii, clamped, zeros2,
+                                                             torch.zeros(n, device=DEV) if mode == O.MODE_GSPLAT else None, zeros3,
+                                                             torch.zeros(n, device=DEV) if mode == O.MODE_GSPLAT else None, c_rgb.to(DEV).contiguous())
+    assert _rel(v_shs.cpu()[same], ins["shs"].grad[same]) < 1e-3
+    assert float(v_shs[:, ncoef:].abs().max()) == 0.0                         # coefficients above the active degree get no gradient
+    if mode == O.MODE_VANILLA and deg > 0:
+        assert _rel(v_means.cpu()[same], ins["means"].grad[same]) < 1e-3      # dgr back-propagates the view direction into the means
+    else:
+        assert float(v_means.abs().max()) == 0.0
+
+    # the standalone op (gsplat.sh.spherical_harmonics): no +0.5 / clamp, direction gradient on request
+    dirs = (sc["means"] - cam.camera_center).clone()
+    d64, s64 = dirs.double().requires_grad_(True), shs.double().requires_grad_(True)
+    unit = d64 / d64.norm(dim=-1, keepdim=True)
+    ref = O.eval_sh(deg, s64, unit)
+    dd, ds = dirs.to(DEV).requires_grad_(True), dshs.clone().requires_grad_(True)
+    out = ops.spherical_harmonics(deg, dd, ds)
+    (out * c_rgb.to(DEV)).sum().backward()
+    (ref * c_rgb.double()).sum().backward()
+    assert torch.allclose(out.detach().cpu().double(), ref.detach(), rtol=1e-4, atol=3e-5)
+    assert _rel(ds.grad, s64.grad) < 1e-3 and (deg == 0 or _rel(dd.grad, d64.grad) < 1e-3)

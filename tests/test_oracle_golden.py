@@ -138,3 +138,15 @@ def test_product_camera_matches_reference_cameras_class():
         ref, mine = cams[0], make_ring_cameras(W, H)[k]
         for name in ("world_to_camera", "full_projection", "camera_center", "fov_x", "fov_y"):
             assert torch.equal(getattr(ref, name), getattr(mine, name)), name
+
+
+def test_sh_degree4_matches_reference():
+    """Degree 4 (sh_utils.py:102-111), values and gradients, against the reference's eval_sh (tests/golden/make_golden_sh4.py)."""
+    d = np.load(os.path.join(GOLDEN, "sh_deg4.npz"))
+    shs = torch.tensor(d["shs"]).requires_grad_(True)
+    dirs = torch.tensor(d["dirs"]).requires_grad_(True)
+    rgb = O.eval_sh(4, shs, dirs)
+    assert torch.allclose(rgb, torch.tensor(d["rgb"]), rtol=1e-5, atol=1e-6)
+    (rgb * torch.tensor(d["cot"])).sum().backward()
+    assert torch.allclose(shs.grad, torch.tensor(d["g_shs"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(dirs.grad, torch.tensor(d["g_dirs"]), rtol=1e-4, atol=1e-5)
