@@ -230,6 +230,20 @@ int b200gs_ipc_free(void* dev_ptr) {
     return B200GS_OK;
 }
 
+int b200gs_selective_adam(int64_t rows, int32_t width, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                          const uint8_t* visible, float lr, float beta1, float beta2, float eps, void* stream) {
+    B200GS_CHECK_ARG(rows >= 0 && width > 0, "bad sizes");
+    B200GS_CHECK_ARG(rows == 0 || (param && grad && exp_avg && exp_avg_sq && visible), "NULL pointer");
+    return launch_selective_adam(rows, width, param, grad, exp_avg, exp_avg_sq, visible, lr, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+int b200gs_densify_stats(int64_t n, const int32_t* radii, const uint8_t* visible, const float* grad, int32_t grad_stride, float scale_x,
+                         float scale_y, float* max_radii2d, float* grad_accum, float* denom, void* stream) {
+    B200GS_CHECK_ARG(n >= 0 && grad_stride >= 2, "bad sizes");
+    B200GS_CHECK_ARG(n == 0 || (radii && grad && max_radii2d && grad_accum && denom), "NULL pointer");
+    return launch_densify_stats(n, radii, visible, grad, grad_stride, scale_x, scale_y, max_radii2d, grad_accum, denom, (cudaStream_t)stream);
+}
+
 int b200gs_sh_fwd(int32_t degree, int32_t sh_stride, int64_t n, const float* dirs, const float* coeffs, float* rgb, void* stream) {
     B200GS_CHECK_ARG(degree >= 0 && degree <= 4, "degree must be 0..4");
     B200GS_CHECK_ARG(sh_stride >= (degree + 1) * (degree + 1), "sh_stride < (degree+1)^2");

@@ -116,6 +116,11 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
              const void* ws_a, void* ws_b, size_t ws_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges, int64_t* host_counts,
              int sync_host, cudaStream_t s);
 
+int launch_selective_adam(int64_t rows, int width, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const uint8_t* visible,
+                          float lr, float b1, float b2, float eps, cudaStream_t s);
+int launch_densify_stats(int64_t n, const int32_t* radii, const uint8_t* visible, const float* grad, int grad_stride, float sx, float sy,
+                         float* max_radii2d, float* grad_accum, float* denom, cudaStream_t s);
+
 int64_t loss_blocks(int channels, int width, int height);
 int launch_loss_fwd(int channels, int width, int height, const float* img, const float* gt, float* dmaps, float* partials, cudaStream_t s);
 int launch_loss_bwd(int channels, int width, int height, const float* img, const float* gt, const float* dmaps, float lambda_dssim,

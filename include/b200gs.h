@@ -120,6 +120,19 @@ B200GS_API int b200gs_project_bwd_raw(const B200gsView* view, int64_t n, const f
                            float* v_log_scales, float* v_raw_quats, float* v_opacity_logits, float* v_shs_dc, float* v_shs_rest,
                            void* stream);
 
+/* ---- per-Gaussian passes next to the renderer in a training step ---------------------------------------
+ * b200gs_selective_adam: visibility-masked Adam step of one [rows, width] parameter tensor (gsplat.optimizers.SelectiveAdam /
+ *     diff-accel SparseGaussianAdam, internal/optimizers.py:26-90): for the rows with visible[row] != 0
+ *     m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr m / (sqrt(v) + eps)   (no bias correction, like those kernels);
+ *     rows that did not take part in the view keep parameter and moments untouched.
+ * b200gs_densify_stats: VanillaDensityControllerImpl.update_states (vanilla_density_controller.py:101-123) in one pass: on the
+ *     visible rows (visible[n] bytes, or radii > 0 when NULL) max_radii2d = max(max_radii2d, radii), grad_accum += |grad[:, :2] *
+ *     (scale_x, scale_y)|, denom += 1.  grad has grad_stride floats per row (2 for gsplat xys, 3 for dgr's screenspace points). */
+B200GS_API int b200gs_selective_adam(int64_t rows, int32_t width, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                     const uint8_t* visible, float lr, float beta1, float beta2, float eps, void* stream);
+B200GS_API int b200gs_densify_stats(int64_t n, const int32_t* radii, const uint8_t* visible, const float* grad, int32_t grad_stride,
+                                    float scale_x, float scale_y, float* max_radii2d, float* grad_accum, float* denom, void* stream);
+
 /* ---- standalone SH (gsplat.sh.spherical_harmonics; gsplat_renderer.py:105) -------------------------------------------
  * dirs[n,3] need not be unit (normalised inside, as gsplat does).  out rgb[n,3] = SH (no +0.5, no clamp).
  * bwd: v_coeffs[n,sh_stride,3] fully written; v_dirs[n,3] nullable. */

@@ -337,11 +337,16 @@ def sort_and_ranges(keys: torch.Tensor, ids: torch.Tensor, n_tiles: int):
 # --------------------------------------------------------------------------------------------------------------------
 def blend(mode: int, xy: torch.Tensor, conic: torch.Tensor, opacity: torch.Tensor, colors: torch.Tensor,
           sorted_ids: torch.Tensor, ranges: torch.Tensor, bg: Optional[torch.Tensor], width: int, height: int,
-          block: int = BLOCK):
+          block: int = BLOCK, margins: Optional[list] = None):
     """Per-tile front-to-back compositing.  xy [N,2], conic [N,3], opacity [N], colors [N,D].
 
     Returns image [D,H,W], alpha [H,W] (= 1 - T_final), n_contrib int32 [H,W] (1-based index, inside the tile's
     list, of the last splat that contributed — dgr's n_contrib), all on CPU.  Differentiable wrt xy/conic/opacity/colors.
+
+    margins: pass an empty list to receive ONE [H,W] tensor: per pixel, the smallest relative distance of any of its
+    (pixel, splat) samples to a branch threshold of the loop (alpha vs 1/255, remaining T vs 1e-4, power vs 0, alpha vs the
+    clamp of the gsplat backward).  A sample closer to a threshold than fp32 resolves may take the other branch in a
+    float32 implementation; tests use this map to tell such pixels from real errors.
     """
     dt = xy.dtype
     D = colors.shape[1]
@@ -364,6 +369,7 @@ def blend(mode: int, xy: torch.Tensor, conic: torch.Tensor, opacity: torch.Tenso
             PX = px[None, :].expand(y1 - y0, x1 - x0).reshape(-1)
             PY = py[:, None].expand(y1 - y0, x1 - x0).reshape(-1)
             npx = PX.shape[0]
+            tile_margin = torch.full((npx,), float("inf"), dtype=dt)
             if e <= s:
                 C = torch.zeros(npx, D, dtype=dt)
                 Tf = torch.ones(npx, dtype=dt)
@@ -386,6 +392,14 @@ def blend(mode: int, xy: torch.Tensor, conic: torch.Tensor, opacity: torch.Tenso
                     testT = torch.cumprod(1.0 - a_eff, dim=1)
                     alive = (testT > 1e-4) if mode == MODE_GSPLAT else (testT >= 1e-4)
                     active = valid & alive
+                    if margins is not None:
+                        reach = torch.cat([torch.ones(npx, 1, dtype=torch.bool), alive[:, :-1]], dim=1)   # the sample is evaluated at all
+                        big = torch.full((), float("inf"), dtype=dt)
+                        m_alpha = torch.where(reach & (power <= 0), (raw - 1.0 / 255.0).abs() * 255.0, big)
+                        m_T = torch.where(reach & valid, (testT - 1e-4).abs() / 1e-4, big)
+                        m_pow = torch.where(reach, power.abs() / 1e-3, big)          # power > 0 is skipped: absolute scale 1e-3
+                        m_clamp = torch.where(reach & valid, (raw - amax).abs() / amax, big)
+                        tile_margin = torch.minimum(torch.minimum(m_alpha, m_T), torch.minimum(m_pow, m_clamp)).min(dim=1).values
                     idx = torch.arange(1, e - s + 1, dtype=torch.int32)[None, :].expand_as(active)
                     last = torch.where(active, idx, torch.zeros((), dtype=torch.int32)).max(dim=1).values
                 a_act = torch.where(active, a, torch.zeros((), dtype=dt))
@@ -398,12 +412,13 @@ def blend(mode: int, xy: torch.Tensor, conic: torch.Tensor, opacity: torch.Tenso
             if bg is not None:
                 C = C + Tf[:, None] * bg.to(dt)[None, :]
             row_tiles.append((C.reshape(y1 - y0, x1 - x0, D), (1.0 - Tf).reshape(y1 - y0, x1 - x0),
-                              last.reshape(y1 - y0, x1 - x0)))
-        img_rows.append((torch.cat([r[0] for r in row_tiles], dim=1), torch.cat([r[1] for r in row_tiles], dim=1),
-                         torch.cat([r[2] for r in row_tiles], dim=1)))
+                              last.reshape(y1 - y0, x1 - x0), tile_margin.detach().reshape(y1 - y0, x1 - x0)))
+        img_rows.append(tuple(torch.cat([r[k] for r in row_tiles], dim=1) for k in range(4)))
     img = torch.cat([r[0] for r in img_rows], dim=0)
     alpha_img = torch.cat([r[1] for r in img_rows], dim=0)
     ncontrib = torch.cat([r[2] for r in img_rows], dim=0)
+    if margins is not None:
+        margins.append(torch.cat([r[3] for r in img_rows], dim=0))
     return img.permute(2, 0, 1), alpha_img, ncontrib
 
 
@@ -413,7 +428,7 @@ def blend(mode: int, xy: torch.Tensor, conic: torch.Tensor, opacity: torch.Tenso
 def render(mode: int, means: torch.Tensor, scales: torch.Tensor, quats: torch.Tensor, opacities: torch.Tensor,
            shs: Optional[torch.Tensor], view: View, bg: Optional[torch.Tensor], sh_degree: int = 3,
            scale_modifier: float = 1.0, colors_precomp: Optional[torch.Tensor] = None, anti_aliased: bool = True,
-           eps2d: float = 0.3):
+           eps2d: float = 0.3, margins: Optional[list] = None):
     """End-to-end oracle of VanillaRenderer.forward (vanilla_renderer.py:25-129) / GSPlatRenderer.forward's rgb path
     (gsplat_renderer.py:58-108) on activated parameters.  opacities [N,1] or [N]."""
     proj = project(mode, means, scales, quats, view, scale_modifier, eps2d)
@@ -431,7 +446,7 @@ def render(mode: int, means: torch.Tensor, scales: torch.Tensor, quats: torch.Te
     xy = proj["xy"]
     if xy.requires_grad:
         xy.retain_grad()
-    img, alpha, ncontrib = blend(mode, xy, proj["conic"], op, colors, sids, ranges, bg, view.width, view.height)
+    img, alpha, ncontrib = blend(mode, xy, proj["conic"], op, colors, sids, ranges, bg, view.width, view.height, margins=margins)
     return {
         "render": img, "alpha": alpha, "n_contrib": ncontrib, "xy": xy, "radii": proj["radii"], "proj": proj,
         "colors": colors, "sorted_keys": skeys, "sorted_ids": sids, "ranges": ranges,

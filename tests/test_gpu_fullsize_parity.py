@@ -5,8 +5,11 @@ the WHOLE scene (cheap), builds and stably sorts all (tile|depth) keys, and then
 non-empty tiles.  The CUDA renderer runs the full frame; its pixels inside the sampled tiles must match within 1e-4
 abs, and — with the cotangent masked to those tiles, so that only the Gaussians listed in them receive gradient — every
 parameter gradient must match autograd through the oracle within 1e-3 (of the tensor's max magnitude), both constant
-sets, plug-in path with fused and unfused activations.  Threshold-flip pixels (a sample whose alpha sits within fp32
-rounding of 1/255 takes the other branch) are counted and the count is asserted.
+sets, plug-in path with fused and unfused activations.  Threshold flips are not tolerated blindly: the oracle reports, per
+pixel, how close any of its samples comes to a branch threshold of the blend loop (alpha vs 1/255, T vs 1e-4, ...);
+pixels closer than AMBIGUOUS (relative) may legitimately take the other branch in fp32 — they are excluded from the
+cotangent (their gradient contribution is branch-dependent), counted, and bounded; every other sampled pixel must
+match within 1e-4, no exceptions.
 """
 import json
 import os
@@ -20,9 +23,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 SIZES = [(30_000, 800, 800, 0, 0.01, 48), (1_000_000, 1920, 1080, 0, 0.01, 48)]
-# measured on B200 (gpurun_out/flip_counts.json of the run that introduced this test): at most 1 pixel of the 12 288
-# sampled ones is off by more than 1e-4, and never by more than one alpha step (1/255) x |colour| <= 1
-MAX_FLIPS = 3
+AMBIGUOUS = 5e-4      # fp32 resolves alpha = o * exp2(q) to ~2e-6 and a product of ~1000 (1 - alpha) factors to ~6e-5, relative
+# measured on B200 (profiles/round2_flip_counts.json): of ~12.7 k sampled pixels 0 (1 M scenes) to 2 (30 k scenes) are off by more
+# than 1e-4, all of them among the pixels the oracle marks ambiguous
+MAX_AMBIGUOUS_FRACTION = 0.05
 
 
 def _oracle_sampled(mode, act, cam, bg, n_tiles_sample, seed=5):
@@ -58,16 +62,19 @@ def _oracle_sampled(mode, act, cam, bg, n_tiles_sample, seed=5):
     xy = p["xy"]
     xy.retain_grad()
     sub_sids = remap[sids.long()].clamp_min(0).to(torch.int32)      # entries outside the sampled tiles are never read
-    img, alpha, _ = O.blend(mode, xy, p["conic"], op, colors, sub_sids, sel_ranges, bg.double(), W, H)
+    margins = []
+    img, alpha, _ = O.blend(mode, xy, p["conic"], op, colors, sub_sids, sel_ranges, bg.double(), W, H, margins=margins)
+    ambiguous = margins[0] < AMBIGUOUS
     mask = torch.zeros(gy * 16, gx * 16, dtype=torch.bool)
     for t in pick.tolist():
         ty, tx = divmod(t, gx)
         mask[ty * 16:(ty + 1) * 16, tx * 16:(tx + 1) * 16] = True
     mask = mask[:H, :W]
-    cot = (torch.rand(3, H, W, generator=torch.Generator().manual_seed(1)) * 2 - 1) * mask
+    ambiguous = ambiguous & mask
+    cot = (torch.rand(3, H, W, generator=torch.Generator().manual_seed(1)) * 2 - 1) * (mask & ~ambiguous)
     (img * cot.double()).sum().backward()
     grads = {k: sub[k].grad for k in sub}
-    return pick, img.detach(), S, grads, cot, mask, O.viewspace_grad(mode, xy.grad, W, H)
+    return pick, img.detach(), S, grads, cot, mask, O.viewspace_grad(mode, xy.grad, W, H), ambiguous
 
 
 def _rel(a, b):
@@ -84,8 +91,10 @@ def test_sampled_tiles_match_oracle_at_benchmark_sizes(mode, n, W, H, seed, ms, 
     act = activate(raw)
     cam = make_ring_cameras(W, H)[0]
     bg = torch.tensor([0.3, 0.1, 0.7])
-    pick, ref_img, S, ref_g, cot, mask, ref_vs = _oracle_sampled(mode, act, cam, bg, n_sample)
+    pick, ref_img, S, ref_g, cot, mask, ref_vs, ambiguous = _oracle_sampled(mode, act, cam, bg, n_sample)
     assert S.numel() > 100 and int(mask.sum()) >= 16 * 16 * (n_sample // 2)
+    assert int(ambiguous.sum()) <= MAX_AMBIGUOUS_FRACTION * int(mask.sum())
+    clear = mask & ~ambiguous
 
     R = B200VanillaRenderer if mode == O.MODE_VANILLA else B200GSplatRenderer
     cam_d = cam.to_device(DEV)
@@ -94,11 +103,12 @@ def test_sampled_tiles_match_oracle_at_benchmark_sizes(mode, n, W, H, seed, ms, 
     out = R.render(gp["means"], gp["opacities"], gp["scales"], gp["rotations"], gp["shs"], 3, cam_d, bg.to(DEV))
     out["viewspace_points"].retain_grad()
     (out["render"] * cot.to(DEV)).sum().backward()
-    err = (out["render"].detach().cpu().double() - ref_img).abs().max(dim=0).values[mask]
-    flips = int((err > 1e-4).sum())
-    rec = {"mode": mode, "n": n, "size": [W, H], "sampled_pixels": int(mask.sum()), "pixels_over_1e-4": flips,
-           "max_err": float(err.max()), "median_err": float(err.median())}
-    assert flips <= MAX_FLIPS, rec
+    err_map = (out["render"].detach().cpu().double() - ref_img).abs().max(dim=0).values
+    err = err_map[mask]
+    rec = {"mode": mode, "n": n, "size": [W, H], "sampled_pixels": int(mask.sum()), "ambiguous_pixels": int(ambiguous.sum()),
+           "pixels_over_1e-4": int((err > 1e-4).sum()), "unexplained_pixels_over_1e-4": int((err_map[clear] > 1e-4).sum()),
+           "max_err": float(err.max()), "max_err_clear": float(err_map[clear].max()), "median_err": float(err.median())}
+    assert rec["unexplained_pixels_over_1e-4"] == 0, rec
     assert float(err.max()) < 1.0 / 255.0 + 1e-4, rec
     assert float(err.median()) < 1e-6, rec
     names = {"means": "means", "scales": "scales", "rotations": "rotations", "opacities": "opacities", "shs": "shs"}
@@ -124,7 +134,7 @@ def test_sampled_tiles_match_oracle_at_benchmark_sizes(mode, n, W, H, seed, ms, 
         out2 = R(**kw).to(DEV)(cam_d, model, bg.to(DEV))
         (out2["render"] * cot.to(DEV)).sum().backward()
         e2 = (out2["render"].detach().cpu().double() - ref_img).abs().max(dim=0).values[mask]
-        assert int((e2 > 2e-4).sum()) <= MAX_FLIPS and float(e2.median()) < 2e-6     # torch-GPU activations differ by ulps
+        assert int((e2 > 2e-4).sum()) <= int(ambiguous.sum()) + 2 and float(e2.median()) < 2e-6     # torch-GPU activations differ by ulps
         for k, ref in chain.items():
             assert _rel(model.gaussians[k].grad[Sd], ref[Sd]) < 2e-3, (k, kw)
     try:   # measured flip counts, for the record (profiles/)

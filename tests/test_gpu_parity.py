@@ -38,16 +38,25 @@ def _cview(cam, mode, sh_degree=3, sh_stride=16):
     return _view_with(camera_view(cam, mode, cache=False), sh_degree=sh_degree, sh_stride=sh_stride)
 
 
-def _assert_pixels(img, ref, what=""):
-    """Forward bar: 1e-4 abs.  A sample whose alpha (or remaining T) sits within an ulp of the 1/255 (or 1e-4) cut-off
-    takes the other branch in fp32 than in the float64 oracle and moves that one pixel by up to alpha*T*c <= 1/255;
-    such isolated pixels are counted and bounded instead of failing the image."""
+AMBIGUOUS = 5e-4   # relative distance of a sample to a branch threshold below which fp32 may legitimately take the other branch
+
+
+def _assert_pixels(img, ref, what="", margin=None):
+    """Forward bar: 1e-4 abs on every pixel — except those the ORACLE marks ambiguous: a sample whose alpha (or remaining T)
+    sits within AMBIGUOUS (relative) of the 1/255 (or 1e-4) cut-off may take the other branch in fp32 than in float64 and
+    moves that pixel by up to alpha*T*c <= 1/255.  `margin` is the oracle's per-pixel map of that distance (gs_oracle.blend);
+    every pixel off by more than 1e-4 must be one of them (no unexplained flips), their error stays below one alpha step,
+    and they are rare."""
     err = (img.detach().cpu().double() - ref.detach().cpu().double()).abs()
     per_pixel = err if err.dim() == 2 else err.max(dim=0).values      # [C,H,W] -> [H,W]
-    n_bad = int((per_pixel > 1e-4).sum())
-    # expected flips: ~1e-7 per (pixel, splat) evaluation (relative fp32 error of o*exp(q) around the cut-off)
-    assert n_bad <= max(4, per_pixel.numel() // 10000), f"{what}: {n_bad} pixels off by more than 1e-4 (max {float(err.max()):.3e})"
-    assert float(err.max()) < 4.5e-3, f"{what}: max err {float(err.max()):.3e}"
+    bad = per_pixel > 1e-4
+    if margin is not None:
+        ambiguous = margin < AMBIGUOUS
+        assert int((bad & ~ambiguous).sum()) == 0, f"{what}: {int((bad & ~ambiguous).sum())} pixels off by more than 1e-4 away from any threshold (max {float(per_pixel[~ambiguous].max()):.3e})"
+        assert int(ambiguous.sum()) <= max(8, per_pixel.numel() // 20), f"{what}: {int(ambiguous.sum())} ambiguous pixels"
+    else:
+        assert int(bad.sum()) <= max(4, per_pixel.numel() // 10000), f"{what}: {int(bad.sum())} pixels off by more than 1e-4 (max {float(err.max()):.3e})"
+    assert float(err.max()) < 1.0 / 255.0 + 1e-4, f"{what}: max err {float(err.max()):.3e}"
     assert float(err.median()) < 1e-6
 
 
@@ -223,7 +232,8 @@ def test_blend_forward_backward(mode, n, W, H, seed, pose, ms):
     conic = ref["conic"].clone().requires_grad_(True)
     opr = op.clone().requires_grad_(True)
     col = colors.clone().requires_grad_(True)
-    img, alpha, ncontrib = O.blend(mode, xy, conic, opr, col, sids, ranges, bg, W, H)
+    margins = []
+    img, alpha, ncontrib = O.blend(mode, xy, conic, opr, col, sids, ranges, bg, W, H, margins=margins)
     gen = torch.Generator().manual_seed(1)
     cot = torch.rand(3, H, W, generator=gen) * 2 - 1
     cot_a = torch.rand(H, W, generator=gen) * 2 - 1 if mode == O.MODE_GSPLAT else None
@@ -235,9 +245,9 @@ def test_blend_forward_backward(mode, n, W, H, seed, pose, ms):
     dxy, dcon, dop, dcol = (t.detach().to(DEV).contiguous() for t in (xy, conic, opr, col))
     image, final_T, n_contrib, a_out = ops.blend_forward(mode, W, H, binning, dxy, dcon, dop, dcol, bg.to(DEV), planar, True)
     image_chw = image if planar else image.permute(2, 0, 1)
-    _assert_pixels(image_chw, img, "image")
-    _assert_pixels(a_out, alpha, "alpha")
-    assert int((n_contrib.cpu() != ncontrib).sum()) <= max(2, W * H // 20000)
+    _assert_pixels(image_chw, img, "image", margins[0])
+    _assert_pixels(a_out, alpha, "alpha", margins[0])
+    assert int(((n_contrib.cpu() != ncontrib) & (margins[0] >= AMBIGUOUS)).sum()) == 0      # same last contributor wherever no sample is ambiguous
 
     v_image = cot.to(DEV).contiguous() if planar else cot.permute(1, 2, 0).contiguous().to(DEV)
     v_alpha = cot_a.to(DEV) if cot_a is not None else None
@@ -314,7 +324,8 @@ def test_renderer_end_to_end(mode, n, W, H, seed, pose, ms):
     cot = torch.rand(3, H, W, generator=gen) * 2 - 1
 
     ap = {k: v.double().requires_grad_(True) for k, v in act.items()}
-    out_ref = O.render(mode, ap["means"], ap["scales"], ap["rotations"], ap["opacities"], ap["shs"], _oview(cam), bg.double())
+    margins = []
+    out_ref = O.render(mode, ap["means"], ap["scales"], ap["rotations"], ap["opacities"], ap["shs"], _oview(cam), bg.double(), margins=margins)
     (out_ref["render"] * cot.double()).sum().backward()
 
     gp = {k: v.to(DEV).requires_grad_(True) for k, v in act.items()}
@@ -324,7 +335,7 @@ def test_renderer_end_to_end(mode, n, W, H, seed, pose, ms):
     out["viewspace_points"].retain_grad()
     (out["render"] * cot.to(DEV)).sum().backward()
 
-    _assert_pixels(out["render"], out_ref["render"], "render")
+    _assert_pixels(out["render"], out_ref["render"], "render", margins[0])
     assert int((out["radii"].cpu() != out_ref["radii"]).sum()) <= 1
     assert torch.equal(out["visibility_filter"].cpu(), out["radii"].cpu() > 0)
     for k in ap:
