@@ -121,7 +121,7 @@ int b200gs_project_bwd_rows(const B200gsView* view, int64_t n, const float* mean
     if (rc) return rc;
     B200GS_CHECK_ARG(n >= 0, "n < 0");
     if (n > 0) {
-        B200GS_CHECK_ARG(means && log_scales && raw_quats && opacity_logits && shs_dc && radii && clamped && row_offsets, "NULL input pointer");
+        B200GS_CHECK_ARG(means && log_scales && raw_quats && opacity_logits && shs_dc && radii && clamped, "NULL input pointer");
         B200GS_CHECK_ARG(view->sh_stride == 1 || (shs_rest && v_shs_rest), "shs_rest / v_shs_rest required when sh_stride > 1");
         B200GS_CHECK_ARG(v_means && v_log_scales && v_raw_quats && v_opacity_logits && v_shs_dc, "NULL output pointer");
     }
@@ -328,6 +328,19 @@ int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int32_t channe
     return launch_blend_bwd(mode, width, height, channels, tile_ranges, sorted_ids, 0, xy, conic, opacity, colors, bg, final_T,
                             n_contrib, v_image, pix_stride, ch_stride, v_alpha, xy_scale_x, xy_scale_y, v_xy, v_conic,
                             v_opacity, v_colors, v_xy_abs, (cudaStream_t)stream);
+}
+
+int b200gs_blend_bwd_to_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
+                             const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
+                             const float* final_T, const int32_t* n_contrib, const float* v_image, int64_t pix_stride, int64_t ch_stride,
+                             const float* v_alpha, float xy_scale_x, float xy_scale_y, float* v_rows, float* v_xy_abs, void* stream) {
+    B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
+    B200GS_CHECK_ARG(width > 0 && height > 0, "bad size");
+    B200GS_CHECK_ARG(tile_ranges && final_T && n_contrib && v_image, "NULL input pointer");
+    B200GS_CHECK_ARG(v_rows != nullptr && (reinterpret_cast<uintptr_t>(v_rows) & 15) == 0, "v_rows must be a 16-byte aligned [n,12] buffer");
+    return launch_blend_bwd(mode, width, height, 3, tile_ranges, sorted_ids, 0, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image,
+                            pix_stride, ch_stride, v_alpha, xy_scale_x, xy_scale_y, v_rows + B200GS_ROW_XY, v_rows + B200GS_ROW_CONIC,
+                            v_rows + B200GS_ROW_OPACITY, v_rows + B200GS_ROW_RGB, v_xy_abs, (cudaStream_t)stream, B200GS_ROW_FLOATS);
 }
 
 int b200gs_publish_i64(const int64_t* d_values, int64_t* host_values, int32_t n, void* stream) {

@@ -366,263 +366,10 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_asy
     }
 }
 
-// ---- warp reduce-scatter: RB values per lane -> lane keeps the 32-lane total of slot rs_slot(lane) ---------------------
-template <int RB>
-__device__ __forceinline__ int rs_slot(unsigned lane);
-template <>
-__device__ __forceinline__ int rs_slot<8>(unsigned lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
-template <>
-__device__ __forceinline__ int rs_slot<4>(unsigned lane) { return ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1); }
-
-__device__ __forceinline__ float rs_step(float lo, float hi, bool up, int mask) {
-    const float send = up ? lo : hi;
-    const float keep = up ? hi : lo;
-    return keep + __shfl_xor_sync(FULL, send, mask);
-}
-
-template <int RB>
-__device__ __forceinline__ float reduce_scatter(const float* p, unsigned lane);
-
-template <>
-__device__ __forceinline__ float reduce_scatter<8>(const float* p, unsigned lane) {
-    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
-    const float q0 = rs_step(p[0], p[4], b16, 16), q1 = rs_step(p[1], p[5], b16, 16);
-    const float q2 = rs_step(p[2], p[6], b16, 16), q3 = rs_step(p[3], p[7], b16, 16);
-    const float r0 = rs_step(q0, q2, b8, 8), r1 = rs_step(q1, q3, b8, 8);
-    float s = rs_step(r0, r1, b4, 4);
-    s += __shfl_xor_sync(FULL, s, 2);
-    s += __shfl_xor_sync(FULL, s, 1);
-    return s;
-}
-
-template <>
-__device__ __forceinline__ float reduce_scatter<4>(const float* p, unsigned lane) {
-    const bool b16 = lane & 16, b8 = lane & 8;
-    const float q0 = rs_step(p[0], p[2], b16, 16), q1 = rs_step(p[1], p[3], b16, 16);
-    float s = rs_step(q0, q1, b8, 8);
-    s += __shfl_xor_sync(FULL, s, 4);
-    s += __shfl_xor_sync(FULL, s, 2);
-    s += __shfl_xor_sync(FULL, s, 1);
-    return s;
-}
-
-// VS ("value scatter", experimental, opt-in with B200GS_BWD_VS=1, CH == 3, RB == 4, no absgrad): after the two entry-splitting
-// steps of the reduce-scatter the nine totals of an entry are reduced over the remaining 8 lanes with a reduce-scatter over
-// the VALUES (5 + 3 + 3 shuffles instead of 27), so each of the 8 lanes ends up owning one total (lane 0 of the group owns
-// the coupled pair sum(vs dx), sum(vs dy)) and issues its own atomic: two lane-parallel REDs instead of nine serial ones.
-template <int CH, bool GSPLAT, bool ABS, int RB, bool VS = false>
-__global__ void __launch_bounds__(BLOCK_PIX, (RB == 4 && !ABS) ? 4 : 1) blend_bwd_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
-                                                              const int32_t* __restrict__ ids, const SplatStrides st, const float* __restrict__ xy,
-                                                              const float* __restrict__ conic, const float* __restrict__ opacity,
-                                                              const float* __restrict__ colors, const float* __restrict__ bg,
-                                                              const float* __restrict__ final_T, const int32_t* __restrict__ n_contrib,
-                                                              const float* __restrict__ v_image, int64_t pix_stride, int64_t ch_stride,
-                                                              const float* __restrict__ v_alpha, float sx, float sy,
-                                                              float* __restrict__ v_xy, float* __restrict__ v_conic,
-                                                              float* __restrict__ v_opacity, float* __restrict__ v_colors,
-                                                              float* __restrict__ v_xy_abs) {
-    // reduced per splat: the six moments  sum(go), sum(vs dx), sum(vs dy), sum(vs dx^2), sum(vs dx dy), sum(vs dy^2)  (vs = dL/dsigma,
-    // go = dL/dopacity) — the conic/mean gradients are linear in them, so the writer lane finishes the products once per
-    // splat instead of every lane per sample — plus the colour sums, plus |grad xy| when the absgrad side channel is on.
-    constexpr int NT = 6 + CH + (ABS ? 2 : 0);
-    static_assert(!VS || (CH == 3 && RB == 4 && !ABS), "value-scatter variant: 3 channels, RB 4, no absgrad");
-    __shared__ float4 s_rec[(BLOCK_PIX + 1) * 3];
-    __shared__ unsigned char s_mask[BLOCK_PIX];
-    __shared__ unsigned short s_list[NWARP][BLOCK_PIX + 2 * LIST_PAD];
-    __shared__ int s_wmax[NWARP];
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const unsigned lane = tid & 31u;
-    // VS: which total lane (lane & 7) of an 8-lane group owns, and where it goes
-    float* vs_base = nullptr;
-    int vs_stride = 0;
-    float vs_scale = 1.0f;
-    if (VS) {
-        switch (lane & 7u) {
-            case 0: vs_base = v_xy; vs_stride = st.xs; vs_scale = sx; break;              // + the y component, see the writer
-            case 1: vs_base = v_opacity; vs_stride = st.os; break;
-            case 2: vs_base = v_conic; vs_stride = st.cs; vs_scale = 0.5f; break;
-            case 3: vs_base = v_conic + 1; vs_stride = st.cs; break;
-            case 4: vs_base = v_conic + 2; vs_stride = st.cs; vs_scale = 0.5f; break;
-            case 5: vs_base = v_colors; vs_stride = st.ks; break;
-            case 6: vs_base = v_colors + 1; vs_stride = st.ks; break;
-            default: vs_base = v_colors + 2; vs_stride = st.ks; break;
-        }
-    }
-    const int tile = blockIdx.y * grid_x + blockIdx.x;
-    int lx, ly;
-    pixel_of_thread(tid, lx, ly);
-    const int px = blockIdx.x * TILE + lx, py = blockIdx.y * TILE + ly;
-    const bool inside = (px < width) && (py < height);
-    const float off = GSPLAT ? 0.5f : 0.0f;
-    const float pxf = float(px) + off, pyf = float(py) + off;
-    const float ox = float(blockIdx.x * TILE) + off, oy = float(blockIdx.y * TILE) + off;
-    const float amax = GSPLAT ? 0.999f : 0.99f;
-    const int64_t pix = int64_t(py) * width + px;
-    if (tid < 3) s_rec[DUMMY * 3 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    const int2 range = ranges[tile];
-    const float Tf = inside ? final_T[pix] : 0.f;
-    const int last = inside ? n_contrib[pix] : 0;
-    float vo[4] = {0.f, 0.f, 0.f, 0.f};
-    float bg_dot = 0.f;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        vo[c] = inside ? __ldg(v_image + pix * pix_stride + c * ch_stride) : 0.f;
-        if (bg) bg_dot += __ldg(bg + c) * vo[c];
-    }
-    const float va = (v_alpha && inside) ? __ldg(v_alpha + pix) : 0.f;
-    const float tail = Tf * (va - bg_dot);  // d(out)/d(alpha_i) through everything behind the last contributor
-
-    const int wmax = __reduce_max_sync(FULL, last);
-    if (lane == 0) s_wmax[warp] = wmax;
-    __syncthreads();
-    int max_last = 0;
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) max_last = max(max_last, s_wmax[w]);
-    if (max_last == 0) return;
-
-    float T = Tf;
-    float D = 0.f;   // <colour accumulated behind the current splat, v_image> for this pixel
-    const int my_slot = rs_slot<RB>(lane);
-    const bool writer = (lane & (32 / RB - 1)) == 0;
-
-    for (int hi = max_last; hi > 0; hi -= BLOCK_PIX) {
-        const int lo = max(0, hi - BLOCK_PIX);
-        const int cnt = hi - lo;
-        __syncthreads();
-        if (tid < cnt) {
-            const int g = __ldg(ids + range.x + lo + tid);
-            const float2 m = __ldg(reinterpret_cast<const float2*>(xy + int64_t(g) * st.xs));
-            const float* cq = conic + int64_t(g) * st.cs;
-            const float A = __ldg(cq), B = __ldg(cq + 1), Cc = __ldg(cq + 2);
-            const float o = __ldg(opacity + int64_t(g) * st.os);
-            float col[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * st.ks + c);
-            s_rec[tid * 3 + 0] = make_float4(m.x, m.y, (-0.5f * LOG2E) * A, -LOG2E * B);
-            s_rec[tid * 3 + 1] = make_float4((-0.5f * LOG2E) * Cc, o, col[0], col[1]);
-            s_rec[tid * 3 + 2] = make_float4(col[2], col[3], __int_as_float(g), 0.f);
-            s_mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
-        }
-        __syncthreads();
-        if (wmax <= lo) continue;  // this warp has no contributor in the batch
-        const unsigned short* my_list = s_list[warp] + LIST_PAD;   // my_list[-LIST_PAD..-1] are DUMMY
-        const int nl = build_list(s_mask, s_list[warp], min(cnt, wmax - lo), warp, lane);
-        for (int ii = nl - 1; ii >= 0; ii -= RB) {
-            float part[NT][RB];
-            unsigned present = 0;  // bit u set when any lane of the warp has a valid sample of list entry ii-u
-#pragma unroll
-            for (int u = 0; u < RB; ++u) {
-                const int j = my_list[ii - u];
-                const float4 r0 = s_rec[j * 3 + 0];
-                const float4 r1 = s_rec[j * 3 + 1];
-                const float dx = r0.x - pxf, dy = r0.y - pyf;
-                // same arithmetic as the forward: power * log2(e) = a' dx^2 + b' dx dy + c' dy^2
-                const float p2 = fmaf(r1.x * dy, dy, fmaf(r0.w, dy, r0.z * dx) * dx);
-                const float G = ex2_approx(p2);
-                const float a = fminf(amax, r1.y * G);
-                const bool valid = ((lo + j) < last) && !(p2 > 0.0f) && (a >= ALPHA_MIN);
-                present |= (__ballot_sync(FULL, valid) != 0u) ? (1u << u) : 0u;
-                float vs = 0.f, fac = 0.f, go = 0.f;
-                if (valid) {
-                    const float ra = 1.0f / (1.0f - a);
-                    T *= ra;
-                    fac = a * T;
-                    float S = r1.z * vo[0];
-                    if (CH > 1) S = fmaf(r1.w, vo[1], S);
-                    if (CH > 2) {
-                        const float2 r2 = *reinterpret_cast<const float2*>(&s_rec[j * 3 + 2]);
-                        S = fmaf(r2.x, vo[2], S);
-                        if (CH > 3) S = fmaf(r2.y, vo[3], S);
-                    }
-                    // dL/dalpha = T <c, v> - (<colour behind, v> + T_final (bg.v - v_alpha)) / (1 - alpha);  D = <colour behind, v>
-                    const float v_al = fmaf(T, S, ra * (tail - D));
-                    D = fmaf(fac, S, D);
-                    if (!GSPLAT || (r1.y * G <= 0.999f)) {
-                        go = G * v_al;
-                        vs = -r1.y * go;
-                    }
-                }
-                const float t1 = vs * dx, t2 = vs * dy;
-                part[0][u] = go;
-                part[1][u] = t1;
-                part[2][u] = t2;
-                part[3][u] = t1 * dx;
-                part[4][u] = t1 * dy;
-                part[5][u] = t2 * dy;
-#pragma unroll
-                for (int c = 0; c < CH; ++c) part[6 + c][u] = fac * vo[c];
-                if (ABS) {
-                    part[6 + CH][u] = fabsf(r0.z * t1 + 0.5f * r0.w * t2) * (2.0f / LOG2E);
-                    part[(7 + CH) % NT][u] = fabsf(0.5f * r0.w * t1 + r1.x * t2) * (2.0f / LOG2E);
-                }
-            }
-            if (present == 0u) continue;
-            if (VS) {
-                const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
-                float sv[NT];      // entry split: this lane's entry (slot my_slot), summed over the lanes that differ in bits 16 and 8
-#pragma unroll
-                for (int k = 0; k < NT; ++k)
-                    sv[k] = rs_step(rs_step(part[k][0], part[k][2], b16, 16), rs_step(part[k][1], part[k][3], b16, 16), b8, 8);
-                // value split over the 8 lanes of the group.  sv: 0 go, 1 t1, 2 t2, 3..5 conic moments, 6..8 colours
-                const float r0 = rs_step(sv[1], sv[5], b4, 4), r1 = rs_step(sv[2], sv[6], b4, 4);
-                const float r3 = rs_step(sv[3], sv[7], b4, 4), r4 = rs_step(sv[4], sv[8], b4, 4);
-                const float r2 = sv[0] + __shfl_xor_sync(FULL, sv[0], 4);
-                const float u0 = rs_step(r0, r3, b2, 2), u1 = rs_step(r1, r4, b2, 2);
-                const float u2 = r2 + __shfl_xor_sync(FULL, r2, 2);
-                const float w = rs_step(u0, u1, b1, 1);                     // lane&7: 0 t1, 2 m3, 3 m4, 4 m5, 5 c0, 6 c1, 7 c2
-                const float t2tot = u1 + __shfl_xor_sync(FULL, u1, 1);      // valid on lanes 0/1 of the group
-                const float gotot = u2 + __shfl_xor_sync(FULL, u2, 1);      // valid on lanes 0/1 of the group
-                if ((present >> my_slot) & 1u) {
-                    const int j = my_list[ii - my_slot];
-                    const int g = __float_as_int(s_rec[j * 3 + 2].z);
-                    const unsigned l8 = lane & 7u;
-                    float outv = vs_scale * (l8 == 1u ? gotot : w);
-                    float outy = 0.f;
-                    if (l8 == 0u) {
-                        const float4 r0c = s_rec[j * 3 + 0];
-                        const float A = r0c.z * (-2.0f / LOG2E), B = r0c.w * (-1.0f / LOG2E), Cc = s_rec[j * 3 + 1].x * (-2.0f / LOG2E);
-                        outv = (A * w + B * t2tot) * sx;
-                        outy = (B * w + Cc * t2tot) * sy;
-                    }
-                    float* dst = vs_base + int64_t(g) * vs_stride;
-                    atomicAdd(dst, outv);
-                    if (l8 == 0u) atomicAdd(dst + 1, outy);
-                }
-                continue;
-            }
-            float tot[NT];
-#pragma unroll
-            for (int k = 0; k < NT; ++k) tot[k] = reduce_scatter<RB>(part[k], lane);
-            if (writer && ((present >> my_slot) & 1u)) {
-                const int j = my_list[ii - my_slot];
-                const float4 r0 = s_rec[j * 3 + 0];
-                const float A = r0.z * (-2.0f / LOG2E), B = r0.w * (-1.0f / LOG2E), Cc = s_rec[j * 3 + 1].x * (-2.0f / LOG2E);
-                const int g = __float_as_int(s_rec[j * 3 + 2].z);
-                float* vx = v_xy + int64_t(g) * st.xs;
-                float* vc = v_conic + int64_t(g) * st.cs;
-                atomicAdd(vx, (A * tot[1] + B * tot[2]) * sx);
-                atomicAdd(vx + 1, (B * tot[1] + Cc * tot[2]) * sy);
-                atomicAdd(vc, 0.5f * tot[3]);
-                atomicAdd(vc + 1, tot[4]);
-                atomicAdd(vc + 2, 0.5f * tot[5]);
-                atomicAdd(v_opacity + int64_t(g) * st.os, tot[0]);
-#pragma unroll
-                for (int c = 0; c < CH; ++c) atomicAdd(v_colors + int64_t(g) * st.ks + c, tot[6 + c]);
-                if (ABS) {
-                    atomicAdd(v_xy_abs + 2 * g, tot[6 + CH]);
-                    atomicAdd(v_xy_abs + 2 * g + 1, tot[(7 + CH) % NT]);
-                }
-            }
-        }
-    }
-}
-
-// ---- backward, transpose-reduce variant (default) -----------------------------------------------------------------------
-// The butterfly above spends 63 of its 119 warp instructions per (warp, list entry) on moving nine partial sums between
-// lanes (SHFL issues at one warp instruction per clock per SM) and on a single writer lane.  Here each pixel lane only
+// ---- backward: transpose-reduce --------------------------------------------------------------------------------------------
+// Round 1's kernel reduced nine partial sums per (warp, list entry) with a shuffle butterfly and a single writer lane: 63 of
+// its 119 warp instructions per entry (SHFL issues at one warp instruction per clock per SM); measured 0.69 ms at 1 M / 1080p
+// against 0.53 ms for this kernel with scalar atomics (profiles/round2_*).  Here each pixel lane only
 // produces TWO numbers per entry —  go = dL/d(opacity-weighted Gaussian)  and  fac = alpha*T  — and stores them as one
 // float2 into a per-warp shared-memory tile [GE entries][32 lanes].  After GE = 16 entries the roles flip: lane (e, h)
 // owns entry e and the 16 pixels of half h of the warp's 8x4 block, reads its row with 128-bit loads (rows are padded by
@@ -651,9 +398,12 @@ struct TrSmem {
 };
 static_assert(sizeof(TrSmem<false>) <= 57344, "4 CTAs per SM need <= 56 KB each");
 
-template <int CH, bool GSPLAT, bool ABS>
+// VROWS: the gradient outputs are the columns of one [n,12] row buffer (include/b200gs.h row layout; v_xy = its base): the nine
+// sums of an entry leave as THREE 128-bit reductions (REDG.E.ADD.F32x4: {xy, -, conic0} {conic1, conic2, -, opacity} {rgb, -})
+// instead of nine 32-bit ones — a third of the L2 atomic operations, which bound this kernel once the shuffles were gone.
+template <int CH, bool GSPLAT, bool ABS, bool VROWS>
 __global__ void __launch_bounds__(BLOCK_PIX, ABS ? 3 : 4) blend_bwd_tr_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
-                                                                    const int32_t* __restrict__ ids, const SplatStrides st,
+                                                                    const int32_t* __restrict__ ids, const SplatStrides st, const SplatStrides so,
                                                                     const float* __restrict__ xy, const float* __restrict__ conic,
                                                                     const float* __restrict__ opacity, const float* __restrict__ colors,
                                                                     const float* __restrict__ bg, const float* __restrict__ final_T,
@@ -838,17 +588,28 @@ __global__ void __launch_bounds__(BLOCK_PIX, ABS ? 3 : 4) blend_bwd_tr_kernel(in
                         const float M3 = no * fmaf(ex, fmaf(ex, S0, -2.0f * Sx), Sxx);
                         const float M4 = no * (fmaf(ex, fmaf(ey, S0, -Sy), Sxy) - ey * Sx);
                         const float M5 = no * fmaf(ey, fmaf(ey, S0, -2.0f * Sy), Syy);
-                        float* vx = v_xy + int64_t(g) * st.xs;
-                        float* vc = v_conic + int64_t(g) * st.cs;
-                        atomicAdd(vx, (A * M1 + B * M2) * sx);
-                        atomicAdd(vx + 1, (B * M1 + Cc * M2) * sy);
-                        atomicAdd(vc, 0.5f * M3);
-                        atomicAdd(vc + 1, M4);
-                        atomicAdd(vc + 2, 0.5f * M5);
+                        const float gx = (A * M1 + B * M2) * sx, gy = (B * M1 + Cc * M2) * sy;
+                        if (VROWS) {
+                            float4* row = reinterpret_cast<float4*>(v_xy + int64_t(g) * B200GS_ROW_FLOATS);
+                            atomicAdd(row, make_float4(gx, gy, 0.f, 0.5f * M3));
+                            atomicAdd(row + 1, make_float4(M4, 0.5f * M5, 0.f, S0));
+                        } else {
+                            float* vx = v_xy + int64_t(g) * so.xs;
+                            float* vc = v_conic + int64_t(g) * so.cs;
+                            atomicAdd(vx, gx);
+                            atomicAdd(vx + 1, gy);
+                            atomicAdd(vc, 0.5f * M3);
+                            atomicAdd(vc + 1, M4);
+                            atomicAdd(vc + 2, 0.5f * M5);
+                        }
                     } else {
-                        atomicAdd(v_opacity + int64_t(g) * st.os, S0);
+                        if (VROWS) {
+                            atomicAdd(reinterpret_cast<float4*>(v_xy + int64_t(g) * B200GS_ROW_FLOATS) + 2, make_float4(Cs[0], Cs[1], Cs[2], 0.f));
+                        } else {
+                            atomicAdd(v_opacity + int64_t(g) * so.os, S0);
 #pragma unroll
-                        for (int c = 0; c < CH; ++c) atomicAdd(v_colors + int64_t(g) * st.ks + c, Cs[c]);
+                            for (int c = 0; c < CH; ++c) atomicAdd(v_colors + int64_t(g) * so.ks + c, Cs[c]);
+                        }
                         if (ABS) {
                             atomicAdd(v_xy_abs + 2 * int64_t(g), Ax);
                             atomicAdd(v_xy_abs + 2 * int64_t(g) + 1, Ay);
@@ -861,242 +622,6 @@ __global__ void __launch_bounds__(BLOCK_PIX, ABS ? 3 : 4) blend_bwd_tr_kernel(in
     }
 }
 
-// ---- backward, tensor-core reduction variant -------------------------------------------------------------------------
-// The cross-lane reduction of the backward IS a small dense contraction: for the 8 list entries of a group, every
-// output is  sum_over_the_32_pixel_lanes( weight[row][lane] * value[lane][entry] )  with weights that are FIXED for the warp:
-//   rows 0..5  : 1, cx, cy, cx^2, cx*cy, cy^2   (pixel coordinates relative to the centre of the warp's 8x4 block)   x  g = dL/d(opacity)
-//   rows 8..8+CH-1 : v_image[channel] of the lane's pixel                                                             x  f = alpha*T
-// (the mean/conic gradients are linear in the six pixel-coordinate moments of g, see the writer below).  That is a
-// [16 x 64] x [64 x 8] GEMM per group: mma.sync.m16n8k8 TF32 with the 3xTF32 split (hi*hi + hi*lo + lo*hi; the coordinate
-// weights are exact in TF32) -> fp32-level accuracy, ~23 issue slots per splat for reduction + writer instead of ~58 with
-// the shuffle butterfly.  Values go lane -> fragment through a 2 KB per-warp shared-memory tile (XOR-swizzled: both the
-// stores and the fragment loads are bank-conflict free).
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-
-__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-template <int CH, bool GSPLAT>
-__global__ void __launch_bounds__(BLOCK_PIX, 3) blend_bwd_mma_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
-                                                                     const int32_t* __restrict__ ids, const SplatStrides st,
-                                                                     const float* __restrict__ xy, const float* __restrict__ conic,
-                                                                     const float* __restrict__ opacity, const float* __restrict__ colors,
-                                                                     const float* __restrict__ bg, const float* __restrict__ final_T,
-                                                                     const int32_t* __restrict__ n_contrib, const float* __restrict__ v_image,
-                                                                     int64_t pix_stride, int64_t ch_stride, const float* __restrict__ v_alpha,
-                                                                     float sx, float sy, float* __restrict__ v_xy, float* __restrict__ v_conic,
-                                                                     float* __restrict__ v_opacity, float* __restrict__ v_colors) {
-    constexpr int GB = 8;  // list entries per group = N of the MMA tile
-    __shared__ float4 s_rec[(BLOCK_PIX + 1) * 3];
-    __shared__ unsigned char s_mask[BLOCK_PIX];
-    __shared__ unsigned short s_list[NWARP][BLOCK_PIX + 2 * LIST_PAD];
-    __shared__ float s_b[NWARP][2][GB][32];
-    __shared__ int s_wmax[NWARP];
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const unsigned lane = tid & 31u;
-    const int gid = lane >> 2, tig = lane & 3;
-    const int tile = blockIdx.y * grid_x + blockIdx.x;
-    int lx, ly;
-    pixel_of_thread(tid, lx, ly);
-    const int px = blockIdx.x * TILE + lx, py = blockIdx.y * TILE + ly;
-    const bool inside = (px < width) && (py < height);
-    const float off = GSPLAT ? 0.5f : 0.0f;
-    const float pxf = float(px) + off, pyf = float(py) + off;
-    const float ox = float(blockIdx.x * TILE) + off, oy = float(blockIdx.y * TILE) + off;
-    // centre of this warp's 8x4 block of pixel samples
-    const float bcx = ox + float((warp & 1) << 3) + 3.5f, bcy = oy + float((warp >> 1) << 2) + 1.5f;
-    const float amax = GSPLAT ? 0.999f : 0.99f;
-    const int64_t pix = int64_t(py) * width + px;
-    if (tid < 3) s_rec[DUMMY * 3 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    const int2 range = ranges[tile];
-    const float Tf = inside ? final_T[pix] : 0.f;
-    const int last = inside ? n_contrib[pix] : 0;
-    float vo[4] = {0.f, 0.f, 0.f, 0.f};
-    float bg_dot = 0.f;
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        vo[c] = inside ? __ldg(v_image + pix * pix_stride + c * ch_stride) : 0.f;
-        if (bg) bg_dot += __ldg(bg + c) * vo[c];
-    }
-    const float va = (v_alpha && inside) ? __ldg(v_alpha + pix) : 0.f;
-    const float tail = Tf * (va - bg_dot);
-
-    // fixed A fragments.  G part (k-steps 0..3): rows 0..5 in a0/a2;  F part (k-steps 4..7): rows 8..8+CH-1 in a1/a3 (hi + lo)
-    uint32_t aG0[4], aG2[4], aF1h[4], aF1l[4], aF3h[4], aF3l[4];
-#pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int k = 8 * s4 + tig + 4 * h;                 // pixel lane this fragment element multiplies
-            const float cx = float(k & 7) - 3.5f, cy = float(k >> 3) - 1.5f;
-            float w = 0.f;
-            if (gid == 0) w = 1.0f;
-            else if (gid == 1) w = cx;
-            else if (gid == 2) w = cy;
-            else if (gid == 3) w = cx * cx;
-            else if (gid == 4) w = cx * cy;
-            else if (gid == 5) w = cy * cy;
-            float v = 0.f;
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const float t = __shfl_sync(FULL, vo[c], k);
-                if (gid == c) v = t;
-            }
-            const uint32_t vh = to_tf32(v);
-            const uint32_t vl = to_tf32(v - __uint_as_float(vh));
-            if (h == 0) { aG0[s4] = to_tf32(w); aF1h[s4] = vh; aF1l[s4] = vl; }
-            else { aG2[s4] = to_tf32(w); aF3h[s4] = vh; aF3l[s4] = vl; }
-        }
-    }
-
-    const int wmax = __reduce_max_sync(FULL, last);
-    if (lane == 0) s_wmax[warp] = wmax;
-    __syncthreads();
-    int max_last = 0;
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) max_last = max(max_last, s_wmax[w]);
-    if (max_last == 0) return;
-
-    float T = Tf;
-    float D = 0.f;
-    float* sbG = &s_b[warp][0][0][0];
-    float* sbF = &s_b[warp][1][0][0];
-
-    for (int hi = max_last; hi > 0; hi -= BLOCK_PIX) {
-        const int lo = max(0, hi - BLOCK_PIX);
-        const int cnt = hi - lo;
-        __syncthreads();
-        if (tid < cnt) {
-            const int g = __ldg(ids + range.x + lo + tid);
-            const float2 m = __ldg(reinterpret_cast<const float2*>(xy + int64_t(g) * st.xs));
-            const float* cq = conic + int64_t(g) * st.cs;
-            const float A = __ldg(cq), B = __ldg(cq + 1), Cc = __ldg(cq + 2);
-            const float o = __ldg(opacity + int64_t(g) * st.os);
-            float col[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c = 0; c < CH; ++c) col[c] = __ldg(colors + int64_t(g) * st.ks + c);
-            s_rec[tid * 3 + 0] = make_float4(m.x, m.y, (-0.5f * LOG2E) * A, -LOG2E * B);
-            s_rec[tid * 3 + 1] = make_float4((-0.5f * LOG2E) * Cc, o, col[0], col[1]);
-            s_rec[tid * 3 + 2] = make_float4(col[2], col[3], __int_as_float(g), 0.f);
-            s_mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
-        }
-        __syncthreads();
-        if (wmax <= lo) continue;
-        const unsigned short* my_list = s_list[warp] + LIST_PAD;
-        const int nl = build_list(s_mask, s_list[warp], min(cnt, wmax - lo), warp, lane);
-        for (int ii = nl - 1; ii >= 0; ii -= GB) {
-            unsigned present = 0;
-#pragma unroll
-            for (int u = 0; u < GB; ++u) {
-                const int j = my_list[ii - u];
-                const float4 r0 = s_rec[j * 3 + 0];
-                const float4 r1 = s_rec[j * 3 + 1];
-                const float dx = r0.x - pxf, dy = r0.y - pyf;
-                const float p2 = fmaf(r1.x * dy, dy, fmaf(r0.w, dy, r0.z * dx) * dx);
-                const float G = ex2_approx(p2);
-                const float a = fminf(amax, r1.y * G);
-                const bool valid = ((lo + j) < last) && !(p2 > 0.0f) && (a >= ALPHA_MIN);
-                present |= (__ballot_sync(FULL, valid) != 0u) ? (1u << u) : 0u;
-                float fac = 0.f, go = 0.f;
-                if (valid) {
-                    const float ra = 1.0f / (1.0f - a);
-                    T *= ra;
-                    fac = a * T;
-                    float S = r1.z * vo[0];
-                    if (CH > 1) S = fmaf(r1.w, vo[1], S);
-                    if (CH > 2) {
-                        const float2 r2 = *reinterpret_cast<const float2*>(&s_rec[j * 3 + 2]);
-                        S = fmaf(r2.x, vo[2], S);
-                        if (CH > 3) S = fmaf(r2.y, vo[3], S);
-                    }
-                    const float v_al = fmaf(T, S, ra * (tail - D));
-                    D = fmaf(fac, S, D);
-                    if (!GSPLAT || (r1.y * G <= 0.999f)) go = G * v_al;
-                }
-                sbG[u * 32 + (lane ^ (4 * u))] = go;
-                sbF[u * 32 + (lane ^ (4 * u))] = fac;
-            }
-            if (present == 0u) continue;
-            __syncwarp();
-            float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f}, acc3[4] = {0.f, 0.f, 0.f, 0.f};   // independent MMA chains
-#pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4) {
-                const int k0 = (8 * s4 + tig) ^ (4 * gid), k1 = (8 * s4 + tig + 4) ^ (4 * gid);
-                {
-                    const float b0 = sbG[gid * 32 + k0], b1 = sbG[gid * 32 + k1];
-                    const uint32_t b0h = to_tf32(b0), b1h = to_tf32(b1);
-                    const uint32_t b0l = to_tf32(b0 - __uint_as_float(b0h)), b1l = to_tf32(b1 - __uint_as_float(b1h));
-                    mma_tf32(acc, aG0[s4], 0u, aG2[s4], 0u, b0h, b1h);
-                    mma_tf32(acc2, aG0[s4], 0u, aG2[s4], 0u, b0l, b1l);
-                }
-                {
-                    const float b0 = sbF[gid * 32 + k0], b1 = sbF[gid * 32 + k1];
-                    const uint32_t b0h = to_tf32(b0), b1h = to_tf32(b1);
-                    const uint32_t b0l = to_tf32(b0 - __uint_as_float(b0h)), b1l = to_tf32(b1 - __uint_as_float(b1h));
-                    mma_tf32(acc3, 0u, aF1h[s4], 0u, aF3h[s4], b0h, b1h);
-                    mma_tf32(acc2, 0u, aF1l[s4], 0u, aF3l[s4], b0h, b1h);
-                    mma_tf32(acc, 0u, aF1h[s4], 0u, aF3h[s4], b0l, b1l);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] += acc2[q] + acc3[q];
-            __syncwarp();
-            // acc[0], acc[1]: row gid (moment gid), entries 2*tig, 2*tig+1;  acc[2], acc[3]: row 8+gid (colour gid), same entries.
-            // Collect the six moments and the colour sums of entries 2*tig+e in the gid==0 lane of each tig.
-            float mom[2][6], csum[2][4];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-                mom[0][r] = __shfl_sync(FULL, acc[0], (r << 2) | tig);
-                mom[1][r] = __shfl_sync(FULL, acc[1], (r << 2) | tig);
-            }
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                csum[0][c] = __shfl_sync(FULL, acc[2], (c << 2) | tig);
-                csum[1][c] = __shfl_sync(FULL, acc[3], (c << 2) | tig);
-            }
-            if (gid == 0) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int n = 2 * tig + e;
-                    if (!((present >> n) & 1u)) continue;
-                    const int j = my_list[ii - n];
-                    const float4 r0 = s_rec[j * 3 + 0];
-                    const float4 r1 = s_rec[j * 3 + 1];
-                    const float A = r0.z * (-2.0f / LOG2E), B = r0.w * (-1.0f / LOG2E), Cc = r1.x * (-2.0f / LOG2E);
-                    const int g = __float_as_int(s_rec[j * 3 + 2].z);
-                    const float ex = r0.x - bcx, ey = r0.y - bcy;   // splat centre relative to the block centre; dx = ex - cx
-                    const float S0 = mom[e][0], Sx = mom[e][1], Sy = mom[e][2], Sxx = mom[e][3], Sxy = mom[e][4], Syy = mom[e][5];
-                    const float no = -r1.y;                          // v_sigma = -opacity * g
-                    const float M1 = no * (ex * S0 - Sx), M2 = no * (ey * S0 - Sy);
-                    const float M3 = no * (ex * ex * S0 - 2.0f * ex * Sx + Sxx);
-                    const float M4 = no * (ex * ey * S0 - ex * Sy - ey * Sx + Sxy);
-                    const float M5 = no * (ey * ey * S0 - 2.0f * ey * Sy + Syy);
-                    float* vx = v_xy + int64_t(g) * st.xs;
-                    float* vc = v_conic + int64_t(g) * st.cs;
-                    atomicAdd(vx, (A * M1 + B * M2) * sx);
-                    atomicAdd(vx + 1, (B * M1 + Cc * M2) * sy);
-                    atomicAdd(vc, 0.5f * M3);
-                    atomicAdd(vc + 1, M4);
-                    atomicAdd(vc + 2, 0.5f * M5);
-                    atomicAdd(v_opacity + int64_t(g) * st.os, S0);
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) atomicAdd(v_colors + int64_t(g) * st.ks + c, csum[e][c]);
-                }
-            }
-        }
-    }
-}
-
 template <int CH>
 int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy, const float* conic,
                  const float* opacity, const float* colors, const float* bg, float* image, int64_t ps, int64_t cs, float* final_T,
@@ -1104,8 +629,11 @@ int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
     const int gx = div_up(width, TILE), gy = div_up(height, TILE);
     dim3 grid(gx, gy);
     const SplatStrides st = row_stride > 0 ? SplatStrides{row_stride, row_stride, row_stride, row_stride} : SplatStrides{2, 3, 1, CH};
-    // default: asynchronous (cp.async, double-buffered) slab staging; B200GS_FWD_SYNC=1 selects the synchronous kernel for A/B runs
-    static const bool use_sync = []() { const char* e = getenv("B200GS_FWD_SYNC"); return e && e[0] == '1'; }();
+    // Two stagings of the tile slab.  Synchronous (default): ids -> gathered records -> registers -> shared memory, the latency covered by
+    // the other 2-3 CTAs of the SM.  Asynchronous (B200GS_FWD_ASYNC=1; always for the has_hit_any_pixels variant): cp.async double buffer.
+    // Measured at 1 M Gaussians / 1080p on B200 (profiles/round2_*): 0.281 ms synchronous vs 0.308 ms asynchronous — the eight 4/8-byte
+    // LDGSTS per splat of the separate-array layout cost more issue slots than the overlap returns.
+    static const bool use_sync = []() { const char* e = getenv("B200GS_FWD_ASYNC"); return !(e && e[0] == '1'); }();
     // the row layout is [x, y, depth, A, B, C, comp, opacity, r, g, b, radius] (include/b200gs.h); 16-byte copies need 16-byte aligned rows
     const bool rows16 = row_stride == 12 && CH == 3 && conic == xy + 3 && opacity == xy + 7 && colors == xy + 8 && (reinterpret_cast<uintptr_t>(xy) & 15) == 0;
     if (!use_sync || hit_any != nullptr) {
@@ -1139,89 +667,54 @@ int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
     return B200GS_OK;
 }
 
-#ifndef B200GS_BWD_RB
-#define B200GS_BWD_RB 4
-#endif
-
 template <int CH>
 int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy, const float* conic,
                  const float* opacity, const float* colors, const float* bg, const float* final_T, const int32_t* n_contrib,
-                 const float* v_image, int64_t ps, int64_t cs, const float* v_alpha, float sx, float sy, float* v_xy, float* v_conic,
-                 float* v_opacity, float* v_colors, float* v_xy_abs, cudaStream_t s) {
+                 const float* v_image, int64_t ps, int64_t cs, const float* v_alpha, float sx, float sy, int out_row_stride, float* v_xy,
+                 float* v_conic, float* v_opacity, float* v_colors, float* v_xy_abs, cudaStream_t s) {
     const int gx = div_up(width, TILE), gy = div_up(height, TILE);
     dim3 grid(gx, gy);
-    constexpr int RB = B200GS_BWD_RB;
     const SplatStrides st = row_stride > 0 ? SplatStrides{row_stride, row_stride, row_stride, row_stride} : SplatStrides{2, 3, 1, CH};
-#define B200GS_BWD_ARGS width, height, gx, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, final_T, n_contrib, \
+    const SplatStrides so = out_row_stride > 0 ? SplatStrides{out_row_stride, out_row_stride, out_row_stride, out_row_stride} : SplatStrides{2, 3, 1, CH};
+    // gradient outputs that are the columns of one 16-byte aligned [n,12] row buffer leave as 128-bit reductions
+    const bool vrows = CH == 3 && out_row_stride == B200GS_ROW_FLOATS && v_conic == v_xy + B200GS_ROW_CONIC && v_opacity == v_xy + B200GS_ROW_OPACITY &&
+                       v_colors == v_xy + B200GS_ROW_RGB && (reinterpret_cast<uintptr_t>(v_xy) & 15) == 0;
+#define B200GS_BWD_ARGS width, height, gx, (const int2*)ranges, ids, st, so, xy, conic, opacity, colors, bg, final_T, n_contrib, \
                         v_image, ps, cs, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs
-#define B200GS_BWD_MMA_ARGS width, height, gx, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, final_T, n_contrib, \
-                            v_image, ps, cs, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors
-    // opt-in (B200GS_BWD_MMA=1): measured 0.89 ms vs 0.69 ms for the shuffle butterfly at 1 M Gaussians / 1080p — the TF32 hi/lo
-    // splits, the lane->fragment staging and the writer algebra cost as many issue slots as the butterfly saves (677 M vs
-    // ~620 M warp instructions, ncu), so the shuffle kernel stays the default.
-    static const bool use_mma = []() { const char* e = getenv("B200GS_BWD_MMA"); return e && e[0] == '1'; }();
-    // opt-in (B200GS_BWD_VS=1): value-scatter reduction, see blend_bwd_kernel.  Written from the ncu instruction breakdown of
-    // the default kernel at the end of round 1; NOT yet run on hardware — the default path does not use it.
-    static const bool use_vs = []() { const char* e = getenv("B200GS_BWD_VS"); return e && e[0] == '1'; }();
-    if (CH == 3 && RB == 4 && use_vs && !v_xy_abs) {
-        if constexpr (CH == 3 && RB == 4) {
-            if (mode == B200GS_MODE_GSPLAT)
-                blend_bwd_kernel<CH, true, false, RB, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
-            else
-                blend_bwd_kernel<CH, false, false, RB, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
-            B200GS_LAUNCH_CHECK();
-            return B200GS_OK;
+    static const cudaError_t attr_rc = []() {
+        cudaError_t e = cudaSuccess;
+        auto set = [&e](const void* f, size_t bytes) {
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        };
+        set((const void*)blend_bwd_tr_kernel<CH, true, false, false>, sizeof(TrSmem<false>));
+        set((const void*)blend_bwd_tr_kernel<CH, false, false, false>, sizeof(TrSmem<false>));
+        set((const void*)blend_bwd_tr_kernel<CH, true, true, false>, sizeof(TrSmem<true>));
+        set((const void*)blend_bwd_tr_kernel<CH, false, true, false>, sizeof(TrSmem<true>));
+        if constexpr (CH == 3) {
+            set((const void*)blend_bwd_tr_kernel<CH, true, false, true>, sizeof(TrSmem<false>));
+            set((const void*)blend_bwd_tr_kernel<CH, false, false, true>, sizeof(TrSmem<false>));
+            set((const void*)blend_bwd_tr_kernel<CH, true, true, true>, sizeof(TrSmem<true>));
+            set((const void*)blend_bwd_tr_kernel<CH, false, true, true>, sizeof(TrSmem<true>));
         }
+        return e;
+    }();
+    if (attr_rc != cudaSuccess) {
+        set_error("blend_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_rc));
+        return B200GS_ECUDA;
     }
-    // default: transpose-reduce kernel; B200GS_BWD_BUTTERFLY=1 selects the shuffle butterfly for A/B runs
-    static const bool use_butterfly = []() { const char* e = getenv("B200GS_BWD_BUTTERFLY"); return e && e[0] == '1'; }();
-    if (!use_butterfly && !use_mma) {
-        static const cudaError_t attr_rc = []() {
-            cudaError_t e = cudaSuccess;
-            auto set = [&e](const void* f, size_t bytes) {
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            };
-            set((const void*)blend_bwd_tr_kernel<CH, true, false>, sizeof(TrSmem<false>));
-            set((const void*)blend_bwd_tr_kernel<CH, false, false>, sizeof(TrSmem<false>));
-            set((const void*)blend_bwd_tr_kernel<CH, true, true>, sizeof(TrSmem<true>));
-            set((const void*)blend_bwd_tr_kernel<CH, false, true>, sizeof(TrSmem<true>));
-            return e;
-        }();
-        if (attr_rc != cudaSuccess) {
-            set_error("blend_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_rc));
-            return B200GS_ECUDA;
+#define B200GS_BWD_LAUNCH(G, A, V) blend_bwd_tr_kernel<CH, G, A, V><<<grid, BLOCK_PIX, sizeof(TrSmem<A>), s>>>(B200GS_BWD_ARGS)
+    const bool gs = mode == B200GS_MODE_GSPLAT, ab = v_xy_abs != nullptr;
+    if (vrows) {
+        if constexpr (CH == 3) {
+            if (gs) { if (ab) B200GS_BWD_LAUNCH(true, true, true); else B200GS_BWD_LAUNCH(true, false, true); }
+            else    { if (ab) B200GS_BWD_LAUNCH(false, true, true); else B200GS_BWD_LAUNCH(false, false, true); }
         }
-        if (v_xy_abs) {
-            if (mode == B200GS_MODE_GSPLAT)
-                blend_bwd_tr_kernel<CH, true, true><<<grid, BLOCK_PIX, sizeof(TrSmem<true>), s>>>(B200GS_BWD_ARGS);
-            else
-                blend_bwd_tr_kernel<CH, false, true><<<grid, BLOCK_PIX, sizeof(TrSmem<true>), s>>>(B200GS_BWD_ARGS);
-        } else {
-            if (mode == B200GS_MODE_GSPLAT)
-                blend_bwd_tr_kernel<CH, true, false><<<grid, BLOCK_PIX, sizeof(TrSmem<false>), s>>>(B200GS_BWD_ARGS);
-            else
-                blend_bwd_tr_kernel<CH, false, false><<<grid, BLOCK_PIX, sizeof(TrSmem<false>), s>>>(B200GS_BWD_ARGS);
-        }
-        B200GS_LAUNCH_CHECK();
-        return B200GS_OK;
-    }
-    if (mode == B200GS_MODE_GSPLAT) {
-        if (v_xy_abs)
-            blend_bwd_kernel<CH, true, true, RB><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
-        else if (use_mma)
-            blend_bwd_mma_kernel<CH, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_MMA_ARGS);
-        else
-            blend_bwd_kernel<CH, true, false, RB><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
     } else {
-        if (v_xy_abs)
-            blend_bwd_kernel<CH, false, true, RB><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
-        else if (use_mma)
-            blend_bwd_mma_kernel<CH, false><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_MMA_ARGS);
-        else
-            blend_bwd_kernel<CH, false, false, RB><<<grid, BLOCK_PIX, 0, s>>>(B200GS_BWD_ARGS);
+        if (gs) { if (ab) B200GS_BWD_LAUNCH(true, true, false); else B200GS_BWD_LAUNCH(true, false, false); }
+        else    { if (ab) B200GS_BWD_LAUNCH(false, true, false); else B200GS_BWD_LAUNCH(false, false, false); }
     }
-#undef B200GS_BWD_MMA_ARGS
+#undef B200GS_BWD_LAUNCH
 #undef B200GS_BWD_ARGS
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
@@ -1247,13 +740,17 @@ int launch_blend_bwd(int mode, int width, int height, int channels, const int32_
                      const float* conic, const float* opacity, const float* colors, const float* bg, const float* final_T,
                      const int32_t* n_contrib, const float* v_image, int64_t pix_stride, int64_t ch_stride, const float* v_alpha,
                      float sx, float sy, float* v_xy, float* v_conic, float* v_opacity, float* v_colors, float* v_xy_abs,
-                     cudaStream_t s) {
+                     cudaStream_t s, int out_row_stride) {
+    if (out_row_stride < 0) out_row_stride = row_stride;
+#define B200GS_BWD_CALL(C) bwd_dispatch<C>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, \
+                                           pix_stride, ch_stride, v_alpha, sx, sy, out_row_stride, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s)
     switch (channels) {
-        case 1: return bwd_dispatch<1>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
-        case 2: return bwd_dispatch<2>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
-        case 3: return bwd_dispatch<3>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
-        case 4: return bwd_dispatch<4>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, pix_stride, ch_stride, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s);
+        case 1: return B200GS_BWD_CALL(1);
+        case 2: return B200GS_BWD_CALL(2);
+        case 3: return B200GS_BWD_CALL(3);
+        case 4: return B200GS_BWD_CALL(4);
     }
+#undef B200GS_BWD_CALL
     set_error("blend_bwd: unsupported channel count %d (1..4)", channels);
     return B200GS_EINVAL;
 }

@@ -134,6 +134,6 @@ int launch_blend_bwd(int mode, int width, int height, int channels, const int32_
                      int row_stride, const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
                      const float* final_T, const int32_t* n_contrib, const float* v_image, int64_t pix_stride,
                      int64_t ch_stride, const float* v_alpha, float sx, float sy, float* v_xy, float* v_conic,
-                     float* v_opacity, float* v_colors, float* v_xy_abs, cudaStream_t s);
+                     float* v_opacity, float* v_colors, float* v_xy_abs, cudaStream_t s, int out_row_stride = -1);
 
 }  // namespace b200gs

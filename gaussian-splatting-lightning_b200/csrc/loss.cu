@@ -1,6 +1,5 @@
-// K9/K10 (EXPERIMENTAL — written at the end of round 1 after the GPU budget was spent; compiles for sm_100a, has not run on
-// hardware yet; nothing on the default path calls it).  Fused L1 + SSIM training loss on the rendered image, the op that
-// follows the rasterizer every step:
+// K9/K10: fused L1 + SSIM training loss on the rendered image, the op that follows the rasterizer every step (SURVEY §8f row 2;
+// validated on B200 against the oracle and the reference-generated golden vectors: tests/test_gpu_loss.py):
 //     loss = (1 - lambda) * mean|img - gt| + lambda * (1 - mean(SSIM(img, gt)))          internal/metrics/vanilla_metrics.py:57-74
 //     SSIM: 11-tap Gaussian window (sigma 1.5), zero padding, C1 = 0.01^2, C2 = 0.03^2     internal/utils/ssim.py:23-63
 // The window is separable.  K9 (forward): one CTA per 16x16 tile and channel loads the tile + 5-pixel halo of both images

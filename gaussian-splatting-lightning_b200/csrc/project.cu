@@ -630,11 +630,12 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
     const bool ROWS = RAW && (raw.v_rows != nullptr);
     const bool ACC = RAW && (raw.accumulate != 0);
     // a negative row index = the entry did not fit its fixed-size block (the caller redoes such a step): treated as culled
-    const bool vis = in_range && (radii[i] > 0) && !(ROWS && raw.row_offsets[i] < 0);
+    const int64_t ri = (ROWS && in_range) ? (raw.row_offsets ? int64_t(raw.row_offsets[i]) : i) : 0;   // NULL offsets: row i
+    const bool vis = in_range && (radii[i] > 0) && !(ROWS && ri < 0);
     const int stride3 = v.sh_stride * 3;
     float p[3] = {0.f, 0.f, 0.f};
     if (vis) { p[0] = __ldg(means + 3 * i); p[1] = __ldg(means + 3 * i + 1); p[2] = __ldg(means + 3 * i + 2); }
-    const float* vrow = (ROWS && vis) ? raw.v_rows + int64_t(raw.row_offsets[i]) * B200GS_ROW_FLOATS : nullptr;
+    const float* vrow = (ROWS && vis) ? raw.v_rows + ri * B200GS_ROW_FLOATS : nullptr;
 
     float dm[3] = {0.f, 0.f, 0.f};  // dL/dmean (world)
 

@@ -19,6 +19,8 @@ import torch
 from . import _lib
 from ._lib import MODE_GSPLAT, MODE_VANILLA, TILE, B200gsView, check, lib, ptr
 
+ROW_FLOATS = 12   # include/b200gs.h B200GS_ROW_FLOATS
+
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
@@ -521,12 +523,26 @@ class _RasterizeVanillaRaw(torch.autograd.Function):
         view = ctx.view
         W, H = view.width, view.height
         v_image = _f32c(v_image, "grad_image")
-        v_xy, v_conic, v_opacity, v_colors, _ = blend_backward(MODE_VANILLA, W, H, ctx.binning, xy, conic, opac, rgb, bg, final_T,
-                                                              n_contrib, v_image, None, True, (0.5 * W, 0.5 * H))
-        v_means, v_ls, v_q, v_ol, v_dc, v_rest = project_backward_raw(view, means3D, log_scales, raw_quats, ol, shs_dc, shs_rest,
-                                                                     False, radii, clamped, v_xy, None, v_conic, v_colors, v_opacity)
-        v_means2D = torch.zeros(ctx.means2D_shape, dtype=torch.float32, device=means3D.device)
-        v_means2D[:, :2] = v_xy
+        # K7 accumulates into one zero-filled [N,12] gradient row buffer (128-bit reductions), K8 reads the rows in place
+        n = means3D.shape[0]
+        dev = means3D.device
+        v_rows = torch.zeros(n, ROW_FLOATS, dtype=torch.float32, device=dev)
+        L = lib()
+        with _stage("blend_bwd"):
+            check(L.b200gs_blend_bwd_to_rows(MODE_VANILLA, W, H, ptr(ctx.binning.tile_ranges), ptr(ctx.binning.sorted_ids), ptr(xy), ptr(conic),
+                                             ptr(opac), ptr(rgb), ptr(bg), ptr(final_T), ptr(n_contrib), ptr(v_image), 1, H * W, None,
+                                             0.5 * W, 0.5 * H, ptr(v_rows), None, _stream()), "b200gs_blend_bwd_to_rows")
+        v_means = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        v_ls = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        v_q = torch.empty(n, 4, dtype=torch.float32, device=dev)
+        v_ol = torch.empty(n, dtype=torch.float32, device=dev)
+        v_dc, v_rest = torch.empty_like(shs_dc), torch.empty_like(shs_rest)
+        with _stage("project_bwd"):
+            check(L.b200gs_project_bwd_rows(ctypes.byref(view), n, ptr(means3D), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc), ptr(shs_rest),
+                                            0, ptr(radii), ptr(clamped), None, ptr(v_rows), 0, ptr(v_means), ptr(v_ls), ptr(v_q), ptr(v_ol),
+                                            ptr(v_dc), ptr(v_rest), _stream()), "b200gs_project_bwd_rows")
+        v_means2D = torch.zeros(ctx.means2D_shape, dtype=torch.float32, device=dev)
+        v_means2D[:, :2] = v_rows[:, 0:2]
         return v_means, v_means2D, v_dc, v_rest, v_ol.reshape(ctx.opac_shape), v_ls, v_q, None, None
 
 
@@ -755,7 +771,7 @@ def rasterize_binned(means2d, conics, colors, opacities, binning: Binning, img_h
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# fused L1 + SSIM loss (EXPERIMENTAL: csrc/loss.cu compiles but has not been validated on hardware; not used by the renderers)
+# fused L1 + SSIM loss (csrc/loss.cu; the metric the reference computes right after the renderer, vanilla_metrics.py:57-80)
 # ----------------------------------------------------------------------------------------------------------------------
 class _L1SSIMLoss(torch.autograd.Function):
     @staticmethod

@@ -217,7 +217,16 @@ B200GS_API int b200gs_blend_bwd(int32_t mode, int32_t width, int32_t height, int
                      float xy_scale_x, float xy_scale_y, float* v_xy, float* v_conic, float* v_opacity,
                      float* v_colors, float* v_xy_abs, void* stream);
 
-/* ---- fused L1 + SSIM training loss on the rendered image (EXPERIMENTAL: compiles, not yet validated on hardware) ------------
+/* b200gs_blend_bwd_to_rows: K7 on separate input arrays (3 colour channels) accumulating into ONE zero-filled, 16-byte aligned
+ *     gradient row buffer v_rows[n,12] (row layout below: xy 0..1, conic 3..5, opacity 7, rgb 8..10; the other columns stay 0): the
+ *     nine sums of a (warp, splat) leave the SM as three 128-bit reductions instead of nine 32-bit atomics.  K8 consumes the rows
+ *     directly (b200gs_project_bwd_rows with row_offsets = NULL: row i belongs to Gaussian i). */
+B200GS_API int b200gs_blend_bwd_to_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
+                     const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
+                     const float* final_T, const int32_t* n_contrib, const float* v_image, int64_t pix_stride, int64_t ch_stride,
+                     const float* v_alpha, float xy_scale_x, float xy_scale_y, float* v_rows, float* v_xy_abs, void* stream);
+
+/* ---- fused L1 + SSIM training loss on the rendered image (validated on B200: tests/test_gpu_loss.py) -------------------------
  * replaces  loss = (1-lambda) * l1_loss(image, gt) + lambda * (1 - ssim(image, gt))   (internal/metrics/vanilla_metrics.py:57-74,
  * internal/utils/ssim.py:17-63: 11-tap Gaussian window sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2).  image/target [C,H,W].
  * b200gs_loss_fwd: partials[b200gs_loss_blocks(...)][2] <- per-CTA sums of |image-target| and of the SSIM map (the caller sums them
@@ -254,7 +263,7 @@ B200GS_API int b200gs_loss_bwd(int32_t channels, int32_t width, int32_t height, 
 #define B200GS_ROW_RGB 8
 #define B200GS_ROW_RADIUS 11
 /* b200gs_project_bwd_rows: K8 (fused activations) taking its cotangents straight from compacted [V,12] gradient rows
- *     (v_rows[row_offsets[i]] for visible i) and, when accumulate != 0, ADDING to the gradient buffers — the sharded
+ *     (v_rows[row_offsets[i]] for visible i; row_offsets = NULL: v_rows[i]) and, when accumulate != 0, ADDING to the gradient buffers — the sharded
  *     renderer calls it once per camera of the step without unpack copies or separate sum kernels. */
 B200GS_API int b200gs_project_bwd_rows(const B200gsView* view, int64_t n, const float* means, const float* log_scales,
                                        const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
