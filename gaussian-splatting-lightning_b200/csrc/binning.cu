@@ -285,10 +285,12 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
     const bool vis = area > 0;
     int block_vis;
     const int local = sweep::block_exclusive(vis ? 1 : 0, s_scan, &block_vis);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {     // warp 0: warp-wide look-back over the preceding blocks
         const uint32_t excl = sweep::chained_exclusive(scan_state, t, (uint32_t)block_vis);
-        s_excl = excl;
-        if (t == (int)gridDim.x - 1) counts[3] = (unsigned long long)(excl + (uint32_t)block_vis);
+        if (threadIdx.x == 0) {
+            s_excl = excl;
+            if (t == (int)gridDim.x - 1) counts[3] = (unsigned long long)(excl + (uint32_t)block_vis);
+        }
     }
     __syncthreads();
     if (vis) {
@@ -370,7 +372,10 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restri
     // first slot of this rank: cells of the ranks before it (this block: scan; the blocks before: chained scan)
     int block_cells;
     const int local_start = sweep::block_exclusive(t, s_scan, &block_cells);
-    if (tid == 0) s_lo = (int64_t)sweep::chained_exclusive(scan_state, s_tile, (uint32_t)block_cells);
+    if (tid < 32) {             // warp 0: warp-wide look-back over the preceding blocks
+        const uint32_t before = sweep::chained_exclusive(scan_state, s_tile, (uint32_t)block_cells);
+        if (tid == 0) s_lo = (int64_t)before;
+    }
     // exclusive scan of the row counts
     int inc = nrows;
 #pragma unroll
@@ -942,7 +947,10 @@ __global__ void __launch_bounds__(256) visible_scan_kernel(int64_t n, const int3
     const int v = (i < n && radii[i] > 0) ? 1 : 0;
     int block_total;
     const int local = sweep::block_exclusive(v, s_scan, &block_total);
-    if (threadIdx.x == 0) s_excl = sweep::chained_exclusive(state, t, (uint32_t)block_total);
+    if (threadIdx.x < 32) {
+        const uint32_t excl = sweep::chained_exclusive(state, t, (uint32_t)block_total);
+        if (threadIdx.x == 0) s_excl = excl;
+    }
     __syncthreads();
     if (i < n) scan[i] = (int32_t)(s_excl + (uint32_t)local);
 }

@@ -41,16 +41,26 @@ __device__ __forceinline__ uint32_t key_of(const uint4& r) { return r.w; }
 
 // ---- chained scan --------------------------------------------------------------------------------------------------
 // Exclusive prefix of one 30-bit value per tile over the tiles in ticket order.  `state[t]` must be zero before the launch.
-// Called by one thread; returns the sum of the values of tiles 0..t-1.
+// Called by ALL 32 lanes of ONE warp (same arguments); returns (to every lane) the sum of the values of tiles 0..t-1.
+// The look-back is warp-wide: 32 predecessors per step (lane l polls tile p - l), the walk stops at the nearest tile that
+// has already published its inclusive prefix — in the first wave, when every resident tile starts at once and none has a
+// prefix yet, tile t needs t/32 round trips to L2 instead of t.
 __device__ __forceinline__ uint32_t chained_exclusive(uint32_t* state, int t, uint32_t value) {
-    st_volatile(state + t, (value & VALUE_MASK) | (t == 0 ? FLAG_PREFIX : FLAG_AGG));
+    const unsigned lane = threadIdx.x & 31u;
+    if (lane == 0) st_volatile(state + t, (value & VALUE_MASK) | (t == 0 ? FLAG_PREFIX : FLAG_AGG));
     uint32_t excl = 0;
-    for (int p = t - 1; p >= 0; --p) {
-        const uint32_t v = wait_published(state + p);
-        excl += v & VALUE_MASK;
-        if (v & FLAG_PREFIX) break;
+    for (int p = t - 1; p >= 0; p -= 32) {
+        const int idx = p - (int)lane;
+        const uint32_t v = idx >= 0 ? wait_published(state + idx) : FLAG_PREFIX;
+        const unsigned has_prefix = __ballot_sync(0xffffffffu, (v & FLAG_PREFIX) != 0u);
+        const int first = has_prefix ? __ffs(has_prefix) - 1 : 31;          // nearest tile with an inclusive prefix: stop there
+        uint32_t c = ((int)lane <= first) ? (v & VALUE_MASK) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        excl += c;
+        if (has_prefix) break;
     }
-    if (t > 0) st_volatile(state + t, ((excl + value) & VALUE_MASK) | FLAG_PREFIX);
+    if (lane == 0 && t > 0) st_volatile(state + t, ((excl + value) & VALUE_MASK) | FLAG_PREFIX);
     return excl;
 }
 
@@ -156,10 +166,32 @@ __global__ void __launch_bounds__(THREADS) onesweep_pass_kernel(const Rec* __res
     {
         uint32_t* col = lookback + tid;                                    // lookback[p * RADIX + d]
         st_volatile(col + int64_t(t) * RADIX, (run & VALUE_MASK) | (t == 0 ? FLAG_PREFIX : FLAG_AGG));
-        for (int p = t - 1; p >= 0; --p) {
-            const uint32_t v = wait_published(col + int64_t(p) * RADIX);
-            before_tiles += v & VALUE_MASK;
-            if (v & FLAG_PREFIX) break;
+        // eight independent loads in flight per step (the words of tiles p, p-1, .., p-7 of this digit's column); a word that
+        // is not published yet ends the batch, the walk resumes there
+        for (int p = t - 1; p >= 0;) {
+            uint32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (p - k >= 0) ? ld_volatile(col + int64_t(p - k) * RADIX) : FLAG_PREFIX;
+            int used = 0;
+            bool done = false;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (!done && used == k) {
+                    if ((v[k] >> 30) != 0u) {
+                        before_tiles += v[k] & VALUE_MASK;
+                        used = k + 1;
+                        done = (v[k] & FLAG_PREFIX) != 0u;
+                    }
+                }
+            }
+            if (done) break;
+            p -= used;
+            if (used == 0 && p >= 0) {     // the nearest word is not out yet: wait for it, then go on from the next one
+                const uint32_t w0 = wait_published(col + int64_t(p) * RADIX);
+                before_tiles += w0 & VALUE_MASK;
+                if (w0 & FLAG_PREFIX) break;
+                --p;
+            }
         }
         if (t > 0) st_volatile(col + int64_t(t) * RADIX, ((before_tiles + run) & VALUE_MASK) | FLAG_PREFIX);
     }

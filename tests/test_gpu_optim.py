@@ -1,0 +1,64 @@
+"""Visibility-masked Adam and densification statistics (csrc/optim.cu) against plain torch restatements of the reference-side formulas
+(gsplat SelectiveAdam's update rule; vanilla_density_controller.py:101-123)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_selective_adam_updates_only_visible_rows():
+    from b200gs.optimizers import B200SelectiveAdam
+    g = torch.Generator().manual_seed(3)
+    n = 5000
+    shapes = {"means": (n, 3), "shs_rest": (n, 15, 3), "opacities": (n, 1), "rotations": (n, 4)}
+    params = {k: torch.nn.Parameter(torch.randn(*s, generator=g).to(DEV)) for k, s in shapes.items()}
+    lrs = {"means": 1.6e-4, "shs_rest": 1.25e-4, "opacities": 5e-2, "rotations": 1e-3}
+    opt = B200SelectiveAdam().instantiate([{"params": [p], "name": k, "lr": lrs[k]} for k, p in params.items()], lr=1e-3)
+    ref_p = {k: p.detach().clone().double() for k, p in params.items()}
+    ref_m = {k: torch.zeros_like(v) for k, v in ref_p.items()}
+    ref_v = {k: torch.zeros_like(v) for k, v in ref_p.items()}
+    b1, b2, eps = 0.9, 0.999, 1e-15
+    for step in range(4):
+        vis = torch.rand(n, generator=g) < 0.4
+        grads = {k: torch.randn(*s, generator=g) for k, s in shapes.items()}
+        for k, p in params.items():
+            p.grad = grads[k].to(DEV)
+        vp = torch.zeros(n, 2, device=DEV)
+        vp.has_hit_any_pixels = vis.to(DEV)
+        opt.on_after_backward({"viewspace_points": vp, "visibility_filter": torch.ones(n, dtype=torch.bool, device=DEV)}, None, None, step, None)
+        opt.step()
+        for k in shapes:
+            gk = grads[k].double()
+            m = b1 * ref_m[k] + (1 - b1) * gk
+            v = b2 * ref_v[k] + (1 - b2) * gk * gk
+            upd = ref_p[k] - lrs[k] * m / (v.sqrt() + eps)
+            sel = vis.reshape((n,) + (1,) * (gk.dim() - 1))
+            ref_m[k], ref_v[k], ref_p[k] = torch.where(sel, m, ref_m[k]), torch.where(sel, v, ref_v[k]), torch.where(sel, upd, ref_p[k])
+    for k, p in params.items():
+        st = opt.state[p]
+        assert torch.allclose(p.detach().cpu().double(), ref_p[k], rtol=2e-5, atol=1e-6), k
+        assert torch.allclose(st["exp_avg"].cpu().double(), ref_m[k], rtol=1e-5, atol=1e-7), k
+        assert torch.allclose(st["exp_avg_sq"].cpu().double(), ref_v[k], rtol=1e-5, atol=1e-9), k
+
+
+def test_densification_stats_match_the_controller_formulas():
+    from b200gs.optimizers import update_densification_stats
+    g = torch.Generator().manual_seed(5)
+    n = 7000
+    for stride, scale in ((2, torch.tensor([[400.0, 300.0]])), (3, None)):
+        radii = (torch.randint(0, 40, (n,), generator=g) * (torch.rand(n, generator=g) < 0.6)).to(torch.int32)
+        grad = torch.randn(n, stride, generator=g)
+        max_r, acc, den = torch.rand(n, generator=g) * 30, torch.rand(n, 1, generator=g), torch.randint(0, 5, (n, 1), generator=g).float()
+        vis = radii > 0
+        # reference formulas (vanilla_density_controller.py:107-123)
+        r_max = max_r.clone()
+        r_max[vis] = torch.max(r_max[vis], radii[vis].float())
+        sg = grad[vis, :2] * (scale if scale is not None else 1.0)
+        r_acc, r_den = acc.clone(), den.clone()
+        r_acc[vis] += torch.norm(sg, dim=-1, keepdim=True)
+        r_den[vis] += 1
+        d = [t.to(DEV) for t in (max_r, acc, den)]
+        update_densification_stats(radii.to(DEV), grad.to(DEV), d[0], d[1], d[2], visibility_filter=vis.to(DEV) if stride == 2 else None,
+                                   scale=scale.to(DEV) if scale is not None else None)
+        assert torch.equal(d[0].cpu(), r_max) and torch.allclose(d[1].cpu(), r_acc, rtol=1e-6, atol=1e-6) and torch.equal(d[2].cpu(), r_den)
