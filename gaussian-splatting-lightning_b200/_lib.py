@@ -44,6 +44,8 @@ _SIGNATURES = {
     "b200gs_project_bwd_raw": (c_int32, [POINTER(B200gsView), c_int64] + [_P] * 6 + [c_int32] + [_P] * 2 + [_P] * 5 + [_P] * 6 + [_P]),
     "b200gs_selective_adam": (c_int32, [c_int64, c_int32, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P]),
     "b200gs_densify_stats": (c_int32, [c_int64, _P, _P, _P, c_int32, c_float, c_float, _P, _P, _P, _P]),
+    "b200gs_knn_workspace_bytes": (c_size_t, [c_int64]),
+    "b200gs_knn_mean_dist2": (c_int32, [c_int64, _P, _P, _P, c_size_t, _P]),
     "b200gs_sh_fwd": (c_int32, [c_int32, c_int32, c_int64, _P, _P, _P, _P]),
     "b200gs_sh_bwd": (c_int32, [c_int32, c_int32, c_int64, _P, _P, _P, _P, _P, _P]),
     "b200gs_bin_count_workspace_bytes": (c_size_t, [c_int64]),

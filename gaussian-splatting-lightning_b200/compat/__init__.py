@@ -19,6 +19,15 @@ def install(force: bool = False):
             sys.modules[name] = module
 
     put("diff_gaussian_rasterization", dgr)
+    # simple_knn._C.distCUDA2 (internal/models/vanilla_gaussian.py:122-124)
+    from .. import ops
+    knn = types.ModuleType("simple_knn")
+    knn.__path__ = []
+    knn_c = types.ModuleType("simple_knn._C")
+    knn_c.distCUDA2 = ops.knn_mean_dist2
+    knn._C = knn_c
+    put("simple_knn", knn)
+    put("simple_knn._C", knn_c)
     pkg = types.ModuleType("gsplat")
     pkg.__path__ = []  # mark as package
     pkg.project_gaussians = gsplat_v0.project_gaussians

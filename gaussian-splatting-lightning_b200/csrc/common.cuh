@@ -121,6 +121,9 @@ int launch_selective_adam(int64_t rows, int width, float* param, const float* gr
 int launch_densify_stats(int64_t n, const int32_t* radii, const uint8_t* visible, const float* grad, int grad_stride, float sx, float sy,
                          float* max_radii2d, float* grad_accum, float* denom, cudaStream_t s);
 
+size_t knn_workspace_bytes(int64_t n);
+int launch_knn_mean_dist2(int64_t n, const float* points, float* out, void* ws, size_t ws_bytes, cudaStream_t s);
+
 int64_t loss_blocks(int channels, int width, int height);
 int launch_loss_fwd(int channels, int width, int height, const float* img, const float* gt, float* dmaps, float* partials, cudaStream_t s);
 int launch_loss_bwd(int channels, int width, int height, const float* img, const float* gt, const float* dmaps, float lambda_dssim,

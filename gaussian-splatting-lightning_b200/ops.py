@@ -770,6 +770,19 @@ def rasterize_binned(means2d, conics, colors, opacities, binning: Binning, img_h
     return (images[0] if len(images) == 1 else torch.cat(images, dim=-1)), alpha, hits
 
 
+def knn_mean_dist2(points: torch.Tensor) -> torch.Tensor:
+    """``simple_knn._C.distCUDA2(points [N,3]) -> [N]``: mean squared distance to the 3 nearest neighbours (vanilla_gaussian.py:122-125)."""
+    pts = _f32c(points, "points")
+    if pts.dim() != 2 or pts.shape[1] != 3:
+        raise ValueError("points must be [N, 3]")
+    L = lib()
+    n = pts.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=pts.device)
+    ws = torch.empty(max(int(L.b200gs_knn_workspace_bytes(n)), 256), dtype=torch.uint8, device=pts.device)
+    check(L.b200gs_knn_mean_dist2(n, ptr(pts), ptr(out), ptr(ws), ws.numel(), _stream()), "b200gs_knn_mean_dist2")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # fused L1 + SSIM loss (csrc/loss.cu; the metric the reference computes right after the renderer, vanilla_metrics.py:57-80)
 # ----------------------------------------------------------------------------------------------------------------------

@@ -133,6 +133,12 @@ B200GS_API int b200gs_selective_adam(int64_t rows, int32_t width, float* param, 
 B200GS_API int b200gs_densify_stats(int64_t n, const int32_t* radii, const uint8_t* visible, const float* grad, int32_t grad_stride,
                                     float scale_x, float scale_y, float* max_radii2d, float* grad_accum, float* denom, void* stream);
 
+/* b200gs_knn_mean_dist2: simple_knn's distCUDA2 (vanilla_gaussian.py:122-125, the scale initialiser): mean_dist2[i] = mean of the squared
+ *     distances from points[i] (float[n,3]) to its 3 nearest neighbours (exact).  Synchronises the stream once (the hash grid is sized
+ *     on the host from the bounding box); init-time only. */
+B200GS_API size_t b200gs_knn_workspace_bytes(int64_t n);
+B200GS_API int b200gs_knn_mean_dist2(int64_t n, const float* points, float* mean_dist2, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- standalone SH (gsplat.sh.spherical_harmonics; gsplat_renderer.py:105) -------------------------------------------
  * dirs[n,3] need not be unit (normalised inside, as gsplat does).  out rgb[n,3] = SH (no +0.5, no clamp).
  * bwd: v_coeffs[n,sh_stride,3] fully written; v_dirs[n,3] nullable. */

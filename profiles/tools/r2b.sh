@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_loss.py -q -m gpu > gpurun_out/r2b_gpu_parity.log 2>&1; echo "parity rc=$?"
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_loss.py tests/test_gpu_optim.py -q -m gpu > gpurun_out/r2b_gpu_parity.log 2>&1; echo "parity rc=$?"
 timeout 1200 python -m pytest tests/test_gpu_fullsize_parity.py tests/test_gpu_reference_dropin.py tests/test_gpu_v1_surface.py -q -m gpu > gpurun_out/r2b_gpu_full.log 2>&1; echo "full rc=$?"
 timeout 300 python bench.py --steps 48 --warmup 6 --no-cpu-baseline --no-extras > gpurun_out/r2b_bench.log 2>&1
 timeout 300 python bench.py --steps 48 --warmup 6 --no-cpu-baseline --no-extras --config 0 > gpurun_out/r2b_bench_c0.log 2>&1

@@ -62,3 +62,30 @@ def test_densification_stats_match_the_controller_formulas():
         update_densification_stats(radii.to(DEV), grad.to(DEV), d[0], d[1], d[2], visibility_filter=vis.to(DEV) if stride == 2 else None,
                                    scale=scale.to(DEV) if scale is not None else None)
         assert torch.equal(d[0].cpu(), r_max) and torch.allclose(d[1].cpu(), r_acc, rtol=1e-6, atol=1e-6) and torch.equal(d[2].cpu(), r_den)
+
+
+@pytest.mark.parametrize("n,kind", [(3, "uniform"), (2000, "uniform"), (8000, "clustered"), (5000, "planar"), (4000, "duplicates")])
+def test_knn_mean_dist2_matches_brute_force(n, kind):
+    """simple_knn's distCUDA2: mean squared distance to the 3 nearest neighbours, exact, on distributions that stress the hash grid."""
+    from b200gs import ops
+    g = torch.Generator().manual_seed(n)
+    if kind == "uniform":
+        pts = torch.rand(n, 3, generator=g) * 4 - 2
+    elif kind == "clustered":      # SfM-like: dense clumps + sparse outliers, very non-uniform cell occupancy
+        centers = torch.randn(20, 3, generator=g) * 5
+        pts = centers[torch.randint(0, 20, (n,), generator=g)] + 0.05 * torch.randn(n, 3, generator=g)
+        pts[: n // 50] = torch.randn(n // 50, 3, generator=g) * 40
+    elif kind == "planar":
+        pts = torch.rand(n, 3, generator=g)
+        pts[:, 2] = 0.25
+    else:
+        pts = torch.rand(n // 2, 3, generator=g).repeat(2, 1)
+    out = ops.knn_mean_dist2(pts.to(DEV)).cpu()
+    d = torch.cdist(pts.double(), pts.double()) ** 2
+    d.fill_diagonal_(float("inf"))
+    ref = d.topk(min(3, n - 1), largest=False).values.sum(dim=1) / 3.0
+    assert torch.allclose(out.double(), ref, rtol=1e-4, atol=1e-9), float((out.double() - ref).abs().max())
+    import b200gs.compat as compat
+    compat.install()
+    from simple_knn._C import distCUDA2
+    assert torch.equal(distCUDA2(pts.to(DEV)).cpu(), out)
