@@ -88,7 +88,7 @@ __device__ __forceinline__ int block_exclusive(int v, int* s_warp /*[WARPS + 1]*
 }
 
 // ---- histogram of the four digits of uint2 records ------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) hist4_kernel(const uint2* __restrict__ recs, const int64_t* __restrict__ d_n, int64_t cap,
+static __global__ void __launch_bounds__(THREADS) hist4_kernel(const uint2* __restrict__ recs, const int64_t* __restrict__ d_n, int64_t cap,
                                                        uint32_t* __restrict__ hist /*[4][RADIX]*/) {
     __shared__ uint32_t s_h[4][RADIX];
     const int64_t n = d_n ? min(cap, *d_n) : cap;
