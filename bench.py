@@ -392,6 +392,57 @@ class Workload:
         return steps * self.world / (ms * 1e-3)
 
 
+def loss_stage(width, height, dev, iters=20):
+    """The op right after the renderer in a training step: (1-l) L1 + l (1 - SSIM) forward + backward on a [3,H,W]
+    image.  Ours (two fused kernels) next to the reference's own torch implementation (internal/utils/ssim.py + vanilla_metrics.py:57-74,
+    the code in baseline/_ref) on the same GPU.  Not part of `value`."""
+    from b200gs import ops
+    g = torch.Generator().manual_seed(3)
+    gt = torch.rand(3, height, width, generator=g).to(dev)
+    img = (gt + 0.1 * torch.randn(3, height, width, generator=g).to(dev)).clamp(0, 1)
+    ref_path = os.path.join(ROOT, "baseline", "_ref", "internal", "utils", "ssim.py")
+    kind = "reference (baseline/_ref internal/utils/ssim.py, torch on the GPU)"
+    if os.path.exists(ref_path):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_ssim", ref_path)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        ssim = m.ssim
+    else:
+        ssim, kind = None, "unavailable (baseline/_ref absent): only the fused kernels were timed"
+
+    def ours():
+        x = img.clone().requires_grad_(True)
+        loss, _ = ops.l1_ssim_loss(x, gt, 0.2)
+        loss.backward()
+        return loss
+
+    def theirs():
+        x = img.clone().requires_grad_(True)
+        loss = 0.8 * torch.abs(x - gt).mean() + 0.2 * (1.0 - ssim(x, gt))
+        loss.backward()
+        return loss
+
+    out = {}
+    for name, fn in (("fused_ms", ours), ("torch_ms", theirs)):
+        if fn is theirs and ssim is None:
+            continue
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            val = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = round(e0.elapsed_time(e1) / iters, 4)
+        out[name.replace("_ms", "_loss")] = float(val)
+    out["torch_impl"] = kind
+    out["what"] = f"L1 + SSIM training loss forward + backward on a [3,{height},{width}] image (includes the clone of the input), CUDA events, {iters} iterations"
+    return out
+
+
 def scene_statistics(n, width, height, mode, dev):
     """V, I (rect pairs), I after exact culling, coarse pairs of pose 0 on the full scene (one GPU, no collectives)."""
     from b200gs import ops
@@ -529,6 +580,11 @@ def main():
         "scene": {"N": N, "V": V, "I": I, "I_after_exact_culling": I_culled, "coarse_pairs": C_coarse, "P": P, "stage_sum_ms": round(sum(stage_ms.values()), 4)},
     }
     line.update(extras)
+    if world == 1 and not args.no_extras:
+        try:
+            line["loss_stage"] = loss_stage(W, H, dev)
+        except Exception as e:      # the loss is a side measurement: never lose the main line over it
+            line["loss_stage"] = {"error": repr(e)}
     if not args.no_cpu_baseline and world == 1:
         vps, med, cores, kind = cpu_projection_views_per_sec(N, W, H, args.mode, args.cpu_sample_iters)
         line["cpu_baseline"] = {"value": vps, "unit": UNIT, "cores": cores, "kind": kind, "host_cpus": os.cpu_count() or 1,
