@@ -203,6 +203,10 @@ class PeerExchange:
         if rows_per_block <= self.rows_per_block:
             return True
         L = _lib.lib()
+        # a peer may still be reading the old buffers (its backward of the previous step pulls gradient rows from here): every rank
+        # drains its GPU, then all meet, and only then are the old mappings torn down
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=_host_group(self.group))
         self.release()
         want = int(rows_per_block * 1.25) + 4096
         nbytes = self.world * want * ROW_FLOATS * 4
