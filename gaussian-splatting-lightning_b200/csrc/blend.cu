@@ -145,13 +145,12 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_ker
 
     const int2 range = ranges[tile];
     int todo = range.y - range.x;
-    bool done = !inside;
-    float T = 1.0f;
+    float T = 1.0f, Tc = inside ? 1.0f : 0.0f;     // Tc == 0: this pixel is finished (or outside the image)
     int last = 0;
     float C[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (int base = 0; todo > 0; base += BLOCK_PIX, todo -= BLOCK_PIX) {
-        if (__syncthreads_and(done)) break;
+        if (__syncthreads_and(Tc == 0.0f)) break;
         const int cnt = min(BLOCK_PIX, todo);
         if (tid < cnt) {
             const int g = __ldg(ids + range.x + base + tid);
@@ -168,11 +167,11 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_ker
             s_mask[tid] = (unsigned char)block_mask(m.x, m.y, A, B, Cc, o, ox, oy);
         }
         __syncthreads();
-        if (__all_sync(FULL, done)) continue;  // warp finished: only keeps the block barriers company
+        if (__all_sync(FULL, Tc == 0.0f)) continue;  // warp finished: only keeps the block barriers company
         const unsigned short* my_list = s_list[warp] + LIST_PAD;
         const int nl = build_list(s_mask, s_list[warp], cnt, warp, lane);
         for (int i0 = 0; i0 < nl; i0 += 4) {
-            if (__all_sync(FULL, done)) break;
+            if (__all_sync(FULL, Tc == 0.0f)) break;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = my_list[i0 + u];                 // entries past nl are DUMMY (alpha 0)
@@ -181,12 +180,13 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_ker
                 const float dx = r0.x - pxf, dy = r0.y - pyf;
                 // power * log2(e) = a' dx^2 + b' dx dy + c' dy^2
                 const float p2 = fmaf(r1.x * dy, dy, fmaf(r0.w, dy, r0.z * dx) * dx);
-                const float a = fminf(amax, r1.y * ex2_approx(p2));
-                const float nT = fmaf(-a, T, T);
-                const bool ok = !done && !(p2 > 0.0f) && !(a < ALPHA_MIN);
-                const bool stop = ok && (GSPLAT ? (nT <= T_STOP) : (nT < T_STOP));
-                const bool take = ok && !stop;
-                const float w = take ? a * T : 0.f;
+                float a = fminf(amax, r1.y * ex2_approx(p2));
+                a = (!(p2 > 0.0f) && !(a < ALPHA_MIN)) ? a : 0.f;             // a sample that fails the alpha test composites nothing
+                // Tc is the transmittance used for compositing; it drops to exactly 0 when the pixel stops, so every later sample
+                // weighs nothing without a `done` predicate in the arithmetic; T keeps the value in front of the stopping sample
+                const float nT = fmaf(-a, Tc, Tc);
+                const bool stop = GSPLAT ? (nT <= T_STOP) : (nT < T_STOP);
+                const float w = stop ? 0.f : a * Tc;
                 C[0] = fmaf(r1.z, w, C[0]);
                 if (CH > 1) C[1] = fmaf(r1.w, w, C[1]);
                 if (CH > 2) {
@@ -194,9 +194,9 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_ker
                     C[2] = fmaf(r2.x, w, C[2]);
                     if (CH > 3) C[3] = fmaf(r2.y, w, C[3]);
                 }
-                T = take ? nT : T;
-                last = take ? base + j + 1 : last;
-                done = done || stop;
+                last = (w > 0.f) ? base + j + 1 : last;
+                T = stop ? T : nT;
+                Tc = stop ? 0.f : nT;
             }
         }
     }
@@ -288,8 +288,7 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_asy
 
     const int2 range = ranges[tile];
     const int total = range.y - range.x;
-    bool done = !inside;
-    float T = 1.0f;
+    float T = 1.0f, Tc = inside ? 1.0f : 0.0f;
     int last = 0;
     float C[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -301,7 +300,7 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_asy
     int buf = 0;
     for (int base = 0; base < total; base += BLOCK_PIX, buf ^= 1) {
         cp_async_wait_all();
-        if (__syncthreads_and(done)) break;          // also: every thread's copies of this batch are visible
+        if (__syncthreads_and(Tc == 0.0f)) break;    // also: every thread's copies of this batch are visible
         const int cnt = min(BLOCK_PIX, total - base);
         float4* s_rec = s_buf[buf];
         if (tid < cnt) {
@@ -321,11 +320,11 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_asy
         if (base + BLOCK_PIX + tid < total) stage_async<CH, ROWS>(&s_buf[buf ^ 1][tid * 3], next_id, st, xy, conic, opacity, colors);
         next_id = (base + 2 * BLOCK_PIX + tid < total) ? __ldg(ids + range.x + base + 2 * BLOCK_PIX + tid) : 0;
         __syncthreads();
-        if (__all_sync(FULL, done)) continue;  // warp finished: only keeps the block barriers company
+        if (__all_sync(FULL, Tc == 0.0f)) continue;  // warp finished: only keeps the block barriers company
         const unsigned short* my_list = s_list[warp] + LIST_PAD;
         const int nl = build_list(s_mask, s_list[warp], cnt, warp, lane);
         for (int i0 = 0; i0 < nl; i0 += 4) {
-            if (__all_sync(FULL, done)) break;
+            if (__all_sync(FULL, Tc == 0.0f)) break;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = my_list[i0 + u];                 // entries past nl are DUMMY (alpha 0)
@@ -333,12 +332,11 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_asy
                 const float4 r1 = s_rec[j * 3 + 1];
                 const float dx = r0.x - pxf, dy = r0.y - pyf;
                 const float p2 = fmaf(r1.x * dy, dy, fmaf(r0.w, dy, r0.z * dx) * dx);
-                const float a = fminf(amax, r1.y * ex2_approx(p2));
-                const float nT = fmaf(-a, T, T);
-                const bool ok = !done && !(p2 > 0.0f) && !(a < ALPHA_MIN);
-                const bool stop = ok && (GSPLAT ? (nT <= T_STOP) : (nT < T_STOP));
-                const bool take = ok && !stop;
-                const float w = take ? a * T : 0.f;
+                float a = fminf(amax, r1.y * ex2_approx(p2));
+                a = (!(p2 > 0.0f) && !(a < ALPHA_MIN)) ? a : 0.f;
+                const float nT = fmaf(-a, Tc, Tc);             // same arithmetic as blend_fwd_kernel: see there
+                const bool stop = GSPLAT ? (nT <= T_STOP) : (nT < T_STOP);
+                const float w = stop ? 0.f : a * Tc;
                 C[0] = fmaf(r1.z, w, C[0]);
                 if (CH > 1) C[1] = fmaf(r1.w, w, C[1]);
                 if (CH > 2) {
@@ -346,11 +344,11 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_asy
                     C[2] = fmaf(r2.x, w, C[2]);
                     if (CH > 3) C[3] = fmaf(r2.y, w, C[3]);
                 }
-                T = take ? nT : T;
-                last = take ? base + j + 1 : last;
-                done = done || stop;
+                last = (w > 0.f) ? base + j + 1 : last;
+                T = stop ? T : nT;
+                Tc = stop ? 0.f : nT;
                 if (HITS) {
-                    if (__any_sync(FULL, take) && lane == 0) hit_any[s_gid[j]] = 1;
+                    if (__any_sync(FULL, w > 0.f) && lane == 0) hit_any[s_gid[j]] = 1;
                 }
             }
         }
