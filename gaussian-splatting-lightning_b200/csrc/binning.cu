@@ -47,19 +47,19 @@ static_assert(sizeof(SplatRec) == 32, "SplatRec must be one sector");
 // value type of the coarse partition: {tile mask lo, tile mask hi, Gaussian id, unused}
 typedef uint4 CellEntry;
 
-constexpr int DEPTH_IPT = 16;                        // records per thread of a depth-sort tile (uint2: 32 KB of staging)
-constexpr int CELL_IPT = 8;                          // records per thread of a cell-partition tile (uint4: 32 KB of staging)
-constexpr int DEPTH_TILE = sweep::THREADS * DEPTH_IPT;
-constexpr int CELL_TILE = sweep::THREADS * CELL_IPT;
+constexpr int DEPTH_IPT = 8;                         // records per thread of a depth-sort tile (uint2: 4096 per tile, 32 KB of staging)
+constexpr int CELL_IPT = 4;                          // records per thread of a cell-partition tile (uint4: 2048 per tile, 32 KB of staging)
+constexpr int DEPTH_TILE = sweep::PASS_THREADS * DEPTH_IPT;
+constexpr int CELL_TILE = sweep::PASS_THREADS * CELL_IPT;
 
 struct LayoutA {
     size_t rec_a, rec_b, recs, zero, zero_bytes, hist, tickets, scan_state, lookback, total;
     int64_t tiles, blocks;
 };
 struct LayoutB {
-    size_t entries_in, entries, zero, zero_bytes, cell_hist, tickets, scan_state, lookback, digit_hist, cell_ranges, chunk_base, chunk_cell,
+    size_t entries_in, entries, offsets, zero, zero_bytes, cell_hist, tickets, scan_state, lookback, digit_hist, cell_ranges, chunk_base, chunk_cell,
         chunk_cnt, chunk_pre, tile_start, total;
-    int64_t max_chunks, tiles, blocks;
+    int64_t max_chunks, tiles, blocks, scan_blocks;
 };
 
 inline int bits_for(int n_values) {
@@ -85,7 +85,7 @@ LayoutA make_layout_a(int64_t n) {
     Taker take;
     const size_t nn = (size_t)(n > 0 ? n : 1);
     L.tiles = (int64_t)div_up64((int64_t)nn, DEPTH_TILE);
-    L.blocks = (int64_t)div_up64((int64_t)nn, 256);
+    L.blocks = (int64_t)div_up64((int64_t)nn, 256 * 8);      // depth_keys_kernel: 256 threads x DK_ITEMS Gaussians
     L.rec_a = take(nn * 8);
     L.rec_b = take(nn * 8);
     L.recs = take(nn * sizeof(SplatRec));
@@ -123,12 +123,14 @@ LayoutB make_layout_b(int64_t n, int64_t max_coarse, int width, int height) {
     L.max_chunks = (int64_t)(pp / CHUNK + n_cells + 1);
     L.tiles = (int64_t)div_up64((int64_t)pp, CELL_TILE);
     L.blocks = (int64_t)div_up64(n > 0 ? n : 1, 256);
+    L.scan_blocks = (int64_t)div_up64(n > 0 ? n : 1, 256 * 8);   // rank_offsets_kernel: 256 threads x RO_ITEMS ranks
     L.entries_in = take(pp * sizeof(CellEntry));
     L.entries = take(pp * sizeof(CellEntry));
+    L.offsets = take((size_t)(n > 0 ? n : 1) * 4);
     L.zero = take(0);
     L.cell_hist = take(n_cells * 4);
     L.tickets = take(16 * 4);
-    L.scan_state = take((size_t)L.blocks * 4);
+    L.scan_state = take((size_t)L.scan_blocks * 4);
     L.lookback = take((size_t)2 * L.tiles * sweep::RADIX * 4);
     L.zero_bytes = take.off - L.zero;
     L.digit_hist = take(2 * sweep::RADIX * 4);
@@ -239,52 +241,59 @@ __device__ __forceinline__ void coarsen_rect(int x0, int y0, int x1, int y1, int
     cy1 = ((y1 - 1) >> SUPER_SHIFT) + 1;
 }
 
-// Phase A, one lane per Gaussian, blocks in ticket order: the visible Gaussians (non-empty tile rect) are compacted in index
-// order (block scan + chained scan over the blocks) into {depth key, id} records; each gets the 32-byte record phase B
-// works from.  counts[0] += tiles of the rect (the reference's pair count I: an upper bound of the culled count, exact
-// without culling), counts[1] += coarse cells, counts[3] = V.
+// Phase A, blocks in ticket order, DK_ITEMS consecutive Gaussians per thread (2048 per block: the chained scan advances 32 blocks per
+// round trip to L2, so its length in BLOCKS is what the kernel's latency is made of — profiles/round2b: 53 us with 256-Gaussian
+// blocks).  The visible Gaussians (non-empty tile rect) are compacted in index order (block scan + chained scan) into {depth key, id}
+// records; each gets the 32-byte record phase B works from; the histograms of the four key bytes (what the radix passes start
+// from) are accumulated on the way.  counts[0] += tiles of the rect (the reference's pair count I: an upper bound of the culled
+// count, exact without culling), counts[1] += coarse cells, counts[3] = V.
+constexpr int DK_ITEMS = 8;
+
 template <bool GSPLAT>
 __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, int grid_y, const BinSrc src, uint2* __restrict__ keyrec,
                                                          SplatRec* __restrict__ recs, uint32_t* __restrict__ ticket,
-                                                         uint32_t* __restrict__ scan_state, unsigned long long* __restrict__ counts) {
+                                                         uint32_t* __restrict__ scan_state, uint32_t* __restrict__ hist,
+                                                         unsigned long long* __restrict__ counts) {
     __shared__ unsigned long long s_area[8], s_cells[8];
     __shared__ int s_scan[sweep::WARPS + 1];
     __shared__ int s_tile;
     __shared__ uint32_t s_excl;
+    __shared__ uint32_t s_h[4][sweep::RADIX];
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < 4 * sweep::RADIX; i += 256) (&s_h[0][0])[i] = 0;
     __syncthreads();
     const int t = s_tile;
-    const int64_t i = int64_t(t) * blockDim.x + threadIdx.x;
-    int area = 0, nc = 0;
-    SplatRec rec;
-    rec.x = rec.y = 0.f; rec.A = rec.C = 1.f; rec.B = 0.f; rec.opacity = 1.f; rec.radius = 0; rec.ncells = 0;
-    uint32_t key = 0xFFFFFFFFu;
-    if (i < n) {
-        const int r = src.get_radius(i);
-        rec.radius = r;
-        if (r > 0) {
-            const float2 p = src.get_xy(i);
-            rec.x = p.x; rec.y = p.y;
-            int x0, y0, x1, y1;
-            tile_rect<GSPLAT>(p.x, p.y, (float)r, grid_x, grid_y, x0, y0, x1, y1);
-            area = max(0, x1 - x0) * max(0, y1 - y0);
-            if (area > 0) {
-                int cx0, cy0, cx1, cy1;
-                coarsen_rect(x0, y0, x1, y1, cx0, cy0, cx1, cy1);
-                nc = (cx1 - cx0) * (cy1 - cy0);
-                if (src.conic != nullptr) {
-                    const float* q = src.conic + i * src.cs;
-                    rec.A = q[0]; rec.B = q[1]; rec.C = q[2];
-                    rec.opacity = src.opacity[i * src.os];
+    const int64_t i0 = (int64_t(t) * blockDim.x + threadIdx.x) * DK_ITEMS;
+    unsigned long long area_sum = 0, cell_sum = 0;
+    uint32_t key[DK_ITEMS];
+    int ncell[DK_ITEMS];
+    int my_vis = 0;
+#pragma unroll
+    for (int k = 0; k < DK_ITEMS; ++k) {
+        const int64_t i = i0 + k;
+        key[k] = 0xFFFFFFFFu;
+        ncell[k] = 0;
+        if (i < n) {
+            const int r = src.get_radius(i);
+            if (r > 0) {
+                const float2 p = src.get_xy(i);
+                int x0, y0, x1, y1;
+                tile_rect<GSPLAT>(p.x, p.y, (float)r, grid_x, grid_y, x0, y0, x1, y1);
+                const int area = max(0, x1 - x0) * max(0, y1 - y0);
+                if (area > 0) {
+                    int cx0, cy0, cx1, cy1;
+                    coarsen_rect(x0, y0, x1, y1, cx0, cy0, cx1, cy1);
+                    ncell[k] = (cx1 - cx0) * (cy1 - cy0);
+                    key[k] = __float_as_uint(src.get_depth(i));
+                    area_sum += (unsigned long long)area;
+                    cell_sum += (unsigned long long)ncell[k];
+                    ++my_vis;
                 }
-                key = __float_as_uint(src.get_depth(i));
             }
         }
-        rec.ncells = nc;
     }
-    const bool vis = area > 0;
     int block_vis;
-    const int local = sweep::block_exclusive(vis ? 1 : 0, s_scan, &block_vis);
+    int local = sweep::block_exclusive(my_vis, s_scan, &block_vis);
     if (threadIdx.x < 32) {     // warp 0: warp-wide look-back over the preceding blocks
         const uint32_t excl = sweep::chained_exclusive(scan_state, t, (uint32_t)block_vis);
         if (threadIdx.x == 0) {
@@ -293,13 +302,29 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
         }
     }
     __syncthreads();
-    if (vis) {
-        keyrec[s_excl + (uint32_t)local] = make_uint2(key, (uint32_t)i);
+    const uint32_t base = s_excl;
+#pragma unroll
+    for (int k = 0; k < DK_ITEMS; ++k) {
+        if (ncell[k] == 0) continue;
+        const int64_t i = i0 + k;
+        const float2 p = src.get_xy(i);
+        float A = 1.f, B = 0.f, C = 1.f, o = 1.f;
+        if (src.conic != nullptr) {
+            const float* q = src.conic + i * src.cs;
+            A = q[0]; B = q[1]; C = q[2];
+            o = src.opacity[i * src.os];
+        }
+        keyrec[base + (uint32_t)local] = make_uint2(key[k], (uint32_t)i);
+        ++local;
         float4* out = reinterpret_cast<float4*>(recs + i);
-        out[0] = make_float4(rec.x, rec.y, rec.A, rec.B);
-        out[1] = make_float4(rec.C, rec.opacity, __int_as_float(rec.radius), __int_as_float(rec.ncells));
+        out[0] = make_float4(p.x, p.y, A, B);
+        out[1] = make_float4(C, o, __int_as_float(src.get_radius(i)), __int_as_float(ncell[k]));
+        atomicAdd(&s_h[0][key[k] & 255u], 1u);
+        atomicAdd(&s_h[1][(key[k] >> 8) & 255u], 1u);
+        atomicAdd(&s_h[2][(key[k] >> 16) & 255u], 1u);
+        atomicAdd(&s_h[3][key[k] >> 24], 1u);
     }
-    unsigned long long a = (unsigned long long)area, c = (unsigned long long)nc;
+    unsigned long long a = area_sum, c = cell_sum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -313,6 +338,49 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
         for (int w = 0; w < 8; ++w) { ta += s_area[w]; tc += s_cells[w]; }
         if (ta) atomicAdd(counts, ta);
         if (tc) atomicAdd(counts + 1, tc);
+    }
+    for (int i = threadIdx.x; i < 4 * sweep::RADIX; i += 256) {
+        const uint32_t v = (&s_h[0][0])[i];
+        if (v) atomicAdd(hist + i, v);
+    }
+}
+
+// Exclusive prefix of the coarse-cell counts over the depth-ranked Gaussians: offsets[rank] = first entry slot of that rank.  Big
+// tiles (RO_ITEMS consecutive ranks per thread) for the same reason as above; the cell count of a rank is gathered from its record.
+constexpr int RO_ITEMS = 8;
+
+__global__ void __launch_bounds__(256) rank_offsets_kernel(const int64_t* __restrict__ d_visible, const uint2* __restrict__ order,
+                                                          const SplatRec* __restrict__ recs, uint32_t* __restrict__ offsets,
+                                                          uint32_t* __restrict__ ticket, uint32_t* __restrict__ scan_state) {
+    __shared__ int s_scan[sweep::WARPS + 1];
+    __shared__ int s_tile;
+    __shared__ uint32_t s_excl;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int t = s_tile;
+    const int64_t n = *d_visible;
+    const int64_t r0 = (int64_t(t) * blockDim.x + threadIdx.x) * RO_ITEMS;
+    if (int64_t(t) * blockDim.x * RO_ITEMS >= n) return;
+    int nc[RO_ITEMS];
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < RO_ITEMS; ++k) {
+        nc[k] = 0;
+        if (r0 + k < n) nc[k] = __ldg(&recs[order[r0 + k].y].ncells);
+        mine += nc[k];
+    }
+    int block_total;
+    int local = sweep::block_exclusive(mine, s_scan, &block_total);
+    if (threadIdx.x < 32) {
+        const uint32_t excl = sweep::chained_exclusive(scan_state, t, (uint32_t)block_total);
+        if (threadIdx.x == 0) s_excl = excl;
+    }
+    __syncthreads();
+    uint32_t run = s_excl + (uint32_t)local;
+#pragma unroll
+    for (int k = 0; k < RO_ITEMS; ++k) {
+        if (r0 + k < n) offsets[r0 + k] = run;
+        run += (uint32_t)nc[k];
     }
 }
 
@@ -329,25 +397,20 @@ constexpr int EMIT_HIST = 1024;   // cells counted in shared memory (images up t
 template <bool GSPLAT>
 __global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restrict__ d_visible, int grid_x, int grid_y, int cgrid_x, int cull,
                                                          int64_t max_coarse, const uint2* __restrict__ order, const SplatRec* __restrict__ recs,
-                                                         CellEntry* __restrict__ entries, int n_cells, uint32_t* __restrict__ cell_hist,
-                                                         uint32_t* __restrict__ ticket, uint32_t* __restrict__ scan_state) {
+                                                         const uint32_t* __restrict__ offsets, CellEntry* __restrict__ entries, int n_cells,
+                                                         uint32_t* __restrict__ cell_hist) {
     __shared__ unsigned short s_k[EMIT_SLOTS];
     __shared__ int32_t s_id[EMIT_SLOTS];
     __shared__ unsigned long long s_mask[EMIT_SLOTS];
     __shared__ float s_f[8][256];        // mx, my, B, iA, two_tA, det, ymax, yR
     __shared__ int s_mode[256], s_xr[256], s_yr[256], s_start[256];   // x0 | x1 << 16, y0 | y1 << 16, first slot - block_lo
-    __shared__ int s_rowoff[257];
+    __shared__ int s_rowoff[260];
     __shared__ int s_warp[8];
-    __shared__ int s_scan[sweep::WARPS + 1];
     __shared__ uint32_t s_hist[EMIT_HIST];
-    __shared__ int64_t s_lo;
-    __shared__ int s_tile;
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u, w = tid >> 5;
-    if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
-    __syncthreads();
     const int64_t n = *d_visible;
-    const int64_t rank0 = int64_t(s_tile) * blockDim.x;
+    const int64_t rank0 = int64_t(blockIdx.x) * blockDim.x;
     if (rank0 >= n) return;
     const bool smem_hist = n_cells <= EMIT_HIST;
     if (smem_hist)
@@ -369,13 +432,11 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restri
             nrows = (e.mode == 2) ? 0 : y1 - y0;
         }
     }
-    // first slot of this rank: cells of the ranks before it (this block: scan; the blocks before: chained scan)
-    int block_cells;
-    const int local_start = sweep::block_exclusive(t, s_scan, &block_cells);
-    if (tid < 32) {             // warp 0: warp-wide look-back over the preceding blocks
-        const uint32_t before = sweep::chained_exclusive(scan_state, s_tile, (uint32_t)block_cells);
-        if (tid == 0) s_lo = (int64_t)before;
-    }
+    // first slot of this rank = cells of the ranks before it (rank_offsets_kernel); the block's ranks own one contiguous window
+    const int64_t block_lo = (int64_t)offsets[rank0];
+    const int64_t last_rank = min(rank0 + (int64_t)blockDim.x, n) - 1;
+    const int block_cells = (int)((int64_t)offsets[last_rank] + __ldg(&recs[order[last_rank].y].ncells) - block_lo);
+    const int local_start = (rnk < n) ? (int)((int64_t)offsets[rnk] - block_lo) : block_cells;
     // exclusive scan of the row counts
     int inc = nrows;
 #pragma unroll
@@ -388,7 +449,8 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restri
     int wbase = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) wbase += (k < (int)w) ? s_warp[k] : 0;
-    const int64_t block_lo = s_lo;
+    __syncthreads();   // every warp has read s_warp before anything below is stored (racecheck, round 2: a slow warp's read of
+                       // s_warp raced with the stores that follow in a fast warp)
     s_rowoff[tid] = wbase + inc - nrows;
     if (tid == 255) s_rowoff[256] = wbase + inc;
     s_f[0][tid] = e.mx; s_f[1][tid] = e.my; s_f[2][tid] = e.B; s_f[3][tid] = e.iA;
@@ -827,18 +889,16 @@ int bin_count(int mode, int width, int height, int64_t n, int row_stride, const 
         const unsigned blocks = (unsigned)L.blocks;
         const BinSrc src = make_src(row_stride, xy, depth, radii, conic, opacity);
         if (mode == B200GS_MODE_GSPLAT)
-            depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, rec_a, recs, tickets, scan_state, (unsigned long long*)d_counts);
+            depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, rec_a, recs, tickets, scan_state, hist, (unsigned long long*)d_counts);
         else
-            depth_keys_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, rec_a, recs, tickets, scan_state, (unsigned long long*)d_counts);
+            depth_keys_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, rec_a, recs, tickets, scan_state, hist, (unsigned long long*)d_counts);
         B200GS_LAUNCH_CHECK();
-        // stable LSD sort of the V visible {depth key, id} records (V = d_counts[3], known on the device only)
+        // stable LSD sort of the V visible {depth key, id} records (V = d_counts[3], known on the device only; byte histograms from above)
         const int64_t* d_visible = d_counts + 3;
-        sweep::hist4_kernel<<<(unsigned)min((int64_t)592, L.blocks), sweep::THREADS, 0, s>>>(rec_a, d_visible, n, hist);
-        B200GS_LAUNCH_CHECK();
         uint2* src_rec = rec_a;
         uint2* dst_rec = rec_b;
         for (int pass = 0; pass < 4; ++pass) {
-            sweep::onesweep_pass_kernel<uint2, DEPTH_IPT><<<(unsigned)L.tiles, sweep::THREADS, 0, s>>>(
+            sweep::onesweep_pass_kernel<uint2, DEPTH_IPT><<<(unsigned)L.tiles, sweep::PASS_THREADS, 0, s>>>(
                 src_rec, dst_rec, d_visible, n, 8 * pass, hist + pass * sweep::RADIX, lookback + (size_t)pass * L.tiles * sweep::RADIX, tickets + 1 + pass);
             B200GS_LAUNCH_CHECK();
             uint2* tmp = src_rec; src_rec = dst_rec; dst_rec = tmp;
@@ -878,6 +938,7 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
     const SplatRec* recs = (const SplatRec*)(wa + LA.recs);
     CellEntry* entries_in = (CellEntry*)(w + L.entries_in);
     CellEntry* entries = (CellEntry*)(w + L.entries);
+    uint32_t* offsets = (uint32_t*)(w + L.offsets);
     uint32_t* cell_hist = (uint32_t*)(w + L.cell_hist);
     uint32_t* tickets = (uint32_t*)(w + L.tickets);
     uint32_t* scan_state = (uint32_t*)(w + L.scan_state);
@@ -896,24 +957,26 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
     B200GS_CUDA(cudaMemsetAsync(w + L.zero, 0, L.zero_bytes, s));
     const bool two_pass = n_cells > sweep::RADIX;
     CellEntry* emit_dst = two_pass ? entries : entries_in;   // one pass: in -> entries; two passes: entries -> in -> entries
+    rank_offsets_kernel<<<(unsigned)L.scan_blocks, 256, 0, s>>>(d_visible, order, recs, offsets, tickets, scan_state);
+    B200GS_LAUNCH_CHECK();
     if (mode == B200GS_MODE_GSPLAT)
-        emit_cells_kernel<true><<<(unsigned)L.blocks, 256, 0, s>>>(d_visible, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, emit_dst, n_cells,
-                                                                    cell_hist, tickets, scan_state);
+        emit_cells_kernel<true><<<(unsigned)L.blocks, 256, 0, s>>>(d_visible, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, emit_dst,
+                                                                    n_cells, cell_hist);
     else
-        emit_cells_kernel<false><<<(unsigned)L.blocks, 256, 0, s>>>(d_visible, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, emit_dst, n_cells,
-                                                                     cell_hist, tickets, scan_state);
+        emit_cells_kernel<false><<<(unsigned)L.blocks, 256, 0, s>>>(d_visible, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, emit_dst,
+                                                                     n_cells, cell_hist);
     B200GS_LAUNCH_CHECK();
     cell_table_kernel<<<1, 1024, 0, s>>>(n_cells, cell_hist, cell_ranges, chunk_base, chunk_cell, digit_hist, n_tiles, tile_start);
     B200GS_LAUNCH_CHECK();
     // stable partition by cell: one onesweep pass per byte of the cell id (the entry carries its cell in .w)
     if (two_pass) {
-        sweep::onesweep_pass_kernel<CellEntry, CELL_IPT><<<(unsigned)L.tiles, sweep::THREADS, 0, s>>>(entries, entries_in, d_coarse, max_coarse, 0, digit_hist,
+        sweep::onesweep_pass_kernel<CellEntry, CELL_IPT><<<(unsigned)L.tiles, sweep::PASS_THREADS, 0, s>>>(entries, entries_in, d_coarse, max_coarse, 0, digit_hist,
                                                                                                       lookback, tickets + 1);
         B200GS_LAUNCH_CHECK();
-        sweep::onesweep_pass_kernel<CellEntry, CELL_IPT><<<(unsigned)L.tiles, sweep::THREADS, 0, s>>>(
+        sweep::onesweep_pass_kernel<CellEntry, CELL_IPT><<<(unsigned)L.tiles, sweep::PASS_THREADS, 0, s>>>(
             entries_in, entries, d_coarse, max_coarse, 8, digit_hist + sweep::RADIX, lookback + (size_t)L.tiles * sweep::RADIX, tickets + 2);
     } else {
-        sweep::onesweep_pass_kernel<CellEntry, CELL_IPT><<<(unsigned)L.tiles, sweep::THREADS, 0, s>>>(entries_in, entries, d_coarse, max_coarse, 0, digit_hist,
+        sweep::onesweep_pass_kernel<CellEntry, CELL_IPT><<<(unsigned)L.tiles, sweep::PASS_THREADS, 0, s>>>(entries_in, entries, d_coarse, max_coarse, 0, digit_hist,
                                                                                                       lookback, tickets + 1);
     }
     B200GS_LAUNCH_CHECK();

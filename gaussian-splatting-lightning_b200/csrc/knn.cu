@@ -122,14 +122,14 @@ struct KnnLayout {
     int64_t tiles, max_cells;
 };
 
-constexpr int KNN_IPT = 16;
+constexpr int KNN_IPT = 8;
 
 KnnLayout knn_layout(int64_t n) {
     KnnLayout L{};
     size_t off = 0;
     auto take = [&off](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t nn = (size_t)(n > 0 ? n : 1);
-    L.tiles = div_up64((int64_t)nn, sweep::THREADS * KNN_IPT);
+    L.tiles = div_up64((int64_t)nn, sweep::PASS_THREADS * KNN_IPT);
     L.max_cells = (int64_t)(4 * nn + 64);
     L.bounds = take(6 * 4);
     L.rec_a = take(nn * 8);
@@ -216,7 +216,7 @@ int launch_knn_mean_dist2(int64_t n, const float* points, float* out, void* ws, 
     uint2* src = rec_a;
     uint2* dst = rec_b;
     for (int pass = 0; pass < passes; ++pass) {
-        sweep::onesweep_pass_kernel<uint2, KNN_IPT><<<(unsigned)L.tiles, sweep::THREADS, 0, s>>>(src, dst, nullptr, n, 8 * pass, hist + pass * sweep::RADIX,
+        sweep::onesweep_pass_kernel<uint2, KNN_IPT><<<(unsigned)L.tiles, sweep::PASS_THREADS, 0, s>>>(src, dst, nullptr, n, 8 * pass, hist + pass * sweep::RADIX,
                                                                                             lookback + (size_t)pass * L.tiles * sweep::RADIX, tickets + pass);
         B200GS_LAUNCH_CHECK();
         uint2* t = src; src = dst; dst = t;

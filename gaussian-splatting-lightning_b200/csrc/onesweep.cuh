@@ -64,8 +64,9 @@ __device__ __forceinline__ uint32_t chained_exclusive(uint32_t* state, int t, ui
     return excl;
 }
 
-// block-wide exclusive scan of one int per thread (THREADS threads); returns the exclusive prefix, *total = block sum
-__device__ __forceinline__ int block_exclusive(int v, int* s_warp /*[WARPS + 1]*/, int* total) {
+// block-wide exclusive scan of one int per thread (NW warps); returns the exclusive prefix, *total = block sum
+template <int NW = WARPS>
+__device__ __forceinline__ int block_exclusive(int v, int* s_warp /*[NW + 1]*/, int* total) {
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     int inc = v;
 #pragma unroll
@@ -77,7 +78,7 @@ __device__ __forceinline__ int block_exclusive(int v, int* s_warp /*[WARPS + 1]*
     __syncthreads();
     int base = 0, tot = 0;
 #pragma unroll
-    for (int k = 0; k < WARPS; ++k) {
+    for (int k = 0; k < NW; ++k) {
         const int c = s_warp[k];
         base += (k < (int)w) ? c : 0;
         tot += c;
@@ -110,21 +111,29 @@ static __global__ void __launch_bounds__(THREADS) hist4_kernel(const uint2* __re
 
 // ---- one digit pass ----------------------------------------------------------------------------------------------------
 // hist[RADIX]: global count of every digit value of this pass; lookback[tiles][RADIX] and *ticket zero before the launch.
+// PASS_THREADS threads per tile, IPT records per thread (tile = 4096 8-byte or 2048 16-byte records: 32 KB of staging).  16 warps
+// per tile and <= 64 registers keep two tiles = 32 warps resident per SM: the ranking loop is a chain of dependent shared-memory
+// read-modify-writes per warp, latency that only other warps can hide (profiles/round2b: 256 threads x 16 records at 127 registers ran
+// at 19 % of the issue slots, 20 us per pass over 0.65 M records).
+constexpr int PASS_THREADS = 512;
+constexpr int PASS_WARPS = PASS_THREADS / 32;
+
 template <typename Rec, int IPT>
-__global__ void __launch_bounds__(THREADS) onesweep_pass_kernel(const Rec* __restrict__ in, Rec* __restrict__ out, const int64_t* __restrict__ d_n,
-                                                               int64_t cap, int shift, const uint32_t* __restrict__ hist,
-                                                               uint32_t* __restrict__ lookback, uint32_t* __restrict__ ticket) {
-    constexpr int TILE_ITEMS = THREADS * IPT;
-    __shared__ uint32_t s_cnt[WARPS][RADIX];     // per-warp digit counts -> exclusive offsets of the warp inside the tile's digit run
-    __shared__ int s_base[RADIX];                // global index of the tile's first record of a digit, minus its slot in the tile
-    __shared__ int s_scan[WARPS + 1];
+__global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Rec* __restrict__ in, Rec* __restrict__ out, const int64_t* __restrict__ d_n,
+                                                                        int64_t cap, int shift, const uint32_t* __restrict__ hist,
+                                                                        uint32_t* __restrict__ lookback, uint32_t* __restrict__ ticket) {
+    constexpr int TILE_ITEMS = PASS_THREADS * IPT;
+    static_assert(TILE_ITEMS < 65536, "per-warp digit counts are 16-bit");
+    __shared__ unsigned short s_cnt[PASS_WARPS][RADIX];   // per-warp digit counts -> offsets of the warp inside the tile's digit run
+    __shared__ int s_base[RADIX];                         // global index of the tile's first record of a digit, minus its slot in the tile
+    __shared__ int s_scan[PASS_WARPS + 1];
     __shared__ int s_tile;
     __shared__ Rec s_stage[TILE_ITEMS];
     const int64_t n = d_n ? min(cap, *d_n) : cap;
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31u, w = tid >> 5;
     if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
-    for (int i = tid; i < WARPS * RADIX; i += THREADS) (&s_cnt[0][0])[i] = 0;
+    for (int i = tid; i < PASS_WARPS * RADIX / 2; i += PASS_THREADS) reinterpret_cast<uint32_t*>(&s_cnt[0][0])[i] = 0;
     __syncthreads();
     const int t = s_tile;
     const int64_t tile_lo = int64_t(t) * TILE_ITEMS;
@@ -134,7 +143,7 @@ __global__ void __launch_bounds__(THREADS) onesweep_pass_kernel(const Rec* __res
     Rec rec[IPT];
     int dig[IPT];      // 0..255, or 256 for the slots past the end
     int rank[IPT];
-    uint32_t* my_cnt = s_cnt[w];
+    unsigned short* my_cnt = s_cnt[w];
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         const int local = (int)w * (32 * IPT) + i * 32 + (int)lane;
@@ -146,24 +155,23 @@ __global__ void __launch_bounds__(THREADS) onesweep_pass_kernel(const Rec* __res
     for (int i = 0; i < IPT; ++i) {
         const unsigned peers = __match_any_sync(0xffffffffu, dig[i]);
         const int lt = __popc(peers & ((1u << lane) - 1u));
-        uint32_t before = 0;
+        int before = 0;
         if (dig[i] < 256) before = my_cnt[dig[i]];
         __syncwarp();
-        if (dig[i] < 256 && lt == 0) my_cnt[dig[i]] = before + __popc(peers);
+        if (dig[i] < 256 && lt == 0) my_cnt[dig[i]] = (unsigned short)(before + __popc(peers));
         __syncwarp();
-        rank[i] = (int)before + lt;
+        rank[i] = before + lt;
     }
     __syncthreads();
-    // thread d owns digit d: offsets of the warps inside the digit's run, the tile's count, the look-back
-    uint32_t run = 0;
+    // thread d (< RADIX) owns digit d: offsets of the warps inside the digit's run, the tile's count, the look-back
+    uint32_t run = 0, before_tiles = 0;
+    if (tid < RADIX) {
 #pragma unroll
-    for (int k = 0; k < WARPS; ++k) {
-        const uint32_t c = s_cnt[k][tid];
-        s_cnt[k][tid] = run;
-        run += c;
-    }
-    uint32_t before_tiles = 0;
-    {
+        for (int k = 0; k < PASS_WARPS; ++k) {
+            const uint32_t c = s_cnt[k][tid];
+            s_cnt[k][tid] = (unsigned short)run;
+            run += c;
+        }
         uint32_t* col = lookback + tid;                                    // lookback[p * RADIX + d]
         st_volatile(col + int64_t(t) * RADIX, (run & VALUE_MASK) | (t == 0 ? FLAG_PREFIX : FLAG_AGG));
         // eight independent loads in flight per step (the words of tiles p, p-1, .., p-7 of this digit's column); a word that
@@ -196,18 +204,20 @@ __global__ void __launch_bounds__(THREADS) onesweep_pass_kernel(const Rec* __res
         if (t > 0) st_volatile(col + int64_t(t) * RADIX, ((before_tiles + run) & VALUE_MASK) | FLAG_PREFIX);
     }
     int tot;
-    const int digit_start = block_exclusive((int)hist[tid], s_scan, &tot);   // first global index of digit d
-    const int tile_start = block_exclusive((int)run, s_scan, &tot);          // first slot of digit d in the staged tile
-    s_base[tid] = digit_start + (int)before_tiles - tile_start;
-    // slot of a record = tile_start[d] + warp offset + rank; fold tile_start into the warp offsets
+    const int digit_start = block_exclusive<PASS_WARPS>(tid < RADIX ? (int)hist[tid] : 0, s_scan, &tot);   // first global index of digit d
+    const int tile_start = block_exclusive<PASS_WARPS>((int)run, s_scan, &tot);                              // first slot of digit d in the staged tile
+    if (tid < RADIX) {
+        s_base[tid] = digit_start + (int)before_tiles - tile_start;
+        // slot of a record = tile_start[d] + warp offset + rank; fold tile_start into the warp offsets
 #pragma unroll
-    for (int k = 0; k < WARPS; ++k) s_cnt[k][tid] += (uint32_t)tile_start;
+        for (int k = 0; k < PASS_WARPS; ++k) s_cnt[k][tid] = (unsigned short)(s_cnt[k][tid] + tile_start);
+    }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
         if (dig[i] < 256) s_stage[my_cnt[dig[i]] + rank[i]] = rec[i];
     __syncthreads();
-    for (int s = tid; s < tile_n; s += THREADS) {
+    for (int s = tid; s < tile_n; s += PASS_THREADS) {
         const Rec r = s_stage[s];
         const int d = (int)((key_of(r) >> shift) & 255u);
         out[s_base[d] + s] = r;

@@ -76,13 +76,10 @@ def kernels():
     blocks, cur = [], None
     for r in src:
         if r and r[0] == "Kernel Name":
-            cur = {"name": None, "hdr": None, "rows": []}
+            cur = {"name": short(r[1]) if len(r) > 1 else "?", "hdr": None, "rows": []}
             blocks.append(cur)
             continue
         if cur is None:
-            continue
-        if cur["name"] is None:
-            cur["name"] = short(r[0]) if r else "?"
             continue
         if cur["hdr"] is None:
             cur["hdr"] = r
@@ -103,7 +100,7 @@ def kernels():
                 continue
             op = (t[1] if t[0].startswith("@") and len(t) > 1 else t[0]).split(".")[0]
             mix[op] += int(r[ia])
-        stall_cols = [(i, c) for i, c in enumerate(h) if c.startswith("stall_") or c.startswith("Warp Stall Sampling")]
+        stall_cols = [(i, c) for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
         lines += ["", f"### `{b['name']}`: opcode mix (share of {tot} executed warp instructions)", "",
                   ", ".join(f"{op} {c / tot * 100:.1f}%" for op, c in mix.most_common(18))]
         if stall_cols:

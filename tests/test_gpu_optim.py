@@ -33,7 +33,7 @@ def test_selective_adam_updates_only_visible_rows():
             m = b1 * ref_m[k] + (1 - b1) * gk
             v = b2 * ref_v[k] + (1 - b2) * gk * gk
             upd = ref_p[k] - lrs[k] * m / (v.sqrt() + eps)
-            sel = vis.reshape((n,) + (1,) * (gk.dim() - 1))
+            sel = vis.cpu().reshape((n,) + (1,) * (gk.dim() - 1))
             ref_m[k], ref_v[k], ref_p[k] = torch.where(sel, m, ref_m[k]), torch.where(sel, v, ref_v[k]), torch.where(sel, upd, ref_p[k])
     for k, p in params.items():
         st = opt.state[p]
