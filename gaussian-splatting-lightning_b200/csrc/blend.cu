@@ -388,7 +388,8 @@ struct TrSmem {
     static constexpr int VAL_BYTES = ABS ? 16 : 8;              // per (entry, pixel): {go, fac} or {go, fac, |gx|, |gy|}
     static constexpr int VAL_ROW = 32 * VAL_BYTES + 16;         // bytes per entry row of the value tile (+ pad)
     float4 rec[(BLOCK_PIX + 1) * 3];
-    float4 vo[NWARP][32];
+    float4 vo[NWARP][33];                                        // v_image of the warp's pixels; pixel p at slot p + (p >> 4): the two halves
+                                                                 // of a warp read different banks in the same instruction
     unsigned char val[NWARP][GE * VAL_ROW];
     unsigned short list[NWARP][BWD_LIST];
     unsigned char mask[BLOCK_PIX];
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(BLOCK_PIX, ABS ? 3 : 4) blend_bwd_tr_kernel(in
         vo[c] = inside ? __ldg(v_image + pix * pix_stride + c * ch_stride) : 0.f;
         if (bg) bg_dot += __ldg(bg + c) * vo[c];
     }
-    sm.vo[warp][lane] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+    sm.vo[warp][lane + (lane >> 4)] = make_float4(vo[0], vo[1], vo[2], vo[3]);
     const float va = (v_alpha && inside) ? __ldg(v_alpha + pix) : 0.f;
     const float tail = Tf * (va - bg_dot);  // d(out)/d(alpha_i) through everything behind the last contributor
 
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(BLOCK_PIX, ABS ? 3 : 4) blend_bwd_tr_kernel(in
     unsigned char* my_val = sm.val[warp] + lane * VAL_BYTES;      // eval phase: this pixel's value column
     const int re = lane & (GE - 1), rh = lane >> 4;               // reduce phase: entry and pixel half of this lane
     const float4* my_row = reinterpret_cast<const float4*>(sm.val[warp] + re * VAL_ROW + rh * 16 * VAL_BYTES);
-    const float4* my_vo = sm.vo[warp] + rh * 16;
+    const float4* my_vo = sm.vo[warp] + rh * 17;
     // origin of the warp's 8x4 block of pixel samples; the reduce lane's pixels are rows 2 rh, 2 rh + 1 of it
     const float bx0 = ox + float((warp & 1) << 3), by0 = oy + float((warp >> 1) << 2);
     const float hh = float(2 * rh);

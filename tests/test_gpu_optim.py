@@ -15,7 +15,7 @@ def test_selective_adam_updates_only_visible_rows():
     params = {k: torch.nn.Parameter(torch.randn(*s, generator=g).to(DEV)) for k, s in shapes.items()}
     lrs = {"means": 1.6e-4, "shs_rest": 1.25e-4, "opacities": 5e-2, "rotations": 1e-3}
     opt = B200SelectiveAdam().instantiate([{"params": [p], "name": k, "lr": lrs[k]} for k, p in params.items()], lr=1e-3)
-    ref_p = {k: p.detach().clone().double() for k, p in params.items()}
+    ref_p = {k: p.detach().cpu().clone().double() for k, p in params.items()}
     ref_m = {k: torch.zeros_like(v) for k, v in ref_p.items()}
     ref_v = {k: torch.zeros_like(v) for k, v in ref_p.items()}
     b1, b2, eps = 0.9, 0.999, 1e-15
