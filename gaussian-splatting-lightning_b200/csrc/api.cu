@@ -41,7 +41,7 @@ using namespace b200gs;
 extern "C" {
 
 const char* b200gs_last_error(void) { return g_error; }
-int b200gs_version(void) { return 210; }
+int b200gs_version(void) { return 220; }
 int64_t b200gs_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int b200gs_project_fwd(const B200gsView* view, int64_t n, const float* means, const float* scales, const float* quats,
@@ -91,6 +91,22 @@ int b200gs_project_fwd_raw(const B200gsView* view, int64_t n, const float* means
     }
     return launch_project_fwd_raw(*view, n, means, log_scales, raw_quats, opacity_logits, shs_dc, shs_rest, anti_aliased, xy, depth,
                                   radii, conic, comp, tiles, nullptr, rgb, clamped, opacity_out, (cudaStream_t)stream);
+}
+
+int b200gs_project_fwd_rows(const B200gsView* view, int64_t n, const float* means, const float* log_scales, const float* raw_quats,
+                            const float* opacity_logits, const float* shs_dc, const float* shs_rest, int32_t anti_aliased, float* rows,
+                            int32_t* radii, uint8_t* clamped, int32_t* tiles, void* stream) {
+    int rc = check_view(view, true);
+    if (rc) return rc;
+    B200GS_CHECK_ARG(n >= 0, "n < 0");
+    if (n > 0) {
+        B200GS_CHECK_ARG(means && log_scales && raw_quats && opacity_logits && shs_dc, "NULL input pointer");
+        B200GS_CHECK_ARG(view->sh_stride == 1 || shs_rest, "shs_rest required when sh_stride > 1");
+        B200GS_CHECK_ARG(rows && radii && clamped, "NULL output pointer");
+        B200GS_CHECK_ARG((reinterpret_cast<uintptr_t>(rows) & 15u) == 0, "rows must be 16-byte aligned");
+    }
+    return launch_project_fwd_raw(*view, n, means, log_scales, raw_quats, opacity_logits, shs_dc, shs_rest, anti_aliased, nullptr, nullptr,
+                                  radii, nullptr, nullptr, tiles, nullptr, nullptr, clamped, nullptr, (cudaStream_t)stream, rows);
 }
 
 int b200gs_project_bwd_raw(const B200gsView* view, int64_t n, const float* means, const float* log_scales, const float* raw_quats,
@@ -422,12 +438,13 @@ int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int
 
 int b200gs_blend_bwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                           const float* rows, const float* bg, const float* final_T, const int32_t* n_contrib, const float* v_image,
-                          int64_t pix_stride, int64_t ch_stride, const float* v_alpha, float* v_rows, void* stream) {
+                          int64_t pix_stride, int64_t ch_stride, const float* v_alpha, float grad_scale_x, float grad_scale_y,
+                          float* v_rows, void* stream) {
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
     B200GS_CHECK_ARG(width > 0 && height > 0 && tile_ranges && final_T && n_contrib && v_image && v_rows, "bad argument");
     return launch_blend_bwd(mode, width, height, 3, tile_ranges, sorted_ids, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY,
                             rows + B200GS_ROW_CONIC, rows + B200GS_ROW_OPACITY, rows + B200GS_ROW_RGB, bg, final_T, n_contrib, v_image,
-                            pix_stride, ch_stride, v_alpha, 1.0f, 1.0f, v_rows + B200GS_ROW_XY, v_rows + B200GS_ROW_CONIC,
+                            pix_stride, ch_stride, v_alpha, grad_scale_x, grad_scale_y, v_rows + B200GS_ROW_XY, v_rows + B200GS_ROW_CONIC,
                             v_rows + B200GS_ROW_OPACITY, v_rows + B200GS_ROW_RGB, nullptr, (cudaStream_t)stream);
 }
 

@@ -82,7 +82,7 @@ int launch_project_bwd(const B200gsView& v, int64_t n, const float* means, const
 int launch_project_fwd_raw(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
                            const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased, float* xy,
                            float* depth, int32_t* radii, float* conic, float* comp, int32_t* tiles, float* cov3d, float* rgb,
-                           uint8_t* clamped, float* opac_out, cudaStream_t s);
+                           uint8_t* clamped, float* opac_out, cudaStream_t s, float* rows = nullptr);
 int launch_project_bwd_raw(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
                            const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased,
                            const int32_t* radii, const uint8_t* clamped, const float* v_xy, const float* v_depth,

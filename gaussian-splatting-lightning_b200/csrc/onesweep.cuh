@@ -42,26 +42,49 @@ __device__ __forceinline__ uint32_t key_of(const uint4& r) { return r.w; }
 // ---- chained scan --------------------------------------------------------------------------------------------------
 // Exclusive prefix of one 30-bit value per tile over the tiles in ticket order.  `state[t]` must be zero before the launch.
 // Called by ALL 32 lanes of ONE warp (same arguments); returns (to every lane) the sum of the values of tiles 0..t-1.
-// The look-back is warp-wide: 32 predecessors per step (lane l polls tile p - l), the walk stops at the nearest tile that
-// has already published its inclusive prefix — in the first wave, when every resident tile starts at once and none has a
-// prefix yet, tile t needs t/32 round trips to L2 instead of t.
+// The look-back is warp-wide and four words deep: 128 predecessors per step (lane l loads tiles p - l - 32 j, j = 0..3, all four
+// loads in flight together); the walk stops at the nearest tile that has already published its inclusive prefix and resumes at
+// the first word that is not published yet.  When a whole wave of tiles starts at once none has a prefix yet, and tile t needs
+// t / 128 round trips to L2 (with one predecessor per step: t; measured: profiles/round2_call2_launches.md).
 __device__ __forceinline__ uint32_t chained_exclusive(uint32_t* state, int t, uint32_t value) {
+    constexpr int DEPTH = 4;
     const unsigned lane = threadIdx.x & 31u;
     if (lane == 0) st_volatile(state + t, (value & VALUE_MASK) | (t == 0 ? FLAG_PREFIX : FLAG_AGG));
-    uint32_t excl = 0;
-    for (int p = t - 1; p >= 0; p -= 32) {
-        const int idx = p - (int)lane;
-        const uint32_t v = idx >= 0 ? wait_published(state + idx) : FLAG_PREFIX;
-        const unsigned has_prefix = __ballot_sync(0xffffffffu, (v & FLAG_PREFIX) != 0u);
-        const int first = has_prefix ? __ffs(has_prefix) - 1 : 31;          // nearest tile with an inclusive prefix: stop there
-        uint32_t c = ((int)lane <= first) ? (v & VALUE_MASK) : 0u;
+    uint32_t acc = 0;                 // per-lane partial sum, reduced once at the end
+    bool done = (t == 0);
+    unsigned spins = 0;
+    int depth = 1;                    // 32 words in the first step, then 64, 128, 128, ..
+    for (int p = t - 1; !done;) {
+        uint32_t v[DEPTH];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        excl += c;
-        if (has_prefix) break;
+        for (int j = 0; j < DEPTH; ++j) {
+            const int idx = p - (int)lane - 32 * j;
+            v[j] = (j >= depth) ? 0u : (idx >= 0 ? ld_volatile(state + idx) : FLAG_PREFIX);      // before tile 0: an empty prefix
+        }
+        int consumed = 0;
+        bool stalled = false;
+#pragma unroll
+        for (int j = 0; j < DEPTH; ++j) {
+            if (!done && !stalled && j < depth) {
+                const unsigned pub = __ballot_sync(0xffffffffu, (v[j] >> 30) != 0u);
+                const unsigned pre = __ballot_sync(0xffffffffu, (v[j] & FLAG_PREFIX) != 0u);
+                const int n_pub = (pub == 0xffffffffu) ? 32 : __ffs(~pub) - 1;     // run of published words, nearest first
+                const int first_pre = pre ? __ffs(pre) - 1 : 32;
+                const int take = min(n_pub, first_pre + 1);
+                acc += ((int)lane < take) ? (v[j] & VALUE_MASK) : 0u;
+                consumed += take;
+                done = first_pre < n_pub;
+                stalled = !done && n_pub < 32;
+            }
+        }
+        p -= consumed;
+        if (!stalled) depth = min(2 * depth, DEPTH);
+        if (consumed == 0 && ++spins > (1u << 27)) asm volatile("trap;");   // a word that is never published: a logic error, not a hang
     }
-    if (lane == 0 && t > 0) st_volatile(state + t, ((excl + value) & VALUE_MASK) | FLAG_PREFIX);
-    return excl;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0 && t > 0) st_volatile(state + t, ((acc + value) & VALUE_MASK) | FLAG_PREFIX);
+    return acc;
 }
 
 // block-wide exclusive scan of one int per thread (NW warps); returns the exclusive prefix, *total = block sum
@@ -163,8 +186,9 @@ __global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Re
         rank[i] = before + lt;
     }
     __syncthreads();
-    // thread d (< RADIX) owns digit d: offsets of the warps inside the digit's run, the tile's count, the look-back
-    uint32_t run = 0, before_tiles = 0;
+    // thread d (< RADIX) owns digit d: offsets of the warps inside the digit's run, the tile's count
+    uint32_t run = 0;
+    uint32_t* col = lookback + (tid & (RADIX - 1));                        // lookback[p * RADIX + d]
     if (tid < RADIX) {
 #pragma unroll
         for (int k = 0; k < PASS_WARPS; ++k) {
@@ -172,28 +196,48 @@ __global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Re
             s_cnt[k][tid] = (unsigned short)run;
             run += c;
         }
-        uint32_t* col = lookback + tid;                                    // lookback[p * RADIX + d]
         st_volatile(col + int64_t(t) * RADIX, (run & VALUE_MASK) | (t == 0 ? FLAG_PREFIX : FLAG_AGG));
-        // eight independent loads in flight per step (the words of tiles p, p-1, .., p-7 of this digit's column); a word that
-        // is not published yet ends the batch, the walk resumes there
+    }
+    int tot;
+    const int tile_start = block_exclusive<PASS_WARPS>((int)run, s_scan, &tot);                              // first slot of digit d in the staged tile
+    if (tid < RADIX) {
+        // slot of a record = tile_start[d] + warp offset + rank; fold tile_start into the warp offsets
+#pragma unroll
+        for (int k = 0; k < PASS_WARPS; ++k) s_cnt[k][tid] = (unsigned short)(s_cnt[k][tid] + tile_start);
+    }
+    __syncthreads();
+    // the records go to their slot of the staged tile BEFORE the look-back: the slot does not depend on the other tiles, and the
+    // look-back then has the registers of the records for its loads
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+        if (dig[i] < 256) s_stage[my_cnt[dig[i]] + rank[i]] = rec[i];
+    // look-back over the preceding tiles' words of digit d, `width` independent loads in flight per step, width = 4, 8, 16, 32, 32, ..
+    // When a whole wave of tiles starts at once no tile has a prefix yet and tile t has to sum the counts of all its predecessors:
+    // with a fixed 8 per step that was 20 dependent round trips to L2 = 14 of the 20 us of a pass over 0.65 M records
+    // (profiles/round2_call3_launches.md).  In the steady state of a long pass the nearest predecessor's prefix is usually out
+    // already, and a fixed 32 per step wasted 4x the L2 requests (measured: +0.08 ms per binning at 2.3 M records) — hence the
+    // doubling.  A word that is not published yet ends the batch; the walk resumes there.
+    constexpr int LB = 32;
+    uint32_t before_tiles = 0;
+    if (tid < RADIX) {
+        int width = 4;
         for (int p = t - 1; p >= 0;) {
-            uint32_t v[8];
+            uint32_t v[LB];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = (p - k >= 0) ? ld_volatile(col + int64_t(p - k) * RADIX) : FLAG_PREFIX;
+            for (int k = 0; k < LB; ++k) v[k] = (k >= width) ? 0u : ((p - k >= 0) ? ld_volatile(col + int64_t(p - k) * RADIX) : FLAG_PREFIX);
             int used = 0;
-            bool done = false;
+            bool done = false, open = true;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (!done && used == k) {
-                    if ((v[k] >> 30) != 0u) {
-                        before_tiles += v[k] & VALUE_MASK;
-                        used = k + 1;
-                        done = (v[k] & FLAG_PREFIX) != 0u;
-                    }
-                }
+            for (int k = 0; k < LB; ++k) {
+                const bool pub = (v[k] >> 30) != 0u;                       // words past `width` read as unpublished
+                open = open && !done && pub;                               // still inside the run of published words, before any prefix
+                before_tiles += open ? (v[k] & VALUE_MASK) : 0u;
+                used += open ? 1 : 0;
+                done = done || (open && (v[k] & FLAG_PREFIX) != 0u);
             }
             if (done) break;
             p -= used;
+            if (used == width) width = min(2 * width, LB);
             if (used == 0 && p >= 0) {     // the nearest word is not out yet: wait for it, then go on from the next one
                 const uint32_t w0 = wait_published(col + int64_t(p) * RADIX);
                 before_tiles += w0 & VALUE_MASK;
@@ -203,19 +247,8 @@ __global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Re
         }
         if (t > 0) st_volatile(col + int64_t(t) * RADIX, ((before_tiles + run) & VALUE_MASK) | FLAG_PREFIX);
     }
-    int tot;
     const int digit_start = block_exclusive<PASS_WARPS>(tid < RADIX ? (int)hist[tid] : 0, s_scan, &tot);   // first global index of digit d
-    const int tile_start = block_exclusive<PASS_WARPS>((int)run, s_scan, &tot);                              // first slot of digit d in the staged tile
-    if (tid < RADIX) {
-        s_base[tid] = digit_start + (int)before_tiles - tile_start;
-        // slot of a record = tile_start[d] + warp offset + rank; fold tile_start into the warp offsets
-#pragma unroll
-        for (int k = 0; k < PASS_WARPS; ++k) s_cnt[k][tid] = (unsigned short)(s_cnt[k][tid] + tile_start);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < IPT; ++i)
-        if (dig[i] < 256) s_stage[my_cnt[dig[i]] + rank[i]] = rec[i];
+    if (tid < RADIX) s_base[tid] = digit_start + (int)before_tiles - tile_start;
     __syncthreads();
     for (int s = tid; s < tile_n; s += PASS_THREADS) {
         const Rec r = s_stage[s];

@@ -265,10 +265,16 @@ struct ProjOut {
     float2* xy; float* depth; int32_t* radii; float* conic; float* comp; int32_t* tiles; float* cov3d; float* rgb; uint8_t* clamped;
 };
 
-// Projection of Gaussian (p, sc, q) into view v; writes the outputs at index o and returns the visibility.
+// What one (view, Gaussian) projection produces (all zero when the Gaussian is culled)
+struct ProjVals {
+    float px, py, depth, cA, cB, cC, comp, opac;
+    int32_t radius, ntiles;
+};
+
+// Projection of Gaussian (p, sc, q) into view v -> pv; returns the visibility.  cov3d (optional) is written at index o.
 template <bool GSPLAT, bool RAW>
 __device__ __forceinline__ bool project_one(const B200gsView& v, const RawIO& raw, int64_t i, int64_t o, const float* p, const double* sc,
-                                            const double* q, const ProjOut& out, float* opac_out) {
+                                            const double* q, float* cov3d_out, ProjVals& pv) {
     typedef double R;
     Proj<R> g;
     project_geometry<GSPLAT, R>(v, p, sc, q, g);
@@ -305,34 +311,39 @@ __device__ __forceinline__ bool project_one(const B200gsView& v, const RawIO& ra
     const int ntiles = (x1 - x0) * (y1 - y0);
     vis = vis && (ntiles > 0) && (radius > 0.f);  // NaN radius compares false
 
+    pv.px = pv.py = pv.depth = pv.cA = pv.cB = pv.cC = pv.comp = pv.opac = 0.f;
+    pv.radius = pv.ntiles = 0;
     if (vis) {
-        out.xy[o] = make_float2(px, py);
-        out.depth[o] = float(g.tz);
-        out.radii[o] = (int32_t)radius;
-        out.conic[3 * o + 0] = float(g.c * inv_det);
-        out.conic[3 * o + 1] = float(-g.b * inv_det);
-        out.conic[3 * o + 2] = float(g.a * inv_det);
-        if (out.tiles) out.tiles[o] = ntiles;
-        const float comp = GSPLAT ? float(sqrt(fmax(g.det0 * inv_det, R(0)))) : 1.0f;
-        if (out.comp) out.comp[o] = comp;
+        pv.px = px; pv.py = py;
+        pv.depth = float(g.tz);
+        pv.radius = (int32_t)radius;
+        pv.cA = float(g.c * inv_det);
+        pv.cB = float(-g.b * inv_det);
+        pv.cC = float(g.a * inv_det);
+        pv.ntiles = ntiles;
+        pv.comp = GSPLAT ? float(sqrt(fmax(g.det0 * inv_det, R(0)))) : 1.0f;
         if (RAW) {
             const float op = 1.0f / (1.0f + expf(-__ldg(raw.opac_in + i)));
-            opac_out[o] = (GSPLAT && raw.anti_aliased) ? op * comp : op;
+            pv.opac = (GSPLAT && raw.anti_aliased) ? op * pv.comp : op;
         }
-    } else {
-        if (RAW) opac_out[o] = 0.f;
-        out.xy[o] = make_float2(0.f, 0.f);
-        out.depth[o] = 0.f;
-        out.radii[o] = 0;
-        out.conic[3 * o + 0] = 0.f; out.conic[3 * o + 1] = 0.f; out.conic[3 * o + 2] = 0.f;
-        if (out.tiles) out.tiles[o] = 0;
-        if (out.comp) out.comp[o] = 0.f;
     }
-    if (out.cov3d) {
+    if (cov3d_out) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) out.cov3d[6 * o + k] = vis ? float(g.S3[k]) : 0.f;
+        for (int k = 0; k < 6; ++k) cov3d_out[6 * o + k] = vis ? float(g.S3[k]) : 0.f;
     }
     return vis;
+}
+
+// separate-array outputs of one projection at element o
+template <bool RAW>
+__device__ __forceinline__ void store_soa(const ProjOut& out, float* opac_out, int64_t o, const ProjVals& pv) {
+    out.xy[o] = make_float2(pv.px, pv.py);
+    out.depth[o] = pv.depth;
+    out.radii[o] = pv.radius;
+    out.conic[3 * o + 0] = pv.cA; out.conic[3 * o + 1] = pv.cB; out.conic[3 * o + 2] = pv.cC;
+    if (out.tiles) out.tiles[o] = pv.ntiles;
+    if (out.comp) out.comp[o] = pv.radius > 0 ? pv.comp : 0.f;
+    if (RAW) opac_out[o] = pv.opac;
 }
 
 // max(SH colour + 0.5, 0) of a visible Gaussian seen from v.campos; bit c of *cl set where channel c was clamped
@@ -361,33 +372,47 @@ __device__ __forceinline__ void sh_color_one(const B200gsView& v, const float* p
     if (bc < 0.f) { bc = 0.f; cl |= 4; }
 }
 
+// rows_out (raw mode only): instead of the separate arrays, ONE [n,12] row per Gaussian (xy 0..1, depth 2, conic 3..5, compensation 6,
+// blend opacity 7, rgb 8..10, radius bits 11) — three 128-bit stores; the binning and the blend kernels read the rows in place (one
+// 48-byte record per splat instead of four separate sectors).  radii_out / clamped_out (what K8 needs) are still written.
 template <bool GSPLAT, bool RAW, int MC>
-__global__ void __launch_bounds__(256) project_fwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
+__global__ void __launch_bounds__(256, 3) project_fwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
                                                           const float* __restrict__ means, const float* __restrict__ scales,
                                                           const float* __restrict__ quats, const float* __restrict__ shs,
                                                           float2* __restrict__ xy_out, float* __restrict__ depth_out,
                                                           int32_t* __restrict__ radii_out, float* __restrict__ conic_out,
                                                           float* __restrict__ comp_out, int32_t* __restrict__ tiles_out,
                                                           float* __restrict__ cov3d_out, float* __restrict__ rgb_out,
-                                                          uint8_t* __restrict__ clamped_out) {
+                                                          uint8_t* __restrict__ clamped_out, float* __restrict__ rows_out) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
     double sc[3], q[4], inv_qn;
     load_scale_quat<RAW, double>(scales, quats, i, sc, q, &inv_qn);
     const ProjOut out{xy_out, depth_out, radii_out, conic_out, comp_out, tiles_out, cov3d_out, rgb_out, clamped_out};
-    const bool vis = project_one<GSPLAT, RAW>(v, raw, i, i, p, sc, q, out, raw.opac_out);
+    ProjVals pv;
+    const bool vis = project_one<GSPLAT, RAW>(v, raw, i, i, p, sc, q, cov3d_out, pv);
+    const bool rows = RAW && rows_out != nullptr;
+    if (!rows) store_soa<RAW>(out, raw.opac_out, i, pv);
+    float r = 0.f, gc = 0.f, bc = 0.f;
+    uint8_t cl = 0;
     if (shs != nullptr) {
-        float r = 0.f, gc = 0.f, bc = 0.f;
-        uint8_t cl = 0;
         if (vis) {
             const int deg = v.sh_degree;
             float sh[MC * 3];
             load_sh_any<RAW, MC>(shs, raw.shs_rest, i, v.sh_stride, (deg + 1) * (deg + 1), sh);
             sh_color_one<MC>(v, p, sh, r, gc, bc, cl);
         }
-        rgb_out[3 * i + 0] = r; rgb_out[3 * i + 1] = gc; rgb_out[3 * i + 2] = bc;
+        if (!rows) { rgb_out[3 * i + 0] = r; rgb_out[3 * i + 1] = gc; rgb_out[3 * i + 2] = bc; }
         clamped_out[i] = cl;
+    }
+    if (rows) {
+        float4* row = reinterpret_cast<float4*>(rows_out + i * B200GS_ROW_FLOATS);
+        radii_out[i] = pv.radius;
+        if (tiles_out) tiles_out[i] = pv.ntiles;
+        row[0] = make_float4(pv.px, pv.py, pv.depth, pv.cA);             // zeros when culled (the mean2D columns are handed out)
+        if (vis) row[1] = make_float4(pv.cB, pv.cC, pv.comp, pv.opac);
+        row[2] = make_float4(r, gc, bc, __int_as_float(pv.radius));      // radius 0 = culled: all the kernels look at of such a row
     }
 }
 
@@ -413,8 +438,11 @@ __global__ void __launch_bounds__(256) project_fwd_multi_kernel(const __grid_con
     const ProjOut out{xy_out, depth_out, radii_out, conic_out, nullptr, nullptr, nullptr, rgb_out, clamped_out};
     unsigned vismask = 0;
 #pragma unroll 1
-    for (int j = 0; j < nviews; ++j)
-        if (project_one<true, true>(vp.v[j], raw, i, int64_t(j) * n + i, p, sc, q, out, raw.opac_out)) vismask |= 1u << j;
+    for (int j = 0; j < nviews; ++j) {
+        ProjVals pv;
+        if (project_one<true, true>(vp.v[j], raw, i, int64_t(j) * n + i, p, sc, q, nullptr, pv)) vismask |= 1u << j;
+        store_soa<true>(out, raw.opac_out, int64_t(j) * n + i, pv);
+    }
     float sh[MC * 3];
     if (vismask) {
         const int deg = vp.v[0].sh_degree;
@@ -901,19 +929,19 @@ int launch_project_fwd(const B200gsView& v, int64_t n, const float* means, const
                        const float* shs, float* xy, float* depth, int32_t* radii, float* conic, float* comp,
                        int32_t* tiles, float* cov3d, float* rgb, uint8_t* clamped, cudaStream_t s) {
     return launch_project_fwd_raw(v, n, means, scales, quats, nullptr, shs, nullptr, 0, xy, depth, radii, conic, comp, tiles, cov3d,
-                                  rgb, clamped, nullptr, s);
+                                  rgb, clamped, nullptr, s, nullptr);
 }
 
 int launch_project_fwd_raw(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
                            const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased, float* xy,
                            float* depth, int32_t* radii, float* conic, float* comp, int32_t* tiles, float* cov3d, float* rgb,
-                           uint8_t* clamped, float* opac_out, cudaStream_t s) {
+                           uint8_t* clamped, float* opac_out, cudaStream_t s, float* rows) {
     if (n == 0) return B200GS_OK;
     const int threads = 256;
     const unsigned blocks = (unsigned)div_up64(n, threads);
-    const bool raw_mode = opac_out != nullptr;
+    const bool raw_mode = opac_out != nullptr || rows != nullptr;
     RawIO raw{opac_logits, shs_rest, opac_out, nullptr, nullptr, nullptr, anti_aliased, nullptr, nullptr, 0};
-#define B200GS_PF_ARGS v, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth, radii, conic, comp, tiles, cov3d, rgb, clamped
+#define B200GS_PF_ARGS v, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth, radii, conic, comp, tiles, cov3d, rgb, clamped, rows
 #define B200GS_PF_LAUNCH(MC)                                                                                    \
     do {                                                                                                         \
         if (v.mode == B200GS_MODE_GSPLAT) {                                                                      \

@@ -18,7 +18,9 @@ Mirrors ``internal/renderers/gsplat_distributed_renderer.py`` (SURVEY.md ยง3d, ย
 The distributed image is bit-identical to the single-GPU gsplat-mode render of the unsharded model
 (tests/test_gpu_distributed.py).  A per-pixel reduce of partial images would NOT be (SURVEY ยง0.4).
 """
+import os
 import threading
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -280,7 +282,7 @@ class _ShardStep:
     """What the two autograd nodes of one sharded step share (buffers of the projection, the exchange and the raster)."""
     __slots__ = ("views", "cam_views", "rank", "world", "group", "n", "aa", "sh_degree", "peer", "xy", "depth", "conic", "rgb", "opac", "radii",
                  "clamped", "row_index", "fixed_cap", "counts", "recv", "binning", "final_T", "n_contrib", "hw", "v_rows", "v_send", "parity",
-                 "peer_mode")
+                 "peer_mode", "xys_refs", "want_xy")
 
 
 def _project_shard(st: _ShardStep, means, log_scales, raw_quats, ol, shs_dc, shs_rest):
@@ -501,8 +503,21 @@ class _ExchangeRasterize(torch.autograd.Function):
             v_recv = torch.zeros_like(st.recv)
         with ops._stage("blend_bwd"):
             check(L.b200gs_blend_bwd_rows(MODE_GSPLAT, W, H, ptr(st.binning.tile_ranges), ptr(st.binning.sorted_ids), ptr(st.recv), ptr(bg),
-                                          ptr(st.final_T), ptr(st.n_contrib), ptr(v_image), 3, 1, None, ptr(v_recv), stream), "b200gs_blend_bwd_rows")
+                                          ptr(st.final_T), ptr(st.n_contrib), ptr(v_image), 3, 1, None, 1.0, 1.0, ptr(v_recv), stream), "b200gs_blend_bwd_rows")
         grads = []
+
+        def xy_grad(j, rows, shift):
+            """d loss / d mean2D of camera j's projections = columns 0..1 of their gradient rows.  Only materialised when somebody
+            will read it (`retain_grad()` on the per-camera xys, as the distributed density controller does, or want_xy_grads): node
+            A's K8 reads the full rows itself.  Gather without a host sync (no boolean-mask indexing)."""
+            ref = st.xys_refs[j]() if st.xys_refs is not None else None
+            if not st.want_xy and (ref is None or not ref.retains_grad):
+                return None
+            idx = st.row_index[j * n:(j + 1) * n]
+            vis = (st.radii[j * n:(j + 1) * n] > 0) & (idx >= 0)
+            k = (idx.long() + shift).clamp_(0, rows.shape[0] - 1)
+            return rows[:, 0:2][k] * vis.unsqueeze(1)
+
         if peer_mode:
             # one barrier: every camera owner's K7 is done.  Entry (j, i) with row_index = j*cap + k lives at row rank*cap + k of owner
             # j's buffer: shift each base pointer so that K8 can index it with row_index directly.
@@ -512,14 +527,7 @@ class _ExchangeRasterize(torch.autograd.Function):
             st.v_rows = [pe.peers["vrecv"][j] + (rank * cap - j * cap) * ROW_FLOATS * 4 for j in range(world)]
             st.v_send = v_recv
             for j in range(world):
-                g = torch.zeros(n, 2, dtype=torch.float32, device=dev)
-                vis = st.radii[j * n:(j + 1) * n] > 0
-                k = st.row_index[j * n:(j + 1) * n][vis].long() - j * cap
-                ok = k >= 0
-                src = pe.peer_tensor("vrecv", j, world * cap)
-                sel = torch.nonzero(vis).reshape(-1)[ok]
-                g[sel] = src[rank * cap + k[ok], 0:2]
-                grads.append(g)
+                grads.append(xy_grad(j, pe.peer_tensor("vrecv", j, world * cap), rank * cap - j * cap))
         else:
             if cap:
                 v_send = torch.empty_like(v_recv)
@@ -531,11 +539,7 @@ class _ExchangeRasterize(torch.autograd.Function):
             st.v_send = v_send
             st.v_rows = [v_send.data_ptr()] * world
             for j in range(world):
-                g = torch.zeros(n, 2, dtype=torch.float32, device=dev)
-                idx = st.row_index[j * n:(j + 1) * n]
-                vis = (st.radii[j * n:(j + 1) * n] > 0) & (idx >= 0)
-                g[vis] = v_send[idx[vis].long(), 0:2]
-                grads.append(g)
+                grads.append(xy_grad(j, v_send, 0))
         st.recv = st.binning = st.final_T = st.n_contrib = None
         return (None, None) + tuple(grads)
 
@@ -617,7 +621,8 @@ class B200DistributedRenderer(Renderer):
         self.anti_aliased = self.config.anti_aliased
         self.group = group
         self.fused = self.config.fused
-        self.peer_exchange = self.config.peer_exchange
+        # B200GS_PEER_EXCHANGE=0: measurement switch (NCCL all-to-alls instead of the peer-mapped buffers), same on every rank
+        self.peer_exchange = self.config.peer_exchange and os.environ.get("B200GS_PEER_EXCHANGE", "1") != "0"
         self.want_xy_grads = want_xy_grads   # kept for callers of the previous interface: the per-camera gradients are `.grad` of the xys now
         self.cache_cameras = cache_cameras   # False when camera poses are optimised (the packed host view is cached on the camera)
         self.world_size, self.global_rank = 1, 0
@@ -705,7 +710,9 @@ class B200DistributedRenderer(Renderer):
         st.aa, st.sh_degree = bool(self.anti_aliased), int(pc.active_sh_degree)
         st.peer = _peer_exchange(self.group, dev) if (self.peer_exchange and bg_color.is_cuda and dist.get_backend(self.group) == "nccl") else None
         st.v_rows = st.v_send = None
+        st.xys_refs, st.want_xy = None, bool(self.want_xy_grads)
         xys = _ProjectShard.apply(raw["means"], raw["scales"], raw["rotations"], raw["opacities"], raw["shs_dc"], raw["shs_rest"], st)
+        st.xys_refs = [weakref.ref(x) for x in xys]
         n = st.n
         projection_results_list = [(st.radii[j * n:(j + 1) * n], xys[j], st.depth[j * n:(j + 1) * n], st.conic[j * n:(j + 1) * n], None)
                                    for j in range(world)]

@@ -265,25 +265,26 @@ def bin_rows(mode: int, width: int, height: int, rows: torch.Tensor, cull: bool 
     return _bin(("rows", mode, width, height, bool(cull)), mode, width, height, n, rows.device, bool(cull), lazy, count_call)
 
 
-def blend_forward_rows(mode, width, height, binning: Binning, rows, bg):
-    """K6 on rows -> image [H,W,3], final_T, n_contrib."""
+def blend_forward_rows(mode, width, height, binning: Binning, rows, bg, planar=False):
+    """K6 on rows -> image [H,W,3] (planar: [3,H,W]), final_T, n_contrib."""
     L = lib()
     dev = rows.device
-    image = torch.empty(height, width, 3, dtype=torch.float32, device=dev)
+    image = torch.empty((3, height, width) if planar else (height, width, 3), dtype=torch.float32, device=dev)
     final_T = torch.empty(height, width, dtype=torch.float32, device=dev)
     n_contrib = torch.empty(height, width, dtype=torch.int32, device=dev)
+    pix_stride, ch_stride = (1, height * width) if planar else (3, 1)
     with _stage("blend_fwd"):
         check(L.b200gs_blend_fwd_rows(mode, width, height, ptr(binning.tile_ranges), ptr(binning.sorted_ids), ptr(rows), ptr(bg), ptr(image),
-                                      3, 1, ptr(final_T), ptr(n_contrib), None, _stream()), "b200gs_blend_fwd_rows")
+                                      pix_stride, ch_stride, ptr(final_T), ptr(n_contrib), None, _stream()), "b200gs_blend_fwd_rows")
     return image, final_T, n_contrib
 
 
-def bin_and_blend_rows(mode, width, height, rows, bg, cull=True):
+def bin_and_blend_rows(mode, width, height, rows, bg, cull=True, planar=False):
     binning = bin_rows(mode, width, height, rows, cull, lazy=True)
-    out = blend_forward_rows(mode, width, height, binning, rows, bg)
+    out = blend_forward_rows(mode, width, height, binning, rows, bg, planar)
     if not binning.resolve():
         binning = bin_rows(mode, width, height, rows, cull, lazy=False)
-        out = blend_forward_rows(mode, width, height, binning, rows, bg)
+        out = blend_forward_rows(mode, width, height, binning, rows, bg, planar)
     return binning, out
 
 
@@ -492,9 +493,14 @@ def project_backward_raw(view: B200gsView, means, log_scales, raw_quats, opac_lo
     return v_means, v_ls, v_q, v_ol, v_dc, v_rest
 
 
-class _RasterizeVanillaRaw(torch.autograd.Function):
+class _RasterizeRaw(torch.autograd.Function):
+    """The whole renderer step as ONE autograd node on the model's RAW parameters, either constant set: K1 (activations + SH fused)
+    writes one [N,12] row per Gaussian, K2-K6 read the rows in place; backward: K7 accumulates [N,12] gradient rows (128-bit
+    reductions), K8 reads them in place.  `means2D` is the viewspace-points tensor of the renderer contract ([N,3] zeros in vanilla
+    mode, [N,2] in gsplat mode where it is also filled with the projected means): its `.grad` receives d loss / d mean2D."""
+
     @staticmethod
-    def forward(ctx, means3D, means2D, shs_dc, shs_rest, opacity_logits, log_scales, raw_quats, bg, view: B200gsView):
+    def forward(ctx, mode, means3D, means2D, shs_dc, shs_rest, opacity_logits, log_scales, raw_quats, bg, view: B200gsView, anti_aliased):
         means3D = _f32c(means3D, "means3D")
         log_scales = _f32c(log_scales, "scales")
         raw_quats = _f32c(raw_quats, "rotations")
@@ -504,34 +510,43 @@ class _RasterizeVanillaRaw(torch.autograd.Function):
         bg = _f32c(bg, "bg")
         view = _copy_view(view, sh_stride=int(shs_dc.shape[1] + shs_rest.shape[1]))
         W, H = view.width, view.height
-        xy, depth, radii, conic, _, tiles, rgb, clamped, opac = project_forward_raw(view, means3D, log_scales, raw_quats, ol, shs_dc,
-                                                                                    shs_rest)
-        binning, (image, final_T, n_contrib, _) = bin_and_blend(MODE_VANILLA, W, H, xy, depth, radii, conic, opac, rgb, bg, True, False)
-        ctx.view = view
+        n, dev = means3D.shape[0], means3D.device
+        rows = torch.empty(n, ROW_FLOATS, dtype=torch.float32, device=dev)
+        radii = torch.empty(n, dtype=torch.int32, device=dev)
+        clamped = torch.empty(n, dtype=torch.uint8, device=dev)
+        with _stage("project_fwd"):
+            check(lib().b200gs_project_fwd_rows(ctypes.byref(view), n, ptr(means3D), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc),
+                                                ptr(shs_rest), int(bool(anti_aliased)), ptr(rows), ptr(radii), ptr(clamped), None, _stream()),
+                  "b200gs_project_fwd_rows")
+        binning, (image, final_T, n_contrib) = bin_and_blend_rows(mode, W, H, rows, bg, True, mode == MODE_VANILLA)
+        if mode == MODE_GSPLAT:
+            means2D.detach()[:, :2].copy_(rows[:, 0:2])     # the gsplat renderers hand the projected means out as `viewspace_points`
+        ctx.view, ctx.mode, ctx.aa = view, mode, bool(anti_aliased)
         ctx.binning = binning
         ctx.means2D_shape = tuple(means2D.shape)
         ctx.opac_shape = tuple(opacity_logits.shape)
-        ctx.save_for_backward(means3D, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, xy, conic, radii, clamped, rgb, opac,
-                              final_T, n_contrib)
+        ctx.save_for_backward(means3D, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, rows, radii, clamped, final_T, n_contrib)
         ctx.mark_non_differentiable(radii)
         return image, radii
 
     @staticmethod
     def backward(ctx, v_image, _v_radii):
-        (means3D, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, xy, conic, radii, clamped, rgb, opac, final_T,
-         n_contrib) = ctx.saved_tensors
-        view = ctx.view
+        means3D, log_scales, raw_quats, ol, shs_dc, shs_rest, bg, rows, radii, clamped, final_T, n_contrib = ctx.saved_tensors
+        view, mode = ctx.view, ctx.mode
         W, H = view.width, view.height
         v_image = _f32c(v_image, "grad_image")
-        # K7 accumulates into one zero-filled [N,12] gradient row buffer (128-bit reductions), K8 reads the rows in place
         n = means3D.shape[0]
         dev = means3D.device
         v_rows = torch.zeros(n, ROW_FLOATS, dtype=torch.float32, device=dev)
         L = lib()
+        if mode == MODE_VANILLA:      # [3,H,W] image, mean2D gradient in NDC units (the vanilla rasterizer's convention)
+            pix_stride, ch_stride, gsx, gsy = 1, H * W, 0.5 * W, 0.5 * H
+        else:                         # [H,W,3] image, mean2D gradient in pixels
+            pix_stride, ch_stride, gsx, gsy = 3, 1, 1.0, 1.0
         with _stage("blend_bwd"):
-            check(L.b200gs_blend_bwd_to_rows(MODE_VANILLA, W, H, ptr(ctx.binning.tile_ranges), ptr(ctx.binning.sorted_ids), ptr(xy), ptr(conic),
-                                             ptr(opac), ptr(rgb), ptr(bg), ptr(final_T), ptr(n_contrib), ptr(v_image), 1, H * W, None,
-                                             0.5 * W, 0.5 * H, ptr(v_rows), None, _stream()), "b200gs_blend_bwd_to_rows")
+            check(L.b200gs_blend_bwd_rows(mode, W, H, ptr(ctx.binning.tile_ranges), ptr(ctx.binning.sorted_ids), ptr(rows), ptr(bg), ptr(final_T),
+                                          ptr(n_contrib), ptr(v_image), pix_stride, ch_stride, None, gsx, gsy, ptr(v_rows), _stream()),
+                  "b200gs_blend_bwd_rows")
         v_means = torch.empty(n, 3, dtype=torch.float32, device=dev)
         v_ls = torch.empty(n, 3, dtype=torch.float32, device=dev)
         v_q = torch.empty(n, 4, dtype=torch.float32, device=dev)
@@ -539,17 +554,26 @@ class _RasterizeVanillaRaw(torch.autograd.Function):
         v_dc, v_rest = torch.empty_like(shs_dc), torch.empty_like(shs_rest)
         with _stage("project_bwd"):
             check(L.b200gs_project_bwd_rows(ctypes.byref(view), n, ptr(means3D), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc), ptr(shs_rest),
-                                            0, ptr(radii), ptr(clamped), None, ptr(v_rows), 0, ptr(v_means), ptr(v_ls), ptr(v_q), ptr(v_ol),
+                                            int(ctx.aa), ptr(radii), ptr(clamped), None, ptr(v_rows), 0, ptr(v_means), ptr(v_ls), ptr(v_q), ptr(v_ol),
                                             ptr(v_dc), ptr(v_rest), _stream()), "b200gs_project_bwd_rows")
-        v_means2D = torch.zeros(ctx.means2D_shape, dtype=torch.float32, device=dev)
-        v_means2D[:, :2] = v_rows[:, 0:2]
-        return v_means, v_means2D, v_dc, v_rest, v_ol.reshape(ctx.opac_shape), v_ls, v_q, None, None
+        if ctx.means2D_shape[1] == 2:
+            v_means2D = v_rows[:, 0:2].contiguous()
+        else:
+            v_means2D = torch.zeros(ctx.means2D_shape, dtype=torch.float32, device=dev)
+            v_means2D[:, :2] = v_rows[:, 0:2]
+        return None, v_means, v_means2D, v_dc, v_rest, v_ol.reshape(ctx.opac_shape), v_ls, v_q, None, None, None
 
 
 def rasterize_vanilla_raw(means3D, means2D, shs_dc, shs_rest, opacity_logits, log_scales, raw_quats, bg, view: B200gsView):
     """Fused-activation variant of rasterize_vanilla: inputs are the model's RAW parameters
     (means, shs_dc [N,1,3], shs_rest [N,K-1,3], opacity logits, log-scales, un-normalised quaternions)."""
-    return _RasterizeVanillaRaw.apply(means3D, means2D, shs_dc, shs_rest, opacity_logits, log_scales, raw_quats, bg, view)
+    return _RasterizeRaw.apply(MODE_VANILLA, means3D, means2D, shs_dc, shs_rest, opacity_logits, log_scales, raw_quats, bg, view, False)
+
+
+def rasterize_gsplat_raw(means3D, means2D, shs_dc, shs_rest, opacity_logits, log_scales, raw_quats, bg, view: B200gsView, anti_aliased=True):
+    """The gsplat-semantics counterpart: -> ([H,W,3] image, radii); `means2D` [N,2] receives the projected means (values) and
+    d loss / d mean2D in pixels (`.grad`)."""
+    return _RasterizeRaw.apply(MODE_GSPLAT, means3D, means2D, shs_dc, shs_rest, opacity_logits, log_scales, raw_quats, bg, view, anti_aliased)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

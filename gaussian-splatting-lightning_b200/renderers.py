@@ -213,6 +213,19 @@ class B200VanillaRenderer(Renderer):
 # ----------------------------------------------------------------------------------------------------------------------
 # gsplat
 # ----------------------------------------------------------------------------------------------------------------------
+_GRAD_SCALES = {}
+
+
+def _grad_scale(width: int, height: int, device) -> torch.Tensor:
+    """0.5 * [[W, H]] on the device (gsplat_renderer.py:200), built once per (size, device): a fresh torch.tensor(...).to(device)
+    every step is a pageable host->device copy, i.e. a stream synchronisation in the middle of the step."""
+    key = (int(width), int(height), str(device))
+    t = _GRAD_SCALES.get(key)
+    if t is None:
+        t = _GRAD_SCALES[key] = 0.5 * torch.tensor([[float(width), float(height)]], dtype=torch.float32).to(device)
+    return t
+
+
 class B200GSplatRenderer(Renderer):
     _RGB_REQUIRED = 1
     _ALPHA_REQUIRED = 1 << 1
@@ -268,25 +281,28 @@ class B200GSplatRenderer(Renderer):
 
     def forward(self, viewpoint_camera, pc, bg_color: torch.Tensor, scaling_modifier=1.0, render_types: list = None, **kwargs):
         bits = self.parse_render_types(render_types)
-        img_height, img_width = int(viewpoint_camera.height), int(viewpoint_camera.width)
         raw = _raw_parameters(pc) if (self.fused_activations and bits == self._RGB_REQUIRED) else None
         if raw is not None:
+            # one autograd node for the whole step (K1..K6 / K7 -> gradient rows -> K8); image size from the cached host view: no
+            # device->host read, no pageable host->device copy anywhere in the step
             view = camera_view(viewpoint_camera, MODE_GSPLAT, self.cache_cameras)
             view = _view_with(view, scale_modifier=float(scaling_modifier), eps2d=float(getattr(self, "filter_2d_kernel_size", 0.3)),
                               sh_degree=int(pc.active_sh_degree))
-            xys, depths, radii, conics, tiles, opac, rgbs = ops.project_gaussians_raw(
-                raw["means"], raw["scales"], raw["rotations"], raw["opacities"], raw["shs_dc"], raw["shs_rest"], view, self.anti_aliased)
-            rgb = ops.rasterize_gaussians(xys, depths, radii, conics, tiles, rgbs, opac, img_height, img_width, self.block_size,
-                                          bg_color, False).permute(2, 0, 1)
+            img_height, img_width = int(view.height), int(view.width)
+            xys = torch.zeros(raw["means"].shape[0], 2, dtype=torch.float32, device=raw["means"].device, requires_grad=True)
+            image, radii = ops.rasterize_gsplat_raw(raw["means"], xys, raw["shs_dc"], raw["shs_rest"], raw["opacities"], raw["scales"],
+                                                    raw["rotations"], bg_color, view, self.anti_aliased)
+            rgb = image.permute(2, 0, 1)
             none = None
             return {
                 "render": rgb, "alpha": none, "acc_depth": none, "acc_depth_inverted": none, "exp_depth": none,
                 "exp_depth_inverted": none, "inverse_depth": none, "hard_depth": none, "hard_inverse_depth": none,
                 "viewspace_points": xys,
-                "viewspace_points_grad_scale": 0.5 * torch.tensor([[img_width, img_height]]).to(xys),
+                "viewspace_points_grad_scale": _grad_scale(img_width, img_height, xys.device),
                 "visibility_filter": radii > 0,
                 "radii": radii,
             }
+        img_height, img_width = int(viewpoint_camera.height), int(viewpoint_camera.width)
         quats = pc.get_rotation
         quats = quats / quats.norm(dim=-1, keepdim=True)  # gsplat_renderer.py:68
         xys, depths, radii, conics, comp, num_tiles_hit, cov3d = self._project(
@@ -347,7 +363,7 @@ class B200GSplatRenderer(Renderer):
             "hard_depth": hard_depth_im,
             "hard_inverse_depth": hard_inverse_depth_im,
             "viewspace_points": xys,
-            "viewspace_points_grad_scale": 0.5 * torch.tensor([[img_width, img_height]]).to(xys),
+            "viewspace_points_grad_scale": _grad_scale(img_width, img_height, xys.device),
             "visibility_filter": radii > 0,
             "radii": radii,
         }
@@ -374,7 +390,7 @@ class B200GSplatRenderer(Renderer):
         return {
             "render": rgb.permute(2, 0, 1),
             "viewspace_points": xys,
-            "viewspace_points_grad_scale": 0.5 * torch.tensor([[img_width, img_height]]).to(xys),
+            "viewspace_points_grad_scale": _grad_scale(img_width, img_height, xys.device),
             "visibility_filter": radii > 0,
             "radii": radii,
         }
@@ -410,7 +426,7 @@ class B200GSplatRenderer(Renderer):
         return {
             "render": rgb.permute(2, 0, 1),
             "viewspace_points": xys,
-            "viewspace_points_grad_scale": 0.5 * torch.tensor([[img_width, img_height]]).to(xys),
+            "viewspace_points_grad_scale": _grad_scale(img_width, img_height, xys.device),
             "visibility_filter": radii > 0,
             "radii": radii,
         }

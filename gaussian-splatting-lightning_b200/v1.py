@@ -43,7 +43,16 @@ class B200GSplatV1:
         from .renderers import camera_view
         view = camera_view(viewpoint_camera, MODE_GSPLAT)
         viewmats = viewpoint_camera.world_to_camera.T.unsqueeze(0)
-        Ks = torch.tensor([[[view.fx, 0., view.cx], [0., view.fy, view.cy], [0., 0., 1.]]], dtype=torch.float, device=viewmats.device)
+        key = (view.fx, view.fy, view.cx, view.cy, str(viewmats.device))
+        cached = getattr(viewpoint_camera, "_b200gs_Ks", None)      # a fresh torch.tensor(..., device=cuda) per step = a synchronising H2D copy
+        if cached is None or cached[0] != key:
+            Ks = torch.tensor([[[view.fx, 0., view.cx], [0., view.fy, view.cy], [0., 0., 1.]]], dtype=torch.float, device=viewmats.device)
+            try:
+                viewpoint_camera._b200gs_Ks = (key, Ks)
+            except AttributeError:
+                pass
+        else:
+            Ks = cached[1]
         pc = PreprocessedCamera((viewmats, Ks, (int(view.width), int(view.height))))
         pc.view = view
         return pc

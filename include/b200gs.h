@@ -268,6 +268,13 @@ B200GS_API int b200gs_loss_bwd(int32_t channels, int32_t width, int32_t height, 
 #define B200GS_ROW_OPACITY 7
 #define B200GS_ROW_RGB 8
 #define B200GS_ROW_RADIUS 11
+/* b200gs_project_fwd_rows: K1 (fused activations, either constant set) writing ONE [n,12] row per Gaussian instead of the separate
+ *     arrays — the single-GPU renderers' fast path: K2-K7 read the rows in place (b200gs_bin_count_rows, b200gs_blend_fwd_rows,
+ *     b200gs_blend_bwd_rows), K8 reads the gradient rows (b200gs_project_bwd_rows with row_offsets = NULL).  Rows of culled
+ *     Gaussians have radius 0, zeros in columns 0..3 and 8..10 (columns 4..7 unspecified).  radii[n], clamped[n] (what K8 needs) are written too; tiles may be NULL. */
+B200GS_API int b200gs_project_fwd_rows(const B200gsView* view, int64_t n, const float* means, const float* log_scales,
+                                       const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
+                                       int32_t anti_aliased, float* rows, int32_t* radii, uint8_t* clamped, int32_t* tiles, void* stream);
 /* b200gs_project_bwd_rows: K8 (fused activations) taking its cotangents straight from compacted [V,12] gradient rows
  *     (v_rows[row_offsets[i]] for visible i; row_offsets = NULL: v_rows[i]) and, when accumulate != 0, ADDING to the gradient buffers — the sharded
  *     renderer calls it once per camera of the step without unpack copies or separate sum kernels. */
@@ -317,10 +324,12 @@ B200GS_API int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height
 B200GS_API int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                                      const float* rows, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride,
                                      float* final_T, int32_t* n_contrib, float* alpha, void* stream);
+/* grad_scale_x / _y: factor on the mean2D columns of the gradient rows (vanilla renderers: 0.5 W, 0.5 H — the vanilla rasterizer's
+ *     NDC-unit convention; gsplat renderers: 1, 1).  v_rows must be zero-filled: the kernel accumulates with 128-bit reductions. */
 B200GS_API int b200gs_blend_bwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                                      const float* rows, const float* bg, const float* final_T, const int32_t* n_contrib,
-                                     const float* v_image, int64_t pix_stride, int64_t ch_stride, const float* v_alpha, float* v_rows,
-                                     void* stream);
+                                     const float* v_image, int64_t pix_stride, int64_t ch_stride, const float* v_alpha,
+                                     float grad_scale_x, float grad_scale_y, float* v_rows, void* stream);
 
 #ifdef __cplusplus
 }
