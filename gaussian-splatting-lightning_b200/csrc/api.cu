@@ -179,6 +179,31 @@ int b200gs_project_fwd_raw_multi(const B200gsView* views, int32_t n_views, int64
                                     radii, conic, rgb, clamped, opacity_out, (cudaStream_t)stream);
 }
 
+size_t b200gs_project_pack_workspace_bytes(int32_t n_views, int64_t n) { return project_pack_workspace_bytes(n_views, n); }
+
+int b200gs_project_pack_multi(const B200gsView* views, int32_t n_views, int64_t n, const float* means, const float* log_scales,
+                              const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
+                              int32_t anti_aliased, float* xy, int32_t* radii, uint8_t* clamped, int32_t* row_index, void* const* dst_rows,
+                              int64_t block_rows, void* workspace, size_t workspace_bytes, int64_t* d_count, void* stream) {
+    B200GS_CHECK_ARG(views && n_views >= 1 && n_views <= B200GS_MAX_VIEWS, "n_views must be 1..B200GS_MAX_VIEWS");
+    B200GS_CHECK_ARG(n >= 0 && n < (int64_t(1) << 30) && block_rows > 0 && block_rows < (int64_t(1) << 30), "bad size");
+    for (int j = 0; j < n_views; ++j) {
+        int rc = check_view(views + j, true);
+        if (rc) return rc;
+        B200GS_CHECK_ARG(views[j].mode == B200GS_MODE_GSPLAT, "multi-view launches use the gsplat constant set");
+        B200GS_CHECK_ARG(dst_rows && dst_rows[j] && (reinterpret_cast<uintptr_t>(dst_rows[j]) & 15u) == 0, "dst_rows: NULL or misaligned");
+    }
+    if (n > 0) {
+        B200GS_CHECK_ARG(means && log_scales && raw_quats && opacity_logits && shs_dc, "NULL input pointer");
+        B200GS_CHECK_ARG(views[0].sh_stride == 1 || shs_rest, "shs_rest required when sh_stride > 1");
+        B200GS_CHECK_ARG(xy && radii && clamped && row_index && workspace, "NULL output pointer");
+    }
+    B200GS_CHECK_ARG(d_count, "NULL d_count");
+    return launch_project_pack_multi(views, n_views, n, means, log_scales, raw_quats, opacity_logits, shs_dc, shs_rest, anti_aliased, xy, radii,
+                                     clamped, row_index, (float* const*)dst_rows, block_rows, workspace, workspace_bytes, d_count,
+                                     (cudaStream_t)stream);
+}
+
 int b200gs_project_bwd_rows_multi(const B200gsView* views, int32_t n_views, int64_t n, const float* means, const float* log_scales,
                                   const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
                                   int32_t anti_aliased, const int32_t* radii, const uint8_t* clamped, const int32_t* row_index,
@@ -416,14 +441,15 @@ int b200gs_unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offs
 }
 
 int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull, void* workspace,
-                          size_t workspace_bytes, int64_t* d_counts, int64_t* host_counts, int32_t sync_host, void* stream) {
+                          size_t workspace_bytes, int64_t* d_counts, int64_t* host_counts, int32_t sync_host, void* stream,
+                          const int64_t* block_counts, int64_t block_rows) {
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
     B200GS_CHECK_ARG(width > 0 && height > 0 && n >= 0 && n < (int64_t(1) << 31), "bad size");
     B200GS_CHECK_ARG(workspace && d_counts && (n == 0 || rows), "NULL pointer");
     return bin_count(mode, width, height, n, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY, rows + B200GS_ROW_DEPTH,
                      (const int32_t*)(rows + B200GS_ROW_RADIUS), cull ? rows + B200GS_ROW_CONIC : nullptr,
                      cull ? rows + B200GS_ROW_OPACITY : nullptr, workspace, workspace_bytes, d_counts, host_counts, sync_host,
-                     (cudaStream_t)stream);
+                     (cudaStream_t)stream, block_counts, block_rows);
 }
 
 int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,

@@ -165,9 +165,18 @@ LayoutB make_layout_b(int64_t n, int64_t max_coarse, int width, int height) {
 struct BinSrc {
     const float* xy; const float* depth; const int32_t* radii; const float* conic; const float* opacity;
     int xs, ds, rs, cs, os;
+    // rows that arrive in fixed-size blocks (the sharded exchange): block b holds blk_cnt[b] valid rows, the rest of its blk_rows
+    // rows is stale memory and reads as culled — no padding pass over the receive buffer
+    const int64_t* blk_cnt; int blk_rows;
     __device__ __forceinline__ float2 get_xy(int64_t i) const { return *reinterpret_cast<const float2*>(xy + i * xs); }
     __device__ __forceinline__ float get_depth(int64_t i) const { return depth[i * ds]; }
-    __device__ __forceinline__ int get_radius(int64_t i) const { return radii[i * rs]; }
+    __device__ __forceinline__ int get_radius(int64_t i) const {
+        if (blk_cnt != nullptr) {
+            const int b = (int)i / blk_rows;
+            if ((int)i - b * blk_rows >= (int)blk_cnt[b]) return 0;
+        }
+        return radii[i * rs];
+    }
 };
 
 struct CullE {
@@ -814,9 +823,12 @@ __global__ void __launch_bounds__(CHUNK) scatter_ids_kernel(int n_cells, int cgr
 size_t bin_count_workspace_bytes(int64_t n) { return make_layout_a(n).total; }
 size_t bin_sort_workspace_bytes(int64_t n, int64_t max_coarse, int width, int height) { return make_layout_b(n, max_coarse, width, height).total; }
 
-static BinSrc make_src(int row_stride, const float* xy, const float* depth, const int32_t* radii, const float* conic, const float* opacity) {
-    if (row_stride > 0) return BinSrc{xy, depth, radii, conic, opacity, row_stride, row_stride, row_stride, row_stride, row_stride};
-    return BinSrc{xy, depth, radii, conic, opacity, 2, 1, 1, 3, 1};
+static BinSrc make_src(int row_stride, const float* xy, const float* depth, const int32_t* radii, const float* conic, const float* opacity,
+                       const int64_t* block_counts, int64_t block_rows) {
+    if (block_rows <= 0) block_counts = nullptr;
+    if (row_stride > 0)
+        return BinSrc{xy, depth, radii, conic, opacity, row_stride, row_stride, row_stride, row_stride, row_stride, block_counts, (int)block_rows};
+    return BinSrc{xy, depth, radii, conic, opacity, 2, 1, 1, 3, 1, block_counts, (int)block_rows};
 }
 
 // Counter read-back.  For pinned (mapped) host memory the counters are PUBLISHED by a kernel with system-scope stores
@@ -864,7 +876,7 @@ int publish_i64(const int64_t* d_values, int64_t* host_values, int n, cudaStream
 
 int bin_count(int mode, int width, int height, int64_t n, int row_stride, const float* xy, const float* depth, const int32_t* radii,
               const float* conic, const float* opacity, void* ws, size_t ws_bytes, int64_t* d_counts, int64_t* host_counts,
-              int sync_host, cudaStream_t s) {
+              int sync_host, cudaStream_t s, const int64_t* block_counts, int64_t block_rows) {
     const LayoutA L = make_layout_a(n);
     if (ws_bytes < L.total) {
         set_error("bin_count: workspace too small (%zu < %zu)", ws_bytes, L.total);
@@ -887,7 +899,7 @@ int bin_count(int mode, int width, int height, int64_t n, int row_stride, const 
     if (n > 0) {
         B200GS_CUDA(cudaMemsetAsync(w + L.zero, 0, L.zero_bytes, s));
         const unsigned blocks = (unsigned)L.blocks;
-        const BinSrc src = make_src(row_stride, xy, depth, radii, conic, opacity);
+        const BinSrc src = make_src(row_stride, xy, depth, radii, conic, opacity, block_counts, block_rows);
         if (mode == B200GS_MODE_GSPLAT)
             depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, rec_a, recs, tickets, scan_state, hist, (unsigned long long*)d_counts);
         else

@@ -23,6 +23,18 @@ __device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+// relaxed gpu-scope load, executed only when `pred` (otherwise `dflt`): a predicated LDG, no branch around it
+__device__ __forceinline__ uint32_t ld_relaxed_if(const uint32_t* p, bool pred, uint32_t dflt) {
+    uint32_t v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u32 %0, %3;\n\t@q ld.relaxed.gpu.global.u32 %0, [%1];\n\t}"
+                 : "=r"(v) : "l"(p), "r"((uint32_t)pred), "r"(dflt) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // Wait until a look-back word has been published.  Tiles take tickets in launch order, so the tile that owns the word is
@@ -141,10 +153,15 @@ static __global__ void __launch_bounds__(THREADS) hist4_kernel(const uint2* __re
 constexpr int PASS_THREADS = 512;
 constexpr int PASS_WARPS = PASS_THREADS / 32;
 
-template <typename Rec, int IPT>
+// LB0 / LBMAX: first and largest look-back batch; LDMODE 0: volatile loads (branch per load), 1: predicated relaxed.gpu loads;
+// TRACE: thread 0 of every tile records %globaltimer at the phase boundaries into trace[tile][8] (profiles/tools/sweep_bench.cu)
+template <typename Rec, int IPT, int LB0 = 4, int LBMAX = 32, int LDMODE = 0, bool TRACE = false>
 __global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Rec* __restrict__ in, Rec* __restrict__ out, const int64_t* __restrict__ d_n,
                                                                         int64_t cap, int shift, const uint32_t* __restrict__ hist,
-                                                                        uint32_t* __restrict__ lookback, uint32_t* __restrict__ ticket) {
+                                                                        uint32_t* __restrict__ lookback, uint32_t* __restrict__ ticket,
+                                                                        unsigned long long* __restrict__ trace = nullptr) {
+    unsigned long long tr[8];
+    if (TRACE) tr[0] = global_ns();
     constexpr int TILE_ITEMS = PASS_THREADS * IPT;
     static_assert(TILE_ITEMS < 65536, "per-warp digit counts are 16-bit");
     __shared__ unsigned short s_cnt[PASS_WARPS][RADIX];   // per-warp digit counts -> offsets of the warp inside the tile's digit run
@@ -162,6 +179,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Re
     const int64_t tile_lo = int64_t(t) * TILE_ITEMS;
     if (tile_lo >= n) return;
     const int tile_n = (int)min((int64_t)TILE_ITEMS, n - tile_lo);
+    if (TRACE) tr[1] = global_ns();
 
     Rec rec[IPT];
     int dig[IPT];      // 0..255, or 256 for the slots past the end
@@ -186,6 +204,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Re
         rank[i] = before + lt;
     }
     __syncthreads();
+    if (TRACE) tr[2] = global_ns();
     // thread d (< RADIX) owns digit d: offsets of the warps inside the digit's run, the tile's count
     uint32_t run = 0;
     uint32_t* col = lookback + (tid & (RADIX - 1));                        // lookback[p * RADIX + d]
@@ -217,14 +236,20 @@ __global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Re
     // (profiles/round2_call3_launches.md).  In the steady state of a long pass the nearest predecessor's prefix is usually out
     // already, and a fixed 32 per step wasted 4x the L2 requests (measured: +0.08 ms per binning at 2.3 M records) — hence the
     // doubling.  A word that is not published yet ends the batch; the walk resumes there.
-    constexpr int LB = 32;
+    constexpr int LB = LBMAX;
     uint32_t before_tiles = 0;
+    if (TRACE) tr[3] = global_ns();
     if (tid < RADIX) {
-        int width = 4;
+        int width = LB0;
         for (int p = t - 1; p >= 0;) {
             uint32_t v[LB];
 #pragma unroll
-            for (int k = 0; k < LB; ++k) v[k] = (k >= width) ? 0u : ((p - k >= 0) ? ld_volatile(col + int64_t(p - k) * RADIX) : FLAG_PREFIX);
+            for (int k = 0; k < LB; ++k) {
+                if (LDMODE == 1)
+                    v[k] = ld_relaxed_if(col + int64_t(max(p - k, 0)) * RADIX, k < width && p - k >= 0, (k < width) ? FLAG_PREFIX : 0u);
+                else
+                    v[k] = (k >= width) ? 0u : ((p - k >= 0) ? ld_volatile(col + int64_t(p - k) * RADIX) : FLAG_PREFIX);
+            }
             int used = 0;
             bool done = false, open = true;
 #pragma unroll
@@ -247,6 +272,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Re
         }
         if (t > 0) st_volatile(col + int64_t(t) * RADIX, ((before_tiles + run) & VALUE_MASK) | FLAG_PREFIX);
     }
+    if (TRACE) tr[4] = global_ns();
     const int digit_start = block_exclusive<PASS_WARPS>(tid < RADIX ? (int)hist[tid] : 0, s_scan, &tot);   // first global index of digit d
     if (tid < RADIX) s_base[tid] = digit_start + (int)before_tiles - tile_start;
     __syncthreads();
@@ -254,6 +280,11 @@ __global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Re
         const Rec r = s_stage[s];
         const int d = (int)((key_of(r) >> shift) & 255u);
         out[s_base[d] + s] = r;
+    }
+    if (TRACE) {
+        tr[5] = global_ns();
+        if (tid == 0 && trace != nullptr)
+            for (int k = 0; k < 6; ++k) trace[size_t(t) * 8 + k] = tr[k];
     }
 }
 

@@ -9,6 +9,7 @@
 // HBM-bound: per visible Gaussian 268 B fwd / 552 B bwd at SH degree 3.  SH coefficients are streamed with
 // 128-bit read-only loads (ld.global.nc), outputs written with 64/128-bit stores where the layout allows.
 #include "common.cuh"
+#include "onesweep.cuh"
 
 namespace b200gs {
 
@@ -456,6 +457,129 @@ __global__ void __launch_bounds__(256) project_fwd_multi_kernel(const __grid_con
         const int64_t o = int64_t(j) * n + i;
         rgb_out[3 * o + 0] = r; rgb_out[3 * o + 1] = gc; rgb_out[3 * o + 2] = bc;
         clamped_out[o] = cl;
+    }
+}
+
+// K1 of a shard for all W cameras FUSED with the exchange's packing: the visible splats of camera j leave this kernel as [.,12]
+// rows stored straight into block `dst.p[j]` (capacity `cap` rows) of the rank that owns camera j — a peer GPU's receive buffer
+// mapped over NVLink, or a local send buffer — in Gaussian-index order (what keeps the sharded image bit-identical to the
+// single-GPU one).  No intermediate arrays, no separate scan / pack / pad kernels: blocks take tickets, every warp compacts its
+// visible lanes per camera into a shared-memory row tile (ballot), warp j runs camera j's chained scan over the blocks
+// (decoupled look-back, one value per block and camera), and the block copies its rows out as contiguous runs.  Rows beyond
+// `cap` are dropped and show up in d_count[j] (total visible of camera j; the caller compares with cap and redoes the step with
+// the exact exchange).  What the backward needs stays local: radii, clamped, row_index (block-relative row j*cap + k, or -1
+// when dropped) at [j*n + i], and the mean2D (the per-camera viewspace points the renderer hands out).
+struct PackDst {
+    float* p[B200GS_MAX_VIEWS];
+};
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_WARPS = PACK_THREADS / 32;
+
+template <int MC>
+__global__ void __launch_bounds__(PACK_THREADS) project_pack_multi_kernel(const __grid_constant__ ViewPack vp, int nviews, const RawIO raw, int64_t n,
+                                                                        const float* __restrict__ means, const float* __restrict__ scales,
+                                                                        const float* __restrict__ quats, const float* __restrict__ shs_dc,
+                                                                        float2* __restrict__ xy_out, int32_t* __restrict__ radii_out,
+                                                                        uint8_t* __restrict__ clamped_out, int32_t* __restrict__ row_index_out,
+                                                                        const PackDst dst, int64_t cap, uint32_t* __restrict__ ticket,
+                                                                        uint32_t* __restrict__ scan_state /*[nviews][gridDim.x]*/,
+                                                                        int64_t* __restrict__ d_count) {
+    extern __shared__ float4 s_rows[];                           // [nviews][PACK_THREADS slots][3]: slot = warp * 32 + rank among the warp's visible lanes
+    __shared__ int s_cnt[B200GS_MAX_VIEWS][PACK_WARPS];          // visible lanes per (camera, warp)
+    __shared__ uint32_t s_pre[B200GS_MAX_VIEWS][PACK_WARPS];     // global row (within the block of `cap`) of the warp's first row
+    __shared__ int s_tile;
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, w = tid >> 5;
+    if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int t = s_tile;
+    const int64_t i = int64_t(t) * PACK_THREADS + tid;
+    const bool live = i < n;
+    float p[3] = {0.f, 0.f, 0.f};
+    double sc[3] = {1.0, 1.0, 1.0}, q[4] = {1.0, 0.0, 0.0, 0.0}, inv_qn;
+    if (live) {
+        p[0] = __ldg(means + 3 * i); p[1] = __ldg(means + 3 * i + 1); p[2] = __ldg(means + 3 * i + 2);
+        load_scale_quat<true, double>(scales, quats, i, sc, q, &inv_qn);
+    }
+    unsigned vismask = 0;
+    unsigned long long kpos = 0;            // 8 bits per camera: this lane's rank among the warp's visible lanes
+#pragma unroll 1
+    for (int j = 0; j < nviews; ++j) {
+        ProjVals pv;
+        bool vis = false;
+        if (live) vis = project_one<true, true>(vp.v[j], raw, i, 0, p, sc, q, nullptr, pv);
+        const unsigned b = __ballot_sync(0xffffffffu, vis);
+        const int k = __popc(b & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[j][w] = __popc(b);
+        if (live) {
+            const int64_t o = int64_t(j) * n + i;
+            xy_out[o] = make_float2(pv.px, pv.py);
+            radii_out[o] = pv.radius;
+        }
+        if (vis) {
+            vismask |= 1u << j;
+            kpos |= (unsigned long long)k << (8 * j);
+            float4* row = s_rows + (size_t(j) * PACK_THREADS + w * 32 + k) * 3;
+            row[0] = make_float4(pv.px, pv.py, pv.depth, pv.cA);
+            row[1] = make_float4(pv.cB, pv.cC, pv.comp, pv.opac);
+            row[2].w = __int_as_float(pv.radius);
+        }
+    }
+    float sh[MC * 3];
+    if (vismask) {
+        const int deg = vp.v[0].sh_degree;
+        load_sh_any<true, MC>(shs_dc, raw.shs_rest, i, vp.v[0].sh_stride, (deg + 1) * (deg + 1), sh);
+    }
+#pragma unroll 1
+    for (int j = 0; j < nviews; ++j) {
+        uint8_t cl = 0;
+        if ((vismask >> j) & 1u) {
+            float r, gc, bc;
+            sh_color_one<MC>(vp.v[j], p, sh, r, gc, bc, cl);
+            float* row2 = reinterpret_cast<float*>(s_rows + (size_t(j) * PACK_THREADS + w * 32 + (int)((kpos >> (8 * j)) & 255ull)) * 3 + 2);
+            row2[0] = r; row2[1] = gc; row2[2] = bc;
+        }
+        if (live) clamped_out[int64_t(j) * n + i] = cl;
+    }
+    __syncthreads();
+    // warp j: camera j's block total -> chained scan over the blocks -> first row of every warp's run
+    if ((int)w < nviews) {
+        const int j = (int)w;
+        const int c = (lane < PACK_WARPS) ? s_cnt[j][lane] : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < PACK_WARPS; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)lane >= o) inc += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, inc, PACK_WARPS - 1);
+        const uint32_t base = sweep::chained_exclusive(scan_state + size_t(j) * gridDim.x, t, (uint32_t)total);
+        if (lane < PACK_WARPS) s_pre[j][lane] = base + (uint32_t)(inc - c);
+        if (lane == 0 && t == (int)gridDim.x - 1) d_count[j] = (int64_t)base + total;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < nviews; ++j) {
+        if (live) {
+            int32_t ri = -1;
+            if ((vismask >> j) & 1u) {
+                const int64_t pos = (int64_t)s_pre[j][w] + (int64_t)((kpos >> (8 * j)) & 255ull);
+                ri = pos < cap ? (int32_t)(int64_t(j) * cap + pos) : -1;
+            }
+            row_index_out[int64_t(j) * n + i] = ri;
+        }
+        // copy-out: 8 warps x 32 slots x 3 float4 per camera; consecutive threads -> consecutive 16-byte pieces of a warp's run
+        float4* out = reinterpret_cast<float4*>(dst.p[j]);
+        const float4* src = s_rows + size_t(j) * PACK_THREADS * 3;
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int item = it * PACK_THREADS + tid;       // = (warp segment * 32 + r) * 3 + part
+            const int seg = item / 96, r = (item - seg * 96) / 3, part = item - seg * 96 - r * 3;
+            if (r < s_cnt[j][seg]) {
+                const int64_t pos = (int64_t)s_pre[j][seg] + r;
+                if (pos < cap) out[pos * 3 + part] = src[(seg * 32 + r) * 3 + part];
+            }
+        }
     }
 }
 
@@ -1013,6 +1137,54 @@ int launch_project_fwd_multi(const B200gsView* views, int n_views, int64_t n, co
     else
         project_fwd_multi_kernel<16><<<(unsigned)div_up64(n, 256), 256, 0, s>>>(vp, n_views, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth,
                                                                                 radii, conic, rgb, clamped);
+    B200GS_LAUNCH_CHECK();
+    return B200GS_OK;
+}
+
+size_t project_pack_workspace_bytes(int n_views, int64_t n) {
+    return 256 + (size_t)n_views * (size_t)div_up64(n > 0 ? n : 1, PACK_THREADS) * sizeof(uint32_t);
+}
+
+int launch_project_pack_multi(const B200gsView* views, int n_views, int64_t n, const float* means, const float* scales, const float* quats,
+                              const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased, float* xy, int32_t* radii,
+                              uint8_t* clamped, int32_t* row_index, float* const* dst_rows, int64_t cap, void* workspace, size_t workspace_bytes,
+                              int64_t* d_count, cudaStream_t s) {
+    if (n_views == 0) return B200GS_OK;
+    if (n == 0) {
+        B200GS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t) * (size_t)n_views, s));
+        return B200GS_OK;
+    }
+    const size_t need = project_pack_workspace_bytes(n_views, n);
+    if (workspace_bytes < need) {
+        set_error("project_pack_multi: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return B200GS_EINVAL;
+    }
+    ViewPack vp;
+    PackDst dst;
+    for (int j = 0; j < B200GS_MAX_VIEWS; ++j) {
+        vp.v[j] = views[j < n_views ? j : 0];
+        dst.p[j] = j < n_views ? dst_rows[j] : nullptr;
+    }
+    RawIO raw{opac_logits, shs_rest, nullptr, nullptr, nullptr, nullptr, anti_aliased, nullptr, nullptr, 0};
+    B200GS_CUDA(cudaMemsetAsync(workspace, 0, need, s));
+    uint32_t* ticket = (uint32_t*)workspace;
+    uint32_t* state = ticket + 64;
+    const unsigned blocks = (unsigned)div_up64(n, PACK_THREADS);
+    const size_t smem = (size_t)n_views * PACK_THREADS * 3 * sizeof(float4);
+    static bool configured = false;         // raise the dynamic shared-memory limit once (8 cameras: 96 KB)
+    if (!configured) {
+        B200GS_CUDA(cudaFuncSetAttribute((const void*)project_pack_multi_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         B200GS_MAX_VIEWS * PACK_THREADS * 3 * (int)sizeof(float4)));
+        B200GS_CUDA(cudaFuncSetAttribute((const void*)project_pack_multi_kernel<25>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         B200GS_MAX_VIEWS * PACK_THREADS * 3 * (int)sizeof(float4)));
+        configured = true;
+    }
+    if (views[0].sh_degree > 3)
+        project_pack_multi_kernel<25><<<blocks, PACK_THREADS, smem, s>>>(vp, n_views, raw, n, means, scales, quats, shs_dc, (float2*)xy, radii, clamped,
+                                                                         row_index, dst, cap, ticket, state, d_count);
+    else
+        project_pack_multi_kernel<16><<<blocks, PACK_THREADS, smem, s>>>(vp, n_views, raw, n, means, scales, quats, shs_dc, (float2*)xy, radii, clamped,
+                                                                         row_index, dst, cap, ticket, state, d_count);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
 }

@@ -282,7 +282,7 @@ class _ShardStep:
     """What the two autograd nodes of one sharded step share (buffers of the projection, the exchange and the raster)."""
     __slots__ = ("views", "cam_views", "rank", "world", "group", "n", "aa", "sh_degree", "peer", "xy", "depth", "conic", "rgb", "opac", "radii",
                  "clamped", "row_index", "fixed_cap", "counts", "recv", "binning", "final_T", "n_contrib", "hw", "v_rows", "v_send", "parity",
-                 "peer_mode", "xys_refs", "want_xy")
+                 "peer_mode", "xys_refs", "want_xy", "plan_cap", "plan_peer", "d_count", "send_rows", "params")
 
 
 def _project_shard(st: _ShardStep, means, log_scales, raw_quats, ol, shs_dc, shs_rest):
@@ -318,6 +318,44 @@ def _project_shard(st: _ShardStep, means, log_scales, raw_quats, ol, shs_dc, shs
                       "b200gs_project_fwd_raw")
 
 
+def _project_pack_shard(st: _ShardStep, means, log_scales, raw_quats, ol, shs_dc, shs_rest):
+    """K1 of the shard for all cameras FUSED with the packing of the exchange (b200gs_project_pack_multi; fixed-capacity steps, <= 8
+    cameras): camera j's visible splats go, as [.,12] rows in Gaussian-index order, straight into this rank's block of camera j's
+    owner's receive buffer (peer memory over NVLink) or of a local send buffer (NCCL mode).  Kept locally: mean2D, radii, clamped,
+    row_index, and d_count[j] = visible splats of camera j."""
+    import ctypes
+    from . import ops
+    from ._lib import B200gsView, check, lib, ptr
+    L = lib()
+    dev, n, world, rank, cap = means.device, st.n, st.world, st.rank, st.plan_cap
+    wn = world * n
+    st.xy = torch.empty(wn, 2, dtype=torch.float32, device=dev)
+    st.radii = torch.empty(wn, dtype=torch.int32, device=dev)
+    st.clamped = torch.empty(wn, dtype=torch.uint8, device=dev)
+    st.row_index = torch.empty(wn, dtype=torch.int32, device=dev)
+    st.d_count = torch.empty(world, dtype=torch.int64, device=dev)
+    st.depth = st.conic = st.rgb = st.opac = None
+    st.cam_views = [ops._copy_view(v, sh_degree=int(st.sh_degree), sh_stride=int(shs_dc.shape[1] + shs_rest.shape[1])) for v in st.views]
+    row_bytes = ROW_FLOATS * 4
+    if st.plan_peer:
+        pe = st.peer
+        pe.step += 1
+        st.parity = pe.step & 1
+        name = "recv1" if st.parity else "recv0"
+        dst = [pe.peers[name][j] + rank * cap * row_bytes for j in range(world)]      # my block in camera j's owner's buffer
+        st.send_rows = None
+    else:
+        st.send_rows = torch.empty(world * cap, ROW_FLOATS, dtype=torch.float32, device=dev)
+        dst = [st.send_rows.data_ptr() + j * cap * row_bytes for j in range(world)]
+    ws = torch.empty(int(L.b200gs_project_pack_workspace_bytes(world, n)), dtype=torch.uint8, device=dev)
+    arr = (B200gsView * world)(*st.cam_views)
+    dst_arr = (ctypes.c_void_p * world)(*dst)
+    with ops._stage("project_fwd"):
+        check(L.b200gs_project_pack_multi(arr, world, n, ptr(means), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc), ptr(shs_rest),
+                                          int(st.aa), ptr(st.xy), ptr(st.radii), ptr(st.clamped), ptr(st.row_index), dst_arr, cap, ptr(ws),
+                                          ws.numel(), ptr(st.d_count), ops._stream()), "b200gs_project_pack_multi")
+
+
 class _ProjectShard(torch.autograd.Function):
     """Node A of a sharded step: raw shard parameters -> the mean2D of every (camera, Gaussian) pair, one [n,2] tensor per camera
     (graph tensors: the distributed density controller calls retain_grad() on them, distributed_vanilla_density_controller.py:
@@ -330,7 +368,11 @@ class _ProjectShard(torch.autograd.Function):
         means, log_scales, raw_quats = means.contiguous(), log_scales.contiguous(), raw_quats.contiguous()
         ol = opac_logits.contiguous().reshape(-1)
         shs_dc, shs_rest = shs_dc.contiguous(), shs_rest.contiguous()
-        _project_shard(st, means, log_scales, raw_quats, ol, shs_dc, shs_rest)
+        if st.plan_cap:
+            _project_pack_shard(st, means, log_scales, raw_quats, ol, shs_dc, shs_rest)
+        else:
+            _project_shard(st, means, log_scales, raw_quats, ol, shs_dc, shs_rest)
+        st.params = (means, log_scales, raw_quats, ol, shs_dc, shs_rest)      # for node B's overflow fallback; dropped there
         ctx.st = st
         ctx.opac_shape = tuple(opac_logits.shape)
         ctx.save_for_backward(means, log_scales, raw_quats, ol, shs_dc, shs_rest)
@@ -395,14 +437,14 @@ class _ExchangeRasterize(torch.autograd.Function):
         stream = ops._stream()
         bg = bg.contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
-        st.row_index = torch.empty(wn, dtype=torch.int32, device=dev)
-        ws = torch.empty(max(int(L.b200gs_pack_rows_workspace_bytes(wn)), 256), dtype=torch.uint8, device=dev)
         gv = st.views[rank]
         W, H = gv.width, gv.height
         key = _group_key(group, world)
 
         def exact():
-            """size exchange + host syncs: first step and overflow fallback"""
+            """size exchange + host syncs: first step and overflow fallback (works from the separate arrays of the unfused K1)"""
+            st.row_index = torch.empty(wn, dtype=torch.int32, device=dev)
+            ws = torch.empty(max(int(L.b200gs_pack_rows_workspace_bytes(wn)), 256), dtype=torch.uint8, device=dev)
             rows = torch.empty(wn, ROW_FLOATS, **f32)          # upper bound; the first sum(V_j) rows are the send buffer
             d_count = torch.empty(1, dtype=torch.int64, device=dev)
             with ops._stage("pack"):
@@ -427,42 +469,30 @@ class _ExchangeRasterize(torch.autograd.Function):
                 st.peer.ensure(cap)                      # collective: every rank takes this branch in the same step
             return (send_counts, recv_counts), recv, binning, out
 
-        with _STATE_LOCK:
-            cap = _EXCHANGE_CAP.get(key)
+        cap = st.plan_cap
         result = None
-        st.fixed_cap, st.parity, st.peer_mode = 0, 0, False
-        if cap is not None:
-            use_peer = st.peer is not None and st.peer.ensure(cap)
-            d_count = torch.empty(world, dtype=torch.int64, device=dev)
-            if use_peer:
-                pe = st.peer
-                pe.step += 1
-                st.parity = pe.step & 1
-                name = "recv1" if st.parity else "recv0"
-                dst = (ctypes.c_void_p * world)(*pe.peers[name])
-                with ops._stage("pack"):
-                    check(L.b200gs_pack_rows_peer(wn, n, cap, ptr(st.xy), ptr(st.depth), ptr(st.conic), None, ptr(st.opac), ptr(st.rgb),
-                                                  ptr(st.radii), ptr(ws), ws.numel(), ptr(st.row_index), dst, rank * cap, ptr(d_count), stream),
-                          "b200gs_pack_rows_peer")
-                recv = pe.tensor(name, world * cap)
-            else:
-                rows = torch.empty(world * cap, ROW_FLOATS, **f32)
-                with ops._stage("pack"):
-                    check(L.b200gs_pack_rows(wn, n, cap, ptr(st.xy), ptr(st.depth), ptr(st.conic), None, ptr(st.opac), ptr(st.rgb), ptr(st.radii),
-                                             ptr(ws), ws.numel(), ptr(st.row_index), ptr(rows), ptr(d_count), stream), "b200gs_pack_rows")
-            gmax_dev = d_count.max().reshape(1)
-            # global maximum of the block fill; in peer mode ALSO the barrier: when it completes on this rank, every rank's
-            # pack kernel (which precedes its all_reduce in stream order) has finished storing into this rank's buffer
-            dist.all_reduce(gmax_dev, op=dist.ReduceOp.MAX, group=group)
+        st.fixed_cap, st.peer_mode = 0, False
+        if cap:
+            # node A's fused kernel has already stored every rank's rows where they are consumed (peer mode) or into the send buffer.
+            # ONE small collective: all-gather of the per-camera row counts -> the valid rows of each received block (no padding pass),
+            # the global maximum (overflow check), and — peer mode — the barrier: when it completes here, every rank's K1 (which
+            # precedes its all-gather in stream order) has finished storing into this rank's buffer.
+            use_peer = st.plan_peer
+            all_counts = torch.empty(world * world, dtype=torch.int64, device=dev)             # [source rank][camera]
+            dist.all_gather_into_tensor(all_counts, st.d_count, group=group)
+            gmax_dev = all_counts.max().reshape(1)
             gmax_host = ops._host_counts()
             check(L.b200gs_publish_i64(ptr(gmax_dev), gmax_host.data_ptr(), 1, stream), "b200gs_publish_i64")
             published = torch.cuda.Event()
             published.record()
-            if not use_peer:
+            recv_counts = all_counts.view(world, world)[:, rank].clamp(max=cap).contiguous()
+            if use_peer:
+                recv = st.peer.tensor("recv1" if st.parity else "recv0", world * cap)
+            else:
                 recv = torch.empty(world * cap, ROW_FLOATS, **f32)
-                dist.all_to_all_single(recv, rows, group=group)
-                del rows
-            binning, out = ops.bin_and_blend_rows(MODE_GSPLAT, W, H, recv, bg, True)
+                dist.all_to_all_single(recv, st.send_rows, group=group)
+                st.send_rows = None
+            binning, out = ops.bin_and_blend_rows(MODE_GSPLAT, W, H, recv, bg, True, False, recv_counts, cap)
             published.synchronize()                           # long past: the blend has been enqueued behind it
             gmax = int(gmax_host[0])
             ops._return_host_counts(gmax_host)
@@ -471,9 +501,12 @@ class _ExchangeRasterize(torch.autograd.Function):
                     _EXCHANGE_CAP[key] = int(gmax * EXCHANGE_SLACK) + 1024
                 result = (None, recv, binning, out)
                 st.fixed_cap, st.peer_mode = cap, use_peer
+            else:                                             # a > 15 % jump: redo with the unfused projection and the exact exchange
+                _project_shard(st, *st.params)
         if result is None:
             st.fixed_cap, st.peer_mode = 0, False             # the exact step exchanges through NCCL in both directions
             result = exact()
+        st.params = None
         st.counts, st.recv, st.binning, (image, st.final_T, st.n_contrib) = result
         st.hw = (H, W)
         st.xy = st.depth = st.conic = st.rgb = st.opac = None      # consumed: the rows hold everything from here on
@@ -709,13 +742,18 @@ class B200DistributedRenderer(Renderer):
         st.rank, st.world, st.group, st.n = rank, world, self.group, int(raw["means"].shape[0])
         st.aa, st.sh_degree = bool(self.anti_aliased), int(pc.active_sh_degree)
         st.peer = _peer_exchange(self.group, dev) if (self.peer_exchange and bg_color.is_cuda and dist.get_backend(self.group) == "nccl") else None
-        st.v_rows = st.v_send = None
+        st.v_rows = st.v_send = st.d_count = st.send_rows = st.params = None
+        with _STATE_LOCK:
+            cap = _EXCHANGE_CAP.get(_group_key(self.group, world))
+        st.plan_cap = int(cap) if (cap and world <= 8 and bg_color.is_cuda) else 0        # fixed-capacity step: K1 fused with the packing
+        st.plan_peer = bool(st.plan_cap and st.peer is not None and st.peer.ensure(st.plan_cap))
         st.xys_refs, st.want_xy = None, bool(self.want_xy_grads)
         xys = _ProjectShard.apply(raw["means"], raw["scales"], raw["rotations"], raw["opacities"], raw["shs_dc"], raw["shs_rest"], st)
         st.xys_refs = [weakref.ref(x) for x in xys]
         n = st.n
-        projection_results_list = [(st.radii[j * n:(j + 1) * n], xys[j], st.depth[j * n:(j + 1) * n], st.conic[j * n:(j + 1) * n], None)
-                                   for j in range(world)]
+        # (radii, means2d, depths, conics, compensations) per camera like the reference; its consumers read [0] and [1] only
+        # (distributed_vanilla_density_controller.py:28-37) — depths / conics live in the exchanged rows and are not duplicated here
+        projection_results_list = [(st.radii[j * n:(j + 1) * n], xys[j], None, None, None) for j in range(world)]
         visible_mask_list = [r[0] > 0 for r in projection_results_list]
         img = _ExchangeRasterize.apply(bg_color, st, *xys)
         return {

@@ -253,14 +253,17 @@ def bin_gaussians(mode: int, width: int, height: int, xy: torch.Tensor, depth: t
     return _bin((mode, width, height, n, cull), mode, width, height, n, xy.device, cull, lazy, count_call)
 
 
-def bin_rows(mode: int, width: int, height: int, rows: torch.Tensor, cull: bool = True, lazy: bool = False) -> Binning:
-    """K2-K5 on a [n,12] splat-row buffer read in place (b200gs_bin_count_rows); same lazy protocol as bin_gaussians."""
+def bin_rows(mode: int, width: int, height: int, rows: torch.Tensor, cull: bool = True, lazy: bool = False, block_counts=None,
+             block_rows: int = 0) -> Binning:
+    """K2-K5 on a [n,12] splat-row buffer read in place (b200gs_bin_count_rows); same lazy protocol as bin_gaussians.
+    block_counts (int64 device tensor) / block_rows: the rows come in fixed-size blocks of which only the first block_counts[b] rows
+    are valid (the sharded exchange)."""
     L = lib()
     n = rows.shape[0]
 
     def count_call(ws_a, ws_a_bytes, d_counts, host, sync, st):
-        check(L.b200gs_bin_count_rows(mode, width, height, n, ptr(rows), int(cull), ws_a, ws_a_bytes, d_counts, host, sync, st),
-              "b200gs_bin_count_rows")
+        check(L.b200gs_bin_count_rows(mode, width, height, n, ptr(rows), int(cull), ws_a, ws_a_bytes, d_counts, host, sync, st,
+                                      ptr(block_counts), int(block_rows) if block_counts is not None else 0), "b200gs_bin_count_rows")
 
     return _bin(("rows", mode, width, height, bool(cull)), mode, width, height, n, rows.device, bool(cull), lazy, count_call)
 
@@ -279,11 +282,11 @@ def blend_forward_rows(mode, width, height, binning: Binning, rows, bg, planar=F
     return image, final_T, n_contrib
 
 
-def bin_and_blend_rows(mode, width, height, rows, bg, cull=True, planar=False):
-    binning = bin_rows(mode, width, height, rows, cull, lazy=True)
+def bin_and_blend_rows(mode, width, height, rows, bg, cull=True, planar=False, block_counts=None, block_rows=0):
+    binning = bin_rows(mode, width, height, rows, cull, lazy=True, block_counts=block_counts, block_rows=block_rows)
     out = blend_forward_rows(mode, width, height, binning, rows, bg, planar)
     if not binning.resolve():
-        binning = bin_rows(mode, width, height, rows, cull, lazy=False)
+        binning = bin_rows(mode, width, height, rows, cull, lazy=False, block_counts=block_counts, block_rows=block_rows)
         out = blend_forward_rows(mode, width, height, binning, rows, bg, planar)
     return binning, out
 

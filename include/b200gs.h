@@ -293,6 +293,18 @@ B200GS_API int b200gs_project_fwd_raw_multi(const B200gsView* views, int32_t n_v
                                             const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
                                             int32_t anti_aliased, float* xy, float* depth, int32_t* radii, float* conic, float* rgb,
                                             uint8_t* clamped, float* opacity_out, void* stream);
+/* b200gs_project_pack_multi: K1 of one shard for all n_views cameras FUSED with the packing of the exchange.  The visible splats of
+ *     camera j leave the kernel as [.,12] rows, in Gaussian-index order, stored straight into dst_rows[j] (a HOST array of n_views device
+ *     pointers: block of block_rows rows in the receive buffer of the rank that owns camera j — peer memory over NVLink — or in a local
+ *     send buffer); rows past block_rows are dropped.  d_count[j] = visible splats of camera j (compare with block_rows).  Kept locally
+ *     for K8 and the renderer contract, camera-major ([j*n + i]): xy (mean2D), radii, clamped, row_index (j*block_rows + k, -1 = dropped).
+ *     Replaces b200gs_project_fwd_raw_multi + b200gs_pack_rows(_peer) (gsplat_distributed_renderer.py:127-217: project, then all-to-all). */
+B200GS_API size_t b200gs_project_pack_workspace_bytes(int32_t n_views, int64_t n);
+B200GS_API int b200gs_project_pack_multi(const B200gsView* views, int32_t n_views, int64_t n, const float* means, const float* log_scales,
+                                         const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
+                                         int32_t anti_aliased, float* xy, int32_t* radii, uint8_t* clamped, int32_t* row_index,
+                                         void* const* dst_rows, int64_t block_rows, void* workspace, size_t workspace_bytes,
+                                         int64_t* d_count, void* stream);
 B200GS_API int b200gs_project_bwd_rows_multi(const B200gsView* views, int32_t n_views, int64_t n, const float* means, const float* log_scales,
                                              const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
                                              int32_t anti_aliased, const int32_t* radii, const uint8_t* clamped, const int32_t* row_index,
@@ -318,9 +330,12 @@ B200GS_API int b200gs_pack_rows(int64_t n, int64_t segment_len, int64_t segment_
                                 void* workspace, size_t workspace_bytes, int32_t* row_index, float* rows, int64_t* d_count, void* stream);
 B200GS_API int b200gs_unpack_rows_grad(int64_t n, const int32_t* radii, const int32_t* offsets, const float* v_rows, float* v_xy,
                                        float* v_depth, float* v_conic, float* v_comp, float* v_opacity, float* v_rgb, void* stream);
+/* block_counts / block_rows (optional; NULL / 0 = every row counts): the rows arrive in blocks of block_rows rows of which only the first
+ *     block_counts[b] are valid (the fixed-capacity exchange of the sharded renderer) — the rest reads as culled, so the receive buffer
+ *     needs no padding pass. */
 B200GS_API int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull,
                                      void* workspace_a, size_t workspace_a_bytes, int64_t* d_counts, int64_t* host_counts,
-                                     int32_t sync_host, void* stream);
+                                     int32_t sync_host, void* stream, const int64_t* block_counts, int64_t block_rows);
 B200GS_API int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                                      const float* rows, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride,
                                      float* final_T, int32_t* n_contrib, float* alpha, void* stream);

@@ -30,8 +30,12 @@ def test_selective_adam_updates_only_visible_rows():
         opt.step()
         for k in shapes:
             gk = grads[k].double()
-            m = b1 * ref_m[k] + (1 - b1) * gk
-            v = b2 * ref_v[k] + (1 - b2) * gk * gk
+            # the kernel's (and gsplat's) constants are fp32: 1.0f - 0.999f = 0.00100004673 (4.7e-5 off the real 0.001)
+            f32 = torch.float32
+            b1f, b2f = float(torch.tensor(b1, dtype=f32)), float(torch.tensor(b2, dtype=f32))
+            omb1, omb2 = float(torch.tensor(1.0, dtype=f32) - torch.tensor(b1, dtype=f32)), float(torch.tensor(1.0, dtype=f32) - torch.tensor(b2, dtype=f32))
+            m = b1f * ref_m[k] + omb1 * gk
+            v = b2f * ref_v[k] + omb2 * gk * gk
             upd = ref_p[k] - lrs[k] * m / (v.sqrt() + eps)
             sel = vis.cpu().reshape((n,) + (1,) * (gk.dim() - 1))
             ref_m[k], ref_v[k], ref_p[k] = torch.where(sel, m, ref_m[k]), torch.where(sel, v, ref_v[k]), torch.where(sel, upd, ref_p[k])
