@@ -250,21 +250,27 @@ __device__ __forceinline__ void coarsen_rect(int x0, int y0, int x1, int y1, int
     cy1 = ((y1 - 1) >> SUPER_SHIFT) + 1;
 }
 
-// Phase A, blocks in ticket order, DK_ITEMS consecutive Gaussians per thread (2048 per block: the chained scan advances 32 blocks per
-// round trip to L2, so its length in BLOCKS is what the kernel's latency is made of — profiles/round2b: 53 us with 256-Gaussian
-// blocks).  The visible Gaussians (non-empty tile rect) are compacted in index order (block scan + chained scan) into {depth key, id}
-// records; each gets the 32-byte record phase B works from; the histograms of the four key bytes (what the radix passes start
-// from) are accumulated on the way.  counts[0] += tiles of the rect (the reference's pair count I: an upper bound of the culled
-// count, exact without culling), counts[1] += coarse cells, counts[3] = V.
+// Phase A, blocks in ticket order, 2048 consecutive Gaussians per block (the chained scan advances 32..128 blocks per round trip to
+// L2, so its length in BLOCKS is what bounds the kernel's latency — profiles/round2b: 53 us with 256-Gaussian blocks).  The block
+// walks its Gaussians in DK_ITEMS STRIPED rounds (round k, thread t: Gaussian 256 k + t), so every load and the 32-byte record
+// stores are coalesced (the first version gave each thread 8 consecutive Gaussians: 384-byte lane stride, 32 sectors per request).
+// The visible Gaussians (non-empty tile rect) are compacted in index order into {depth key, id} records: rank = visible Gaussians
+// of the rounds before (per-(round, warp) ballot counts, one 64-entry scan) + lanes below in the own ballot + the chained scan over
+// the blocks.  Each visible Gaussian gets the 32-byte record phase B works from (indexed by Gaussian id: written right away); the
+// histograms of the four key bytes (what the radix passes start from) are accumulated on the way — the two high bytes, which take
+// only a handful of values in a scene, with warp-aggregated increments (match.any), the low bytes with plain shared-memory atomics.
+// counts[0] += tiles of the rect (the reference's pair count I: an upper bound of the culled count, exact without culling),
+// counts[1] += coarse cells, counts[3] = V.
 constexpr int DK_ITEMS = 8;
 
-template <bool GSPLAT>
+// ROWS16: the inputs are the columns of one 16-byte aligned [n,12] row buffer (b200gs.h row layout): three 128-bit loads per Gaussian
+template <bool GSPLAT, bool ROWS16>
 __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, int grid_y, const BinSrc src, uint2* __restrict__ keyrec,
                                                          SplatRec* __restrict__ recs, uint32_t* __restrict__ ticket,
                                                          uint32_t* __restrict__ scan_state, uint32_t* __restrict__ hist,
                                                          unsigned long long* __restrict__ counts) {
     __shared__ unsigned long long s_area[8], s_cells[8];
-    __shared__ int s_scan[sweep::WARPS + 1];
+    __shared__ int s_cnt[DK_ITEMS * 8];      // visible Gaussians of (round, warp); then their exclusive scan
     __shared__ int s_tile;
     __shared__ uint32_t s_excl;
     __shared__ uint32_t s_h[4][sweep::RADIX];
@@ -272,39 +278,85 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
     for (int i = threadIdx.x; i < 4 * sweep::RADIX; i += 256) (&s_h[0][0])[i] = 0;
     __syncthreads();
     const int t = s_tile;
-    const int64_t i0 = (int64_t(t) * blockDim.x + threadIdx.x) * DK_ITEMS;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const int64_t base_i = int64_t(t) * (256 * DK_ITEMS) + threadIdx.x;
     unsigned long long area_sum = 0, cell_sum = 0;
     uint32_t key[DK_ITEMS];
-    int ncell[DK_ITEMS];
-    int my_vis = 0;
+    unsigned vis_bits = 0;           // bit k: this thread's Gaussian of round k is visible
+    unsigned below[DK_ITEMS];        // visible lanes below this one in round k's ballot
 #pragma unroll
     for (int k = 0; k < DK_ITEMS; ++k) {
-        const int64_t i = i0 + k;
+        const int64_t i = base_i + k * 256;
         key[k] = 0xFFFFFFFFu;
-        ncell[k] = 0;
+        bool vis = false;
         if (i < n) {
-            const int r = src.get_radius(i);
+            float px, py, dep, A = 1.f, B = 0.f, C = 1.f, o = 1.f;
+            int r;
+            if (ROWS16) {
+                const float4* row = reinterpret_cast<const float4*>(src.xy + i * B200GS_ROW_FLOATS);
+                const float4 q0 = row[0], q1 = row[1], q2 = row[2];
+                px = q0.x; py = q0.y; dep = q0.z; A = q0.w; B = q1.x; C = q1.y; o = q1.w;
+                r = __float_as_int(q2.w);
+                if (src.blk_cnt != nullptr) {
+                    const int b = (int)i / src.blk_rows;
+                    if ((int)i - b * src.blk_rows >= (int)src.blk_cnt[b]) r = 0;
+                }
+            } else {
+                r = src.get_radius(i);
+                const float2 pp = src.get_xy(i);
+                px = pp.x; py = pp.y;
+                dep = src.get_depth(i);
+                if (src.conic != nullptr) {
+                    const float* q = src.conic + i * src.cs;
+                    A = q[0]; B = q[1]; C = q[2];
+                    o = src.opacity[i * src.os];
+                }
+            }
             if (r > 0) {
-                const float2 p = src.get_xy(i);
                 int x0, y0, x1, y1;
-                tile_rect<GSPLAT>(p.x, p.y, (float)r, grid_x, grid_y, x0, y0, x1, y1);
+                tile_rect<GSPLAT>(px, py, (float)r, grid_x, grid_y, x0, y0, x1, y1);
                 const int area = max(0, x1 - x0) * max(0, y1 - y0);
                 if (area > 0) {
                     int cx0, cy0, cx1, cy1;
                     coarsen_rect(x0, y0, x1, y1, cx0, cy0, cx1, cy1);
-                    ncell[k] = (cx1 - cx0) * (cy1 - cy0);
-                    key[k] = __float_as_uint(src.get_depth(i));
+                    const int ncell = (cx1 - cx0) * (cy1 - cy0);
+                    key[k] = __float_as_uint(dep);
                     area_sum += (unsigned long long)area;
-                    cell_sum += (unsigned long long)ncell[k];
-                    ++my_vis;
+                    cell_sum += (unsigned long long)ncell;
+                    vis = true;
+                    float4* out = reinterpret_cast<float4*>(recs + i);
+                    out[0] = make_float4(px, py, A, B);
+                    out[1] = make_float4(C, o, __int_as_float(r), __int_as_float(ncell));
                 }
             }
         }
+        const unsigned bal = __ballot_sync(0xffffffffu, vis);
+        below[k] = __popc(bal & ((1u << lane) - 1u));
+        vis_bits |= vis ? (1u << k) : 0u;
+        if (lane == 0) s_cnt[k * 8 + w] = __popc(bal);
+        // byte histograms: bytes 3 and 2 (few distinct values per scene) warp-aggregated, bytes 1 and 0 with plain atomics
+        const unsigned grp = __match_any_sync(0xffffffffu, vis ? (key[k] >> 16) : 0xFFFFFFFFu);
+        if (vis) {
+            if ((grp & ((1u << lane) - 1u)) == 0u) atomicAdd(&s_h[2][(key[k] >> 16) & 255u], (uint32_t)__popc(grp));
+            atomicAdd(&s_h[1][(key[k] >> 8) & 255u], 1u);
+            atomicAdd(&s_h[0][key[k] & 255u], 1u);
+        }
+        const unsigned grp3 = __match_any_sync(0xffffffffu, vis ? (key[k] >> 24) : 0xFFFFFFFFu);
+        if (vis && (grp3 & ((1u << lane) - 1u)) == 0u) atomicAdd(&s_h[3][key[k] >> 24], (uint32_t)__popc(grp3));
     }
-    int block_vis;
-    int local = sweep::block_exclusive(my_vis, s_scan, &block_vis);
-    if (threadIdx.x < 32) {     // warp 0: warp-wide look-back over the preceding blocks
-        const uint32_t excl = sweep::chained_exclusive(scan_state, t, (uint32_t)block_vis);
+    __syncthreads();
+    if (threadIdx.x < 32) {     // warp 0: scan of the 64 (round, warp) counts, then the warp-wide look-back over the preceding blocks
+        const int c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
+        int inc = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)lane >= o) inc += v;
+        }
+        const int block_vis = __shfl_sync(0xffffffffu, inc, 31);
+        s_cnt[2 * lane] = inc - c0 - c1;
+        s_cnt[2 * lane + 1] = inc - c1;
+        const uint32_t excl = sweep::chained_exclusive<8, 8>(scan_state, t, (uint32_t)block_vis);
         if (threadIdx.x == 0) {
             s_excl = excl;
             if (t == (int)gridDim.x - 1) counts[3] = (unsigned long long)(excl + (uint32_t)block_vis);
@@ -314,24 +366,8 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
     const uint32_t base = s_excl;
 #pragma unroll
     for (int k = 0; k < DK_ITEMS; ++k) {
-        if (ncell[k] == 0) continue;
-        const int64_t i = i0 + k;
-        const float2 p = src.get_xy(i);
-        float A = 1.f, B = 0.f, C = 1.f, o = 1.f;
-        if (src.conic != nullptr) {
-            const float* q = src.conic + i * src.cs;
-            A = q[0]; B = q[1]; C = q[2];
-            o = src.opacity[i * src.os];
-        }
-        keyrec[base + (uint32_t)local] = make_uint2(key[k], (uint32_t)i);
-        ++local;
-        float4* out = reinterpret_cast<float4*>(recs + i);
-        out[0] = make_float4(p.x, p.y, A, B);
-        out[1] = make_float4(C, o, __int_as_float(src.get_radius(i)), __int_as_float(ncell[k]));
-        atomicAdd(&s_h[0][key[k] & 255u], 1u);
-        atomicAdd(&s_h[1][(key[k] >> 8) & 255u], 1u);
-        atomicAdd(&s_h[2][(key[k] >> 16) & 255u], 1u);
-        atomicAdd(&s_h[3][key[k] >> 24], 1u);
+        if (!((vis_bits >> k) & 1u)) continue;
+        keyrec[base + (uint32_t)s_cnt[k * 8 + w] + below[k]] = make_uint2(key[k], (uint32_t)(base_i + k * 256));
     }
     unsigned long long a = area_sum, c = cell_sum;
 #pragma unroll
@@ -344,7 +380,7 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
     if (threadIdx.x == 0) {
         unsigned long long ta = 0, tc = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { ta += s_area[w]; tc += s_cells[w]; }
+        for (int w2 = 0; w2 < 8; ++w2) { ta += s_area[w2]; tc += s_cells[w2]; }
         if (ta) atomicAdd(counts, ta);
         if (tc) atomicAdd(counts + 1, tc);
     }
@@ -381,7 +417,7 @@ __global__ void __launch_bounds__(256) rank_offsets_kernel(const int64_t* __rest
     int block_total;
     int local = sweep::block_exclusive(mine, s_scan, &block_total);
     if (threadIdx.x < 32) {
-        const uint32_t excl = sweep::chained_exclusive(scan_state, t, (uint32_t)block_total);
+        const uint32_t excl = sweep::chained_exclusive<8, 8>(scan_state, t, (uint32_t)block_total);
         if (threadIdx.x == 0) s_excl = excl;
     }
     __syncthreads();
@@ -589,11 +625,17 @@ __global__ void __launch_bounds__(1024) cell_table_kernel(int n_cells, const uin
     for (int i = tid; i < 2 * sweep::RADIX; i += 1024) digit_hist[i] = (&s_dh[0][0])[i];
     for (int i = tid; i < n_tiles; i += 1024) tile_total[i] = 0;    // accumulated by chunk_counts_kernel
     __syncthreads();                                                // chunk_base (written by this block) is visible
+    __shared__ int s_cb[1024];                                      // chunk_base of up to 1024 cells (images up to 4096 x 4096): the
+    const bool in_smem = n_cells <= 1024;                           // binary search below is a chain of dependent loads per chunk
+    if (in_smem) {
+        if (tid < n_cells) s_cb[tid] = chunk_base[tid];
+        __syncthreads();
+    }
     for (int c = tid; c < total; c += 1024) {
         int lo = 0, hi = n_cells;   // invariant: chunk_base[lo] <= c < chunk_base[hi]; cells without entries own no chunk
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if (chunk_base[mid] <= c) lo = mid; else hi = mid;
+            if ((in_smem ? s_cb[mid] : chunk_base[mid]) <= c) lo = mid; else hi = mid;
         }
         chunk_cell[c] = lo;
     }
@@ -664,7 +706,27 @@ __global__ void __launch_bounds__(1024) chunk_prefix_kernel(int n_cells, int n_t
         const int c0 = chunk_base[cell], c1 = chunk_base[cell + 1];
         const int per = (c1 - c0 + 15) >> 4;
         const int a = min(c1, c0 + j * per), b = min(c1, a + per);
+        // the walk is a chain of dependent L2 round trips unless the loads are issued together: up to PRE_REG counts per thread live in
+        // registers (all loads in flight at once, read once), longer parts fall back to the two-pass loop
+        constexpr int PRE_REG = 16;
         uint32_t sum = 0;
+        if (per <= PRE_REG) {
+            uint32_t v[PRE_REG];
+#pragma unroll
+            for (int q = 0; q < PRE_REG; ++q) v[q] = (a + q < b) ? (uint32_t)chunk_cnt[int64_t(a + q) * CELL_TILES + t] : 0u;
+#pragma unroll
+            for (int q = 0; q < PRE_REG; ++q) sum += v[q];
+            s_part[j][t] = sum;
+            __syncthreads();
+            uint32_t run = 0;
+            for (int k = 0; k < j; ++k) run += s_part[k][t];
+#pragma unroll
+            for (int q = 0; q < PRE_REG; ++q) {
+                if (a + q < b) chunk_pre[int64_t(a + q) * CELL_TILES + t] = run;
+                run += v[q];
+            }
+            return;
+        }
 #pragma unroll 4
         for (int c = a; c < b; ++c) sum += chunk_cnt[int64_t(c) * CELL_TILES + t];
         s_part[j][t] = sum;
@@ -900,10 +962,14 @@ int bin_count(int mode, int width, int height, int64_t n, int row_stride, const 
         B200GS_CUDA(cudaMemsetAsync(w + L.zero, 0, L.zero_bytes, s));
         const unsigned blocks = (unsigned)L.blocks;
         const BinSrc src = make_src(row_stride, xy, depth, radii, conic, opacity, block_counts, block_rows);
-        if (mode == B200GS_MODE_GSPLAT)
-            depth_keys_kernel<true><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, rec_a, recs, tickets, scan_state, hist, (unsigned long long*)d_counts);
-        else
-            depth_keys_kernel<false><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, rec_a, recs, tickets, scan_state, hist, (unsigned long long*)d_counts);
+        // all five inputs are columns of one 16-byte aligned [n,12] row buffer -> 128-bit row loads
+        const bool rows16 = row_stride == B200GS_ROW_FLOATS && conic != nullptr && depth == xy + B200GS_ROW_DEPTH && conic == xy + B200GS_ROW_CONIC &&
+                            opacity == xy + B200GS_ROW_OPACITY && reinterpret_cast<const float*>(radii) == xy + B200GS_ROW_RADIUS &&
+                            (reinterpret_cast<uintptr_t>(xy) & 15) == 0;
+#define B200GS_DK_LAUNCH(G, R) depth_keys_kernel<G, R><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, rec_a, recs, tickets, scan_state, hist, (unsigned long long*)d_counts)
+        if (mode == B200GS_MODE_GSPLAT) { if (rows16) B200GS_DK_LAUNCH(true, true); else B200GS_DK_LAUNCH(true, false); }
+        else                            { if (rows16) B200GS_DK_LAUNCH(false, true); else B200GS_DK_LAUNCH(false, false); }
+#undef B200GS_DK_LAUNCH
         B200GS_LAUNCH_CHECK();
         // stable LSD sort of the V visible {depth key, id} records (V = d_counts[3], known on the device only; byte histograms from above)
         const int64_t* d_visible = d_counts + 3;

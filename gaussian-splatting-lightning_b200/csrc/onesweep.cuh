@@ -58,14 +58,17 @@ __device__ __forceinline__ uint32_t key_of(const uint4& r) { return r.w; }
 // loads in flight together); the walk stops at the nearest tile that has already published its inclusive prefix and resumes at
 // the first word that is not published yet.  When a whole wave of tiles starts at once none has a prefix yet, and tile t needs
 // t / 128 round trips to L2 (with one predecessor per step: t; measured: profiles/round2_call2_launches.md).
+// DEPTH0 / DEPTH: words per lane in the first step / at most.  The default ramps 32 -> 64 -> 128 predecessors per step (long grids: in the
+// steady state the nearest predecessor's prefix is out already and wide steps only waste L2 requests); grids of a few hundred blocks
+// that all start together (depth_keys, rank_offsets: one wave) use <8, 8>: 256 predecessors in the first round trip.
+template <int DEPTH0 = 1, int DEPTH = 4>
 __device__ __forceinline__ uint32_t chained_exclusive(uint32_t* state, int t, uint32_t value) {
-    constexpr int DEPTH = 4;
     const unsigned lane = threadIdx.x & 31u;
     if (lane == 0) st_volatile(state + t, (value & VALUE_MASK) | (t == 0 ? FLAG_PREFIX : FLAG_AGG));
     uint32_t acc = 0;                 // per-lane partial sum, reduced once at the end
     bool done = (t == 0);
     unsigned spins = 0;
-    int depth = 1;                    // 32 words in the first step, then 64, 128, 128, ..
+    int depth = DEPTH0;               // default: 32 words in the first step, then 64, 128, 128, ..
     for (int p = t - 1; !done;) {
         uint32_t v[DEPTH];
 #pragma unroll
@@ -155,7 +158,10 @@ constexpr int PASS_WARPS = PASS_THREADS / 32;
 
 // LB0 / LBMAX: first and largest look-back batch; LDMODE 0: volatile loads (branch per load), 1: predicated relaxed.gpu loads;
 // TRACE: thread 0 of every tile records %globaltimer at the phase boundaries into trace[tile][8] (profiles/tools/sweep_bench.cu)
-template <typename Rec, int IPT, int LB0 = 4, int LBMAX = 32, int LDMODE = 0, bool TRACE = false>
+// Measured (profiles/tools/sweep_bench.cu on B200, one pass over 0.65 M / 2.3 M 8-byte records): a fixed batch of 8 with predicated
+// relaxed loads 19.0 / 35.4 us, the doubling 4..32 batches 23.1 / 43.5 us, fixed 32 21.0 us — the wide batches cost more in L2
+// requests than they save in round trips.  Default: fixed 8, relaxed.
+template <typename Rec, int IPT, int LB0 = 8, int LBMAX = 8, int LDMODE = 1, bool TRACE = false>
 __global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Rec* __restrict__ in, Rec* __restrict__ out, const int64_t* __restrict__ d_n,
                                                                         int64_t cap, int shift, const uint32_t* __restrict__ hist,
                                                                         uint32_t* __restrict__ lookback, uint32_t* __restrict__ ticket,
@@ -192,14 +198,31 @@ __global__ void __launch_bounds__(PASS_THREADS, 2) onesweep_pass_kernel(const Re
         if (valid) rec[i] = in[tile_lo + local];
         dig[i] = valid ? (int)((key_of(rec[i]) >> shift) & 255u) : 256;
     }
+    // Lanes with the same digit.  `match.any` peels one distinct value per round: with ~30 distinct 8-bit digits in a warp it took
+    // ~0.5 us per record (sweep_bench, round 2: ranking 4.6 us of a 10 us tile with 256 digit values, 1.0 us with 4).  Eight ballots
+    // (one per digit bit, plus one for the slots past the end) cost the same whatever the digits are, and the ballots of the IPT
+    // records are independent of each other: they pipeline, only the counter updates below are a dependent chain.
+    unsigned peers[IPT];
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-        const unsigned peers = __match_any_sync(0xffffffffu, dig[i]);
-        const int lt = __popc(peers & ((1u << lane) - 1u));
+        const bool valid = dig[i] < 256;
+        const unsigned mv = __ballot_sync(0xffffffffu, valid);
+        unsigned pm = valid ? mv : ~mv;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (dig[i] >> b) & 1;
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            pm &= bit ? m : ~m;
+        }
+        peers[i] = pm;
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const int lt = __popc(peers[i] & ((1u << lane) - 1u));
         int before = 0;
         if (dig[i] < 256) before = my_cnt[dig[i]];
         __syncwarp();
-        if (dig[i] < 256 && lt == 0) my_cnt[dig[i]] = (unsigned short)(before + __popc(peers));
+        if (dig[i] < 256 && lt == 0) my_cnt[dig[i]] = (unsigned short)(before + __popc(peers[i]));
         __syncwarp();
         rank[i] = before + lt;
     }

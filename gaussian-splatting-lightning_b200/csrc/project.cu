@@ -8,6 +8,8 @@
 //
 // HBM-bound: per visible Gaussian 268 B fwd / 552 B bwd at SH degree 3.  SH coefficients are streamed with
 // 128-bit read-only loads (ld.global.nc), outputs written with 64/128-bit stores where the layout allows.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "onesweep.cuh"
 
@@ -142,16 +144,13 @@ __device__ __forceinline__ void quat_to_rot(const R* q, R* Rm) {
     Rm[6] = R(2) * (x * z - r * y); Rm[7] = R(2) * (y * z + r * x); Rm[8] = R(1) - R(2) * (x * x + y * y);
 }
 
-template <bool GSPLAT, typename R>
-__device__ __forceinline__ void project_geometry(const B200gsView& v, const float* p, const R* sc, const R* q, Proj<R>& g) {
-    const float* V = v.viewmatrix;
-    const R p0 = p[0], p1 = p[1], p2 = p[2];
-    g.tx = p0 * R(V[0]) + p1 * R(V[4]) + p2 * R(V[8]) + R(V[12]);
-    g.ty = p0 * R(V[1]) + p1 * R(V[5]) + p2 * R(V[9]) + R(V[13]);
-    g.tz = p0 * R(V[2]) + p1 * R(V[6]) + p2 * R(V[10]) + R(V[14]);
+// The camera-independent half of the geometry: rotation, scaled axes, cov3D = (R S)(R S)^T.  The multi-view kernels of the sharded
+// renderer evaluate it ONCE per Gaussian (scale_modifier of views[0]) and only project_view per camera.
+template <typename R>
+__device__ __forceinline__ void gaussian_cov3d(const R* sc, const R* q, float scale_modifier, Proj<R>& g) {
     quat_to_rot<R>(q, g.Rm);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) g.s[k] = sc[k] * R(v.scale_modifier);
+    for (int k = 0; k < 3; ++k) g.s[k] = sc[k] * R(scale_modifier);
     R M[9];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -163,6 +162,25 @@ __device__ __forceinline__ void project_geometry(const B200gsView& v, const floa
     g.S3[3] = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
     g.S3[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
     g.S3[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
+}
+
+template <bool GSPLAT, typename R>
+__device__ __forceinline__ void project_view(const B200gsView& v, const float* p, Proj<R>& g);
+
+template <bool GSPLAT, typename R>
+__device__ __forceinline__ void project_geometry(const B200gsView& v, const float* p, const R* sc, const R* q, Proj<R>& g) {
+    gaussian_cov3d<R>(sc, q, v.scale_modifier, g);
+    project_view<GSPLAT, R>(v, p, g);
+}
+
+// The per-camera half: camera-space mean, Jacobian, cov2D (+ blur), determinants.  g.S3 (and Rm, s for the backward) are inputs.
+template <bool GSPLAT, typename R>
+__device__ __forceinline__ void project_view(const B200gsView& v, const float* p, Proj<R>& g) {
+    const float* V = v.viewmatrix;
+    const R p0 = p[0], p1 = p[1], p2 = p[2];
+    g.tx = p0 * R(V[0]) + p1 * R(V[4]) + p2 * R(V[8]) + R(V[12]);
+    g.ty = p0 * R(V[1]) + p1 * R(V[5]) + p2 * R(V[9]) + R(V[13]);
+    g.tz = p0 * R(V[2]) + p1 * R(V[6]) + p2 * R(V[10]) + R(V[14]);
 
     R tanx, tany;
     if (GSPLAT) {
@@ -221,6 +239,7 @@ struct RawIO {
     const float* v_rows;
     const int32_t* row_offsets;
     int accumulate;
+    int prefetch_sh;         // K1: L2 prefetch of the SH row of every Gaussian in front of the camera, issued before the fp64 geometry
 };
 
 template <bool RAW, typename R>
@@ -274,11 +293,23 @@ struct ProjVals {
 
 // Projection of Gaussian (p, sc, q) into view v -> pv; returns the visibility.  cov3d (optional) is written at index o.
 template <bool GSPLAT, bool RAW>
+__device__ __forceinline__ bool project_one_view(const B200gsView& v, const RawIO& raw, int64_t i, int64_t o, const float* p, Proj<double>& g,
+                                                 float* cov3d_out, ProjVals& pv);
+
+template <bool GSPLAT, bool RAW>
 __device__ __forceinline__ bool project_one(const B200gsView& v, const RawIO& raw, int64_t i, int64_t o, const float* p, const double* sc,
                                             const double* q, float* cov3d_out, ProjVals& pv) {
+    Proj<double> g;
+    gaussian_cov3d<double>(sc, q, v.scale_modifier, g);
+    return project_one_view<GSPLAT, RAW>(v, raw, i, o, p, g, cov3d_out, pv);
+}
+
+// g: gaussian_cov3d already evaluated
+template <bool GSPLAT, bool RAW>
+__device__ __forceinline__ bool project_one_view(const B200gsView& v, const RawIO& raw, int64_t i, int64_t o, const float* p, Proj<double>& g,
+                                                 float* cov3d_out, ProjVals& pv) {
     typedef double R;
-    Proj<R> g;
-    project_geometry<GSPLAT, R>(v, p, sc, q, g);
+    project_view<GSPLAT, R>(v, p, g);
 
     const float near = near_of<GSPLAT>(v);
     bool vis = GSPLAT ? (float(g.tz) >= near) : (float(g.tz) > near);
@@ -373,10 +404,91 @@ __device__ __forceinline__ void sh_color_one(const B200gsView& v, const float* p
     if (bc < 0.f) { bc = 0.f; cl |= 4; }
 }
 
+// ---- warp-cooperative SH rows -------------------------------------------------------------------------------------------
+// A lane-per-Gaussian read of a 180/192-byte SH row touches 32 different sectors per load instruction (ncu, round 2: 18.9 sectors per
+// request, `lg_throttle` 24 % of K1's stall samples) and keeps 48 coefficient registers live.  Here the WARP copies the rows of its
+// visible lanes: for each set bit of the visibility ballot the 32 lanes read consecutive floats of that row (one or two coalesced
+// requests per row, four rows in flight), park them in shared memory at an odd row pitch, and every lane then reads its own row
+// conflict-free.  Culled Gaussians cost no SH traffic at all, and the coefficient registers are gone.
+constexpr unsigned FULLW = 0xffffffffu;
+
+template <int MC>
+struct ShStage {
+    static constexpr int NIT = (MC * 3 + 31) / 32;     // 32-float pieces of a row
+    static constexpr int PITCH = (MC * 3) | 1;         // floats per staged row (odd: lane-per-row reads are conflict-free)
+    static constexpr int WARP_FLOATS = 32 * PITCH;
+};
+
+// rows r (bits of vis) of the warp: global row r starts at warp_base + r * row_stride; the first nw floats go to s_dst[r * PITCH ..]
+template <int MC>
+__device__ __forceinline__ void warp_stage_rows(const float* __restrict__ warp_base, int row_stride, int nw, unsigned vis, float* s_dst,
+                                                unsigned lane) {
+    constexpr int NIT = ShStage<MC>::NIT, PITCH = ShStage<MC>::PITCH;
+    unsigned m = vis;
+    while (m) {
+        int r[4];
+        float val[4][NIT];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            r[u] = m ? __ffs(m) - 1 : -1;
+            m &= m - 1;          // 0 & anything = 0
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float* row = warp_base + int64_t(max(r[u], 0)) * row_stride;
+#pragma unroll
+            for (int q = 0; q < NIT; ++q) {
+                const int c = q * 32 + (int)lane;
+                val[u][q] = (r[u] >= 0 && c < nw) ? __ldg(row + c) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (r[u] < 0) continue;
+#pragma unroll
+            for (int q = 0; q < NIT; ++q) {
+                const int c = q * 32 + (int)lane;
+                if (c < nw) s_dst[r[u] * PITCH + c] = val[u][q];
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// sh_color_one with the coefficients in a staged row: coefficient k, channel c = dc[c] for k = 0 when dc != nullptr (then row holds
+// coefficients 1..), else row[3 k + c]
+template <int MC>
+__device__ __forceinline__ void sh_color_staged(const B200gsView& v, const float* p, const float* dc, const float* row, float& r, float& gc,
+                                                float& bc, uint8_t& cl) {
+    const int deg = v.sh_degree;
+    const int ncoef = (deg + 1) * (deg + 1);
+    float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
+    const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= inv_len; dy *= inv_len; dz *= inv_len;
+    float bs[MC];
+    sh_basis<MC>(deg, dx, dy, dz, bs);
+    const int off = dc ? -3 : 0;
+    if (dc) { r = bs[0] * dc[0]; gc = bs[0] * dc[1]; bc = bs[0] * dc[2]; }
+    else    { r = bs[0] * row[0]; gc = bs[0] * row[1]; bc = bs[0] * row[2]; }
+#pragma unroll
+    for (int k = 1; k < MC; ++k) {
+        if (k < ncoef) {
+            r += bs[k] * row[3 * k + off];
+            gc += bs[k] * row[3 * k + off + 1];
+            bc += bs[k] * row[3 * k + off + 2];
+        }
+    }
+    r += 0.5f; gc += 0.5f; bc += 0.5f;
+    cl = 0;
+    if (r < 0.f) { r = 0.f; cl |= 1; }
+    if (gc < 0.f) { gc = 0.f; cl |= 2; }
+    if (bc < 0.f) { bc = 0.f; cl |= 4; }
+}
+
 // rows_out (raw mode only): instead of the separate arrays, ONE [n,12] row per Gaussian (xy 0..1, depth 2, conic 3..5, compensation 6,
 // blend opacity 7, rgb 8..10, radius bits 11) — three 128-bit stores; the binning and the blend kernels read the rows in place (one
 // 48-byte record per splat instead of four separate sectors).  radii_out / clamped_out (what K8 needs) are still written.
-template <bool GSPLAT, bool RAW, int MC>
+template <bool GSPLAT, bool RAW, int MC, bool COOP>
 __global__ void __launch_bounds__(256, 3) project_fwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
                                                           const float* __restrict__ means, const float* __restrict__ scales,
                                                           const float* __restrict__ quats, const float* __restrict__ shs,
@@ -385,28 +497,64 @@ __global__ void __launch_bounds__(256, 3) project_fwd_kernel(const __grid_consta
                                                           float* __restrict__ comp_out, int32_t* __restrict__ tiles_out,
                                                           float* __restrict__ cov3d_out, float* __restrict__ rgb_out,
                                                           uint8_t* __restrict__ clamped_out, float* __restrict__ rows_out) {
+    extern __shared__ float s_sh[];                              // COOP: [warps][32 * PITCH] staged SH rows
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
+    if (!COOP && i >= n) return;
+    const bool in_range = i < n;
+    const int64_t il = in_range ? i : n - 1;                     // COOP: out-of-range lanes stay for the warp-wide copies
+    const float p[3] = {__ldg(means + 3 * il), __ldg(means + 3 * il + 1), __ldg(means + 3 * il + 2)};
+    if (!COOP && raw.prefetch_sh && shs != nullptr) {
+        // The SH row is only needed once the Gaussian is known to be visible, i.e. after ~150 dependent fp64 operations: its DRAM latency
+        // would sit at the end of that chain (ncu: long_scoreboard 33 % of K1's stall samples).  Everything in front of the camera gets
+        // its row pulled into L2 now; culled-by-frustum Gaussians in front of the camera cost some extra traffic.
+        const float* V = v.viewmatrix;
+        const float tz = p[0] * V[2] + p[1] * V[6] + p[2] * V[10] + V[14];
+        if (tz > 0.f) {
+            const int rw = (RAW ? v.sh_stride - 1 : v.sh_stride) * 3;
+            const int need = ((v.sh_degree + 1) * (v.sh_degree + 1) - (RAW ? 1 : 0)) * 3;
+            const char* row = reinterpret_cast<const char*>((RAW ? raw.shs_rest : shs) + il * int64_t(rw));
+            const int bytes = min(rw, need) * 4;
+            for (int off = 0; off < bytes; off += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+            if (bytes > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + bytes - 4));
+        }
+    }
     double sc[3], q[4], inv_qn;
-    load_scale_quat<RAW, double>(scales, quats, i, sc, q, &inv_qn);
+    load_scale_quat<RAW, double>(scales, quats, il, sc, q, &inv_qn);
     const ProjOut out{xy_out, depth_out, radii_out, conic_out, comp_out, tiles_out, cov3d_out, rgb_out, clamped_out};
     ProjVals pv;
-    const bool vis = project_one<GSPLAT, RAW>(v, raw, i, i, p, sc, q, cov3d_out, pv);
+    const bool vis = project_one<GSPLAT, RAW>(v, raw, il, il, p, sc, q, in_range ? cov3d_out : nullptr, pv) && in_range;
     const bool rows = RAW && rows_out != nullptr;
-    if (!rows) store_soa<RAW>(out, raw.opac_out, i, pv);
+    if (!rows && in_range) store_soa<RAW>(out, raw.opac_out, i, pv);
     float r = 0.f, gc = 0.f, bc = 0.f;
     uint8_t cl = 0;
     if (shs != nullptr) {
-        if (vis) {
-            const int deg = v.sh_degree;
+        const int deg = v.sh_degree;
+        const int ncoef = (deg + 1) * (deg + 1);
+        if (COOP) {
+            const unsigned lane = threadIdx.x & 31u;
+            const unsigned vm = __ballot_sync(FULLW, vis);
+            float* sw = s_sh + (threadIdx.x >> 5) * ShStage<MC>::WARP_FLOATS;
+            const int64_t i0 = i - lane;                         // the warp's first Gaussian (always < n when any lane is visible)
+            if (RAW) {
+                if (ncoef > 1) warp_stage_rows<MC>(raw.shs_rest + i0 * int64_t(v.sh_stride - 1) * 3, (v.sh_stride - 1) * 3, ncoef * 3 - 3, vm, sw, lane);
+                if (vis) {
+                    const float dc[3] = {__ldg(shs + 3 * i), __ldg(shs + 3 * i + 1), __ldg(shs + 3 * i + 2)};
+                    sh_color_staged<MC>(v, p, dc, sw + lane * ShStage<MC>::PITCH, r, gc, bc, cl);
+                }
+            } else {
+                warp_stage_rows<MC>(shs + i0 * int64_t(v.sh_stride) * 3, v.sh_stride * 3, ncoef * 3, vm, sw, lane);
+                if (vis) sh_color_staged<MC>(v, p, nullptr, sw + lane * ShStage<MC>::PITCH, r, gc, bc, cl);
+            }
+        } else if (vis) {
             float sh[MC * 3];
-            load_sh_any<RAW, MC>(shs, raw.shs_rest, i, v.sh_stride, (deg + 1) * (deg + 1), sh);
+            load_sh_any<RAW, MC>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
             sh_color_one<MC>(v, p, sh, r, gc, bc, cl);
         }
+        if (!in_range) return;
         if (!rows) { rgb_out[3 * i + 0] = r; rgb_out[3 * i + 1] = gc; rgb_out[3 * i + 2] = bc; }
         clamped_out[i] = cl;
     }
+    if (!in_range) return;
     if (rows) {
         float4* row = reinterpret_cast<float4*>(rows_out + i * B200GS_ROW_FLOATS);
         radii_out[i] = pv.radius;
@@ -415,6 +563,14 @@ __global__ void __launch_bounds__(256, 3) project_fwd_kernel(const __grid_consta
         if (vis) row[1] = make_float4(pv.cB, pv.cC, pv.comp, pv.opac);
         row[2] = make_float4(r, gc, bc, __int_as_float(pv.radius));      // radius 0 = culled: all the kernels look at of such a row
     }
+}
+
+// L2 prefetch of the first `floats` floats at `row` (one request per 64 bytes + the last word)
+__device__ __forceinline__ void prefetch_l2(const float* row, int floats) {
+    const char* r = reinterpret_cast<const char*>(row);
+    const int bytes = floats * 4;
+    for (int off = 0; off < bytes; off += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + off));
+    if (bytes > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + bytes - 4));
 }
 
 // The sharded renderer projects ONE shard into the W cameras of a step: one launch, the parameters (and the SH block, if any view
@@ -436,12 +592,18 @@ __global__ void __launch_bounds__(256) project_fwd_multi_kernel(const __grid_con
     const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
     double sc[3], q[4], inv_qn;
     load_scale_quat<true, double>(scales, quats, i, sc, q, &inv_qn);
+    {   // the SH row is needed after the whole camera loop: pull it into L2 now (nearly every Gaussian of a shard is seen by some camera)
+        const int deg0 = vp.v[0].sh_degree;
+        prefetch_l2(raw.shs_rest + i * int64_t(vp.v[0].sh_stride - 1) * 3, min((vp.v[0].sh_stride - 1) * 3, ((deg0 + 1) * (deg0 + 1) - 1) * 3));
+    }
+    Proj<double> g3;
+    gaussian_cov3d<double>(sc, q, vp.v[0].scale_modifier, g3);      // once per Gaussian; project_one_view per camera
     const ProjOut out{xy_out, depth_out, radii_out, conic_out, nullptr, nullptr, nullptr, rgb_out, clamped_out};
     unsigned vismask = 0;
 #pragma unroll 1
     for (int j = 0; j < nviews; ++j) {
         ProjVals pv;
-        if (project_one<true, true>(vp.v[j], raw, i, int64_t(j) * n + i, p, sc, q, nullptr, pv)) vismask |= 1u << j;
+        if (project_one_view<true, true>(vp.v[j], raw, i, int64_t(j) * n + i, p, g3, nullptr, pv)) vismask |= 1u << j;
         store_soa<true>(out, raw.opac_out, int64_t(j) * n + i, pv);
     }
     float sh[MC * 3];
@@ -476,7 +638,7 @@ constexpr int PACK_THREADS = 256;
 constexpr int PACK_WARPS = PACK_THREADS / 32;
 
 template <int MC>
-__global__ void __launch_bounds__(PACK_THREADS) project_pack_multi_kernel(const __grid_constant__ ViewPack vp, int nviews, const RawIO raw, int64_t n,
+__global__ void __launch_bounds__(PACK_THREADS, (MC <= 16 ? 3 : 2)) project_pack_multi_kernel(const __grid_constant__ ViewPack vp, int nviews, const RawIO raw, int64_t n,
                                                                         const float* __restrict__ means, const float* __restrict__ scales,
                                                                         const float* __restrict__ quats, const float* __restrict__ shs_dc,
                                                                         float2* __restrict__ xy_out, int32_t* __restrict__ radii_out,
@@ -500,14 +662,18 @@ __global__ void __launch_bounds__(PACK_THREADS) project_pack_multi_kernel(const 
     if (live) {
         p[0] = __ldg(means + 3 * i); p[1] = __ldg(means + 3 * i + 1); p[2] = __ldg(means + 3 * i + 2);
         load_scale_quat<true, double>(scales, quats, i, sc, q, &inv_qn);
+        const int deg0 = vp.v[0].sh_degree;   // the SH row is needed after the whole camera loop: pull it into L2 now
+        prefetch_l2(raw.shs_rest + i * int64_t(vp.v[0].sh_stride - 1) * 3, min((vp.v[0].sh_stride - 1) * 3, ((deg0 + 1) * (deg0 + 1) - 1) * 3));
     }
+    Proj<double> g3;
+    gaussian_cov3d<double>(sc, q, vp.v[0].scale_modifier, g3);      // once per Gaussian; project_one_view per camera
     unsigned vismask = 0;
     unsigned long long kpos = 0;            // 8 bits per camera: this lane's rank among the warp's visible lanes
 #pragma unroll 1
     for (int j = 0; j < nviews; ++j) {
         ProjVals pv;
         bool vis = false;
-        if (live) vis = project_one<true, true>(vp.v[j], raw, i, 0, p, sc, q, nullptr, pv);
+        if (live) vis = project_one_view<true, true>(vp.v[j], raw, i, 0, p, g3, nullptr, pv);
         const unsigned b = __ballot_sync(0xffffffffu, vis);
         const int k = __popc(b & ((1u << lane) - 1u));
         if (lane == 0) s_cnt[j][w] = __popc(b);
@@ -713,6 +879,38 @@ __device__ __forceinline__ void geometry_backward(const B200gsView& v, const flo
 // SH-gradient rows of a warp's 32 Gaussians: staged in shared memory (odd row stride: conflict-free) and written back with
 // fully coalesced 128-bit stores: every row must be written (zeros for culled Gaussians), so the warp's 32 rows are one
 // contiguous 5.6-6 KB span of the output.  out[] holds this lane's 48 values (dc first); RAW: dc goes to v_shs, rest to dst_base.
+// second half of store_sh_rows: the warp's staged rows (row of lane l at s_rows_warp + l * (rw | 1)) -> global memory, coalesced
+template <bool RAW>
+__device__ __forceinline__ void flush_sh_rows(const float* s_rows_warp, int rw, int64_t i, int64_t n, unsigned lane, float* __restrict__ dst_base,
+                                              bool ACC) {
+    const int rwp = rw | 1;
+    __syncwarp();
+    const int64_t i0 = i - lane;
+    const int rows_valid = (i0 < n) ? (int)min((int64_t)32, n - i0) : 0;
+    const int total = rows_valid * rw;
+    float* dst = dst_base + i0 * rw;
+    const float* sw = s_rows_warp;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        for (int idx = lane; idx * 4 + 3 < total; idx += 32) {
+            int f = idx * 4, r = f / rw, c = f - r * rw;
+            float t[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                t[e] = sw[r * rwp + c];
+                if (++c == rw) { c = 0; ++r; }
+            }
+            if (ACC) {
+                const float4 old = reinterpret_cast<const float4*>(dst)[idx];
+                t[0] += old.x; t[1] += old.y; t[2] += old.z; t[3] += old.w;
+            }
+            reinterpret_cast<float4*>(dst)[idx] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        for (int f = (total & ~3) + lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw] + (ACC ? dst[f] : 0.f);
+    } else {
+        for (int f = lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw] + (ACC ? dst[f] : 0.f);
+    }
+}
+
 template <bool RAW, int MC>
 __device__ __forceinline__ void store_sh_rows(float* s_rows_warp, const float* out, int64_t i, int64_t n, bool in_range, int stride3, unsigned lane,
                                               float* __restrict__ v_shs, float* __restrict__ v_shs_rest, bool ACC) {
@@ -731,31 +929,7 @@ __device__ __forceinline__ void store_sh_rows(float* s_rows_warp, const float* o
             const int c = RAW ? k - 3 : k;
             if (c >= 0 && c < rw) row[c] = out[k];
         }
-        __syncwarp();
-        const int64_t i0 = i - lane;
-        const int rows_valid = (i0 < n) ? (int)min((int64_t)32, n - i0) : 0;
-        const int total = rows_valid * rw;
-        float* dst = dst_base + i0 * rw;
-        const float* sw = s_rows_warp;
-        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-            for (int idx = lane; idx * 4 + 3 < total; idx += 32) {
-                int f = idx * 4, r = f / rw, c = f - r * rw;
-                float t[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    t[e] = sw[r * rwp + c];
-                    if (++c == rw) { c = 0; ++r; }
-                }
-                if (ACC) {
-                    const float4 old = reinterpret_cast<const float4*>(dst)[idx];
-                    t[0] += old.x; t[1] += old.y; t[2] += old.z; t[3] += old.w;
-                }
-                reinterpret_cast<float4*>(dst)[idx] = make_float4(t[0], t[1], t[2], t[3]);
-            }
-            for (int f = (total & ~3) + lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw] + (ACC ? dst[f] : 0.f);
-        } else {
-            for (int f = lane; f < total; f += 32) dst[f] = sw[(f / rw) * rwp + f % rw] + (ACC ? dst[f] : 0.f);
-        }
+        flush_sh_rows<RAW>(s_rows_warp, rw, i, n, lane, dst_base, ACC);
     } else if (in_range) {  // wider coefficient storage than the kernel evaluates: plain per-thread rows
         float* o = dst_base + i * int64_t(rw);
 #pragma unroll
@@ -764,8 +938,8 @@ __device__ __forceinline__ void store_sh_rows(float* s_rows_warp, const float* o
     }
 }
 
-template <bool GSPLAT, bool RAW, int MC>
-__global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
+template <bool GSPLAT, bool RAW, int MC, bool COOP>
+__global__ void __launch_bounds__(BWD_THREADS, (MC <= 16 ? 5 : 3)) project_bwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
                                                           const float* __restrict__ means, const float* __restrict__ scales,
                                                           const float* __restrict__ quats, const float* __restrict__ shs,
                                                           const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
@@ -816,9 +990,38 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_kernel(const __grid_c
                 out[3 * k + 0] = bk * gr; out[3 * k + 1] = bk * gg; out[3 * k + 2] = bk * gb;
             }
         }
+        if (COOP && !GSPLAT && deg > 0) {
+            // view direction -> mean (dgr back-propagates it; gsplat renderers detach the direction).  The SH rows of the warp's visible
+            // lanes come through the staging buffer (coalesced, see warp_stage_rows) before it is reused for the gradient rows.
+            constexpr int PITCH = ShStage<MC>::PITCH;
+            static_assert(ShStage<MC>::WARP_FLOATS <= 32 * (MC * 3 + 1), "staging buffer too small");
+            const unsigned vm = __ballot_sync(FULLW, vis);
+            const int64_t i0 = i - lane;
+            const int off = RAW ? -3 : 0;
+            if (RAW) warp_stage_rows<MC>(raw.shs_rest + i0 * int64_t(v.sh_stride - 1) * 3, (v.sh_stride - 1) * 3, ncoef * 3 - 3, vm, s_rows[warp], lane);
+            else warp_stage_rows<MC>(shs + i0 * int64_t(v.sh_stride) * 3, v.sh_stride * 3, ncoef * 3, vm, s_rows[warp], lane);
+            if (vis) {
+                const float* row = s_rows[warp] + lane * PITCH;
+                float bx[MC], by[MC], bz[MC];
+                sh_basis_grad<MC>(deg, dx, dy, dz, bx, by, bz);
+                float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+#pragma unroll
+                for (int k = 1; k < MC; ++k) {
+                    if (k < ncoef) {
+                        const float w = row[3 * k + off] * gr + row[3 * k + off + 1] * gg + row[3 * k + off + 2] * gb;
+                        ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
+                    }
+                }
+                const float dot = dx * ddx + dy * ddy + dz * ddz;
+                dm[0] += (ddx - dx * dot) * inv_len;
+                dm[1] += (ddy - dy * dot) * inv_len;
+                dm[2] += (ddz - dz * dot) * inv_len;
+            }
+            __syncwarp();   // every lane has read its row: the buffer may be overwritten
+        }
         store_sh_rows<RAW, MC>(s_rows[warp], out, i, n, in_range, stride3, lane, v_shs, raw.v_shs_rest, ACC);
-        if (vis && !GSPLAT && deg > 0) {
-            // view direction -> mean (dgr back-propagates it; gsplat renderers detach the direction)
+        if (!COOP && vis && !GSPLAT && deg > 0) {
+            // view direction -> mean, per-lane loads of the SH block (B200GS_K8_COOP=0)
             float sh[MC * 3];
             load_sh_any<RAW, MC>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
             float bx[MC], by[MC], bz[MC];
@@ -916,13 +1119,17 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __
     const int stride3 = vp.v[0].sh_stride * 3;
     const int deg = vp.v[0].sh_degree;
     const int ncoef = (deg + 1) * (deg + 1);
-    float out[MC * 3];
-#pragma unroll
-    for (int k = 0; k < MC * 3; ++k) out[k] = 0.f;
+    // SH-gradient accumulators over the cameras: the dc coefficient in registers, the rest in this lane's row of the staging buffer
+    // (48 accumulator registers kept the kernel at 183 registers = 8 warps per SM); rows wider than the buffer keep the register path
+    const int rw = stride3 - 3;                      // <= MC * 3: the launcher picks MC by the storage width
+    float* my_row = s_rows[warp] + lane * (rw | 1);
+    float dc_acc[3] = {0.f, 0.f, 0.f};
+    for (int c = 0; c < rw; ++c) my_row[c] = 0.f;
     float dm[3] = {0.f, 0.f, 0.f}, dscale[3] = {0.f, 0.f, 0.f}, dlogit = 0.f;
     float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
     float p[3] = {0.f, 0.f, 0.f}, sc[3] = {1.f, 1.f, 1.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, inv_qn = 1.f, o = 0.f;
     bool loaded = false;
+    Proj<float> g;
 #pragma unroll 1
     for (int j = 0; j < nviews; ++j) {
         const int64_t e = int64_t(j) * n + i;
@@ -936,6 +1143,8 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __
             p[0] = __ldg(means + 3 * i); p[1] = __ldg(means + 3 * i + 1); p[2] = __ldg(means + 3 * i + 2);
             load_scale_quat<true, float>(scales, quats, i, sc, q, &inv_qn);
             o = 1.0f / (1.0f + expf(-__ldg(raw.opac_in + i)));
+            gaussian_cov3d<float>(sc, q, vp.v[0].scale_modifier, g);      // once per Gaussian; project_view per camera
+            g.qr = q[0]; g.qx = q[1]; g.qy = q[2]; g.qz = q[3];
             loaded = true;
         }
         const B200gsView& v = vp.v[j];
@@ -948,17 +1157,16 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __
             dx *= inv_len; dy *= inv_len; dz *= inv_len;
             float bs[MC];
             sh_basis<MC>(deg, dx, dy, dz, bs);
+            dc_acc[0] = fmaf(bs[0], gr, dc_acc[0]); dc_acc[1] = fmaf(bs[0], gg, dc_acc[1]); dc_acc[2] = fmaf(bs[0], gb, dc_acc[2]);
 #pragma unroll
-            for (int k = 0; k < MC; ++k) {
-                const float bk = (k < ncoef) ? bs[k] : 0.f;
-                out[3 * k + 0] = fmaf(bk, gr, out[3 * k + 0]);
-                out[3 * k + 1] = fmaf(bk, gg, out[3 * k + 1]);
-                out[3 * k + 2] = fmaf(bk, gb, out[3 * k + 2]);
+            for (int k = 1; k < MC; ++k) {
+                if (k < ncoef && 3 * k < rw + 3) {
+                    float* a = my_row + 3 * k - 3;
+                    a[0] = fmaf(bs[k], gr, a[0]); a[1] = fmaf(bs[k], gg, a[1]); a[2] = fmaf(bs[k], gb, a[2]);
+                }
             }
         }
-        Proj<float> g;
-        project_geometry<true, float>(v, p, sc, q, g);
-        g.qr = q[0]; g.qx = q[1]; g.qy = q[2]; g.qz = q[3];
+        project_view<true, float>(v, p, g);
         ProjCot c;
         c.vxy = make_float2(w0.x, w0.y);
         c.vdepth = w0.z;
@@ -974,7 +1182,8 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __
         dlogit += v_sig * o * (1.0f - o);
         geometry_backward<true>(v, p, g, c, dm, dscale, dq);
     }
-    store_sh_rows<true, MC>(s_rows[warp], out, i, n, in_range, stride3, lane, v_shs_dc, raw.v_shs_rest, false);
+    if (in_range) { v_shs_dc[3 * i] = dc_acc[0]; v_shs_dc[3 * i + 1] = dc_acc[1]; v_shs_dc[3 * i + 2] = dc_acc[2]; }
+    flush_sh_rows<true>(s_rows[warp], rw, i, n, lane, raw.v_shs_rest, false);
     if (!in_range) return;
     v_means[3 * i] = dm[0]; v_means[3 * i + 1] = dm[1]; v_means[3 * i + 2] = dm[2];
 #pragma unroll
@@ -1066,19 +1275,37 @@ int launch_project_fwd_raw(const B200gsView& v, int64_t n, const float* means, c
     const bool raw_mode = opac_out != nullptr || rows != nullptr;
     RawIO raw{opac_logits, shs_rest, opac_out, nullptr, nullptr, nullptr, anti_aliased, nullptr, nullptr, 0};
 #define B200GS_PF_ARGS v, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth, radii, conic, comp, tiles, cov3d, rgb, clamped, rows
+    // SH rows through per-lane loads (default) or the warp-cooperative staging (B200GS_K1_COOP=1)
+    // Measured at 1 M / 1080p (profiles/round2_call5_*): the staging cuts K1's L1 sectors 4x (5.3 instead of 18.9 per request) but the
+    // kernel is latency- not LSU-bound and the per-row loop has fewer loads in flight: 0.099 ms against 0.074 ms.  Off by default.
+    static const bool coop_env = []() { const char* e = getenv("B200GS_K1_COOP"); return e && e[0] == '1'; }();
+    static const bool prefetch_env = []() { const char* e = getenv("B200GS_K1_PREFETCH"); return !(e && e[0] == '0'); }();
+    const bool coop = coop_env && shs_dc != nullptr;
+    raw.prefetch_sh = prefetch_env ? 1 : 0;
+#define B200GS_PF_ONE(G, R, MC, C)                                                                               \
+    do {                                                                                                         \
+        const size_t smem = (C) ? sizeof(float) * (threads / 32) * ShStage<MC>::WARP_FLOATS : 0;                 \
+        if (C) {                                                                                                 \
+            static const cudaError_t attr = cudaFuncSetAttribute((const void*)project_fwd_kernel<G, R, MC, C>,   \
+                                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (attr != cudaSuccess) { set_error("project_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr)); return B200GS_ECUDA; } \
+        }                                                                                                        \
+        project_fwd_kernel<G, R, MC, C><<<blocks, threads, smem, s>>>(B200GS_PF_ARGS);                           \
+    } while (0)
 #define B200GS_PF_LAUNCH(MC)                                                                                    \
     do {                                                                                                         \
         if (v.mode == B200GS_MODE_GSPLAT) {                                                                      \
-            if (raw_mode) project_fwd_kernel<true, true, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);         \
-            else project_fwd_kernel<true, false, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);                 \
+            if (raw_mode) { if (coop) B200GS_PF_ONE(true, true, MC, true); else B200GS_PF_ONE(true, true, MC, false); }       \
+            else          { if (coop) B200GS_PF_ONE(true, false, MC, true); else B200GS_PF_ONE(true, false, MC, false); }     \
         } else {                                                                                                 \
-            if (raw_mode) project_fwd_kernel<false, true, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);        \
-            else project_fwd_kernel<false, false, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);                \
+            if (raw_mode) { if (coop) B200GS_PF_ONE(false, true, MC, true); else B200GS_PF_ONE(false, true, MC, false); }     \
+            else          { if (coop) B200GS_PF_ONE(false, false, MC, true); else B200GS_PF_ONE(false, false, MC, false); }   \
         }                                                                                                        \
     } while (0)
     if (shs_dc != nullptr && v.sh_degree > 3) B200GS_PF_LAUNCH(25);
     else B200GS_PF_LAUNCH(16);
 #undef B200GS_PF_LAUNCH
+#undef B200GS_PF_ONE
 #undef B200GS_PF_ARGS
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
@@ -1105,14 +1332,20 @@ int launch_project_bwd_raw(const B200gsView& v, int64_t n, const float* means, c
     RawIO raw{opac_logits, shs_rest, nullptr, v_opac, v_opac_logit, v_shs_rest, anti_aliased, v_rows, row_offsets, accumulate};
 #define B200GS_PB_ARGS v, raw, n, means, scales, quats, shs_dc, radii, clamped, (const float2*)v_xy, v_depth, v_conic, v_comp, v_rgb, \
                        v_means, v_scales, (float4*)v_quats, v_shs_dc
+    // vanilla mode re-reads the SH rows for the view-direction gradient: per-lane loads (default) or warp-cooperative staging (B200GS_K8_COOP=1)
+    // measured slower than the per-lane loads (0.153 vs 0.129 ms at 1 M / 1080p, profiles/round2_call5_*): opt-in
+    static const bool coop = []() { const char* e = getenv("B200GS_K8_COOP"); return e && e[0] == '1'; }();
 #define B200GS_PB_LAUNCH(MC)                                                                                    \
     do {                                                                                                         \
         if (v.mode == B200GS_MODE_GSPLAT) {                                                                      \
-            if (raw_mode) project_bwd_kernel<true, true, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);         \
-            else project_bwd_kernel<true, false, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);                 \
+            if (raw_mode) project_bwd_kernel<true, true, MC, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);  \
+            else project_bwd_kernel<true, false, MC, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);          \
+        } else if (coop) {                                                                                       \
+            if (raw_mode) project_bwd_kernel<false, true, MC, true><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);  \
+            else project_bwd_kernel<false, false, MC, true><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);          \
         } else {                                                                                                 \
-            if (raw_mode) project_bwd_kernel<false, true, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);        \
-            else project_bwd_kernel<false, false, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);                \
+            if (raw_mode) project_bwd_kernel<false, true, MC, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS); \
+            else project_bwd_kernel<false, false, MC, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);         \
         }                                                                                                        \
     } while (0)
     if (v_shs_dc != nullptr && v.sh_degree > 3) B200GS_PB_LAUNCH(25);
@@ -1203,7 +1436,12 @@ int launch_project_bwd_multi(const B200gsView* views, int n_views, int64_t n, co
         src.rows[j] = (j < n_views && v_rows[j]) ? v_rows[j] : dummy;   // NULL only when no row of that view is ever read
     }
     RawIO raw{opac_logits, shs_rest, nullptr, nullptr, v_opac_logit, v_shs_rest, anti_aliased, nullptr, nullptr, 0};
-    if (views[0].sh_degree > 3)
+    // the SH-gradient rows accumulate in the kernel's staging buffer: coefficient storage wider than 16 takes the 25-coefficient instantiation
+    if (views[0].sh_stride > 25) {
+        set_error("project_bwd_multi: sh_stride %d exceeds 25 coefficients", views[0].sh_stride);
+        return B200GS_EINVAL;
+    }
+    if (views[0].sh_degree > 3 || views[0].sh_stride > 16)
         project_bwd_multi_kernel<25><<<(unsigned)div_up64(n, BWD_THREADS), BWD_THREADS, 0, s>>>(vp, n_views, raw, src, n, means, scales, quats, radii,
                                                                                                 clamped, row_index, v_means, v_scales, (float4*)v_quats,
                                                                                                 v_shs_dc);
