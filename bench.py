@@ -314,12 +314,15 @@ class Workload:
         cam = self.cams[(i * self.world + self.rank) % len(self.cams)]   # each rank renders a different pose
         for p in self.model.parameters():
             p.grad = None
+        out = self.renderer(cam, self.model, self.bg)
         if e2e:
+            # the uploaded image is first needed by the loss, not by the renderer: the compute stream waits for it HERE, so an upload
+            # that takes longer than the previous step's backward (24.9 MB over PCIe ~ 0.5 ms vs ~0.57 ms of backward) runs on under
+            # this step's forward instead of stalling it (round 2: e2e fell to 490 views/s in some runs with the wait in front)
             torch.cuda.current_stream().wait_event(self.in_ready[i & 1])
             c = self.in_bufs[i & 1]
         else:
             c = self.cot
-        out = self.renderer(cam, self.model, self.bg)
         if e2e and more:
             self.prefetch(i + 1)
         loss = (out["render"] * c).sum()

@@ -132,10 +132,11 @@ int b200gs_project_bwd_rows(const B200gsView* view, int64_t n, const float* mean
                             const float* opacity_logits, const float* shs_dc, const float* shs_rest, int32_t anti_aliased,
                             const int32_t* radii, const uint8_t* clamped, const int32_t* row_offsets, const float* v_rows,
                             int32_t accumulate, float* v_means, float* v_log_scales, float* v_raw_quats, float* v_opacity_logits,
-                            float* v_shs_dc, float* v_shs_rest, void* stream) {
+                            float* v_shs_dc, float* v_shs_rest, float* v_mean2d, int32_t v_mean2d_cols, void* stream) {
     int rc = check_view(view, true);
     if (rc) return rc;
     B200GS_CHECK_ARG(n >= 0, "n < 0");
+    B200GS_CHECK_ARG(v_mean2d == nullptr || v_mean2d_cols == 2 || v_mean2d_cols == 3, "v_mean2d_cols must be 2 or 3");
     if (n > 0) {
         B200GS_CHECK_ARG(means && log_scales && raw_quats && opacity_logits && shs_dc && radii && clamped, "NULL input pointer");
         B200GS_CHECK_ARG(view->sh_stride == 1 || (shs_rest && v_shs_rest), "shs_rest / v_shs_rest required when sh_stride > 1");
@@ -145,7 +146,7 @@ int b200gs_project_bwd_rows(const B200gsView* view, int64_t n, const float* mean
     return launch_project_bwd_raw(*view, n, means, log_scales, raw_quats, opacity_logits, shs_dc, shs_rest, anti_aliased, radii,
                                   clamped, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v_means, v_log_scales, v_raw_quats,
                                   v_opacity_logits, v_shs_dc, v_shs_rest, (cudaStream_t)stream, v_rows ? v_rows : &dummy, row_offsets,
-                                  accumulate);
+                                  accumulate, v_mean2d, v_mean2d_cols);
 }
 
 static int check_views(const B200gsView* views, int32_t n_views) {
@@ -454,24 +455,29 @@ int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height, int64_t n
 
 int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                           const float* rows, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride, float* final_T,
-                          int32_t* n_contrib, float* alpha, void* stream) {
+                          int32_t* n_contrib, float* alpha, const int32_t* tile_order, void* stream) {
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
     B200GS_CHECK_ARG(width > 0 && height > 0 && tile_ranges && image && final_T && n_contrib, "bad argument");
     return launch_blend_fwd(mode, width, height, 3, tile_ranges, sorted_ids, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY,
                             rows + B200GS_ROW_CONIC, rows + B200GS_ROW_OPACITY, rows + B200GS_ROW_RGB, bg, image, pix_stride,
-                            ch_stride, final_T, n_contrib, alpha, (cudaStream_t)stream);
+                            ch_stride, final_T, n_contrib, alpha, (cudaStream_t)stream, nullptr, tile_order);
+}
+
+int b200gs_tile_order(int32_t width, int32_t height, const int32_t* tile_ranges, int32_t* tile_order, void* stream) {
+    B200GS_CHECK_ARG(width > 0 && height > 0 && tile_ranges && tile_order, "bad argument");
+    return tile_order_impl(width, height, tile_ranges, tile_order, (cudaStream_t)stream);
 }
 
 int b200gs_blend_bwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                           const float* rows, const float* bg, const float* final_T, const int32_t* n_contrib, const float* v_image,
                           int64_t pix_stride, int64_t ch_stride, const float* v_alpha, float grad_scale_x, float grad_scale_y,
-                          float* v_rows, void* stream) {
+                          float* v_rows, const int32_t* tile_order, void* stream) {
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
     B200GS_CHECK_ARG(width > 0 && height > 0 && tile_ranges && final_T && n_contrib && v_image && v_rows, "bad argument");
     return launch_blend_bwd(mode, width, height, 3, tile_ranges, sorted_ids, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY,
                             rows + B200GS_ROW_CONIC, rows + B200GS_ROW_OPACITY, rows + B200GS_ROW_RGB, bg, final_T, n_contrib, v_image,
                             pix_stride, ch_stride, v_alpha, grad_scale_x, grad_scale_y, v_rows + B200GS_ROW_XY, v_rows + B200GS_ROW_CONIC,
-                            v_rows + B200GS_ROW_OPACITY, v_rows + B200GS_ROW_RGB, nullptr, (cudaStream_t)stream);
+                            v_rows + B200GS_ROW_OPACITY, v_rows + B200GS_ROW_RGB, nullptr, (cudaStream_t)stream, -1, tile_order);
 }
 
 }  // extern "C"

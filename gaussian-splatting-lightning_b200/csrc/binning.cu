@@ -102,6 +102,17 @@ LayoutA make_layout_a(int64_t n) {
     return L;
 }
 
+// The sort payload is the Gaussian id; when the id fits 24 bits and a rect can cover at most 255 coarse cells, the cell count of the
+// rect rides in the top byte ({key, ncells << 24 | id}): rank_offsets then reads its counts from the sorted records it streams through
+// anyway instead of gathering one random 32-byte sector per rank (0.65 M L2 requests = most of that kernel's 21 us).  Decided from
+// (n, width, height) alone, so bin_count and bin_sort agree.
+inline bool pack_ncells(int64_t n, int width, int height) {
+    const int gx = div_up(width, TILE), gy = div_up(height, TILE);
+    const int cells = div_up(gx, 1 << 3) * div_up(gy, 1 << 3);
+    return n < (int64_t(1) << 24) && cells <= 255;
+}
+constexpr uint32_t ID_MASK = (1u << 24) - 1u;
+
 inline void cell_grid(int width, int height, int& grid_x, int& grid_y, int& cgrid_x, int& cgrid_y) {
     grid_x = div_up(width, TILE);
     grid_y = div_up(height, TILE);
@@ -265,7 +276,7 @@ constexpr int DK_ITEMS = 8;
 
 // ROWS16: the inputs are the columns of one 16-byte aligned [n,12] row buffer (b200gs.h row layout): three 128-bit loads per Gaussian
 template <bool GSPLAT, bool ROWS16>
-__global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, int grid_y, const BinSrc src, uint2* __restrict__ keyrec,
+__global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, int grid_y, int pack, const BinSrc src, uint2* __restrict__ keyrec,
                                                          SplatRec* __restrict__ recs, uint32_t* __restrict__ ticket,
                                                          uint32_t* __restrict__ scan_state, uint32_t* __restrict__ hist,
                                                          unsigned long long* __restrict__ counts) {
@@ -282,12 +293,14 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
     const int64_t base_i = int64_t(t) * (256 * DK_ITEMS) + threadIdx.x;
     unsigned long long area_sum = 0, cell_sum = 0;
     uint32_t key[DK_ITEMS];
+    uint32_t hi8[DK_ITEMS];          // pack: the rect's cell count << 24 (rides in the top byte of the sort payload), else 0
     unsigned vis_bits = 0;           // bit k: this thread's Gaussian of round k is visible
     unsigned below[DK_ITEMS];        // visible lanes below this one in round k's ballot
 #pragma unroll
     for (int k = 0; k < DK_ITEMS; ++k) {
         const int64_t i = base_i + k * 256;
         key[k] = 0xFFFFFFFFu;
+        hi8[k] = 0u;
         bool vis = false;
         if (i < n) {
             float px, py, dep, A = 1.f, B = 0.f, C = 1.f, o = 1.f;
@@ -321,6 +334,7 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
                     coarsen_rect(x0, y0, x1, y1, cx0, cy0, cx1, cy1);
                     const int ncell = (cx1 - cx0) * (cy1 - cy0);
                     key[k] = __float_as_uint(dep);
+                    hi8[k] = pack ? ((uint32_t)ncell << 24) : 0u;
                     area_sum += (unsigned long long)area;
                     cell_sum += (unsigned long long)ncell;
                     vis = true;
@@ -356,7 +370,7 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
         const int block_vis = __shfl_sync(0xffffffffu, inc, 31);
         s_cnt[2 * lane] = inc - c0 - c1;
         s_cnt[2 * lane + 1] = inc - c1;
-        const uint32_t excl = sweep::chained_exclusive<8, 8>(scan_state, t, (uint32_t)block_vis);
+        const uint32_t excl = sweep::chained_exclusive(scan_state, t, (uint32_t)block_vis);
         if (threadIdx.x == 0) {
             s_excl = excl;
             if (t == (int)gridDim.x - 1) counts[3] = (unsigned long long)(excl + (uint32_t)block_vis);
@@ -367,7 +381,7 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
 #pragma unroll
     for (int k = 0; k < DK_ITEMS; ++k) {
         if (!((vis_bits >> k) & 1u)) continue;
-        keyrec[base + (uint32_t)s_cnt[k * 8 + w] + below[k]] = make_uint2(key[k], (uint32_t)(base_i + k * 256));
+        keyrec[base + (uint32_t)s_cnt[k * 8 + w] + below[k]] = make_uint2(key[k], (uint32_t)(base_i + k * 256) | hi8[k]);
     }
     unsigned long long a = area_sum, c = cell_sum;
 #pragma unroll
@@ -394,7 +408,7 @@ __global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, int grid_x, 
 // tiles (RO_ITEMS consecutive ranks per thread) for the same reason as above; the cell count of a rank is gathered from its record.
 constexpr int RO_ITEMS = 8;
 
-__global__ void __launch_bounds__(256) rank_offsets_kernel(const int64_t* __restrict__ d_visible, const uint2* __restrict__ order,
+__global__ void __launch_bounds__(256) rank_offsets_kernel(const int64_t* __restrict__ d_visible, int pack, const uint2* __restrict__ order,
                                                           const SplatRec* __restrict__ recs, uint32_t* __restrict__ offsets,
                                                           uint32_t* __restrict__ ticket, uint32_t* __restrict__ scan_state) {
     __shared__ int s_scan[sweep::WARPS + 1];
@@ -411,13 +425,16 @@ __global__ void __launch_bounds__(256) rank_offsets_kernel(const int64_t* __rest
 #pragma unroll
     for (int k = 0; k < RO_ITEMS; ++k) {
         nc[k] = 0;
-        if (r0 + k < n) nc[k] = __ldg(&recs[order[r0 + k].y].ncells);
+        if (r0 + k < n) {
+            const uint32_t y = order[r0 + k].y;
+            nc[k] = pack ? (int)(y >> 24) : __ldg(&recs[y].ncells);
+        }
         mine += nc[k];
     }
     int block_total;
     int local = sweep::block_exclusive(mine, s_scan, &block_total);
     if (threadIdx.x < 32) {
-        const uint32_t excl = sweep::chained_exclusive<8, 8>(scan_state, t, (uint32_t)block_total);
+        const uint32_t excl = sweep::chained_exclusive(scan_state, t, (uint32_t)block_total);
         if (threadIdx.x == 0) s_excl = excl;
     }
     __syncthreads();
@@ -437,10 +454,11 @@ __global__ void __launch_bounds__(256) rank_offsets_kernel(const int64_t* __rest
 // for the one lane that owns a large splat.  The block also counts its entries per cell (the histogram the partition and
 // the cell ranges are derived from).
 constexpr int EMIT_SLOTS = 2048;
+constexpr int EMIT_ITEMS = 2048;  // (rank, row) work items resolved through a table instead of a binary search
 constexpr int EMIT_HIST = 1024;   // cells counted in shared memory (images up to 4096 x 4096); larger grids count straight in global memory
 
 template <bool GSPLAT>
-__global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restrict__ d_visible, int grid_x, int grid_y, int cgrid_x, int cull,
+__global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restrict__ d_visible, int pack, int grid_x, int grid_y, int cgrid_x, int cull,
                                                          int64_t max_coarse, const uint2* __restrict__ order, const SplatRec* __restrict__ recs,
                                                          const uint32_t* __restrict__ offsets, CellEntry* __restrict__ entries, int n_cells,
                                                          uint32_t* __restrict__ cell_hist) {
@@ -450,6 +468,7 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restri
     __shared__ float s_f[8][256];        // mx, my, B, iA, two_tA, det, ymax, yR
     __shared__ int s_mode[256], s_xr[256], s_yr[256], s_start[256];   // x0 | x1 << 16, y0 | y1 << 16, first slot - block_lo
     __shared__ int s_rowoff[260];
+    __shared__ unsigned char s_item[EMIT_ITEMS];   // work item -> rank of the block (when the block has <= EMIT_ITEMS tile rows)
     __shared__ int s_warp[8];
     __shared__ uint32_t s_hist[EMIT_HIST];
     const int tid = threadIdx.x;
@@ -464,7 +483,7 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restri
     int g = -1, x0 = 0, y0 = 0, x1 = 0, y1 = 0, t = 0, nrows = 0;
     CullE e{};
     if (rnk < n) {
-        g = (int)order[rnk].y;
+        g = (int)(pack ? (order[rnk].y & ID_MASK) : order[rnk].y);
         const float4* rp = reinterpret_cast<const float4*>(recs + g);
         const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
         SplatRec rec;
@@ -480,7 +499,8 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restri
     // first slot of this rank = cells of the ranks before it (rank_offsets_kernel); the block's ranks own one contiguous window
     const int64_t block_lo = (int64_t)offsets[rank0];
     const int64_t last_rank = min(rank0 + (int64_t)blockDim.x, n) - 1;
-    const int block_cells = (int)((int64_t)offsets[last_rank] + __ldg(&recs[order[last_rank].y].ncells) - block_lo);
+    const uint32_t last_y = order[last_rank].y;
+    const int block_cells = (int)((int64_t)offsets[last_rank] + (pack ? (int)(last_y >> 24) : __ldg(&recs[last_y].ncells)) - block_lo);
     const int local_start = (rnk < n) ? (int)((int64_t)offsets[rnk] - block_lo) : block_cells;
     // exclusive scan of the row counts
     int inc = nrows;
@@ -508,6 +528,11 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restri
     const int cw = t > 0 ? ((x1 - 1) >> SUPER_SHIFT) - cx0 + 1 : 1;
     __syncthreads();
     const int total_rows = s_rowoff[256];
+    const bool item_table = total_rows <= EMIT_ITEMS;
+    if (item_table) {     // rank tid owns items [s_rowoff[tid], s_rowoff[tid] + nrows)
+        const int o = s_rowoff[tid];
+        for (int k = 0; k < nrows; ++k) s_item[o + k] = (unsigned char)tid;
+    }                     // visible to the item loop after the barrier that follows the cell/id stores below
     const int64_t block_hi = min(block_lo + block_cells, max_coarse);
     for (int64_t lo = block_lo; lo < block_hi; lo += EMIT_SLOTS) {
         const int cn = (int)min((int64_t)EMIT_SLOTS, block_hi - lo);
@@ -531,9 +556,13 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(const int64_t* __restri
         // (rank, row) work items
         for (int it = tid; it < total_rows; it += 256) {
             int r = 0;
+            if (item_table) {
+                r = s_item[it];
+            } else {
 #pragma unroll
-            for (int step = 128; step >= 1; step >>= 1)
-                if (s_rowoff[r + step] <= it) r += step;
+                for (int step = 128; step >= 1; step >>= 1)
+                    if (s_rowoff[r + step] <= it) r += step;
+            }
             CullE q;
             q.mx = s_f[0][r]; q.my = s_f[1][r]; q.B = s_f[2][r]; q.iA = s_f[3][r];
             q.two_tA = s_f[4][r]; q.det = s_f[5][r]; q.ymax = s_f[6][r]; q.yR = s_f[7][r];
@@ -966,7 +995,8 @@ int bin_count(int mode, int width, int height, int64_t n, int row_stride, const 
         const bool rows16 = row_stride == B200GS_ROW_FLOATS && conic != nullptr && depth == xy + B200GS_ROW_DEPTH && conic == xy + B200GS_ROW_CONIC &&
                             opacity == xy + B200GS_ROW_OPACITY && reinterpret_cast<const float*>(radii) == xy + B200GS_ROW_RADIUS &&
                             (reinterpret_cast<uintptr_t>(xy) & 15) == 0;
-#define B200GS_DK_LAUNCH(G, R) depth_keys_kernel<G, R><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, src, rec_a, recs, tickets, scan_state, hist, (unsigned long long*)d_counts)
+        const int pack = pack_ncells(n, width, height) ? 1 : 0;
+#define B200GS_DK_LAUNCH(G, R) depth_keys_kernel<G, R><<<blocks, 256, 0, s>>>(n, grid_x, grid_y, pack, src, rec_a, recs, tickets, scan_state, hist, (unsigned long long*)d_counts)
         if (mode == B200GS_MODE_GSPLAT) { if (rows16) B200GS_DK_LAUNCH(true, true); else B200GS_DK_LAUNCH(true, false); }
         else                            { if (rows16) B200GS_DK_LAUNCH(false, true); else B200GS_DK_LAUNCH(false, false); }
 #undef B200GS_DK_LAUNCH
@@ -1035,13 +1065,14 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
     B200GS_CUDA(cudaMemsetAsync(w + L.zero, 0, L.zero_bytes, s));
     const bool two_pass = n_cells > sweep::RADIX;
     CellEntry* emit_dst = two_pass ? entries : entries_in;   // one pass: in -> entries; two passes: entries -> in -> entries
-    rank_offsets_kernel<<<(unsigned)L.scan_blocks, 256, 0, s>>>(d_visible, order, recs, offsets, tickets, scan_state);
+    const int pack = pack_ncells(n, width, height) ? 1 : 0;
+    rank_offsets_kernel<<<(unsigned)L.scan_blocks, 256, 0, s>>>(d_visible, pack, order, recs, offsets, tickets, scan_state);
     B200GS_LAUNCH_CHECK();
     if (mode == B200GS_MODE_GSPLAT)
-        emit_cells_kernel<true><<<(unsigned)L.blocks, 256, 0, s>>>(d_visible, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, emit_dst,
+        emit_cells_kernel<true><<<(unsigned)L.blocks, 256, 0, s>>>(d_visible, pack, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, emit_dst,
                                                                     n_cells, cell_hist);
     else
-        emit_cells_kernel<false><<<(unsigned)L.blocks, 256, 0, s>>>(d_visible, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, emit_dst,
+        emit_cells_kernel<false><<<(unsigned)L.blocks, 256, 0, s>>>(d_visible, pack, grid_x, grid_y, cgrid_x, cull, max_coarse, order, recs, offsets, emit_dst,
                                                                      n_cells, cell_hist);
     B200GS_LAUNCH_CHECK();
     cell_table_kernel<<<1, 1024, 0, s>>>(n_cells, cell_hist, cell_ranges, chunk_base, chunk_cell, digit_hist, n_tiles, tile_start);
@@ -1070,6 +1101,47 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
                                                 tile_start, sorted_ids);
     B200GS_LAUNCH_CHECK();
     return copy_counts(d_counts, host_counts, sync_host, s);
+}
+
+// ---- processing order of the tiles for the blend kernels ---------------------------------------------------------------------
+// One CTA per tile and ~14-18 waves of CTAs: in natural (row-major) order the kernel ends when the last-started long tile ends, with
+// most SMs idle (ncu, round 2: K7 averaged 28 of its 32 resident warps).  order[] lists the tiles by decreasing list length — counting
+// sort on 4 x log2 buckets, tiles of a bucket roughly in row-major order (neighbouring tiles share their splats in L2) — so the long
+// tiles start first and the tail is made of short ones (longest-processing-time-first list scheduling).  One block.
+constexpr int ORDER_BUCKETS = 4 * 32 + 1;
+
+__global__ void __launch_bounds__(1024) tile_order_kernel(int n_tiles, const int2* __restrict__ ranges, int32_t* __restrict__ order) {
+    __shared__ int s_cnt[ORDER_BUCKETS];
+    __shared__ int s_pos[ORDER_BUCKETS];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < ORDER_BUCKETS; i += 1024) s_cnt[i] = 0;
+    __syncthreads();
+    auto bucket = [](int2 r) {
+        const int c = r.y - r.x;
+        if (c <= 0) return 0;
+        const int lg = 31 - __clz(c);                                   // 0..30
+        const int frac = lg >= 2 ? ((c >> (lg - 2)) & 3) : 0;           // next two bits below the leading one
+        return 1 + 4 * lg + frac;
+    };
+    for (int i = tid; i < n_tiles; i += 1024) atomicAdd(&s_cnt[bucket(ranges[i])], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int b = ORDER_BUCKETS - 1; b >= 0; --b) { s_pos[b] = run; run += s_cnt[b]; }
+    }
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {                  // sweep by sweep: keeps a bucket's tiles near row-major order
+        const int i = base + tid;
+        if (i < n_tiles) order[atomicAdd(&s_pos[bucket(ranges[i])], 1)] = i;
+        __syncthreads();
+    }
+}
+
+int tile_order_impl(int width, int height, const int32_t* tile_ranges, int32_t* order, cudaStream_t s) {
+    const int n_tiles = div_up(width, TILE) * div_up(height, TILE);
+    tile_order_kernel<<<1, 1024, 0, s>>>(n_tiles, (const int2*)tile_ranges, order);
+    B200GS_LAUNCH_CHECK();
+    return B200GS_OK;
 }
 
 // ---- row packing for the Gaussian-sharded exchange -------------------------------------------------------------------

@@ -50,27 +50,51 @@ __device__ __forceinline__ void load_sh(const float* __restrict__ base, int ncoe
     }
 }
 
-// basis values for unit direction (x,y,z); writes (deg+1)^2 entries
+// ---- arithmetic with the evaluation order written out ---------------------------------------------------------------------
+// The same inline function compiled into two kernels is NOT guaranteed to round the same way: where a product has several uses (x*x,
+// b*b, ...) nvcc's fmul+fadd -> fma contraction depends on the surrounding code (measured, round 2: the SH colours of the single-view
+// K1 and of the multi-view K1 of the sharded renderer differed in the last bit for ~1 % of the splats -> a sharded image 1 ulp off
+// the single-GPU image).  Everything the FORWARD projection computes therefore goes through these helpers: __fmul_rn / __fadd_rn /
+// __fmaf_rn (and the double versions) are never contracted, split or reassociated, so every kernel that inlines the functions below
+// produces the same bits (tests/test_gpu_sharded_kernels.py).
+__device__ __forceinline__ float xm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xf(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double xm(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xa(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xf(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// unit view direction camera -> Gaussian and 1 / distance
+__device__ __forceinline__ void view_dir(const float* p, const float* campos, float& dx, float& dy, float& dz, float& inv_len) {
+    dx = xa(p[0], -campos[0]); dy = xa(p[1], -campos[1]); dz = xa(p[2], -campos[2]);
+    inv_len = rsqrtf(xf(dz, dz, xf(dy, dy, xm(dx, dx))));
+    dx = xm(dx, inv_len); dy = xm(dy, inv_len); dz = xm(dz, inv_len);
+}
+
+// basis values for unit direction (x,y,z); writes (deg+1)^2 entries (sh_utils.py:57-112)
 template <int MC>
 __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float* b) {
     b[0] = SH_C0;
     if (deg > 0) {
-        b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
+        b[1] = xm(-SH_C1, y); b[2] = xm(SH_C1, z); b[3] = xm(-SH_C1, x);
         if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            b[4] = SH_C2[0] * xy; b[5] = SH_C2[1] * yz; b[6] = SH_C2[2] * (2.0f * zz - xx - yy);
-            b[7] = SH_C2[3] * xz; b[8] = SH_C2[4] * (xx - yy);
+            const float xx = xm(x, x), yy = xm(y, y), zz = xm(z, z), xy = xm(x, y), yz = xm(y, z), xz = xm(x, z);
+            const float xx_yy = xa(xx, -yy);
+            b[4] = xm(SH_C2[0], xy); b[5] = xm(SH_C2[1], yz); b[6] = xm(SH_C2[2], xa(xf(2.0f, zz, -xx), -yy));
+            b[7] = xm(SH_C2[3], xz); b[8] = xm(SH_C2[4], xx_yy);
             if (deg > 2) {
-                b[9] = SH_C3[0] * y * (3.0f * xx - yy); b[10] = SH_C3[1] * xy * z;
-                b[11] = SH_C3[2] * y * (4.0f * zz - xx - yy); b[12] = SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-                b[13] = SH_C3[4] * x * (4.0f * zz - xx - yy); b[14] = SH_C3[5] * z * (xx - yy);
-                b[15] = SH_C3[6] * x * (xx - 3.0f * yy);
+                const float t4 = xa(xf(4.0f, zz, -xx), -yy);          // 4 zz - xx - yy
+                b[9] = xm(xm(SH_C3[0], y), xf(3.0f, xx, -yy)); b[10] = xm(xm(SH_C3[1], xy), z);
+                b[11] = xm(xm(SH_C3[2], y), t4); b[12] = xm(xm(SH_C3[3], z), xf(-3.0f, yy, xf(-3.0f, xx, xm(2.0f, zz))));
+                b[13] = xm(xm(SH_C3[4], x), t4); b[14] = xm(xm(SH_C3[5], z), xx_yy);
+                b[15] = xm(xm(SH_C3[6], x), xf(-3.0f, yy, xx));
                 if (MC > 16 && deg > 3) {
-                    b[16] = SH_C4[0] * xy * (xx - yy); b[17] = SH_C4[1] * yz * (3.0f * xx - yy);
-                    b[18] = SH_C4[2] * xy * (7.0f * zz - 1.0f); b[19] = SH_C4[3] * yz * (7.0f * zz - 3.0f);
-                    b[20] = SH_C4[4] * (zz * (35.0f * zz - 30.0f) + 3.0f); b[21] = SH_C4[5] * xz * (7.0f * zz - 3.0f);
-                    b[22] = SH_C4[6] * (xx - yy) * (7.0f * zz - 1.0f); b[23] = SH_C4[7] * xz * (xx - 3.0f * yy);
-                    b[24] = SH_C4[8] * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy));
+                    const float s7 = xf(7.0f, zz, -1.0f), t7 = xf(7.0f, zz, -3.0f);
+                    b[16] = xm(xm(SH_C4[0], xy), xx_yy); b[17] = xm(xm(SH_C4[1], yz), xf(3.0f, xx, -yy));
+                    b[18] = xm(xm(SH_C4[2], xy), s7); b[19] = xm(xm(SH_C4[3], yz), t7);
+                    b[20] = xm(SH_C4[4], xf(zz, xf(35.0f, zz, -30.0f), 3.0f)); b[21] = xm(xm(SH_C4[5], xz), t7);
+                    b[22] = xm(xm(SH_C4[6], xx_yy), s7); b[23] = xm(xm(SH_C4[7], xz), xf(-3.0f, yy, xx));
+                    b[24] = xm(SH_C4[8], xf(xx, xf(-3.0f, yy, xx), -xm(yy, xf(3.0f, xx, -yy))));
                 }
             }
         }
@@ -139,9 +163,10 @@ struct Proj {
 template <typename R>
 __device__ __forceinline__ void quat_to_rot(const R* q, R* Rm) {
     const R r = q[0], x = q[1], y = q[2], z = q[3];
-    Rm[0] = R(1) - R(2) * (y * y + z * z); Rm[1] = R(2) * (x * y - r * z); Rm[2] = R(2) * (x * z + r * y);
-    Rm[3] = R(2) * (x * y + r * z); Rm[4] = R(1) - R(2) * (x * x + z * z); Rm[5] = R(2) * (y * z - r * x);
-    Rm[6] = R(2) * (x * z - r * y); Rm[7] = R(2) * (y * z + r * x); Rm[8] = R(1) - R(2) * (x * x + y * y);
+    const R two = R(2), one = R(1);
+    Rm[0] = xf(-two, xf(z, z, xm(y, y)), one); Rm[1] = xm(two, xf(-r, z, xm(x, y))); Rm[2] = xm(two, xf(r, y, xm(x, z)));
+    Rm[3] = xm(two, xf(r, z, xm(x, y))); Rm[4] = xf(-two, xf(z, z, xm(x, x)), one); Rm[5] = xm(two, xf(-r, x, xm(y, z)));
+    Rm[6] = xm(two, xf(-r, y, xm(x, z))); Rm[7] = xm(two, xf(r, x, xm(y, z))); Rm[8] = xf(-two, xf(y, y, xm(x, x)), one);
 }
 
 // The camera-independent half of the geometry: rotation, scaled axes, cov3D = (R S)(R S)^T.  The multi-view kernels of the sharded
@@ -150,18 +175,18 @@ template <typename R>
 __device__ __forceinline__ void gaussian_cov3d(const R* sc, const R* q, float scale_modifier, Proj<R>& g) {
     quat_to_rot<R>(q, g.Rm);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) g.s[k] = sc[k] * R(scale_modifier);
+    for (int k = 0; k < 3; ++k) g.s[k] = xm(sc[k], R(scale_modifier));
     R M[9];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) M[i * 3 + k] = g.Rm[i * 3 + k] * g.s[k];
-    g.S3[0] = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
-    g.S3[1] = M[0] * M[3] + M[1] * M[4] + M[2] * M[5];
-    g.S3[2] = M[0] * M[6] + M[1] * M[7] + M[2] * M[8];
-    g.S3[3] = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
-    g.S3[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
-    g.S3[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
+        for (int k = 0; k < 3; ++k) M[i * 3 + k] = xm(g.Rm[i * 3 + k], g.s[k]);
+    g.S3[0] = xf(M[2], M[2], xf(M[1], M[1], xm(M[0], M[0])));
+    g.S3[1] = xf(M[2], M[5], xf(M[1], M[4], xm(M[0], M[3])));
+    g.S3[2] = xf(M[2], M[8], xf(M[1], M[7], xm(M[0], M[6])));
+    g.S3[3] = xf(M[5], M[5], xf(M[4], M[4], xm(M[3], M[3])));
+    g.S3[4] = xf(M[5], M[8], xf(M[4], M[7], xm(M[3], M[6])));
+    g.S3[5] = xf(M[8], M[8], xf(M[7], M[7], xm(M[6], M[6])));
 }
 
 template <bool GSPLAT, typename R>
@@ -178,50 +203,52 @@ template <bool GSPLAT, typename R>
 __device__ __forceinline__ void project_view(const B200gsView& v, const float* p, Proj<R>& g) {
     const float* V = v.viewmatrix;
     const R p0 = p[0], p1 = p[1], p2 = p[2];
-    g.tx = p0 * R(V[0]) + p1 * R(V[4]) + p2 * R(V[8]) + R(V[12]);
-    g.ty = p0 * R(V[1]) + p1 * R(V[5]) + p2 * R(V[9]) + R(V[13]);
-    g.tz = p0 * R(V[2]) + p1 * R(V[6]) + p2 * R(V[10]) + R(V[14]);
+    g.tx = xa(xf(p2, R(V[8]), xf(p1, R(V[4]), xm(p0, R(V[0])))), R(V[12]));
+    g.ty = xa(xf(p2, R(V[9]), xf(p1, R(V[5]), xm(p0, R(V[1])))), R(V[13]));
+    g.tz = xa(xf(p2, R(V[10]), xf(p1, R(V[6]), xm(p0, R(V[2])))), R(V[14]));
 
     R tanx, tany;
     if (GSPLAT) {
         g.fx = v.fx; g.fy = v.fy;
-        tanx = (R(0.5) * R(v.width)) / R(v.fx);
-        tany = (R(0.5) * R(v.height)) / R(v.fy);
+        tanx = xm(R(0.5), R(v.width)) / R(v.fx);
+        tany = xm(R(0.5), R(v.height)) / R(v.fy);
     } else {
         tanx = v.tanfovx; tany = v.tanfovy;
-        g.fx = R(v.width) / (R(2) * tanx);
-        g.fy = R(v.height) / (R(2) * tany);
+        g.fx = R(v.width) / xm(R(2), tanx);
+        g.fy = R(v.height) / xm(R(2), tany);
     }
-    const R limx = R(1.3) * tanx, limy = R(1.3) * tany;
+    const R limx = xm(R(1.3), tanx), limy = xm(R(1.3), tany);
     const R txtz = g.tx / g.tz, tytz = g.ty / g.tz;
     g.clx = (txtz < -limx) || (txtz > limx);
     g.cly = (tytz < -limy) || (tytz > limy);
-    g.cxp = fmin(limx, fmax(-limx, txtz)) * g.tz;
-    g.cyp = fmin(limy, fmax(-limy, tytz)) * g.tz;
+    g.cxp = xm(fmin(limx, fmax(-limx, txtz)), g.tz);
+    g.cyp = xm(fmin(limy, fmax(-limy, tytz)), g.tz);
     const R itz = R(1) / g.tz;
-    const R j00 = g.fx * itz, j02 = -(g.fx * g.cxp) * itz * itz;
-    const R j11 = g.fy * itz, j12 = -(g.fy * g.cyp) * itz * itz;
+    const R j00 = xm(g.fx, itz), j02 = xm(xm(-xm(g.fx, g.cxp), itz), itz);
+    const R j11 = xm(g.fy, itz), j12 = xm(xm(-xm(g.fy, g.cyp), itz), itz);
     // T = J * Rw ; Rw[j][i] = V[i*4+j]
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        g.T[i] = j00 * R(V[i * 4 + 0]) + j02 * R(V[i * 4 + 2]);
-        g.T[3 + i] = j11 * R(V[i * 4 + 1]) + j12 * R(V[i * 4 + 2]);
+        g.T[i] = xf(j02, R(V[i * 4 + 2]), xm(j00, R(V[i * 4 + 0])));
+        g.T[3 + i] = xf(j12, R(V[i * 4 + 2]), xm(j11, R(V[i * 4 + 1])));
     }
     // cov2D = T S3 T^T
     const R* S = g.S3;
-    const R u0 = S[0] * g.T[0] + S[1] * g.T[1] + S[2] * g.T[2];
-    const R u1 = S[1] * g.T[0] + S[3] * g.T[1] + S[4] * g.T[2];
-    const R u2 = S[2] * g.T[0] + S[4] * g.T[1] + S[5] * g.T[2];
-    const R w0 = S[0] * g.T[3] + S[1] * g.T[4] + S[2] * g.T[5];
-    const R w1 = S[1] * g.T[3] + S[3] * g.T[4] + S[4] * g.T[5];
-    const R w2 = S[2] * g.T[3] + S[4] * g.T[4] + S[5] * g.T[5];
-    g.a0 = g.T[0] * u0 + g.T[1] * u1 + g.T[2] * u2;
-    g.b = g.T[3] * u0 + g.T[4] * u1 + g.T[5] * u2;
-    g.c0 = g.T[3] * w0 + g.T[4] * w1 + g.T[5] * w2;
-    g.det0 = g.a0 * g.c0 - g.b * g.b;
-    g.a = g.a0 + R(v.eps2d);
-    g.c = g.c0 + R(v.eps2d);
-    g.det = g.a * g.c - g.b * g.b;
+    const R* T = g.T;
+    const R u0 = xf(S[2], T[2], xf(S[1], T[1], xm(S[0], T[0])));
+    const R u1 = xf(S[4], T[2], xf(S[3], T[1], xm(S[1], T[0])));
+    const R u2 = xf(S[5], T[2], xf(S[4], T[1], xm(S[2], T[0])));
+    const R w0 = xf(S[2], T[5], xf(S[1], T[4], xm(S[0], T[3])));
+    const R w1 = xf(S[4], T[5], xf(S[3], T[4], xm(S[1], T[3])));
+    const R w2 = xf(S[5], T[5], xf(S[4], T[4], xm(S[2], T[3])));
+    g.a0 = xf(T[2], u2, xf(T[1], u1, xm(T[0], u0)));
+    g.b = xf(T[5], u2, xf(T[4], u1, xm(T[3], u0)));
+    g.c0 = xf(T[5], w2, xf(T[4], w1, xm(T[3], w0)));
+    const R bb = xm(g.b, g.b);
+    g.det0 = xf(g.a0, g.c0, -bb);
+    g.a = xa(g.a0, R(v.eps2d));
+    g.c = xa(g.c0, R(v.eps2d));
+    g.det = xf(g.a, g.c, -bb);
 }
 
 // Optional fused-activation ("raw parameter") operands: the model's exp / normalize / sigmoid activations and the
@@ -240,6 +267,8 @@ struct RawIO {
     const int32_t* row_offsets;
     int accumulate;
     int prefetch_sh;         // K1: L2 prefetch of the SH row of every Gaussian in front of the camera, issued before the fp64 geometry
+    float* v_mean2d;         // K8 (rows path, optional): [n, v_mean2d_cols] <- (dL/dmean2D.x, .y[, 0]) of every Gaussian, zeros for culled ones:
+    int v_mean2d_cols;       // the `viewspace_points.grad` of the renderer contract, written here instead of by a fill + strided copy
 };
 
 template <bool RAW, typename R>
@@ -250,8 +279,8 @@ __device__ __forceinline__ void load_scale_quat(const float* __restrict__ scales
     if (RAW) {
         sc[0] = exp(R(s0)); sc[1] = exp(R(s1)); sc[2] = exp(R(s2));
         const R w = q4.x, x = q4.y, y = q4.z, z = q4.w;
-        const R inv = R(1) / fmax(sqrt(w * w + x * x + y * y + z * z), R(1e-12));  // F.normalize eps
-        q[0] = w * inv; q[1] = x * inv; q[2] = y * inv; q[3] = z * inv;
+        const R inv = R(1) / fmax(sqrt(xf(z, z, xf(y, y, xf(x, x, xm(w, w))))), R(1e-12));  // F.normalize eps
+        q[0] = xm(w, inv); q[1] = xm(x, inv); q[2] = xm(y, inv); q[3] = xm(z, inv);
         *inv_qnorm = inv;
     } else {
         sc[0] = s0; sc[1] = s1; sc[2] = s2;
@@ -317,26 +346,26 @@ __device__ __forceinline__ bool project_one_view(const B200gsView& v, const RawI
 
     R pxd, pyd;
     if (GSPLAT) {
-        const R iz = R(1) / (g.tz + R(1e-6));
-        const R zn = g.tz * iz;
-        pxd = (g.tx * iz) * R(v.fx) + zn * R(v.cx);
-        pyd = (g.ty * iz) * R(v.fy) + zn * R(v.cy);
+        const R iz = R(1) / xa(g.tz, R(1e-6));
+        const R zn = xm(g.tz, iz);
+        pxd = xf(zn, R(v.cx), xm(xm(g.tx, iz), R(v.fx)));
+        pyd = xf(zn, R(v.cy), xm(xm(g.ty, iz), R(v.fy)));
     } else {
         const float* P = v.projmatrix;
         const R p0 = p[0], p1 = p[1], p2 = p[2];
-        const R hx = p0 * R(P[0]) + p1 * R(P[4]) + p2 * R(P[8]) + R(P[12]);
-        const R hy = p0 * R(P[1]) + p1 * R(P[5]) + p2 * R(P[9]) + R(P[13]);
-        const R hw = p0 * R(P[3]) + p1 * R(P[7]) + p2 * R(P[11]) + R(P[15]);
-        const R iw = R(1) / (hw + R(0.0000001));
-        pxd = ((hx * iw + R(1)) * R(v.width) - R(1)) * R(0.5);
-        pyd = ((hy * iw + R(1)) * R(v.height) - R(1)) * R(0.5);
+        const R hx = xa(xf(p2, R(P[8]), xf(p1, R(P[4]), xm(p0, R(P[0])))), R(P[12]));
+        const R hy = xa(xf(p2, R(P[9]), xf(p1, R(P[5]), xm(p0, R(P[1])))), R(P[13]));
+        const R hw = xa(xf(p2, R(P[11]), xf(p1, R(P[7]), xm(p0, R(P[3])))), R(P[15]));
+        const R iw = R(1) / xa(hw, R(0.0000001));
+        pxd = xm(xf(xf(hx, iw, R(1)), R(v.width), R(-1)), R(0.5));
+        pyd = xm(xf(xf(hy, iw, R(1)), R(v.height), R(-1)), R(0.5));
     }
     const float px = float(pxd), py = float(pyd);
     const R inv_det = R(1) / g.det;
-    const R mid = R(0.5) * (g.a + g.c);
-    const R sq = sqrt(fmax(R(0.1), mid * mid - g.det));
-    const R lam = fmax(mid + sq, mid - sq);
-    const float radius = float(ceil(R(3) * sqrt(lam)));
+    const R mid = xm(R(0.5), xa(g.a, g.c));
+    const R sq = sqrt(fmax(R(0.1), xf(mid, mid, -g.det)));
+    const R lam = fmax(xa(mid, sq), xa(mid, -sq));
+    const float radius = float(ceil(xm(R(3), sqrt(lam))));
     const int grid_x = div_up(v.width, TILE), grid_y = div_up(v.height, TILE);
     int x0, y0, x1, y1;
     tile_rect<GSPLAT>(px, py, radius, grid_x, grid_y, x0, y0, x1, y1);
@@ -349,14 +378,14 @@ __device__ __forceinline__ bool project_one_view(const B200gsView& v, const RawI
         pv.px = px; pv.py = py;
         pv.depth = float(g.tz);
         pv.radius = (int32_t)radius;
-        pv.cA = float(g.c * inv_det);
-        pv.cB = float(-g.b * inv_det);
-        pv.cC = float(g.a * inv_det);
+        pv.cA = float(xm(g.c, inv_det));
+        pv.cB = float(xm(-g.b, inv_det));
+        pv.cC = float(xm(g.a, inv_det));
         pv.ntiles = ntiles;
-        pv.comp = GSPLAT ? float(sqrt(fmax(g.det0 * inv_det, R(0)))) : 1.0f;
+        pv.comp = GSPLAT ? float(sqrt(fmax(xm(g.det0, inv_det), R(0)))) : 1.0f;
         if (RAW) {
-            const float op = 1.0f / (1.0f + expf(-__ldg(raw.opac_in + i)));
-            pv.opac = (GSPLAT && raw.anti_aliased) ? op * pv.comp : op;
+            const float op = __frcp_rn(xa(1.0f, __expf(-__ldg(raw.opac_in + i))));
+            pv.opac = (GSPLAT && raw.anti_aliased) ? xm(op, pv.comp) : op;
         }
     }
     if (cov3d_out) {
@@ -383,186 +412,24 @@ template <int MC>
 __device__ __forceinline__ void sh_color_one(const B200gsView& v, const float* p, const float* sh, float& r, float& gc, float& bc, uint8_t& cl) {
     const int deg = v.sh_degree;
     const int ncoef = (deg + 1) * (deg + 1);
-    float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
-    const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-    dx *= inv_len; dy *= inv_len; dz *= inv_len;
+    float dx, dy, dz, inv_len;
+    view_dir(p, v.campos, dx, dy, dz, inv_len);
     float bs[MC];
     sh_basis<MC>(deg, dx, dy, dz, bs);
-    r = gc = bc = 0.f;
-#pragma unroll
-    for (int k = 0; k < MC; ++k) {
-        if (k < ncoef) {
-            r += bs[k] * sh[3 * k + 0];
-            gc += bs[k] * sh[3 * k + 1];
-            bc += bs[k] * sh[3 * k + 2];
-        }
-    }
-    r += 0.5f; gc += 0.5f; bc += 0.5f;
-    cl = 0;
-    if (r < 0.f) { r = 0.f; cl |= 1; }
-    if (gc < 0.f) { gc = 0.f; cl |= 2; }
-    if (bc < 0.f) { bc = 0.f; cl |= 4; }
-}
-
-// ---- warp-cooperative SH rows -------------------------------------------------------------------------------------------
-// A lane-per-Gaussian read of a 180/192-byte SH row touches 32 different sectors per load instruction (ncu, round 2: 18.9 sectors per
-// request, `lg_throttle` 24 % of K1's stall samples) and keeps 48 coefficient registers live.  Here the WARP copies the rows of its
-// visible lanes: for each set bit of the visibility ballot the 32 lanes read consecutive floats of that row (one or two coalesced
-// requests per row, four rows in flight), park them in shared memory at an odd row pitch, and every lane then reads its own row
-// conflict-free.  Culled Gaussians cost no SH traffic at all, and the coefficient registers are gone.
-constexpr unsigned FULLW = 0xffffffffu;
-
-template <int MC>
-struct ShStage {
-    static constexpr int NIT = (MC * 3 + 31) / 32;     // 32-float pieces of a row
-    static constexpr int PITCH = (MC * 3) | 1;         // floats per staged row (odd: lane-per-row reads are conflict-free)
-    static constexpr int WARP_FLOATS = 32 * PITCH;
-};
-
-// rows r (bits of vis) of the warp: global row r starts at warp_base + r * row_stride; the first nw floats go to s_dst[r * PITCH ..]
-template <int MC>
-__device__ __forceinline__ void warp_stage_rows(const float* __restrict__ warp_base, int row_stride, int nw, unsigned vis, float* s_dst,
-                                                unsigned lane) {
-    constexpr int NIT = ShStage<MC>::NIT, PITCH = ShStage<MC>::PITCH;
-    unsigned m = vis;
-    while (m) {
-        int r[4];
-        float val[4][NIT];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            r[u] = m ? __ffs(m) - 1 : -1;
-            m &= m - 1;          // 0 & anything = 0
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float* row = warp_base + int64_t(max(r[u], 0)) * row_stride;
-#pragma unroll
-            for (int q = 0; q < NIT; ++q) {
-                const int c = q * 32 + (int)lane;
-                val[u][q] = (r[u] >= 0 && c < nw) ? __ldg(row + c) : 0.f;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (r[u] < 0) continue;
-#pragma unroll
-            for (int q = 0; q < NIT; ++q) {
-                const int c = q * 32 + (int)lane;
-                if (c < nw) s_dst[r[u] * PITCH + c] = val[u][q];
-            }
-        }
-    }
-    __syncwarp();
-}
-
-// sh_color_one with the coefficients in a staged row: coefficient k, channel c = dc[c] for k = 0 when dc != nullptr (then row holds
-// coefficients 1..), else row[3 k + c]
-template <int MC>
-__device__ __forceinline__ void sh_color_staged(const B200gsView& v, const float* p, const float* dc, const float* row, float& r, float& gc,
-                                                float& bc, uint8_t& cl) {
-    const int deg = v.sh_degree;
-    const int ncoef = (deg + 1) * (deg + 1);
-    float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
-    const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-    dx *= inv_len; dy *= inv_len; dz *= inv_len;
-    float bs[MC];
-    sh_basis<MC>(deg, dx, dy, dz, bs);
-    const int off = dc ? -3 : 0;
-    if (dc) { r = bs[0] * dc[0]; gc = bs[0] * dc[1]; bc = bs[0] * dc[2]; }
-    else    { r = bs[0] * row[0]; gc = bs[0] * row[1]; bc = bs[0] * row[2]; }
+    r = xm(bs[0], sh[0]); gc = xm(bs[0], sh[1]); bc = xm(bs[0], sh[2]);
 #pragma unroll
     for (int k = 1; k < MC; ++k) {
         if (k < ncoef) {
-            r += bs[k] * row[3 * k + off];
-            gc += bs[k] * row[3 * k + off + 1];
-            bc += bs[k] * row[3 * k + off + 2];
+            r = xf(bs[k], sh[3 * k + 0], r);
+            gc = xf(bs[k], sh[3 * k + 1], gc);
+            bc = xf(bs[k], sh[3 * k + 2], bc);
         }
     }
-    r += 0.5f; gc += 0.5f; bc += 0.5f;
+    r = xa(r, 0.5f); gc = xa(gc, 0.5f); bc = xa(bc, 0.5f);
     cl = 0;
     if (r < 0.f) { r = 0.f; cl |= 1; }
     if (gc < 0.f) { gc = 0.f; cl |= 2; }
     if (bc < 0.f) { bc = 0.f; cl |= 4; }
-}
-
-// rows_out (raw mode only): instead of the separate arrays, ONE [n,12] row per Gaussian (xy 0..1, depth 2, conic 3..5, compensation 6,
-// blend opacity 7, rgb 8..10, radius bits 11) — three 128-bit stores; the binning and the blend kernels read the rows in place (one
-// 48-byte record per splat instead of four separate sectors).  radii_out / clamped_out (what K8 needs) are still written.
-template <bool GSPLAT, bool RAW, int MC, bool COOP>
-__global__ void __launch_bounds__(256, 3) project_fwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
-                                                          const float* __restrict__ means, const float* __restrict__ scales,
-                                                          const float* __restrict__ quats, const float* __restrict__ shs,
-                                                          float2* __restrict__ xy_out, float* __restrict__ depth_out,
-                                                          int32_t* __restrict__ radii_out, float* __restrict__ conic_out,
-                                                          float* __restrict__ comp_out, int32_t* __restrict__ tiles_out,
-                                                          float* __restrict__ cov3d_out, float* __restrict__ rgb_out,
-                                                          uint8_t* __restrict__ clamped_out, float* __restrict__ rows_out) {
-    extern __shared__ float s_sh[];                              // COOP: [warps][32 * PITCH] staged SH rows
-    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (!COOP && i >= n) return;
-    const bool in_range = i < n;
-    const int64_t il = in_range ? i : n - 1;                     // COOP: out-of-range lanes stay for the warp-wide copies
-    const float p[3] = {__ldg(means + 3 * il), __ldg(means + 3 * il + 1), __ldg(means + 3 * il + 2)};
-    if (!COOP && raw.prefetch_sh && shs != nullptr) {
-        // The SH row is only needed once the Gaussian is known to be visible, i.e. after ~150 dependent fp64 operations: its DRAM latency
-        // would sit at the end of that chain (ncu: long_scoreboard 33 % of K1's stall samples).  Everything in front of the camera gets
-        // its row pulled into L2 now; culled-by-frustum Gaussians in front of the camera cost some extra traffic.
-        const float* V = v.viewmatrix;
-        const float tz = p[0] * V[2] + p[1] * V[6] + p[2] * V[10] + V[14];
-        if (tz > 0.f) {
-            const int rw = (RAW ? v.sh_stride - 1 : v.sh_stride) * 3;
-            const int need = ((v.sh_degree + 1) * (v.sh_degree + 1) - (RAW ? 1 : 0)) * 3;
-            const char* row = reinterpret_cast<const char*>((RAW ? raw.shs_rest : shs) + il * int64_t(rw));
-            const int bytes = min(rw, need) * 4;
-            for (int off = 0; off < bytes; off += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
-            if (bytes > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + bytes - 4));
-        }
-    }
-    double sc[3], q[4], inv_qn;
-    load_scale_quat<RAW, double>(scales, quats, il, sc, q, &inv_qn);
-    const ProjOut out{xy_out, depth_out, radii_out, conic_out, comp_out, tiles_out, cov3d_out, rgb_out, clamped_out};
-    ProjVals pv;
-    const bool vis = project_one<GSPLAT, RAW>(v, raw, il, il, p, sc, q, in_range ? cov3d_out : nullptr, pv) && in_range;
-    const bool rows = RAW && rows_out != nullptr;
-    if (!rows && in_range) store_soa<RAW>(out, raw.opac_out, i, pv);
-    float r = 0.f, gc = 0.f, bc = 0.f;
-    uint8_t cl = 0;
-    if (shs != nullptr) {
-        const int deg = v.sh_degree;
-        const int ncoef = (deg + 1) * (deg + 1);
-        if (COOP) {
-            const unsigned lane = threadIdx.x & 31u;
-            const unsigned vm = __ballot_sync(FULLW, vis);
-            float* sw = s_sh + (threadIdx.x >> 5) * ShStage<MC>::WARP_FLOATS;
-            const int64_t i0 = i - lane;                         // the warp's first Gaussian (always < n when any lane is visible)
-            if (RAW) {
-                if (ncoef > 1) warp_stage_rows<MC>(raw.shs_rest + i0 * int64_t(v.sh_stride - 1) * 3, (v.sh_stride - 1) * 3, ncoef * 3 - 3, vm, sw, lane);
-                if (vis) {
-                    const float dc[3] = {__ldg(shs + 3 * i), __ldg(shs + 3 * i + 1), __ldg(shs + 3 * i + 2)};
-                    sh_color_staged<MC>(v, p, dc, sw + lane * ShStage<MC>::PITCH, r, gc, bc, cl);
-                }
-            } else {
-                warp_stage_rows<MC>(shs + i0 * int64_t(v.sh_stride) * 3, v.sh_stride * 3, ncoef * 3, vm, sw, lane);
-                if (vis) sh_color_staged<MC>(v, p, nullptr, sw + lane * ShStage<MC>::PITCH, r, gc, bc, cl);
-            }
-        } else if (vis) {
-            float sh[MC * 3];
-            load_sh_any<RAW, MC>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
-            sh_color_one<MC>(v, p, sh, r, gc, bc, cl);
-        }
-        if (!in_range) return;
-        if (!rows) { rgb_out[3 * i + 0] = r; rgb_out[3 * i + 1] = gc; rgb_out[3 * i + 2] = bc; }
-        clamped_out[i] = cl;
-    }
-    if (!in_range) return;
-    if (rows) {
-        float4* row = reinterpret_cast<float4*>(rows_out + i * B200GS_ROW_FLOATS);
-        radii_out[i] = pv.radius;
-        if (tiles_out) tiles_out[i] = pv.ntiles;
-        row[0] = make_float4(pv.px, pv.py, pv.depth, pv.cA);             // zeros when culled (the mean2D columns are handed out)
-        if (vis) row[1] = make_float4(pv.cB, pv.cC, pv.comp, pv.opac);
-        row[2] = make_float4(r, gc, bc, __int_as_float(pv.radius));      // radius 0 = culled: all the kernels look at of such a row
-    }
 }
 
 // L2 prefetch of the first `floats` floats at `row` (one request per 64 bytes + the last word)
@@ -571,6 +438,61 @@ __device__ __forceinline__ void prefetch_l2(const float* row, int floats) {
     const int bytes = floats * 4;
     for (int off = 0; off < bytes; off += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + off));
     if (bytes > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + bytes - 4));
+}
+
+// rows_out (raw mode only): instead of the separate arrays, ONE [n,12] row per Gaussian (xy 0..1, depth 2, conic 3..5, compensation 6,
+// blend opacity 7, rgb 8..10, radius bits 11) — three 128-bit stores; the binning and the blend kernels read the rows in place (one
+// 48-byte record per splat instead of four separate sectors).  radii_out / clamped_out (what K8 needs) are still written.
+template <bool GSPLAT, bool RAW, int MC>
+__global__ void __launch_bounds__(256, 3) project_fwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
+                                                          const float* __restrict__ means, const float* __restrict__ scales,
+                                                          const float* __restrict__ quats, const float* __restrict__ shs,
+                                                          float2* __restrict__ xy_out, float* __restrict__ depth_out,
+                                                          int32_t* __restrict__ radii_out, float* __restrict__ conic_out,
+                                                          float* __restrict__ comp_out, int32_t* __restrict__ tiles_out,
+                                                          float* __restrict__ cov3d_out, float* __restrict__ rgb_out,
+                                                          uint8_t* __restrict__ clamped_out, float* __restrict__ rows_out) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
+    if (raw.prefetch_sh && shs != nullptr) {
+        // The SH row is only needed once the Gaussian is known to be visible, i.e. after ~150 dependent fp64 operations.  Opt-in
+        // (B200GS_K1_PREFETCH=1): everything in front of the camera gets its row pulled into L2 before the geometry.
+        const float* V = v.viewmatrix;
+        const float tz = p[0] * V[2] + p[1] * V[6] + p[2] * V[10] + V[14];
+        if (tz > 0.f) {
+            const int rw = (RAW ? v.sh_stride - 1 : v.sh_stride) * 3;
+            const int need = ((v.sh_degree + 1) * (v.sh_degree + 1) - (RAW ? 1 : 0)) * 3;
+            prefetch_l2((RAW ? raw.shs_rest : shs) + i * int64_t(rw), min(rw, need));
+        }
+    }
+    double sc[3], q[4], inv_qn;
+    load_scale_quat<RAW, double>(scales, quats, i, sc, q, &inv_qn);
+    const ProjOut out{xy_out, depth_out, radii_out, conic_out, comp_out, tiles_out, cov3d_out, rgb_out, clamped_out};
+    ProjVals pv;
+    const bool vis = project_one<GSPLAT, RAW>(v, raw, i, i, p, sc, q, cov3d_out, pv);
+    const bool rows = RAW && rows_out != nullptr;
+    if (!rows) store_soa<RAW>(out, raw.opac_out, i, pv);
+    float r = 0.f, gc = 0.f, bc = 0.f;
+    uint8_t cl = 0;
+    if (shs != nullptr) {
+        if (vis) {
+            const int deg = v.sh_degree;
+            float sh[MC * 3];
+            load_sh_any<RAW, MC>(shs, raw.shs_rest, i, v.sh_stride, (deg + 1) * (deg + 1), sh);
+            sh_color_one<MC>(v, p, sh, r, gc, bc, cl);
+        }
+        if (!rows) { rgb_out[3 * i + 0] = r; rgb_out[3 * i + 1] = gc; rgb_out[3 * i + 2] = bc; }
+        clamped_out[i] = cl;
+    }
+    if (rows) {
+        float4* row = reinterpret_cast<float4*>(rows_out + i * B200GS_ROW_FLOATS);
+        radii_out[i] = pv.radius;
+        if (tiles_out) tiles_out[i] = pv.ntiles;
+        row[0] = make_float4(pv.px, pv.py, pv.depth, pv.cA);             // zeros when culled (the mean2D columns are handed out)
+        if (vis) row[1] = make_float4(pv.cB, pv.cC, pv.comp, pv.opac);
+        row[2] = make_float4(r, gc, bc, __int_as_float(pv.radius));      // radius 0 = culled: all the kernels look at of such a row
+    }
 }
 
 // The sharded renderer projects ONE shard into the W cameras of a step: one launch, the parameters (and the SH block, if any view
@@ -592,7 +514,7 @@ __global__ void __launch_bounds__(256) project_fwd_multi_kernel(const __grid_con
     const float p[3] = {__ldg(means + 3 * i), __ldg(means + 3 * i + 1), __ldg(means + 3 * i + 2)};
     double sc[3], q[4], inv_qn;
     load_scale_quat<true, double>(scales, quats, i, sc, q, &inv_qn);
-    {   // the SH row is needed after the whole camera loop: pull it into L2 now (nearly every Gaussian of a shard is seen by some camera)
+    if (raw.prefetch_sh) {   // the SH row is needed after the whole camera loop: pull it into L2 now (B200GS_K1_PREFETCH=1)
         const int deg0 = vp.v[0].sh_degree;
         prefetch_l2(raw.shs_rest + i * int64_t(vp.v[0].sh_stride - 1) * 3, min((vp.v[0].sh_stride - 1) * 3, ((deg0 + 1) * (deg0 + 1) - 1) * 3));
     }
@@ -662,8 +584,10 @@ __global__ void __launch_bounds__(PACK_THREADS, (MC <= 16 ? 3 : 2)) project_pack
     if (live) {
         p[0] = __ldg(means + 3 * i); p[1] = __ldg(means + 3 * i + 1); p[2] = __ldg(means + 3 * i + 2);
         load_scale_quat<true, double>(scales, quats, i, sc, q, &inv_qn);
-        const int deg0 = vp.v[0].sh_degree;   // the SH row is needed after the whole camera loop: pull it into L2 now
-        prefetch_l2(raw.shs_rest + i * int64_t(vp.v[0].sh_stride - 1) * 3, min((vp.v[0].sh_stride - 1) * 3, ((deg0 + 1) * (deg0 + 1) - 1) * 3));
+        if (raw.prefetch_sh) {   // the SH row is needed after the whole camera loop: pull it into L2 now (B200GS_K1_PREFETCH=1)
+            const int deg0 = vp.v[0].sh_degree;
+            prefetch_l2(raw.shs_rest + i * int64_t(vp.v[0].sh_stride - 1) * 3, min((vp.v[0].sh_stride - 1) * 3, ((deg0 + 1) * (deg0 + 1) - 1) * 3));
+        }
     }
     Proj<double> g3;
     gaussian_cov3d<double>(sc, q, vp.v[0].scale_modifier, g3);      // once per Gaussian; project_one_view per camera
@@ -938,8 +862,8 @@ __device__ __forceinline__ void store_sh_rows(float* s_rows_warp, const float* o
     }
 }
 
-template <bool GSPLAT, bool RAW, int MC, bool COOP>
-__global__ void __launch_bounds__(BWD_THREADS, (MC <= 16 ? 5 : 3)) project_bwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
+template <bool GSPLAT, bool RAW, int MC>
+__global__ void __launch_bounds__(BWD_THREADS, (MC <= 16 ? (GSPLAT ? 7 : 6) : 3)) project_bwd_kernel(const __grid_constant__ B200gsView v, const RawIO raw, int64_t n,
                                                           const float* __restrict__ means, const float* __restrict__ scales,
                                                           const float* __restrict__ quats, const float* __restrict__ shs,
                                                           const int32_t* __restrict__ radii, const uint8_t* __restrict__ clamped,
@@ -970,77 +894,74 @@ __global__ void __launch_bounds__(BWD_THREADS, (MC <= 16 ? 5 : 3)) project_bwd_k
         const int deg = v.sh_degree;
         const int ncoef = (deg + 1) * (deg + 1);
         float gr = 0.f, gg = 0.f, gb = 0.f, dx = 0.f, dy = 0.f, dz = 1.f, inv_len = 0.f;
-        float out[MC * 3];
+        float bs[MC];
 #pragma unroll
-        for (int k = 0; k < MC * 3; ++k) out[k] = 0.f;
+        for (int k = 0; k < MC; ++k) bs[k] = 0.f;
         if (vis) {
             const uint8_t cl = clamped[i];
             const float* crgb = ROWS ? vrow + B200GS_ROW_RGB : v_rgb + 3 * i;
             gr = (cl & 1) ? 0.f : __ldg(crgb + 0);
             gg = (cl & 2) ? 0.f : __ldg(crgb + 1);
             gb = (cl & 4) ? 0.f : __ldg(crgb + 2);
-            dx = p[0] - v.campos[0]; dy = p[1] - v.campos[1]; dz = p[2] - v.campos[2];
-            inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-            dx *= inv_len; dy *= inv_len; dz *= inv_len;
-            float bs[MC];
+            view_dir(p, v.campos, dx, dy, dz, inv_len);
             sh_basis<MC>(deg, dx, dy, dz, bs);
-#pragma unroll
-            for (int k = 0; k < MC; ++k) {
-                const float bk = (k < ncoef) ? bs[k] : 0.f;
-                out[3 * k + 0] = bk * gr; out[3 * k + 1] = bk * gg; out[3 * k + 2] = bk * gb;
-            }
         }
-        if (COOP && !GSPLAT && deg > 0) {
-            // view direction -> mean (dgr back-propagates it; gsplat renderers detach the direction).  The SH rows of the warp's visible
-            // lanes come through the staging buffer (coalesced, see warp_stage_rows) before it is reused for the gradient rows.
-            constexpr int PITCH = ShStage<MC>::PITCH;
-            static_assert(ShStage<MC>::WARP_FLOATS <= 32 * (MC * 3 + 1), "staging buffer too small");
-            const unsigned vm = __ballot_sync(FULLW, vis);
-            const int64_t i0 = i - lane;
-            const int off = RAW ? -3 : 0;
-            if (RAW) warp_stage_rows<MC>(raw.shs_rest + i0 * int64_t(v.sh_stride - 1) * 3, (v.sh_stride - 1) * 3, ncoef * 3 - 3, vm, s_rows[warp], lane);
-            else warp_stage_rows<MC>(shs + i0 * int64_t(v.sh_stride) * 3, v.sh_stride * 3, ncoef * 3, vm, s_rows[warp], lane);
-            if (vis) {
-                const float* row = s_rows[warp] + lane * PITCH;
-                float bx[MC], by[MC], bz[MC];
-                sh_basis_grad<MC>(deg, dx, dy, dz, bx, by, bz);
-                float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+        if (vis && !GSPLAT && deg > 0) {
+            // view direction -> mean (dgr back-propagates it; gsplat renderers detach the direction)
+            // w_k = <sh_k, v_rgb> first (the 48 coefficients are consumed as they arrive: 16 live values instead of 48), then the basis
+            // derivatives
+            const float* c0 = RAW ? raw.shs_rest + i * int64_t(v.sh_stride - 1) * 3 - 3 : shs + i * int64_t(v.sh_stride) * 3;   // coefficient k at c0 + 3 k (k >= 1)
+            float w[MC];
 #pragma unroll
-                for (int k = 1; k < MC; ++k) {
-                    if (k < ncoef) {
-                        const float w = row[3 * k + off] * gr + row[3 * k + off + 1] * gg + row[3 * k + off + 2] * gb;
-                        ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
-                    }
-                }
-                const float dot = dx * ddx + dy * ddy + dz * ddz;
-                dm[0] += (ddx - dx * dot) * inv_len;
-                dm[1] += (ddy - dy * dot) * inv_len;
-                dm[2] += (ddz - dz * dot) * inv_len;
-            }
-            __syncwarp();   // every lane has read its row: the buffer may be overwritten
-        }
-        store_sh_rows<RAW, MC>(s_rows[warp], out, i, n, in_range, stride3, lane, v_shs, raw.v_shs_rest, ACC);
-        if (!COOP && vis && !GSPLAT && deg > 0) {
-            // view direction -> mean, per-lane loads of the SH block (B200GS_K8_COOP=0)
-            float sh[MC * 3];
-            load_sh_any<RAW, MC>(shs, raw.shs_rest, i, v.sh_stride, ncoef, sh);
+            for (int k = 1; k < MC; ++k) w[k] = (k < ncoef) ? __ldg(c0 + 3 * k) * gr + __ldg(c0 + 3 * k + 1) * gg + __ldg(c0 + 3 * k + 2) * gb : 0.f;
             float bx[MC], by[MC], bz[MC];
             sh_basis_grad<MC>(deg, dx, dy, dz, bx, by, bz);
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
 #pragma unroll
             for (int k = 1; k < MC; ++k) {
-                if (k < ncoef) {
-                    const float w = sh[3 * k] * gr + sh[3 * k + 1] * gg + sh[3 * k + 2] * gb;
-                    ddx += bx[k] * w; ddy += by[k] * w; ddz += bz[k] * w;
-                }
+                if (k < ncoef) { ddx += bx[k] * w[k]; ddy += by[k] * w[k]; ddz += bz[k] * w[k]; }
             }
             const float dot = dx * ddx + dy * ddy + dz * ddz;
             dm[0] += (ddx - dx * dot) * inv_len;
             dm[1] += (ddy - dy * dot) * inv_len;
             dm[2] += (ddz - dz * dot) * inv_len;
         }
+        // SH-gradient row of this Gaussian (coefficient k, channel c: basis_k * v_rgb_c; zeros when culled) straight into the warp's
+        // staging rows — 48 values that used to sit in registers until the store (96 registers, 5 blocks per SM) — then out coalesced
+        const int rw = RAW ? stride3 - 3 : stride3;          // floats per output row
+        if (rw <= MC * 3) {
+            if (RAW && in_range) {
+                float o0 = bs[0] * gr, o1 = bs[0] * gg, o2 = bs[0] * gb;
+                if (ACC) { o0 += v_shs[3 * i]; o1 += v_shs[3 * i + 1]; o2 += v_shs[3 * i + 2]; }
+                v_shs[3 * i] = o0; v_shs[3 * i + 1] = o1; v_shs[3 * i + 2] = o2;
+            }
+            float* row = s_rows[warp] + lane * (rw | 1);
+#pragma unroll
+            for (int k = RAW ? 1 : 0; k < MC; ++k) {
+                const int c = RAW ? 3 * k - 3 : 3 * k;
+                if (c < rw) {
+                    const float bk = (k < ncoef) ? bs[k] : 0.f;
+                    row[c] = bk * gr; row[c + 1] = bk * gg; row[c + 2] = bk * gb;
+                }
+            }
+            flush_sh_rows<RAW>(s_rows[warp], rw, i, n, lane, RAW ? raw.v_shs_rest : v_shs, ACC);
+        } else {   // wider coefficient storage than the kernel evaluates: the register path of store_sh_rows
+            float out[MC * 3];
+#pragma unroll
+            for (int k = 0; k < MC; ++k) {
+                const float bk = (k < ncoef) ? bs[k] : 0.f;
+                out[3 * k + 0] = bk * gr; out[3 * k + 1] = bk * gg; out[3 * k + 2] = bk * gb;
+            }
+            store_sh_rows<RAW, MC>(s_rows[warp], out, i, n, in_range, stride3, lane, v_shs, raw.v_shs_rest, ACC);
+        }
     }
     if (!in_range) return;
+    if (RAW && raw.v_mean2d != nullptr) {
+        float* m2 = raw.v_mean2d + i * raw.v_mean2d_cols;
+        m2[0] = (ROWS && vis) ? __ldg(vrow) : 0.f;
+        m2[1] = (ROWS && vis) ? __ldg(vrow + 1) : 0.f;
+        if (raw.v_mean2d_cols > 2) m2[2] = 0.f;
+    }
     if (!vis) {
         if (!ACC) {
             v_means[3 * i] = 0.f; v_means[3 * i + 1] = 0.f; v_means[3 * i + 2] = 0.f;
@@ -1152,9 +1073,8 @@ __global__ void __launch_bounds__(BWD_THREADS) project_bwd_multi_kernel(const __
         {
             const uint8_t cl = clamped[e];
             const float gr = (cl & 1) ? 0.f : w2.x, gg = (cl & 2) ? 0.f : w2.y, gb = (cl & 4) ? 0.f : w2.z;
-            float dx = p[0] - v.campos[0], dy = p[1] - v.campos[1], dz = p[2] - v.campos[2];
-            const float inv_len = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-            dx *= inv_len; dy *= inv_len; dz *= inv_len;
+            float dx, dy, dz, inv_len;
+            view_dir(p, v.campos, dx, dy, dz, inv_len);
             float bs[MC];
             sh_basis<MC>(deg, dx, dy, dz, bs);
             dc_acc[0] = fmaf(bs[0], gr, dc_acc[0]); dc_acc[1] = fmaf(bs[0], gg, dc_acc[1]); dc_acc[2] = fmaf(bs[0], gb, dc_acc[2]);
@@ -1265,6 +1185,11 @@ int launch_project_fwd(const B200gsView& v, int64_t n, const float* means, const
                                   rgb, clamped, nullptr, s, nullptr);
 }
 
+static bool sh_prefetch_enabled() {
+    static const bool on = []() { const char* e = getenv("B200GS_K1_PREFETCH"); return e && e[0] == '1'; }();
+    return on;
+}
+
 int launch_project_fwd_raw(const B200gsView& v, int64_t n, const float* means, const float* scales, const float* quats,
                            const float* opac_logits, const float* shs_dc, const float* shs_rest, int anti_aliased, float* xy,
                            float* depth, int32_t* radii, float* conic, float* comp, int32_t* tiles, float* cov3d, float* rgb,
@@ -1275,37 +1200,22 @@ int launch_project_fwd_raw(const B200gsView& v, int64_t n, const float* means, c
     const bool raw_mode = opac_out != nullptr || rows != nullptr;
     RawIO raw{opac_logits, shs_rest, opac_out, nullptr, nullptr, nullptr, anti_aliased, nullptr, nullptr, 0};
 #define B200GS_PF_ARGS v, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth, radii, conic, comp, tiles, cov3d, rgb, clamped, rows
-    // SH rows through per-lane loads (default) or the warp-cooperative staging (B200GS_K1_COOP=1)
-    // Measured at 1 M / 1080p (profiles/round2_call5_*): the staging cuts K1's L1 sectors 4x (5.3 instead of 18.9 per request) but the
-    // kernel is latency- not LSU-bound and the per-row loop has fewer loads in flight: 0.099 ms against 0.074 ms.  Off by default.
-    static const bool coop_env = []() { const char* e = getenv("B200GS_K1_COOP"); return e && e[0] == '1'; }();
-    static const bool prefetch_env = []() { const char* e = getenv("B200GS_K1_PREFETCH"); return !(e && e[0] == '0'); }();
-    const bool coop = coop_env && shs_dc != nullptr;
-    raw.prefetch_sh = prefetch_env ? 1 : 0;
-#define B200GS_PF_ONE(G, R, MC, C)                                                                               \
-    do {                                                                                                         \
-        const size_t smem = (C) ? sizeof(float) * (threads / 32) * ShStage<MC>::WARP_FLOATS : 0;                 \
-        if (C) {                                                                                                 \
-            static const cudaError_t attr = cudaFuncSetAttribute((const void*)project_fwd_kernel<G, R, MC, C>,   \
-                                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (attr != cudaSuccess) { set_error("project_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr)); return B200GS_ECUDA; } \
-        }                                                                                                        \
-        project_fwd_kernel<G, R, MC, C><<<blocks, threads, smem, s>>>(B200GS_PF_ARGS);                           \
-    } while (0)
+    // L2 prefetch of the SH rows ahead of the fp64 geometry: measured 0.085 ms with, 0.079 ms without at 1 M / 1080p (the extra
+    // requests of the frustum-culled Gaussians cost more than the hidden latency returns): opt-in (B200GS_K1_PREFETCH=1)
+    raw.prefetch_sh = sh_prefetch_enabled() ? 1 : 0;
 #define B200GS_PF_LAUNCH(MC)                                                                                    \
     do {                                                                                                         \
         if (v.mode == B200GS_MODE_GSPLAT) {                                                                      \
-            if (raw_mode) { if (coop) B200GS_PF_ONE(true, true, MC, true); else B200GS_PF_ONE(true, true, MC, false); }       \
-            else          { if (coop) B200GS_PF_ONE(true, false, MC, true); else B200GS_PF_ONE(true, false, MC, false); }     \
+            if (raw_mode) project_fwd_kernel<true, true, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);         \
+            else project_fwd_kernel<true, false, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);                 \
         } else {                                                                                                 \
-            if (raw_mode) { if (coop) B200GS_PF_ONE(false, true, MC, true); else B200GS_PF_ONE(false, true, MC, false); }     \
-            else          { if (coop) B200GS_PF_ONE(false, false, MC, true); else B200GS_PF_ONE(false, false, MC, false); }   \
+            if (raw_mode) project_fwd_kernel<false, true, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);        \
+            else project_fwd_kernel<false, false, MC><<<blocks, threads, 0, s>>>(B200GS_PF_ARGS);                \
         }                                                                                                        \
     } while (0)
     if (shs_dc != nullptr && v.sh_degree > 3) B200GS_PF_LAUNCH(25);
     else B200GS_PF_LAUNCH(16);
 #undef B200GS_PF_LAUNCH
-#undef B200GS_PF_ONE
 #undef B200GS_PF_ARGS
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
@@ -1324,28 +1234,22 @@ int launch_project_bwd_raw(const B200gsView& v, int64_t n, const float* means, c
                            const int32_t* radii, const uint8_t* clamped, const float* v_xy, const float* v_depth,
                            const float* v_conic, const float* v_comp, const float* v_rgb, const float* v_opac, float* v_means,
                            float* v_scales, float* v_quats, float* v_opac_logit, float* v_shs_dc, float* v_shs_rest,
-                           cudaStream_t s, const float* v_rows, const int32_t* row_offsets, int accumulate) {
+                           cudaStream_t s, const float* v_rows, const int32_t* row_offsets, int accumulate, float* v_mean2d, int v_mean2d_cols) {
     if (n == 0) return B200GS_OK;
     const int threads = BWD_THREADS;
     const unsigned blocks = (unsigned)div_up64(n, threads);
     const bool raw_mode = v_opac_logit != nullptr;
-    RawIO raw{opac_logits, shs_rest, nullptr, v_opac, v_opac_logit, v_shs_rest, anti_aliased, v_rows, row_offsets, accumulate};
+    RawIO raw{opac_logits, shs_rest, nullptr, v_opac, v_opac_logit, v_shs_rest, anti_aliased, v_rows, row_offsets, accumulate, 0, v_mean2d, v_mean2d_cols};
 #define B200GS_PB_ARGS v, raw, n, means, scales, quats, shs_dc, radii, clamped, (const float2*)v_xy, v_depth, v_conic, v_comp, v_rgb, \
                        v_means, v_scales, (float4*)v_quats, v_shs_dc
-    // vanilla mode re-reads the SH rows for the view-direction gradient: per-lane loads (default) or warp-cooperative staging (B200GS_K8_COOP=1)
-    // measured slower than the per-lane loads (0.153 vs 0.129 ms at 1 M / 1080p, profiles/round2_call5_*): opt-in
-    static const bool coop = []() { const char* e = getenv("B200GS_K8_COOP"); return e && e[0] == '1'; }();
 #define B200GS_PB_LAUNCH(MC)                                                                                    \
     do {                                                                                                         \
         if (v.mode == B200GS_MODE_GSPLAT) {                                                                      \
-            if (raw_mode) project_bwd_kernel<true, true, MC, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);  \
-            else project_bwd_kernel<true, false, MC, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);          \
-        } else if (coop) {                                                                                       \
-            if (raw_mode) project_bwd_kernel<false, true, MC, true><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);  \
-            else project_bwd_kernel<false, false, MC, true><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);          \
+            if (raw_mode) project_bwd_kernel<true, true, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);         \
+            else project_bwd_kernel<true, false, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);                 \
         } else {                                                                                                 \
-            if (raw_mode) project_bwd_kernel<false, true, MC, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS); \
-            else project_bwd_kernel<false, false, MC, false><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);         \
+            if (raw_mode) project_bwd_kernel<false, true, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);        \
+            else project_bwd_kernel<false, false, MC><<<blocks, threads, 0, s>>>(B200GS_PB_ARGS);                \
         }                                                                                                        \
     } while (0)
     if (v_shs_dc != nullptr && v.sh_degree > 3) B200GS_PB_LAUNCH(25);
@@ -1364,6 +1268,7 @@ int launch_project_fwd_multi(const B200gsView* views, int n_views, int64_t n, co
     for (int j = 0; j < n_views; ++j) vp.v[j] = views[j];
     for (int j = n_views; j < B200GS_MAX_VIEWS; ++j) vp.v[j] = views[0];
     RawIO raw{opac_logits, shs_rest, opac_out, nullptr, nullptr, nullptr, anti_aliased, nullptr, nullptr, 0};
+    raw.prefetch_sh = sh_prefetch_enabled() ? 1 : 0;
     if (views[0].sh_degree > 3)
         project_fwd_multi_kernel<25><<<(unsigned)div_up64(n, 256), 256, 0, s>>>(vp, n_views, raw, n, means, scales, quats, shs_dc, (float2*)xy, depth,
                                                                                 radii, conic, rgb, clamped);
@@ -1399,6 +1304,7 @@ int launch_project_pack_multi(const B200gsView* views, int n_views, int64_t n, c
         dst.p[j] = j < n_views ? dst_rows[j] : nullptr;
     }
     RawIO raw{opac_logits, shs_rest, nullptr, nullptr, nullptr, nullptr, anti_aliased, nullptr, nullptr, 0};
+    raw.prefetch_sh = sh_prefetch_enabled() ? 1 : 0;
     B200GS_CUDA(cudaMemsetAsync(workspace, 0, need, s));
     uint32_t* ticket = (uint32_t*)workspace;
     uint32_t* state = ticket + 64;

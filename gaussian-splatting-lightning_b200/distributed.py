@@ -407,7 +407,7 @@ class _ProjectShard(torch.autograd.Function):
                     check(L.b200gs_project_bwd_rows(ctypes.byref(view), n, ptr(means), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc),
                                                     ptr(shs_rest), int(st.aa), st.radii.data_ptr() + 4 * j * n, st.clamped.data_ptr() + j * n,
                                                     st.row_index.data_ptr() + 4 * j * n, int(st.v_rows[j]), 1 if j > 0 else 0, ptr(v_means),
-                                                    ptr(v_ls), ptr(v_q), ptr(v_ol), ptr(v_dc), ptr(v_rest), stream), "b200gs_project_bwd_rows")
+                                                    ptr(v_ls), ptr(v_q), ptr(v_ol), ptr(v_dc), ptr(v_rest), None, 0, stream), "b200gs_project_bwd_rows")
         st.v_send = None
         return v_means, v_ls, v_q, v_ol.reshape(ctx.opac_shape), v_dc, v_rest, None
 
@@ -536,7 +536,8 @@ class _ExchangeRasterize(torch.autograd.Function):
             v_recv = torch.zeros_like(st.recv)
         with ops._stage("blend_bwd"):
             check(L.b200gs_blend_bwd_rows(MODE_GSPLAT, W, H, ptr(st.binning.tile_ranges), ptr(st.binning.sorted_ids), ptr(st.recv), ptr(bg),
-                                          ptr(st.final_T), ptr(st.n_contrib), ptr(v_image), 3, 1, None, 1.0, 1.0, ptr(v_recv), stream), "b200gs_blend_bwd_rows")
+                                          ptr(st.final_T), ptr(st.n_contrib), ptr(v_image), 3, 1, None, 1.0, 1.0, ptr(v_recv), ptr(st.binning.tile_order),
+                                          stream), "b200gs_blend_bwd_rows")
         grads = []
 
         def xy_grad(j, rows, shift):

@@ -11,6 +11,7 @@ Functions
   rasterize_gaussians(...)    gsplat v0 ``rasterize_gaussians``        (gsplat_renderer.py:86-99)
 """
 import ctypes
+import os
 import threading
 from typing import Optional, Tuple
 
@@ -23,6 +24,10 @@ ROW_FLOATS = 12   # include/b200gs.h B200GS_ROW_FLOATS
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+# Longest-tile-first processing order for the blend kernels of the row paths (B200GS_TILE_ORDER=0: row-major, for A/B measurements)
+TILE_ORDER = os.environ.get("B200GS_TILE_ORDER", "1") != "0"
 
 
 def _stream() -> int:
@@ -135,10 +140,11 @@ class Binning:
     (every tile of the 3-sigma rects; bounds `total`), `coarse_pairs` = (8x8-tile cell, Gaussian) pairs of the first
     binning level, `total` = number of listed pairs.  In lazy mode the counters arrive asynchronously: rect/coarse are
     None until resolve(), `total` waits for its own copy when first read (see bin_gaussians)."""
-    __slots__ = ("sorted_ids", "tile_ranges", "rect_pairs", "coarse_pairs", "_total", "_pending", "_host", "_event_b")
+    __slots__ = ("sorted_ids", "tile_ranges", "tile_order", "rect_pairs", "coarse_pairs", "_total", "_pending", "_host", "_event_b")
 
     def __init__(self, sorted_ids, tile_ranges, total=None, host=None, pending=None, event_b=None):
         self.sorted_ids, self.tile_ranges, self._total = sorted_ids, tile_ranges, total
+        self.tile_order = None        # [n_tiles] int32, tiles by decreasing list length (filled by blend_forward_rows: b200gs_tile_order)
         self.rect_pairs = self.coarse_pairs = None
         self._host, self._pending, self._event_b = host, pending, event_b
         if host is not None and pending is None:
@@ -555,13 +561,15 @@ class _RasterizeRaw(torch.autograd.Function):
         v_q = torch.empty(n, 4, dtype=torch.float32, device=dev)
         v_ol = torch.empty(n, dtype=torch.float32, device=dev)
         v_dc, v_rest = torch.empty_like(shs_dc), torch.empty_like(shs_rest)
+        # d loss / d mean2D (`viewspace_points.grad`): K8 writes it while it has the gradient row in registers
+        cols = int(ctx.means2D_shape[1])
+        v_means2D = torch.empty(n, cols, dtype=torch.float32, device=dev) if (ctx.needs_input_grad[2] and cols in (2, 3)) else None
         with _stage("project_bwd"):
             check(L.b200gs_project_bwd_rows(ctypes.byref(view), n, ptr(means3D), ptr(log_scales), ptr(raw_quats), ptr(ol), ptr(shs_dc), ptr(shs_rest),
                                             int(ctx.aa), ptr(radii), ptr(clamped), None, ptr(v_rows), 0, ptr(v_means), ptr(v_ls), ptr(v_q), ptr(v_ol),
-                                            ptr(v_dc), ptr(v_rest), _stream()), "b200gs_project_bwd_rows")
-        if ctx.means2D_shape[1] == 2:
-            v_means2D = v_rows[:, 0:2].contiguous()
-        else:
+                                            ptr(v_dc), ptr(v_rest), ptr(v_means2D), cols if v_means2D is not None else 0, _stream()),
+                  "b200gs_project_bwd_rows")
+        if v_means2D is None and ctx.needs_input_grad[2]:
             v_means2D = torch.zeros(ctx.means2D_shape, dtype=torch.float32, device=dev)
             v_means2D[:, :2] = v_rows[:, 0:2]
         return None, v_means, v_means2D, v_dc, v_rest, v_ol.reshape(ctx.opac_shape), v_ls, v_q, None, None, None

@@ -161,7 +161,9 @@ class B200VanillaRenderer(Renderer):
         raw = _raw_parameters(pc) if (self.fused_activations and override_color is None) else None
         if raw is not None:
             # fused path: exp / sigmoid / normalize / cat run inside K1 and K8 on the raw parameter tensors
-            screenspace_points = torch.zeros_like(raw["means"], requires_grad=True) + 0
+            # a LEAF that requires grad: `.grad` is populated exactly as for the reference's `zeros_like(...) + 0` + retain_grad()
+            # (vanilla_renderer.py:55-56; retain_grad() on a leaf is a no-op), without the extra elementwise kernel
+            screenspace_points = torch.zeros_like(raw["means"], requires_grad=True)
             view = camera_view(viewpoint_camera, MODE_VANILLA, self.cache_cameras)
             view = _view_with(view, sh_degree=int(pc.active_sh_degree), scale_modifier=float(scaling_modifier))
             image, radii = ops.rasterize_vanilla_raw(raw["means"], screenspace_points, raw["shs_dc"], raw["shs_rest"],

@@ -277,12 +277,16 @@ B200GS_API int b200gs_project_fwd_rows(const B200gsView* view, int64_t n, const 
                                        int32_t anti_aliased, float* rows, int32_t* radii, uint8_t* clamped, int32_t* tiles, void* stream);
 /* b200gs_project_bwd_rows: K8 (fused activations) taking its cotangents straight from compacted [V,12] gradient rows
  *     (v_rows[row_offsets[i]] for visible i; row_offsets = NULL: v_rows[i]) and, when accumulate != 0, ADDING to the gradient buffers — the sharded
- *     renderer calls it once per camera of the step without unpack copies or separate sum kernels. */
+ *     renderer calls it once per camera of the step without unpack copies or separate sum kernels.
+ *     v_mean2d (optional, may be NULL): [n, v_mean2d_cols] (2 or 3 columns) <- dL/dmean2D of every Gaussian (columns 0..1 of its gradient row; zeros
+ *     for culled Gaussians and in column 2): the `.grad` of the renderer contract's `viewspace_points` (vanilla_renderer.py:55-56,
+ *     vanilla_density_controller.py:101-123), written here instead of by a fill + strided copy after the kernel. */
 B200GS_API int b200gs_project_bwd_rows(const B200gsView* view, int64_t n, const float* means, const float* log_scales,
                                        const float* raw_quats, const float* opacity_logits, const float* shs_dc, const float* shs_rest,
                                        int32_t anti_aliased, const int32_t* radii, const uint8_t* clamped, const int32_t* row_offsets,
                                        const float* v_rows, int32_t accumulate, float* v_means, float* v_log_scales, float* v_raw_quats,
-                                       float* v_opacity_logits, float* v_shs_dc, float* v_shs_rest, void* stream);
+                                       float* v_opacity_logits, float* v_shs_dc, float* v_shs_rest, float* v_mean2d, int32_t v_mean2d_cols,
+                                       void* stream);
 /* b200gs_project_fwd_raw_multi / b200gs_project_bwd_rows_multi: K1 / K8 of one shard for ALL n_views (<= B200GS_MAX_VIEWS) cameras of a
  *     step in one launch each (gsplat constants, raw parameters; sh_degree / sh_stride / scale_modifier of views[0] apply to all).
  *     fwd: camera-major outputs, view j at elements [j*n, (j+1)*n); parameters and SH blocks are read once per Gaussian.
@@ -336,15 +340,19 @@ B200GS_API int b200gs_unpack_rows_grad(int64_t n, const int32_t* radii, const in
 B200GS_API int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull,
                                      void* workspace_a, size_t workspace_a_bytes, int64_t* d_counts, int64_t* host_counts,
                                      int32_t sync_host, void* stream, const int64_t* block_counts, int64_t block_rows);
+/* tile_order (optional, NULL = row-major): the order in which the blend kernels take the tiles, from b200gs_tile_order — tiles by
+ *     decreasing list length, so that the long tiles start first and the kernels' tails are made of short ones.  Results do not depend
+ *     on it (tiles are independent). */
+B200GS_API int b200gs_tile_order(int32_t width, int32_t height, const int32_t* tile_ranges, int32_t* tile_order /* [n_tiles] */, void* stream);
 B200GS_API int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                                      const float* rows, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride,
-                                     float* final_T, int32_t* n_contrib, float* alpha, void* stream);
+                                     float* final_T, int32_t* n_contrib, float* alpha, const int32_t* tile_order, void* stream);
 /* grad_scale_x / _y: factor on the mean2D columns of the gradient rows (vanilla renderers: 0.5 W, 0.5 H — the vanilla rasterizer's
  *     NDC-unit convention; gsplat renderers: 1, 1).  v_rows must be zero-filled: the kernel accumulates with 128-bit reductions. */
 B200GS_API int b200gs_blend_bwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                                      const float* rows, const float* bg, const float* final_T, const int32_t* n_contrib,
                                      const float* v_image, int64_t pix_stride, int64_t ch_stride, const float* v_alpha,
-                                     float grad_scale_x, float grad_scale_y, float* v_rows, void* stream);
+                                     float grad_scale_x, float grad_scale_y, float* v_rows, const int32_t* tile_order, void* stream);
 
 #ifdef __cplusplus
 }
