@@ -283,8 +283,12 @@ def blend_forward_rows(mode, width, height, binning: Binning, rows, bg, planar=F
     n_contrib = torch.empty(height, width, dtype=torch.int32, device=dev)
     pix_stride, ch_stride = (1, height * width) if planar else (3, 1)
     with _stage("blend_fwd"):
+        if binning.tile_order is None and TILE_ORDER:     # tiles by decreasing list length: long tiles first, short ones in the tail (K6 and K7)
+            binning.tile_order = torch.empty(binning.tile_ranges.shape[0], dtype=torch.int32, device=dev)
+            check(L.b200gs_tile_order(width, height, ptr(binning.tile_ranges), ptr(binning.tile_order), _stream()), "b200gs_tile_order")
         check(L.b200gs_blend_fwd_rows(mode, width, height, ptr(binning.tile_ranges), ptr(binning.sorted_ids), ptr(rows), ptr(bg), ptr(image),
-                                      pix_stride, ch_stride, ptr(final_T), ptr(n_contrib), None, _stream()), "b200gs_blend_fwd_rows")
+                                      pix_stride, ch_stride, ptr(final_T), ptr(n_contrib), None, ptr(binning.tile_order), _stream()),
+              "b200gs_blend_fwd_rows")
     return image, final_T, n_contrib
 
 
