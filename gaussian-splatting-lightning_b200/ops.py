@@ -558,7 +558,8 @@ class _RasterizeRaw(torch.autograd.Function):
             pix_stride, ch_stride, gsx, gsy = 3, 1, 1.0, 1.0
         with _stage("blend_bwd"):
             check(L.b200gs_blend_bwd_rows(mode, W, H, ptr(ctx.binning.tile_ranges), ptr(ctx.binning.sorted_ids), ptr(rows), ptr(bg), ptr(final_T),
-                                          ptr(n_contrib), ptr(v_image), pix_stride, ch_stride, None, gsx, gsy, ptr(v_rows), _stream()),
+                                          ptr(n_contrib), ptr(v_image), pix_stride, ch_stride, None, gsx, gsy, ptr(v_rows), ptr(ctx.binning.tile_order),
+                                          _stream()),
                   "b200gs_blend_bwd_rows")
         v_means = torch.empty(n, 3, dtype=torch.float32, device=dev)
         v_ls = torch.empty(n, 3, dtype=torch.float32, device=dev)

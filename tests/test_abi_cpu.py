@@ -85,3 +85,26 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in re.sub(r'"""[\s\S]*?"""|#.*', "", src), f"{f} references oracle/"
+
+
+def test_every_python_call_site_passes_the_declared_number_of_arguments():
+    """ctypes only reports a wrong argument count when the call runs, i.e. on the GPU box: check the call sites of the host code
+    statically against the signature table (a call through *args / **kwargs is skipped)."""
+    import ast
+    import glob
+    from b200gs import _lib
+    sig = _lib._SIGNATURES
+    pkg = os.path.join(ROOT, "gaussian-splatting-lightning_b200")
+    files = glob.glob(os.path.join(pkg, "*.py")) + glob.glob(os.path.join(pkg, "compat", "*.py")) + [os.path.join(ROOT, "bench.py")] \
+        + glob.glob(os.path.join(ROOT, "tests", "*.py")) + glob.glob(os.path.join(ROOT, "profiles", "tools", "*.py"))
+    checked = 0
+    for path in files:
+        tree = ast.parse(open(path).read(), filename=path)
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in sig:
+                if any(isinstance(a, ast.Starred) for a in node.args) or node.keywords:
+                    continue
+                want = len(sig[node.func.attr][1])
+                assert len(node.args) == want, f"{os.path.relpath(path, ROOT)}:{node.lineno}: {node.func.attr} called with {len(node.args)} arguments, declared {want}"
+                checked += 1
+    assert checked > 40
