@@ -75,9 +75,8 @@ _SIGNATURES = {
     "b200gs_bin_count_rows": (c_int32, [c_int32, c_int32, c_int32, c_int64, _P, c_int32, _P, c_size_t, _P, _P, c_int32, _P, _P, c_int64]),
     "b200gs_project_pack_workspace_bytes": (c_size_t, [c_int32, c_int64]),
     "b200gs_project_pack_multi": (c_int32, [POINTER(B200gsView), c_int32, c_int64] + [_P] * 6 + [c_int32] + [_P] * 4 + [POINTER(c_void_p), c_int64, _P, c_size_t, _P, _P]),
-    "b200gs_blend_fwd_rows": (c_int32, [c_int32] * 3 + [_P] * 5 + [c_int64, c_int64, _P, _P, _P, _P, _P]),
-    "b200gs_blend_bwd_rows": (c_int32, [c_int32] * 3 + [_P] * 7 + [c_int64, c_int64, _P, ctypes.c_float, ctypes.c_float, _P, _P, _P]),
-    "b200gs_tile_order": (c_int32, [c_int32, c_int32, _P, _P, _P]),
+    "b200gs_blend_fwd_rows": (c_int32, [c_int32] * 3 + [_P] * 5 + [c_int64, c_int64, _P, _P, _P, _P]),
+    "b200gs_blend_bwd_rows": (c_int32, [c_int32] * 3 + [_P] * 7 + [c_int64, c_int64, _P, ctypes.c_float, ctypes.c_float, _P, _P]),
     "b200gs_project_fwd_rows": (c_int32, [POINTER(B200gsView), c_int64] + [_P] * 6 + [c_int32] + [_P] * 4 + [_P]),
 }
 

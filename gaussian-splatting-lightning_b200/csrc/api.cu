@@ -455,29 +455,24 @@ int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height, int64_t n
 
 int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                           const float* rows, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride, float* final_T,
-                          int32_t* n_contrib, float* alpha, const int32_t* tile_order, void* stream) {
+                          int32_t* n_contrib, float* alpha, void* stream) {
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
     B200GS_CHECK_ARG(width > 0 && height > 0 && tile_ranges && image && final_T && n_contrib, "bad argument");
     return launch_blend_fwd(mode, width, height, 3, tile_ranges, sorted_ids, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY,
                             rows + B200GS_ROW_CONIC, rows + B200GS_ROW_OPACITY, rows + B200GS_ROW_RGB, bg, image, pix_stride,
-                            ch_stride, final_T, n_contrib, alpha, (cudaStream_t)stream, nullptr, tile_order);
-}
-
-int b200gs_tile_order(int32_t width, int32_t height, const int32_t* tile_ranges, int32_t* tile_order, void* stream) {
-    B200GS_CHECK_ARG(width > 0 && height > 0 && tile_ranges && tile_order, "bad argument");
-    return tile_order_impl(width, height, tile_ranges, tile_order, (cudaStream_t)stream);
+                            ch_stride, final_T, n_contrib, alpha, (cudaStream_t)stream);
 }
 
 int b200gs_blend_bwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                           const float* rows, const float* bg, const float* final_T, const int32_t* n_contrib, const float* v_image,
                           int64_t pix_stride, int64_t ch_stride, const float* v_alpha, float grad_scale_x, float grad_scale_y,
-                          float* v_rows, const int32_t* tile_order, void* stream) {
+                          float* v_rows, void* stream) {
     B200GS_CHECK_ARG(mode == B200GS_MODE_VANILLA || mode == B200GS_MODE_GSPLAT, "bad mode");
     B200GS_CHECK_ARG(width > 0 && height > 0 && tile_ranges && final_T && n_contrib && v_image && v_rows, "bad argument");
     return launch_blend_bwd(mode, width, height, 3, tile_ranges, sorted_ids, B200GS_ROW_FLOATS, rows + B200GS_ROW_XY,
                             rows + B200GS_ROW_CONIC, rows + B200GS_ROW_OPACITY, rows + B200GS_ROW_RGB, bg, final_T, n_contrib, v_image,
                             pix_stride, ch_stride, v_alpha, grad_scale_x, grad_scale_y, v_rows + B200GS_ROW_XY, v_rows + B200GS_ROW_CONIC,
-                            v_rows + B200GS_ROW_OPACITY, v_rows + B200GS_ROW_RGB, nullptr, (cudaStream_t)stream, -1, tile_order);
+                            v_rows + B200GS_ROW_OPACITY, v_rows + B200GS_ROW_RGB, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

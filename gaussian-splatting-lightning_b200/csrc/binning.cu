@@ -1103,47 +1103,6 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
     return copy_counts(d_counts, host_counts, sync_host, s);
 }
 
-// ---- processing order of the tiles for the blend kernels ---------------------------------------------------------------------
-// One CTA per tile and ~14-18 waves of CTAs: in natural (row-major) order the kernel ends when the last-started long tile ends, with
-// most SMs idle (ncu, round 2: K7 averaged 28 of its 32 resident warps).  order[] lists the tiles by decreasing list length — counting
-// sort on 4 x log2 buckets, tiles of a bucket roughly in row-major order (neighbouring tiles share their splats in L2) — so the long
-// tiles start first and the tail is made of short ones (longest-processing-time-first list scheduling).  One block.
-constexpr int ORDER_BUCKETS = 4 * 32 + 1;
-
-__global__ void __launch_bounds__(1024) tile_order_kernel(int n_tiles, const int2* __restrict__ ranges, int32_t* __restrict__ order) {
-    __shared__ int s_cnt[ORDER_BUCKETS];
-    __shared__ int s_pos[ORDER_BUCKETS];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < ORDER_BUCKETS; i += 1024) s_cnt[i] = 0;
-    __syncthreads();
-    auto bucket = [](int2 r) {
-        const int c = r.y - r.x;
-        if (c <= 0) return 0;
-        const int lg = 31 - __clz(c);                                   // 0..30
-        const int frac = lg >= 2 ? ((c >> (lg - 2)) & 3) : 0;           // next two bits below the leading one
-        return 1 + 4 * lg + frac;
-    };
-    for (int i = tid; i < n_tiles; i += 1024) atomicAdd(&s_cnt[bucket(ranges[i])], 1);
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int b = ORDER_BUCKETS - 1; b >= 0; --b) { s_pos[b] = run; run += s_cnt[b]; }
-    }
-    __syncthreads();
-    for (int base = 0; base < n_tiles; base += 1024) {                  // sweep by sweep: keeps a bucket's tiles near row-major order
-        const int i = base + tid;
-        if (i < n_tiles) order[atomicAdd(&s_pos[bucket(ranges[i])], 1)] = i;
-        __syncthreads();
-    }
-}
-
-int tile_order_impl(int width, int height, const int32_t* tile_ranges, int32_t* order, cudaStream_t s) {
-    const int n_tiles = div_up(width, TILE) * div_up(height, TILE);
-    tile_order_kernel<<<1, 1024, 0, s>>>(n_tiles, (const int2*)tile_ranges, order);
-    B200GS_LAUNCH_CHECK();
-    return B200GS_OK;
-}
-
 // ---- row packing for the Gaussian-sharded exchange -------------------------------------------------------------------
 namespace {
 

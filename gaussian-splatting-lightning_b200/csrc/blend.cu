@@ -118,7 +118,7 @@ __device__ __forceinline__ int build_list(const unsigned char* __restrict__ s_ma
 #endif
 
 template <int CH, bool GSPLAT>
-__global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_kernel(int width, int height, int grid_x, const int32_t* __restrict__ order, const int2* __restrict__ ranges,
+__global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
                                                               const int32_t* __restrict__ ids, const SplatStrides st, const float* __restrict__ xy,
                                                               const float* __restrict__ conic, const float* __restrict__ opacity,
                                                               const float* __restrict__ colors, const float* __restrict__ bg,
@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_ker
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const unsigned lane = tid & 31u;
-    // 1-D grid over the tiles; `order` (optional) = tiles by decreasing list length (b200gs_tile_order): the long tiles start first and the
-    // kernel's tail is made of the short ones
-    const int tile = order ? __ldg(order + blockIdx.x) : (int)blockIdx.x;
+    // 1-D grid over the tiles, row-major.  (A longest-list-first order, from a counting sort of the tile counts, was measured in round 2:
+    // K6 0.286 -> 0.287 ms, K7 0.4405 -> 0.4423 ms, plus 11 us for the ordering kernel — the kernels' tails are not what limits them.)
+    const int tile = (int)blockIdx.x;
     const int tile_y = tile / grid_x, tile_x = tile - tile_y * grid_x;
     int lx, ly;
     pixel_of_thread(tid, lx, ly);
@@ -263,7 +263,7 @@ __device__ __forceinline__ void stage_async(float4* slot, int g, const SplatStri
 // HITS: also mark every splat that contributed to at least one pixel (gsplat's `means2d.has_hit_any_pixels`, read by
 // SelectiveAdam, optimizers.py:39, and exported as `acc_vis`, gsplat_v1_renderer.py:287): one byte store per (warp, contributing entry).
 template <int CH, bool GSPLAT, bool ROWS, bool HITS>
-__global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_async_kernel(int width, int height, int grid_x, const int32_t* __restrict__ order, const int2* __restrict__ ranges,
+__global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_async_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
                                                               const int32_t* __restrict__ ids, const SplatStrides st, const float* __restrict__ xy,
                                                               const float* __restrict__ conic, const float* __restrict__ opacity,
                                                               const float* __restrict__ colors, const float* __restrict__ bg,
@@ -278,9 +278,7 @@ __global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_asy
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const unsigned lane = tid & 31u;
-    // 1-D grid over the tiles; `order` (optional) = tiles by decreasing list length (b200gs_tile_order): the long tiles start first and the
-    // kernel's tail is made of the short ones
-    const int tile = order ? __ldg(order + blockIdx.x) : (int)blockIdx.x;
+    const int tile = (int)blockIdx.x;
     const int tile_y = tile / grid_x, tile_x = tile - tile_y * grid_x;
     int lx, ly;
     pixel_of_thread(tid, lx, ly);
@@ -407,7 +405,7 @@ static_assert(sizeof(TrSmem<false>) <= 57344, "4 CTAs per SM need <= 56 KB each"
 // sums of an entry leave as THREE 128-bit reductions (REDG.E.ADD.F32x4: {xy, -, conic0} {conic1, conic2, -, opacity} {rgb, -})
 // instead of nine 32-bit ones — a third of the L2 atomic operations, which bound this kernel once the shuffles were gone.
 template <int CH, bool GSPLAT, bool ABS, bool VROWS>
-__global__ void __launch_bounds__(BLOCK_PIX, ABS ? 3 : 4) blend_bwd_tr_kernel(int width, int height, int grid_x, const int32_t* __restrict__ order, const int2* __restrict__ ranges,
+__global__ void __launch_bounds__(BLOCK_PIX, ABS ? 3 : 4) blend_bwd_tr_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
                                                                     const int32_t* __restrict__ ids, const SplatStrides st, const SplatStrides so,
                                                                     const float* __restrict__ xy, const float* __restrict__ conic,
                                                                     const float* __restrict__ opacity, const float* __restrict__ colors,
@@ -426,9 +424,7 @@ __global__ void __launch_bounds__(BLOCK_PIX, ABS ? 3 : 4) blend_bwd_tr_kernel(in
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const unsigned lane = tid & 31u;
-    // 1-D grid over the tiles; `order` (optional) = tiles by decreasing list length (b200gs_tile_order): the long tiles start first and the
-    // kernel's tail is made of the short ones
-    const int tile = order ? __ldg(order + blockIdx.x) : (int)blockIdx.x;
+    const int tile = (int)blockIdx.x;
     const int tile_y = tile / grid_x, tile_x = tile - tile_y * grid_x;
     int lx, ly;
     pixel_of_thread(tid, lx, ly);
@@ -633,7 +629,7 @@ __global__ void __launch_bounds__(BLOCK_PIX, ABS ? 3 : 4) blend_bwd_tr_kernel(in
 template <int CH>
 int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy, const float* conic,
                  const float* opacity, const float* colors, const float* bg, float* image, int64_t ps, int64_t cs, float* final_T,
-                 int32_t* n_contrib, float* alpha, uint8_t* hit_any, cudaStream_t s, const int32_t* order) {
+                 int32_t* n_contrib, float* alpha, uint8_t* hit_any, cudaStream_t s) {
     const int gx = div_up(width, TILE), gy = div_up(height, TILE);
     dim3 grid(gx * gy);
     const SplatStrides st = row_stride > 0 ? SplatStrides{row_stride, row_stride, row_stride, row_stride} : SplatStrides{2, 3, 1, CH};
@@ -645,7 +641,7 @@ int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
     // the row layout is [x, y, depth, A, B, C, comp, opacity, r, g, b, radius] (include/b200gs.h); 16-byte copies need 16-byte aligned rows
     const bool rows16 = row_stride == 12 && CH == 3 && conic == xy + 3 && opacity == xy + 7 && colors == xy + 8 && (reinterpret_cast<uintptr_t>(xy) & 15) == 0;
     if (!use_sync || hit_any != nullptr) {
-#define B200GS_FWD_ARGS width, height, gx, order, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, image, ps, cs, final_T, n_contrib, alpha, hit_any
+#define B200GS_FWD_ARGS width, height, gx, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, image, ps, cs, final_T, n_contrib, alpha, hit_any
 #define B200GS_FWD_LAUNCH(G, R)                                                                                                   \
     do {                                                                                                                           \
         if (hit_any) blend_fwd_async_kernel<CH, G, R, true><<<grid, BLOCK_PIX, 0, s>>>(B200GS_FWD_ARGS);                          \
@@ -666,10 +662,10 @@ int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
         return B200GS_OK;
     }
     if (mode == B200GS_MODE_GSPLAT)
-        blend_fwd_kernel<CH, true><<<grid, BLOCK_PIX, 0, s>>>(width, height, gx, order, (const int2*)ranges, ids, st, xy, conic,
+        blend_fwd_kernel<CH, true><<<grid, BLOCK_PIX, 0, s>>>(width, height, gx, (const int2*)ranges, ids, st, xy, conic,
                                                               opacity, colors, bg, image, ps, cs, final_T, n_contrib, alpha);
     else
-        blend_fwd_kernel<CH, false><<<grid, BLOCK_PIX, 0, s>>>(width, height, gx, order, (const int2*)ranges, ids, st, xy, conic,
+        blend_fwd_kernel<CH, false><<<grid, BLOCK_PIX, 0, s>>>(width, height, gx, (const int2*)ranges, ids, st, xy, conic,
                                                                opacity, colors, bg, image, ps, cs, final_T, n_contrib, alpha);
     B200GS_LAUNCH_CHECK();
     return B200GS_OK;
@@ -679,7 +675,7 @@ template <int CH>
 int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy, const float* conic,
                  const float* opacity, const float* colors, const float* bg, const float* final_T, const int32_t* n_contrib,
                  const float* v_image, int64_t ps, int64_t cs, const float* v_alpha, float sx, float sy, int out_row_stride, float* v_xy,
-                 float* v_conic, float* v_opacity, float* v_colors, float* v_xy_abs, cudaStream_t s, const int32_t* order) {
+                 float* v_conic, float* v_opacity, float* v_colors, float* v_xy_abs, cudaStream_t s) {
     const int gx = div_up(width, TILE), gy = div_up(height, TILE);
     dim3 grid(gx * gy);
     const SplatStrides st = row_stride > 0 ? SplatStrides{row_stride, row_stride, row_stride, row_stride} : SplatStrides{2, 3, 1, CH};
@@ -687,7 +683,7 @@ int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
     // gradient outputs that are the columns of one 16-byte aligned [n,12] row buffer leave as 128-bit reductions
     const bool vrows = CH == 3 && out_row_stride == B200GS_ROW_FLOATS && v_conic == v_xy + B200GS_ROW_CONIC && v_opacity == v_xy + B200GS_ROW_OPACITY &&
                        v_colors == v_xy + B200GS_ROW_RGB && (reinterpret_cast<uintptr_t>(v_xy) & 15) == 0;
-#define B200GS_BWD_ARGS width, height, gx, order, (const int2*)ranges, ids, st, so, xy, conic, opacity, colors, bg, final_T, n_contrib, \
+#define B200GS_BWD_ARGS width, height, gx, (const int2*)ranges, ids, st, so, xy, conic, opacity, colors, bg, final_T, n_contrib, \
                         v_image, ps, cs, v_alpha, sx, sy, v_xy, v_conic, v_opacity, v_colors, v_xy_abs
     static const cudaError_t attr_rc = []() {
         cudaError_t e = cudaSuccess;
@@ -733,12 +729,12 @@ int bwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
 int launch_blend_fwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids, int row_stride, const float* xy,
                      const float* conic, const float* opacity, const float* colors, const float* bg, float* image,
                      int64_t pix_stride, int64_t ch_stride, float* final_T, int32_t* n_contrib, float* alpha, cudaStream_t s,
-                     uint8_t* hit_any, const int32_t* order) {
+                     uint8_t* hit_any) {
     switch (channels) {
-        case 1: return fwd_dispatch<1>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s, order);
-        case 2: return fwd_dispatch<2>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s, order);
-        case 3: return fwd_dispatch<3>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s, order);
-        case 4: return fwd_dispatch<4>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s, order);
+        case 1: return fwd_dispatch<1>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s);
+        case 2: return fwd_dispatch<2>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s);
+        case 3: return fwd_dispatch<3>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s);
+        case 4: return fwd_dispatch<4>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, image, pix_stride, ch_stride, final_T, n_contrib, alpha, hit_any, s);
     }
     set_error("blend_fwd: unsupported channel count %d (1..4)", channels);
     return B200GS_EINVAL;
@@ -748,10 +744,10 @@ int launch_blend_bwd(int mode, int width, int height, int channels, const int32_
                      const float* conic, const float* opacity, const float* colors, const float* bg, const float* final_T,
                      const int32_t* n_contrib, const float* v_image, int64_t pix_stride, int64_t ch_stride, const float* v_alpha,
                      float sx, float sy, float* v_xy, float* v_conic, float* v_opacity, float* v_colors, float* v_xy_abs,
-                     cudaStream_t s, int out_row_stride, const int32_t* order) {
+                     cudaStream_t s, int out_row_stride) {
     if (out_row_stride < 0) out_row_stride = row_stride;
 #define B200GS_BWD_CALL(C) bwd_dispatch<C>(mode, width, height, ranges, ids, row_stride, xy, conic, opacity, colors, bg, final_T, n_contrib, v_image, \
-                                           pix_stride, ch_stride, v_alpha, sx, sy, out_row_stride, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s, order)
+                                           pix_stride, ch_stride, v_alpha, sx, sy, out_row_stride, v_xy, v_conic, v_opacity, v_colors, v_xy_abs, s)
     switch (channels) {
         case 1: return B200GS_BWD_CALL(1);
         case 2: return B200GS_BWD_CALL(2);

@@ -122,8 +122,6 @@ int bin_sort(int mode, int width, int height, int64_t n, int cull, int64_t max_c
              const void* ws_a, void* ws_b, size_t ws_b_bytes, int32_t* sorted_ids, int32_t* tile_ranges, int64_t* host_counts,
              int sync_host, cudaStream_t s);
 
-int tile_order_impl(int width, int height, const int32_t* tile_ranges, int32_t* order, cudaStream_t s);
-
 int launch_selective_adam(int64_t rows, int width, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const uint8_t* visible,
                           float lr, float b1, float b2, float eps, cudaStream_t s);
 int launch_densify_stats(int64_t n, const int32_t* radii, const uint8_t* visible, const float* grad, int grad_stride, float sx, float sy,
@@ -140,12 +138,11 @@ int launch_loss_bwd(int channels, int width, int height, const float* img, const
 int launch_blend_fwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids,
                      int row_stride, const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
                      float* image, int64_t pix_stride, int64_t ch_stride, float* final_T, int32_t* n_contrib,
-                     float* alpha, cudaStream_t s, uint8_t* hit_any = nullptr, const int32_t* order = nullptr);
+                     float* alpha, cudaStream_t s, uint8_t* hit_any = nullptr);
 int launch_blend_bwd(int mode, int width, int height, int channels, const int32_t* ranges, const int32_t* ids,
                      int row_stride, const float* xy, const float* conic, const float* opacity, const float* colors, const float* bg,
                      const float* final_T, const int32_t* n_contrib, const float* v_image, int64_t pix_stride,
                      int64_t ch_stride, const float* v_alpha, float sx, float sy, float* v_xy, float* v_conic,
-                     float* v_opacity, float* v_colors, float* v_xy_abs, cudaStream_t s, int out_row_stride = -1,
-                     const int32_t* order = nullptr);
+                     float* v_opacity, float* v_colors, float* v_xy_abs, cudaStream_t s, int out_row_stride = -1);
 
 }  // namespace b200gs

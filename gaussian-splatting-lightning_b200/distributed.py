@@ -536,8 +536,7 @@ class _ExchangeRasterize(torch.autograd.Function):
             v_recv = torch.zeros_like(st.recv)
         with ops._stage("blend_bwd"):
             check(L.b200gs_blend_bwd_rows(MODE_GSPLAT, W, H, ptr(st.binning.tile_ranges), ptr(st.binning.sorted_ids), ptr(st.recv), ptr(bg),
-                                          ptr(st.final_T), ptr(st.n_contrib), ptr(v_image), 3, 1, None, 1.0, 1.0, ptr(v_recv), ptr(st.binning.tile_order),
-                                          stream), "b200gs_blend_bwd_rows")
+                                          ptr(st.final_T), ptr(st.n_contrib), ptr(v_image), 3, 1, None, 1.0, 1.0, ptr(v_recv), stream), "b200gs_blend_bwd_rows")
         grads = []
 
         def xy_grad(j, rows, shift):

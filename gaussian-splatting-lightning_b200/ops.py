@@ -26,10 +26,6 @@ ROW_FLOATS = 12   # include/b200gs.h B200GS_ROW_FLOATS
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
-# Longest-tile-first processing order for the blend kernels of the row paths (B200GS_TILE_ORDER=0: row-major, for A/B measurements)
-TILE_ORDER = os.environ.get("B200GS_TILE_ORDER", "1") != "0"
-
-
 def _stream() -> int:
     """cudaStream_t of torch's current stream on the current device (raw handle; ~20x cheaper than current_stream())."""
     if _raw_stream is not None:
@@ -140,11 +136,10 @@ class Binning:
     (every tile of the 3-sigma rects; bounds `total`), `coarse_pairs` = (8x8-tile cell, Gaussian) pairs of the first
     binning level, `total` = number of listed pairs.  In lazy mode the counters arrive asynchronously: rect/coarse are
     None until resolve(), `total` waits for its own copy when first read (see bin_gaussians)."""
-    __slots__ = ("sorted_ids", "tile_ranges", "tile_order", "rect_pairs", "coarse_pairs", "_total", "_pending", "_host", "_event_b")
+    __slots__ = ("sorted_ids", "tile_ranges", "rect_pairs", "coarse_pairs", "_total", "_pending", "_host", "_event_b")
 
     def __init__(self, sorted_ids, tile_ranges, total=None, host=None, pending=None, event_b=None):
         self.sorted_ids, self.tile_ranges, self._total = sorted_ids, tile_ranges, total
-        self.tile_order = None        # [n_tiles] int32, tiles by decreasing list length (filled by blend_forward_rows: b200gs_tile_order)
         self.rect_pairs = self.coarse_pairs = None
         self._host, self._pending, self._event_b = host, pending, event_b
         if host is not None and pending is None:
@@ -283,12 +278,8 @@ def blend_forward_rows(mode, width, height, binning: Binning, rows, bg, planar=F
     n_contrib = torch.empty(height, width, dtype=torch.int32, device=dev)
     pix_stride, ch_stride = (1, height * width) if planar else (3, 1)
     with _stage("blend_fwd"):
-        if binning.tile_order is None and TILE_ORDER:     # tiles by decreasing list length: long tiles first, short ones in the tail (K6 and K7)
-            binning.tile_order = torch.empty(binning.tile_ranges.shape[0], dtype=torch.int32, device=dev)
-            check(L.b200gs_tile_order(width, height, ptr(binning.tile_ranges), ptr(binning.tile_order), _stream()), "b200gs_tile_order")
         check(L.b200gs_blend_fwd_rows(mode, width, height, ptr(binning.tile_ranges), ptr(binning.sorted_ids), ptr(rows), ptr(bg), ptr(image),
-                                      pix_stride, ch_stride, ptr(final_T), ptr(n_contrib), None, ptr(binning.tile_order), _stream()),
-              "b200gs_blend_fwd_rows")
+                                      pix_stride, ch_stride, ptr(final_T), ptr(n_contrib), None, _stream()), "b200gs_blend_fwd_rows")
     return image, final_T, n_contrib
 
 
@@ -558,8 +549,7 @@ class _RasterizeRaw(torch.autograd.Function):
             pix_stride, ch_stride, gsx, gsy = 3, 1, 1.0, 1.0
         with _stage("blend_bwd"):
             check(L.b200gs_blend_bwd_rows(mode, W, H, ptr(ctx.binning.tile_ranges), ptr(ctx.binning.sorted_ids), ptr(rows), ptr(bg), ptr(final_T),
-                                          ptr(n_contrib), ptr(v_image), pix_stride, ch_stride, None, gsx, gsy, ptr(v_rows), ptr(ctx.binning.tile_order),
-                                          _stream()),
+                                          ptr(n_contrib), ptr(v_image), pix_stride, ch_stride, None, gsx, gsy, ptr(v_rows), _stream()),
                   "b200gs_blend_bwd_rows")
         v_means = torch.empty(n, 3, dtype=torch.float32, device=dev)
         v_ls = torch.empty(n, 3, dtype=torch.float32, device=dev)

@@ -340,19 +340,15 @@ B200GS_API int b200gs_unpack_rows_grad(int64_t n, const int32_t* radii, const in
 B200GS_API int b200gs_bin_count_rows(int32_t mode, int32_t width, int32_t height, int64_t n, const float* rows, int32_t cull,
                                      void* workspace_a, size_t workspace_a_bytes, int64_t* d_counts, int64_t* host_counts,
                                      int32_t sync_host, void* stream, const int64_t* block_counts, int64_t block_rows);
-/* tile_order (optional, NULL = row-major): the order in which the blend kernels take the tiles, from b200gs_tile_order — tiles by
- *     decreasing list length, so that the long tiles start first and the kernels' tails are made of short ones.  Results do not depend
- *     on it (tiles are independent). */
-B200GS_API int b200gs_tile_order(int32_t width, int32_t height, const int32_t* tile_ranges, int32_t* tile_order /* [n_tiles] */, void* stream);
 B200GS_API int b200gs_blend_fwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                                      const float* rows, const float* bg, float* image, int64_t pix_stride, int64_t ch_stride,
-                                     float* final_T, int32_t* n_contrib, float* alpha, const int32_t* tile_order, void* stream);
+                                     float* final_T, int32_t* n_contrib, float* alpha, void* stream);
 /* grad_scale_x / _y: factor on the mean2D columns of the gradient rows (vanilla renderers: 0.5 W, 0.5 H — the vanilla rasterizer's
  *     NDC-unit convention; gsplat renderers: 1, 1).  v_rows must be zero-filled: the kernel accumulates with 128-bit reductions. */
 B200GS_API int b200gs_blend_bwd_rows(int32_t mode, int32_t width, int32_t height, const int32_t* tile_ranges, const int32_t* sorted_ids,
                                      const float* rows, const float* bg, const float* final_T, const int32_t* n_contrib,
                                      const float* v_image, int64_t pix_stride, int64_t ch_stride, const float* v_alpha,
-                                     float grad_scale_x, float grad_scale_y, float* v_rows, const int32_t* tile_order, void* stream);
+                                     float grad_scale_x, float grad_scale_y, float* v_rows, void* stream);
 
 #ifdef __cplusplus
 }
