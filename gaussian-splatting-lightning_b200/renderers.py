@@ -252,10 +252,14 @@ class B200GSplatRenderer(Renderer):
     }
 
     def __init__(self, block_size: int = DEFAULT_BLOCK_SIZE, anti_aliased: bool = DEFAULT_ANTI_ALIASED_STATUS,
-                 kernel_size: float = 0.3, cache_cameras: bool = True, fused_activations: bool = True) -> None:
+                 kernel_size: float = 0.3, cache_cameras: bool = True, fused_activations: bool = True, absgrad: bool = False) -> None:
+        """absgrad: also accumulate |dL/dmean2D| per Gaussian and hand it out as ``viewspace_points.absgrad`` after backward — what the
+        density controller reads when its ``absgrad`` option is on (vanilla_density_controller.py:112-113); the rgb pass computes it
+        (the op-by-op path: the fused single-node path has no absgrad output)."""
         super().__init__()
         if block_size != DEFAULT_BLOCK_SIZE:
             raise ValueError("b200gs supports block_size 16 only")
+        self.absgrad = bool(absgrad)
         self.block_size = block_size
         self.anti_aliased = anti_aliased
         self.filter_2d_kernel_size = kernel_size
@@ -283,7 +287,7 @@ class B200GSplatRenderer(Renderer):
 
     def forward(self, viewpoint_camera, pc, bg_color: torch.Tensor, scaling_modifier=1.0, render_types: list = None, **kwargs):
         bits = self.parse_render_types(render_types)
-        raw = _raw_parameters(pc) if (self.fused_activations and bits == self._RGB_REQUIRED) else None
+        raw = _raw_parameters(pc) if (self.fused_activations and bits == self._RGB_REQUIRED and not getattr(self, "absgrad", False)) else None
         if raw is not None:
             # one autograd node for the whole step (K1..K6 / K7 -> gradient rows -> K8); image size from the cached host view: no
             # device->host read, no pageable host->device copy anywhere in the step
@@ -324,7 +328,11 @@ class B200GSplatRenderer(Renderer):
             viewdirs = pc.get_xyz.detach() - viewpoint_camera.camera_center
             rgbs = ops.spherical_harmonics(pc.active_sh_degree, viewdirs, pc.get_features)
             rgbs = torch.clamp(rgbs + 0.5, min=0.0)
-            rgb = rasterize(rgbs, bg_color).permute(2, 0, 1)
+            if getattr(self, "absgrad", False):
+                rgb = ops.rasterize_gaussians(xys, depths, radii, conics, num_tiles_hit, rgbs, opacities, img_height, img_width, self.block_size,
+                                              bg_color, False, absgrad=True).permute(2, 0, 1)
+            else:
+                rgb = rasterize(rgbs, bg_color).permute(2, 0, 1)
 
         alpha = acc_depth_im = acc_depth_inverted_im = exp_depth_im = exp_depth_inverted_im = None
         zero1 = torch.zeros((1,), dtype=torch.float, device=bg_color.device)
@@ -462,6 +470,7 @@ class B200GSplatRendererConfig(RendererConfig):
     block_size: int = DEFAULT_BLOCK_SIZE
     anti_aliased: bool = DEFAULT_ANTI_ALIASED_STATUS
     kernel_size: float = 0.3
+    absgrad: bool = False
 
     def instantiate(self, *args, **kwargs) -> Renderer:
-        return B200GSplatRenderer(self.block_size, self.anti_aliased, self.kernel_size)
+        return B200GSplatRenderer(self.block_size, self.anti_aliased, self.kernel_size, absgrad=self.absgrad)

@@ -93,3 +93,33 @@ def test_v1_multichannel_side_channels_and_hooks():
     od = d(cam, model, torch.zeros(3, device=DEV), render_types=["rgb", "alpha"])
     assert torch.allclose(od["render"][0], od["alpha"][0], atol=1e-6)            # white splats on black: every channel equals alpha
     assert float(od["alpha"].mean()) < float(out["alpha"].mean()) if out["alpha"] is not None else True
+
+
+def test_v0_renderer_absgrad_option_matches_v1_side_channel():
+    """`absgrad: true` of the density controller (vanilla_density_controller.py:112-113) reads `viewspace_points.absgrad`: the v0-surface
+    renderer provides it through its `absgrad` option (also on the config dataclass); same values as the v1 renderer's side channel."""
+    from b200gs.renderers import B200GSplatRenderer, B200GSplatRendererConfig
+    from b200gs.v1 import B200GSplatV1Renderer
+    raw, model, cam = _setup()
+    bg = torch.tensor([0.2, 0.1, 0.5], device=DEV)
+    r0 = B200GSplatRendererConfig(absgrad=True).instantiate().to(DEV)
+    assert isinstance(r0, B200GSplatRenderer) and r0.absgrad
+    out0 = r0(cam, model, bg)
+    vp0 = out0["viewspace_points"]
+    vp0.retain_grad()
+    out0["render"].square().sum().backward()
+    assert vp0.grad is not None and hasattr(vp0, "absgrad") and vp0.absgrad.shape[0] == vp0.grad.shape[0]
+    assert bool((vp0.absgrad >= vp0.grad.abs()[:, :2] - 1e-4 * vp0.absgrad.max()).all()) and float(vp0.absgrad.sum()) > 0
+    for p in model.parameters():
+        p.grad = None
+    r1 = B200GSplatV1Renderer(tile_based_culling=True).instantiate().to(DEV)
+    out1 = r1(cam, model, bg)
+    vp1 = out1["viewspace_points"]
+    vp1.retain_grad()
+    out1["render"].square().sum().backward()
+    scale = float(vp1.absgrad.max())
+    assert float((vp0.absgrad - vp1.absgrad).abs().max()) < 2e-4 * scale
+    # without the option nothing is attached (and the fused single-node path stays in use)
+    out2 = B200GSplatRenderer().to(DEV)(cam, model, bg)
+    out2["render"].sum().backward()
+    assert not hasattr(out2["viewspace_points"], "absgrad")
