@@ -138,13 +138,114 @@ def _host_group(group):
     return g
 
 
+class _ShmBoard:
+    """Host-side all-gather of a few floats per rank and step through POSIX shared memory, for process groups whose ranks all live
+    on one host (the NVSwitch box the peer exchange needs anyway).  A gloo all_gather of 8 x 160 bytes took ~0.8 ms of HOST time per
+    step at 8 ranks (profiles/round2_timeline_n8.md) — with ~1.2 ms of other host work per step that made the host, not the GPUs, the
+    bottleneck of the 8-GPU step.  Here every rank writes its record and a sequence number into its own slot of an mmap'ed file in
+    /dev/shm and reads the others' once their sequence number has arrived: a few microseconds.  Slots are double-buffered by step
+    parity: a rank can be at most one step ahead of the slowest reader (it cannot finish step s+1's gather before every rank has
+    written its step s+1 record, which a rank does only after reading step s).  Stores and loads are in program order on x86 hosts
+    (the sequence number is written after the record and read before it)."""
+
+    SLOT_BYTES = 256 * ((VIEW_FLOATS * 4 + 8 + 255) // 256)
+
+    def __init__(self, group):
+        import mmap
+        import numpy as np
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        hg = _host_group(group)
+        size = 2 * self.world * self.SLOT_BYTES
+        path = [None]
+        if self.rank == 0:
+            name = f"/dev/shm/b200gs_board_{os.getpid()}_{int.from_bytes(os.urandom(6), 'little'):x}"
+            fd = os.open(name, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, size)
+            path[0] = name
+        dist.broadcast_object_list(path, src=dist.get_global_rank(hg, 0), group=hg)
+        if self.rank != 0:
+            fd = os.open(path[0], os.O_RDWR)
+        self._mm = mmap.mmap(fd, size)
+        os.close(fd)
+        dist.barrier(group=hg)            # everybody has mapped the file: its name can go (no leak if a rank dies later)
+        if self.rank == 0:
+            os.unlink(path[0])
+        self._buf = np.frombuffer(self._mm, dtype=np.uint8)
+        self._np = np
+        self.seq = 0
+
+    def _slot(self, parity, j):
+        o = (parity * self.world + j) * self.SLOT_BYTES
+        return self._buf[o:o + 8].view(self._np.int64), self._buf[o + 8:o + 8 + VIEW_FLOATS * 4].view(self._np.float32)
+
+    def all_gather(self, mine: torch.Tensor) -> torch.Tensor:
+        import time
+        self.seq += 1
+        p = self.seq & 1
+        seq_w, rec_w = self._slot(p, self.rank)
+        rec_w[:] = mine.numpy()
+        seq_w[0] = self.seq
+        out = torch.empty(self.world, VIEW_FLOATS, dtype=torch.float32)
+        o = out.numpy()
+        t0 = None
+        for j in range(self.world):
+            seq_r, rec_r = self._slot(p, j)
+            spins = 0
+            while int(seq_r[0]) != self.seq:
+                spins += 1
+                if spins % 2000 == 0:
+                    time.sleep(0)
+                    t0 = t0 or time.monotonic()
+                    if time.monotonic() - t0 > 600.0:
+                        raise RuntimeError(f"b200gs: rank {j} did not post its camera for step {self.seq} within 600 s")
+            o[j] = rec_r
+        return out
+
+
+_BOARDS = {}
+
+
+def _same_host(group) -> bool:
+    import socket
+    names = [None] * dist.get_world_size(group)
+    dist.all_gather_object(names, socket.gethostname(), group=_host_group(group))
+    return len(set(names)) == 1 and os.path.isdir("/dev/shm")
+
+
+def _board(group):
+    """The shared-memory board of `group`, or None when its ranks span several hosts (collective on first use)."""
+    key = id(group) if group is not None else None
+    with _STATE_LOCK:
+        if key in _BOARDS:
+            return _BOARDS[key]
+    board = None
+    if os.environ.get("B200GS_SHM_BOARD", "1") != "0":
+        ok = _same_host(group)
+        if ok:
+            try:
+                board = _ShmBoard(group)
+            except OSError:
+                board = None
+            flags = [None] * dist.get_world_size(group)
+            dist.all_gather_object(flags, board is not None, group=_host_group(group))
+            if not all(flags):
+                board = None
+    with _STATE_LOCK:
+        _BOARDS[key] = board
+    return board
+
+
 def gather_views_host(camera, group=None, cache: bool = True) -> torch.Tensor:
     """[world, VIEW_FLOATS] CPU tensor with every rank's camera, no device synchronisation (cache=False re-reads the camera's
-    device tensors every call — one sync — for cameras whose pose is being optimised)."""
+    device tensors every call — one sync — for cameras whose pose is being optimised).  Ranks of one host exchange through shared
+    memory (_ShmBoard), otherwise through the gloo twin of the group."""
     world = dist.get_world_size(group)
-    mine = pack_view_host(camera, cache)
+    mine = pack_view_host(camera, cache).contiguous()
+    board = _board(group)
+    if board is not None:
+        return board.all_gather(mine)
     out = torch.empty(world * VIEW_FLOATS, dtype=torch.float32)
-    dist.all_gather_into_tensor(out, mine.contiguous(), group=_host_group(group))
+    dist.all_gather_into_tensor(out, mine, group=_host_group(group))
     return out.reshape(world, VIEW_FLOATS)
 
 

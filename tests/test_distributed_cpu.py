@@ -207,3 +207,51 @@ def test_shard_range_matches_reference_rule():
         for r in range(w):
             lo, hi = shard_range(n, w, r)
             assert lo == per * r and hi == (n if r == w - 1 else per * (r + 1))
+
+
+def _board_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import time
+        from b200gs import distributed as D
+        board = D._board(None)
+        assert board is not None, "ranks of one host with /dev/shm must get the shared-memory board"
+        for step in range(300):
+            if step % 37 == rank:            # skew: one rank arrives late
+                time.sleep(0.002)
+            mine = torch.arange(D.VIEW_FLOATS, dtype=torch.float32) + 1000.0 * step + 100000.0 * rank
+            got = board.all_gather(mine)
+            assert got.shape == (world, D.VIEW_FLOATS)
+            for j in range(world):
+                assert torch.equal(got[j], torch.arange(D.VIEW_FLOATS, dtype=torch.float32) + 1000.0 * step + 100000.0 * j), (step, j)
+        # the public entry point takes the board, and gives what the gloo path gives
+        from b200gs.scene import make_ring_cameras
+        cams = make_ring_cameras(64, 48)
+        a = D.gather_views_host(cams[2 + rank], None, cache=False)
+        with D._STATE_LOCK:
+            D._BOARDS[None] = None           # force the gloo path
+        b = D.gather_views_host(cams[2 + rank], None, cache=False)
+        assert torch.equal(a, b)
+        q.put((rank, "ok"))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_memory_board_world_3():
+    """The host-side camera exchange of one-host groups (b200gs.distributed._ShmBoard): 300 steps with skewed arrival, 3 ranks."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_board_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, msg in res:
+        assert msg == "ok", f"rank {rank}: {msg}"
