@@ -219,7 +219,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, "single" if world == 1 else "sharded-by-gaussian-index+all-to-all"),
+        "config": workload_config(args, "single" if world == 1 else "sharded-by-gaussian-index+exchange-of-projected-splats(peer stores over NVLink; all-to-all fallback)"),
         "cpu_baseline": {"value": vps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -568,7 +568,7 @@ def main():
     line = {
         "metric": METRIC, "value": views_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, ("sharded-by-gaussian-index+all-to-all" if sharded else "replicas") if world > 1 else "single"),
+        "data": "synthetic", "config": workload_config(args, ("sharded-by-gaussian-index+exchange-of-projected-splats(peer stores over NVLink; all-to-all fallback)" if sharded else "replicas") if world > 1 else "single"),
         "e2e": {"value": e2e_vps, "unit": UNIT, "h2d_bytes_per_step": cot_bytes, "d2h_bytes_per_step": 4,
                 "note": "per step: the [3,H,W] input image pinned-host->device and the scalar result device->host, inside the timed region; "
                         "the 32 camera poses (40 floats each) are device-resident before the loop, as a training set's cameras are"},

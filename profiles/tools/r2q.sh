@@ -1,5 +1,6 @@
 # final call of round 2 (1 GPU): full GPU test suite, the bench lines the driver asks for, launch list + full ncu capture, sanitizers
 mkdir -p gpurun_out
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/r2q_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r2q_smoke.log
 timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/r2q_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r2q_tests.log | cut -c1-300
 timeout 900 python bench.py > gpurun_out/r2q_bench_default.log 2>&1; echo "bench default rc=$?"
 timeout 600 python bench.py --impl reference > gpurun_out/r2q_bench_reference.log 2>&1; echo "bench reference rc=$?"
