@@ -66,7 +66,7 @@ def kernels():
                 cells.append("-")
         lines.append(f"| `{label}` | " + " | ".join(cells) + " |")
         key = {"blend_bwd_tr_kernel": "blend_bwd", "blend_fwd_kernel": "blend_fwd", "blend_fwd_async_kernel": "blend_fwd", "project_fwd_kernel": "project_fwd",
-               "project_bwd_kernel": "project_bwd"}.get(name.split("<")[0])
+               "project_bwd_kernel": "project_bwd", "depth_keys_kernel": "bin_count", "emit_cells_kernel": "bin_sort"}.get(name.split("::")[-1].split("<")[0])
         if key and key not in traffic:
             ir, iw, ii = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("smsp__inst_executed.sum")
             traffic[key] = int(to_bytes(vals[ir], units[ir]) + to_bytes(vals[iw], units[iw]))
