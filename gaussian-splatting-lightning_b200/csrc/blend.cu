@@ -263,7 +263,7 @@ __device__ __forceinline__ void stage_async(float4* slot, int g, const SplatStri
 // HITS: also mark every splat that contributed to at least one pixel (gsplat's `means2d.has_hit_any_pixels`, read by
 // SelectiveAdam, optimizers.py:39, and exported as `acc_vis`, gsplat_v1_renderer.py:287): one byte store per (warp, contributing entry).
 template <int CH, bool GSPLAT, bool ROWS, bool HITS>
-__global__ void __launch_bounds__(BLOCK_PIX, B200GS_FWD_MINBLOCKS) blend_fwd_async_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
+__global__ void __launch_bounds__(BLOCK_PIX, 3) blend_fwd_async_kernel(int width, int height, int grid_x, const int2* __restrict__ ranges,
                                                               const int32_t* __restrict__ ids, const SplatStrides st, const float* __restrict__ xy,
                                                               const float* __restrict__ conic, const float* __restrict__ opacity,
                                                               const float* __restrict__ colors, const float* __restrict__ bg,
@@ -633,14 +633,18 @@ int fwd_dispatch(int mode, int width, int height, const int32_t* ranges, const i
     const int gx = div_up(width, TILE), gy = div_up(height, TILE);
     dim3 grid(gx * gy);
     const SplatStrides st = row_stride > 0 ? SplatStrides{row_stride, row_stride, row_stride, row_stride} : SplatStrides{2, 3, 1, CH};
-    // Two stagings of the tile slab.  Synchronous (default): ids -> gathered records -> registers -> shared memory, the latency covered by
-    // the other 2-3 CTAs of the SM.  Asynchronous (B200GS_FWD_ASYNC=1; always for the has_hit_any_pixels variant): cp.async double buffer.
-    // Measured at 1 M Gaussians / 1080p on B200 (profiles/round2_*): 0.281 ms synchronous vs 0.308 ms asynchronous — the eight 4/8-byte
-    // LDGSTS per splat of the separate-array layout cost more issue slots than the overlap returns.
-    static const bool use_sync = []() { const char* e = getenv("B200GS_FWD_ASYNC"); return !(e && e[0] == '1'); }();
+    // Two stagings of the tile slab.  Synchronous: ids -> gathered records -> registers -> shared memory, the latency covered by the other
+    // CTAs of the SM.  Asynchronous: cp.async (LDGSTS) double buffer.  Measured at 1 M Gaussians / 1080p on B200 (profiles/round2_*):
+    //   first version of the asynchronous kernel (81 registers = 2 blocks per SM)            0.308-0.310 ms   vs synchronous 0.281-0.290 ms
+    //   asynchronous kernel capped at 80 registers (3 blocks per SM), [n,12] rows (3 x 16 B)  0.277 ms         vs synchronous 0.290 ms
+    // so the asynchronous staging is the default for the row layout (what the fused renderers and the sharded renderer use) and for the
+    // has_hit_any_pixels variant; the separate-array layout (eight 4/8-byte LDGSTS per splat) stays synchronous.
+    // B200GS_FWD_ASYNC=1 / =0 forces one or the other everywhere.
+    static const int async_env = []() { const char* e = getenv("B200GS_FWD_ASYNC"); return (e && e[0] == '1') ? 1 : (e && e[0] == '0') ? 0 : -1; }();
     // the row layout is [x, y, depth, A, B, C, comp, opacity, r, g, b, radius] (include/b200gs.h); 16-byte copies need 16-byte aligned rows
     const bool rows16 = row_stride == 12 && CH == 3 && conic == xy + 3 && opacity == xy + 7 && colors == xy + 8 && (reinterpret_cast<uintptr_t>(xy) & 15) == 0;
-    if (!use_sync || hit_any != nullptr) {
+    const bool use_async = async_env == 1 || (async_env == -1 && rows16);
+    if (use_async || hit_any != nullptr) {
 #define B200GS_FWD_ARGS width, height, gx, (const int2*)ranges, ids, st, xy, conic, opacity, colors, bg, image, ps, cs, final_T, n_contrib, alpha, hit_any
 #define B200GS_FWD_LAUNCH(G, R)                                                                                                   \
     do {                                                                                                                           \
