@@ -583,6 +583,10 @@ def main():
         "scene": {"N": N, "V": V, "I": I, "I_after_exact_culling": I_culled, "coarse_pairs": C_coarse, "P": P, "stage_sum_ms": round(sum(stage_ms.values()), 4)},
     }
     line.update(extras)
+    if world > 1:
+        line["scaling_note"] = ("N > 1 lines run configs[3] (and configs[4] at N = 8) as the north_star names them; the N = 1 headline line is configs[1], "
+                                "a lighter workload: value / (N * value_N1) mixes workloads. The like-for-like single-GPU denominator, measured in this "
+                                "run on rank 0 alone, is single_gpu_same_workload.value (also scaling_base.value in the N = 1 line).")
     if world == 1 and not args.no_extras:
         try:
             line["loss_stage"] = loss_stage(W, H, dev)
