@@ -108,3 +108,15 @@ def test_every_python_call_site_passes_the_declared_number_of_arguments():
                 assert len(node.args) == want, f"{os.path.relpath(path, ROOT)}:{node.lineno}: {node.func.attr} called with {len(node.args)} arguments, declared {want}"
                 checked += 1
     assert checked > 40
+
+
+def test_header_prototypes_and_ctypes_table_agree_on_argument_counts(lib):
+    """Every prototype of include/b200gs.h has as many parameters as its entry of the ctypes signature table (a drifted table only
+    fails when the call runs, i.e. on the GPU box)."""
+    text = re.sub(r"/\*.*?\*/", " ", open(HEADER).read(), flags=re.S)       # comments may contain commas and parentheses
+    protos = re.findall(r"B200GS_API\s+[\w\s\*]+?\b(b200gs_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) == len(lib.EXPORTED_SYMBOLS)
+    for name, args in protos:
+        args = args.strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        assert n == len(lib._SIGNATURES[name][1]), f"{name}: header has {n} parameters, ctypes table {len(lib._SIGNATURES[name][1])}"
